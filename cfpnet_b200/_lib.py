@@ -1,0 +1,128 @@
+"""ctypes binding of libcfp.so (the C ABI declared in include/cfp.h).
+
+There is no fallback: if the library is missing or a call is rejected the
+product path raises.  PyTorch is only the owner of device memory and streams;
+every tensor is handed to the library as a raw device pointer.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import torch
+
+from .geometry import ZoneGeometry
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcfp.so")
+
+CFP_F32, CFP_BF16 = 0, 1
+ABI_VERSION = 1
+_fp = C.POINTER(C.c_float)
+
+
+class CfpGeom(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "zone_num", "pad_h", "pad_w", "p1", "p2", "sy_wo", "sx_wo", "ey_wo", "ex_wo",
+        "tzh", "tzw", "interpolate", "ry0", "ry1", "rx0", "rx1")]
+
+    @classmethod
+    def from_geometry(cls, g: ZoneGeometry) -> "CfpGeom":
+        return cls(**{n: getattr(g, n) for n, _ in cls._fields_})
+
+
+class CfpLoftrW(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "wq_t", "wkv_t", "wm_t", "w1_t", "w2_t", "ln1_g", "ln1_b", "ln2_g", "ln2_b")]
+
+
+class CfpDapmW(C.Structure):
+    _fields_ = [("attn", CfpLoftrW)] + [(n, C.c_void_p) for n in ("conv1_t", "shift1", "conv2_t", "shift2")]
+
+
+class CfpLkpmW(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "dw_t", "dw_shift", "ln_g", "ln_b", "pw1_t", "pw1_b", "pw2_t", "pw2_b")] + [("ksize", C.c_int32)]
+
+
+class CfpTwinsW(C.Structure):
+    _fields_ = [("lsa", CfpLoftrW), ("gsa", CfpLoftrW)] + \
+               [(n, C.c_void_p) for n in ("sr_t", "sr_b", "srln_g", "srln_b")] + [("ws", C.c_int32)]
+
+
+class CfpHistW(C.Structure):
+    _fields_ = [("w_t", C.c_void_p * 9), ("b", C.c_void_p * 9)]
+
+
+# name -> (restype, argtypes); must list every symbol include/cfp.h declares.
+_i, _p, _sz, _i64 = C.c_int, C.c_void_p, C.c_size_t, C.c_int64
+SIGNATURES = {
+    "cfp_version": (_i, []),
+    "cfp_last_error": (C.c_char_p, []),
+    "cfp_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, C.POINTER(CfpGeom)]),
+    "cfp_hist_encoder_fwd": (_i, [_p, _p, _p, _p, _i64, C.POINTER(CfpHistW), _i, _p]),
+    "cfp_zone_masks": (_i, [_p, _p, _p, _p, _i, _i, _i, C.POINTER(CfpGeom), _p]),
+    "cfp_posenc_tokens_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "cfp_tokens_to_nchw": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
+    "cfp_d2i_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, C.POINTER(CfpGeom),
+                         C.POINTER(CfpLoftrW), _i, _p, _sz, _i, _p]),
+    "cfp_dapm_fwd": (_i, [_p, _i, _i, _i, _i, C.POINTER(CfpGeom), C.POINTER(CfpDapmW), _p, _sz, _i, _p]),
+    "cfp_lkpm_fwd": (_i, [_p, _i, _i, _i, _i, C.POINTER(CfpLkpmW), _p, _sz, _i, _p]),
+    "cfp_twins_fwd": (_i, [_p, _i, _i, _i, _i, C.POINTER(CfpTwinsW), _p, _sz, _i, _p]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+class CfpError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load libcfp.so (once).  Raises CfpError when it has not been built."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise CfpError(f"{LIB_PATH} not found: build it with `python -m cfpnet_b200.build` "
+                                   "(there is no CPU or PyTorch fallback for the fusion path)")
+                lib = C.CDLL(LIB_PATH)
+                for name, (res, args) in SIGNATURES.items():
+                    fn = getattr(lib, name)
+                    fn.restype, fn.argtypes = res, args
+                if lib.cfp_version() != ABI_VERSION:
+                    raise CfpError(f"libcfp ABI {lib.cfp_version()} != expected {ABI_VERSION}; rebuild")
+                _lib = lib
+    return _lib
+
+
+def call(name: str, *args) -> None:
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise CfpError(f"{name}: {lib.cfp_last_error().decode()}")
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    if dt == torch.float32:
+        return CFP_F32
+    if dt == torch.bfloat16:
+        return CFP_BF16
+    raise CfpError(f"libcfp serves float32 and bfloat16 activations, not {dt}")
+
+
+def require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise CfpError(f"{what} must live on a CUDA device: the fusion path has no CPU implementation "
+                       f"(got device {t.device})")
+
+
+def ptr(t) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream

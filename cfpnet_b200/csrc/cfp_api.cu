@@ -1,0 +1,178 @@
+// extern "C" surface of libcfp (declared in include/cfp.h): argument validation, workspace
+// partitioning and the per-layer launch sequences.  No device allocation, no synchronisation,
+// no global mutable state (the error message is thread-local).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include "cfp_common.cuh"
+#include "cfp_internal.h"
+
+namespace cfp {
+
+ErrorState& tls_error() {
+    static thread_local ErrorState e = {{0}};
+    return e;
+}
+int fail(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(tls_error().msg, sizeof(tls_error().msg), fmt, ap);
+    va_end(ap);
+    return 1;
+}
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail("%s launch failed: %s", what, cudaGetErrorString(e));
+    return 0;
+}
+
+static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+WsLayout ws_layout(int B, int H, int W, int C, int ws, int dtype, const cfp_geom* g) {
+    WsLayout L{};
+    const size_t es = elem_size(dtype);
+    const int Z = g ? g->zone_num * g->zone_num : 64;
+    const size_t nwin = ws > 0 ? (size_t)((H + ws - 1) / ws) * ((W + ws - 1) / ws) : 0;
+    const size_t zone_state = (size_t)B * Z * ((size_t)C * (C / 4) + C);      // hist2image / DAPM, 4 heads
+    const size_t win_state = (size_t)B * nwin * ((size_t)C * (C / 8) + C);    // LSA / GSA, 8 heads
+    size_t off = 0;
+    L.kv = off;
+    L.kv_bytes = align256((zone_state > win_state ? zone_state : win_state) * sizeof(float));
+    off += L.kv_bytes;
+    L.tok_bytes = align256((size_t)B * H * W * C * es);
+    L.tok_a = off; off += L.tok_bytes;
+    L.tok_b = off; off += L.tok_bytes;
+    L.sr = off;
+    L.sr_bytes = ws > 0 ? align256((size_t)B * (H / ws) * (W / ws) * C * sizeof(float)) : 0;
+    off += L.sr_bytes;
+    L.canvas = off;
+    L.canvas_bytes = (g && g->interpolate) ? align256((size_t)B * Z * g->p1 * g->p2 * C * es) : 0;
+    off += L.canvas_bytes;
+    L.total = off;
+    return L;
+}
+
+static int check_common(const void* p, int B, int H, int W, int C, int dtype) {
+    CFP_REQUIRE(p != nullptr, "null device pointer");
+    CFP_REQUIRE(B > 0 && H > 0 && W > 0, "bad shape B=%d H=%d W=%d", B, H, W);
+    CFP_REQUIRE(C == 32 || C == 64 || C == 128, "unsupported embedding_dim C=%d (decoder.py:90-94 uses 32/64/128)", C);
+    CFP_REQUIRE(dtype == CFP_F32 || dtype == CFP_BF16, "unsupported dtype %d", dtype);
+    return 0;
+}
+static int check_geom(const cfp_geom* g, int H, int W) {
+    CFP_REQUIRE(g != nullptr, "null geometry");
+    CFP_REQUIRE(g->zone_num > 0 && g->p1 > 0 && g->p2 > 0 && g->tzh > 0 && g->tzw > 0, "degenerate zone geometry");
+    CFP_REQUIRE(0 <= g->ry0 && g->ry0 <= g->ry1 && g->ry1 <= H && 0 <= g->rx0 && g->rx0 <= g->rx1 && g->rx1 <= W,
+                "zone rectangle [%d:%d,%d:%d] outside the %dx%d map", g->ry0, g->ry1, g->rx0, g->rx1, H, W);
+    CFP_REQUIRE(g->interpolate || (g->tzh == g->zone_num * g->p1 && g->tzw == g->zone_num * g->p2),
+                "canvas %dx%d != zone_num*patch and interpolate flag not set", g->tzh, g->tzw);
+    return 0;
+}
+
+}  // namespace cfp
+
+using namespace cfp;
+
+extern "C" {
+
+CFP_API int cfp_version(void) { return CFP_ABI_VERSION; }
+CFP_API const char* cfp_last_error(void) { return tls_error().msg; }
+
+CFP_API size_t cfp_workspace_bytes(int B, int H, int W, int C, int ws, int dtype, const cfp_geom* g) {
+    return ws_layout(B, H, W, C, ws, dtype, g).total;
+}
+
+CFP_API int cfp_hist_encoder_fwd(const float* hist, void* out32, void* out64, void* out128, int64_t rows,
+                         const cfp_hist_w* w, int dtype, void* stream) {
+    CFP_REQUIRE(hist && out32 && out64 && out128 && w, "null pointer");
+    CFP_REQUIRE(dtype == CFP_F32 || dtype == CFP_BF16, "unsupported dtype %d", dtype);
+    if (rows == 0) return 0;
+    CFP_REQUIRE(rows > 0 && rows < ((int64_t)1 << 31) * 32, "bad row count");
+    return hist_encoder(hist, out32, out64, out128, rows, *w, dtype, (cudaStream_t)stream);
+}
+
+CFP_API int cfp_zone_masks(const uint8_t* mask, uint8_t* zone_mask, uint8_t* hist_mask, uint8_t* pad_mask, int B, int H,
+                   int W, const cfp_geom* g, void* stream) {
+    CFP_REQUIRE(mask && zone_mask && hist_mask && pad_mask, "null pointer");
+    if (int e = check_geom(g, H, W)) return e;
+    return zone_masks(mask, zone_mask, hist_mask, pad_mask, B, H, W, *g, (cudaStream_t)stream);
+}
+
+CFP_API int cfp_posenc_tokens_fwd(const void* x_nchw, const float* pos, void* tokens, int B, int C, int H, int W, int pos_w,
+                          int oy, int ox, int dtype, void* stream) {
+    CFP_REQUIRE(x_nchw && pos && tokens, "null pointer");
+    CFP_REQUIRE(B > 0 && B <= 65535 && C > 0 && H > 0 && W > 0, "bad shape");
+    CFP_REQUIRE(oy >= 0 && ox >= 0 && ox + W <= pos_w, "positional-encoding crop out of range");
+    CFP_REQUIRE(dtype == CFP_F32 || dtype == CFP_BF16, "unsupported dtype %d", dtype);
+    return posenc_tokens(x_nchw, pos, tokens, B, C, H, W, pos_w, oy, ox, dtype, (cudaStream_t)stream);
+}
+
+CFP_API int cfp_tokens_to_nchw(const void* tokens, void* out_nchw, int B, int C, int H, int W, int dtype, void* stream) {
+    CFP_REQUIRE(tokens && out_nchw, "null pointer");
+    CFP_REQUIRE(B > 0 && B <= 65535 && C > 0 && H > 0 && W > 0, "bad shape");
+    CFP_REQUIRE(dtype == CFP_F32 || dtype == CFP_BF16, "unsupported dtype %d", dtype);
+    return tokens_to_nchw(tokens, out_nchw, B, C, H, W, dtype, (cudaStream_t)stream);
+}
+
+CFP_API int cfp_d2i_fwd(void* feat0, const void* emb, const void* zone_tok, const float* pos2, const uint8_t* mask, int B,
+                int H, int W, int C, int S, const cfp_geom* g, const cfp_loftr_w* w, int assign, void* workspace,
+                size_t workspace_bytes, int dtype, void* stream) {
+    if (int e = check_common(feat0, B, H, W, C, dtype)) return e;
+    if (int e = check_geom(g, H, W)) return e;
+    CFP_REQUIRE(emb && zone_tok && pos2 && mask && w && workspace, "null pointer");
+    CFP_REQUIRE(S > 0, "zone_sample_num must be positive");
+    // rows of the zone canvas must map one-to-one onto the zone rectangle (fusion.py:157)
+    const int top = g->sy_wo < 0 ? -g->sy_wo : 0, left = g->sx_wo < 0 ? -g->sx_wo : 0;
+    const int bot = g->ey_wo > H ? g->ey_wo - H : 0, right = g->ex_wo > W ? g->ex_wo - W : 0;
+    CFP_REQUIRE(g->tzh - top - bot == g->ry1 - g->ry0 && g->tzw - left - right == g->rx1 - g->rx0,
+                "zone canvas does not match the zone rectangle (the reference's index_put fails here too)");
+    WsLayout L = ws_layout(B, H, W, C, 0, dtype, g);
+    CFP_REQUIRE(workspace_bytes >= L.total, "workspace too small: %zu < %zu", workspace_bytes, L.total);
+    return d2i(feat0, emb, zone_tok, pos2, mask, B, H, W, C, S, *g, *w, assign, (char*)workspace, L, dtype,
+               (cudaStream_t)stream);
+}
+
+CFP_API int cfp_dapm_fwd(void* feat0, int B, int H, int W, int C, const cfp_geom* g, const cfp_dapm_w* w, void* workspace,
+                 size_t workspace_bytes, int dtype, void* stream) {
+    if (int e = check_common(feat0, B, H, W, C, dtype)) return e;
+    if (int e = check_geom(g, H, W)) return e;
+    CFP_REQUIRE(w && workspace, "null pointer");
+    CFP_REQUIRE(B <= 65535, "B too large for grid.z");
+    WsLayout L = ws_layout(B, H, W, C, 0, dtype, g);
+    CFP_REQUIRE(workspace_bytes >= L.kv_bytes + 2 * L.tok_bytes, "workspace too small: %zu < %zu", workspace_bytes,
+                L.kv_bytes + 2 * L.tok_bytes);
+    char* ws = (char*)workspace;
+    cudaStream_t st = (cudaStream_t)stream;
+    void* msg_map = ws + L.tok_a;     // written only outside the zone rectangle; read as zero inside
+    void* mid = ws + L.tok_b;
+    if (int e = dapm_attention(feat0, msg_map, B, H, W, C, *g, w->attn, ws, L, dtype, st)) return e;
+    if (int e = conv3x3(feat0, msg_map, w->conv1_t, w->shift1, nullptr, mid, B, H, W, C, g->ry0, g->ry1, g->rx0,
+                        g->rx1, dtype, st)) return e;
+    return conv3x3(mid, nullptr, w->conv2_t, w->shift2, feat0, feat0, B, H, W, C, 0, 0, 0, 0, dtype, st);
+}
+
+CFP_API int cfp_lkpm_fwd(void* feat0, int B, int H, int W, int C, const cfp_lkpm_w* w, void* workspace, size_t workspace_bytes,
+                 int dtype, void* stream) {
+    if (int e = check_common(feat0, B, H, W, C, dtype)) return e;
+    CFP_REQUIRE(w && workspace, "null pointer");
+    WsLayout L = ws_layout(B, H, W, C, 0, dtype, nullptr);
+    CFP_REQUIRE(workspace_bytes >= L.kv_bytes + L.tok_bytes, "workspace too small");
+    char* ws = (char*)workspace;
+    cudaStream_t st = (cudaStream_t)stream;
+    void* y = ws + L.tok_a;
+    if (int e = dwconv_bn_relu(feat0, y, B, H, W, C, w->ksize, w->dw_t, w->dw_shift, dtype, st)) return e;
+    return lkpm_mlp(feat0, y, (int64_t)B * H * W, C, *w, dtype, st);
+}
+
+CFP_API int cfp_twins_fwd(void* feat0, int B, int H, int W, int C, const cfp_twins_w* w, void* workspace,
+                  size_t workspace_bytes, int dtype, void* stream) {
+    if (int e = check_common(feat0, B, H, W, C, dtype)) return e;
+    CFP_REQUIRE(w && workspace, "null pointer");
+    CFP_REQUIRE(w->ws > 1, "window size must be > 1 (transformer.py:79)");
+    CFP_REQUIRE(C % 8 == 0, "dim %d should be divided by num_heads 8 (transformer.py:81)", C);
+    WsLayout L = ws_layout(B, H, W, C, w->ws, dtype, nullptr);
+    CFP_REQUIRE(workspace_bytes >= L.total, "workspace too small: %zu < %zu", workspace_bytes, L.total);
+    return twins(feat0, B, H, W, C, *w, (char*)workspace, L, dtype, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,58 @@
+// Internal (C++) launch interface between cfp_api.cu and the kernel files.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+#include "../../include/cfp.h"
+
+namespace cfp {
+
+// Workspace partition of one fusion call (all offsets in bytes, 256-aligned).
+struct WsLayout {
+    size_t kv, kv_bytes;        // fp32 attention state: [groups][C*dh] KV then [groups][C] Ksum
+    size_t tok_a, tok_b;        // two token-major scratch maps [B][N][C] in the activation dtype
+    size_t tok_bytes;
+    size_t sr, sr_bytes;        // GSA sub-sampled tokens, fp32 [B][Ns][C]
+    size_t canvas, canvas_bytes;  // hist2image resize branch: [B][zn*p1*zn*p2][C] activation dtype
+    size_t total;
+};
+WsLayout ws_layout(int B, int H, int W, int C, int ws, int dtype, const cfp_geom* g);
+
+inline size_t elem_size(int dtype) { return dtype == CFP_F32 ? 4 : 2; }
+
+// k_layout.cu
+int posenc_tokens(const void* x, const float* pos, void* tokens, int B, int C, int H, int W, int pos_w,
+                  int oy, int ox, int dtype, cudaStream_t st);
+int tokens_to_nchw(const void* tokens, void* out, int B, int C, int H, int W, int dtype, cudaStream_t st);
+int zone_masks(const uint8_t* mask, uint8_t* zm, uint8_t* hm, uint8_t* pm, int B, int H, int W,
+               const cfp_geom& g, cudaStream_t st);
+
+// k_hist.cu
+int hist_encoder(const float* hist, void* o32, void* o64, void* o128, int64_t rows, const cfp_hist_w& w,
+                 int dtype, cudaStream_t st);
+
+// k_loftr.cu
+int d2i(void* feat0, const void* emb, const void* zone_tok, const float* pos2, const uint8_t* mask, int B,
+        int H, int W, int C, int S, const cfp_geom& g, const cfp_loftr_w& w, int assign, char* ws,
+        const WsLayout& L, int dtype, cudaStream_t st);
+int dapm_attention(const void* feat0, void* msg_map, int B, int H, int W, int C, const cfp_geom& g,
+                   const cfp_loftr_w& w, char* ws, const WsLayout& L, int dtype, cudaStream_t st);
+int twins(void* feat0, int B, int H, int W, int C, const cfp_twins_w& w, char* ws, const WsLayout& L,
+          int dtype, cudaStream_t st);
+
+// k_conv.cu
+// out = conv3x3(cat[in0, in1]) + shift (+ residual); in1 may be null; in1 is read as zero inside
+// the rectangle (zy0..zy1, zx0..zx1).
+int conv3x3(const void* in0, const void* in1, const float* w_t, const float* shift, const void* residual,
+            void* out, int B, int H, int W, int C, int zy0, int zy1, int zx0, int zx1, int dtype,
+            cudaStream_t st);
+int sr_conv_ln(const void* feat0, float* sr_tok, int B, int H, int W, int C, int ws, const float* sr_t,
+               const float* sr_b, const float* g, const float* b, int dtype, cudaStream_t st);
+
+// k_lkpm.cu
+int dwconv_bn_relu(const void* in, void* out, int B, int H, int W, int C, int ksize, const float* dw_t,
+                   const float* dw_shift, int dtype, cudaStream_t st);
+int lkpm_mlp(void* feat0, const void* y, int64_t rows, int C, const cfp_lkpm_w& w, int dtype,
+             cudaStream_t st);
+
+}  // namespace cfp

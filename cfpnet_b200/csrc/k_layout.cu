@@ -1,0 +1,108 @@
+// Layout kernels of the fusion module boundary (memory-bound):
+//   a4  positional-encoding add + NCHW -> token-major   (fusion.py:92-97)
+//       token-major -> NCHW                              (fusion.py:186)
+//   a3  bit-exact export of zone_mask / hist_mask / pad_mask (fusion.py:103-120)
+#include "cfp_common.cuh"
+#include "cfp_internal.h"
+
+namespace cfp {
+
+// 32x32 (pixel x channel) transpose tile through shared memory so that both the
+// NCHW side (pixels contiguous) and the token side (channels contiguous) are
+// accessed with full 128-byte lines.
+template <typename T, bool kToTokens>
+__global__ void __launch_bounds__(256) layout_kernel(const T* __restrict__ src, const float* __restrict__ pos,
+                                                     T* __restrict__ dst, int C, int H, int W, int pos_w,
+                                                     int oy, int ox) {
+    __shared__ float tile[32][33];
+    const int N = H * W;
+    const int b = blockIdx.z;
+    const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    if (kToTokens) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int c = c0 + ty + 8 * i, n = n0 + tx;
+            if (c < C && n < N) tile[ty + 8 * i][tx] = IO<T>::ld(src + ((size_t)b * C + c) * N + n);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int n = n0 + ty + 8 * i, c = c0 + tx;
+            if (c < C && n < N) {
+                int y = n / W, x = n - y * W;
+                float p = pos[((size_t)(oy + y) * pos_w + (ox + x)) * C + c];
+                IO<T>::st(dst + ((size_t)b * N + n) * C + c, tile[tx][ty + 8 * i] + p);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int n = n0 + ty + 8 * i, c = c0 + tx;
+            if (c < C && n < N) tile[ty + 8 * i][tx] = IO<T>::ld(src + ((size_t)b * N + n) * C + c);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int c = c0 + ty + 8 * i, n = n0 + tx;
+            if (c < C && n < N) IO<T>::st(dst + ((size_t)b * C + c) * N + n, tile[tx][ty + 8 * i]);
+        }
+    }
+}
+
+template <typename T>
+static int launch_layout(bool to_tokens, const void* src, const float* pos, void* dst, int B, int C, int H,
+                         int W, int pos_w, int oy, int ox, cudaStream_t st) {
+    dim3 grid((H * W + 31) / 32, (C + 31) / 32, B);
+    if (to_tokens)
+        layout_kernel<T, true><<<grid, 256, 0, st>>>((const T*)src, pos, (T*)dst, C, H, W, pos_w, oy, ox);
+    else
+        layout_kernel<T, false><<<grid, 256, 0, st>>>((const T*)src, pos, (T*)dst, C, H, W, pos_w, oy, ox);
+    return check_launch("layout_kernel");
+}
+
+int posenc_tokens(const void* x, const float* pos, void* tokens, int B, int C, int H, int W, int pos_w,
+                  int oy, int ox, int dtype, cudaStream_t st) {
+    return dtype == CFP_F32 ? launch_layout<float>(true, x, pos, tokens, B, C, H, W, pos_w, oy, ox, st)
+                            : launch_layout<bf16>(true, x, pos, tokens, B, C, H, W, pos_w, oy, ox, st);
+}
+int tokens_to_nchw(const void* tokens, void* out, int B, int C, int H, int W, int dtype, cudaStream_t st) {
+    return dtype == CFP_F32 ? launch_layout<float>(false, tokens, nullptr, out, B, C, H, W, 0, 0, 0, st)
+                            : launch_layout<bf16>(false, tokens, nullptr, out, B, C, H, W, 0, 0, 0, st);
+}
+
+// ---------------------------------------------------------------- masks
+__global__ void zone_masks_kernel(const uint8_t* __restrict__ mask, uint8_t* __restrict__ zone_mask,
+                                  uint8_t* __restrict__ hist_mask, uint8_t* __restrict__ pad_mask, int B,
+                                  int H, int W, cfp_geom g) {
+    const int Z = g.zone_num * g.zone_num, P = g.p1 * g.p2;
+    const long n_zone = (long)B * H * W, n_hist = (long)B * Z * P, n_pad = (long)B * g.tzh * g.tzw;
+    const long total = n_zone + n_hist + n_pad;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        if (i < n_zone) {
+            int n = (int)(i % (H * W)), y = n / W, x = n - y * W;
+            zone_mask[i] = (y >= g.ry0 && y < g.ry1 && x >= g.rx0 && x < g.rx1) ? 1 : 0;
+        } else if (i < n_zone + n_hist) {
+            long j = i - n_zone;
+            hist_mask[j] = mask[j / P] ? 1 : 0;
+        } else {
+            long j = i - n_zone - n_hist;
+            int cx = (int)(j % g.tzw), cy = (int)((j / g.tzw) % g.tzh);
+            uint8_t v = 1;
+            if (g.pad_h > 0 || g.pad_w > 0) {     // fusion.py:112-118
+                int top = max(-g.sy_wo, 0), left = max(-g.sx_wo, 0);
+                int bot = max(g.ey_wo - H, 0), right = max(g.ex_wo - W, 0);
+                if (cy < top || cy >= g.tzh - bot || cx < left || cx >= g.tzw - right) v = 0;
+            }
+            pad_mask[j] = v;
+        }
+    }
+}
+
+int zone_masks(const uint8_t* mask, uint8_t* zm, uint8_t* hm, uint8_t* pm, int B, int H, int W,
+               const cfp_geom& g, cudaStream_t st) {
+    zone_masks_kernel<<<148 * 4, 256, 0, st>>>(mask, zm, hm, pm, B, H, W, g);
+    return check_launch("zone_masks_kernel");
+}
+
+}  // namespace cfp

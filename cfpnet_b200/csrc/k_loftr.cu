@@ -1,0 +1,451 @@
+// Linear-attention layers of the fusion path:
+//   a5  hist2image   (fusion.py:132-157, transformer.py:41-71, attention.py:20-52)
+//   a6  DAPM attention half (transformer.py:215-234)
+//   a9  Twins LSA / GSA (transformer.py:89-116, 138-150)
+//
+// All four are the same two-phase computation and share two kernels:
+//   phase 1  kv_state_kernel : source rows -> k|v projection -> K = elu(k)+1 ->
+//            per-group state  KV[h] = sum_s K_s^T V_s  (dh x dh per head) and Ksum[h] = sum_s K_s
+//   phase 2  loftr_query_kernel : query rows -> q projection -> Q = elu(q)+1 ->
+//            msg = (Q KV) / (Q.Ksum + eps) -> merge -> LN -> MLP([x,msg]) -> LN -> x + msg
+// (the reference divides V by S before the sum and multiplies the message by S afterwards,
+// attention.py:42,49 — an fp16-overflow guard that cancels exactly in real arithmetic; the
+// state here is accumulated in fp32 and skips it).
+//
+// What differs per layer is only WHICH rows form a group and where they live; that is a
+// "row provider": it maps a dense row index to a gather address (zone patch cell, window
+// cell, outside-zone cell, ...) and scatters the result back.  No mask tensor and no
+// gathered copy of the tokens is ever materialised.
+//
+// A CTA keeps its BM-row tile in shared memory through the whole chain (RowsGemm), so a
+// layer reads its tokens once and writes them once.
+#include "cfp_common.cuh"
+#include "cfp_internal.h"
+
+namespace cfp {
+
+template <int C> struct Tile { static constexpr int BM = C >= 128 ? 32 : 64; };
+
+// ------------------------------------------------------------------ providers
+// Common interface:
+//   int64_t rows;                     total dense rows
+//   int group(int64_t r)              attention group of row r
+//   float4 load4(int64_t r, int c)    channels c..c+3 of row r (zeros for padding)
+//   void store4(int64_t r, int c, float4 v)      (query providers only)
+
+template <typename T>
+struct ZoneTokSrc {            // hist2image keys/values: zone tokens + positional_encodings2
+    const T* tok; const float* pos2; int S, C; int64_t rows;
+    __device__ int group(int64_t r) const { return (int)(r / S); }
+    __device__ float4 load4(int64_t r, int c) const {
+        float4 v = IO<T>::ld4(tok + r * C + c);
+        float4 p = *reinterpret_cast<const float4*>(pos2 + (r % S) * C + c);
+        return make_float4(v.x + p.x, v.y + p.y, v.z + p.z, v.w + p.w);
+    }
+};
+
+template <typename T>
+struct WindowRows {            // LSA: ws x ws windows over the zero-padded map (queries and keys)
+    T* feat; int H, W, C, ws, nwx, nwin; int64_t rows;
+    __device__ int group(int64_t r) const { return (int)(r / (ws * ws)); }
+    __device__ bool locate(int64_t r, int64_t& off) const {
+        int g = (int)(r / (ws * ws)), l = (int)(r % (ws * ws));
+        int b = g / nwin, wi = g % nwin;
+        int y = (wi / nwx) * ws + l / ws, x = (wi % nwx) * ws + l % ws;
+        off = ((int64_t)b * H * W + (int64_t)y * W + x) * C;
+        return y < H && x < W;
+    }
+    __device__ float4 load4(int64_t r, int c) const {
+        int64_t off;
+        return locate(r, off) ? IO<T>::ld4(feat + off + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __device__ void store4(int64_t r, int c, float4 v) const {
+        int64_t off;
+        if (locate(r, off)) IO<T>::st4(feat + off + c, v);
+    }
+};
+
+template <typename T>
+struct FrameRows {             // GSA queries: every token of a frame, group = frame
+    T* feat; int N, C; int64_t rows;
+    __device__ int group(int64_t r) const { return (int)(r / N); }
+    __device__ float4 load4(int64_t r, int c) const { return IO<T>::ld4(feat + r * C + c); }
+    __device__ void store4(int64_t r, int c, float4 v) const { IO<T>::st4(feat + r * C + c, v); }
+};
+
+struct SrTokSrc {              // GSA keys/values: fp32 sub-sampled tokens [B][Ns][C]
+    const float* tok; int Ns, C; int64_t rows;
+    __device__ int group(int64_t r) const { return (int)(r / Ns); }
+    __device__ float4 load4(int64_t r, int c) const { return *reinterpret_cast<const float4*>(tok + r * C + c); }
+};
+
+template <typename T>
+struct InsideSrc {             // DAPM keys/values: tokens inside the zone rectangle, raster order
+    const T* feat; int H, W, C, ry0, rx0, rw, Ni; int64_t rows;
+    __device__ int group(int64_t r) const { return (int)(r / Ni); }
+    __device__ float4 load4(int64_t r, int c) const {
+        int b = (int)(r / Ni), i = (int)(r % Ni);
+        int y = ry0 + i / rw, x = rx0 + i % rw;
+        return IO<T>::ld4(feat + ((int64_t)b * H * W + (int64_t)y * W + x) * C + c);
+    }
+};
+
+template <typename T>
+struct OutsideRows {           // DAPM queries: tokens outside the rectangle; message map out
+    const T* feat; T* msg; int H, W, C, ry0, ry1, rx0, rx1, No; int64_t rows;
+    __device__ int group(int64_t r) const { return (int)(r / No); }
+    __device__ int64_t locate(int64_t r) const {
+        int b = (int)(r / No), o = (int)(r % No);
+        const int rw = rx1 - rx0, top = ry0 * W, mid = (ry1 - ry0) * (W - rw);
+        int n;
+        if (o < top) n = o;
+        else if (o < top + mid) {
+            int q = o - top, row = q / (W - rw), j = q % (W - rw);
+            n = (ry0 + row) * W + (j < rx0 ? j : j + rw);
+        } else n = ry1 * W + (o - top - mid);
+        return ((int64_t)b * H * W + n) * C;
+    }
+    __device__ float4 load4(int64_t r, int c) const { return IO<T>::ld4(feat + locate(r) + c); }
+    __device__ void store4(int64_t r, int c, float4 v) const { IO<T>::st4(msg + locate(r) + c, v); }
+};
+
+template <typename T>
+struct ZonePatchRows {         // hist2image queries: cells of the zone canvas, grouped per zone
+    T* feat0; const T* emb; T* canvas; const uint8_t* mask;
+    int H, W, C, zn, p1, p2, sy_wo, sx_wo, tzh, tzw, interpolate, assign; int64_t rows;
+    __device__ int group(int64_t r) const { return (int)(r / (p1 * p2)); }
+    __device__ void cell(int64_t r, int& b, int& cy, int& cx) const {
+        int g = (int)(r / (p1 * p2)), l = (int)(r % (p1 * p2));
+        b = g / (zn * zn);
+        int z = g % (zn * zn);
+        cy = (z / zn) * p1 + l / p2;
+        cx = (z % zn) * p2 + l % p2;
+    }
+    // value of the zero-padded map at canvas cell (ty,tx) of the un-resized canvas
+    __device__ float4 canvas_at(int b, int ty, int tx, int c) const {
+        int y = sy_wo + ty, x = sx_wo + tx;
+        if (y < 0 || y >= H || x < 0 || x >= W) return make_float4(0.f, 0.f, 0.f, 0.f);
+        return IO<T>::ld4(emb + ((int64_t)b * H * W + (int64_t)y * W + x) * C + c);
+    }
+    __device__ float4 load4(int64_t r, int c) const {
+        int b, cy, cx;
+        cell(r, b, cy, cx);
+        if (!interpolate) return canvas_at(b, cy, cx, c);
+        // F.interpolate(bilinear, align_corners=True) from [tzh,tzw] to [zn*p1, zn*p2]  (fusion.py:141)
+        const int oh = zn * p1, ow = zn * p2;
+        float fy = oh > 1 ? cy * ((float)(tzh - 1) / (float)(oh - 1)) : 0.f;
+        float fx = ow > 1 ? cx * ((float)(tzw - 1) / (float)(ow - 1)) : 0.f;
+        int y0 = (int)fy, x0 = (int)fx;
+        int y1 = min(y0 + 1, tzh - 1), x1 = min(x0 + 1, tzw - 1);
+        float ly = fy - y0, lx = fx - x0;
+        float4 a = canvas_at(b, y0, x0, c), bq = canvas_at(b, y0, x1, c);
+        float4 cq = canvas_at(b, y1, x0, c), d = canvas_at(b, y1, x1, c);
+        float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+        return make_float4(w00 * a.x + w01 * bq.x + w10 * cq.x + w11 * d.x,
+                           w00 * a.y + w01 * bq.y + w10 * cq.y + w11 * d.y,
+                           w00 * a.z + w01 * bq.z + w10 * cq.z + w11 * d.z,
+                           w00 * a.w + w01 * bq.w + w10 * cq.w + w11 * d.w);
+    }
+    __device__ void store4(int64_t r, int c, float4 v) const {
+        int b, cy, cx;
+        cell(r, b, cy, cx);
+        const bool valid = mask[group(r)] != 0;           // zone_feature[~hist_mask] = 0  (fusion.py:144)
+        if (!valid) v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (interpolate) {                                // resized back by canvas_resize_add_kernel
+            IO<T>::st4(canvas + (((int64_t)b * zn * p1 + cy) * (zn * p2) + cx) * C + c, v);
+            return;
+        }
+        int y = sy_wo + cy, x = sx_wo + cx;
+        if (y < 0 || y >= H || x < 0 || x >= W) return;    // pad_mask (fusion.py:112-118)
+        T* dst = feat0 + ((int64_t)b * H * W + (int64_t)y * W + x) * C + c;
+        if (assign) { IO<T>::st4(dst, v); return; }       // --no_skip_inside (fusion.py:154-155)
+        if (!valid) return;
+        float4 o = IO<T>::ld4(dst);                       // feat0[zone_mask] += ...  (fusion.py:157)
+        IO<T>::st4(dst, make_float4(o.x + v.x, o.y + v.y, o.z + v.z, o.w + v.w));
+    }
+};
+
+// ------------------------------------------------------------------ phase 1
+template <int C, int NH, class Src>
+__global__ void __launch_bounds__(kThreads) kv_state_kernel(Src src, const float* __restrict__ wkv_t,
+                                                            float* __restrict__ kv, float* __restrict__ ksum) {
+    constexpr int BM = Tile<C>::BM, DH = C / NH, LDX = C + 4, LDK = 2 * C + 4;
+    extern __shared__ __align__(16) float smem[];
+    float* xs = smem;                       // [BM][LDX]
+    float* kvs = xs + BM * LDX;             // [BM][LDK]  K | V
+    float* wbuf = kvs + BM * LDK;
+    const int64_t row0 = (int64_t)blockIdx.x * BM;
+
+    for (int i = threadIdx.x; i < BM * (C / 4); i += kThreads) {
+        int r = i / (C / 4), c4 = i % (C / 4);
+        float4 v = row0 + r < src.rows ? src.load4(row0 + r, c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(xs + r * LDX + c4 * 4) = v;
+    }
+    __syncthreads();
+    gemm_to_smem<BM, 2 * C>(SmemRows{xs, LDX}, wkv_t, C, wbuf, kvs, LDK,
+                            [](int c, float v) { return c < C ? elu1(v) : v; });
+    __syncthreads();
+
+    const int nrows = (int)min((int64_t)BM, src.rows - row0);
+    int r = 0;
+    while (r < nrows) {                     // one segment per group present in the tile
+        const int g = src.group(row0 + r);
+        int e = r + 1;
+        while (e < nrows && src.group(row0 + e) == g) ++e;
+        for (int idx = threadIdx.x; idx < C * DH; idx += kThreads) {
+            const int kc = idx / DH, vc = (kc / DH) * DH + idx % DH;
+            float s = 0.f;
+            for (int t = r; t < e; ++t) s = fmaf(kvs[t * LDK + kc], kvs[t * LDK + C + vc], s);
+            atomicAdd(kv + (size_t)g * (C * DH) + idx, s);
+        }
+        for (int c = threadIdx.x; c < C; c += kThreads) {
+            float s = 0.f;
+            for (int t = r; t < e; ++t) s += kvs[t * LDK + c];
+            atomicAdd(ksum + (size_t)g * C + c, s);
+        }
+        r = e;
+    }
+}
+
+// ------------------------------------------------------------------ phase 2
+template <int C, int NH, bool kAttnOnly, class Q>
+__global__ void __launch_bounds__(kThreads) loftr_query_kernel(Q q, cfp_loftr_w w, const float* __restrict__ kv,
+                                                               const float* __restrict__ ksum) {
+    constexpr int BM = Tile<C>::BM, DH = C / NH, LD = 2 * C + 4;
+    extern __shared__ __align__(16) float smem[];
+    float* cat = smem;                      // [BM][LD]   x | msg
+    float* hb = cat + BM * LD;              // [BM][LD]   q | raw msg, later MLP hidden
+    float* wbuf = hb + BM * LD;
+    __shared__ int gid[BM];
+    const int64_t row0 = (int64_t)blockIdx.x * BM;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    for (int i = threadIdx.x; i < BM * (C / 4); i += kThreads) {
+        int r = i / (C / 4), c4 = i % (C / 4);
+        float4 v = row0 + r < q.rows ? q.load4(row0 + r, c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(cat + r * LD + c4 * 4) = v;
+    }
+    if (threadIdx.x < BM) gid[threadIdx.x] = row0 + threadIdx.x < q.rows ? q.group(row0 + threadIdx.x) : -1;
+    __syncthreads();
+
+    // Q = elu(x Wq^T) + 1
+    gemm_to_smem<BM, C>(SmemRows{cat, LD}, w.wq_t, C, wbuf, hb, LD, [](int, float v) { return elu1(v); });
+    __syncthreads();
+
+    // msg[h] = (Q_h KV_h) / (Q_h . Ksum_h + eps)           attention.py:44-49
+    for (int r = warp; r < BM; r += kThreads / 32) {
+        const int g = gid[r];
+        const float* qr = hb + r * LD;
+#pragma unroll
+        for (int i = 0; i < C / 32; ++i) {
+            const int c = lane + 32 * i, h0 = (c / DH) * DH, v = c - h0;
+            float m = 0.f;
+            if (g >= 0) {
+                const float* kvg = kv + (size_t)g * (C * DH) + (size_t)h0 * DH + v;
+                const float* ksg = ksum + (size_t)g * C + h0;
+                float num = 0.f, den = 0.f;
+#pragma unroll 8
+                for (int d = 0; d < DH; ++d) {
+                    const float qv = qr[h0 + d];
+                    num = fmaf(qv, kvg[d * DH], num);
+                    den = fmaf(qv, ksg[d], den);
+                }
+                m = num / (den + kAttnEps);
+            }
+            hb[r * LD + C + c] = m;
+        }
+    }
+    __syncthreads();
+
+    if (kAttnOnly) {                        // DAPM: the message map is the output
+        for (int i = threadIdx.x; i < BM * (C / 4); i += kThreads) {
+            int r = i / (C / 4), c4 = i % (C / 4);
+            if (row0 + r < q.rows)
+                q.store4(row0 + r, c4 * 4, *reinterpret_cast<const float4*>(hb + r * LD + C + c4 * 4));
+        }
+        return;
+    }
+
+    // message = LN1(merge(msg))                            transformer.py:64-65
+    gemm_to_smem<BM, C>(SmemRows{hb + C, LD}, w.wm_t, C, wbuf, cat + C, LD, [](int, float v) { return v; });
+    __syncthreads();
+    layernorm_rows<BM, C>(cat + C, LD, w.ln1_g, w.ln1_b, kLnEps);
+    __syncthreads();
+    // message = LN2(W2 relu(W1 [x, message]))              transformer.py:68-69
+    gemm_to_smem<BM, 2 * C>(SmemRows{cat, LD}, w.w1_t, 2 * C, wbuf, hb, LD,
+                            [](int, float v) { return fmaxf(v, 0.f); });
+    __syncthreads();
+    gemm_to_smem<BM, C>(SmemRows{hb, LD}, w.w2_t, 2 * C, wbuf, cat + C, LD, [](int, float v) { return v; });
+    __syncthreads();
+    layernorm_rows<BM, C>(cat + C, LD, w.ln2_g, w.ln2_b, kLnEps);
+    __syncthreads();
+    // x + message                                          transformer.py:71
+    for (int i = threadIdx.x; i < BM * (C / 4); i += kThreads) {
+        int r = i / (C / 4), c4 = i % (C / 4);
+        if (row0 + r < q.rows) {
+            float4 x = *reinterpret_cast<const float4*>(cat + r * LD + c4 * 4);
+            float4 m = *reinterpret_cast<const float4*>(cat + r * LD + C + c4 * 4);
+            q.store4(row0 + r, c4 * 4, make_float4(x.x + m.x, x.y + m.y, x.z + m.z, x.w + m.w));
+        }
+    }
+}
+
+// hist2image resize branch, second half (fusion.py:146-149,157): the layer output on the
+// [zn*p1, zn*p2] canvas is resized back to [tzh, tzw] (bilinear, align_corners) and its
+// in-image part is added onto (or assigned to) the zone rectangle of feat0.
+template <typename T>
+__global__ void canvas_resize_add_kernel(const T* __restrict__ canvas, T* __restrict__ feat0, int B, int H, int W,
+                                         int C, cfp_geom g, int assign) {
+    const int oh = g.zone_num * g.p1, ow = g.zone_num * g.p2;
+    const int rh = g.ry1 - g.ry0, rw = g.rx1 - g.rx0, V = C / 4;
+    const int64_t total = (int64_t)B * rh * rw * V;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(i % V) * 4;
+        int64_t p = i / V;
+        int x = g.rx0 + (int)(p % rw), y = g.ry0 + (int)((p / rw) % rh), b = (int)(p / ((int64_t)rw * rh));
+        int ty = y - g.sy_wo, tx = x - g.sx_wo;            // cell of the [tzh,tzw] canvas
+        float fy = g.tzh > 1 ? ty * ((float)(oh - 1) / (float)(g.tzh - 1)) : 0.f;
+        float fx = g.tzw > 1 ? tx * ((float)(ow - 1) / (float)(g.tzw - 1)) : 0.f;
+        int y0 = (int)fy, x0 = (int)fx, y1 = min(y0 + 1, oh - 1), x1 = min(x0 + 1, ow - 1);
+        float ly = fy - y0, lx = fx - x0;
+        const T* base = canvas + (int64_t)b * oh * ow * C + c;
+        float4 a = IO<T>::ld4(base + ((int64_t)y0 * ow + x0) * C), bq = IO<T>::ld4(base + ((int64_t)y0 * ow + x1) * C);
+        float4 cq = IO<T>::ld4(base + ((int64_t)y1 * ow + x0) * C), d = IO<T>::ld4(base + ((int64_t)y1 * ow + x1) * C);
+        float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+        float4 v = make_float4(w00 * a.x + w01 * bq.x + w10 * cq.x + w11 * d.x, w00 * a.y + w01 * bq.y + w10 * cq.y + w11 * d.y,
+                               w00 * a.z + w01 * bq.z + w10 * cq.z + w11 * d.z, w00 * a.w + w01 * bq.w + w10 * cq.w + w11 * d.w);
+        T* dst = feat0 + ((int64_t)b * H * W + (int64_t)y * W + x) * C + c;
+        if (!assign) {
+            float4 o = IO<T>::ld4(dst);
+            v = make_float4(o.x + v.x, o.y + v.y, o.z + v.z, o.w + v.w);
+        }
+        IO<T>::st4(dst, v);
+    }
+}
+
+// ------------------------------------------------------------------ launchers
+template <int C> constexpr size_t kv_smem() {
+    constexpr int BM = Tile<C>::BM, NT = 2 * C > 256 ? 256 : 2 * C;
+    return (size_t)(BM * (C + 4) + BM * (2 * C + 4) + 2 * 32 * NT) * sizeof(float);
+}
+template <int C> constexpr size_t query_smem() {
+    constexpr int BM = Tile<C>::BM, NT = 2 * C > 256 ? 256 : 2 * C;
+    return (size_t)(2 * BM * (2 * C + 4) + 2 * 32 * NT) * sizeof(float);
+}
+
+template <int C, int NH, class Src>
+static int run_kv_state(const Src& src, int groups, const float* wkv_t, float* kv, float* ksum, cudaStream_t st) {
+    constexpr int DH = C / NH;
+    cudaError_t e = cudaMemsetAsync(kv, 0, (size_t)groups * (C * DH + C) * sizeof(float), st);
+    if (e != cudaSuccess) return fail("cudaMemsetAsync(kv state): %s", cudaGetErrorString(e));
+    auto k = kv_state_kernel<C, NH, Src>;
+    if (int err = set_smem(k, kv_smem<C>())) return err;
+    const unsigned grid = (unsigned)((src.rows + Tile<C>::BM - 1) / Tile<C>::BM);
+    k<<<grid, kThreads, kv_smem<C>(), st>>>(src, wkv_t, kv, ksum);
+    return check_launch("kv_state_kernel");
+}
+template <int C, int NH, bool kAttnOnly, class Q>
+static int run_query(const Q& q, const cfp_loftr_w& w, const float* kv, const float* ksum, cudaStream_t st) {
+    auto k = loftr_query_kernel<C, NH, kAttnOnly, Q>;
+    if (int err = set_smem(k, query_smem<C>())) return err;
+    const unsigned grid = (unsigned)((q.rows + Tile<C>::BM - 1) / Tile<C>::BM);
+    k<<<grid, kThreads, query_smem<C>(), st>>>(q, w, kv, ksum);
+    return check_launch("loftr_query_kernel");
+}
+
+// KV state for `groups` groups with head dim DH lives at ws+L.kv: [groups][C*DH] then [groups][C].
+template <int C, int NH>
+static inline void kv_ptrs(char* ws, const WsLayout& L, int groups, float*& kv, float*& ksum) {
+    kv = reinterpret_cast<float*>(ws + L.kv);
+    ksum = kv + (size_t)groups * (C * (C / NH));
+}
+
+template <int C, typename T>
+static int d2i_impl(void* feat0, const void* emb, const void* zone_tok, const float* pos2, const uint8_t* mask,
+                    int B, int H, int W, int S, const cfp_geom& g, const cfp_loftr_w& w, int assign, char* ws,
+                    const WsLayout& L, cudaStream_t st) {
+    const int Z = g.zone_num * g.zone_num, groups = B * Z;
+    float *kv, *ksum;
+    kv_ptrs<C, 4>(ws, L, groups, kv, ksum);
+    ZoneTokSrc<T> src{(const T*)zone_tok, pos2, S, C, (int64_t)groups * S};
+    if (int e = run_kv_state<C, 4>(src, groups, w.wkv_t, kv, ksum, st)) return e;
+    ZonePatchRows<T> q{(T*)feat0, (const T*)emb, (T*)(ws + L.canvas), mask, H, W, C, g.zone_num, g.p1, g.p2,
+                       g.sy_wo, g.sx_wo, g.tzh, g.tzw, g.interpolate, assign, (int64_t)groups * g.p1 * g.p2};
+    if (int e = run_query<C, 4, false>(q, w, kv, ksum, st)) return e;
+    if (g.interpolate) {
+        const int64_t total = (int64_t)B * (g.ry1 - g.ry0) * (g.rx1 - g.rx0) * (C / 4);
+        const int64_t want = (total + 255) / 256;
+        const unsigned grid = (unsigned)(want < 148 * 8 ? want : 148 * 8);
+        canvas_resize_add_kernel<T><<<grid, 256, 0, st>>>((const T*)(ws + L.canvas), (T*)feat0, B, H, W, C, g, assign);
+        return check_launch("canvas_resize_add_kernel");
+    }
+    return 0;
+}
+
+template <int C, typename T>
+static int dapm_impl(const void* feat0, void* msg_map, int B, int H, int W, const cfp_geom& g,
+                     const cfp_loftr_w& w, char* ws, const WsLayout& L, cudaStream_t st) {
+    const int rw = g.rx1 - g.rx0, Ni = (g.ry1 - g.ry0) * rw, No = H * W - Ni;
+    float *kv, *ksum;
+    kv_ptrs<C, 4>(ws, L, B, kv, ksum);
+    if (Ni > 0) {
+        InsideSrc<T> src{(const T*)feat0, H, W, C, g.ry0, g.rx0, rw, Ni, (int64_t)B * Ni};
+        if (int e = run_kv_state<C, 4>(src, B, w.wkv_t, kv, ksum, st)) return e;
+    } else {
+        cudaMemsetAsync(kv, 0, (size_t)B * (C * (C / 4) + C) * sizeof(float), st);
+    }
+    if (No == 0) return 0;
+    OutsideRows<T> q{(const T*)feat0, (T*)msg_map, H, W, C, g.ry0, g.ry1, g.rx0, g.rx1, No, (int64_t)B * No};
+    return run_query<C, 4, true>(q, w, kv, ksum, st);
+}
+
+template <int C, typename T>
+static int twins_impl(void* feat0, int B, int H, int W, const cfp_twins_w& w, char* ws, const WsLayout& L,
+                      cudaStream_t st) {
+    const int wsz = w.ws;
+    // LSA (transformer.py:94-116): pad to a multiple of ws, attention inside each window, 8 heads
+    const int nwy = (H + wsz - 1) / wsz, nwx = (W + wsz - 1) / wsz, nwin = nwy * nwx, groups = B * nwin;
+    float *kv, *ksum;
+    kv_ptrs<C, 8>(ws, L, groups, kv, ksum);
+    WindowRows<T> win{(T*)feat0, H, W, C, wsz, nwx, nwin, (int64_t)groups * wsz * wsz};
+    if (int e = run_kv_state<C, 8>(win, groups, w.lsa.wkv_t, kv, ksum, st)) return e;
+    if (int e = run_query<C, 8, false>(win, w.lsa, kv, ksum, st)) return e;
+    // GSA (transformer.py:138-150): keys/values = LN(sr(x)), stride-ws conv without padding
+    const int Ns = (H / wsz) * (W / wsz);
+    float* sr_tok = reinterpret_cast<float*>(ws + L.sr);
+    if (int e = sr_conv_ln(feat0, sr_tok, B, H, W, C, wsz, w.sr_t, w.sr_b, w.srln_g, w.srln_b,
+                           sizeof(T) == 4 ? CFP_F32 : CFP_BF16, st)) return e;
+    kv_ptrs<C, 8>(ws, L, B, kv, ksum);
+    SrTokSrc src{sr_tok, Ns, C, (int64_t)B * Ns};
+    if (int e = run_kv_state<C, 8>(src, B, w.gsa.wkv_t, kv, ksum, st)) return e;
+    FrameRows<T> fr{(T*)feat0, H * W, C, (int64_t)B * H * W};
+    return run_query<C, 8, false>(fr, w.gsa, kv, ksum, st);
+}
+
+#define CFP_DISPATCH_C_T(FN, ...)                                                        \
+    if (dtype == CFP_F32) {                                                              \
+        if (C == 32) return FN<32, float>(__VA_ARGS__);                                  \
+        if (C == 64) return FN<64, float>(__VA_ARGS__);                                  \
+        if (C == 128) return FN<128, float>(__VA_ARGS__);                                \
+    } else if (dtype == CFP_BF16) {                                                      \
+        if (C == 32) return FN<32, bf16>(__VA_ARGS__);                                   \
+        if (C == 64) return FN<64, bf16>(__VA_ARGS__);                                   \
+        if (C == 128) return FN<128, bf16>(__VA_ARGS__);                                 \
+    }                                                                                    \
+    return fail("unsupported (C=%d, dtype=%d): libcfp serves C in {32,64,128}, fp32/bf16", C, dtype);
+
+int d2i(void* feat0, const void* emb, const void* zone_tok, const float* pos2, const uint8_t* mask, int B, int H,
+        int W, int C, int S, const cfp_geom& g, const cfp_loftr_w& w, int assign, char* ws, const WsLayout& L,
+        int dtype, cudaStream_t st) {
+    CFP_DISPATCH_C_T(d2i_impl, feat0, emb, zone_tok, pos2, mask, B, H, W, S, g, w, assign, ws, L, st)
+}
+int dapm_attention(const void* feat0, void* msg_map, int B, int H, int W, int C, const cfp_geom& g,
+                   const cfp_loftr_w& w, char* ws, const WsLayout& L, int dtype, cudaStream_t st) {
+    CFP_DISPATCH_C_T(dapm_impl, feat0, msg_map, B, H, W, g, w, ws, L, st)
+}
+int twins(void* feat0, int B, int H, int W, int C, const cfp_twins_w& w, char* ws, const WsLayout& L, int dtype,
+          cudaStream_t st) {
+    CFP_DISPATCH_C_T(twins_impl, feat0, B, H, W, w, ws, L, st)
+}
+
+}  // namespace cfp

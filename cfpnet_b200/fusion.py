@@ -1,0 +1,132 @@
+"""Drop-in for the reference's ``TransformerFusion`` (``src/models/fusion.py:12-188``).
+
+Same constructor signature, same ``forward(x, feat1, **kwargs)`` contract
+(kwargs: ``rect_data``, ``mask``, ``patch_info``, ``rgb``), same parameter names
+and shapes, same draws from torch's global CPU generator for the positional-
+encoding crop.  Every tensor op of the reference's forward is replaced by
+hand-written sm_100a kernels behind the C ABI of include/cfp.h; this file only
+computes the host integers, owns the memory and sequences the launches.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .config import args
+from .geometry import check_geometry, zone_geometry
+from .layers import Combine1, LoFTREncoderLayer, TwinsTransformer
+from .packing import PackCache
+
+
+class TransformerFusion(nn.Module):
+    def __init__(self, embedding_dim, max_resolution, num_heads=4, large_kernel=None, patch_size=None):
+        super().__init__()
+        if num_heads != 4:
+            raise NotImplementedError("libcfp serves the hist2image / DAPM layers with 4 heads (fusion.py:13)")
+        self.zone_sample_num = args.zone_sample_num
+        self.max_resolution = max_resolution
+        self.embedding_dim = embedding_dim
+        self.positional_encodings = nn.Parameter(
+            torch.rand(max_resolution[0] * max_resolution[1], embedding_dim), requires_grad=True)
+        self.positional_encodings2 = nn.Parameter(
+            torch.rand(self.zone_sample_num, embedding_dim), requires_grad=True)
+        nn.init.trunc_normal_(self.positional_encodings, std=0.2)
+        nn.init.trunc_normal_(self.positional_encodings2, std=0.2)
+
+        self.layer_names = list(args.attention_layer)
+        self.ws = math.ceil(math.sqrt(math.sqrt(max_resolution[0] * max_resolution[1])))   # fusion.py:28
+        layers = []
+        for name in self.layer_names:
+            if name == "image":
+                layers.append(TwinsTransformer(embedding_dim, num_heads, ws=self.ws))
+            elif name == "hist2image":
+                layers.append(LoFTREncoderLayer(embedding_dim, num_heads))
+            elif name == "combine1":
+                layers.append(Combine1(embedding_dim, num_heads, large_kernel=large_kernel))
+            else:
+                raise NotImplementedError(name)           # fusion.py:37
+        self.layers = nn.ModuleList(layers)
+        self.conv_patch_size = 640 / self.max_resolution[1]
+        self._cache = PackCache(self)
+
+    # ------------------------------------------------------------------ packing
+    def _pack(self):
+        keep = []
+        packed = []
+        for layer, name in zip(self.layers, self.layer_names):
+            if name == "combine1":
+                packed.append((layer.transformer_path.pack(keep), layer.large_kernel_path.pack(keep)))
+            else:
+                packed.append(layer.pack(keep))
+        pos = self.positional_encodings.detach().float().contiguous()
+        pos2 = self.positional_encodings2.detach().float().contiguous()
+        keep += [pos, pos2]
+        return packed, pos, pos2, keep
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x, feat1, **kwargs):
+        if self.training:
+            raise NotImplementedError("libcfp serves eval-mode BatchNorm only (running statistics folded); "
+                                      "the training step is a later row of the scope table")
+        _lib.require_cuda(x, "x")
+        B, D, H, W = x.shape
+        if D != self.embedding_dim:
+            raise ValueError(f"x has {D} channels, module was built for {self.embedding_dim}")
+        dt = x.dtype
+        code = _lib.dtype_code(dt)
+        S = feat1.size(2)
+        g = zone_geometry(kwargs["patch_info"], self.max_resolution[1], H, W)
+        uses_zones = any(n in ("hist2image", "combine1") for n in self.layer_names)
+        if uses_zones:
+            check_geometry(g, H, W)
+        if feat1.shape[0] != B or feat1.shape[1] != g.zone_num ** 2 or feat1.shape[3] != D:
+            raise ValueError(f"feat1 {tuple(feat1.shape)} does not match B={B}, zones={g.zone_num ** 2}, D={D}")
+
+        # positional-encoding crop: same draws, same order as fusion.py:87-91
+        oy = ox = 0
+        if H < self.max_resolution[0]:
+            oy = int(torch.randint(0, self.max_resolution[0] - H + 1, [1]))
+        if W < self.max_resolution[1]:
+            ox = int(torch.randint(0, self.max_resolution[1] - W + 1, [1]))
+        if H > self.max_resolution[0] or W > self.max_resolution[1]:
+            raise ValueError("feature map larger than the positional-encoding table")
+
+        packed, pos, pos2, _keep = self._cache.get(self._pack)
+        dev = x.device
+        x = x.detach().contiguous()
+        feat1 = feat1.detach().to(dt).contiguous()
+        mask = kwargs["mask"].to(device=dev, dtype=torch.uint8).contiguous()
+        cg = _lib.CfpGeom.from_geometry(g)
+        st = None
+        with torch.cuda.device(dev):
+            lib = _lib.load()
+            ws_bytes = lib.cfp_workspace_bytes(B, H, W, D, self.ws, code, C.byref(cg))
+            work = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+            feat0 = torch.empty(B, H * W, D, device=dev, dtype=dt)
+            st = _lib.stream_ptr()
+            _lib.call("cfp_posenc_tokens_fwd", x.data_ptr(), pos.data_ptr(), feat0.data_ptr(), B, D, H, W,
+                      self.max_resolution[1], oy, ox, code, st)
+            emb = feat0
+            if not args.change_embedding and "hist2image" in self.layer_names:
+                emb = feat0.clone()                          # fusion.py:134-136: canvas cut from the first map
+            for w, name in zip(packed, self.layer_names):
+                if name == "image":
+                    _lib.call("cfp_twins_fwd", feat0.data_ptr(), B, H, W, D, C.byref(w), work.data_ptr(),
+                              ws_bytes, code, st)
+                elif name == "hist2image":
+                    _lib.call("cfp_d2i_fwd", feat0.data_ptr(), emb.data_ptr(), feat1.data_ptr(), pos2.data_ptr(),
+                              mask.data_ptr(), B, H, W, D, S, C.byref(cg), C.byref(w),
+                              int(bool(args.no_skip_inside)), work.data_ptr(), ws_bytes, code, st)
+                else:   # combine1: DAPM then LKPM (transformer.py:270-273)
+                    dapm_w, lkpm_w = w
+                    _lib.call("cfp_dapm_fwd", feat0.data_ptr(), B, H, W, D, C.byref(cg), C.byref(dapm_w),
+                              work.data_ptr(), ws_bytes, code, st)
+                    _lib.call("cfp_lkpm_fwd", feat0.data_ptr(), B, H, W, D, C.byref(lkpm_w), work.data_ptr(),
+                              ws_bytes, code, st)
+            out = torch.empty(B, D, H, W, device=dev, dtype=dt)
+            _lib.call("cfp_tokens_to_nchw", feat0.data_ptr(), out.data_ptr(), B, D, H, W, code, st)
+        return out

@@ -1,0 +1,224 @@
+"""Parameter containers + weight packing for the layers inside ``TransformerFusion``.
+
+Class and parameter names follow the reference (``src/models/transformer.py``,
+``src/models/convnext.py``) so that ``state_dict`` keys are identical, including
+the parameters the reference constructs but never uses (kept registered, never
+given a gradient: SURVEY.md §2).  The classes hold no torch arithmetic: their
+``pack()`` methods emit the C structs of include/cfp.h and the launch itself is
+``TransformerFusion.forward`` -> libcfp.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .packing import fold_bn, linear_t
+
+
+class LinearAttention(nn.Module):
+    """Parameter-free; kept so module trees print like the reference (attention.py:10-14)."""
+
+    def __init__(self, eps=1e-6):
+        super().__init__()
+        self.eps = eps
+
+
+class LoFTREncoderLayer(nn.Module):
+    """transformer.py:14-39."""
+
+    def __init__(self, d_model, nhead):
+        super().__init__()
+        self.dim = d_model // nhead
+        self.nhead = nhead
+        self.q_proj = nn.Linear(d_model, d_model, bias=False)
+        self.k_proj = nn.Linear(d_model, d_model, bias=False)
+        self.v_proj = nn.Linear(d_model, d_model, bias=False)
+        self.attention = LinearAttention()
+        self.merge = nn.Linear(d_model, d_model, bias=False)
+        self.mlp = nn.Sequential(
+            nn.Linear(d_model * 2, d_model * 2, bias=False),
+            nn.ReLU(True),
+            nn.Linear(d_model * 2, d_model, bias=False),
+        )
+        self.norm1 = nn.LayerNorm(d_model)
+        self.norm2 = nn.LayerNorm(d_model)
+
+    def pack(self, keep: list) -> _lib.CfpLoftrW:
+        t = dict(
+            wq_t=linear_t(self.q_proj.weight),
+            wkv_t=torch.cat([linear_t(self.k_proj.weight), linear_t(self.v_proj.weight)], dim=1).contiguous(),
+            wm_t=linear_t(self.merge.weight),
+            w1_t=linear_t(self.mlp[0].weight),
+            w2_t=linear_t(self.mlp[2].weight),
+            ln1_g=self.norm1.weight.detach().float().contiguous(),
+            ln1_b=self.norm1.bias.detach().float().contiguous(),
+            ln2_g=self.norm2.weight.detach().float().contiguous(),
+            ln2_b=self.norm2.bias.detach().float().contiguous(),
+        )
+        keep.extend(t.values())
+        return _lib.CfpLoftrW(**{k: v.data_ptr() for k, v in t.items()})
+
+
+class LocallyGroupedAttn(nn.Module):
+    """LSA, transformer.py:75-87 (8 heads by default, :78)."""
+
+    def __init__(self, dim, num_heads=8, ws=1):
+        assert ws != 1
+        super().__init__()
+        assert dim % num_heads == 0, f"dim {dim} should be divided by num_heads {num_heads}."
+        self.dim, self.num_heads, self.ws = dim, num_heads, ws
+        self.encoder_layer = LoFTREncoderLayer(dim, num_heads)
+
+
+class GlobalSubSampleAttn(nn.Module):
+    """GSA, transformer.py:119-136."""
+
+    def __init__(self, dim, num_heads=8, sr_ratio=1):
+        super().__init__()
+        assert dim % num_heads == 0, f"dim {dim} should be divided by num_heads {num_heads}."
+        self.dim, self.num_heads, self.sr_ratio = dim, num_heads, sr_ratio
+        self.encoder_layer = LoFTREncoderLayer(dim, num_heads)
+        if sr_ratio > 1:
+            self.sr = nn.Conv2d(dim, dim, kernel_size=sr_ratio, stride=sr_ratio)
+            self.norm = nn.LayerNorm(dim)
+        else:
+            self.sr = None
+            self.norm = None
+
+
+class TwinsTransformer(nn.Module):
+    """`image` layer, transformer.py:154-158.  ``num_heads`` is accepted and ignored
+    exactly like the reference: LSA and GSA are built with their default 8 heads."""
+
+    def __init__(self, dim, num_heads=8, ws=1):
+        super().__init__()
+        self.lga = LocallyGroupedAttn(dim=dim, ws=ws)
+        self.gsa = GlobalSubSampleAttn(dim=dim, sr_ratio=ws)
+
+    def pack(self, keep: list) -> _lib.CfpTwinsW:
+        if self.gsa.sr is None:
+            raise _lib.CfpError("libcfp serves GSA with sr_ratio > 1 only")
+        C, ws = self.gsa.dim, self.gsa.sr_ratio
+        w = _lib.CfpTwinsW()
+        w.lsa = self.lga.encoder_layer.pack(keep)
+        w.gsa = self.gsa.encoder_layer.pack(keep)
+        # [Cout,Cin,ws,ws] -> [(dy,dx,cin)][Cout]
+        sr_t = self.gsa.sr.weight.detach().float().permute(2, 3, 1, 0).reshape(ws * ws * C, C).contiguous()
+        t = dict(sr_t=sr_t, sr_b=self.gsa.sr.bias.detach().float().contiguous(),
+                 srln_g=self.gsa.norm.weight.detach().float().contiguous(),
+                 srln_b=self.gsa.norm.bias.detach().float().contiguous())
+        keep.extend(t.values())
+        for k, v in t.items():
+            setattr(w, k, v.data_ptr())
+        w.ws = ws
+        return w
+
+
+class LoFTREncoderLayer_newcross9(nn.Module):
+    """DAPM, transformer.py:169-202.  merge / mlp / norm1 / norm2 exist only for
+    state_dict compatibility (never used by the reference's forward)."""
+
+    def __init__(self, d_model, nhead):
+        super().__init__()
+        self.dim = d_model // nhead
+        self.nhead = nhead
+        self.q_proj = nn.Linear(d_model, d_model, bias=False)
+        self.k_proj = nn.Linear(d_model, d_model, bias=False)
+        self.v_proj = nn.Linear(d_model, d_model, bias=False)
+        self.attention = LinearAttention()
+        self.merge = nn.Linear(d_model, d_model, bias=False)
+        self.mlp = nn.Sequential(
+            nn.Linear(d_model * 2, d_model * 2, bias=False),
+            nn.ReLU(True),
+            nn.Linear(d_model * 2, d_model, bias=False),
+        )
+        self.norm1 = nn.LayerNorm(d_model)
+        self.norm2 = nn.LayerNorm(d_model)
+        self.conv1 = nn.Conv2d(d_model * 2, d_model, kernel_size=3, bias=False, padding=1)
+        self.bn1 = nn.BatchNorm2d(d_model)
+        self.conv2 = nn.Conv2d(d_model, d_model, kernel_size=3, bias=False, padding=1)
+        self.bn2 = nn.BatchNorm2d(d_model)
+        self.relu = nn.ReLU()
+
+    def pack(self, keep: list) -> _lib.CfpDapmW:
+        if self.nhead != 4:
+            raise _lib.CfpError("libcfp serves DAPM with 4 heads (fusion.py:13)")
+        w = _lib.CfpDapmW()
+        t = dict(
+            wq_t=linear_t(self.q_proj.weight),
+            wkv_t=torch.cat([linear_t(self.k_proj.weight), linear_t(self.v_proj.weight)], dim=1).contiguous(),
+        )
+        keep.extend(t.values())
+        w.attn = _lib.CfpLoftrW(**{k: v.data_ptr() for k, v in t.items()})
+        for i, (conv, bn) in enumerate(((self.conv1, self.bn1), (self.conv2, self.bn2)), start=1):
+            scale, shift = fold_bn(bn)
+            wt = conv.weight.detach().float() * scale[:, None, None, None]          # [Cout,Cin,3,3]
+            wt = wt.permute(2, 3, 1, 0).reshape(9 * wt.shape[1], wt.shape[0]).contiguous()
+            shift = shift.contiguous()
+            keep.extend((wt, shift))
+            setattr(w, f"conv{i}_t", wt.data_ptr())
+            setattr(w, f"shift{i}", shift.data_ptr())
+        return w
+
+
+class LayerNorm(nn.Module):
+    """channels_last LayerNorm container of convnext.py:60-72."""
+
+    def __init__(self, normalized_shape, eps=1e-6, data_format="channels_last"):
+        super().__init__()
+        if data_format != "channels_last":
+            raise NotImplementedError
+        self.weight = nn.Parameter(torch.ones(normalized_shape))
+        self.bias = nn.Parameter(torch.zeros(normalized_shape))
+        self.eps = eps
+
+
+class Block14(nn.Module):
+    """LKPM, convnext.py:16-40.  ``conv1`` is never used by the reference's forward;
+    gamma is None because layer_scale_init_value = 0."""
+
+    def __init__(self, dim, drop_path=0., layer_scale_init_value=0, large_kernel=7):
+        super().__init__()
+        if drop_path > 0 or layer_scale_init_value > 0:
+            raise NotImplementedError("libcfp serves Block14 as the reference instantiates it "
+                                      "(drop_path=0, no layer scale; transformer.py:259)")
+        self.dwconv2 = nn.Conv2d(dim, dim, kernel_size=large_kernel, padding=((large_kernel - 1) // 2), groups=dim)
+        self.norm = LayerNorm(dim, eps=1e-6)
+        self.pwconv1 = nn.Linear(dim, 4 * dim)
+        self.act = nn.GELU()
+        self.pwconv2 = nn.Linear(4 * dim, dim)
+        self.gamma = None
+        self.drop_path = nn.Identity()
+        self.conv1 = nn.Conv2d(dim * 2, dim, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(dim)
+        self.relu = nn.ReLU()
+
+    def pack(self, keep: list) -> _lib.CfpLkpmW:
+        k = self.dwconv2.kernel_size[0]
+        scale, shift = fold_bn(self.bn1)
+        C = scale.numel()
+        taps = self.dwconv2.weight.detach().float()[:, 0] * scale[:, None, None]        # [C,k,k]
+        t = dict(
+            dw_t=taps.permute(1, 2, 0).reshape(k * k, C).contiguous(),
+            dw_shift=(self.dwconv2.bias.detach().float() * scale + shift).contiguous(),
+            ln_g=self.norm.weight.detach().float().contiguous(),
+            ln_b=self.norm.bias.detach().float().contiguous(),
+            pw1_t=linear_t(self.pwconv1.weight),
+            pw1_b=self.pwconv1.bias.detach().float().contiguous(),
+            pw2_t=linear_t(self.pwconv2.weight),
+            pw2_b=self.pwconv2.bias.detach().float().contiguous(),
+        )
+        keep.extend(t.values())
+        w = _lib.CfpLkpmW(**{n: v.data_ptr() for n, v in t.items()})
+        w.ksize = k
+        return w
+
+
+class Combine1(nn.Module):
+    """DAPM -> LKPM, transformer.py:251-259."""
+
+    def __init__(self, d_model, nhead, large_kernel):
+        super().__init__()
+        self.transformer_path = LoFTREncoderLayer_newcross9(d_model, nhead)
+        self.large_kernel_path = Block14(d_model, large_kernel=large_kernel)

@@ -1,0 +1,123 @@
+"""Deterministic synthetic inputs and weights for the fusion path.
+
+Shared by ``tests/``, ``tools/make_golden.py`` and ``bench.py`` so that every
+party (reference modules in the build container, CPU oracle, CUDA path) sees
+byte-identical inputs and weights without shipping them: everything is a pure
+function of (name, shape, seed) on torch's CPU generator.
+
+Input recipe = SURVEY.md §8d: decoder features ``x ~ N(0,1)`` per level, zone
+samples ``linspace(mu-3s, mu+3s, 16)`` with ``mu~U(0.3,4)``, ``s~U(0.01,0.2)``
+(the reference's ``sample_uniform`` path, ``src/utils/dataloader.py:74-79``),
+zeros for invalid zones, ``mask ~ Bernoulli(0.8)``, zone rectangles on a
+centred grid.
+"""
+from __future__ import annotations
+
+import math
+import zlib
+from typing import Dict, Mapping, Sequence, Tuple
+
+import torch
+
+from .geometry import patch_info_from_rect_data, collate_patch_info
+
+# name -> (image H, image W, zone px)   (SURVEY.md §8 geometries)
+GEOMETRIES = {
+    "G416": (416, 544, 48),
+    "G480": (480, 640, 56),      # L3 takes the bilinear-resize branch
+    "G480pad": (480, 640, 64),   # zones reach outside the image: pad_mask path
+}
+# level -> (C, downscale, max_resolution, large_kernel)   (decoder.py:82-94)
+LEVELS = {
+    3: (128, 16, (30, 40), 7),
+    2: (64, 8, (60, 80), 15),
+    1: (32, 4, (120, 160), 31),
+}
+COMBINE1_LAYERS = ("hist2image", "combine1", "image", "hist2image", "combine1", "image")
+BASELINE_LAYERS = ("hist2image", "image", "hist2image", "image")
+
+
+def _gen(seed: int, name: str) -> torch.Generator:
+    g = torch.Generator(device="cpu")
+    g.manual_seed((seed * 1000003 + zlib.crc32(name.encode())) % (2 ** 63))
+    return g
+
+
+def centred_rects(img_h: int, img_w: int, zone_px: int, zone_num: int = 8) -> torch.Tensor:
+    """[Z,4] float (y0,x0,y1,x1): zone_num x zone_num grid of square zones
+    centred in the image, row-major (what ``get_hist_parallel`` emits,
+    ``src/utils/dataloader.py:101-123``)."""
+    y0 = int((img_h - zone_px * zone_num) / 2)
+    x0 = int((img_w - zone_px * zone_num) / 2)
+    ys = torch.arange(zone_num, dtype=torch.float32) * zone_px + y0
+    xs = torch.arange(zone_num, dtype=torch.float32) * zone_px + x0
+    yy, xx = torch.meshgrid(ys, xs, indexing="ij")
+    return torch.stack([yy, xx, yy + zone_px, xx + zone_px], dim=-1).reshape(-1, 4)
+
+
+def level_hw(geometry: str, level: int) -> Tuple[int, int]:
+    img_h, img_w, _ = GEOMETRIES[geometry]
+    s = LEVELS[level][1]
+    return img_h // s, img_w // s
+
+
+def make_inputs(geometry: str, batch: int, seed: int = 1, levels: Sequence[int] = (3, 2, 1),
+                dtype=torch.float32, zone_num: int = 8, p_valid: float = 0.8) -> dict:
+    """One synthetic batch: ``x{level}`` [B,C,h,w], ``hist_data`` [B,Z,16],
+    ``mask`` [B,Z] bool, ``rect_data`` [B,Z,4], ``patch_info`` (collated)."""
+    img_h, img_w, zone_px = GEOMETRIES[geometry]
+    Z = zone_num * zone_num
+    out = {}
+    for lv in levels:
+        C = LEVELS[lv][0]
+        h, w = level_hw(geometry, lv)
+        out[f"x{lv}"] = torch.randn(batch, C, h, w, generator=_gen(seed, f"x{lv}")).to(dtype)
+    g = _gen(seed, "hist")
+    mu = torch.rand(batch, Z, generator=g) * 3.7 + 0.3
+    sg = torch.rand(batch, Z, generator=g) * 0.19 + 0.01
+    mask = torch.rand(batch, Z, generator=g) < p_valid
+    t = torch.linspace(0, 1, 16)
+    samples = (mu - 3 * sg).unsqueeze(-1) * (1 - t) + (mu + 3 * sg).unsqueeze(-1) * t
+    out["hist_data"] = (samples * mask.unsqueeze(-1)).to(torch.float32)
+    out["mask"] = mask
+    rect = centred_rects(img_h, img_w, zone_px, zone_num)
+    out["rect_data"] = rect.unsqueeze(0).repeat(batch, 1, 1)
+    out["patch_info"] = collate_patch_info([patch_info_from_rect_data(rect)] * batch)
+    return out
+
+
+def synthetic_state_dict(shapes: Mapping[str, Sequence[int]], seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Deterministic weights for any module given its state_dict shapes.
+
+    Magnitudes follow ``Deltar._reset_parameters`` (``deltar.py:23-32``):
+    kaiming-normal fan_out for conv/linear weights, ``trunc_normal(std=0.2)``
+    for the positional tables (``fusion.py:22-23``) — but norm layers and BN
+    running statistics are *randomised* (not 1/0) so that BN folding, affine
+    LayerNorm and biases are actually exercised by the parity tests.
+    """
+    sd = {}
+    for name, shape in shapes.items():
+        shape = tuple(shape)
+        g = _gen(seed, name)
+        leaf = name.rsplit(".", 1)[-1]
+        parent = name.rsplit(".", 2)[-2] if name.count(".") else ""
+        is_norm = parent.startswith(("bn", "norm"))
+        if leaf == "num_batches_tracked":
+            t = torch.tensor(7, dtype=torch.long)
+        elif name.endswith("positional_encodings") or name.endswith("positional_encodings2"):
+            t = (torch.randn(shape, generator=g) * 0.2).clamp_(-0.4, 0.4)
+        elif leaf == "running_mean":
+            t = torch.randn(shape, generator=g) * 0.2
+        elif leaf == "running_var":
+            t = torch.rand(shape, generator=g) + 0.5
+        elif is_norm and leaf == "weight":
+            t = torch.rand(shape, generator=g) + 0.5
+        elif leaf == "bias":
+            t = torch.randn(shape, generator=g) * 0.1
+        elif leaf == "weight" and len(shape) >= 2:
+            fan_out = shape[0] * int(math.prod(shape[2:]))
+            t = torch.randn(shape, generator=g) * math.sqrt(2.0 / fan_out)
+        else:
+            raise KeyError(f"no synthetic rule for {name} {shape}")
+        sd[name] = t
+    return sd

@@ -1,0 +1,150 @@
+/* libcfp — C ABI of the B200-native CFP fusion + cross-zone propagation path.
+ *
+ * The reference (denyingmxd/CFPNet) is pure PyTorch and has no FFI of its own;
+ * this header is the boundary a maintainer binds with ctypes from the
+ * reference's `src/models` modules.  Each entry point
+ * names the reference code it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch); the
+ *     library borrows it for the duration of the enqueue, allocates nothing
+ *     persistent and never synchronises the device;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*) of the
+ *     caller's current device; the library is re-entrant (no global mutable
+ *     state; the last error message is thread-local);
+ *   - activations are token-major [B, N=H*W, C] unless stated otherwise;
+ *     `dtype` selects the activation element type (CFP_F32 or CFP_BF16);
+ *     packed weights are always fp32 in the layouts documented per struct;
+ *   - return value 0 = enqueued; non-zero = rejected, message in
+ *     cfp_last_error().  Unsupported (C, kernel size, dtype) combinations are
+ *     hard errors: there is no fallback path.
+ */
+#ifndef CFP_H_
+#define CFP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CFP_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define CFP_API __attribute__((visibility("default")))
+#else
+#define CFP_API
+#endif
+
+enum cfp_dtype { CFP_F32 = 0, CFP_BF16 = 1 };
+
+/* Per-level zone geometry: the host integers TransformerFusion.forward derives
+ * from patch_info (src/models/fusion.py:67-84) plus the clipped in-image zone
+ * rectangle of fusion.py:104.  Computed by cfpnet_b200.geometry.zone_geometry. */
+typedef struct cfp_geom {
+    int32_t zone_num;            /* zones per side (8)                                  */
+    int32_t pad_h, pad_w;        /* F.pad amounts, fusion.py:136                        */
+    int32_t p1, p2;              /* patch cells per zone                                */
+    int32_t sy_wo, sx_wo, ey_wo, ex_wo; /* zone canvas in un-padded map coordinates     */
+    int32_t tzh, tzw;            /* canvas size = ey-sy, ex-sx                          */
+    int32_t interpolate;         /* canvas != zone_num*p -> bilinear resize branch      */
+    int32_t ry0, ry1, rx0, rx1;  /* in-image zone rectangle (zone_mask), rows/cols      */
+} cfp_geom;
+
+/* One LoFTREncoderLayer (src/models/transformer.py:14-71), packed:
+ *   wq_t [C][C], wkv_t [C][2C] (k_proj | v_proj), wm_t [C][C], w1_t [2C][2C],
+ *   w2_t [2C][C]: nn.Linear weights transposed to [in][out];
+ *   ln1_g/b, ln2_g/b [C].  DAPM uses only wq_t and wkv_t. */
+typedef struct cfp_loftr_w {
+    const float *wq_t, *wkv_t, *wm_t, *w1_t, *w2_t;
+    const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+} cfp_loftr_w;
+
+/* DAPM convs (transformer.py:197-200, 239-244) with eval-mode BN folded:
+ *   conv1_t [(tap,cin<2C)][C], conv2_t [(tap,cin<C)][C]  (tap = ky*3+kx),
+ *   weights pre-multiplied by the BN scale; shift1/shift2 [C]. */
+typedef struct cfp_dapm_w {
+    cfp_loftr_w attn;
+    const float *conv1_t, *shift1, *conv2_t, *shift2;
+} cfp_dapm_w;
+
+/* LKPM Block14 (src/models/convnext.py:42-58), eval-mode BN folded:
+ *   dw_t [k*k][C] depthwise taps (tap = ky*k+kx) times BN scale, dw_shift [C];
+ *   ln_g/b [C]; pw1_t [C][4C], pw1_b [4C]; pw2_t [4C][C], pw2_b [C]. */
+typedef struct cfp_lkpm_w {
+    const float *dw_t, *dw_shift, *ln_g, *ln_b, *pw1_t, *pw1_b, *pw2_t, *pw2_b;
+    int32_t ksize;
+} cfp_lkpm_w;
+
+/* TwinsTransformer (transformer.py:154-165): LSA layer, GSA layer, and the GSA
+ * sub-sampling conv sr_t [(dy,dx,cin)][C] + sr_b [C] + LayerNorm srln_g/b [C]. */
+typedef struct cfp_twins_w {
+    cfp_loftr_w lsa, gsa;
+    const float *sr_t, *sr_b, *srln_g, *srln_b;
+    int32_t ws;
+} cfp_twins_w;
+
+/* HistogramEncoder (src/models/encoder.py:6-50): 9 pointwise stages with
+ * eval-mode BN folded; w_t[i] is [Cin][Cout], b[i] is [Cout]. */
+typedef struct cfp_hist_w {
+    const float *w_t[9];
+    const float *b[9];
+} cfp_hist_w;
+
+CFP_API int cfp_version(void);
+/* Thread-local message of the last failed call ("" if none). */
+CFP_API const char *cfp_last_error(void);
+
+/* Scratch bytes (fp32 attention state + token scratch) one fusion call needs;
+ * the caller allocates it (torch.empty) and passes it to the layer calls. */
+CFP_API size_t cfp_workspace_bytes(int B, int H, int W, int C, int ws, int dtype, const cfp_geom *g);
+
+/* a1. HistogramEncoder.forward (encoder.py:45-50; deltar.py:40).
+ * hist [rows] fp32 zone depth samples (rows = B*Z*S) -> out32 [rows][32],
+ * out64 [rows][64], out128 [rows][128] in `dtype`. */
+CFP_API int cfp_hist_encoder_fwd(const float *hist, void *out32, void *out64, void *out128, int64_t rows,
+                         const cfp_hist_w *w, int dtype, void *stream);
+
+/* a3. The three masks TransformerFusion.forward materialises (fusion.py:103-120),
+ * as bytes (0/1), without the channel repeat: zone_mask [B][H*W],
+ * hist_mask [B*Z][p1*p2], pad_mask [B][tzh][tzw].  mask = [B][Z] validity bytes.
+ * Export for the bit-exact tests; the layer kernels use cfp_geom directly. */
+CFP_API int cfp_zone_masks(const uint8_t *mask, uint8_t *zone_mask, uint8_t *hist_mask, uint8_t *pad_mask,
+                   int B, int H, int W, const cfp_geom *g, void *stream);
+
+/* a4. Positional-encoding add + NCHW -> token-major (fusion.py:92-97):
+ * tokens[b][y*W+x][c] = x[b][c][y][x] + pos[(oy+y)*pos_w + ox+x][c]. */
+CFP_API int cfp_posenc_tokens_fwd(const void *x_nchw, const float *pos, void *tokens, int B, int C, int H,
+                          int W, int pos_w, int oy, int ox, int dtype, void *stream);
+/* fusion.py:186: token-major -> contiguous NCHW. */
+CFP_API int cfp_tokens_to_nchw(const void *tokens, void *out_nchw, int B, int C, int H, int W, int dtype,
+                       void *stream);
+
+/* a5. `hist2image` branch (fusion.py:132-157 + transformer.py:41-71 +
+ * attention.py:20-52).  feat0 [B][N][C] is updated in place; emb is the map the
+ * zone canvas is cut from (== feat0 under --change_embedding).  zone_tok
+ * [B*Z][S][C] are the raw histogram tokens (positional_encodings2 `pos2` [S][C]
+ * is added inside); mask [B][Z] bytes.  assign != 0 = --no_skip_inside. */
+CFP_API int cfp_d2i_fwd(void *feat0, const void *emb, const void *zone_tok, const float *pos2,
+                const uint8_t *mask, int B, int H, int W, int C, int S, const cfp_geom *g,
+                const cfp_loftr_w *w, int assign, void *workspace, size_t workspace_bytes,
+                int dtype, void *stream);
+
+/* a6. DAPM, LoFTREncoderLayer_newcross9.forward (transformer.py:204-248); in place. */
+CFP_API int cfp_dapm_fwd(void *feat0, int B, int H, int W, int C, const cfp_geom *g, const cfp_dapm_w *w,
+                 void *workspace, size_t workspace_bytes, int dtype, void *stream);
+
+/* a7. LKPM, Block14.forward (convnext.py:42-58) on token-major maps; in place. */
+CFP_API int cfp_lkpm_fwd(void *feat0, int B, int H, int W, int C, const cfp_lkpm_w *w, void *workspace,
+                 size_t workspace_bytes, int dtype, void *stream);
+
+/* a9. `image` layer, TwinsTransformer.forward (transformer.py:89-116, 138-150,
+ * 160-165): LSA then GSA, 8 heads; in place. */
+CFP_API int cfp_twins_fwd(void *feat0, int B, int H, int W, int C, const cfp_twins_w *w, void *workspace,
+                  size_t workspace_bytes, int dtype, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CFP_H_ */

@@ -1,0 +1,219 @@
+"""Parity of the CUDA path (through the drop-in modules -> C ABI -> sm_100a kernels) against
+the CPU oracle and the committed reference outputs.  Tolerances:
+masks / indices bit-exact; fp32 features rel-L2 <= 1e-3; bf16 rel-L2 <= 2e-2 (vs fp64 truth)."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cfpnet_b200
+from cfpnet_b200 import _lib, geometry, synth
+from cfpnet_b200.config import args
+from helpers import FUSION_CASES, FusionCase, GOLDEN, ref_keys, rel_l2
+from oracle import cfp_oracle as O
+
+pytestmark = pytest.mark.gpu
+FP32_TOL, BF16_TOL = 1e-3, 2e-2
+DEV = "cuda:0"
+
+
+def build_fusion(case_or_level, layers=synth.COMBINE1_LAYERS, change_embedding=True, no_skip_inside=False,
+                 dtype=torch.float32):
+    if isinstance(case_or_level, FusionCase):
+        c = case_or_level
+        level, layers, change_embedding, no_skip_inside = c.level, c.layers, c.change_embedding, c.no_skip_inside
+    else:
+        level = case_or_level
+    C, _, max_res, lk = synth.LEVELS[level]
+    args.attention_layer = list(layers)
+    args.change_embedding, args.no_skip_inside = change_embedding, no_skip_inside
+    m = cfpnet_b200.TransformerFusion(C, list(max_res), large_kernel=lk, patch_size=640 // max_res[1])
+    kind = "baseline" if tuple(layers) == synth.BASELINE_LAYERS else "combine1"
+    sd = synth.synthetic_state_dict(ref_keys()[f"fusion_{kind}_L{level}"], seed=level)
+    m.load_state_dict(sd, strict=True)
+    return m.to(DEV).to(dtype).eval(), sd
+
+
+def build_hist(dtype=torch.float32):
+    enc = cfpnet_b200.HistogramEncoder()
+    sd = synth.synthetic_state_dict(ref_keys()["hist_encoder"], seed=0)
+    enc.load_state_dict(sd, strict=True)
+    enc = enc.to(DEV).eval()
+    enc.out_dtype = dtype
+    return enc, sd
+
+
+@pytest.fixture(autouse=True)
+def _restore_flags():
+    saved = (list(args.attention_layer), args.change_embedding, args.no_skip_inside)
+    yield
+    args.attention_layer, args.change_embedding, args.no_skip_inside = saved
+
+
+# ------------------------------------------------------------------ a1
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 4e-3)])
+def test_hist_encoder(dtype, tol):
+    enc, sd = build_hist(dtype)
+    inp = synth.make_inputs("G416", 2, seed=1, levels=())
+    outs = enc(inp["hist_data"].to(DEV).unsqueeze(-1))
+    z = np.load(os.path.join(GOLDEN, "hist_encoder_B2.npz"))
+    truth = O.hist_encoder(sd, inp["hist_data"].double())
+    for c, o, t in zip((32, 64, 128), outs, truth):
+        assert o.shape == (2, 64, 16, c) and o.dtype == dtype
+        assert rel_l2(o, torch.from_numpy(z[f"out{c}"])) <= tol      # the reference's own output
+        assert rel_l2(o, t) <= tol                                     # fp64 oracle
+
+
+def test_hist_encoder_ragged_rows():
+    """Row counts that are not a multiple of the 64-row tile, and a single zone."""
+    enc, sd = build_hist()
+    for B, Z in ((1, 1), (3, 5), (1, 64)):
+        h = torch.rand(B, Z, 16, generator=torch.Generator().manual_seed(B * 7 + Z)) * 4
+        outs = enc(h.to(DEV).unsqueeze(-1))
+        for o, t in zip(outs, O.hist_encoder(sd, h.double())):
+            assert rel_l2(o, t) <= 1e-5
+
+
+# ------------------------------------------------------------------ a2/a3
+@pytest.mark.parametrize("tag", ["G416_L3_B2", "G480_L3_B1", "G480pad_L3_B1", "G480pad_L2_B1", "G416_L1_B1"])
+def test_masks_bit_exact(tag):
+    case = FusionCase(tag)
+    inp = case.inputs()
+    H, W = synth.level_hw(case.geometry, case.level)
+    g = geometry.zone_geometry(inp["patch_info"], case.max_res[1], H, W)
+    cg = _lib.CfpGeom.from_geometry(g)
+    B, P = case.batch, g.p1 * g.p2
+    mask = inp["mask"].to(DEV, torch.uint8).contiguous()
+    zm = torch.empty(B, H * W, dtype=torch.uint8, device=DEV)
+    hm = torch.empty(B * 64, P, dtype=torch.uint8, device=DEV)
+    pm = torch.empty(B, g.tzh, g.tzw, dtype=torch.uint8, device=DEV)
+    _lib.call("cfp_zone_masks", mask.data_ptr(), zm.data_ptr(), hm.data_ptr(), pm.data_ptr(), B, H, W,
+              ctypes.byref(cg), _lib.stream_ptr())
+    torch.cuda.synchronize()
+    assert np.array_equal(zm.cpu().numpy().astype(bool), case.mask_bits("zone_mask"))
+    assert np.array_equal(hm.cpu().numpy().astype(bool), case.mask_bits("hist_mask"))
+    assert np.array_equal(pm.cpu().numpy().astype(bool), case.mask_bits("pad_mask"))
+    # and against the oracle's restatement, with the channel repeat
+    ozm, ohm, opm = O.zone_masks(g.asdict(), inp["mask"], B, H, W, case.C)
+    assert torch.equal(zm.cpu().bool(), ozm[:, :, 0]) and torch.equal(hm.cpu().bool(), ohm[:, :, 0])
+    assert torch.equal(pm.cpu().bool().reshape(-1), opm.view(-1, case.C)[:, 0])
+
+
+# ------------------------------------------------------------------ a4-a9 through TransformerFusion
+def run_case(case, dtype):
+    m, sd = build_fusion(case, dtype=dtype)
+    enc, hsd = build_hist(dtype)
+    inp = case.inputs()
+    feats = enc(inp["hist_data"].to(DEV).unsqueeze(-1))
+    feat1 = {32: feats[0], 64: feats[1], 128: feats[2]}[case.C]
+    torch.manual_seed(2)                       # same positional-encoding crop draws as the reference run
+    out = m(inp[f"x{case.level}"].to(DEV, dtype), feat1, rect_data=inp["rect_data"], mask=inp["mask"].to(DEV),
+            patch_info=inp["patch_info"], rgb=None)
+    torch.cuda.synchronize()
+    return out, inp, sd, hsd
+
+
+@pytest.mark.parametrize("tag", FUSION_CASES)
+def test_fusion_fp32_vs_reference(tag):
+    case = FusionCase(tag)
+    out, *_ = run_case(case, torch.float32)
+    assert out.dtype == torch.float32 and out.is_contiguous()
+    case.check_output(out, FP32_TOL, f"cuda fp32 {tag}")
+
+
+@pytest.mark.parametrize("tag", FUSION_CASES)
+def test_fusion_bf16_vs_reference(tag):
+    case = FusionCase(tag)
+    out, *_ = run_case(case, torch.bfloat16)
+    assert out.dtype == torch.bfloat16
+    case.check_output(out, BF16_TOL, f"cuda bf16 {tag}")
+
+
+@pytest.mark.parametrize("level", [3, 2, 1])
+def test_fusion_vs_oracle_batch3(level):
+    """Batch > 1 with per-frame masks, against the fp64 oracle on the same seeded inputs."""
+    m, sd = build_fusion(level)
+    enc, hsd = build_hist()
+    C, _, max_res, _ = synth.LEVELS[level]
+    inp = synth.make_inputs("G416", 3, seed=5, levels=(level,))
+    feats = enc(inp["hist_data"].to(DEV).unsqueeze(-1))
+    feat1 = {32: feats[0], 64: feats[1], 128: feats[2]}[C]
+    torch.manual_seed(11)
+    out = m(inp[f"x{level}"].to(DEV), feat1, rect_data=inp["rect_data"], mask=inp["mask"].to(DEV),
+            patch_info=inp["patch_info"], rgb=None)
+    torch.manual_seed(11)
+    of = O.hist_encoder(hsd, inp["hist_data"].double())
+    truth = O.transformer_fusion(sd, synth.COMBINE1_LAYERS, max_res, inp[f"x{level}"].double(),
+                                 {32: of[0], 64: of[1], 128: of[2]}[C], inp["mask"], inp["patch_info"])
+    assert rel_l2(out, truth) <= FP32_TOL
+
+
+def test_all_zones_invalid_leaves_zone_cells_untouched_by_hist2image():
+    """mask all False: hist2image contributes nothing (fusion.py:144), the rest still runs."""
+    level = 3
+    m, sd = build_fusion(level)
+    enc, hsd = build_hist()
+    inp = synth.make_inputs("G416", 1, seed=3, levels=(level,))
+    mask = torch.zeros_like(inp["mask"])
+    feats = enc(inp["hist_data"].to(DEV).unsqueeze(-1))
+    torch.manual_seed(4)
+    out = m(inp["x3"].to(DEV), feats[2], rect_data=inp["rect_data"], mask=mask.to(DEV),
+            patch_info=inp["patch_info"], rgb=None)
+    torch.manual_seed(4)
+    of = O.hist_encoder(hsd, inp["hist_data"].double())
+    truth = O.transformer_fusion(sd, synth.COMBINE1_LAYERS, (30, 40), inp["x3"].double(), of[2], mask,
+                                 inp["patch_info"])
+    assert rel_l2(out, truth) <= FP32_TOL
+
+
+def test_same_seed_same_output_and_rng_consumption():
+    """The drop-in draws from the global CPU generator exactly like the reference:
+    two draws at 416x544, none at 480x640 (fusion.py:88-91)."""
+    m, _ = build_fusion(3)
+    enc, _ = build_hist()
+    inp = synth.make_inputs("G416", 1, levels=(3,))
+    feats = enc(inp["hist_data"].to(DEV).unsqueeze(-1))
+    kw = dict(rect_data=inp["rect_data"], mask=inp["mask"].to(DEV), patch_info=inp["patch_info"], rgb=None)
+    torch.manual_seed(2)
+    a = m(inp["x3"].to(DEV), feats[2], **kw)
+    after = torch.randint(0, 1000, [1])
+    torch.manual_seed(2)
+    b = m(inp["x3"].to(DEV), feats[2], **kw)
+    assert torch.equal(a, b)
+    torch.manual_seed(2)
+    torch.randint(0, 5, [1]); torch.randint(0, 7, [1])
+    assert torch.equal(after, torch.randint(0, 1000, [1]))
+    inp = synth.make_inputs("G480", 1, levels=(3,))
+    state = torch.get_rng_state()
+    m(inp["x3"].to(DEV), feats[2], rect_data=inp["rect_data"], mask=inp["mask"].to(DEV),
+      patch_info=inp["patch_info"], rgb=None)
+    assert torch.equal(state, torch.get_rng_state())
+
+
+def test_full_batch_properties():
+    """BASELINE.json config 3 size (B=64, bf16, G416): size-independent properties instead of a
+    64-frame oracle run — (1) frames are independent: frame i of the batch equals the same frame run
+    alone (identical kernels, identical per-frame arithmetic -> bit-exact), (2) outputs finite."""
+    dtype = torch.bfloat16
+    enc, _ = build_hist(dtype)
+    B = 64
+    inp = synth.make_inputs("G416", B, seed=9)
+    feats = enc(inp["hist_data"].to(DEV).unsqueeze(-1))
+    for level in (3, 2, 1):
+        m, _ = build_fusion(level, dtype=dtype)
+        C = synth.LEVELS[level][0]
+        feat1 = {32: feats[0], 64: feats[1], 128: feats[2]}[C]
+        x = inp[f"x{level}"].to(DEV, dtype)
+        kw = dict(rect_data=inp["rect_data"], rgb=None)
+        torch.manual_seed(2)
+        full = m(x, feat1, mask=inp["mask"].to(DEV), patch_info=inp["patch_info"], **kw)
+        assert torch.isfinite(full).all()
+        for i in (0, 37, 63):
+            pi = {k: ({kk: vv[i:i + 1] for kk, vv in v.items()} if isinstance(v, dict) else v[i:i + 1])
+                  for k, v in inp["patch_info"].items()}
+            torch.manual_seed(2)
+            one = m(x[i:i + 1], feat1[i:i + 1], mask=inp["mask"][i:i + 1].to(DEV), patch_info=pi, **kw)
+            # fp32 atomics in the attention state make the last bits order-dependent
+            assert rel_l2(one, full[i:i + 1]) <= 1e-2

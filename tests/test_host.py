@@ -1,0 +1,166 @@
+"""CPU tests of the host side: geometry, drop-in contract (state_dict keys), the C-ABI
+library's symbol table, and loud failure without a GPU.  No compute calls."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import cfpnet_b200
+from cfpnet_b200 import _lib, geometry, synth
+from cfpnet_b200.config import args
+from helpers import FUSION_CASES, FusionCase, ref_keys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from cfpnet_b200.build import build
+    build()
+    return _lib.load()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    header = open(os.path.join(ROOT, "include", "cfp.h")).read()
+    declared = sorted(set(re.findall(r"\b(cfp_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 11
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(raw, name), f"{name} declared in include/cfp.h but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
+    assert lib.cfp_version() == _lib.ABI_VERSION
+    assert lib.cfp_last_error() is not None
+
+
+def test_ctypes_structs_match_header_layout():
+    assert ctypes.sizeof(_lib.CfpGeom) == 16 * 4
+    assert ctypes.sizeof(_lib.CfpLoftrW) == 9 * 8
+    assert ctypes.sizeof(_lib.CfpDapmW) == 13 * 8
+    assert ctypes.sizeof(_lib.CfpLkpmW) == 9 * 8          # 8 pointers + int32 (+pad)
+    assert ctypes.sizeof(_lib.CfpTwinsW) == 18 * 8 + 4 * 8 + 8
+    assert ctypes.sizeof(_lib.CfpHistW) == 18 * 8
+
+
+def test_workspace_bytes_is_pure_host_arithmetic(lib):
+    g = _lib.CfpGeom(zone_num=8, p1=3, p2=3, tzh=24, tzw=24, ry1=24, rx1=24)
+    small = lib.cfp_workspace_bytes(1, 26, 34, 128, 6, _lib.CFP_F32, ctypes.byref(g))
+    big = lib.cfp_workspace_bytes(4, 26, 34, 128, 6, _lib.CFP_F32, ctypes.byref(g))
+    half = lib.cfp_workspace_bytes(4, 26, 34, 128, 6, _lib.CFP_BF16, ctypes.byref(g))
+    assert 0 < small < big and half < big
+
+
+def test_rejected_call_sets_thread_local_message(lib):
+    rc = lib.cfp_lkpm_fwd(None, 1, 8, 8, 48, None, None, 0, 0, None)
+    assert rc != 0 and b"null" in lib.cfp_last_error().lower()
+    rc = lib.cfp_lkpm_fwd(ctypes.c_void_p(256), 1, 8, 8, 48, None, None, 0, 0, None)
+    assert rc != 0 and b"embedding_dim" in lib.cfp_last_error()
+
+
+@pytest.mark.parametrize("tag", FUSION_CASES)
+def test_zone_geometry_matches_reference(tag):
+    case = FusionCase(tag)
+    inp = case.inputs()
+    H, W = synth.level_hw(case.geometry, case.level)
+    g = geometry.zone_geometry(inp["patch_info"], case.max_res[1], H, W)
+    ref = case.geo
+    got = dict(pad_height=g.pad_h, pad_width=g.pad_w, p1=g.p1, p2=g.p2, sy_wo_pad=g.sy_wo, sx_wo_pad=g.sx_wo,
+               ey_wo_pad=g.ey_wo, ex_wo_pad=g.ex_wo, sy=g.sy, ey=g.ey, sx=g.sx, ex=g.ex, tzh=g.tzh, tzw=g.tzw,
+               interpolate=g.interpolate, zone_num=g.zone_num)
+    for k, v in got.items():
+        assert v == ref[k], (k, v, ref[k])
+    geometry.check_geometry(g, H, W)
+    zm = case.mask_bits("zone_mask").reshape(case.batch, H, W)
+    rect = np.zeros((H, W), dtype=bool)
+    rect[g.ry0:g.ry1, g.rx0:g.rx1] = True
+    assert all(np.array_equal(zm[b], rect) for b in range(case.batch))
+    assert g.n_inside == int(rect.sum())
+
+
+def test_patch_info_truncation_and_padding_rules():
+    # negative starts truncate toward zero; pads are relative to the hard-coded 480x640 canvas
+    rect = synth.centred_rects(480, 640, 64)             # rows -16 .. 496
+    pi = geometry.patch_info_from_rect_data(rect)
+    assert pi["zone_num"] == 8
+    assert pi[16]["pad_size"].tolist() == [1, 0] and pi[4]["pad_size"].tolist() == [4, 0]
+    assert pi[16]["index_wo_pad"].tolist() == [-1, 4, 31, 36]
+    rect2 = rect.clone()
+    rect2[:, 0] += 6                                      # y0 = -10 -> trunc(-10/16) = 0, pad = ceil(10/16) = 1
+    rect2[:, 2] += 6
+    pi2 = geometry.patch_info_from_rect_data(rect2)
+    assert pi2[16]["index_wo_pad"][0].item() == 0 and pi2[16]["pad_size"][0].item() == 2
+    assert pi2[16]["patch_size"].tolist() == [4, 4]
+    # ragged zones: the largest zone defines the patch size (ceil)
+    rect3 = synth.centred_rects(416, 544, 48)
+    rect3[5, 2] += 5
+    assert geometry.patch_info_from_rect_data(rect3)[16]["patch_size"].tolist() == [4, 3]
+
+
+def test_check_geometry_rejects_what_the_reference_cannot_run():
+    # zones hanging below a 416-row image but inside 480: pad = 0, the canvas slice would be cut short
+    rect = synth.centred_rects(416, 544, 48)
+    rect[:, 0] += 40
+    rect[:, 2] += 40
+    pi = geometry.collate_patch_info([geometry.patch_info_from_rect_data(rect)])
+    g = geometry.zone_geometry(pi, 40, 26, 34)
+    with pytest.raises(ValueError):
+        geometry.check_geometry(g, 26, 34)
+
+
+def test_state_dict_keys_match_reference():
+    keys = ref_keys()
+    enc = cfpnet_b200.HistogramEncoder()
+    assert {k: list(v.shape) for k, v in enc.state_dict().items()} == keys["hist_encoder"]
+    saved = list(args.attention_layer)
+    try:
+        for kind, layers in (("combine1", synth.COMBINE1_LAYERS), ("baseline", synth.BASELINE_LAYERS)):
+            args.attention_layer = list(layers)
+            for level, (C, _, max_res, lk) in synth.LEVELS.items():
+                m = cfpnet_b200.TransformerFusion(C, list(max_res), large_kernel=lk, patch_size=640 // max_res[1])
+                mine = {k: list(v.shape) for k, v in m.state_dict().items()}
+                assert mine == keys[f"fusion_{kind}_L{level}"], (kind, level)
+                m.load_state_dict(synth.synthetic_state_dict(keys[f"fusion_{kind}_L{level}"], seed=level), strict=True)
+    finally:
+        args.attention_layer = saved
+
+
+def test_unknown_layer_name_raises_like_reference():
+    saved = list(args.attention_layer)
+    try:
+        args.attention_layer = ["hist2image", "bogus"]
+        with pytest.raises(NotImplementedError):
+            cfpnet_b200.TransformerFusion(32, [120, 160], large_kernel=31, patch_size=4)
+    finally:
+        args.attention_layer = saved
+
+
+def test_product_path_has_no_cpu_fallback():
+    m = cfpnet_b200.TransformerFusion(128, [30, 40], large_kernel=7, patch_size=4).eval()
+    inp = synth.make_inputs("G416", 1, levels=(3,))
+    with pytest.raises(_lib.CfpError, match="no CPU implementation"):
+        m(inp["x3"], torch.zeros(1, 64, 16, 128), mask=inp["mask"], patch_info=inp["patch_info"],
+          rect_data=inp["rect_data"], rgb=None)
+    enc = cfpnet_b200.HistogramEncoder().eval()
+    with pytest.raises(_lib.CfpError, match="no CPU implementation"):
+        enc(inp["hist_data"].unsqueeze(-1))
+    with pytest.raises(NotImplementedError):
+        enc.train()(inp["hist_data"].unsqueeze(-1))
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "cfpnet_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(root, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle|cfp_oracle|import_module\(.oracle", src, re.M), f
+
+
+def test_synthetic_inputs_are_deterministic():
+    a, b = synth.make_inputs("G416", 2, levels=(3,)), synth.make_inputs("G416", 2, levels=(3,))
+    assert torch.equal(a["x3"], b["x3"]) and torch.equal(a["hist_data"], b["hist_data"])
+    assert torch.equal(a["mask"], b["mask"])
+    assert (a["hist_data"][~a["mask"]] == 0).all()
+    assert 0.6 < a["mask"].float().mean() < 0.95

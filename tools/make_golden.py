@@ -1,0 +1,179 @@
+"""Generate ``tests/golden/*.npz`` from the REFERENCE modules (container only).
+
+    python tools/make_golden.py
+
+Imports denyingmxd/CFPNet's own ``TransformerFusion`` / ``HistogramEncoder``
+from /root/reference (via tools/ref_import.py), loads the deterministic
+synthetic weights of ``cfpnet_b200.synth``, runs them in float64 on the
+synthetic inputs and stores
+
+  * the module outputs (float64 run, stored as float32; small cases in full,
+    large ones as a fixed random sample + channel-sum map + per-channel sums),
+  * the integer geometry and the three boolean masks the reference materialises
+    inside ``forward`` (captured from its frame locals), bit-packed,
+  * the positional-encoding crop offsets it drew.
+
+The fixtures pin ``oracle/cfp_oracle.py`` (tests/test_oracle_golden.py) and are
+compared with the CUDA path directly (tests/test_gpu_parity.py).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+from ref_import import import_reference  # noqa: E402
+from cfpnet_b200 import synth  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+SAMPLE_N = 32768
+FULL_LIMIT = 300_000        # elements; larger outputs are stored sampled
+
+ref = import_reference()
+args = ref["args"]
+TransformerFusion = ref["fusion"].TransformerFusion
+HistogramEncoder = ref["encoder"].HistogramEncoder
+
+GEO_KEYS = ["pad_height", "pad_width", "p1", "p2", "sy_wo_pad", "sx_wo_pad", "ey_wo_pad",
+            "ex_wo_pad", "sy", "ey", "sx", "ex", "tzh", "tzw", "interpolate", "zone_num",
+            "offset_y", "offset_x"]
+
+
+def run_captured(module, *a, **kw):
+    """Run module.forward and grab its frame locals at return."""
+    code = type(module).forward.__code__
+    grabbed = {}
+
+    def prof(frame, event, arg):
+        if event == "return" and frame.f_code is code:
+            loc = frame.f_locals
+            for k in GEO_KEYS:
+                grabbed[k] = int(loc[k])
+            for k in ("zone_mask", "hist_mask", "pad_mask"):
+                grabbed[k] = loc[k].detach().cpu().clone()
+
+    sys.setprofile(prof)
+    try:
+        out = module(*a, **kw)
+    finally:
+        sys.setprofile(None)
+    return out, grabbed
+
+
+def channel_const(m, D):
+    """Masks are repeated along the channel dim; store one channel."""
+    m = m.reshape(-1, D)
+    assert bool((m == m[:, :1]).all())
+    return m[:, 0].numpy()
+
+
+def pack_output(t: torch.Tensor, name: str, seed: int = 1234):
+    """t: [B,C,H,W] float64."""
+    rec = {}
+    t32 = t.to(torch.float32).numpy()
+    if t.numel() <= FULL_LIMIT:
+        rec["out_full"] = t32
+    else:
+        g = torch.Generator().manual_seed(seed)
+        idx = torch.randperm(t.numel(), generator=g)[:SAMPLE_N].numpy().astype(np.int64)
+        rec["out_idx"] = idx
+        rec["out_sample"] = t32.reshape(-1)[idx]
+        rec["out_chansum"] = t.sum(dim=1).to(torch.float32).numpy()          # [B,H,W]
+        rec["out_perchan"] = t.sum(dim=(2, 3)).to(torch.float32).numpy()     # [B,C]
+    rec["out_shape"] = np.array(t.shape)
+    rec["out_rms"] = np.float64(t.pow(2).mean().sqrt())
+    return rec
+
+
+def hist_case():
+    enc = HistogramEncoder().double().eval()
+    shapes = {k: v.shape for k, v in enc.state_dict().items()}
+    enc.load_state_dict({k: v.double() if v.is_floating_point() else v
+                         for k, v in synth.synthetic_state_dict(shapes, seed=0).items()}, strict=True)
+    inp = synth.make_inputs("G416", 2, seed=1, levels=())
+    with torch.no_grad():
+        outs = enc(inp["hist_data"].double().unsqueeze(-1))
+    np.savez_compressed(os.path.join(OUT, "hist_encoder_B2.npz"),
+                        **{f"out{c}": o.to(torch.float32).numpy() for c, o in zip((32, 64, 128), outs)})
+    return enc, shapes
+
+
+def fusion_case(tag, geometry, level, batch, layers, change_embedding=True, no_skip_inside=False):
+    C, _, max_res, lk = synth.LEVELS[level]
+    args.attention_layer = list(layers)
+    args.change_embedding = change_embedding
+    args.no_skip_inside = no_skip_inside
+    mod = TransformerFusion(C, list(max_res), large_kernel=lk, patch_size=640 // max_res[1]).double().eval()
+    shapes = {k: v.shape for k, v in mod.state_dict().items()}
+    sd = synth.synthetic_state_dict(shapes, seed=level)
+    mod.load_state_dict({k: v.double() if v.is_floating_point() else v for k, v in sd.items()}, strict=True)
+
+    henc = HistogramEncoder().double().eval()
+    hshapes = {k: v.shape for k, v in henc.state_dict().items()}
+    henc.load_state_dict({k: v.double() if v.is_floating_point() else v
+                          for k, v in synth.synthetic_state_dict(hshapes, seed=0).items()}, strict=True)
+
+    inp = synth.make_inputs(geometry, batch, seed=1, levels=(level,))
+    # the reference's own patch_info producer, collated like its DataLoader
+    ref_pi = [ref["dataloader"].patch_info_from_rect_data(r) for r in inp["rect_data"]]
+    pi = synth.collate_patch_info(ref_pi)
+    for cps in (4, 8, 16):
+        for k in pi[cps]:
+            assert torch.equal(pi[cps][k], inp["patch_info"][cps][k]), (cps, k)
+    with torch.no_grad():
+        feats = henc(inp["hist_data"].double().unsqueeze(-1))
+        feat1 = {32: feats[0], 64: feats[1], 128: feats[2]}[C]
+        torch.manual_seed(2)
+        out, cap = run_captured(mod, inp[f"x{level}"].double(), feat1, rect_data=inp["rect_data"],
+                                mask=inp["mask"], patch_info=pi, rgb=None)
+    rec = pack_output(out, tag)
+    rec["geo_keys"] = np.array(GEO_KEYS)
+    rec["geo_vals"] = np.array([cap[k] for k in GEO_KEYS], dtype=np.int64)
+    B, H, W = out.shape[0], out.shape[2], out.shape[3]
+    zm = channel_const(cap["zone_mask"], C).reshape(B, H * W)
+    hm = channel_const(cap["hist_mask"], C).reshape(B * 64, cap["p1"] * cap["p2"])
+    pm = channel_const(cap["pad_mask"], C).reshape(B, cap["tzh"], cap["tzw"])
+    rec["zone_mask_bits"], rec["zone_mask_shape"] = np.packbits(zm), np.array(zm.shape)
+    rec["hist_mask_bits"], rec["hist_mask_shape"] = np.packbits(hm), np.array(hm.shape)
+    rec["pad_mask_bits"], rec["pad_mask_shape"] = np.packbits(pm), np.array(pm.shape)
+    rec["meta"] = np.array([geometry, str(level), str(batch), ",".join(layers),
+                            str(int(change_embedding)), str(int(no_skip_inside))])
+    np.savez_compressed(os.path.join(OUT, f"fusion_{tag}.npz"), **rec)
+    print(f"{tag:28s} out {tuple(out.shape)} rms {float(rec['out_rms']):.3f} "
+          f"interp {cap['interpolate']} pad ({cap['pad_height']},{cap['pad_width']}) "
+          f"off ({cap['offset_y']},{cap['offset_x']})")
+
+
+def dump_keys():
+    """state_dict key -> shape of the reference modules (drop-in contract)."""
+    import json
+    rec = {}
+    enc = HistogramEncoder()
+    rec["hist_encoder"] = {k: list(v.shape) for k, v in enc.state_dict().items()}
+    for tag, layers in (("combine1", synth.COMBINE1_LAYERS), ("baseline", synth.BASELINE_LAYERS)):
+        args.attention_layer = list(layers)
+        for level, (C, _, max_res, lk) in synth.LEVELS.items():
+            mod = TransformerFusion(C, list(max_res), large_kernel=lk, patch_size=640 // max_res[1])
+            rec[f"fusion_{tag}_L{level}"] = {k: list(v.shape) for k, v in mod.state_dict().items()}
+    with open(os.path.join(OUT, "state_dict_keys.json"), "w") as fh:
+        json.dump(rec, fh, indent=0, sort_keys=True)
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    dump_keys()
+    hist_case()
+    C1, BL = synth.COMBINE1_LAYERS, synth.BASELINE_LAYERS
+    fusion_case("G416_L3_B2", "G416", 3, 2, C1)
+    fusion_case("G416_L2_B1", "G416", 2, 1, C1)
+    fusion_case("G416_L1_B1", "G416", 1, 1, C1)
+    fusion_case("G480_L3_B1", "G480", 3, 1, C1)          # bilinear-resize branch
+    fusion_case("G480pad_L3_B1", "G480pad", 3, 1, C1)    # pad_mask branch
+    fusion_case("G480pad_L2_B1", "G480pad", 2, 1, C1)
+    fusion_case("G416_L3_B1_baseline", "G416", 3, 1, BL)
+    fusion_case("G416_L3_B1_noskip", "G416", 3, 1, C1, no_skip_inside=True)
+    fusion_case("G416_L3_B1_keepemb", "G416", 3, 1, C1, change_embedding=False)
