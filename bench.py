@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""Benchmark of the CFP fusion + cross-zone propagation path (BASELINE.json metric:
+"CFP fusion frames/s @416x544, 8x8 zones").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl cfp|reference]
+
+One *step* = one pass of the hot path (histogram encoder + the three TransformerFusion
+calls) over one batch of synthetic frames.  Workload = BASELINE.json configs[2]:
+combine1 layer list, bf16, 64 frames per GPU, 416x544 input with 8x8 zones of 48 px.
+Launched under torchrun for N>1: one process per GPU, frames sharded by batch, no
+data-path collective (weak scaling); the time is the max over ranks.
+
+``--impl reference`` times the reference's CPU algorithm (the oracle port of the PyTorch
+modules, oracle/cfp_oracle.py) on the host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from cfpnet_b200 import synth  # noqa: E402
+
+METRIC = "CFP fusion frames/s @416x544, 8x8 zones"
+GEOMETRY = "G416"
+# SURVEY.md §8d / BASELINE.md §3 (combine1, 416x544): algorithmic work per frame
+FLOP_PER_FRAME = 13.22e9
+DENSE_FLOP_PER_FRAME = 11.26e9
+ELEMS_PER_FRAME = 15.43e6
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            p = json.load(fh)
+        return {"hbm_gbs": float(p["hbm_gbs"]), "bf16_tflops": float(p["bf16_tflops"]),
+                "bf16_tflops_sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0,
+                "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag, self.proc = index, [], False, None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.samples.append([v.strip() for v in line.split(",")])
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = [float(s[0]) for s in self.samples if len(s) >= 6 and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) >= 6 and s[1].replace(".", "").isdigit()]
+        reasons = set()
+        for s in self.samples:
+            if len(s) >= 6:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------- reference arm
+def oracle_modules():
+    from oracle import cfp_oracle as O
+    from cfpnet_b200 import FusionPath
+    path = FusionPath(synth.COMBINE1_LAYERS)
+    sds = {"hist_encoder": synth.synthetic_state_dict({k: v.shape for k, v in path.hist_encoder.state_dict().items()}, 0)}
+    for lv, name in ((3, "cross_atten3"), (2, "cross_atten2"), (1, "cross_atten1")):
+        sds[name] = synth.synthetic_state_dict({k: v.shape for k, v in getattr(path, name).state_dict().items()}, lv)
+    return O, sds
+
+
+def time_cpu_frames(n_frames, steps, warmup, seed=1):
+    """Time the oracle port (fp32, all host threads) on `n_frames`-frame batches."""
+    O, sds = oracle_modules()
+    torch.set_num_threads(os.cpu_count() or 1)
+    inp = synth.make_inputs(GEOMETRY, n_frames, seed=seed)
+    xs = [inp["x3"], inp["x2"], inp["x1"]]
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            torch.manual_seed(2)
+            t0 = time.perf_counter()
+            O.fusion_path(sds, synth.COMBINE1_LAYERS, xs, inp["hist_data"], inp["mask"], inp["patch_info"])
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    return times
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    probe = time_cpu_frames(1, 1, 1)[0]
+    budget_s = 90.0
+    n = max(1, min(64, int(budget_s / ((a.steps + a.warmup) * max(probe, 1e-3)))))
+    times = time_cpu_frames(n, a.steps, a.warmup)
+    total = sum(times)
+    fps = n * a.steps / total
+    sample = f"{n} frames/step x {a.steps} steps (+{a.warmup} warm-up), fp32, torch CPU ops, {cores} threads"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * total / a.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(a, per_gpu_batch=n),
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(a, per_gpu_batch):
+    return {"workload": "CFPNet combine1 fusion path (hist encoder + cross_atten3/2/1), 416x544, 8x8 zones of 48 px, "
+                        f"{per_gpu_batch} frames per GPU, batch-sharded (BASELINE.json configs[2])",
+            "layers": list(synth.COMBINE1_LAYERS), "per_gpu_batch": per_gpu_batch, "global_batch": per_gpu_batch * a.gpus,
+            "l2_policy": "inputs rotate over 3 distinct batches + workspace > 126 MB L2 between reuse"}
+
+
+# ---------------------------------------------------------------------------------- product arm
+def run_cfp(a):
+    import torch.distributed as dist
+    from cfpnet_b200 import FusionPath, _lib
+    from cfpnet_b200.build import build
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl cfp needs a CUDA device: the fusion path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    build()
+    dtype = {"bf16": torch.bfloat16, "f32": torch.float32}[a.dtype]
+    B = a.batch
+
+    path = FusionPath(synth.COMBINE1_LAYERS)
+    path.hist_encoder.load_state_dict(synth.synthetic_state_dict(
+        {k: v.shape for k, v in path.hist_encoder.state_dict().items()}, 0))
+    for lv, name in ((3, "cross_atten3"), (2, "cross_atten2"), (1, "cross_atten1")):
+        m = getattr(path, name)
+        m.load_state_dict(synth.synthetic_state_dict({k: v.shape for k, v in m.state_dict().items()}, lv))
+    path = path.to(dev).eval().set_dtype(dtype)
+
+    # three distinct input batches per rank (rotated so consecutive steps never reuse L2 contents)
+    NSETS = 3
+    host_sets, dev_sets = [], []
+    for s in range(NSETS):
+        inp = synth.make_inputs(GEOMETRY, B, seed=100 + rank * NSETS + s)
+        h = {"x3": inp["x3"].to(dtype).pin_memory(), "x2": inp["x2"].to(dtype).pin_memory(),
+             "x1": inp["x1"].to(dtype).pin_memory(), "hist_data": inp["hist_data"].pin_memory(),
+             "mask": inp["mask"].pin_memory()}
+        host_sets.append(h)
+        dev_sets.append({k: v.to(dev) for k, v in h.items()})
+        patch_info = inp["patch_info"]
+    h2d = sum(v.numel() * v.element_size() for v in host_sets[0].values())
+
+    def step(i):
+        d = dev_sets[i % NSETS]
+        torch.manual_seed(2 + i)            # same positional-encoding crop on every rank
+        return path(d["x3"], d["x2"], d["x1"], d["hist_data"], d["mask"], patch_info)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    with torch.no_grad():
+        for i in range(a.warmup):
+            outs = step(i)
+        d2h = sum(o.numel() * o.element_size() for o in outs)
+        # ---- device-resident throughput ("value")
+        barrier()
+        sampler = ClockSampler(local) if rank == 0 else None
+        if sampler:
+            sampler.start()
+        n0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(a.steps):
+            step(i)
+        e1.record()
+        barrier()
+        launches = _lib.launch_count() - n0
+        ms_total = max_over_ranks(e0.elapsed_time(e1))
+        clocks = sampler.finish() if sampler else None
+
+        # ---- end-to-end through the public host-buffer API ("e2e")
+        for i in range(min(a.warmup, 3)):
+            path.forward_host(host_sets[i % NSETS], patch_info, dev)
+        barrier()
+        e0.record()
+        for i in range(a.steps):
+            torch.manual_seed(2 + i)
+            path.forward_host(host_sets[i % NSETS], patch_info, dev)
+        e1.record()
+        barrier()
+        ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+
+        # ---- per-kernel breakdown with CUDA events on the launch stream (roofline)
+        prof = None
+        if rank == 0:
+            barrier_local = torch.cuda.synchronize
+            barrier_local()
+            _lib.profile_start()
+            for i in range(a.steps):
+                step(i)
+            prof = _lib.profile_stop()
+    if world > 1:
+        dist.barrier()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = load_peaks()
+    frames = B * world * a.steps
+    value = frames / (ms_total * 1e-3)
+    es = 2 if dtype == torch.bfloat16 else 4
+    line = {
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": a.dtype, "data": "synthetic", "config": workload_config(a, B),
+        "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    # whole-path roofline view (algorithmic bytes / dense flops per frame x measured frames/s)
+    per_gpu_fps = value / world
+    line["path"] = {"algorithmic_GBps": ELEMS_PER_FRAME * es * per_gpu_fps / 1e9,
+                    "dense_TFLOPs": DENSE_FLOP_PER_FRAME * per_gpu_fps / 1e12,
+                    "hbm_peak_GBps": peaks["hbm_gbs"], "bf16_peak_TFLOPs": peaks["bf16_tflops_sustained"]}
+    if prof:
+        line["roofline"], line["kernels"] = roofline_from_profile(prof, a.steps, B, es, peaks)
+    if not a.no_cpu:
+        cores = os.cpu_count() or 1
+        t = time_cpu_frames(1, 10, 3)
+        med = statistics.median(t)
+        line["cpu_baseline"] = {"value": 1.0 / med, "unit": "frames/s", "cores": cores, "kind": "port",
+                                "sample": "1 frame/step, 3 warm-up + 10 timed, median, fp32 torch CPU ops on all host threads"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# Per-frame algorithmic work of each kernel at G416 (derived in DESIGN.md §kernels):
+#   name -> (bound, units per frame) ; units = bytes/elem-size for "hbm" kernels, flops for "tensor"/"fma"
+def kernel_work(B, es):
+    N = {3: 884, 2: 3536, 1: 14144}
+    C = {3: 128, 2: 64, 1: 32}
+    K = {3: 7, 2: 15, 1: 31}
+    work = {}
+    # depthwise: FMA-pipe flops (2*N*C*k^2) and compulsory bytes (read + write the map once)
+    for lv in (3, 2, 1):
+        work[f"dwconv<{K[lv]}>"] = {"flops": 2.0 * N[lv] * C[lv] * K[lv] ** 2 * B, "bytes": 2.0 * N[lv] * C[lv] * es * B}
+    return work
+
+
+def roofline_from_profile(prof, steps, B, es, peaks):
+    total_ms = sum(v[1] for v in prof.values())
+    kernels = {k: {"launches_per_step": v[0] / steps, "ms_per_step": v[1] / steps,
+                   "share": v[1] / total_ms if total_ms else None} for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
+    top = max(prof.items(), key=lambda kv: kv[1][1])
+    name, (count, ms) = top
+    avg_s = ms / count * 1e-3
+    work = kernel_work(B, es)
+    if name in work:
+        # the large-kernel depthwise conv is FMA-pipe bound as a direct stencil; north_star asks
+        # for its HBM evidence, so report achieved compulsory GB/s against the measured copy bandwidth and give
+        # the FMA-pipe fraction beside it.
+        w = work[name]
+        ach = w["bytes"] / avg_s / 1e9
+        fma_peak = 148 * 128 * 2 * 1.965e9 / 1e12
+        roof = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+                "avg_launch_ms": avg_s * 1e3,
+                "fma_pipe": {"achieved_TFLOPs": w["flops"] / avg_s / 1e12, "peak_TFLOPs": fma_peak,
+                             "frac": w["flops"] / avg_s / 1e12 / fma_peak}}
+    else:
+        roof = {"kernel": name, "bound": "tensor", "achieved": None, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": None, "traffic": None, "peak_source": peaks["source"], "avg_launch_ms": avg_s * 1e3}
+    return roof, kernels
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cfp", choices=["cfp", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="frames per GPU per step")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl == "cfp" else a.warmup
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_cfp(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -7,7 +7,8 @@ Host-side mirror of the reference's ``src/models`` interface for this path
 from .config import args
 from .encoder import HistogramEncoder
 from .fusion import TransformerFusion
+from .pipeline import FusionPath
 from .geometry import ZoneGeometry, collate_patch_info, patch_info_from_rect_data, zone_geometry
 
-__all__ = ["args", "HistogramEncoder", "TransformerFusion", "ZoneGeometry", "collate_patch_info",
+__all__ = ["args", "HistogramEncoder", "TransformerFusion", "FusionPath", "ZoneGeometry", "collate_patch_info",
            "patch_info_from_rect_data", "zone_geometry"]

@@ -70,6 +70,9 @@ SIGNATURES = {
     "cfp_dapm_fwd": (_i, [_p, _i, _i, _i, _i, C.POINTER(CfpGeom), C.POINTER(CfpDapmW), _p, _sz, _i, _p]),
     "cfp_lkpm_fwd": (_i, [_p, _i, _i, _i, _i, C.POINTER(CfpLkpmW), _p, _sz, _i, _p]),
     "cfp_twins_fwd": (_i, [_p, _i, _i, _i, _i, C.POINTER(CfpTwinsW), _p, _sz, _i, _p]),
+    "cfp_launch_count": (_i64, []),
+    "cfp_profile_start": (_i, []),
+    "cfp_profile_stop": (_i, [C.c_char_p, _sz]),
 }
 
 _lib = None
@@ -126,3 +129,19 @@ def ptr(t) -> int:
 
 def stream_ptr() -> int:
     return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count() -> int:
+    return int(load().cfp_launch_count())
+
+
+def profile_start() -> None:
+    call("cfp_profile_start")
+
+
+def profile_stop() -> dict:
+    """{kernel name: (launches, total ms)} of the calls made by this thread since profile_start()."""
+    import json
+    buf = C.create_string_buffer(1 << 16)
+    call("cfp_profile_stop", buf, len(buf))
+    return {k: (int(v[0]), float(v[1])) for k, v in json.loads(buf.value.decode()).items()}

@@ -4,6 +4,8 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <string>
+#include <vector>
 #include "cfp_common.cuh"
 #include "cfp_internal.h"
 
@@ -20,9 +22,39 @@ int fail(const char* fmt, ...) {
     va_end(ap);
     return 1;
 }
+// Per-thread launch accounting and the optional event profiler (cfp_profile_*): when on, one
+// CUDA event is recorded on the call's stream after every kernel launch, so a kernel's time is
+// the gap to the previous event on that (in-order) stream.
+struct ThreadState {
+    cudaStream_t stream = nullptr;
+    int64_t launches = 0;
+    bool profiling = false;
+    cudaEvent_t first = nullptr;
+    std::vector<std::pair<const char*, cudaEvent_t>> events;
+};
+static ThreadState& tstate() {
+    static thread_local ThreadState t;
+    return t;
+}
+static void begin_call(void* stream) {
+    ThreadState& t = tstate();
+    t.stream = (cudaStream_t)stream;
+    if (t.profiling && !t.first) {
+        cudaEventCreate(&t.first);
+        cudaEventRecord(t.first, t.stream);
+    }
+}
 int check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail("%s launch failed: %s", what, cudaGetErrorString(e));
+    ThreadState& t = tstate();
+    ++t.launches;
+    if (t.profiling) {
+        cudaEvent_t ev;
+        cudaEventCreate(&ev);
+        cudaEventRecord(ev, t.stream);
+        t.events.emplace_back(what, ev);
+    }
     return 0;
 }
 
@@ -84,6 +116,7 @@ CFP_API size_t cfp_workspace_bytes(int B, int H, int W, int C, int ws, int dtype
 
 CFP_API int cfp_hist_encoder_fwd(const float* hist, void* out32, void* out64, void* out128, int64_t rows,
                          const cfp_hist_w* w, int dtype, void* stream) {
+    begin_call(stream);
     CFP_REQUIRE(hist && out32 && out64 && out128 && w, "null pointer");
     CFP_REQUIRE(dtype == CFP_F32 || dtype == CFP_BF16, "unsupported dtype %d", dtype);
     if (rows == 0) return 0;
@@ -93,6 +126,7 @@ CFP_API int cfp_hist_encoder_fwd(const float* hist, void* out32, void* out64, vo
 
 CFP_API int cfp_zone_masks(const uint8_t* mask, uint8_t* zone_mask, uint8_t* hist_mask, uint8_t* pad_mask, int B, int H,
                    int W, const cfp_geom* g, void* stream) {
+    begin_call(stream);
     CFP_REQUIRE(mask && zone_mask && hist_mask && pad_mask, "null pointer");
     if (int e = check_geom(g, H, W)) return e;
     return zone_masks(mask, zone_mask, hist_mask, pad_mask, B, H, W, *g, (cudaStream_t)stream);
@@ -100,6 +134,7 @@ CFP_API int cfp_zone_masks(const uint8_t* mask, uint8_t* zone_mask, uint8_t* his
 
 CFP_API int cfp_posenc_tokens_fwd(const void* x_nchw, const float* pos, void* tokens, int B, int C, int H, int W, int pos_w,
                           int oy, int ox, int dtype, void* stream) {
+    begin_call(stream);
     CFP_REQUIRE(x_nchw && pos && tokens, "null pointer");
     CFP_REQUIRE(B > 0 && B <= 65535 && C > 0 && H > 0 && W > 0, "bad shape");
     CFP_REQUIRE(oy >= 0 && ox >= 0 && ox + W <= pos_w, "positional-encoding crop out of range");
@@ -108,6 +143,7 @@ CFP_API int cfp_posenc_tokens_fwd(const void* x_nchw, const float* pos, void* to
 }
 
 CFP_API int cfp_tokens_to_nchw(const void* tokens, void* out_nchw, int B, int C, int H, int W, int dtype, void* stream) {
+    begin_call(stream);
     CFP_REQUIRE(tokens && out_nchw, "null pointer");
     CFP_REQUIRE(B > 0 && B <= 65535 && C > 0 && H > 0 && W > 0, "bad shape");
     CFP_REQUIRE(dtype == CFP_F32 || dtype == CFP_BF16, "unsupported dtype %d", dtype);
@@ -117,6 +153,7 @@ CFP_API int cfp_tokens_to_nchw(const void* tokens, void* out_nchw, int B, int C,
 CFP_API int cfp_d2i_fwd(void* feat0, const void* emb, const void* zone_tok, const float* pos2, const uint8_t* mask, int B,
                 int H, int W, int C, int S, const cfp_geom* g, const cfp_loftr_w* w, int assign, void* workspace,
                 size_t workspace_bytes, int dtype, void* stream) {
+    begin_call(stream);
     if (int e = check_common(feat0, B, H, W, C, dtype)) return e;
     if (int e = check_geom(g, H, W)) return e;
     CFP_REQUIRE(emb && zone_tok && pos2 && mask && w && workspace, "null pointer");
@@ -134,6 +171,7 @@ CFP_API int cfp_d2i_fwd(void* feat0, const void* emb, const void* zone_tok, cons
 
 CFP_API int cfp_dapm_fwd(void* feat0, int B, int H, int W, int C, const cfp_geom* g, const cfp_dapm_w* w, void* workspace,
                  size_t workspace_bytes, int dtype, void* stream) {
+    begin_call(stream);
     if (int e = check_common(feat0, B, H, W, C, dtype)) return e;
     if (int e = check_geom(g, H, W)) return e;
     CFP_REQUIRE(w && workspace, "null pointer");
@@ -153,6 +191,7 @@ CFP_API int cfp_dapm_fwd(void* feat0, int B, int H, int W, int C, const cfp_geom
 
 CFP_API int cfp_lkpm_fwd(void* feat0, int B, int H, int W, int C, const cfp_lkpm_w* w, void* workspace, size_t workspace_bytes,
                  int dtype, void* stream) {
+    begin_call(stream);
     if (int e = check_common(feat0, B, H, W, C, dtype)) return e;
     CFP_REQUIRE(w && workspace, "null pointer");
     WsLayout L = ws_layout(B, H, W, C, 0, dtype, nullptr);
@@ -166,6 +205,7 @@ CFP_API int cfp_lkpm_fwd(void* feat0, int B, int H, int W, int C, const cfp_lkpm
 
 CFP_API int cfp_twins_fwd(void* feat0, int B, int H, int W, int C, const cfp_twins_w* w, void* workspace,
                   size_t workspace_bytes, int dtype, void* stream) {
+    begin_call(stream);
     if (int e = check_common(feat0, B, H, W, C, dtype)) return e;
     CFP_REQUIRE(w && workspace, "null pointer");
     CFP_REQUIRE(w->ws > 1, "window size must be > 1 (transformer.py:79)");
@@ -173,6 +213,51 @@ CFP_API int cfp_twins_fwd(void* feat0, int B, int H, int W, int C, const cfp_twi
     WsLayout L = ws_layout(B, H, W, C, w->ws, dtype, nullptr);
     CFP_REQUIRE(workspace_bytes >= L.total, "workspace too small: %zu < %zu", workspace_bytes, L.total);
     return twins(feat0, B, H, W, C, *w, (char*)workspace, L, dtype, (cudaStream_t)stream);
+}
+
+CFP_API int64_t cfp_launch_count(void) { return tstate().launches; }
+
+CFP_API int cfp_profile_start(void) {
+    ThreadState& t = tstate();
+    for (auto& e : t.events) cudaEventDestroy(e.second);
+    t.events.clear();
+    if (t.first) cudaEventDestroy(t.first);
+    t.first = nullptr;
+    t.profiling = true;
+    return 0;
+}
+
+CFP_API int cfp_profile_stop(char* out, size_t cap) {
+    ThreadState& t = tstate();
+    t.profiling = false;
+    CFP_REQUIRE(out && cap > 2, "null output buffer");
+    struct Acc { const char* name; int count; double ms; };
+    std::vector<Acc> acc;
+    cudaEvent_t prev = t.first;
+    for (auto& e : t.events) {
+        cudaEventSynchronize(e.second);
+        float ms = 0.f;
+        if (prev) cudaEventElapsedTime(&ms, prev, e.second);
+        prev = e.second;
+        bool found = false;
+        for (auto& a : acc)
+            if (std::strcmp(a.name, e.first) == 0) { a.count++; a.ms += ms; found = true; break; }
+        if (!found) acc.push_back({e.first, 1, (double)ms});
+    }
+    std::string js = "{";
+    for (size_t i = 0; i < acc.size(); ++i) {
+        char buf[256];
+        snprintf(buf, sizeof(buf), "%s\"%s\": [%d, %.6f]", i ? ", " : "", acc[i].name, acc[i].count, acc[i].ms);
+        js += buf;
+    }
+    js += "}";
+    for (auto& e : t.events) cudaEventDestroy(e.second);
+    t.events.clear();
+    if (t.first) cudaEventDestroy(t.first);
+    t.first = nullptr;
+    CFP_REQUIRE(js.size() + 1 <= cap, "profile buffer too small (%zu needed)", js.size() + 1);
+    std::memcpy(out, js.c_str(), js.size() + 1);
+    return 0;
 }
 
 }  // extern "C"

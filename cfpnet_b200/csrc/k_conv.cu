@@ -83,7 +83,7 @@ static int conv3x3_impl(const void* in0, const void* in1, const float* w_t, cons
         k<<<grid, kThreads, smem, st>>>((const T*)in0, nullptr, w_t, shift, (const T*)residual, (T*)out, H, W, 0, 0,
                                         0, 0);
     }
-    return check_launch("conv3x3_kernel");
+    return check_launch(in1 ? "conv3x3<2C->C>" : "conv3x3<C->C>");
 }
 
 // ------------------------------------------------------------------ GSA sr conv + LN

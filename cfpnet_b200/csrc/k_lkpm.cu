@@ -96,7 +96,7 @@ static int dw_launch(const void* in, void* out, int B, int H, int W, int C, cons
     if (int e = set_smem(k, smem)) return e;
     dim3 grid((W + kDwTile - 1) / kDwTile, (H + kDwTile - 1) / kDwTile, B * (C / kDwCh));
     k<<<grid, kThreads, smem, st>>>((const T*)in, (T*)out, H, W, C, dw_t, dw_shift);
-    return check_launch("dwconv_bn_relu_kernel");
+    return check_launch(K == 31 ? "dwconv<31>" : K == 15 ? "dwconv<15>" : "dwconv<7>");
 }
 
 int dwconv_bn_relu(const void* in, void* out, int B, int H, int W, int C, int ksize, const float* dw_t,

@@ -334,7 +334,8 @@ template <int C> constexpr size_t query_smem() {
 }
 
 template <int C, int NH, class Src>
-static int run_kv_state(const Src& src, int groups, const float* wkv_t, float* kv, float* ksum, cudaStream_t st) {
+static int run_kv_state(const char* name, const Src& src, int groups, const float* wkv_t, float* kv, float* ksum,
+                        cudaStream_t st) {
     constexpr int DH = C / NH;
     cudaError_t e = cudaMemsetAsync(kv, 0, (size_t)groups * (C * DH + C) * sizeof(float), st);
     if (e != cudaSuccess) return fail("cudaMemsetAsync(kv state): %s", cudaGetErrorString(e));
@@ -342,15 +343,16 @@ static int run_kv_state(const Src& src, int groups, const float* wkv_t, float* k
     if (int err = set_smem(k, kv_smem<C>())) return err;
     const unsigned grid = (unsigned)((src.rows + Tile<C>::BM - 1) / Tile<C>::BM);
     k<<<grid, kThreads, kv_smem<C>(), st>>>(src, wkv_t, kv, ksum);
-    return check_launch("kv_state_kernel");
+    return check_launch(name);
 }
 template <int C, int NH, bool kAttnOnly, class Q>
-static int run_query(const Q& q, const cfp_loftr_w& w, const float* kv, const float* ksum, cudaStream_t st) {
+static int run_query(const char* name, const Q& q, const cfp_loftr_w& w, const float* kv, const float* ksum,
+                     cudaStream_t st) {
     auto k = loftr_query_kernel<C, NH, kAttnOnly, Q>;
     if (int err = set_smem(k, query_smem<C>())) return err;
     const unsigned grid = (unsigned)((q.rows + Tile<C>::BM - 1) / Tile<C>::BM);
     k<<<grid, kThreads, query_smem<C>(), st>>>(q, w, kv, ksum);
-    return check_launch("loftr_query_kernel");
+    return check_launch(name);
 }
 
 // KV state for `groups` groups with head dim DH lives at ws+L.kv: [groups][C*DH] then [groups][C].
@@ -368,10 +370,10 @@ static int d2i_impl(void* feat0, const void* emb, const void* zone_tok, const fl
     float *kv, *ksum;
     kv_ptrs<C, 4>(ws, L, groups, kv, ksum);
     ZoneTokSrc<T> src{(const T*)zone_tok, pos2, S, C, (int64_t)groups * S};
-    if (int e = run_kv_state<C, 4>(src, groups, w.wkv_t, kv, ksum, st)) return e;
+    if (int e = run_kv_state<C, 4>("kv_state<hist2image>", src, groups, w.wkv_t, kv, ksum, st)) return e;
     ZonePatchRows<T> q{(T*)feat0, (const T*)emb, (T*)(ws + L.canvas), mask, H, W, C, g.zone_num, g.p1, g.p2,
                        g.sy_wo, g.sx_wo, g.tzh, g.tzw, g.interpolate, assign, (int64_t)groups * g.p1 * g.p2};
-    if (int e = run_query<C, 4, false>(q, w, kv, ksum, st)) return e;
+    if (int e = run_query<C, 4, false>("loftr_query<hist2image>", q, w, kv, ksum, st)) return e;
     if (g.interpolate) {
         const int64_t total = (int64_t)B * (g.ry1 - g.ry0) * (g.rx1 - g.rx0) * (C / 4);
         const int64_t want = (total + 255) / 256;
@@ -390,13 +392,13 @@ static int dapm_impl(const void* feat0, void* msg_map, int B, int H, int W, cons
     kv_ptrs<C, 4>(ws, L, B, kv, ksum);
     if (Ni > 0) {
         InsideSrc<T> src{(const T*)feat0, H, W, C, g.ry0, g.rx0, rw, Ni, (int64_t)B * Ni};
-        if (int e = run_kv_state<C, 4>(src, B, w.wkv_t, kv, ksum, st)) return e;
+        if (int e = run_kv_state<C, 4>("kv_state<dapm>", src, B, w.wkv_t, kv, ksum, st)) return e;
     } else {
         cudaMemsetAsync(kv, 0, (size_t)B * (C * (C / 4) + C) * sizeof(float), st);
     }
     if (No == 0) return 0;
     OutsideRows<T> q{(const T*)feat0, (T*)msg_map, H, W, C, g.ry0, g.ry1, g.rx0, g.rx1, No, (int64_t)B * No};
-    return run_query<C, 4, true>(q, w, kv, ksum, st);
+    return run_query<C, 4, true>("attn_query<dapm>", q, w, kv, ksum, st);
 }
 
 template <int C, typename T>
@@ -408,8 +410,8 @@ static int twins_impl(void* feat0, int B, int H, int W, const cfp_twins_w& w, ch
     float *kv, *ksum;
     kv_ptrs<C, 8>(ws, L, groups, kv, ksum);
     WindowRows<T> win{(T*)feat0, H, W, C, wsz, nwx, nwin, (int64_t)groups * wsz * wsz};
-    if (int e = run_kv_state<C, 8>(win, groups, w.lsa.wkv_t, kv, ksum, st)) return e;
-    if (int e = run_query<C, 8, false>(win, w.lsa, kv, ksum, st)) return e;
+    if (int e = run_kv_state<C, 8>("kv_state<lsa>", win, groups, w.lsa.wkv_t, kv, ksum, st)) return e;
+    if (int e = run_query<C, 8, false>("loftr_query<lsa>", win, w.lsa, kv, ksum, st)) return e;
     // GSA (transformer.py:138-150): keys/values = LN(sr(x)), stride-ws conv without padding
     const int Ns = (H / wsz) * (W / wsz);
     float* sr_tok = reinterpret_cast<float*>(ws + L.sr);
@@ -417,9 +419,9 @@ static int twins_impl(void* feat0, int B, int H, int W, const cfp_twins_w& w, ch
                            sizeof(T) == 4 ? CFP_F32 : CFP_BF16, st)) return e;
     kv_ptrs<C, 8>(ws, L, B, kv, ksum);
     SrTokSrc src{sr_tok, Ns, C, (int64_t)B * Ns};
-    if (int e = run_kv_state<C, 8>(src, B, w.gsa.wkv_t, kv, ksum, st)) return e;
+    if (int e = run_kv_state<C, 8>("kv_state<gsa>", src, B, w.gsa.wkv_t, kv, ksum, st)) return e;
     FrameRows<T> fr{(T*)feat0, H * W, C, (int64_t)B * H * W};
-    return run_query<C, 8, false>(fr, w.gsa, kv, ksum, st);
+    return run_query<C, 8, false>("loftr_query<gsa>", fr, w.gsa, kv, ksum, st);
 }
 
 #define CFP_DISPATCH_C_T(FN, ...)                                                        \

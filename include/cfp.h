@@ -144,6 +144,15 @@ CFP_API int cfp_lkpm_fwd(void *feat0, int B, int H, int W, int C, const cfp_lkpm
 CFP_API int cfp_twins_fwd(void *feat0, int B, int H, int W, int C, const cfp_twins_w *w, void *workspace,
                   size_t workspace_bytes, int dtype, void *stream);
 
+/* Accounting / tracing (no reference counterpart: the reference has no profiling hooks,
+ * SURVEY.md §5).  cfp_launch_count: kernels this thread has enqueued since load.
+ * cfp_profile_start: from now on this thread records one CUDA event per kernel launch on the
+ * call's stream.  cfp_profile_stop: waits for the recorded events (the one place the library
+ * blocks), writes {"kernel_name": [launches, total_ms], ...} as JSON into out[cap]. */
+CFP_API int64_t cfp_launch_count(void);
+CFP_API int cfp_profile_start(void);
+CFP_API int cfp_profile_stop(char *out, size_t cap);
+
 #ifdef __cplusplus
 }
 #endif
