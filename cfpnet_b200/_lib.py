@@ -71,6 +71,7 @@ SIGNATURES = {
     "cfp_lkpm_fwd": (_i, [_p, _i, _i, _i, _i, C.POINTER(CfpLkpmW), _p, _sz, _i, _p]),
     "cfp_twins_fwd": (_i, [_p, _i, _i, _i, _i, C.POINTER(CfpTwinsW), _p, _sz, _i, _p]),
     "cfp_launch_count": (_i64, []),
+    "cfp_selftest_umma": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),
     "cfp_profile_start": (_i, []),
     "cfp_profile_stop": (_i, [C.c_char_p, _sz]),
 }

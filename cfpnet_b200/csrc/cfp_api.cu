@@ -215,6 +215,13 @@ CFP_API int cfp_twins_fwd(void* feat0, int B, int H, int W, int C, const cfp_twi
     return twins(feat0, B, H, W, C, *w, (char*)workspace, L, dtype, (cudaStream_t)stream);
 }
 
+CFP_API int cfp_selftest_umma(const void* a, const void* b, float* d, int rows_a, int n, int k, int row_shift,
+                              void* stream) {
+    begin_call(stream);
+    CFP_REQUIRE(a && b && d, "null pointer");
+    return umma_selftest(a, b, d, rows_a, n, k, row_shift, (cudaStream_t)stream);
+}
+
 CFP_API int64_t cfp_launch_count(void) { return tstate().launches; }
 
 CFP_API int cfp_profile_start(void) {

@@ -55,4 +55,7 @@ int dwconv_bn_relu(const void* in, void* out, int B, int H, int W, int C, int ks
 int lkpm_mlp(void* feat0, const void* y, int64_t rows, int C, const cfp_lkpm_w& w, int dtype,
              cudaStream_t st);
 
+// k_selftest.cu
+int umma_selftest(const void* A, const void* B, float* D, int rows_a, int N, int K, int row_shift, cudaStream_t st);
+
 }  // namespace cfp

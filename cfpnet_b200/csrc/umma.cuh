@@ -1,0 +1,136 @@
+// tcgen05 / TMEM / mbarrier / bulk-copy primitives for sm_100a (inline PTX, no CUTLASS).
+//
+// Operand layout used throughout libcfp's tensor-core kernels: the *canonical K-major,
+// no-swizzle* UMMA layout with row-contiguous core matrices.  For an operand tile of R rows
+// (M rows of A or N rows of B) and K bf16 columns, element (r, k) lives at byte
+//
+//        (k / 8) * LBO  +  r * 16  +  (k % 8) * 2          with LBO >= R * 16
+//
+// i.e. one 16-byte chunk (8 bf16 along K) per (row, k-group), chunks of consecutive rows
+// adjacent, k-groups LBO bytes apart.  In descriptor terms: core matrix = 8 rows x 16 B
+// (128 contiguous bytes), SBO (8-row group stride) = 128 B, LBO (k-group stride) = LBO.
+// Two properties make this the layout of choice here:
+//   * a row-shifted view of the same buffer is just "start address + shift*16": the nine taps
+//     of a 3x3 convolution become nine MMAs over one staged raster (no im2col);
+//   * thread r of an epilogue warp owns accumulator row r (TMEM lane r) and writes its 16-byte
+//     chunks at consecutive addresses across the warp: conflict-free stores that are directly
+//     the A operand of the next GEMM of a fused chain.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cfp {
+namespace umma {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ---------------------------------------------------------------- descriptors
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start address
+// [0,14) >>4, LBO [16,30) >>4, SBO [32,46) >>4, version [46,48) = 1, layout type [61,64) = 0.
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes = 128) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46);
+}
+// Instruction descriptor, kind::f16, A/B = bf16 K-major, D = fp32 (cute::UMMA::InstrDescriptor).
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------- MMA issue / commit
+// D[tmem] (+)= A[smem] * B[smem]^T, M x N x 16, issued by ONE thread.
+__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
+// Arrive on an mbarrier when all MMAs issued so far by this thread have completed.
+__device__ __forceinline__ void commit(uint64_t* mbar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(mbar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+// Make generic-proxy shared-memory writes visible to the async proxy (tcgen05.mma operand reads).
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+// ---------------------------------------------------------------- TMEM
+// One full warp allocates `cols` (power of two >= 32) columns; the base address lands in *slot.
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(slot)), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t base, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(base), "r"(cols) : "memory");
+}
+// Warp-collective: lane t of warp w (w % 4 selects TMEM lanes 32*(w%4)..+31) receives columns
+// [col, col+16) of accumulator row 32*(w%4)+t.
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ uint32_t tmem_addr(uint32_t base, int lane, int col) {
+    return base + ((uint32_t)lane << 16) + (uint32_t)col;
+}
+
+// ---------------------------------------------------------------- mbarrier
+__device__ __forceinline__ void mbar_init(uint64_t* mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(mbar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* mbar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(mbar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
+    while (!mbar_try_wait(mbar, parity)) {
+    }
+}
+
+// ---------------------------------------------------------------- bulk async copy (TMA engine, 1-D)
+// global -> shared, completion signalled on `mbar` via complete_tx; bytes % 16 == 0, 16-B aligned.
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(mbar))
+                 : "memory");
+}
+
+// ---------------------------------------------------------------- packing helpers
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+// 8 consecutive-K values of one row -> the 16-byte chunk of the canonical layout.
+__device__ __forceinline__ void store_chunk(void* tile, uint32_t lbo_bytes, int row, int kgroup, const float (&v)[8]) {
+    uint4 u;
+    u.x = pack_bf16(v[0], v[1]);
+    u.y = pack_bf16(v[2], v[3]);
+    u.z = pack_bf16(v[4], v[5]);
+    u.w = pack_bf16(v[6], v[7]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<char*>(tile) + (size_t)kgroup * lbo_bytes + (size_t)row * 16) = u;
+}
+
+}  // namespace umma
+}  // namespace cfp

@@ -150,6 +150,10 @@ CFP_API int cfp_twins_fwd(void *feat0, int B, int H, int W, int C, const cfp_twi
  * call's stream.  cfp_profile_stop: waits for the recorded events (the one place the library
  * blocks), writes {"kernel_name": [launches, total_ms], ...} as JSON into out[cap]. */
 CFP_API int64_t cfp_launch_count(void);
+/* Known-answer self-test of the tcgen05 engine (tests only): d[m][j] = sum_k a[m+row_shift][k] *
+ * b[j][k] for m < 128; a [rows_a][k] and b [n][k] are bf16 row-major, d [128][n] fp32. */
+CFP_API int cfp_selftest_umma(const void *a, const void *b, float *d, int rows_a, int n, int k, int row_shift,
+                              void *stream);
 CFP_API int cfp_profile_start(void);
 CFP_API int cfp_profile_stop(char *out, size_t cap);
 
