@@ -18,7 +18,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcfp.so")
 
 CFP_F32, CFP_BF16 = 0, 1
-ABI_VERSION = 1
+ABI_VERSION = 2
 _fp = C.POINTER(C.c_float)
 
 
@@ -38,7 +38,8 @@ class CfpLoftrW(C.Structure):
 
 
 class CfpDapmW(C.Structure):
-    _fields_ = [("attn", CfpLoftrW)] + [(n, C.c_void_p) for n in ("conv1_t", "shift1", "conv2_t", "shift2")]
+    _fields_ = [("attn", CfpLoftrW)] + [(n, C.c_void_p) for n in ("conv1_t", "shift1", "conv2_t", "shift2",
+                                                                      "conv1_pk", "conv2_pk")]
 
 
 class CfpLkpmW(C.Structure):

@@ -184,6 +184,12 @@ CFP_API int cfp_dapm_fwd(void* feat0, int B, int H, int W, int C, const cfp_geom
     void* msg_map = ws + L.tok_a;     // written only outside the zone rectangle; read as zero inside
     void* mid = ws + L.tok_b;
     if (int e = dapm_attention(feat0, msg_map, B, H, W, C, *g, w->attn, ws, L, dtype, st)) return e;
+    if (dtype == CFP_BF16) {     // tensor-core implicit GEMM (k_conv_tc.cu)
+        CFP_REQUIRE(w->conv1_pk && w->conv2_pk, "bf16 DAPM needs the packed tensor-core weights (conv*_pk)");
+        if (int e = conv3x3_tc(feat0, msg_map, w->conv1_pk, w->shift1, nullptr, mid, B, H, W, C, g->ry0, g->ry1,
+                               g->rx0, g->rx1, st)) return e;
+        return conv3x3_tc(mid, nullptr, w->conv2_pk, w->shift2, feat0, feat0, B, H, W, C, 0, 0, 0, 0, st);
+    }
     if (int e = conv3x3(feat0, msg_map, w->conv1_t, w->shift1, nullptr, mid, B, H, W, C, g->ry0, g->ry1, g->rx0,
                         g->rx1, dtype, st)) return e;
     return conv3x3(mid, nullptr, w->conv2_t, w->shift2, feat0, feat0, B, H, W, C, 0, 0, 0, 0, dtype, st);

@@ -1,0 +1,208 @@
+// DAPM 3x3 convolutions on the 5th-gen tensor cores (bf16 path).
+//
+//   out = conv3x3(cat[in0, in1]) (+BN folded) (+ residual)          transformer.py:239-247
+//
+// Implicit GEMM without im2col.  A CTA owns R consecutive image rows of one frame.  It stages
+// the zero-padded raster of those rows (+1 halo row above and below, +1 halo column left and
+// right: WP = W + 2 cells per row) ONCE in shared memory in the canonical K-major no-swizzle
+// UMMA layout [channel-group][cell][16 B].  Output positions are indexed by the same padded
+// raster, so the A operand of tap (dy,dx) for the M-tile of output cells [128 t, 128 t + 128)
+// is the same buffer viewed from cell 128 t + dy*WP + dx - 1: nine tcgen05.mma groups over nine
+// start addresses.  The two junk columns per raster row cost 2/WP of the MMA work and are
+// dropped in the epilogue.
+//
+// Per CTA:  warps 0-3  stage the raster (per source), then run the epilogue: thread = TMEM lane
+//                      = output cell; adds shift (+ residual) and writes bf16 tokens;
+//           warp 4     lane 0 streams the per-(source, tap) weight blocks [C x C] (pre-packed in
+//                      the canonical layout by the host) through a ring with the bulk-copy (TMA)
+//                      engine, mbarrier complete_tx;
+//           warp 5     lane 0 issues tcgen05.mma (M=128, N=C, K=16) into T accumulators of C
+//                      TMEM columns each and releases ring slots with tcgen05.commit.
+// The concatenated input of conv1 is processed as two K-halves (sources) through the same
+// raster buffer; the message-map source is zero inside the zone rectangle by construction
+// (transformer.py:233-234) and those cells are never read.
+#include "cfp_common.cuh"
+#include "cfp_internal.h"
+#include "umma.cuh"
+
+namespace cfp {
+
+template <int C> struct ConvTC {
+    static constexpr int T = 256 / C;                 // M-tiles per CTA: T*C = 256 TMEM columns
+    static constexpr int NSLOT = C >= 128 ? 2 : 3;    // weight ring depth
+    static constexpr int SLOT_BYTES = C * C * 2;      // one [C x C] bf16 block
+    static constexpr int KG = C / 8;                  // 16-byte channel groups per source
+};
+
+struct ConvTCBars {
+    uint64_t full[3], empty[3], a_ready, a_free, acc_ready;
+    uint32_t tmem_slot;
+};
+
+template <int C>
+__global__ void __launch_bounds__(192) conv3x3_tc_kernel(const bf16* __restrict__ in0, const bf16* __restrict__ in1,
+                                                         const bf16* __restrict__ wpk,
+                                                         const float* __restrict__ shift,
+                                                         const bf16* __restrict__ residual, bf16* __restrict__ out,
+                                                         int H, int W, int R, int cells, int zy0, int zy1, int zx0,
+                                                         int zx1) {
+    using P = ConvTC<C>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ ConvTCBars bars;
+    const int WP = W + 2;
+    const uint32_t lbo_a = (uint32_t)cells * 16;
+    uint8_t* a_buf = smem;                                  // [KG][cells][16 B]
+    uint8_t* ring = a_buf + (size_t)P::KG * lbo_a;          // [NSLOT][SLOT_BYTES]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.y, y0 = blockIdx.x * R;
+    const int nsrc = in1 ? 2 : 1;
+    const size_t frame = (size_t)b * H * W;
+
+    if (tid == 0) {
+        for (int i = 0; i < P::NSLOT; ++i) { umma::mbar_init(&bars.full[i], 1); umma::mbar_init(&bars.empty[i], 1); }
+        umma::mbar_init(&bars.a_ready, 128);
+        umma::mbar_init(&bars.a_free, 1);
+        umma::mbar_init(&bars.acc_ready, 1);
+        umma::fence_mbar_init();
+    }
+    if (warp == 4) umma::tmem_alloc(&bars.tmem_slot, 256);
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = bars.tmem_slot;
+
+    if (warp < 4) {
+        // ---------------- stage the raster, one source at a time
+        for (int s = 0; s < nsrc; ++s) {
+            if (s > 0) umma::mbar_wait(&bars.a_free, 0);    // all MMAs reading source 0 have completed
+            const bf16* src = s == 0 ? in0 : in1;
+            for (int i = tid; i < cells * P::KG; i += 128) {
+                const int ci = i / P::KG, kg = i % P::KG;
+                const int idx = ci - 1;                     // one slack cell in front (tap dx=0 of cell 0)
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                if (idx >= 0) {
+                    const int pr = idx / WP, px = idx - pr * WP;
+                    const int y = y0 - 1 + pr, x = px - 1;
+                    if (pr < R + 2 && y >= 0 && y < H && x >= 0 && x < W &&
+                        !(s == 1 && y >= zy0 && y < zy1 && x >= zx0 && x < zx1))
+                        v = *reinterpret_cast<const uint4*>(src + (frame + (size_t)y * W + x) * C + kg * 8);
+                }
+                *reinterpret_cast<uint4*>(a_buf + (size_t)kg * lbo_a + (size_t)ci * 16) = v;
+            }
+            umma::fence_async_smem();
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(umma::smem_u32(&bars.a_ready)) : "memory");
+        }
+        // ---------------- epilogue: thread = accumulator row = output cell of the padded raster
+        umma::mbar_wait(&bars.acc_ready, 0);
+        umma::fence_after_sync();
+#pragma unroll 1
+        for (int t = 0; t < P::T; ++t) {
+            const int o = t * 128 + warp * 32 + lane;
+            const int r = o / WP, px = o - r * WP;
+            const int y = y0 + r, x = px - 1;
+            const bool live = r < R && y < H && x >= 0 && x < W;
+            const size_t off = (frame + (size_t)y * W + x) * C;
+#pragma unroll 1
+            for (int c0 = 0; c0 < C; c0 += 16) {
+                float v[16];
+                umma::tmem_ld16(umma::tmem_addr(tmem, warp * 32, t * C + c0), v);   // warp-collective
+                if (live) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] += shift[c0 + j];
+                    if (residual) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            float4 a = IO<bf16>::ld4(residual + off + c0 + 8 * h), c = IO<bf16>::ld4(residual + off + c0 + 8 * h + 4);
+                            v[8 * h + 0] += a.x; v[8 * h + 1] += a.y; v[8 * h + 2] += a.z; v[8 * h + 3] += a.w;
+                            v[8 * h + 4] += c.x; v[8 * h + 5] += c.y; v[8 * h + 6] += c.z; v[8 * h + 7] += c.w;
+                        }
+                    }
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        uint4 u;
+                        u.x = umma::pack_bf16(v[8 * h + 0], v[8 * h + 1]);
+                        u.y = umma::pack_bf16(v[8 * h + 2], v[8 * h + 3]);
+                        u.z = umma::pack_bf16(v[8 * h + 4], v[8 * h + 5]);
+                        u.w = umma::pack_bf16(v[8 * h + 6], v[8 * h + 7]);
+                        *reinterpret_cast<uint4*>(out + off + c0 + 8 * h) = u;
+                    }
+                }
+            }
+        }
+        umma::fence_before_sync();
+    } else if (warp == 4) {
+        // ---------------- weight producer (bulk async copies, L2 -> shared)
+        if (lane == 0) {
+            const int nchunk = nsrc * 9;
+            for (int c = 0; c < nchunk; ++c) {
+                const int slot = c % P::NSLOT, round = c / P::NSLOT;
+                if (round > 0) umma::mbar_wait(&bars.empty[slot], (round - 1) & 1);
+                umma::mbar_expect_tx(&bars.full[slot], P::SLOT_BYTES);
+                umma::bulk_g2s(ring + (size_t)slot * P::SLOT_BYTES, wpk + (size_t)c * C * C, P::SLOT_BYTES, &bars.full[slot]);
+            }
+        }
+    } else {
+        // ---------------- MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = umma::idesc_bf16(128, C);
+            const uint32_t a0 = umma::smem_u32(a_buf), w0 = umma::smem_u32(ring);
+            constexpr uint32_t lbo_b = C * 16;
+            int c = 0;
+            for (int s = 0; s < nsrc; ++s) {
+                umma::mbar_wait(&bars.a_ready, s & 1);
+                umma::fence_after_sync();
+                for (int tap = 0; tap < 9; ++tap, ++c) {
+                    const int slot = c % P::NSLOT, round = c / P::NSLOT;
+                    umma::mbar_wait(&bars.full[slot], round & 1);
+                    umma::fence_after_sync();
+                    const uint32_t tap_cell = (tap / 3) * WP + (tap % 3);      // (+1 slack, -1 for dx) cancel
+                    const uint32_t wb = w0 + slot * P::SLOT_BYTES;
+                    for (int t = 0; t < P::T; ++t) {
+                        const uint32_t ab = a0 + (t * 128 + tap_cell) * 16;
+#pragma unroll
+                        for (int ks = 0; ks < C / 16; ++ks)
+                            umma::mma_bf16(tmem + t * C, umma::smem_desc(ab + ks * 2 * lbo_a, lbo_a),
+                                           umma::smem_desc(wb + ks * 2 * lbo_b, lbo_b), idesc, (c | ks) != 0);
+                    }
+                    umma::commit(&bars.empty[slot]);
+                }
+                umma::commit(s + 1 < nsrc ? &bars.a_free : &bars.acc_ready);
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 4) {
+        umma::fence_after_sync();
+        umma::tmem_dealloc(tmem, 256);
+    }
+}
+
+template <int C>
+static int conv_tc_launch(const void* in0, const void* in1, const void* wpk, const float* shift, const void* residual,
+                          void* out, int B, int H, int W, int zy0, int zy1, int zx0, int zx1, cudaStream_t st) {
+    using P = ConvTC<C>;
+    const int WP = W + 2;
+    const int R = (P::T * 128) / WP;
+    CFP_REQUIRE(R >= 1, "conv3x3 (tensor-core path): map width %d exceeds %d", W, P::T * 128 - 2);
+    int cells = P::T * 128 + 2 * WP + 2;
+    while (cells % 8 != 1) ++cells;              // LBO/16 = 1 (mod 8): conflict-free staging stores
+    const size_t smem = (size_t)P::KG * cells * 16 + (size_t)P::NSLOT * P::SLOT_BYTES;
+    CFP_REQUIRE(smem <= 220 * 1024, "conv3x3 (tensor-core path): %zu B shared memory", smem);
+    auto k = conv3x3_tc_kernel<C>;
+    if (int e = set_smem(k, smem)) return e;
+    dim3 grid((H + R - 1) / R, B);
+    k<<<grid, 192, smem, st>>>((const bf16*)in0, (const bf16*)in1, (const bf16*)wpk, shift, (const bf16*)residual,
+                               (bf16*)out, H, W, R, cells, zy0, zy1, zx0, zx1);
+    return check_launch(in1 ? "conv3x3_tc<2C->C>" : "conv3x3_tc<C->C>");
+}
+
+int conv3x3_tc(const void* in0, const void* in1, const void* wpk, const float* shift, const void* residual, void* out,
+               int B, int H, int W, int C, int zy0, int zy1, int zx0, int zx1, cudaStream_t st) {
+    CFP_REQUIRE(B <= 65535, "B too large for grid.y");
+    if (C == 32) return conv_tc_launch<32>(in0, in1, wpk, shift, residual, out, B, H, W, zy0, zy1, zx0, zx1, st);
+    if (C == 64) return conv_tc_launch<64>(in0, in1, wpk, shift, residual, out, B, H, W, zy0, zy1, zx0, zx1, st);
+    if (C == 128) return conv_tc_launch<128>(in0, in1, wpk, shift, residual, out, B, H, W, zy0, zy1, zx0, zx1, st);
+    return fail("unsupported C=%d", C);
+}
+
+}  // namespace cfp

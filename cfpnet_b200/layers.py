@@ -13,7 +13,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .packing import fold_bn, linear_t
+from .packing import fold_bn, linear_t, umma_block
 
 
 class LinearAttention(nn.Module):
@@ -153,12 +153,17 @@ class LoFTREncoderLayer_newcross9(nn.Module):
         w.attn = _lib.CfpLoftrW(**{k: v.data_ptr() for k, v in t.items()})
         for i, (conv, bn) in enumerate(((self.conv1, self.bn1), (self.conv2, self.bn2)), start=1):
             scale, shift = fold_bn(bn)
-            wt = conv.weight.detach().float() * scale[:, None, None, None]          # [Cout,Cin,3,3]
-            wt = wt.permute(2, 3, 1, 0).reshape(9 * wt.shape[1], wt.shape[0]).contiguous()
+            ws = conv.weight.detach().float() * scale[:, None, None, None]          # [Cout,Cin,3,3]
+            cout, cin = ws.shape[0], ws.shape[1]
+            wt = ws.permute(2, 3, 1, 0).reshape(9 * cin, cout).contiguous()
+            # tensor-core blocks: one [Cout x Cout-wide K] block per (source, tap)
+            pk = torch.stack([umma_block(ws[:, s0:s0 + cout, ky, kx])
+                              for s0 in range(0, cin, cout) for ky in range(3) for kx in range(3)]).contiguous()
             shift = shift.contiguous()
-            keep.extend((wt, shift))
+            keep.extend((wt, shift, pk))
             setattr(w, f"conv{i}_t", wt.data_ptr())
             setattr(w, f"shift{i}", shift.data_ptr())
+            setattr(w, f"conv{i}_pk", pk.data_ptr())
         return w
 
 

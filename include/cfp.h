@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define CFP_ABI_VERSION 1
+#define CFP_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define CFP_API __attribute__((visibility("default")))
@@ -67,6 +67,10 @@ typedef struct cfp_loftr_w {
 typedef struct cfp_dapm_w {
     cfp_loftr_w attn;
     const float *conv1_t, *shift1, *conv2_t, *shift2;
+    /* bf16 tensor-core path: the same (scaled) weights as bf16 blocks in the canonical K-major
+     * UMMA layout, one [C/8][C][8] block per (source, tap): conv1_pk [2*9] blocks (source 0 =
+     * feat0 channels, source 1 = message channels), conv2_pk [9] blocks.  Required for CFP_BF16. */
+    const void *conv1_pk, *conv2_pk;
 } cfp_dapm_w;
 
 /* LKPM Block14 (src/models/convnext.py:42-58), eval-mode BN folded:

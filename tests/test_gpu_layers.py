@@ -1,0 +1,96 @@
+"""Per-layer checks through the C ABI: each bf16 (tensor-core) layer entry point against the
+fp32 (exact FFMA) entry point of the same library on identical inputs, and against the oracle."""
+import ctypes
+
+import pytest
+import torch
+
+import cfpnet_b200
+from cfpnet_b200 import _lib, geometry, synth
+from cfpnet_b200.config import args
+from helpers import ref_keys, rel_l2
+from oracle import cfp_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def module_for(level):
+    C, _, max_res, lk = synth.LEVELS[level]
+    args.attention_layer = list(synth.COMBINE1_LAYERS)
+    m = cfpnet_b200.TransformerFusion(C, list(max_res), large_kernel=lk, patch_size=640 // max_res[1])
+    sd = synth.synthetic_state_dict(ref_keys()[f"fusion_combine1_L{level}"], seed=level)
+    m.load_state_dict(sd)
+    return m.to(DEV).eval(), sd
+
+
+def layer_call(m, name, layer_idx, feat0, geom_name="G416", level=3, mask=None, feat1=None):
+    """Run ONE layer entry point in place on a copy of feat0 [B,N,C]; returns the result."""
+    C = m.embedding_dim
+    H, W = synth.level_hw(geom_name, level)
+    B = feat0.shape[0]
+    inp = synth.make_inputs(geom_name, B, levels=())
+    g = geometry.zone_geometry(inp["patch_info"], m.max_resolution[1], H, W)
+    cg = _lib.CfpGeom.from_geometry(g)
+    code = _lib.dtype_code(feat0.dtype)
+    packed, pos, pos2, _keep = m._cache.get(m._pack)
+    lib = _lib.load()
+    nbytes = lib.cfp_workspace_bytes(B, H, W, C, m.ws, code, ctypes.byref(cg))
+    work = torch.empty(nbytes, device=DEV, dtype=torch.uint8)
+    x = feat0.clone()
+    st = _lib.stream_ptr()
+    w = packed[layer_idx]
+    if name == "dapm":
+        _lib.call("cfp_dapm_fwd", x.data_ptr(), B, H, W, C, ctypes.byref(cg), ctypes.byref(w[0]), work.data_ptr(),
+                  nbytes, code, st)
+    elif name == "lkpm":
+        _lib.call("cfp_lkpm_fwd", x.data_ptr(), B, H, W, C, ctypes.byref(w[1]), work.data_ptr(), nbytes, code, st)
+    elif name == "twins":
+        _lib.call("cfp_twins_fwd", x.data_ptr(), B, H, W, C, ctypes.byref(w), work.data_ptr(), nbytes, code, st)
+    elif name == "d2i":
+        _lib.call("cfp_d2i_fwd", x.data_ptr(), x.data_ptr(), feat1.data_ptr(), pos2.data_ptr(), mask.data_ptr(),
+                  B, H, W, C, feat1.shape[2], ctypes.byref(cg), ctypes.byref(w), 0, work.data_ptr(), nbytes, code, st)
+    torch.cuda.synchronize()
+    return x, g
+
+
+@pytest.fixture(autouse=True)
+def _restore_flags():
+    saved = (list(args.attention_layer), args.change_embedding, args.no_skip_inside)
+    yield
+    args.attention_layer, args.change_embedding, args.no_skip_inside = saved
+
+
+@pytest.mark.parametrize("level", [3, 2, 1])
+@pytest.mark.parametrize("name,idx", [("dapm", 1), ("lkpm", 1), ("twins", 2), ("d2i", 0)])
+def test_bf16_layer_matches_fp32_layer(level, name, idx):
+    m, sd = module_for(level)
+    C = m.embedding_dim
+    H, W = synth.level_hw("G416", level)
+    B = 2
+    g0 = torch.Generator().manual_seed(level * 10 + idx)
+    f32 = torch.randn(B, H * W, C, generator=g0).to(DEV)
+    bf = f32.to(torch.bfloat16)
+    kw = {}
+    if name == "d2i":
+        inp = synth.make_inputs("G416", B, levels=())
+        kw["mask"] = inp["mask"].to(DEV, torch.uint8).contiguous()
+        feat1 = torch.randn(B, 64, 16, C, generator=g0).to(DEV)
+        kw["feat1"] = feat1
+    exact, geom = layer_call(m, name, idx, bf.float(), level=level, **kw)
+    if name == "d2i":
+        kw["feat1"] = kw["feat1"].to(torch.bfloat16)
+    fast, _ = layer_call(m.to(torch.bfloat16), name, idx, bf, level=level, **kw)
+    err = rel_l2(fast, exact)
+    assert err <= 1.5e-2, f"{name} L{level}: bf16 vs fp32 rel-L2 {err:.3e}"
+
+
+@pytest.mark.parametrize("level", [3, 2, 1])
+def test_dapm_layer_vs_oracle(level):
+    m, sd = module_for(level)
+    C = m.embedding_dim
+    H, W = synth.level_hw("G416", level)
+    f = torch.randn(2, H * W, C, generator=torch.Generator().manual_seed(level)).to(DEV)
+    out, g = layer_call(m, "dapm", 1, f, level=level)
+    truth = O.dapm(O.sub(sd, "layers.1.transformer_path."), f.double().cpu(), g.asdict(), H, W)
+    assert rel_l2(out, truth) <= 1e-4
