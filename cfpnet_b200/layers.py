@@ -56,6 +56,11 @@ class LoFTREncoderLayer(nn.Module):
             ln2_g=self.norm2.weight.detach().float().contiguous(),
             ln2_b=self.norm2.bias.detach().float().contiguous(),
         )
+        C = self.q_proj.weight.shape[0]
+        w1, w2 = self.mlp[0].weight, self.mlp[2].weight
+        t["tc"] = torch.stack([umma_block(b) for b in (
+            self.q_proj.weight, self.merge.weight, w1[:C, :C], w1[:C, C:], w1[C:, :C], w1[C:, C:],
+            w2[:, :C], w2[:, C:])]).contiguous()
         keep.extend(t.values())
         return _lib.CfpLoftrW(**{k: v.data_ptr() for k, v in t.items()})
 
@@ -148,6 +153,7 @@ class LoFTREncoderLayer_newcross9(nn.Module):
         t = dict(
             wq_t=linear_t(self.q_proj.weight),
             wkv_t=torch.cat([linear_t(self.k_proj.weight), linear_t(self.v_proj.weight)], dim=1).contiguous(),
+            tc=umma_block(self.q_proj.weight),
         )
         keep.extend(t.values())
         w.attn = _lib.CfpLoftrW(**{k: v.data_ptr() for k, v in t.items()})

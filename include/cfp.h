@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define CFP_ABI_VERSION 2
+#define CFP_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define CFP_API __attribute__((visibility("default")))
@@ -59,6 +59,11 @@ typedef struct cfp_geom {
 typedef struct cfp_loftr_w {
     const float *wq_t, *wkv_t, *wm_t, *w1_t, *w2_t;
     const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+    /* bf16 tensor-core path: the chain's weights as eight [C x C] bf16 blocks in the canonical
+     * K-major UMMA layout ([C/8][C][8] each), in consumption order: Wq, Wm, W1[:C,:C], W1[:C,C:],
+     * W1[C:,:C], W1[C:,C:], W2[:,:C], W2[:,C:] (rows = outputs).  DAPM uses only the first block.
+     * Required for CFP_BF16. */
+    const void *tc;
 } cfp_loftr_w;
 
 /* DAPM convs (transformer.py:197-200, 239-244) with eval-mode BN folded:
