@@ -18,7 +18,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcfp.so")
 
 CFP_F32, CFP_BF16 = 0, 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 _fp = C.POINTER(C.c_float)
 
 
@@ -44,7 +44,7 @@ class CfpDapmW(C.Structure):
 
 class CfpLkpmW(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
-        "dw_t", "dw_shift", "ln_g", "ln_b", "pw1_t", "pw1_b", "pw2_t", "pw2_b")] + [("ksize", C.c_int32)]
+        "dw_t", "dw_shift", "ln_g", "ln_b", "pw1_t", "pw1_b", "pw2_t", "pw2_b", "tc")] + [("ksize", C.c_int32)]
 
 
 class CfpTwinsW(C.Structure):

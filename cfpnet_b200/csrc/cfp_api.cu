@@ -206,6 +206,7 @@ CFP_API int cfp_lkpm_fwd(void* feat0, int B, int H, int W, int C, const cfp_lkpm
     cudaStream_t st = (cudaStream_t)stream;
     void* y = ws + L.tok_a;
     if (int e = dwconv_bn_relu(feat0, y, B, H, W, C, w->ksize, w->dw_t, w->dw_shift, dtype, st)) return e;
+    if (dtype == CFP_BF16) return lkpm_mlp_tc(feat0, y, (int64_t)B * H * W, C, *w, st);
     return lkpm_mlp(feat0, y, (int64_t)B * H * W, C, *w, dtype, st);
 }
 

@@ -59,6 +59,9 @@ int lkpm_mlp(void* feat0, const void* y, int64_t rows, int C, const cfp_lkpm_w& 
 int conv3x3_tc(const void* in0, const void* in1, const void* wpk, const float* shift, const void* residual, void* out,
                int B, int H, int W, int C, int zy0, int zy1, int zx0, int zx1, cudaStream_t st);
 
+// k_chain_tc.cu  (bf16, tcgen05)
+int lkpm_mlp_tc(void* feat0, const void* y, int64_t rows, int C, const cfp_lkpm_w& w, cudaStream_t st);
+
 // k_selftest.cu
 int umma_selftest(const void* A, const void* B, float* D, int rows_a, int N, int K, int row_shift, cudaStream_t st);
 

@@ -314,6 +314,194 @@ static int run_query_tc(const char* name, const Q& q, const cfp_loftr_w& w, cons
     return check_launch(name);
 }
 
+// =====================================================================================
+// LKPM pointwise half on tensor cores (convnext.py:49-58):
+//   out = x + W2 GELU(W1 LN(y) + b1) + b2,   W1: C -> 4C, W2: 4C -> C
+// The 4C hidden dimension is walked in four C-wide slices j: h_j = LN(y) W1_j^T (TMEM cols
+// [0,C)), GELU in registers -> bf16 A tile, out += h_j W2_j^T (TMEM cols [C,2C)); the out
+// accumulator stays in TMEM across the four slices.  MMA2_j and MMA1_{j+1} are issued back to
+// back, so the tensor pipe works on slice j+1 while the row threads apply GELU to slice j.
+// Weight blocks in consumption order: W1_0, W2_0, W1_1, W2_1, W1_2, W2_2, W1_3, W2_3.
+template <int C>
+__global__ void __launch_bounds__(192) lkpm_mlp_tc_kernel(bf16* __restrict__ feat0, const bf16* __restrict__ y,
+                                                          int64_t rows, cfp_lkpm_w w, int ntiles) {
+    using P = ChainTC<C>;
+    constexpr int KG = P::KG;
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ ChainBars bars;
+    uint8_t* a0 = smem;                          // LN(y)        [KG][129][16 B]
+    uint8_t* a1 = a0 + KG * P::LBO;              // GELU(h_j)    [KG][129][16 B]
+    uint8_t* ring = a1 + KG * P::LBO;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        for (int i = 0; i < P::NSLOT; ++i) { umma::mbar_init(&bars.full[i], 1); umma::mbar_init(&bars.empty[i], 1); }
+        umma::mbar_init(&bars.a_ready, 128);
+        umma::mbar_init(&bars.acc_ready, 1);
+        umma::fence_mbar_init();
+    }
+    if (warp == 4) umma::tmem_alloc(&bars.tmem_slot, P::TMEM_COLS);
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = bars.tmem_slot;
+
+    if (warp < 4) {
+        uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int64_t row0 = (int64_t)tile * 128;
+            for (int i = tid; i < 128 * KG; i += 128) {          // coalesced copy of the y tile
+                const int r = i / KG, kg = i % KG;
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                if (row0 + r < rows) v = *reinterpret_cast<const uint4*>(y + (row0 + r) * C + kg * 8);
+                *reinterpret_cast<uint4*>(a0 + (size_t)kg * P::LBO + r * 16) = v;
+            }
+            rows_sync();
+            {   // channels-last LayerNorm (eps 1e-6) of row `tid`, in place
+                float v[C];
+#pragma unroll
+                for (int j = 0; j < C; j += 8) {
+                    float t[8];
+                    unpack8(*reinterpret_cast<const uint4*>(a0 + (size_t)(j / 8) * P::LBO + tid * 16), t);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[j + i] = t[i];
+                }
+                float s = 0.f;
+#pragma unroll
+                for (int i = 0; i < C; ++i) s += v[i];
+                const float mean = s * (1.f / C);
+                float q = 0.f;
+#pragma unroll
+                for (int i = 0; i < C; ++i) { v[i] -= mean; q += v[i] * v[i]; }
+                const float rstd = rsqrtf(q * (1.f / C) + kLkpmLnEps);
+#pragma unroll
+                for (int j = 0; j < C; j += 8) {
+                    float o8[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) o8[i] = v[j + i] * rstd * w.ln_g[j + i] + w.ln_b[j + i];
+                    umma::store_chunk(a0, P::LBO, tid, j / 8, o8);
+                }
+            }
+            umma::fence_async_smem();
+            mbar_arrive(&bars.a_ready);
+#pragma unroll 1
+            for (int js = 0; js < 4; ++js) {                     // hidden slice js: GELU(h + b1) -> a1
+                umma::mbar_wait(&bars.acc_ready, ph); ph ^= 1;
+                umma::fence_after_sync();
+#pragma unroll 1
+                for (int c0 = 0; c0 < C; c0 += 16) {
+                    float t[16];
+                    umma::tmem_ld16(umma::tmem_addr(tmem, warp * 32, c0), t);
+#pragma unroll
+                    for (int j = 0; j < 16; j += 8) {
+                        float o8[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) o8[i] = gelu_erf(t[j + i] + w.pw1_b[js * C + c0 + j + i]);
+                        umma::store_chunk(a1, P::LBO, tid, (c0 + j) / 8, o8);
+                    }
+                }
+                umma::fence_async_smem();
+                umma::fence_before_sync();
+                mbar_arrive(&bars.a_ready);
+            }
+            umma::mbar_wait(&bars.acc_ready, ph); ph ^= 1;       // out accumulator complete
+            umma::fence_after_sync();
+            const int64_t row = row0 + tid;
+#pragma unroll 1
+            for (int c0 = 0; c0 < C; c0 += 16) {
+                float t[16];
+                umma::tmem_ld16(umma::tmem_addr(tmem, warp * 32, C + c0), t);
+                if (row < rows) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 8) {
+                        bf16* p = feat0 + row * C + c0 + j;
+                        float x8[8];
+                        unpack8(*reinterpret_cast<const uint4*>(p), x8);
+                        uint4 u;
+                        u.x = umma::pack_bf16(x8[0] + t[j + 0] + w.pw2_b[c0 + j + 0], x8[1] + t[j + 1] + w.pw2_b[c0 + j + 1]);
+                        u.y = umma::pack_bf16(x8[2] + t[j + 2] + w.pw2_b[c0 + j + 2], x8[3] + t[j + 3] + w.pw2_b[c0 + j + 3]);
+                        u.z = umma::pack_bf16(x8[4] + t[j + 4] + w.pw2_b[c0 + j + 4], x8[5] + t[j + 5] + w.pw2_b[c0 + j + 5]);
+                        u.w = umma::pack_bf16(x8[6] + t[j + 6] + w.pw2_b[c0 + j + 6], x8[7] + t[j + 7] + w.pw2_b[c0 + j + 7]);
+                        *reinterpret_cast<uint4*>(p) = u;
+                    }
+                }
+            }
+            umma::fence_before_sync();
+            rows_sync();
+        }
+    } else if (warp == 4) {
+        if (lane == 0) {
+            const bf16* wsrc = reinterpret_cast<const bf16*>(w.tc);
+            int cc = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+                for (int c = 0; c < 8; ++c, ++cc) {
+                    const int slot = cc % P::NSLOT, round = cc / P::NSLOT;
+                    if (round > 0) umma::mbar_wait(&bars.empty[slot], (round - 1) & 1);
+                    umma::mbar_expect_tx(&bars.full[slot], P::SLOT);
+                    umma::bulk_g2s(ring + (size_t)slot * P::SLOT, wsrc + (size_t)c * C * C, P::SLOT, &bars.full[slot]);
+                }
+        }
+    } else {
+        if (lane == 0) {
+            const uint32_t idesc = umma::idesc_bf16(128, C);
+            const uint32_t a0s = umma::smem_u32(a0), a1s = umma::smem_u32(a1), rs = umma::smem_u32(ring);
+            constexpr uint32_t LBO_B = C * 16;
+            uint32_t ph = 0;
+            int cc = 0;
+            auto block = [&](uint32_t abase, int dcol, bool acc_first) {
+                const int slot = cc % P::NSLOT, round = cc / P::NSLOT;
+                umma::mbar_wait(&bars.full[slot], round & 1);
+                umma::fence_after_sync();
+                const uint32_t wb = rs + slot * P::SLOT;
+#pragma unroll
+                for (int ks = 0; ks < C / 16; ++ks)
+                    umma::mma_bf16(tmem + dcol, umma::smem_desc(abase + 2 * ks * P::LBO, P::LBO),
+                                   umma::smem_desc(wb + ks * 2 * LBO_B, LBO_B), idesc, acc_first || ks > 0);
+                umma::commit(&bars.empty[slot]);
+                ++cc;
+            };
+            auto wait_a = [&]() { umma::mbar_wait(&bars.a_ready, ph); ph ^= 1; umma::fence_after_sync(); };
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                wait_a();
+                block(a0s, 0, false);                          // h_0
+                umma::commit(&bars.acc_ready);
+                for (int js = 0; js < 4; ++js) {
+                    wait_a();                                  // GELU(h_js) staged in a1, h columns free
+                    block(a1s, C, js > 0);                     // out += GELU(h_js) W2_js^T
+                    if (js < 3) block(a0s, 0, false);          // h_{js+1}
+                    umma::commit(&bars.acc_ready);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 4) {
+        umma::fence_after_sync();
+        umma::tmem_dealloc(tmem, P::TMEM_COLS);
+    }
+}
+
+template <int C>
+static int run_lkpm_mlp_tc(void* feat0, const void* y, int64_t rows, const cfp_lkpm_w& w, cudaStream_t st) {
+    using P = ChainTC<C>;
+    CFP_REQUIRE(w.tc != nullptr, "lkpm_mlp: bf16 path needs the packed tensor-core weights (cfp_lkpm_w.tc)");
+    constexpr size_t smem = 2 * (size_t)P::KG * P::LBO + (size_t)P::NSLOT * P::SLOT;
+    auto k = lkpm_mlp_tc_kernel<C>;
+    if (int e = set_smem(k, smem)) return e;
+    const int64_t ntiles = (rows + 127) / 128;
+    const int per_sm = C >= 128 ? 1 : (C == 64 ? 2 : 4);
+    const int grid = (int)(ntiles < 148 * per_sm ? ntiles : 148 * per_sm);
+    k<<<grid, 192, smem, st>>>((bf16*)feat0, (const bf16*)y, rows, w, (int)ntiles);
+    return check_launch("lkpm_mlp_tc");
+}
+
+int lkpm_mlp_tc(void* feat0, const void* y, int64_t rows, int C, const cfp_lkpm_w& w, cudaStream_t st) {
+    if (C == 32) return run_lkpm_mlp_tc<32>(feat0, y, rows, w, st);
+    if (C == 64) return run_lkpm_mlp_tc<64>(feat0, y, rows, w, st);
+    if (C == 128) return run_lkpm_mlp_tc<128>(feat0, y, rows, w, st);
+    return fail("unsupported C=%d", C);
+}
+
 // ---- entry points used by k_loftr.cu's layer implementations (bf16 only)
 #define CFP_TC_DISPATCH(NH, ATTN, NAME)                                                  \
     if (C == 32) return run_query_tc<32, NH, ATTN>(NAME, q, w, kv, ksum, st);            \

@@ -220,6 +220,11 @@ class Block14(nn.Module):
             pw2_t=linear_t(self.pwconv2.weight),
             pw2_b=self.pwconv2.bias.detach().float().contiguous(),
         )
+        w1, w2 = self.pwconv1.weight, self.pwconv2.weight
+        blocks = []
+        for j in range(4):
+            blocks += [umma_block(w1[j * C:(j + 1) * C, :]), umma_block(w2[:, j * C:(j + 1) * C])]
+        t["tc"] = torch.stack(blocks).contiguous()
         keep.extend(t.values())
         w = _lib.CfpLkpmW(**{n: v.data_ptr() for n, v in t.items()})
         w.ksize = k

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define CFP_ABI_VERSION 3
+#define CFP_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define CFP_API __attribute__((visibility("default")))
@@ -83,6 +83,10 @@ typedef struct cfp_dapm_w {
  *   ln_g/b [C]; pw1_t [C][4C], pw1_b [4C]; pw2_t [4C][C], pw2_b [C]. */
 typedef struct cfp_lkpm_w {
     const float *dw_t, *dw_shift, *ln_g, *ln_b, *pw1_t, *pw1_b, *pw2_t, *pw2_b;
+    /* bf16 tensor-core path: eight [C x C] bf16 blocks in the canonical K-major UMMA layout, in
+     * consumption order W1_0, W2_0, ..., W1_3, W2_3 with W1_j = pwconv1.weight[jC:(j+1)C, :] and
+     * W2_j = pwconv2.weight[:, jC:(j+1)C].  Required for CFP_BF16. */
+    const void *tc;
     int32_t ksize;
 } cfp_lkpm_w;
 

@@ -39,7 +39,7 @@ def test_ctypes_structs_match_header_layout():
     assert ctypes.sizeof(_lib.CfpGeom) == 16 * 4
     assert ctypes.sizeof(_lib.CfpLoftrW) == 10 * 8
     assert ctypes.sizeof(_lib.CfpDapmW) == 16 * 8
-    assert ctypes.sizeof(_lib.CfpLkpmW) == 9 * 8          # 8 pointers + int32 (+pad)
+    assert ctypes.sizeof(_lib.CfpLkpmW) == 10 * 8         # 9 pointers + int32 (+pad)
     assert ctypes.sizeof(_lib.CfpTwinsW) == 20 * 8 + 4 * 8 + 8
     assert ctypes.sizeof(_lib.CfpHistW) == 18 * 8
 
