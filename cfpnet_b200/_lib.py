@@ -18,7 +18,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcfp.so")
 
 CFP_F32, CFP_BF16 = 0, 1
-ABI_VERSION = 4
+ABI_VERSION = 6
 _fp = C.POINTER(C.c_float)
 
 
@@ -34,7 +34,7 @@ class CfpGeom(C.Structure):
 
 class CfpLoftrW(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
-        "wq_t", "wkv_t", "wm_t", "w1_t", "w2_t", "ln1_g", "ln1_b", "ln2_g", "ln2_b", "tc")]
+        "wq_t", "wkv_t", "wm_t", "w1_t", "w2_t", "ln1_g", "ln1_b", "ln2_g", "ln2_b", "tc", "kv_tc")]
 
 
 class CfpDapmW(C.Structure):
@@ -49,7 +49,7 @@ class CfpLkpmW(C.Structure):
 
 class CfpTwinsW(C.Structure):
     _fields_ = [("lsa", CfpLoftrW), ("gsa", CfpLoftrW)] + \
-               [(n, C.c_void_p) for n in ("sr_t", "sr_b", "srln_g", "srln_b")] + [("ws", C.c_int32)]
+               [(n, C.c_void_p) for n in ("sr_t", "sr_b", "srln_g", "srln_b", "sr_tc")] + [("ws", C.c_int32)]
 
 
 class CfpHistW(C.Structure):

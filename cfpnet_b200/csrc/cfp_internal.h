@@ -61,6 +61,8 @@ int conv3x3_tc(const void* in0, const void* in1, const void* wpk, const float* s
 
 // k_chain_tc.cu  (bf16, tcgen05)
 int lkpm_mlp_tc(void* feat0, const void* y, int64_t rows, int C, const cfp_lkpm_w& w, cudaStream_t st);
+int sr_conv_ln_tc(const void* feat0, float* sr_tok, int B, int H, int W, int C, int ws, const void* sr_tc,
+                  const float* sr_b, const float* g, const float* b, cudaStream_t st);
 
 // k_selftest.cu
 int umma_selftest(const void* A, const void* B, float* D, int rows_a, int N, int K, int row_shift, cudaStream_t st);

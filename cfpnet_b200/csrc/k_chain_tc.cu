@@ -502,6 +502,389 @@ int lkpm_mlp_tc(void* feat0, const void* y, int64_t rows, int C, const cfp_lkpm_
     return fail("unsupported C=%d", C);
 }
 
+// =====================================================================================
+// Attention state on tensor cores (attention.py:31-44):
+//   K = elu(x Wk^T)+1, V = x Wv^T,  KV[g][h] = sum_{s in g} K_s^T V_s  (dh x dh),  Ksum[g] = sum_s K_s
+// Both contractions are tcgen05.mma:
+//   (1) the projection, [128 rows] x [C] x [2C], exactly like a chain stage;
+//   (2) the reduction over rows.  The row threads write K and V (bf16) back in the chain's
+//       [channel-group][row][16 B] layout; read as an *MN-major* operand (channel = M/N index,
+//       row = K index, SBO = group stride, LBO = 128 B) the very same buffer is K^T and V^T, so
+//       D[c1][c2] = sum_r K[r][c1] V[r][c2] is one M=128, N=C+16 MMA per 16 rows.  The extra 16
+//       columns carry a ones-column, which makes Ksum fall out of the same MMA.  Only the
+//       block-diagonal (same-head) part of D is used: thread c1 (TMEM lane c1) reads its head's
+//       dh columns and adds them to the fp32 state in global memory.
+// Rows are enumerated per group with the group size padded to a multiple of 16, so every
+// 16-row MMA step belongs to one group; consecutive steps of a group form a "run" that
+// accumulates in TMEM before it is flushed (plain stores when groups never straddle a tile).
+template <int C> struct KvTC {
+    static constexpr int KG = C / 8;
+    static constexpr int A1G = 2 * KG + 2 < 16 ? 16 : 2 * KG + 2;   // K | V | ones | zeros (>= 16 groups: M = 128)
+    static constexpr int NRED = C + 16;
+    static constexpr int TMEM_COLS = 3 * C + 16 <= 128 ? 128 : (3 * C + 16 <= 256 ? 256 : 512);
+    static constexpr size_t SMEM = (size_t)(KG + A1G) * ChainTC<C>::LBO + 4 * (size_t)C * C;
+};
+
+template <int C, int NH, bool kComplete, class Src>
+__global__ void __launch_bounds__(192) kv_state_tc_kernel(Src src, int S, int S_pad, int groups, const bf16* __restrict__ wkv_tc,
+                                                          float* __restrict__ kv, float* __restrict__ ksum, int ntiles) {
+    using P = ChainTC<C>;
+    using K = KvTC<C>;
+    constexpr int DH = C / NH, KG = P::KG;
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ ChainBars bars;
+    uint8_t* a0 = smem;                            // x tile                [KG][129][16 B]
+    uint8_t* a1 = a0 + KG * P::LBO;                // K | V | ones | zeros  [A1G][129][16 B]
+    uint8_t* wsm = a1 + K::A1G * P::LBO;           // Wk, Wv blocks
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        umma::mbar_init(&bars.full[0], 1);
+        umma::mbar_init(&bars.a_ready, 128);
+        umma::mbar_init(&bars.acc_ready, 1);
+        umma::fence_mbar_init();
+    }
+    if (warp == 4) umma::tmem_alloc(&bars.tmem_slot, K::TMEM_COLS);
+    if (warp < 4)                                   // zero the groups no one writes later
+        for (int i = tid; i < (K::A1G - 2 * KG) * 129; i += 128)
+            *reinterpret_cast<uint4*>(a1 + (size_t)(2 * KG) * P::LBO + (size_t)i * 16) = make_uint4(0u, 0u, 0u, 0u);
+    umma::fence_async_smem();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = bars.tmem_slot;
+    const int64_t total = (int64_t)groups * S_pad;
+
+    if (warp < 4) {
+        uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int64_t row0 = (int64_t)tile * 128;
+            for (int i = tid; i < 128 * KG; i += 128) {
+                const int r = i / KG, kg = i % KG;
+                const int64_t p = row0 + r;
+                const int g = (int)(p / S_pad), sidx = (int)(p % S_pad);
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                if (p < total && sidx < S) v = load8_bf16(src, (int64_t)g * S + sidx, kg * 8);
+                *reinterpret_cast<uint4*>(a0 + (size_t)kg * P::LBO + r * 16) = v;
+            }
+            const int64_t myp = row0 + tid;
+            const bool real = myp < total && (int)(myp % S_pad) < S;
+            umma::fence_async_smem();
+            mbar_arrive(&bars.a_ready);
+
+            // ---- K = elu(k)+1 and V of row `tid` -> a1 (zeros for padding rows)
+            umma::mbar_wait(&bars.acc_ready, ph); ph ^= 1;
+            umma::fence_after_sync();
+#pragma unroll 1
+            for (int c0 = 0; c0 < 2 * C; c0 += 16) {
+                float t[16];
+                umma::tmem_ld16(umma::tmem_addr(tmem, warp * 32, c0), t);
+#pragma unroll
+                for (int j = 0; j < 16; j += 8) {
+                    float o8[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) o8[i] = !real ? 0.f : (c0 < C ? elu1(t[j + i]) : t[j + i]);
+                    umma::store_chunk(a1, P::LBO, tid, (c0 + j) / 8, o8);
+                }
+            }
+            {
+                const float one8[8] = {real ? 1.f : 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                umma::store_chunk(a1, P::LBO, tid, 2 * KG, one8);
+            }
+            umma::fence_async_smem();
+            umma::fence_before_sync();
+            mbar_arrive(&bars.a_ready);
+
+            // ---- flush the runs: lane c1 adds D[c1][head(c1) block] and D[c1][ones] to the state
+            int ks = 0;
+            while (ks < 8 && row0 + 16 * ks < total) {
+                const int g = (int)((row0 + 16 * ks) / S_pad);
+                int ke = ks + 1;
+                while (ke < 8 && row0 + 16 * ke < total && (int)((row0 + 16 * ke) / S_pad) == g) ++ke;
+                umma::mbar_wait(&bars.acc_ready, ph); ph ^= 1;
+                umma::fence_after_sync();
+                if (warp * 32 < C) {
+                    const int m = warp * 32 + lane;
+                    float t[32], o[16];
+                    umma::tmem_ld16(umma::tmem_addr(tmem, warp * 32, 2 * C + warp * 32), *reinterpret_cast<float(*)[16]>(&t[0]));
+                    umma::tmem_ld16(umma::tmem_addr(tmem, warp * 32, 2 * C + warp * 32 + 16), *reinterpret_cast<float(*)[16]>(&t[16]));
+                    umma::tmem_ld16(umma::tmem_addr(tmem, warp * 32, 3 * C), o);
+                    float* dst = kv + (size_t)g * (C * DH) + (size_t)m * DH;
+#pragma unroll
+                    for (int sb = 0; sb < 32 / DH; ++sb)
+                        if (lane / DH == sb) {
+#pragma unroll
+                            for (int j = 0; j < DH; ++j) {
+                                if (kComplete) dst[j] = t[sb * DH + j];
+                                else atomicAdd(dst + j, t[sb * DH + j]);
+                            }
+                        }
+                    if (kComplete) ksum[(size_t)g * C + m] = o[0];
+                    else atomicAdd(ksum + (size_t)g * C + m, o[0]);
+                }
+                ks = ke;
+                const bool last = !(ks < 8 && row0 + 16 * ks < total);
+                if (!last) {
+                    umma::fence_before_sync();
+                    mbar_arrive(&bars.a_ready);
+                }
+            }
+            umma::fence_before_sync();
+        }
+    } else if (warp == 4) {
+        if (lane == 0) {
+            umma::mbar_expect_tx(&bars.full[0], 4 * C * C);
+            umma::bulk_g2s(wsm, wkv_tc, 4 * C * C, &bars.full[0]);
+        }
+    } else {
+        if (lane == 0) {
+            const uint32_t idesc = umma::idesc_bf16(128, C);
+            const uint32_t idesc_red = umma::idesc_bf16(128, K::NRED) | (1u << 15) | (1u << 16);   // A, B MN-major
+            const uint32_t a0s = umma::smem_u32(a0), a1s = umma::smem_u32(a1), ws = umma::smem_u32(wsm);
+            constexpr uint32_t LBO_B = C * 16;
+            uint32_t ph = 0;
+            auto wait_a = [&]() { umma::mbar_wait(&bars.a_ready, ph); ph ^= 1; umma::fence_after_sync(); };
+            umma::mbar_wait(&bars.full[0], 0);
+            umma::fence_after_sync();
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int64_t row0 = (int64_t)tile * 128;
+                wait_a();
+#pragma unroll
+                for (int half = 0; half < 2; ++half)          // k -> cols [0,C), v -> cols [C,2C)
+#pragma unroll
+                    for (int ks = 0; ks < C / 16; ++ks)
+                        umma::mma_bf16(tmem + half * C, umma::smem_desc(a0s + 2 * ks * P::LBO, P::LBO),
+                                       umma::smem_desc(ws + half * 2 * C * C + ks * 2 * LBO_B, LBO_B), idesc, ks > 0);
+                umma::commit(&bars.acc_ready);
+                wait_a();                                     // K | V | ones staged
+                int ks = 0;
+                bool first = true;
+                while (ks < 8 && row0 + 16 * ks < total) {
+                    const int g = (int)((row0 + 16 * ks) / S_pad);
+                    int ke = ks + 1;
+                    while (ke < 8 && row0 + 16 * ke < total && (int)((row0 + 16 * ke) / S_pad) == g) ++ke;
+                    if (!first) wait_a();                     // previous run's accumulator has been read
+                    first = false;
+                    for (int k = ks; k < ke; ++k)             // MN-major views: SBO = group stride, LBO = 8 rows
+                        umma::mma_bf16(tmem + 2 * C, umma::smem_desc(a1s + k * 256, 128, P::LBO),
+                                       umma::smem_desc(a1s + KG * P::LBO + k * 256, 128, P::LBO), idesc_red, k > ks);
+                    umma::commit(&bars.acc_ready);
+                    ks = ke;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 4) {
+        umma::fence_after_sync();
+        umma::tmem_dealloc(tmem, K::TMEM_COLS);
+    }
+}
+
+template <int C, int NH, class Src>
+static int run_kv_state_tc(const char* name, const Src& src, int S, int groups, const void* wkv_tc, float* kv, float* ksum,
+                           cudaStream_t st) {
+    using K = KvTC<C>;
+    constexpr int DH = C / NH;
+    CFP_REQUIRE(wkv_tc != nullptr, "%s: bf16 path needs the packed tensor-core weights (cfp_loftr_w.kv_tc)", name);
+    const int S_pad = (S + 15) / 16 * 16;
+    const bool complete = 128 % S_pad == 0;          // groups never straddle a tile: plain stores, no memset
+    if (!complete) {
+        cudaError_t e = cudaMemsetAsync(kv, 0, (size_t)groups * (C * DH + C) * sizeof(float), st);
+        if (e != cudaSuccess) return fail("cudaMemsetAsync(kv state): %s", cudaGetErrorString(e));
+    }
+    const int64_t ntiles = ((int64_t)groups * S_pad + 127) / 128;
+    const int per_sm = C >= 128 ? 1 : (C == 64 ? 2 : 4);
+    const int grid = (int)(ntiles < 148 * per_sm ? ntiles : 148 * per_sm);
+    if (complete) {
+        auto k = kv_state_tc_kernel<C, NH, true, Src>;
+        if (int e = set_smem(k, K::SMEM)) return e;
+        k<<<grid, 192, K::SMEM, st>>>(src, S, S_pad, groups, (const bf16*)wkv_tc, kv, ksum, (int)ntiles);
+    } else {
+        auto k = kv_state_tc_kernel<C, NH, false, Src>;
+        if (int e = set_smem(k, K::SMEM)) return e;
+        k<<<grid, 192, K::SMEM, st>>>(src, S, S_pad, groups, (const bf16*)wkv_tc, kv, ksum, (int)ntiles);
+    }
+    return check_launch(name);
+}
+
+#define CFP_KV_DISPATCH(NH, NAME)                                                              \
+    if (C == 32) return run_kv_state_tc<32, NH>(NAME, src, S, groups, wkv_tc, kv, ksum, st);   \
+    if (C == 64) return run_kv_state_tc<64, NH>(NAME, src, S, groups, wkv_tc, kv, ksum, st);   \
+    if (C == 128) return run_kv_state_tc<128, NH>(NAME, src, S, groups, wkv_tc, kv, ksum, st); \
+    return fail("unsupported C=%d", C);
+
+int kv_tc_h2i(int C, const ZoneTokSrc<bf16>& src, int S, int groups, const void* wkv_tc, float* kv, float* ksum,
+              cudaStream_t st) { CFP_KV_DISPATCH(4, "kv_state_tc<hist2image>") }
+int kv_tc_lsa(int C, const WindowRows<bf16>& src, int S, int groups, const void* wkv_tc, float* kv, float* ksum,
+              cudaStream_t st) { CFP_KV_DISPATCH(8, "kv_state_tc<lsa>") }
+int kv_tc_gsa(int C, const SrTokSrc& src, int S, int groups, const void* wkv_tc, float* kv, float* ksum,
+              cudaStream_t st) { CFP_KV_DISPATCH(8, "kv_state_tc<gsa>") }
+int kv_tc_dapm(int C, const InsideSrc<bf16>& src, int S, int groups, const void* wkv_tc, float* kv, float* ksum,
+               cudaStream_t st) { CFP_KV_DISPATCH(4, "kv_state_tc<dapm>") }
+
+// =====================================================================================
+// GSA sub-sampling conv on tensor cores (transformer.py:144-147): a stride-ws, ws x ws conv is a
+// GEMM with K = ws*ws*C whose A rows are gathered per tap.  Only B*Ns (a few thousand) rows exist,
+// so the K dimension (taps) is split across CTAs (grid = row tiles x tap splits) and partial sums
+// are added atomically into an fp32 accumulator; sr_bias_ln_kernel then applies bias + LayerNorm.
+// Per tap: the 128 row threads gather the [128 x C] A slice into a 2-stage ring while the bulk-copy
+// engine brings the [C x C] weight block; the MMA lane consumes both and frees the stage by commit.
+struct SrBars {
+    uint64_t a_full[2], w_full[2], empty[2], acc_ready;
+    uint32_t tmem_slot;
+};
+
+template <int C>
+__global__ void __launch_bounds__(192) sr_conv_tc_kernel(const bf16* __restrict__ feat, float* __restrict__ acc_out,
+                                                         int64_t rows, int H, int W, int ws, int nsx, int Ns,
+                                                         const bf16* __restrict__ sr_tc, int taps_per_cta) {
+    using P = ChainTC<C>;
+    constexpr int KG = P::KG, TCOLS = C < 32 ? 32 : C;
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ SrBars bars;
+    uint8_t* a_st = smem;                                // [2][KG][129][16 B]
+    uint8_t* w_st = a_st + 2 * KG * P::LBO;              // [2][C x C]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ntap = ws * ws;
+    const int t0 = blockIdx.y * taps_per_cta, t1 = min(t0 + taps_per_cta, ntap);
+    const int64_t row0 = (int64_t)blockIdx.x * 128;
+
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            umma::mbar_init(&bars.a_full[i], 128);
+            umma::mbar_init(&bars.w_full[i], 1);
+            umma::mbar_init(&bars.empty[i], 1);
+        }
+        umma::mbar_init(&bars.acc_ready, 1);
+        umma::fence_mbar_init();
+    }
+    if (warp == 4) umma::tmem_alloc(&bars.tmem_slot, TCOLS);
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = bars.tmem_slot;
+
+    if (warp < 4) {
+        for (int t = t0; t < t1; ++t) {
+            const int n = t - t0, st = n & 1;
+            if (n >= 2) umma::mbar_wait(&bars.empty[st], ((n >> 1) - 1) & 1);
+            const int dy = t / ws, dx = t % ws;
+            uint8_t* a = a_st + (size_t)st * KG * P::LBO;
+            for (int i = tid; i < 128 * KG; i += 128) {
+                const int r = i / KG, kg = i % KG;
+                const int64_t row = row0 + r;
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                if (row < rows) {
+                    const int b = (int)(row / Ns), sidx = (int)(row % Ns);
+                    const int y = (sidx / nsx) * ws + dy, x = (sidx % nsx) * ws + dx;
+                    v = *reinterpret_cast<const uint4*>(feat + (((int64_t)b * H + y) * W + x) * C + kg * 8);
+                }
+                *reinterpret_cast<uint4*>(a + (size_t)kg * P::LBO + r * 16) = v;
+            }
+            umma::fence_async_smem();
+            mbar_arrive(&bars.a_full[st]);
+        }
+        umma::mbar_wait(&bars.acc_ready, 0);
+        umma::fence_after_sync();
+        const int64_t row = row0 + tid;
+#pragma unroll 1
+        for (int c0 = 0; c0 < C; c0 += 16) {
+            float v[16];
+            umma::tmem_ld16(umma::tmem_addr(tmem, warp * 32, c0), v);
+            if (row < rows) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) atomicAdd(acc_out + row * C + c0 + j, v[j]);
+            }
+        }
+        umma::fence_before_sync();
+    } else if (warp == 4) {
+        if (lane == 0)
+            for (int t = t0; t < t1; ++t) {
+                const int n = t - t0, st = n & 1;
+                if (n >= 2) umma::mbar_wait(&bars.empty[st], ((n >> 1) - 1) & 1);
+                umma::mbar_expect_tx(&bars.w_full[st], P::SLOT);
+                umma::bulk_g2s(w_st + (size_t)st * P::SLOT, sr_tc + (size_t)t * C * C, P::SLOT, &bars.w_full[st]);
+            }
+    } else {
+        if (lane == 0) {
+            const uint32_t idesc = umma::idesc_bf16(128, C);
+            constexpr uint32_t LBO_B = C * 16;
+            for (int t = t0; t < t1; ++t) {
+                const int n = t - t0, st = n & 1;
+                umma::mbar_wait(&bars.a_full[st], (n >> 1) & 1);
+                umma::mbar_wait(&bars.w_full[st], (n >> 1) & 1);
+                umma::fence_after_sync();
+                const uint32_t ab = umma::smem_u32(a_st) + st * KG * P::LBO, wb = umma::smem_u32(w_st) + st * P::SLOT;
+#pragma unroll
+                for (int ks = 0; ks < C / 16; ++ks)
+                    umma::mma_bf16(tmem, umma::smem_desc(ab + 2 * ks * P::LBO, P::LBO),
+                                   umma::smem_desc(wb + ks * 2 * LBO_B, LBO_B), idesc, n > 0 || ks > 0);
+                umma::commit(&bars.empty[st]);
+            }
+            umma::commit(&bars.acc_ready);
+        }
+    }
+    __syncthreads();
+    if (warp == 4) {
+        umma::fence_after_sync();
+        umma::tmem_dealloc(tmem, TCOLS);
+    }
+}
+
+// sr_tok[row] = LayerNorm(acc[row] + bias), in place on the fp32 accumulator (warp per row).
+template <int C>
+__global__ void sr_bias_ln_kernel(float* __restrict__ sr_tok, int64_t rows, const float* __restrict__ bias,
+                                  const float* __restrict__ gamma, const float* __restrict__ beta) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    constexpr int PER = C / 32;
+    float v[PER], s = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { v[i] = sr_tok[row * C + lane + 32 * i] + bias[lane + 32 * i]; s += v[i]; }
+    const float mean = warp_sum(s) * (1.f / C);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { v[i] -= mean; q += v[i] * v[i]; }
+    const float rstd = rsqrtf(warp_sum(q) * (1.f / C) + kLnEps);
+#pragma unroll
+    for (int i = 0; i < PER; ++i) sr_tok[row * C + lane + 32 * i] = v[i] * rstd * gamma[lane + 32 * i] + beta[lane + 32 * i];
+}
+
+template <int C>
+static int run_sr_conv_tc(const void* feat0, float* sr_tok, int B, int H, int W, int ws, const void* sr_tc,
+                          const float* sr_b, const float* g, const float* b, cudaStream_t st) {
+    using P = ChainTC<C>;
+    CFP_REQUIRE(sr_tc != nullptr, "sr conv: bf16 path needs the packed tensor-core weights (cfp_twins_w.sr_tc)");
+    const int nsx = W / ws, Ns = (H / ws) * nsx;
+    const int64_t rows = (int64_t)B * Ns;
+    if (rows == 0) return 0;
+    cudaError_t e = cudaMemsetAsync(sr_tok, 0, (size_t)rows * C * sizeof(float), st);
+    if (e != cudaSuccess) return fail("cudaMemsetAsync(sr accumulator): %s", cudaGetErrorString(e));
+    const int tiles = (int)((rows + 127) / 128), ntap = ws * ws;
+    int splits = (2 * 148 + tiles - 1) / tiles;                 // ~2 CTAs per SM
+    if (splits > ntap) splits = ntap;
+    const int taps_per_cta = (ntap + splits - 1) / splits;
+    splits = (ntap + taps_per_cta - 1) / taps_per_cta;
+    constexpr size_t smem = 2 * (size_t)P::KG * P::LBO + 2 * (size_t)P::SLOT;
+    auto k = sr_conv_tc_kernel<C>;
+    if (int err = set_smem(k, smem)) return err;
+    k<<<dim3(tiles, splits), 192, smem, st>>>((const bf16*)feat0, sr_tok, rows, H, W, ws, nsx, Ns, (const bf16*)sr_tc,
+                                               taps_per_cta);
+    if (int err = check_launch("sr_conv_tc")) return err;
+    sr_bias_ln_kernel<C><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(sr_tok, rows, sr_b, g, b);
+    return check_launch("sr_bias_ln");
+}
+
+int sr_conv_ln_tc(const void* feat0, float* sr_tok, int B, int H, int W, int C, int ws, const void* sr_tc,
+                  const float* sr_b, const float* g, const float* b, cudaStream_t st) {
+    if (C == 32) return run_sr_conv_tc<32>(feat0, sr_tok, B, H, W, ws, sr_tc, sr_b, g, b, st);
+    if (C == 64) return run_sr_conv_tc<64>(feat0, sr_tok, B, H, W, ws, sr_tc, sr_b, g, b, st);
+    if (C == 128) return run_sr_conv_tc<128>(feat0, sr_tok, B, H, W, ws, sr_tc, sr_b, g, b, st);
+    return fail("unsupported C=%d", C);
+}
+
 // ---- entry points used by k_loftr.cu's layer implementations (bf16 only)
 #define CFP_TC_DISPATCH(NH, ATTN, NAME)                                                  \
     if (C == 32) return run_query_tc<32, NH, ATTN>(NAME, q, w, kv, ksum, st);            \

@@ -231,7 +231,11 @@ static int d2i_impl(void* feat0, const void* emb, const void* zone_tok, const fl
     float *kv, *ksum;
     kv_ptrs<C, 4>(ws, L, groups, kv, ksum);
     ZoneTokSrc<T> src{(const T*)zone_tok, pos2, S, C, (int64_t)groups * S};
-    if (int e = run_kv_state<C, 4>("kv_state<hist2image>", src, groups, w.wkv_t, kv, ksum, st)) return e;
+    if constexpr (std::is_same<T, bf16>::value) {
+        if (int e = kv_tc_h2i(C, src, S, groups, w.kv_tc, kv, ksum, st)) return e;
+    } else {
+        if (int e = run_kv_state<C, 4>("kv_state<hist2image>", src, groups, w.wkv_t, kv, ksum, st)) return e;
+    }
     ZonePatchRows<T> q{(T*)feat0, (const T*)emb, (T*)(ws + L.canvas), mask, H, W, C, g.zone_num, g.p1, g.p2,
                        g.sy_wo, g.sx_wo, g.tzh, g.tzw, g.interpolate, assign, (int64_t)groups * g.p1 * g.p2};
     if constexpr (std::is_same<T, bf16>::value) {
@@ -257,7 +261,11 @@ static int dapm_impl(const void* feat0, void* msg_map, int B, int H, int W, cons
     kv_ptrs<C, 4>(ws, L, B, kv, ksum);
     if (Ni > 0) {
         InsideSrc<T> src{(const T*)feat0, H, W, C, g.ry0, g.rx0, rw, Ni, (int64_t)B * Ni};
-        if (int e = run_kv_state<C, 4>("kv_state<dapm>", src, B, w.wkv_t, kv, ksum, st)) return e;
+        if constexpr (std::is_same<T, bf16>::value) {
+            if (int e = kv_tc_dapm(C, src, Ni, B, w.kv_tc, kv, ksum, st)) return e;
+        } else {
+            if (int e = run_kv_state<C, 4>("kv_state<dapm>", src, B, w.wkv_t, kv, ksum, st)) return e;
+        }
     } else {
         cudaMemsetAsync(kv, 0, (size_t)B * (C * (C / 4) + C) * sizeof(float), st);
     }
@@ -276,7 +284,11 @@ static int twins_impl(void* feat0, int B, int H, int W, const cfp_twins_w& w, ch
     float *kv, *ksum;
     kv_ptrs<C, 8>(ws, L, groups, kv, ksum);
     WindowRows<T> win{(T*)feat0, H, W, C, wsz, nwx, nwin, (int64_t)groups * wsz * wsz};
-    if (int e = run_kv_state<C, 8>("kv_state<lsa>", win, groups, w.lsa.wkv_t, kv, ksum, st)) return e;
+    if constexpr (std::is_same<T, bf16>::value) {
+        if (int e = kv_tc_lsa(C, win, wsz * wsz, groups, w.lsa.kv_tc, kv, ksum, st)) return e;
+    } else {
+        if (int e = run_kv_state<C, 8>("kv_state<lsa>", win, groups, w.lsa.wkv_t, kv, ksum, st)) return e;
+    }
     if constexpr (std::is_same<T, bf16>::value) {
         if (int e = query_tc_lsa(C, win, w.lsa, kv, ksum, st)) return e;
     } else {
@@ -285,11 +297,18 @@ static int twins_impl(void* feat0, int B, int H, int W, const cfp_twins_w& w, ch
     // GSA (transformer.py:138-150): keys/values = LN(sr(x)), stride-ws conv without padding
     const int Ns = (H / wsz) * (W / wsz);
     float* sr_tok = reinterpret_cast<float*>(ws + L.sr);
-    if (int e = sr_conv_ln(feat0, sr_tok, B, H, W, C, wsz, w.sr_t, w.sr_b, w.srln_g, w.srln_b,
-                           sizeof(T) == 4 ? CFP_F32 : CFP_BF16, st)) return e;
+    if constexpr (std::is_same<T, bf16>::value) {
+        if (int e = sr_conv_ln_tc(feat0, sr_tok, B, H, W, C, wsz, w.sr_tc, w.sr_b, w.srln_g, w.srln_b, st)) return e;
+    } else {
+        if (int e = sr_conv_ln(feat0, sr_tok, B, H, W, C, wsz, w.sr_t, w.sr_b, w.srln_g, w.srln_b, CFP_F32, st)) return e;
+    }
     kv_ptrs<C, 8>(ws, L, B, kv, ksum);
     SrTokSrc src{sr_tok, Ns, C, (int64_t)B * Ns};
-    if (int e = run_kv_state<C, 8>("kv_state<gsa>", src, B, w.gsa.wkv_t, kv, ksum, st)) return e;
+    if constexpr (std::is_same<T, bf16>::value) {
+        if (int e = kv_tc_gsa(C, src, Ns, B, w.gsa.kv_tc, kv, ksum, st)) return e;
+    } else {
+        if (int e = run_kv_state<C, 8>("kv_state<gsa>", src, B, w.gsa.wkv_t, kv, ksum, st)) return e;
+    }
     FrameRows<T> fr{(T*)feat0, H * W, C, (int64_t)B * H * W};
     if constexpr (std::is_same<T, bf16>::value) return query_tc_gsa(C, fr, w.gsa, kv, ksum, st);
     else return run_query<C, 8, false>("loftr_query<gsa>", fr, w.gsa, kv, ksum, st);

@@ -177,5 +177,14 @@ int query_tc_gsa(int C, const FrameRows<bf16>& q, const cfp_loftr_w& w, const fl
                  cudaStream_t st);
 int query_tc_dapm(int C, const OutsideRows<bf16>& q, const cfp_loftr_w& w, const float* kv, const float* ksum,
                   cudaStream_t st);
+// attention state on tcgen05; S = rows per group
+int kv_tc_h2i(int C, const ZoneTokSrc<bf16>& src, int S, int groups, const void* wkv_tc, float* kv, float* ksum,
+              cudaStream_t st);
+int kv_tc_lsa(int C, const WindowRows<bf16>& src, int S, int groups, const void* wkv_tc, float* kv, float* ksum,
+              cudaStream_t st);
+int kv_tc_gsa(int C, const SrTokSrc& src, int S, int groups, const void* wkv_tc, float* kv, float* ksum,
+              cudaStream_t st);
+int kv_tc_dapm(int C, const InsideSrc<bf16>& src, int S, int groups, const void* wkv_tc, float* kv, float* ksum,
+               cudaStream_t st);
 
 }  // namespace cfp

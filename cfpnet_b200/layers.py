@@ -61,6 +61,7 @@ class LoFTREncoderLayer(nn.Module):
         t["tc"] = torch.stack([umma_block(b) for b in (
             self.q_proj.weight, self.merge.weight, w1[:C, :C], w1[:C, C:], w1[C:, :C], w1[C:, C:],
             w2[:, :C], w2[:, C:])]).contiguous()
+        t["kv_tc"] = torch.stack([umma_block(self.k_proj.weight), umma_block(self.v_proj.weight)]).contiguous()
         keep.extend(t.values())
         return _lib.CfpLoftrW(**{k: v.data_ptr() for k, v in t.items()})
 
@@ -112,7 +113,9 @@ class TwinsTransformer(nn.Module):
         sr_t = self.gsa.sr.weight.detach().float().permute(2, 3, 1, 0).reshape(ws * ws * C, C).contiguous()
         t = dict(sr_t=sr_t, sr_b=self.gsa.sr.bias.detach().float().contiguous(),
                  srln_g=self.gsa.norm.weight.detach().float().contiguous(),
-                 srln_b=self.gsa.norm.bias.detach().float().contiguous())
+                 srln_b=self.gsa.norm.bias.detach().float().contiguous(),
+                 sr_tc=torch.stack([umma_block(self.gsa.sr.weight[:, :, dy, dx])
+                                    for dy in range(ws) for dx in range(ws)]).contiguous())
         keep.extend(t.values())
         for k, v in t.items():
             setattr(w, k, v.data_ptr())
@@ -154,6 +157,7 @@ class LoFTREncoderLayer_newcross9(nn.Module):
             wq_t=linear_t(self.q_proj.weight),
             wkv_t=torch.cat([linear_t(self.k_proj.weight), linear_t(self.v_proj.weight)], dim=1).contiguous(),
             tc=umma_block(self.q_proj.weight),
+            kv_tc=torch.stack([umma_block(self.k_proj.weight), umma_block(self.v_proj.weight)]).contiguous(),
         )
         keep.extend(t.values())
         w.attn = _lib.CfpLoftrW(**{k: v.data_ptr() for k, v in t.items()})

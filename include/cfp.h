@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define CFP_ABI_VERSION 4
+#define CFP_ABI_VERSION 6
 
 #if defined(__GNUC__)
 #define CFP_API __attribute__((visibility("default")))
@@ -62,8 +62,8 @@ typedef struct cfp_loftr_w {
     /* bf16 tensor-core path: the chain's weights as eight [C x C] bf16 blocks in the canonical
      * K-major UMMA layout ([C/8][C][8] each), in consumption order: Wq, Wm, W1[:C,:C], W1[:C,C:],
      * W1[C:,:C], W1[C:,C:], W2[:,:C], W2[:,C:] (rows = outputs).  DAPM uses only the first block.
-     * Required for CFP_BF16. */
-    const void *tc;
+     * Required for CFP_BF16.  kv_tc: the k_proj and v_proj weights as two such blocks. */
+    const void *tc, *kv_tc;
 } cfp_loftr_w;
 
 /* DAPM convs (transformer.py:197-200, 239-244) with eval-mode BN folded:
@@ -95,6 +95,8 @@ typedef struct cfp_lkpm_w {
 typedef struct cfp_twins_w {
     cfp_loftr_w lsa, gsa;
     const float *sr_t, *sr_b, *srln_g, *srln_b;
+    /* bf16 tensor-core path: one [C x C] bf16 UMMA block per tap (dy*ws+dx) of the sr conv. */
+    const void *sr_tc;
     int32_t ws;
 } cfp_twins_w;
 

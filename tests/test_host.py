@@ -37,10 +37,10 @@ def test_library_exports_every_declared_symbol(lib):
 
 def test_ctypes_structs_match_header_layout():
     assert ctypes.sizeof(_lib.CfpGeom) == 16 * 4
-    assert ctypes.sizeof(_lib.CfpLoftrW) == 10 * 8
-    assert ctypes.sizeof(_lib.CfpDapmW) == 16 * 8
+    assert ctypes.sizeof(_lib.CfpLoftrW) == 11 * 8
+    assert ctypes.sizeof(_lib.CfpDapmW) == 17 * 8
     assert ctypes.sizeof(_lib.CfpLkpmW) == 10 * 8         # 9 pointers + int32 (+pad)
-    assert ctypes.sizeof(_lib.CfpTwinsW) == 20 * 8 + 4 * 8 + 8
+    assert ctypes.sizeof(_lib.CfpTwinsW) == 22 * 8 + 5 * 8 + 8
     assert ctypes.sizeof(_lib.CfpHistW) == 18 * 8
 
 
