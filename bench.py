@@ -52,34 +52,43 @@ def load_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons (B200_PROFILING.md).  The poller is started well before
+    the timed region (its NVML start-up perturbs the GPU for a few hundred ms); only the samples
+    that arrive between mark_begin() and mark_end() are summarised."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag, self.proc = index, [], False, None
+        self.index, self.samples, self.proc = index, [], None
+        self.t0 = self.t1 = None
 
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
-                if self.stop_flag:
-                    break
-                self.samples.append([v.strip() for v in line.split(",")])
+                self.samples.append((time.perf_counter(), [v.strip() for v in line.split(",")]))
         except Exception:
             pass
 
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
+
     def finish(self):
-        self.stop_flag = True
         if self.proc is not None:
             self.proc.terminate()
-        sm = [float(s[0]) for s in self.samples if len(s) >= 6 and s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if len(s) >= 6 and s[1].replace(".", "").isdigit()]
+        inside = [s for t, s in self.samples if self.t0 is not None and self.t0 <= t <= (self.t1 or t) + 0.06]
+        if not inside:      # region shorter than one polling period: take the nearest samples
+            inside = [s for _, s in self.samples[-2:]]
+        sm = [float(s[0]) for s in inside if len(s) >= 6 and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in inside if len(s) >= 6 and s[1].replace(".", "").isdigit()]
         reasons = set()
-        for s in self.samples:
+        for s in inside:
             if len(s) >= 6:
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[2:6]):
                     if v.lower().startswith("active"):
@@ -205,15 +214,24 @@ def run_cfp(a):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    sampler = ClockSampler(local) if rank == 0 else None
+    sampler_t = time.perf_counter()
+    if sampler:
+        sampler.start()
     with torch.no_grad():
         for i in range(a.warmup):
             outs = step(i)
         d2h = sum(o.numel() * o.element_size() for o in outs)
-        # ---- device-resident throughput ("value")
         barrier()
-        sampler = ClockSampler(local) if rank == 0 else None
+        if sampler:                         # let nvidia-smi finish its start-up before timing
+            while not sampler.samples and sampler.is_alive() and time.perf_counter() - sampler_t < 5.0:
+                time.sleep(0.05)
+            for i in range(2):
+                step(i)
+            barrier()
+        # ---- device-resident throughput ("value")
         if sampler:
-            sampler.start()
+            sampler.mark_begin()
         n0 = _lib.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -222,6 +240,8 @@ def run_cfp(a):
         e1.record()
         barrier()
         launches = _lib.launch_count() - n0
+        if sampler:
+            sampler.mark_end()
         ms_total = max_over_ranks(e0.elapsed_time(e1))
         clocks = sampler.finish() if sampler else None
 

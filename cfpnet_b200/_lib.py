@@ -18,7 +18,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcfp.so")
 
 CFP_F32, CFP_BF16 = 0, 1
-ABI_VERSION = 6
+ABI_VERSION = 7
 _fp = C.POINTER(C.c_float)
 
 
@@ -44,7 +44,7 @@ class CfpDapmW(C.Structure):
 
 class CfpLkpmW(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
-        "dw_t", "dw_shift", "ln_g", "ln_b", "pw1_t", "pw1_b", "pw2_t", "pw2_b", "tc")] + [("ksize", C.c_int32)]
+        "dw_t", "dw_shift", "ln_g", "ln_b", "pw1_t", "pw1_b", "pw2_t", "pw2_b", "tc", "dw_toep")] + [("ksize", C.c_int32)]
 
 
 class CfpTwinsW(C.Structure):
@@ -61,7 +61,7 @@ _i, _p, _sz, _i64 = C.c_int, C.c_void_p, C.c_size_t, C.c_int64
 SIGNATURES = {
     "cfp_version": (_i, []),
     "cfp_last_error": (C.c_char_p, []),
-    "cfp_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, C.POINTER(CfpGeom)]),
+    "cfp_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i, C.POINTER(CfpGeom)]),
     "cfp_hist_encoder_fwd": (_i, [_p, _p, _p, _p, _i64, C.POINTER(CfpHistW), _i, _p]),
     "cfp_zone_masks": (_i, [_p, _p, _p, _p, _i, _i, _i, C.POINTER(CfpGeom), _p]),
     "cfp_posenc_tokens_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),

@@ -60,7 +60,7 @@ int check_launch(const char* what) {
 
 static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
-WsLayout ws_layout(int B, int H, int W, int C, int ws, int dtype, const cfp_geom* g) {
+WsLayout ws_layout(int B, int H, int W, int C, int ws, int large_kernel, int dtype, const cfp_geom* g) {
     WsLayout L{};
     const size_t es = elem_size(dtype);
     const int Z = g ? g->zone_num * g->zone_num : 64;
@@ -80,6 +80,9 @@ WsLayout ws_layout(int B, int H, int W, int C, int ws, int dtype, const cfp_geom
     L.canvas = off;
     L.canvas_bytes = (g && g->interpolate) ? align256((size_t)B * Z * g->p1 * g->p2 * C * es) : 0;
     off += L.canvas_bytes;
+    L.planes = off;
+    L.planes_bytes = (dtype == CFP_BF16 && large_kernel > 0) ? align256(dwconv_tc_plane_bytes(B, H, W, C, large_kernel)) : 0;
+    off += L.planes_bytes;
     L.total = off;
     return L;
 }
@@ -110,8 +113,8 @@ extern "C" {
 CFP_API int cfp_version(void) { return CFP_ABI_VERSION; }
 CFP_API const char* cfp_last_error(void) { return tls_error().msg; }
 
-CFP_API size_t cfp_workspace_bytes(int B, int H, int W, int C, int ws, int dtype, const cfp_geom* g) {
-    return ws_layout(B, H, W, C, ws, dtype, g).total;
+CFP_API size_t cfp_workspace_bytes(int B, int H, int W, int C, int ws, int large_kernel, int dtype, const cfp_geom* g) {
+    return ws_layout(B, H, W, C, ws, large_kernel, dtype, g).total;
 }
 
 CFP_API int cfp_hist_encoder_fwd(const float* hist, void* out32, void* out64, void* out128, int64_t rows,
@@ -163,7 +166,7 @@ CFP_API int cfp_d2i_fwd(void* feat0, const void* emb, const void* zone_tok, cons
     const int bot = g->ey_wo > H ? g->ey_wo - H : 0, right = g->ex_wo > W ? g->ex_wo - W : 0;
     CFP_REQUIRE(g->tzh - top - bot == g->ry1 - g->ry0 && g->tzw - left - right == g->rx1 - g->rx0,
                 "zone canvas does not match the zone rectangle (the reference's index_put fails here too)");
-    WsLayout L = ws_layout(B, H, W, C, 0, dtype, g);
+    WsLayout L = ws_layout(B, H, W, C, 0, 0, dtype, g);
     CFP_REQUIRE(workspace_bytes >= L.total, "workspace too small: %zu < %zu", workspace_bytes, L.total);
     return d2i(feat0, emb, zone_tok, pos2, mask, B, H, W, C, S, *g, *w, assign, (char*)workspace, L, dtype,
                (cudaStream_t)stream);
@@ -176,7 +179,7 @@ CFP_API int cfp_dapm_fwd(void* feat0, int B, int H, int W, int C, const cfp_geom
     if (int e = check_geom(g, H, W)) return e;
     CFP_REQUIRE(w && workspace, "null pointer");
     CFP_REQUIRE(B <= 65535, "B too large for grid.z");
-    WsLayout L = ws_layout(B, H, W, C, 0, dtype, g);
+    WsLayout L = ws_layout(B, H, W, C, 0, 0, dtype, g);
     CFP_REQUIRE(workspace_bytes >= L.kv_bytes + 2 * L.tok_bytes, "workspace too small: %zu < %zu", workspace_bytes,
                 L.kv_bytes + 2 * L.tok_bytes);
     char* ws = (char*)workspace;
@@ -200,13 +203,20 @@ CFP_API int cfp_lkpm_fwd(void* feat0, int B, int H, int W, int C, const cfp_lkpm
     begin_call(stream);
     if (int e = check_common(feat0, B, H, W, C, dtype)) return e;
     CFP_REQUIRE(w && workspace, "null pointer");
-    WsLayout L = ws_layout(B, H, W, C, 0, dtype, nullptr);
-    CFP_REQUIRE(workspace_bytes >= L.kv_bytes + L.tok_bytes, "workspace too small");
+    WsLayout L = ws_layout(B, H, W, C, 0, w->ksize, dtype, nullptr);
+    CFP_REQUIRE(workspace_bytes >= L.total, "workspace too small: %zu < %zu", workspace_bytes, L.total);
     char* ws = (char*)workspace;
     cudaStream_t st = (cudaStream_t)stream;
     void* y = ws + L.tok_a;
+    if (dtype == CFP_BF16) {
+        if (w->ksize >= 15) {      // Toeplitz GEMM on the tensor pipe (k_dwconv_tc.cu)
+            if (int e = dwconv_tc(feat0, y, B, H, W, C, w->ksize, w->dw_toep, w->dw_shift, ws + L.planes, st)) return e;
+        } else {
+            if (int e = dwconv_bn_relu(feat0, y, B, H, W, C, w->ksize, w->dw_t, w->dw_shift, dtype, st)) return e;
+        }
+        return lkpm_mlp_tc(feat0, y, (int64_t)B * H * W, C, *w, st);
+    }
     if (int e = dwconv_bn_relu(feat0, y, B, H, W, C, w->ksize, w->dw_t, w->dw_shift, dtype, st)) return e;
-    if (dtype == CFP_BF16) return lkpm_mlp_tc(feat0, y, (int64_t)B * H * W, C, *w, st);
     return lkpm_mlp(feat0, y, (int64_t)B * H * W, C, *w, dtype, st);
 }
 
@@ -217,7 +227,7 @@ CFP_API int cfp_twins_fwd(void* feat0, int B, int H, int W, int C, const cfp_twi
     CFP_REQUIRE(w && workspace, "null pointer");
     CFP_REQUIRE(w->ws > 1, "window size must be > 1 (transformer.py:79)");
     CFP_REQUIRE(C % 8 == 0, "dim %d should be divided by num_heads 8 (transformer.py:81)", C);
-    WsLayout L = ws_layout(B, H, W, C, w->ws, dtype, nullptr);
+    WsLayout L = ws_layout(B, H, W, C, w->ws, 0, dtype, nullptr);
     CFP_REQUIRE(workspace_bytes >= L.total, "workspace too small: %zu < %zu", workspace_bytes, L.total);
     return twins(feat0, B, H, W, C, *w, (char*)workspace, L, dtype, (cudaStream_t)stream);
 }

@@ -14,9 +14,10 @@ struct WsLayout {
     size_t tok_bytes;
     size_t sr, sr_bytes;        // GSA sub-sampled tokens, fp32 [B][Ns][C]
     size_t canvas, canvas_bytes;  // hist2image resize branch: [B][zn*p1*zn*p2][C] activation dtype
+    size_t planes, planes_bytes;  // bf16 LKPM: padded channel planes (UMMA layout) + planar output
     size_t total;
 };
-WsLayout ws_layout(int B, int H, int W, int C, int ws, int dtype, const cfp_geom* g);
+WsLayout ws_layout(int B, int H, int W, int C, int ws, int large_kernel, int dtype, const cfp_geom* g);
 
 inline size_t elem_size(int dtype) { return dtype == CFP_F32 ? 4 : 2; }
 
@@ -63,6 +64,11 @@ int conv3x3_tc(const void* in0, const void* in1, const void* wpk, const float* s
 int lkpm_mlp_tc(void* feat0, const void* y, int64_t rows, int C, const cfp_lkpm_w& w, cudaStream_t st);
 int sr_conv_ln_tc(const void* feat0, float* sr_tok, int B, int H, int W, int C, int ws, const void* sr_tc,
                   const float* sr_b, const float* g, const float* b, cudaStream_t st);
+
+// k_dwconv_tc.cu  (bf16, tcgen05)
+size_t dwconv_tc_plane_bytes(int B, int H, int W, int C, int K);
+int dwconv_tc(const void* in, void* out, int B, int H, int W, int C, int K, const void* toep, const float* shift,
+              char* plane_ws, cudaStream_t st);
 
 // k_selftest.cu
 int umma_selftest(const void* A, const void* B, float* D, int rows_a, int N, int K, int row_shift, cudaStream_t st);

@@ -1,0 +1,252 @@
+// LKPM large-kernel depthwise convolution on the tensor cores (bf16 path).
+//
+//   y[b][r][x][c] = ReLU( sum_{dy,dx} w[c][dy][dx] * in[b][r+dy-p][x+dx-p][c] + shift[c] ),  p = (k-1)/2
+//                                                                   (convnext.py:45-47, BN folded)
+//
+// As a direct stencil the 31x31 case is bound by the fp32 FMA pipe (961 FMA per output).
+// Here each channel plane is a GEMM instead: for one channel and one tile of 32 output columns
+//
+//   D[r][n] = sum_dy sum_kk  A_dy[r][kk] * T_dy[n][kk],     A_dy[r][kk] = plane[r + dy][x0 + kk]
+//                                                            T_dy[n][kk] = w[dy][kk - n]  (0 outside the band)
+//
+// i.e. one M=128 (rows) x N=32 (columns) x K=16 tcgen05.mma per (dy, 16-column slice): the banded
+// Toeplitz matrix T_dy carries the horizontal taps, the vertical tap dy is just a row shift of the A
+// view (start address + 16 B * dy in the canonical K-major layout, umma.cuh).  About half of every
+// T_dy is structural zeros; the tensor pipe is still ~10x faster than the FMA pipe on this op.
+//
+// Data flow: dw_plane_pack_kernel rewrites the token-major map into zero-padded channel planes stored
+// directly in the UMMA layout ([b][c][x-group][padded row][8 columns]), so that the A operand of a
+// (frame, channel, column tile) is ONE contiguous block brought in by a single bulk (TMA) copy.
+// dwconv_tc_kernel: CTA = (column tile, channel); the channel's K Toeplitz blocks (host-packed) stay
+// resident in shared memory while the CTA walks over the frames with a 3-stage A ring and two TMEM
+// accumulators (MMA of frame i+1 overlaps the epilogue of frame i).  The epilogue writes planar
+// rows; dw_plane_unpack_kernel transposes back to token-major for the pointwise MLP.
+#include "cfp_common.cuh"
+#include "cfp_internal.h"
+#include "umma.cuh"
+
+namespace cfp {
+
+struct DwGeom {
+    int H, W, C, K, PAD;
+    int nM;        // 128-row blocks
+    int HP;        // padded plane rows      = nM*128 + K - 1
+    int KS;        // 16-column K-steps per dy = ceil((32 + K - 1) / 16)
+    int nX;        // 32-column output tiles
+    int WG;        // 8-column groups per plane = 4*nX + 2*KS - 4
+};
+static DwGeom dw_geom(int H, int W, int C, int K) {
+    DwGeom g;
+    g.H = H; g.W = W; g.C = C; g.K = K; g.PAD = (K - 1) / 2;
+    g.nM = (H + 127) / 128;
+    g.HP = g.nM * 128 + K - 1;
+    g.KS = (32 + K - 1 + 15) / 16;
+    g.nX = (W + 31) / 32;
+    g.WG = 4 * g.nX + 2 * g.KS - 4;
+    return g;
+}
+size_t dwconv_tc_plane_bytes(int B, int H, int W, int C, int K) {
+    DwGeom g = dw_geom(H, W, C, K);
+    const size_t in_bytes = (size_t)B * C * g.WG * g.HP * 16;
+    const size_t out_bytes = (size_t)B * C * H * W * 2;
+    return ((in_bytes + 255) & ~(size_t)255) + ((out_bytes + 255) & ~(size_t)255);
+}
+
+// ---------------------------------------------------------------- token-major -> padded planes
+// CTA = (frame, 8 consecutive image rows): coalesced read of the [8][W][C] slab, transpose through
+// shared memory, then each thread emits 16-byte chunks (8 columns of one channel, one padded row);
+// 8 consecutive rows of one (channel, x-group) are 128 contiguous bytes of the plane.
+__global__ void __launch_bounds__(256) dw_plane_pack_kernel(const bf16* __restrict__ in, bf16* __restrict__ planes, DwGeom g) {
+    extern __shared__ __align__(16) uint16_t slab[];          // [8 rows][W][C + 2]  (pad: conflict-free column reads)
+    const int b = blockIdx.y, y0 = blockIdx.x * 8;
+    const int C = g.C, W = g.W, LDC = C + 2;
+    const uint16_t* src = reinterpret_cast<const uint16_t*>(in) + ((size_t)b * g.H + y0) * W * C;
+    const int rows = min(8, g.H - y0);
+    for (int i = threadIdx.x; i < rows * W * (C / 2); i += 256) {       // 4-byte granules
+        const int pix = i / (C / 2), c2 = i % (C / 2);
+        const uint32_t v = reinterpret_cast<const uint32_t*>(src)[(size_t)pix * (C / 2) + c2];
+        slab[pix * LDC + 2 * c2] = (uint16_t)(v & 0xffffu);
+        slab[pix * LDC + 2 * c2 + 1] = (uint16_t)(v >> 16);
+    }
+    __syncthreads();
+    // chunks: (c, xg, r) with r fastest so that a warp writes 4 x 128 contiguous bytes
+    const int xg_lo = g.PAD / 8, xg_hi = (g.PAD + W - 1) / 8;          // x-groups that contain image columns
+    const int nxg = xg_hi - xg_lo + 1;
+    for (int i = threadIdx.x; i < C * nxg * 8; i += 256) {
+        const int r = i & 7, xg = xg_lo + (i >> 3) % nxg, c = (i >> 3) / nxg;
+        if (r >= rows) continue;
+        uint16_t v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int x = xg * 8 + j - g.PAD;
+            v[j] = (x >= 0 && x < W) ? slab[(r * W + x) * LDC + c] : (uint16_t)0;
+        }
+        uint4 u;
+        u.x = v[0] | ((uint32_t)v[1] << 16); u.y = v[2] | ((uint32_t)v[3] << 16);
+        u.z = v[4] | ((uint32_t)v[5] << 16); u.w = v[6] | ((uint32_t)v[7] << 16);
+        const size_t off = ((((size_t)b * C + c) * g.WG + xg) * g.HP + (y0 + r + g.PAD)) * 8;
+        *reinterpret_cast<uint4*>(planes + off) = u;
+    }
+}
+
+// ---------------------------------------------------------------- planar rows -> token-major
+__global__ void __launch_bounds__(256) dw_plane_unpack_kernel(const bf16* __restrict__ planar, bf16* __restrict__ out, int H,
+                                                              int W, int C) {
+    __shared__ uint16_t tile[32][34];
+    const int b = blockIdx.z, n0 = blockIdx.x * 32, c0 = blockIdx.y * 32, N = H * W;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const uint16_t* src = reinterpret_cast<const uint16_t*>(planar);
+    uint16_t* dst = reinterpret_cast<uint16_t*>(out);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = c0 + ty + 8 * i, n = n0 + tx;
+        if (c < C && n < N) tile[ty + 8 * i][tx] = src[((size_t)b * C + c) * N + n];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int n = n0 + ty + 8 * i, c = c0 + tx;
+        if (c < C && n < N) dst[((size_t)b * N + n) * C + c] = tile[tx][ty + 8 * i];
+    }
+}
+
+// ---------------------------------------------------------------- the Toeplitz GEMM
+struct DwBars {
+    uint64_t t_full, a_full[3], a_empty[3], acc_full[2], acc_empty[2];
+    uint32_t tmem_slot;
+};
+
+__global__ void __launch_bounds__(192) dwconv_tc_kernel(const bf16* __restrict__ planes, const bf16* __restrict__ toep,
+                                                        const float* __restrict__ shift, bf16* __restrict__ planar_out,
+                                                        int B, DwGeom g) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ DwBars bars;
+    const int xt = blockIdx.x, c = blockIdx.y;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t t_blk = 2 * g.KS * 32 * 16;                 // bytes of one T_dy block  [2*KS groups][32][8]
+    const uint32_t t_bytes = g.K * t_blk;
+    const uint32_t lbo_a = g.HP * 16;
+    const uint32_t a_bytes = 2 * g.KS * lbo_a;
+    uint8_t* t_sm = smem;
+    uint8_t* a_sm = smem + ((t_bytes + 127) & ~127u);          // [3][a_bytes]
+    const uint32_t a_stride = (a_bytes + 127) & ~127u;
+    const int niter = B * g.nM;
+
+    if (tid == 0) {
+        umma::mbar_init(&bars.t_full, 1);
+        for (int i = 0; i < 3; ++i) { umma::mbar_init(&bars.a_full[i], 1); umma::mbar_init(&bars.a_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { umma::mbar_init(&bars.acc_full[i], 1); umma::mbar_init(&bars.acc_empty[i], 128); }
+        umma::fence_mbar_init();
+    }
+    if (warp == 4) umma::tmem_alloc(&bars.tmem_slot, 64);
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = bars.tmem_slot;
+
+    if (warp < 4) {
+        // ---------------- epilogue: thread = output row, 32 columns
+        const float sh = shift[c];
+        for (int it = 0; it < niter; ++it) {
+            const int ab = it & 1, b = it / g.nM, mt = it % g.nM;
+            umma::mbar_wait(&bars.acc_full[ab], (it >> 1) & 1);
+            umma::fence_after_sync();
+            float v[32];
+            umma::tmem_ld16(umma::tmem_addr(tmem, warp * 32, ab * 32), *reinterpret_cast<float(*)[16]>(&v[0]));
+            umma::tmem_ld16(umma::tmem_addr(tmem, warp * 32, ab * 32 + 16), *reinterpret_cast<float(*)[16]>(&v[16]));
+            umma::fence_before_sync();
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(umma::smem_u32(&bars.acc_empty[ab])) : "memory");
+            const int y = mt * 128 + tid, x0 = xt * 32;
+            if (y < g.H) {
+                bf16* dst = planar_out + (((size_t)b * g.C + c) * g.H + y) * g.W + x0;
+                const bool aligned = (((size_t)(dst - planar_out)) & 7) == 0;
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    if (x0 + j + 8 <= g.W && aligned) {
+                        uint4 u;
+                        u.x = umma::pack_bf16(fmaxf(v[j + 0] + sh, 0.f), fmaxf(v[j + 1] + sh, 0.f));
+                        u.y = umma::pack_bf16(fmaxf(v[j + 2] + sh, 0.f), fmaxf(v[j + 3] + sh, 0.f));
+                        u.z = umma::pack_bf16(fmaxf(v[j + 4] + sh, 0.f), fmaxf(v[j + 5] + sh, 0.f));
+                        u.w = umma::pack_bf16(fmaxf(v[j + 6] + sh, 0.f), fmaxf(v[j + 7] + sh, 0.f));
+                        *reinterpret_cast<uint4*>(dst + j) = u;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            if (x0 + j + i < g.W) dst[j + i] = __float2bfloat16_rn(fmaxf(v[j + i] + sh, 0.f));
+                    }
+                }
+            }
+        }
+    } else if (warp == 4) {
+        // ---------------- producer: Toeplitz blocks once, then one bulk copy per (frame, row block)
+        if (lane == 0) {
+            umma::mbar_expect_tx(&bars.t_full, t_bytes);
+            umma::bulk_g2s(t_sm, toep + (size_t)c * g.K * (t_blk / 2), t_bytes, &bars.t_full);
+            for (int it = 0; it < niter; ++it) {
+                const int s = it % 3, b = it / g.nM;
+                if (it >= 3) umma::mbar_wait(&bars.a_empty[s], ((it / 3) - 1) & 1);
+                const bf16* src = planes + ((((size_t)b * g.C + c) * g.WG + 4 * xt) * g.HP) * 8;
+                umma::mbar_expect_tx(&bars.a_full[s], a_bytes);
+                umma::bulk_g2s(a_sm + (size_t)s * a_stride, src, a_bytes, &bars.a_full[s]);
+            }
+        }
+    } else {
+        // ---------------- MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = umma::idesc_bf16(128, 32);
+            const uint32_t ts = umma::smem_u32(t_sm), as0 = umma::smem_u32(a_sm);
+            umma::mbar_wait(&bars.t_full, 0);
+            for (int it = 0; it < niter; ++it) {
+                const int s = it % 3, ab = it & 1, mt = it % g.nM;
+                umma::mbar_wait(&bars.a_full[s], (it / 3) & 1);
+                if (it >= 2) umma::mbar_wait(&bars.acc_empty[ab], ((it >> 1) - 1) & 1);
+                umma::fence_after_sync();
+                const uint32_t ab0 = as0 + s * a_stride + (uint32_t)(mt * 128) * 16;
+                for (int dy = 0; dy < g.K; ++dy) {
+                    const uint32_t tb = ts + dy * t_blk;
+                    for (int j = 0; j < g.KS; ++j)
+                        umma::mma_bf16(tmem + ab * 32, umma::smem_desc(ab0 + dy * 16 + 2 * j * lbo_a, lbo_a),
+                                       umma::smem_desc(tb + 2 * j * 512, 512), idesc, (dy | j) != 0);
+                }
+                umma::commit(&bars.a_empty[s]);
+                umma::commit(&bars.acc_full[ab]);
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 4) {
+        umma::fence_after_sync();
+        umma::tmem_dealloc(tmem, 64);
+    }
+}
+
+int dwconv_tc(const void* in, void* out, int B, int H, int W, int C, int K, const void* toep, const float* shift,
+              char* plane_ws, cudaStream_t st) {
+    CFP_REQUIRE(toep != nullptr, "dwconv: bf16 path needs the packed Toeplitz blocks (cfp_lkpm_w.dw_toep)");
+    CFP_REQUIRE(B <= 65535 && C <= 65535, "grid limits");
+    DwGeom g = dw_geom(H, W, C, K);
+    const size_t in_bytes = ((size_t)B * C * g.WG * g.HP * 16 + 255) & ~(size_t)255;
+    bf16* planes = reinterpret_cast<bf16*>(plane_ws);
+    bf16* planar_out = reinterpret_cast<bf16*>(plane_ws + in_bytes);
+    cudaError_t e = cudaMemsetAsync(planes, 0, in_bytes, st);           // zero padding of the planes
+    if (e != cudaSuccess) return fail("cudaMemsetAsync(planes): %s", cudaGetErrorString(e));
+    {
+        const size_t smem = (size_t)8 * W * (C + 2) * 2;
+        CFP_REQUIRE(smem <= 200 * 1024, "dw_plane_pack: %zu B shared memory", smem);
+        if (int err = set_smem(dw_plane_pack_kernel, smem)) return err;
+        dw_plane_pack_kernel<<<dim3((H + 7) / 8, B), 256, smem, st>>>((const bf16*)in, planes, g);
+        if (int err = check_launch("dw_plane_pack")) return err;
+    }
+    {
+        const uint32_t t_bytes = g.K * 2 * g.KS * 32 * 16, a_bytes = 2 * g.KS * g.HP * 16;
+        const size_t smem = ((t_bytes + 127) & ~127u) + 3 * (size_t)((a_bytes + 127) & ~127u);
+        CFP_REQUIRE(smem <= 225 * 1024, "dwconv (tensor-core path): %zu B shared memory (H=%d too tall)", smem, H);
+        if (int err = set_smem(dwconv_tc_kernel, smem)) return err;
+        dwconv_tc_kernel<<<dim3(g.nX, C), 192, smem, st>>>(planes, (const bf16*)toep, shift, planar_out, B, g);
+        if (int err = check_launch(K == 31 ? "dwconv_tc<31>" : K == 15 ? "dwconv_tc<15>" : "dwconv_tc<7>")) return err;
+    }
+    dw_plane_unpack_kernel<<<dim3((H * W + 31) / 32, (C + 31) / 32, B), 256, 0, st>>>(planar_out, (bf16*)out, H, W, C);
+    return check_launch("dw_plane_unpack");
+}
+
+}  // namespace cfp

@@ -30,6 +30,7 @@ class TransformerFusion(nn.Module):
         self.zone_sample_num = args.zone_sample_num
         self.max_resolution = max_resolution
         self.embedding_dim = embedding_dim
+        self.large_kernel = large_kernel if "combine1" in args.attention_layer else 0
         self.positional_encodings = nn.Parameter(
             torch.rand(max_resolution[0] * max_resolution[1], embedding_dim), requires_grad=True)
         self.positional_encodings2 = nn.Parameter(
@@ -104,7 +105,7 @@ class TransformerFusion(nn.Module):
         st = None
         with torch.cuda.device(dev):
             lib = _lib.load()
-            ws_bytes = lib.cfp_workspace_bytes(B, H, W, D, self.ws, code, C.byref(cg))
+            ws_bytes = lib.cfp_workspace_bytes(B, H, W, D, self.ws, self.large_kernel or 0, code, C.byref(cg))
             work = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
             feat0 = torch.empty(B, H * W, D, device=dev, dtype=dt)
             st = _lib.stream_ptr()

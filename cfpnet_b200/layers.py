@@ -229,6 +229,14 @@ class Block14(nn.Module):
         for j in range(4):
             blocks += [umma_block(w1[j * C:(j + 1) * C, :]), umma_block(w2[:, j * C:(j + 1) * C])]
         t["tc"] = torch.stack(blocks).contiguous()
+        # banded-Toeplitz blocks of the depthwise taps for the tensor-core path (csrc/k_dwconv_tc.cu)
+        ks = (32 + k - 1 + 15) // 16
+        n = torch.arange(32, device=taps.device)[:, None]
+        kk = torch.arange(16 * ks, device=taps.device)[None, :]
+        dx = kk - n
+        band = ((dx >= 0) & (dx < k)).to(taps.dtype)
+        toep = taps[:, :, dx.clamp(0, k - 1)] * band                      # [C, k(dy), 32, 16*ks]
+        t["dw_toep"] = (toep.to(torch.bfloat16).view(C, k, 32, 2 * ks, 8).permute(0, 1, 3, 2, 4).contiguous())
         keep.extend(t.values())
         w = _lib.CfpLkpmW(**{n: v.data_ptr() for n, v in t.items()})
         w.ksize = k

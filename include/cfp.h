@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define CFP_ABI_VERSION 6
+#define CFP_ABI_VERSION 7
 
 #if defined(__GNUC__)
 #define CFP_API __attribute__((visibility("default")))
@@ -87,6 +87,11 @@ typedef struct cfp_lkpm_w {
      * consumption order W1_0, W2_0, ..., W1_3, W2_3 with W1_j = pwconv1.weight[jC:(j+1)C, :] and
      * W2_j = pwconv2.weight[:, jC:(j+1)C].  Required for CFP_BF16. */
     const void *tc;
+    /* bf16 tensor-core depthwise conv: per (channel, dy) one banded-Toeplitz block
+     * T[n][kk] = dw_t-tap(dy, kk-n) (0 outside 0 <= kk-n < k), n < 32, kk < 16*KS,
+     * KS = ceil((31+k)/16), stored as a bf16 UMMA block [2*KS][32][8]; order [C][k].
+     * Required for CFP_BF16 when k >= 15. */
+    const void *dw_toep;
     int32_t ksize;
 } cfp_lkpm_w;
 
@@ -113,7 +118,8 @@ CFP_API const char *cfp_last_error(void);
 
 /* Scratch bytes (fp32 attention state + token scratch) one fusion call needs;
  * the caller allocates it (torch.empty) and passes it to the layer calls. */
-CFP_API size_t cfp_workspace_bytes(int B, int H, int W, int C, int ws, int dtype, const cfp_geom *g);
+CFP_API size_t cfp_workspace_bytes(int B, int H, int W, int C, int ws, int large_kernel, int dtype,
+                                   const cfp_geom *g);
 
 /* a1. HistogramEncoder.forward (encoder.py:45-50; deltar.py:40).
  * hist [rows] fp32 zone depth samples (rows = B*Z*S) -> out32 [rows][32],

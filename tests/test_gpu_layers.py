@@ -35,7 +35,7 @@ def layer_call(m, name, layer_idx, feat0, geom_name="G416", level=3, mask=None, 
     code = _lib.dtype_code(feat0.dtype)
     packed, pos, pos2, _keep = m._cache.get(m._pack)
     lib = _lib.load()
-    nbytes = lib.cfp_workspace_bytes(B, H, W, C, m.ws, code, ctypes.byref(cg))
+    nbytes = lib.cfp_workspace_bytes(B, H, W, C, m.ws, m.large_kernel, code, ctypes.byref(cg))
     work = torch.empty(nbytes, device=DEV, dtype=torch.uint8)
     x = feat0.clone()
     st = _lib.stream_ptr()

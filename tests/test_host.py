@@ -39,16 +39,16 @@ def test_ctypes_structs_match_header_layout():
     assert ctypes.sizeof(_lib.CfpGeom) == 16 * 4
     assert ctypes.sizeof(_lib.CfpLoftrW) == 11 * 8
     assert ctypes.sizeof(_lib.CfpDapmW) == 17 * 8
-    assert ctypes.sizeof(_lib.CfpLkpmW) == 10 * 8         # 9 pointers + int32 (+pad)
+    assert ctypes.sizeof(_lib.CfpLkpmW) == 11 * 8         # 10 pointers + int32 (+pad)
     assert ctypes.sizeof(_lib.CfpTwinsW) == 22 * 8 + 5 * 8 + 8
     assert ctypes.sizeof(_lib.CfpHistW) == 18 * 8
 
 
 def test_workspace_bytes_is_pure_host_arithmetic(lib):
     g = _lib.CfpGeom(zone_num=8, p1=3, p2=3, tzh=24, tzw=24, ry1=24, rx1=24)
-    small = lib.cfp_workspace_bytes(1, 26, 34, 128, 6, _lib.CFP_F32, ctypes.byref(g))
-    big = lib.cfp_workspace_bytes(4, 26, 34, 128, 6, _lib.CFP_F32, ctypes.byref(g))
-    half = lib.cfp_workspace_bytes(4, 26, 34, 128, 6, _lib.CFP_BF16, ctypes.byref(g))
+    small = lib.cfp_workspace_bytes(1, 26, 34, 128, 6, 7, _lib.CFP_F32, ctypes.byref(g))
+    big = lib.cfp_workspace_bytes(4, 26, 34, 128, 6, 7, _lib.CFP_F32, ctypes.byref(g))
+    half = lib.cfp_workspace_bytes(4, 26, 34, 128, 6, 0, _lib.CFP_BF16, ctypes.byref(g))
     assert 0 < small < big and half < big
 
 
