@@ -263,11 +263,14 @@ __global__ void __launch_bounds__(192) loftr_query_tc_kernel(Q q, cfp_loftr_w w,
                 const int slot = cc % P::NSLOT, round = cc / P::NSLOT;
                 umma::mbar_wait(&bars.full[slot], round & 1);
                 umma::fence_after_sync();
-                const uint32_t wb = rs + slot * P::SLOT;
+                uint64_t ad = umma::smem_desc(abase + kg0 * P::LBO, P::LBO);
+                uint64_t wd = umma::smem_desc(rs + slot * P::SLOT, LBO_B);
 #pragma unroll
-                for (int ks = 0; ks < C / 16; ++ks)
-                    umma::mma_bf16(tmem + dcol, umma::smem_desc(abase + (kg0 + 2 * ks) * P::LBO, P::LBO),
-                                   umma::smem_desc(wb + ks * 2 * LBO_B, LBO_B), idesc, acc_first || ks > 0);
+                for (int ks = 0; ks < C / 16; ++ks) {
+                    umma::mma_bf16(tmem + dcol, ad, wd, idesc, acc_first || ks > 0);
+                    ad = umma::desc_advance(ad, 2 * P::LBO);
+                    wd = umma::desc_advance(wd, 2 * LBO_B);
+                }
                 umma::commit(&bars.empty[slot]);
                 ++cc;
             };
@@ -452,11 +455,14 @@ __global__ void __launch_bounds__(192) lkpm_mlp_tc_kernel(bf16* __restrict__ fea
                 const int slot = cc % P::NSLOT, round = cc / P::NSLOT;
                 umma::mbar_wait(&bars.full[slot], round & 1);
                 umma::fence_after_sync();
-                const uint32_t wb = rs + slot * P::SLOT;
+                uint64_t ad = umma::smem_desc(abase, P::LBO);
+                uint64_t wd = umma::smem_desc(rs + slot * P::SLOT, LBO_B);
 #pragma unroll
-                for (int ks = 0; ks < C / 16; ++ks)
-                    umma::mma_bf16(tmem + dcol, umma::smem_desc(abase + 2 * ks * P::LBO, P::LBO),
-                                   umma::smem_desc(wb + ks * 2 * LBO_B, LBO_B), idesc, acc_first || ks > 0);
+                for (int ks = 0; ks < C / 16; ++ks) {
+                    umma::mma_bf16(tmem + dcol, ad, wd, idesc, acc_first || ks > 0);
+                    ad = umma::desc_advance(ad, 2 * P::LBO);
+                    wd = umma::desc_advance(wd, 2 * LBO_B);
+                }
                 umma::commit(&bars.empty[slot]);
                 ++cc;
             };

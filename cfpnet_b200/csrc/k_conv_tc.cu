@@ -44,8 +44,8 @@ __global__ void __launch_bounds__(192) conv3x3_tc_kernel(const bf16* __restrict_
                                                          const bf16* __restrict__ wpk,
                                                          const float* __restrict__ shift,
                                                          const bf16* __restrict__ residual, bf16* __restrict__ out,
-                                                         int H, int W, int R, int cells, int zy0, int zy1, int zx0,
-                                                         int zx1) {
+                                                         int H, int W, int R, int cells, unsigned wp_magic, int zy0,
+                                                         int zy1, int zx0, int zx1) {
     using P = ConvTC<C>;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ ConvTCBars bars;
@@ -76,18 +76,30 @@ __global__ void __launch_bounds__(192) conv3x3_tc_kernel(const bf16* __restrict_
         for (int s = 0; s < nsrc; ++s) {
             if (s > 0) umma::mbar_wait(&bars.a_free, 0);    // all MMAs reading source 0 have completed
             const bf16* src = s == 0 ? in0 : in1;
-            for (int i = tid; i < cells * P::KG; i += 128) {
-                const int ci = i / P::KG, kg = i % P::KG;
-                const int idx = ci - 1;                     // one slack cell in front (tap dx=0 of cell 0)
-                uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                if (idx >= 0) {
-                    const int pr = idx / WP, px = idx - pr * WP;
-                    const int y = y0 - 1 + pr, x = px - 1;
-                    if (pr < R + 2 && y >= 0 && y < H && x >= 0 && x < W &&
-                        !(s == 1 && y >= zy0 && y < zy1 && x >= zx0 && x < zx1))
-                        v = *reinterpret_cast<const uint4*>(src + (frame + (size_t)y * W + x) * C + kg * 8);
+            // 4 independent 16-byte loads in flight per thread (the staging is latency-bound otherwise)
+            const int total = cells * P::KG;
+            for (int i0 = tid; i0 < total; i0 += 4 * 128) {
+                uint4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u * 128;
+                    v[u] = make_uint4(0u, 0u, 0u, 0u);
+                    const int ci = i / P::KG, kg = i % P::KG;
+                    const int idx = ci - 1;                 // one slack cell in front (tap dx=0 of cell 0)
+                    if (i < total && idx >= 0) {
+                        const int pr = (int)__umulhi((unsigned)idx, wp_magic), px = idx - pr * WP;
+                        const int y = y0 - 1 + pr, x = px - 1;
+                        if (pr < R + 2 && y >= 0 && y < H && x >= 0 && x < W &&
+                            !(s == 1 && y >= zy0 && y < zy1 && x >= zx0 && x < zx1))
+                            v[u] = *reinterpret_cast<const uint4*>(src + (frame + (size_t)y * W + x) * C + kg * 8);
+                    }
                 }
-                *reinterpret_cast<uint4*>(a_buf + (size_t)kg * lbo_a + (size_t)ci * 16) = v;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u * 128;
+                    if (i < total)
+                        *reinterpret_cast<uint4*>(a_buf + (size_t)(i % P::KG) * lbo_a + (size_t)(i / P::KG) * 16) = v[u];
+                }
             }
             umma::fence_async_smem();
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(umma::smem_u32(&bars.a_ready)) : "memory");
@@ -98,7 +110,7 @@ __global__ void __launch_bounds__(192) conv3x3_tc_kernel(const bf16* __restrict_
 #pragma unroll 1
         for (int t = 0; t < P::T; ++t) {
             const int o = t * 128 + warp * 32 + lane;
-            const int r = o / WP, px = o - r * WP;
+            const int r = (int)__umulhi((unsigned)o, wp_magic), px = o - r * WP;   // o / WP (exact: o*WP < 2^32)
             const int y = y0 + r, x = px - 1;
             const bool live = r < R && y < H && x >= 0 && x < W;
             const size_t off = (frame + (size_t)y * W + x) * C;
@@ -156,13 +168,18 @@ __global__ void __launch_bounds__(192) conv3x3_tc_kernel(const bf16* __restrict_
                     umma::mbar_wait(&bars.full[slot], round & 1);
                     umma::fence_after_sync();
                     const uint32_t tap_cell = (tap / 3) * WP + (tap % 3);      // (+1 slack, -1 for dx) cancel
-                    const uint32_t wb = w0 + slot * P::SLOT_BYTES;
+                    const uint64_t wd0 = umma::smem_desc(w0 + slot * P::SLOT_BYTES, lbo_b);
+                    uint64_t ad0 = umma::smem_desc(a0 + tap_cell * 16, lbo_a);
+#pragma unroll 1
                     for (int t = 0; t < P::T; ++t) {
-                        const uint32_t ab = a0 + (t * 128 + tap_cell) * 16;
+                        uint64_t ad = ad0, wd = wd0;
 #pragma unroll
-                        for (int ks = 0; ks < C / 16; ++ks)
-                            umma::mma_bf16(tmem + t * C, umma::smem_desc(ab + ks * 2 * lbo_a, lbo_a),
-                                           umma::smem_desc(wb + ks * 2 * lbo_b, lbo_b), idesc, (c | ks) != 0);
+                        for (int ks = 0; ks < C / 16; ++ks) {
+                            umma::mma_bf16(tmem + t * C, ad, wd, idesc, (c | ks) != 0);
+                            ad = umma::desc_advance(ad, 2 * lbo_a);
+                            wd = umma::desc_advance(wd, 2 * lbo_b);
+                        }
+                        ad0 = umma::desc_advance(ad0, 128 * 16);
                     }
                     umma::commit(&bars.empty[slot]);
                 }
@@ -191,8 +208,9 @@ static int conv_tc_launch(const void* in0, const void* in1, const void* wpk, con
     auto k = conv3x3_tc_kernel<C>;
     if (int e = set_smem(k, smem)) return e;
     dim3 grid((H + R - 1) / R, B);
+    const unsigned wp_magic = (unsigned)((((uint64_t)1 << 32) + WP - 1) / WP);   // umulhi(i, magic) == i / WP for i*WP < 2^32
     k<<<grid, 192, smem, st>>>((const bf16*)in0, (const bf16*)in1, (const bf16*)wpk, shift, (const bf16*)residual,
-                               (bf16*)out, H, W, R, cells, zy0, zy1, zx0, zx1);
+                               (bf16*)out, H, W, R, cells, wp_magic, zy0, zy1, zx0, zx1);
     return check_launch(in1 ? "conv3x3_tc<2C->C>" : "conv3x3_tc<C->C>");
 }
 

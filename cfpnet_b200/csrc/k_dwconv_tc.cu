@@ -112,16 +112,28 @@ __global__ void __launch_bounds__(256) dw_plane_unpack_kernel(const bf16* __rest
 
 // ---------------------------------------------------------------- the Toeplitz GEMM
 struct DwBars {
-    uint64_t t_full, a_full[3], a_empty[3], acc_full[2], acc_empty[2];
+    uint64_t t_full, t_empty, a_full[3], a_empty[3], acc_full[2], acc_empty[2];
     uint32_t tmem_slot;
 };
 
+// Work items are (channel, column tile, frame, row block), channel-major; every CTA takes an equal
+// contiguous share, so the grid is one balanced wave and the Toeplitz blocks are reloaded only when
+// a CTA's share crosses a channel boundary.
+struct DwItem { int c, xt, b, mt; };
+__device__ __forceinline__ DwItem dw_item(int i, int B, const DwGeom& g) {
+    DwItem it;
+    it.mt = i % g.nM; i /= g.nM;
+    it.b = i % B; i /= B;
+    it.xt = i % g.nX;
+    it.c = i / g.nX;
+    return it;
+}
+
 __global__ void __launch_bounds__(192) dwconv_tc_kernel(const bf16* __restrict__ planes, const bf16* __restrict__ toep,
                                                         const float* __restrict__ shift, bf16* __restrict__ planar_out,
-                                                        int B, DwGeom g) {
+                                                        int B, DwGeom g, int items_per_cta, int total_items) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ DwBars bars;
-    const int xt = blockIdx.x, c = blockIdx.y;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t t_blk = 2 * g.KS * 32 * 16;                 // bytes of one T_dy block  [2*KS groups][32][8]
     const uint32_t t_bytes = g.K * t_blk;
@@ -130,10 +142,11 @@ __global__ void __launch_bounds__(192) dwconv_tc_kernel(const bf16* __restrict__
     uint8_t* t_sm = smem;
     uint8_t* a_sm = smem + ((t_bytes + 127) & ~127u);          // [3][a_bytes]
     const uint32_t a_stride = (a_bytes + 127) & ~127u;
-    const int niter = B * g.nM;
+    const int i0 = blockIdx.x * items_per_cta, i1 = min(i0 + items_per_cta, total_items);
 
     if (tid == 0) {
         umma::mbar_init(&bars.t_full, 1);
+        umma::mbar_init(&bars.t_empty, 1);
         for (int i = 0; i < 3; ++i) { umma::mbar_init(&bars.a_full[i], 1); umma::mbar_init(&bars.a_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { umma::mbar_init(&bars.acc_full[i], 1); umma::mbar_init(&bars.acc_empty[i], 128); }
         umma::fence_mbar_init();
@@ -146,19 +159,20 @@ __global__ void __launch_bounds__(192) dwconv_tc_kernel(const bf16* __restrict__
 
     if (warp < 4) {
         // ---------------- epilogue: thread = output row, 32 columns
-        const float sh = shift[c];
-        for (int it = 0; it < niter; ++it) {
-            const int ab = it & 1, b = it / g.nM, mt = it % g.nM;
-            umma::mbar_wait(&bars.acc_full[ab], (it >> 1) & 1);
+        for (int i = i0; i < i1; ++i) {
+            const int n = i - i0, ab = n & 1;
+            const DwItem it = dw_item(i, B, g);
+            const float sh = shift[it.c];
+            umma::mbar_wait(&bars.acc_full[ab], (n >> 1) & 1);
             umma::fence_after_sync();
             float v[32];
             umma::tmem_ld16(umma::tmem_addr(tmem, warp * 32, ab * 32), *reinterpret_cast<float(*)[16]>(&v[0]));
             umma::tmem_ld16(umma::tmem_addr(tmem, warp * 32, ab * 32 + 16), *reinterpret_cast<float(*)[16]>(&v[16]));
             umma::fence_before_sync();
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(umma::smem_u32(&bars.acc_empty[ab])) : "memory");
-            const int y = mt * 128 + tid, x0 = xt * 32;
+            const int y = it.mt * 128 + tid, x0 = it.xt * 32;
             if (y < g.H) {
-                bf16* dst = planar_out + (((size_t)b * g.C + c) * g.H + y) * g.W + x0;
+                bf16* dst = planar_out + (((size_t)it.b * g.C + it.c) * g.H + y) * g.W + x0;
                 const bool aligned = (((size_t)(dst - planar_out)) & 7) == 0;
 #pragma unroll
                 for (int j = 0; j < 32; j += 8) {
@@ -171,21 +185,28 @@ __global__ void __launch_bounds__(192) dwconv_tc_kernel(const bf16* __restrict__
                         *reinterpret_cast<uint4*>(dst + j) = u;
                     } else {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            if (x0 + j + i < g.W) dst[j + i] = __float2bfloat16_rn(fmaxf(v[j + i] + sh, 0.f));
+                        for (int q = 0; q < 8; ++q)
+                            if (x0 + j + q < g.W) dst[j + q] = __float2bfloat16_rn(fmaxf(v[j + q] + sh, 0.f));
                     }
                 }
             }
         }
     } else if (warp == 4) {
-        // ---------------- producer: Toeplitz blocks once, then one bulk copy per (frame, row block)
+        // ---------------- producer: Toeplitz blocks per channel, one bulk copy per work item
         if (lane == 0) {
-            umma::mbar_expect_tx(&bars.t_full, t_bytes);
-            umma::bulk_g2s(t_sm, toep + (size_t)c * g.K * (t_blk / 2), t_bytes, &bars.t_full);
-            for (int it = 0; it < niter; ++it) {
-                const int s = it % 3, b = it / g.nM;
-                if (it >= 3) umma::mbar_wait(&bars.a_empty[s], ((it / 3) - 1) & 1);
-                const bf16* src = planes + ((((size_t)b * g.C + c) * g.WG + 4 * xt) * g.HP) * 8;
+            int cur_c = -1, nt = 0;
+            for (int i = i0; i < i1; ++i) {
+                const int n = i - i0, s = n % 3;
+                const DwItem it = dw_item(i, B, g);
+                if (it.c != cur_c) {
+                    if (nt > 0) umma::mbar_wait(&bars.t_empty, (nt - 1) & 1);   // MMAs on the old blocks are done
+                    umma::mbar_expect_tx(&bars.t_full, t_bytes);
+                    umma::bulk_g2s(t_sm, toep + (size_t)it.c * g.K * (t_blk / 2), t_bytes, &bars.t_full);
+                    cur_c = it.c;
+                    ++nt;
+                }
+                if (n >= 3) umma::mbar_wait(&bars.a_empty[s], ((n / 3) - 1) & 1);
+                const bf16* src = planes + ((((size_t)it.b * g.C + it.c) * g.WG + 4 * it.xt) * g.HP) * 8;
                 umma::mbar_expect_tx(&bars.a_full[s], a_bytes);
                 umma::bulk_g2s(a_sm + (size_t)s * a_stride, src, a_bytes, &bars.a_full[s]);
             }
@@ -194,19 +215,33 @@ __global__ void __launch_bounds__(192) dwconv_tc_kernel(const bf16* __restrict__
         // ---------------- MMA issuer
         if (lane == 0) {
             const uint32_t idesc = umma::idesc_bf16(128, 32);
-            const uint32_t ts = umma::smem_u32(t_sm), as0 = umma::smem_u32(a_sm);
-            umma::mbar_wait(&bars.t_full, 0);
-            for (int it = 0; it < niter; ++it) {
-                const int s = it % 3, ab = it & 1, mt = it % g.nM;
-                umma::mbar_wait(&bars.a_full[s], (it / 3) & 1);
-                if (it >= 2) umma::mbar_wait(&bars.acc_empty[ab], ((it >> 1) - 1) & 1);
+            const uint64_t tdesc0 = umma::smem_desc(umma::smem_u32(t_sm), 512);
+            const uint32_t as0 = umma::smem_u32(a_sm);
+            int cur_c = -1, nt = 0;
+            for (int i = i0; i < i1; ++i) {
+                const int n = i - i0, s = n % 3, ab = n & 1;
+                const DwItem it = dw_item(i, B, g);
+                if (it.c != cur_c) {
+                    if (nt > 0) umma::commit(&bars.t_empty);
+                    umma::mbar_wait(&bars.t_full, nt & 1);
+                    cur_c = it.c;
+                    ++nt;
+                }
+                umma::mbar_wait(&bars.a_full[s], (n / 3) & 1);
+                if (n >= 2) umma::mbar_wait(&bars.acc_empty[ab], ((n >> 1) - 1) & 1);
                 umma::fence_after_sync();
-                const uint32_t ab0 = as0 + s * a_stride + (uint32_t)(mt * 128) * 16;
+                uint64_t ad = umma::smem_desc(as0 + s * a_stride + (uint32_t)(it.mt * 128) * 16, lbo_a);
+                uint64_t td = tdesc0;
+                const uint32_t dcol = tmem + ab * 32;
                 for (int dy = 0; dy < g.K; ++dy) {
-                    const uint32_t tb = ts + dy * t_blk;
-                    for (int j = 0; j < g.KS; ++j)
-                        umma::mma_bf16(tmem + ab * 32, umma::smem_desc(ab0 + dy * 16 + 2 * j * lbo_a, lbo_a),
-                                       umma::smem_desc(tb + 2 * j * 512, 512), idesc, (dy | j) != 0);
+                    uint64_t adj = ad, tdj = td;
+                    for (int j = 0; j < g.KS; ++j) {
+                        umma::mma_bf16(dcol, adj, tdj, idesc, (dy | j) != 0);
+                        adj = umma::desc_advance(adj, 2 * lbo_a);
+                        tdj = umma::desc_advance(tdj, 2 * 512);
+                    }
+                    ad = umma::desc_advance(ad, 16);           // next vertical tap: one row down
+                    td = umma::desc_advance(td, t_blk);
                 }
                 umma::commit(&bars.a_empty[s]);
                 umma::commit(&bars.acc_full[ab]);
@@ -242,7 +277,10 @@ int dwconv_tc(const void* in, void* out, int B, int H, int W, int C, int K, cons
         const size_t smem = ((t_bytes + 127) & ~127u) + 3 * (size_t)((a_bytes + 127) & ~127u);
         CFP_REQUIRE(smem <= 225 * 1024, "dwconv (tensor-core path): %zu B shared memory (H=%d too tall)", smem, H);
         if (int err = set_smem(dwconv_tc_kernel, smem)) return err;
-        dwconv_tc_kernel<<<dim3(g.nX, C), 192, smem, st>>>(planes, (const bf16*)toep, shift, planar_out, B, g);
+        const int total = C * g.nX * B * g.nM;
+        const int grid = total < 148 ? total : 148;
+        const int per = (total + grid - 1) / grid;
+        dwconv_tc_kernel<<<(total + per - 1) / per, 192, smem, st>>>(planes, (const bf16*)toep, shift, planar_out, B, g, per, total);
         if (int err = check_launch(K == 31 ? "dwconv_tc<31>" : K == 15 ? "dwconv_tc<15>" : "dwconv_tc<7>")) return err;
     }
     dw_plane_unpack_kernel<<<dim3((H * W + 31) / 32, (C + 31) / 32, B), 256, 0, st>>>(planar_out, (bf16*)out, H, W, C);

@@ -33,6 +33,10 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
     return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46);
 }
+// Advance a descriptor's start address by `bytes` (multiple of 16; no carry out of the 14-bit field
+// as long as the operand stays inside the CTA's shared-memory window).  One 64-bit add in the MMA
+// issue loop instead of rebuilding the descriptor: the single issuing thread is the pacing resource.
+__device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) { return desc + (uint64_t)(bytes >> 4); }
 // Instruction descriptor, kind::f16, A/B = bf16 K-major, D = fp32 (cute::UMMA::InstrDescriptor).
 __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
