@@ -159,7 +159,7 @@ def workload_config(a, per_gpu_batch):
 # ---------------------------------------------------------------------------------- product arm
 def run_cfp(a):
     import torch.distributed as dist
-    from cfpnet_b200 import FusionPath, _lib
+    from cfpnet_b200 import FusionPath, _lib, shard
     from cfpnet_b200.build import build
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -198,7 +198,7 @@ def run_cfp(a):
 
     def step(i):
         d = dev_sets[i % NSETS]
-        torch.manual_seed(2 + i)            # same positional-encoding crop on every rank
+        shard.seed_posenc(i)                # same positional-encoding crop on every rank
         return path(d["x3"], d["x2"], d["x1"], d["hist_data"], d["mask"], patch_info)
 
     def barrier():
@@ -251,7 +251,7 @@ def run_cfp(a):
         barrier()
         e0.record()
         for i in range(a.steps):
-            torch.manual_seed(2 + i)
+            shard.seed_posenc(i)
             path.forward_host(host_sets[i % NSETS], patch_info, dev)
         e1.record()
         barrier()
