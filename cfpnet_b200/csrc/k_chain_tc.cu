@@ -107,15 +107,18 @@ __global__ void __launch_bounds__(192) loftr_query_tc_kernel(Q q, cfp_loftr_w w,
         uint32_t ph = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int64_t row0 = (int64_t)tile * 128;
-            // ---- stage x (coalesced: consecutive threads take consecutive 16-byte channel groups)
-            for (int i = tid; i < 128 * KG; i += 128) {
-                const int r = i / KG, kg = i % KG;
-                uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                if (row0 + r < q.rows) v = load8_bf16(q, row0 + r, kg * 8);
-                *reinterpret_cast<uint4*>(a0 + (size_t)kg * P::LBO + r * 16) = v;
-            }
+            // ---- stage x: thread = row; the row's geometry is located once and reused for the store
             const int64_t row = row0 + tid;
-            const int g = row < q.rows ? q.group(row) : -1;
+            const bool live = row < q.rows;
+            const typename Q::R ref = q.locate(live ? row : 0);
+            const int g = live ? q.group(ref) : -1;
+            {
+                uint4 v[KG];
+#pragma unroll
+                for (int kg = 0; kg < KG; ++kg) v[kg] = live ? load8_bf16(q, ref, kg * 8) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                for (int kg = 0; kg < KG; ++kg) *reinterpret_cast<uint4*>(a0 + (size_t)kg * P::LBO + tid * 16) = v[kg];
+            }
             umma::fence_async_smem();
             mbar_arrive(&bars.a_ready);
 
@@ -163,7 +166,7 @@ __global__ void __launch_bounds__(192) loftr_query_tc_kernel(Q q, cfp_loftr_w w,
 #pragma unroll
                     for (int i = 0; i < 8; ++i) o8[i] = out[j + i];
                     if (kAttnOnly) {
-                        if (g >= 0) store8(q, row, c0 + j, o8);
+                        if (g >= 0) store8(q, ref, c0 + j, o8);
                     } else {
                         umma::store_chunk(a1, P::LBO, tid, (c0 + j) / 8, o8);
                     }
@@ -230,7 +233,7 @@ __global__ void __launch_bounds__(192) loftr_query_tc_kernel(Q q, cfp_loftr_w w,
                         unpack8(*reinterpret_cast<const uint4*>(a0 + (size_t)(j / 8) * P::LBO + tid * 16), x8);
 #pragma unroll
                         for (int i = 0; i < 8; ++i) o8[i] = x8[i] + v[j + i];
-                        store8(q, row, j, o8);
+                        store8(q, ref, j, o8);
                     }
                 }
             }
@@ -399,7 +402,7 @@ __global__ void __launch_bounds__(192) lkpm_mlp_tc_kernel(bf16* __restrict__ fea
                     for (int j = 0; j < 16; j += 8) {
                         float o8[8];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) o8[i] = gelu_erf(t[j + i] + w.pw1_b[js * C + c0 + j + i]);
+                        for (int i = 0; i < 8; ++i) o8[i] = gelu_erf_fast(t[j + i] + w.pw1_b[js * C + c0 + j + i]);
                         umma::store_chunk(a1, P::LBO, tid, (c0 + j) / 8, o8);
                     }
                 }
@@ -565,16 +568,17 @@ __global__ void __launch_bounds__(192) kv_state_tc_kernel(Src src, int S, int S_
         uint32_t ph = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int64_t row0 = (int64_t)tile * 128;
-            for (int i = tid; i < 128 * KG; i += 128) {
-                const int r = i / KG, kg = i % KG;
-                const int64_t p = row0 + r;
-                const int g = (int)(p / S_pad), sidx = (int)(p % S_pad);
-                uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                if (p < total && sidx < S) v = load8_bf16(src, (int64_t)g * S + sidx, kg * 8);
-                *reinterpret_cast<uint4*>(a0 + (size_t)kg * P::LBO + r * 16) = v;
-            }
             const int64_t myp = row0 + tid;
-            const bool real = myp < total && (int)(myp % S_pad) < S;
+            const int myg = (int)(myp / S_pad), mys = (int)(myp - (int64_t)myg * S_pad);
+            const bool real = myp < total && mys < S;
+            {
+                const typename Src::R ref = src.locate(real ? (int64_t)myg * S + mys : 0);
+                uint4 v[KG];
+#pragma unroll
+                for (int kg = 0; kg < KG; ++kg) v[kg] = real ? load8_bf16(src, ref, kg * 8) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                for (int kg = 0; kg < KG; ++kg) *reinterpret_cast<uint4*>(a0 + (size_t)kg * P::LBO + tid * 16) = v[kg];
+            }
             umma::fence_async_smem();
             mbar_arrive(&bars.a_ready);
 

@@ -37,9 +37,15 @@ __global__ void __launch_bounds__(kThreads) kv_state_kernel(Src src, const float
     float* wbuf = kvs + BM * LDK;
     const int64_t row0 = (int64_t)blockIdx.x * BM;
 
+    __shared__ int gid[BM];
     for (int i = threadIdx.x; i < BM * (C / 4); i += kThreads) {
         int r = i / (C / 4), c4 = i % (C / 4);
-        float4 v = row0 + r < src.rows ? src.load4(row0 + r, c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row0 + r < src.rows) {
+            const auto ref = src.locate(row0 + r);
+            v = src.load4(ref, c4 * 4);
+            if (c4 == 0) gid[r] = src.group(ref);
+        }
         *reinterpret_cast<float4*>(xs + r * LDX + c4 * 4) = v;
     }
     __syncthreads();
@@ -50,9 +56,9 @@ __global__ void __launch_bounds__(kThreads) kv_state_kernel(Src src, const float
     const int nrows = (int)min((int64_t)BM, src.rows - row0);
     int r = 0;
     while (r < nrows) {                     // one segment per group present in the tile
-        const int g = src.group(row0 + r);
+        const int g = gid[r];
         int e = r + 1;
-        while (e < nrows && src.group(row0 + e) == g) ++e;
+        while (e < nrows && gid[e] == g) ++e;
         for (int idx = threadIdx.x; idx < C * DH; idx += kThreads) {
             const int kc = idx / DH, vc = (kc / DH) * DH + idx % DH;
             float s = 0.f;
@@ -83,10 +89,14 @@ __global__ void __launch_bounds__(kThreads) loftr_query_kernel(Q q, cfp_loftr_w 
 
     for (int i = threadIdx.x; i < BM * (C / 4); i += kThreads) {
         int r = i / (C / 4), c4 = i % (C / 4);
-        float4 v = row0 + r < q.rows ? q.load4(row0 + r, c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row0 + r < q.rows) {
+            const auto ref = q.locate(row0 + r);
+            v = q.load4(ref, c4 * 4);
+            if (c4 == 0) gid[r] = q.group(ref);
+        } else if (c4 == 0) gid[r] = -1;
         *reinterpret_cast<float4*>(cat + r * LD + c4 * 4) = v;
     }
-    if (threadIdx.x < BM) gid[threadIdx.x] = row0 + threadIdx.x < q.rows ? q.group(row0 + threadIdx.x) : -1;
     __syncthreads();
 
     // Q = elu(x Wq^T) + 1
@@ -122,7 +132,7 @@ __global__ void __launch_bounds__(kThreads) loftr_query_kernel(Q q, cfp_loftr_w 
         for (int i = threadIdx.x; i < BM * (C / 4); i += kThreads) {
             int r = i / (C / 4), c4 = i % (C / 4);
             if (row0 + r < q.rows)
-                q.store4(row0 + r, c4 * 4, *reinterpret_cast<const float4*>(hb + r * LD + C + c4 * 4));
+                q.store4(q.locate(row0 + r), c4 * 4, *reinterpret_cast<const float4*>(hb + r * LD + C + c4 * 4));
         }
         return;
     }
@@ -146,7 +156,7 @@ __global__ void __launch_bounds__(kThreads) loftr_query_kernel(Q q, cfp_loftr_w 
         if (row0 + r < q.rows) {
             float4 x = *reinterpret_cast<const float4*>(cat + r * LD + c4 * 4);
             float4 m = *reinterpret_cast<const float4*>(cat + r * LD + C + c4 * 4);
-            q.store4(row0 + r, c4 * 4, make_float4(x.x + m.x, x.y + m.y, x.z + m.z, x.w + m.w));
+            q.store4(q.locate(row0 + r), c4 * 4, make_float4(x.x + m.x, x.y + m.y, x.z + m.z, x.w + m.w));
         }
     }
 }
@@ -230,14 +240,14 @@ static int d2i_impl(void* feat0, const void* emb, const void* zone_tok, const fl
     const int Z = g.zone_num * g.zone_num, groups = B * Z;
     float *kv, *ksum;
     kv_ptrs<C, 4>(ws, L, groups, kv, ksum);
-    ZoneTokSrc<T> src{(const T*)zone_tok, pos2, S, C, (int64_t)groups * S};
+    ZoneTokSrc<T> src((const T*)zone_tok, pos2, S, C, (int64_t)groups * S);
     if constexpr (std::is_same<T, bf16>::value) {
         if (int e = kv_tc_h2i(C, src, S, groups, w.kv_tc, kv, ksum, st)) return e;
     } else {
         if (int e = run_kv_state<C, 4>("kv_state<hist2image>", src, groups, w.wkv_t, kv, ksum, st)) return e;
     }
-    ZonePatchRows<T> q{(T*)feat0, (const T*)emb, (T*)(ws + L.canvas), mask, H, W, C, g.zone_num, g.p1, g.p2,
-                       g.sy_wo, g.sx_wo, g.tzh, g.tzw, g.interpolate, assign, (int64_t)groups * g.p1 * g.p2};
+    ZonePatchRows<T> q((T*)feat0, (const T*)emb, (T*)(ws + L.canvas), mask, H, W, C, g.zone_num, g.p1, g.p2,
+                       g.sy_wo, g.sx_wo, g.tzh, g.tzw, g.interpolate, assign, (int64_t)groups * g.p1 * g.p2);
     if constexpr (std::is_same<T, bf16>::value) {
         if (int e = query_tc_h2i(C, q, w, kv, ksum, st)) return e;
     } else {
@@ -260,7 +270,7 @@ static int dapm_impl(const void* feat0, void* msg_map, int B, int H, int W, cons
     float *kv, *ksum;
     kv_ptrs<C, 4>(ws, L, B, kv, ksum);
     if (Ni > 0) {
-        InsideSrc<T> src{(const T*)feat0, H, W, C, g.ry0, g.rx0, rw, Ni, (int64_t)B * Ni};
+        InsideSrc<T> src((const T*)feat0, H, W, C, g.ry0, g.rx0, rw, Ni, (int64_t)B * Ni);
         if constexpr (std::is_same<T, bf16>::value) {
             if (int e = kv_tc_dapm(C, src, Ni, B, w.kv_tc, kv, ksum, st)) return e;
         } else {
@@ -270,7 +280,7 @@ static int dapm_impl(const void* feat0, void* msg_map, int B, int H, int W, cons
         cudaMemsetAsync(kv, 0, (size_t)B * (C * (C / 4) + C) * sizeof(float), st);
     }
     if (No == 0) return 0;
-    OutsideRows<T> q{(const T*)feat0, (T*)msg_map, H, W, C, g.ry0, g.ry1, g.rx0, g.rx1, No, (int64_t)B * No};
+    OutsideRows<T> q((const T*)feat0, (T*)msg_map, H, W, C, g.ry0, g.ry1, g.rx0, g.rx1, No, (int64_t)B * No);
     if constexpr (std::is_same<T, bf16>::value) return query_tc_dapm(C, q, w, kv, ksum, st);
     else return run_query<C, 4, true>("attn_query<dapm>", q, w, kv, ksum, st);
 }
@@ -283,7 +293,7 @@ static int twins_impl(void* feat0, int B, int H, int W, const cfp_twins_w& w, ch
     const int nwy = (H + wsz - 1) / wsz, nwx = (W + wsz - 1) / wsz, nwin = nwy * nwx, groups = B * nwin;
     float *kv, *ksum;
     kv_ptrs<C, 8>(ws, L, groups, kv, ksum);
-    WindowRows<T> win{(T*)feat0, H, W, C, wsz, nwx, nwin, (int64_t)groups * wsz * wsz};
+    WindowRows<T> win((T*)feat0, H, W, C, wsz, nwx, nwin, (int64_t)groups * wsz * wsz);
     if constexpr (std::is_same<T, bf16>::value) {
         if (int e = kv_tc_lsa(C, win, wsz * wsz, groups, w.lsa.kv_tc, kv, ksum, st)) return e;
     } else {
@@ -303,13 +313,13 @@ static int twins_impl(void* feat0, int B, int H, int W, const cfp_twins_w& w, ch
         if (int e = sr_conv_ln(feat0, sr_tok, B, H, W, C, wsz, w.sr_t, w.sr_b, w.srln_g, w.srln_b, CFP_F32, st)) return e;
     }
     kv_ptrs<C, 8>(ws, L, B, kv, ksum);
-    SrTokSrc src{sr_tok, Ns, C, (int64_t)B * Ns};
+    SrTokSrc src(sr_tok, Ns, C, (int64_t)B * Ns);
     if constexpr (std::is_same<T, bf16>::value) {
         if (int e = kv_tc_gsa(C, src, Ns, B, w.gsa.kv_tc, kv, ksum, st)) return e;
     } else {
         if (int e = run_kv_state<C, 8>("kv_state<gsa>", src, B, w.gsa.wkv_t, kv, ksum, st)) return e;
     }
-    FrameRows<T> fr{(T*)feat0, H * W, C, (int64_t)B * H * W};
+    FrameRows<T> fr((T*)feat0, H * W, C, (int64_t)B * H * W);
     if constexpr (std::is_same<T, bf16>::value) return query_tc_gsa(C, fr, w.gsa, kv, ksum, st);
     else return run_query<C, 8, false>("loftr_query<gsa>", fr, w.gsa, kv, ksum, st);
 }

@@ -3,6 +3,16 @@
 // query / source set to where that token lives: zone-patch cell of the hist2image canvas, cell
 // of a (zero-padded) LSA window, outside-/inside-zone cell of DAPM, plain frame token, ...
 // No mask tensor and no gathered copy of the tokens is ever materialised.
+//
+// Interface (R = provider-specific reference to a located row):
+//   int64_t rows                          total dense rows
+//   R     locate(int64_t r)               all integer geometry of row r, done ONCE per row
+//   int   group(const R&)                 attention group of the row
+//   float4 load4(const R&, int c)         channels c..c+3 (zeros for padding cells)
+//   void  store4(const R&, int c, float4) query providers only
+// The index arithmetic uses FastDiv (multiply-high by a host-computed reciprocal): the divisors
+// (window size, zones per side, rows per group, ...) are runtime values and a hardware-emulated
+// 64-bit division per chunk used to dominate the staging cost of the small-C layers.
 #pragma once
 #include "cfp_common.cuh"
 #include "cfp_internal.h"
@@ -11,150 +21,186 @@ namespace cfp {
 
 template <int C> struct Tile { static constexpr int BM = C >= 128 ? 32 : 64; };
 
-// ------------------------------------------------------------------ providers
-// Common interface:
-//   int64_t rows;                     total dense rows
-//   int group(int64_t r)              attention group of row r
-//   float4 load4(int64_t r, int c)    channels c..c+3 of row r (zeros for padding)
-//   void store4(int64_t r, int c, float4 v)      (query providers only)
+struct FastDiv {               // exact n / d for 0 <= n < 2^32, 1 <= d < 2^32
+    uint64_t m;
+    uint32_t d;
+    FastDiv() : m(0), d(1) {}
+    explicit FastDiv(uint32_t div) : m(div > 1 ? (~0ull / div) + 1 : 0), d(div ? div : 1) {}
+    __device__ __forceinline__ uint32_t div(uint32_t n) const { return d == 1 ? n : (uint32_t)__umul64hi((uint64_t)n, m); }
+    __device__ __forceinline__ void divmod(uint32_t n, uint32_t& q, uint32_t& r) const { q = div(n); r = n - q * d; }
+};
+
+struct RowRef {                // a located token: element offset into the map, group, validity
+    int64_t off;
+    int g;
+    bool ok;
+};
 
 template <typename T>
 struct ZoneTokSrc {            // hist2image keys/values: zone tokens + positional_encodings2
-    const T* tok; const float* pos2; int S, C; int64_t rows;
-    __device__ int group(int64_t r) const { return (int)(r / S); }
-    __device__ float4 load4(int64_t r, int c) const {
-        float4 v = IO<T>::ld4(tok + r * C + c);
-        float4 p = *reinterpret_cast<const float4*>(pos2 + (r % S) * C + c);
+    const T* tok; const float* pos2; int S, C; int64_t rows; FastDiv dS;
+    ZoneTokSrc(const T* t, const float* p, int S_, int C_, int64_t n) : tok(t), pos2(p), S(S_), C(C_), rows(n), dS(S_) {}
+    struct R { int64_t off; int g, s; };
+    __device__ R locate(int64_t r) const {
+        uint32_t g, s;
+        dS.divmod((uint32_t)r, g, s);
+        return R{r * C, (int)g, (int)s};
+    }
+    __device__ int group(const R& x) const { return x.g; }
+    __device__ float4 load4(const R& x, int c) const {
+        float4 v = IO<T>::ld4(tok + x.off + c);
+        float4 p = *reinterpret_cast<const float4*>(pos2 + x.s * C + c);
         return make_float4(v.x + p.x, v.y + p.y, v.z + p.z, v.w + p.w);
     }
 };
 
 template <typename T>
 struct WindowRows {            // LSA: ws x ws windows over the zero-padded map (queries and keys)
-    T* feat; int H, W, C, ws, nwx, nwin; int64_t rows;
-    __device__ int group(int64_t r) const { return (int)(r / (ws * ws)); }
-    __device__ bool locate(int64_t r, int64_t& off) const {
-        int g = (int)(r / (ws * ws)), l = (int)(r % (ws * ws));
-        int b = g / nwin, wi = g % nwin;
-        int y = (wi / nwx) * ws + l / ws, x = (wi % nwx) * ws + l % ws;
-        off = ((int64_t)b * H * W + (int64_t)y * W + x) * C;
-        return y < H && x < W;
+    T* feat; int H, W, C, ws, nwx, nwin; int64_t rows; FastDiv dL, dWin, dNwx, dWs;
+    WindowRows(T* f, int H_, int W_, int C_, int ws_, int nwx_, int nwin_, int64_t n)
+        : feat(f), H(H_), W(W_), C(C_), ws(ws_), nwx(nwx_), nwin(nwin_), rows(n), dL(ws_ * ws_), dWin(nwin_), dNwx(nwx_), dWs(ws_) {}
+    typedef RowRef R;
+    __device__ R locate(int64_t r) const {
+        uint32_t g, l, b, wi, wy, wx, iy, ix;
+        dL.divmod((uint32_t)r, g, l);
+        dWin.divmod(g, b, wi);
+        dNwx.divmod(wi, wy, wx);
+        dWs.divmod(l, iy, ix);
+        const int y = wy * ws + iy, x = wx * ws + ix;
+        return R{((int64_t)b * H * W + (int64_t)y * W + x) * C, (int)g, y < H && x < W};
     }
-    __device__ float4 load4(int64_t r, int c) const {
-        int64_t off;
-        return locate(r, off) ? IO<T>::ld4(feat + off + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    __device__ int group(const R& x) const { return x.g; }
+    __device__ float4 load4(const R& x, int c) const {
+        return x.ok ? IO<T>::ld4(feat + x.off + c) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    __device__ void store4(int64_t r, int c, float4 v) const {
-        int64_t off;
-        if (locate(r, off)) IO<T>::st4(feat + off + c, v);
+    __device__ void store4(const R& x, int c, float4 v) const {
+        if (x.ok) IO<T>::st4(feat + x.off + c, v);
     }
 };
 
 template <typename T>
 struct FrameRows {             // GSA queries: every token of a frame, group = frame
-    T* feat; int N, C; int64_t rows;
-    __device__ int group(int64_t r) const { return (int)(r / N); }
-    __device__ float4 load4(int64_t r, int c) const { return IO<T>::ld4(feat + r * C + c); }
-    __device__ void store4(int64_t r, int c, float4 v) const { IO<T>::st4(feat + r * C + c, v); }
+    T* feat; int N, C; int64_t rows; FastDiv dN;
+    FrameRows(T* f, int N_, int C_, int64_t n) : feat(f), N(N_), C(C_), rows(n), dN(N_) {}
+    typedef RowRef R;
+    __device__ R locate(int64_t r) const { return R{r * C, (int)dN.div((uint32_t)r), true}; }
+    __device__ int group(const R& x) const { return x.g; }
+    __device__ float4 load4(const R& x, int c) const { return IO<T>::ld4(feat + x.off + c); }
+    __device__ void store4(const R& x, int c, float4 v) const { IO<T>::st4(feat + x.off + c, v); }
 };
 
 struct SrTokSrc {              // GSA keys/values: fp32 sub-sampled tokens [B][Ns][C]
-    const float* tok; int Ns, C; int64_t rows;
-    __device__ int group(int64_t r) const { return (int)(r / Ns); }
-    __device__ float4 load4(int64_t r, int c) const { return *reinterpret_cast<const float4*>(tok + r * C + c); }
+    const float* tok; int Ns, C; int64_t rows; FastDiv dN;
+    SrTokSrc(const float* t, int Ns_, int C_, int64_t n) : tok(t), Ns(Ns_), C(C_), rows(n), dN(Ns_) {}
+    typedef RowRef R;
+    __device__ R locate(int64_t r) const { return R{r * C, (int)dN.div((uint32_t)r), true}; }
+    __device__ int group(const R& x) const { return x.g; }
+    __device__ float4 load4(const R& x, int c) const { return *reinterpret_cast<const float4*>(tok + x.off + c); }
 };
 
 template <typename T>
 struct InsideSrc {             // DAPM keys/values: tokens inside the zone rectangle, raster order
-    const T* feat; int H, W, C, ry0, rx0, rw, Ni; int64_t rows;
-    __device__ int group(int64_t r) const { return (int)(r / Ni); }
-    __device__ float4 load4(int64_t r, int c) const {
-        int b = (int)(r / Ni), i = (int)(r % Ni);
-        int y = ry0 + i / rw, x = rx0 + i % rw;
-        return IO<T>::ld4(feat + ((int64_t)b * H * W + (int64_t)y * W + x) * C + c);
+    const T* feat; int H, W, C, ry0, rx0, rw, Ni; int64_t rows; FastDiv dNi, dRw;
+    InsideSrc(const T* f, int H_, int W_, int C_, int ry0_, int rx0_, int rw_, int Ni_, int64_t n)
+        : feat(f), H(H_), W(W_), C(C_), ry0(ry0_), rx0(rx0_), rw(rw_), Ni(Ni_), rows(n), dNi(Ni_), dRw(rw_) {}
+    typedef RowRef R;
+    __device__ R locate(int64_t r) const {
+        uint32_t b, i, iy, ix;
+        dNi.divmod((uint32_t)r, b, i);
+        dRw.divmod(i, iy, ix);
+        return R{((int64_t)b * H * W + (int64_t)(ry0 + iy) * W + rx0 + ix) * C, (int)b, true};
     }
+    __device__ int group(const R& x) const { return x.g; }
+    __device__ float4 load4(const R& x, int c) const { return IO<T>::ld4(feat + x.off + c); }
 };
 
 template <typename T>
 struct OutsideRows {           // DAPM queries: tokens outside the rectangle; message map out
-    const T* feat; T* msg; int H, W, C, ry0, ry1, rx0, rx1, No; int64_t rows;
-    __device__ int group(int64_t r) const { return (int)(r / No); }
-    __device__ int64_t locate(int64_t r) const {
-        int b = (int)(r / No), o = (int)(r % No);
+    const T* feat; T* msg; int H, W, C, ry0, ry1, rx0, rx1, No; int64_t rows; FastDiv dNo, dOut;
+    OutsideRows(const T* f, T* m, int H_, int W_, int C_, int ry0_, int ry1_, int rx0_, int rx1_, int No_, int64_t n)
+        : feat(f), msg(m), H(H_), W(W_), C(C_), ry0(ry0_), ry1(ry1_), rx0(rx0_), rx1(rx1_), No(No_), rows(n), dNo(No_),
+          dOut(W_ - (rx1_ - rx0_) > 0 ? W_ - (rx1_ - rx0_) : 1) {}
+    typedef RowRef R;
+    __device__ R locate(int64_t r) const {
+        uint32_t b, o;
+        dNo.divmod((uint32_t)r, b, o);
         const int rw = rx1 - rx0, top = ry0 * W, mid = (ry1 - ry0) * (W - rw);
         int n;
-        if (o < top) n = o;
-        else if (o < top + mid) {
-            int q = o - top, row = q / (W - rw), j = q % (W - rw);
-            n = (ry0 + row) * W + (j < rx0 ? j : j + rw);
+        if ((int)o < top) n = o;
+        else if ((int)o < top + mid) {
+            uint32_t row, j;
+            dOut.divmod(o - top, row, j);
+            n = (ry0 + row) * W + ((int)j < rx0 ? j : j + rw);
         } else n = ry1 * W + (o - top - mid);
-        return ((int64_t)b * H * W + n) * C;
+        return R{((int64_t)b * H * W + n) * C, (int)b, true};
     }
-    __device__ float4 load4(int64_t r, int c) const { return IO<T>::ld4(feat + locate(r) + c); }
-    __device__ void store4(int64_t r, int c, float4 v) const { IO<T>::st4(msg + locate(r) + c, v); }
+    __device__ int group(const R& x) const { return x.g; }
+    __device__ float4 load4(const R& x, int c) const { return IO<T>::ld4(feat + x.off + c); }
+    __device__ void store4(const R& x, int c, float4 v) const { IO<T>::st4(msg + x.off + c, v); }
 };
 
 template <typename T>
 struct ZonePatchRows {         // hist2image queries: cells of the zone canvas, grouped per zone
     T* feat0; const T* emb; T* canvas; const uint8_t* mask;
     int H, W, C, zn, p1, p2, sy_wo, sx_wo, tzh, tzw, interpolate, assign; int64_t rows;
-    __device__ int group(int64_t r) const { return (int)(r / (p1 * p2)); }
-    __device__ void cell(int64_t r, int& b, int& cy, int& cx) const {
-        int g = (int)(r / (p1 * p2)), l = (int)(r % (p1 * p2));
-        b = g / (zn * zn);
-        int z = g % (zn * zn);
-        cy = (z / zn) * p1 + l / p2;
-        cx = (z % zn) * p2 + l % p2;
+    FastDiv dP, dZ, dZn, dP2;
+    ZonePatchRows(T* f, const T* e, T* cv, const uint8_t* m, int H_, int W_, int C_, int zn_, int p1_, int p2_, int sy, int sx,
+                  int tzh_, int tzw_, int interp, int assign_, int64_t n)
+        : feat0(f), emb(e), canvas(cv), mask(m), H(H_), W(W_), C(C_), zn(zn_), p1(p1_), p2(p2_), sy_wo(sy), sx_wo(sx),
+          tzh(tzh_), tzw(tzw_), interpolate(interp), assign(assign_), rows(n), dP(p1_ * p2_), dZ(zn_ * zn_), dZn(zn_), dP2(p2_) {}
+    struct R { int b, cy, cx, g; bool valid; };
+    __device__ R locate(int64_t r) const {
+        uint32_t g, l, b, z, zy, zx, py, px;
+        dP.divmod((uint32_t)r, g, l);
+        dZ.divmod(g, b, z);
+        dZn.divmod(z, zy, zx);
+        dP2.divmod(l, py, px);
+        return R{(int)b, (int)(zy * p1 + py), (int)(zx * p2 + px), (int)g, mask[g] != 0};
     }
+    __device__ int group(const R& x) const { return x.g; }
     // value of the zero-padded map at canvas cell (ty,tx) of the un-resized canvas
     __device__ float4 canvas_at(int b, int ty, int tx, int c) const {
         int y = sy_wo + ty, x = sx_wo + tx;
         if (y < 0 || y >= H || x < 0 || x >= W) return make_float4(0.f, 0.f, 0.f, 0.f);
         return IO<T>::ld4(emb + ((int64_t)b * H * W + (int64_t)y * W + x) * C + c);
     }
-    __device__ float4 load4(int64_t r, int c) const {
-        int b, cy, cx;
-        cell(r, b, cy, cx);
-        if (!interpolate) return canvas_at(b, cy, cx, c);
+    __device__ float4 load4(const R& q, int c) const {
+        if (!interpolate) return canvas_at(q.b, q.cy, q.cx, c);
         // F.interpolate(bilinear, align_corners=True) from [tzh,tzw] to [zn*p1, zn*p2]  (fusion.py:141)
         const int oh = zn * p1, ow = zn * p2;
-        float fy = oh > 1 ? cy * ((float)(tzh - 1) / (float)(oh - 1)) : 0.f;
-        float fx = ow > 1 ? cx * ((float)(tzw - 1) / (float)(ow - 1)) : 0.f;
+        float fy = oh > 1 ? q.cy * ((float)(tzh - 1) / (float)(oh - 1)) : 0.f;
+        float fx = ow > 1 ? q.cx * ((float)(tzw - 1) / (float)(ow - 1)) : 0.f;
         int y0 = (int)fy, x0 = (int)fx;
         int y1 = min(y0 + 1, tzh - 1), x1 = min(x0 + 1, tzw - 1);
         float ly = fy - y0, lx = fx - x0;
-        float4 a = canvas_at(b, y0, x0, c), bq = canvas_at(b, y0, x1, c);
-        float4 cq = canvas_at(b, y1, x0, c), d = canvas_at(b, y1, x1, c);
+        float4 a = canvas_at(q.b, y0, x0, c), bq = canvas_at(q.b, y0, x1, c);
+        float4 cq = canvas_at(q.b, y1, x0, c), d = canvas_at(q.b, y1, x1, c);
         float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
         return make_float4(w00 * a.x + w01 * bq.x + w10 * cq.x + w11 * d.x,
                            w00 * a.y + w01 * bq.y + w10 * cq.y + w11 * d.y,
                            w00 * a.z + w01 * bq.z + w10 * cq.z + w11 * d.z,
                            w00 * a.w + w01 * bq.w + w10 * cq.w + w11 * d.w);
     }
-    __device__ void store4(int64_t r, int c, float4 v) const {
-        int b, cy, cx;
-        cell(r, b, cy, cx);
-        const bool valid = mask[group(r)] != 0;           // zone_feature[~hist_mask] = 0  (fusion.py:144)
-        if (!valid) v = make_float4(0.f, 0.f, 0.f, 0.f);
+    __device__ void store4(const R& q, int c, float4 v) const {
+        if (!q.valid) v = make_float4(0.f, 0.f, 0.f, 0.f);   // zone_feature[~hist_mask] = 0  (fusion.py:144)
         if (interpolate) {                                // resized back by canvas_resize_add_kernel
-            IO<T>::st4(canvas + (((int64_t)b * zn * p1 + cy) * (zn * p2) + cx) * C + c, v);
+            IO<T>::st4(canvas + (((int64_t)q.b * zn * p1 + q.cy) * (zn * p2) + q.cx) * C + c, v);
             return;
         }
-        int y = sy_wo + cy, x = sx_wo + cx;
+        int y = sy_wo + q.cy, x = sx_wo + q.cx;
         if (y < 0 || y >= H || x < 0 || x >= W) return;    // pad_mask (fusion.py:112-118)
-        T* dst = feat0 + ((int64_t)b * H * W + (int64_t)y * W + x) * C + c;
+        T* dst = feat0 + ((int64_t)q.b * H * W + (int64_t)y * W + x) * C + c;
         if (assign) { IO<T>::st4(dst, v); return; }       // --no_skip_inside (fusion.py:154-155)
-        if (!valid) return;
+        if (!q.valid) return;
         float4 o = IO<T>::ld4(dst);                       // feat0[zone_mask] += ...  (fusion.py:157)
         IO<T>::st4(dst, make_float4(o.x + v.x, o.y + v.y, o.z + v.z, o.w + v.w));
     }
 };
 
-
-// 8 consecutive channels of a row as packed bf16 (tensor-core path staging)
+// 8 consecutive channels of a located row as packed bf16 (tensor-core path staging)
 template <class P>
-__device__ __forceinline__ uint4 load8_bf16(const P& p, int64_t r, int c) {
-    float4 a = p.load4(r, c), b = p.load4(r, c + 4);
+__device__ __forceinline__ uint4 load8_bf16(const P& p, const typename P::R& ref, int c) {
+    float4 a = p.load4(ref, c), b = p.load4(ref, c + 4);
     __nv_bfloat162 t0 = __floats2bfloat162_rn(a.x, a.y), t1 = __floats2bfloat162_rn(a.z, a.w);
     __nv_bfloat162 t2 = __floats2bfloat162_rn(b.x, b.y), t3 = __floats2bfloat162_rn(b.z, b.w);
     uint4 u;
@@ -163,9 +209,9 @@ __device__ __forceinline__ uint4 load8_bf16(const P& p, int64_t r, int c) {
     return u;
 }
 template <class P>
-__device__ __forceinline__ void store8(const P& p, int64_t r, int c, const float (&v)[8]) {
-    p.store4(r, c, make_float4(v[0], v[1], v[2], v[3]));
-    p.store4(r, c + 4, make_float4(v[4], v[5], v[6], v[7]));
+__device__ __forceinline__ void store8(const P& p, const typename P::R& ref, int c, const float (&v)[8]) {
+    p.store4(ref, c, make_float4(v[0], v[1], v[2], v[3]));
+    p.store4(ref, c + 4, make_float4(v[4], v[5], v[6], v[7]));
 }
 
 // k_chain_tc.cu: the query chain on tcgen05 (bf16 activations only)
