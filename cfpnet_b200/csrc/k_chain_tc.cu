@@ -77,8 +77,10 @@ __device__ __forceinline__ void layernorm_reg(float (&v)[C], const float* __rest
     for (int i = 0; i < C; ++i) v[i] = v[i] * rstd * g[i] + b[i];
 }
 
+template <int C> struct ChainOcc { static constexpr int CTAS = C >= 128 ? 1 : (C == 64 ? 2 : 4); };
+
 template <int C, int NH, bool kAttnOnly, class Q>
-__global__ void __launch_bounds__(192) loftr_query_tc_kernel(Q q, cfp_loftr_w w, const float* __restrict__ kv,
+__global__ void __launch_bounds__(192, ChainOcc<C>::CTAS) loftr_query_tc_kernel(Q q, cfp_loftr_w w, const float* __restrict__ kv,
                                                              const float* __restrict__ ksum, int ntiles) {
     using P = ChainTC<C>;
     constexpr int DH = C / NH, KG = P::KG, G = DH < 16 ? 16 : DH;
@@ -88,7 +90,7 @@ __global__ void __launch_bounds__(192) loftr_query_tc_kernel(Q q, cfp_loftr_w w,
     uint8_t* a0 = smem;                  // [x | LN1(merge(msg))]  2C columns
     uint8_t* a1 = a0 + P::ABUF;          // msg (C columns), later the MLP hidden (2C columns)
     uint8_t* ring = a1 + P::ABUF;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = umma::warp_idx_sync(), lane = tid & 31;
 
     if (tid == 0) {
         for (int i = 0; i < P::NSLOT; ++i) { umma::mbar_init(&bars.full[i], 1); umma::mbar_init(&bars.empty[i], 1); }
@@ -125,50 +127,52 @@ __global__ void __launch_bounds__(192) loftr_query_tc_kernel(Q q, cfp_loftr_w w,
             // ---- epilogue 1: Q = elu(q)+1, msg = (Q KV) / (Q.Ksum + eps)
             umma::mbar_wait(&bars.acc_ready, ph); ph ^= 1;
             umma::fence_after_sync();
+            {
 #pragma unroll 1
-            for (int c0 = 0; c0 < C; c0 += G) {
-                float qv[G], out[G];
+                for (int c0 = 0; c0 < C; c0 += G) {
+                    float qv[G], out[G];
 #pragma unroll
-                for (int j = 0; j < G; j += 16) {
-                    float t[16];
-                    umma::tmem_ld16(umma::tmem_addr(tmem, warp * 32, c0 + j), t);
+                    for (int j = 0; j < G; j += 16) {
+                        float t[16];
+                        umma::tmem_ld16(umma::tmem_addr(tmem, warp * 32, c0 + j), t);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) qv[j + i] = elu1(t[i]);
-                }
+                        for (int i = 0; i < 16; ++i) qv[j + i] = elu1(t[i]);
+                    }
 #pragma unroll
-                for (int hh = 0; hh < G / DH; ++hh) {
-                    const int h0 = c0 + hh * DH;             // first channel of this head
-                    float num[DH], den = kAttnEps;
+                    for (int hh = 0; hh < G / DH; ++hh) {
+                        const int h0 = c0 + hh * DH;             // first channel of this head
+                        float num[DH], den = kAttnEps;
 #pragma unroll
-                    for (int v = 0; v < DH; ++v) num[v] = 0.f;
-                    if (g >= 0) {
-                        const float* kvh = kv + (size_t)g * (C * DH) + (size_t)h0 * DH;
-                        const float* ksh = ksum + (size_t)g * C + h0;
+                        for (int v = 0; v < DH; ++v) num[v] = 0.f;
+                        if (g >= 0) {
+                            const float* kvh = kv + (size_t)g * (C * DH) + (size_t)h0 * DH;
+                            const float* ksh = ksum + (size_t)g * C + h0;
 #pragma unroll
-                        for (int d = 0; d < DH; ++d) {
-                            const float qd = qv[hh * DH + d];
-                            den = fmaf(qd, ksh[d], den);
+                            for (int d = 0; d < DH; ++d) {
+                                const float qd = qv[hh * DH + d];
+                                den = fmaf(qd, ksh[d], den);
 #pragma unroll
-                            for (int v = 0; v < DH; v += 4) {
-                                const float4 k4 = *reinterpret_cast<const float4*>(kvh + d * DH + v);
-                                num[v] = fmaf(qd, k4.x, num[v]); num[v + 1] = fmaf(qd, k4.y, num[v + 1]);
-                                num[v + 2] = fmaf(qd, k4.z, num[v + 2]); num[v + 3] = fmaf(qd, k4.w, num[v + 3]);
+                                for (int v = 0; v < DH; v += 4) {
+                                    const float4 k4 = *reinterpret_cast<const float4*>(kvh + d * DH + v);
+                                    num[v] = fmaf(qd, k4.x, num[v]); num[v + 1] = fmaf(qd, k4.y, num[v + 1]);
+                                    num[v + 2] = fmaf(qd, k4.z, num[v + 2]); num[v + 3] = fmaf(qd, k4.w, num[v + 3]);
+                                }
                             }
                         }
+                        const float inv = 1.f / den;
+#pragma unroll
+                        for (int v = 0; v < DH; ++v) out[hh * DH + v] = num[v] * inv;
                     }
-                    const float inv = 1.f / den;
 #pragma unroll
-                    for (int v = 0; v < DH; ++v) out[hh * DH + v] = num[v] * inv;
-                }
+                    for (int j = 0; j < G; j += 8) {
+                        float o8[8];
 #pragma unroll
-                for (int j = 0; j < G; j += 8) {
-                    float o8[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) o8[i] = out[j + i];
-                    if (kAttnOnly) {
-                        if (g >= 0) store8(q, ref, c0 + j, o8);
-                    } else {
-                        umma::store_chunk(a1, P::LBO, tid, (c0 + j) / 8, o8);
+                        for (int i = 0; i < 8; ++i) o8[i] = out[j + i];
+                        if (kAttnOnly) {
+                            if (g >= 0) store8(q, ref, c0 + j, o8);
+                        } else {
+                            umma::store_chunk(a0, P::LBO, tid, KG + (c0 + j) / 8, o8);
+                        }
                     }
                 }
             }
@@ -242,20 +246,19 @@ __global__ void __launch_bounds__(192) loftr_query_tc_kernel(Q q, cfp_loftr_w w,
         }
     } else if (warp == 4) {
         // =============================================================== weight producer
-        if (lane == 0) {
+        {
             const bf16* wsrc = reinterpret_cast<const bf16*>(w.tc);
             int cc = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
                 for (int c = 0; c < NCHUNK; ++c, ++cc) {
                     const int slot = cc % P::NSLOT, round = cc / P::NSLOT;
                     if (round > 0) umma::mbar_wait(&bars.empty[slot], (round - 1) & 1);
-                    umma::mbar_expect_tx(&bars.full[slot], P::SLOT);
-                    umma::bulk_g2s(ring + (size_t)slot * P::SLOT, wsrc + (size_t)c * C * C, P::SLOT, &bars.full[slot]);
+                    umma::bulk_load(ring + (size_t)slot * P::SLOT, wsrc + (size_t)c * C * C, P::SLOT, &bars.full[slot]);
                 }
         }
     } else {
-        // =============================================================== MMA issuer
-        if (lane == 0) {
+        // =============================================================== MMA issuer (warp-uniform; elected lane issues)
+        {
             const uint32_t idesc = umma::idesc_bf16(128, C);
             const uint32_t a0s = umma::smem_u32(a0), a1s = umma::smem_u32(a1), rs = umma::smem_u32(ring);
             constexpr uint32_t LBO_B = C * 16;
@@ -284,7 +287,7 @@ __global__ void __launch_bounds__(192) loftr_query_tc_kernel(Q q, cfp_loftr_w w,
                 umma::commit(&bars.acc_ready);
                 if (kAttnOnly) continue;
                 wait_a();
-                block(a1s, 0, 0, false);                       // merge
+                block(a0s, KG, 0, false);                      // merge: msg sits in a0[:, C:2C)
                 umma::commit(&bars.acc_ready);
                 wait_a();
                 block(a0s, 0, 0, false);                       // W1 quadrants: (n0,k0) (n0,k1) (n1,k0) (n1,k1)
@@ -311,11 +314,12 @@ static int run_query_tc(const char* name, const Q& q, const cfp_loftr_w& w, cons
                         cudaStream_t st) {
     using P = ChainTC<C>;
     CFP_REQUIRE(w.tc != nullptr, "%s: bf16 path needs the packed tensor-core weights (cfp_loftr_w.tc)", name);
+    const int64_t ntiles = (q.rows + 127) / 128;
+    CFP_REQUIRE(q.rows < ((int64_t)1 << 31), "%s: %lld rows exceed the 32-bit row index", name, (long long)q.rows);
+    const int per_sm = ChainOcc<C>::CTAS;
+    const int grid = (int)(ntiles < 148 * per_sm ? ntiles : 148 * per_sm);
     auto k = loftr_query_tc_kernel<C, NH, kAttnOnly, Q>;
     if (int e = set_smem(k, P::SMEM)) return e;
-    const int64_t ntiles = (q.rows + 127) / 128;
-    const int per_sm = C >= 128 ? 1 : (C == 64 ? 2 : 4);
-    const int grid = (int)(ntiles < 148 * per_sm ? ntiles : 148 * per_sm);
     k<<<grid, 192, P::SMEM, st>>>(q, w, kv, ksum, (int)ntiles);
     return check_launch(name);
 }
@@ -338,7 +342,7 @@ __global__ void __launch_bounds__(192) lkpm_mlp_tc_kernel(bf16* __restrict__ fea
     uint8_t* a0 = smem;                          // LN(y)        [KG][129][16 B]
     uint8_t* a1 = a0 + KG * P::LBO;              // GELU(h_j)    [KG][129][16 B]
     uint8_t* ring = a1 + KG * P::LBO;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = umma::warp_idx_sync(), lane = tid & 31;
 
     if (tid == 0) {
         for (int i = 0; i < P::NSLOT; ++i) { umma::mbar_init(&bars.full[i], 1); umma::mbar_init(&bars.empty[i], 1); }
@@ -436,19 +440,18 @@ __global__ void __launch_bounds__(192) lkpm_mlp_tc_kernel(bf16* __restrict__ fea
             rows_sync();
         }
     } else if (warp == 4) {
-        if (lane == 0) {
+        {
             const bf16* wsrc = reinterpret_cast<const bf16*>(w.tc);
             int cc = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
                 for (int c = 0; c < 8; ++c, ++cc) {
                     const int slot = cc % P::NSLOT, round = cc / P::NSLOT;
                     if (round > 0) umma::mbar_wait(&bars.empty[slot], (round - 1) & 1);
-                    umma::mbar_expect_tx(&bars.full[slot], P::SLOT);
-                    umma::bulk_g2s(ring + (size_t)slot * P::SLOT, wsrc + (size_t)c * C * C, P::SLOT, &bars.full[slot]);
+                    umma::bulk_load(ring + (size_t)slot * P::SLOT, wsrc + (size_t)c * C * C, P::SLOT, &bars.full[slot]);
                 }
         }
     } else {
-        if (lane == 0) {
+        {
             const uint32_t idesc = umma::idesc_bf16(128, C);
             const uint32_t a0s = umma::smem_u32(a0), a1s = umma::smem_u32(a1), rs = umma::smem_u32(ring);
             constexpr uint32_t LBO_B = C * 16;
@@ -501,7 +504,7 @@ static int run_lkpm_mlp_tc(void* feat0, const void* y, int64_t rows, const cfp_l
     const int per_sm = C >= 128 ? 1 : (C == 64 ? 2 : 4);
     const int grid = (int)(ntiles < 148 * per_sm ? ntiles : 148 * per_sm);
     k<<<grid, 192, smem, st>>>((bf16*)feat0, (const bf16*)y, rows, w, (int)ntiles);
-    return check_launch("lkpm_mlp_tc");
+    return check_launch(C == 32 ? "lkpm_mlp_tc<32>" : C == 64 ? "lkpm_mlp_tc<64>" : "lkpm_mlp_tc<128>");
 }
 
 int lkpm_mlp_tc(void* feat0, const void* y, int64_t rows, int C, const cfp_lkpm_w& w, cudaStream_t st) {
@@ -545,7 +548,7 @@ __global__ void __launch_bounds__(192) kv_state_tc_kernel(Src src, int S, int S_
     uint8_t* a0 = smem;                            // x tile                [KG][129][16 B]
     uint8_t* a1 = a0 + KG * P::LBO;                // K | V | ones | zeros  [A1G][129][16 B]
     uint8_t* wsm = a1 + K::A1G * P::LBO;           // Wk, Wv blocks
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = umma::warp_idx_sync(), lane = tid & 31;
 
     if (tid == 0) {
         umma::mbar_init(&bars.full[0], 1);
@@ -615,9 +618,9 @@ __global__ void __launch_bounds__(192) kv_state_tc_kernel(Src src, int S, int S_
                 umma::fence_after_sync();
                 if (warp * 32 < C) {
                     const int m = warp * 32 + lane;
-                    float t[32], o[16];
-                    umma::tmem_ld16(umma::tmem_addr(tmem, warp * 32, 2 * C + warp * 32), *reinterpret_cast<float(*)[16]>(&t[0]));
-                    umma::tmem_ld16(umma::tmem_addr(tmem, warp * 32, 2 * C + warp * 32 + 16), *reinterpret_cast<float(*)[16]>(&t[16]));
+                    float t0[16], t1[16], o[16];
+                    umma::tmem_ld16(umma::tmem_addr(tmem, warp * 32, 2 * C + warp * 32), t0);
+                    umma::tmem_ld16(umma::tmem_addr(tmem, warp * 32, 2 * C + warp * 32 + 16), t1);
                     umma::tmem_ld16(umma::tmem_addr(tmem, warp * 32, 3 * C), o);
                     float* dst = kv + (size_t)g * (C * DH) + (size_t)m * DH;
 #pragma unroll
@@ -625,8 +628,10 @@ __global__ void __launch_bounds__(192) kv_state_tc_kernel(Src src, int S, int S_
                         if (lane / DH == sb) {
 #pragma unroll
                             for (int j = 0; j < DH; ++j) {
-                                if (kComplete) dst[j] = t[sb * DH + j];
-                                else atomicAdd(dst + j, t[sb * DH + j]);
+                                const int col = sb * DH + j;                  // compile-time after unrolling
+                                const float val = col < 16 ? t0[col & 15] : t1[col & 15];
+                                if (kComplete) dst[j] = val;
+                                else atomicAdd(dst + j, val);
                             }
                         }
                     if (kComplete) ksum[(size_t)g * C + m] = o[0];
@@ -642,12 +647,9 @@ __global__ void __launch_bounds__(192) kv_state_tc_kernel(Src src, int S, int S_
             umma::fence_before_sync();
         }
     } else if (warp == 4) {
-        if (lane == 0) {
-            umma::mbar_expect_tx(&bars.full[0], 4 * C * C);
-            umma::bulk_g2s(wsm, wkv_tc, 4 * C * C, &bars.full[0]);
-        }
+        umma::bulk_load(wsm, wkv_tc, 4 * C * C, &bars.full[0]);
     } else {
-        if (lane == 0) {
+        {
             const uint32_t idesc = umma::idesc_bf16(128, C);
             const uint32_t idesc_red = umma::idesc_bf16(128, K::NRED) | (1u << 15) | (1u << 16);   // A, B MN-major
             const uint32_t a0s = umma::smem_u32(a0), a1s = umma::smem_u32(a1), ws = umma::smem_u32(wsm);
@@ -718,20 +720,20 @@ static int run_kv_state_tc(const char* name, const Src& src, int S, int groups, 
     return check_launch(name);
 }
 
-#define CFP_KV_DISPATCH(NH, NAME)                                                              \
-    if (C == 32) return run_kv_state_tc<32, NH>(NAME, src, S, groups, wkv_tc, kv, ksum, st);   \
-    if (C == 64) return run_kv_state_tc<64, NH>(NAME, src, S, groups, wkv_tc, kv, ksum, st);   \
-    if (C == 128) return run_kv_state_tc<128, NH>(NAME, src, S, groups, wkv_tc, kv, ksum, st); \
+#define CFP_KV_DISPATCH(NH, NAME)                                                                     \
+    if (C == 32) return run_kv_state_tc<32, NH>(NAME ",32>", src, S, groups, wkv_tc, kv, ksum, st);   \
+    if (C == 64) return run_kv_state_tc<64, NH>(NAME ",64>", src, S, groups, wkv_tc, kv, ksum, st);   \
+    if (C == 128) return run_kv_state_tc<128, NH>(NAME ",128>", src, S, groups, wkv_tc, kv, ksum, st); \
     return fail("unsupported C=%d", C);
 
 int kv_tc_h2i(int C, const ZoneTokSrc<bf16>& src, int S, int groups, const void* wkv_tc, float* kv, float* ksum,
-              cudaStream_t st) { CFP_KV_DISPATCH(4, "kv_state_tc<hist2image>") }
+              cudaStream_t st) { CFP_KV_DISPATCH(4, "kv_state_tc<hist2image") }
 int kv_tc_lsa(int C, const WindowRows<bf16>& src, int S, int groups, const void* wkv_tc, float* kv, float* ksum,
-              cudaStream_t st) { CFP_KV_DISPATCH(8, "kv_state_tc<lsa>") }
+              cudaStream_t st) { CFP_KV_DISPATCH(8, "kv_state_tc<lsa") }
 int kv_tc_gsa(int C, const SrTokSrc& src, int S, int groups, const void* wkv_tc, float* kv, float* ksum,
-              cudaStream_t st) { CFP_KV_DISPATCH(8, "kv_state_tc<gsa>") }
+              cudaStream_t st) { CFP_KV_DISPATCH(8, "kv_state_tc<gsa") }
 int kv_tc_dapm(int C, const InsideSrc<bf16>& src, int S, int groups, const void* wkv_tc, float* kv, float* ksum,
-               cudaStream_t st) { CFP_KV_DISPATCH(4, "kv_state_tc<dapm>") }
+               cudaStream_t st) { CFP_KV_DISPATCH(4, "kv_state_tc<dapm") }
 
 // =====================================================================================
 // GSA sub-sampling conv on tensor cores (transformer.py:144-147): a stride-ws, ws x ws conv is a
@@ -755,7 +757,7 @@ __global__ void __launch_bounds__(192) sr_conv_tc_kernel(const bf16* __restrict_
     __shared__ SrBars bars;
     uint8_t* a_st = smem;                                // [2][KG][129][16 B]
     uint8_t* w_st = a_st + 2 * KG * P::LBO;              // [2][C x C]
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = umma::warp_idx_sync(), lane = tid & 31;
     const int ntap = ws * ws;
     const int t0 = blockIdx.y * taps_per_cta, t1 = min(t0 + taps_per_cta, ntap);
     const int64_t row0 = (int64_t)blockIdx.x * 128;
@@ -809,15 +811,13 @@ __global__ void __launch_bounds__(192) sr_conv_tc_kernel(const bf16* __restrict_
         }
         umma::fence_before_sync();
     } else if (warp == 4) {
-        if (lane == 0)
-            for (int t = t0; t < t1; ++t) {
-                const int n = t - t0, st = n & 1;
-                if (n >= 2) umma::mbar_wait(&bars.empty[st], ((n >> 1) - 1) & 1);
-                umma::mbar_expect_tx(&bars.w_full[st], P::SLOT);
-                umma::bulk_g2s(w_st + (size_t)st * P::SLOT, sr_tc + (size_t)t * C * C, P::SLOT, &bars.w_full[st]);
-            }
+        for (int t = t0; t < t1; ++t) {
+            const int n = t - t0, st = n & 1;
+            if (n >= 2) umma::mbar_wait(&bars.empty[st], ((n >> 1) - 1) & 1);
+            umma::bulk_load(w_st + (size_t)st * P::SLOT, sr_tc + (size_t)t * C * C, P::SLOT, &bars.w_full[st]);
+        }
     } else {
-        if (lane == 0) {
+        {
             const uint32_t idesc = umma::idesc_bf16(128, C);
             constexpr uint32_t LBO_B = C * 16;
             for (int t = t0; t < t1; ++t) {
@@ -882,7 +882,7 @@ static int run_sr_conv_tc(const void* feat0, float* sr_tok, int B, int H, int W,
     if (int err = set_smem(k, smem)) return err;
     k<<<dim3(tiles, splits), 192, smem, st>>>((const bf16*)feat0, sr_tok, rows, H, W, ws, nsx, Ns, (const bf16*)sr_tc,
                                                taps_per_cta);
-    if (int err = check_launch("sr_conv_tc")) return err;
+    if (int err = check_launch(C == 32 ? "sr_conv_tc<32>" : C == 64 ? "sr_conv_tc<64>" : "sr_conv_tc<128>")) return err;
     sr_bias_ln_kernel<C><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(sr_tok, rows, sr_b, g, b);
     return check_launch("sr_bias_ln");
 }
@@ -897,26 +897,26 @@ int sr_conv_ln_tc(const void* feat0, float* sr_tok, int B, int H, int W, int C, 
 
 // ---- entry points used by k_loftr.cu's layer implementations (bf16 only)
 #define CFP_TC_DISPATCH(NH, ATTN, NAME)                                                  \
-    if (C == 32) return run_query_tc<32, NH, ATTN>(NAME, q, w, kv, ksum, st);            \
-    if (C == 64) return run_query_tc<64, NH, ATTN>(NAME, q, w, kv, ksum, st);            \
-    if (C == 128) return run_query_tc<128, NH, ATTN>(NAME, q, w, kv, ksum, st);          \
+    if (C == 32) return run_query_tc<32, NH, ATTN>(NAME ",32>", q, w, kv, ksum, st);     \
+    if (C == 64) return run_query_tc<64, NH, ATTN>(NAME ",64>", q, w, kv, ksum, st);     \
+    if (C == 128) return run_query_tc<128, NH, ATTN>(NAME ",128>", q, w, kv, ksum, st);  \
     return fail("unsupported C=%d", C);
 
 int query_tc_h2i(int C, const ZonePatchRows<bf16>& q, const cfp_loftr_w& w, const float* kv, const float* ksum,
                  cudaStream_t st) {
-    CFP_TC_DISPATCH(4, false, "loftr_query_tc<hist2image>")
+    CFP_TC_DISPATCH(4, false, "loftr_query_tc<hist2image")
 }
 int query_tc_lsa(int C, const WindowRows<bf16>& q, const cfp_loftr_w& w, const float* kv, const float* ksum,
                  cudaStream_t st) {
-    CFP_TC_DISPATCH(8, false, "loftr_query_tc<lsa>")
+    CFP_TC_DISPATCH(8, false, "loftr_query_tc<lsa")
 }
 int query_tc_gsa(int C, const FrameRows<bf16>& q, const cfp_loftr_w& w, const float* kv, const float* ksum,
                  cudaStream_t st) {
-    CFP_TC_DISPATCH(8, false, "loftr_query_tc<gsa>")
+    CFP_TC_DISPATCH(8, false, "loftr_query_tc<gsa")
 }
 int query_tc_dapm(int C, const OutsideRows<bf16>& q, const cfp_loftr_w& w, const float* kv, const float* ksum,
                   cudaStream_t st) {
-    CFP_TC_DISPATCH(4, true, "attn_query_tc<dapm>")
+    CFP_TC_DISPATCH(4, true, "attn_query_tc<dapm")
 }
 
 }  // namespace cfp

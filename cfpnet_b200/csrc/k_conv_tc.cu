@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(192) conv3x3_tc_kernel(const bf16* __restrict_
     const uint32_t lbo_a = (uint32_t)cells * 16;
     uint8_t* a_buf = smem;                                  // [KG][cells][16 B]
     uint8_t* ring = a_buf + (size_t)P::KG * lbo_a;          // [NSLOT][SLOT_BYTES]
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = umma::warp_idx_sync(), lane = tid & 31;
     const int b = blockIdx.y, y0 = blockIdx.x * R;
     const int nsrc = in1 ? 2 : 1;
     const size_t frame = (size_t)b * H * W;
@@ -144,18 +144,15 @@ __global__ void __launch_bounds__(192) conv3x3_tc_kernel(const bf16* __restrict_
         umma::fence_before_sync();
     } else if (warp == 4) {
         // ---------------- weight producer (bulk async copies, L2 -> shared)
-        if (lane == 0) {
-            const int nchunk = nsrc * 9;
-            for (int c = 0; c < nchunk; ++c) {
-                const int slot = c % P::NSLOT, round = c / P::NSLOT;
-                if (round > 0) umma::mbar_wait(&bars.empty[slot], (round - 1) & 1);
-                umma::mbar_expect_tx(&bars.full[slot], P::SLOT_BYTES);
-                umma::bulk_g2s(ring + (size_t)slot * P::SLOT_BYTES, wpk + (size_t)c * C * C, P::SLOT_BYTES, &bars.full[slot]);
-            }
+        const int nchunk = nsrc * 9;
+        for (int c = 0; c < nchunk; ++c) {
+            const int slot = c % P::NSLOT, round = c / P::NSLOT;
+            if (round > 0) umma::mbar_wait(&bars.empty[slot], (round - 1) & 1);
+            umma::bulk_load(ring + (size_t)slot * P::SLOT_BYTES, wpk + (size_t)c * C * C, P::SLOT_BYTES, &bars.full[slot]);
         }
     } else {
-        // ---------------- MMA issuer
-        if (lane == 0) {
+        // ---------------- MMA issuer (whole warp runs the loop; one elected lane issues)
+        {
             const uint32_t idesc = umma::idesc_bf16(128, C);
             const uint32_t a0 = umma::smem_u32(a_buf), w0 = umma::smem_u32(ring);
             constexpr uint32_t lbo_b = C * 16;
@@ -211,7 +208,8 @@ static int conv_tc_launch(const void* in0, const void* in1, const void* wpk, con
     const unsigned wp_magic = (unsigned)((((uint64_t)1 << 32) + WP - 1) / WP);   // umulhi(i, magic) == i / WP for i*WP < 2^32
     k<<<grid, 192, smem, st>>>((const bf16*)in0, (const bf16*)in1, (const bf16*)wpk, shift, (const bf16*)residual,
                                (bf16*)out, H, W, R, cells, wp_magic, zy0, zy1, zx0, zx1);
-    return check_launch(in1 ? "conv3x3_tc<2C->C>" : "conv3x3_tc<C->C>");
+    return check_launch(in1 ? (C == 32 ? "conv3x3_tc<2C->C,32>" : C == 64 ? "conv3x3_tc<2C->C,64>" : "conv3x3_tc<2C->C,128>")
+                            : (C == 32 ? "conv3x3_tc<C->C,32>" : C == 64 ? "conv3x3_tc<C->C,64>" : "conv3x3_tc<C->C,128>"));
 }
 
 int conv3x3_tc(const void* in0, const void* in1, const void* wpk, const float* shift, const void* residual, void* out,

@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(192) dwconv_tc_kernel(const bf16* __restrict__
                                                         int B, DwGeom g, int items_per_cta, int total_items) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ DwBars bars;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = umma::warp_idx_sync(), lane = tid & 31;
     const uint32_t t_blk = 2 * g.KS * 32 * 16;                 // bytes of one T_dy block  [2*KS groups][32][8]
     const uint32_t t_bytes = g.K * t_blk;
     const uint32_t lbo_a = g.HP * 16;
@@ -165,9 +165,11 @@ __global__ void __launch_bounds__(192) dwconv_tc_kernel(const bf16* __restrict__
             const float sh = shift[it.c];
             umma::mbar_wait(&bars.acc_full[ab], (n >> 1) & 1);
             umma::fence_after_sync();
-            float v[32];
-            umma::tmem_ld16(umma::tmem_addr(tmem, warp * 32, ab * 32), *reinterpret_cast<float(*)[16]>(&v[0]));
-            umma::tmem_ld16(umma::tmem_addr(tmem, warp * 32, ab * 32 + 16), *reinterpret_cast<float(*)[16]>(&v[16]));
+            float v0[16], v1[16], v[32];
+            umma::tmem_ld16(umma::tmem_addr(tmem, warp * 32, ab * 32), v0);
+            umma::tmem_ld16(umma::tmem_addr(tmem, warp * 32, ab * 32 + 16), v1);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { v[j] = v0[j]; v[16 + j] = v1[j]; }
             umma::fence_before_sync();
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(umma::smem_u32(&bars.acc_empty[ab])) : "memory");
             const int y = it.mt * 128 + tid, x0 = it.xt * 32;
@@ -193,27 +195,25 @@ __global__ void __launch_bounds__(192) dwconv_tc_kernel(const bf16* __restrict__
         }
     } else if (warp == 4) {
         // ---------------- producer: Toeplitz blocks per channel, one bulk copy per work item
-        if (lane == 0) {
+        {
             int cur_c = -1, nt = 0;
             for (int i = i0; i < i1; ++i) {
                 const int n = i - i0, s = n % 3;
                 const DwItem it = dw_item(i, B, g);
                 if (it.c != cur_c) {
                     if (nt > 0) umma::mbar_wait(&bars.t_empty, (nt - 1) & 1);   // MMAs on the old blocks are done
-                    umma::mbar_expect_tx(&bars.t_full, t_bytes);
-                    umma::bulk_g2s(t_sm, toep + (size_t)it.c * g.K * (t_blk / 2), t_bytes, &bars.t_full);
+                    umma::bulk_load(t_sm, toep + (size_t)it.c * g.K * (t_blk / 2), t_bytes, &bars.t_full);
                     cur_c = it.c;
                     ++nt;
                 }
                 if (n >= 3) umma::mbar_wait(&bars.a_empty[s], ((n / 3) - 1) & 1);
                 const bf16* src = planes + ((((size_t)it.b * g.C + it.c) * g.WG + 4 * it.xt) * g.HP) * 8;
-                umma::mbar_expect_tx(&bars.a_full[s], a_bytes);
-                umma::bulk_g2s(a_sm + (size_t)s * a_stride, src, a_bytes, &bars.a_full[s]);
+                umma::bulk_load(a_sm + (size_t)s * a_stride, src, a_bytes, &bars.a_full[s]);
             }
         }
     } else {
-        // ---------------- MMA issuer
-        if (lane == 0) {
+        // ---------------- MMA issuer (warp-uniform control flow; one elected lane issues)
+        {
             const uint32_t idesc = umma::idesc_bf16(128, 32);
             const uint64_t tdesc0 = umma::smem_desc(umma::smem_u32(t_sm), 512);
             const uint32_t as0 = umma::smem_u32(a_sm);

@@ -18,7 +18,7 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(const bf16* __restri
     const uint32_t lbo_a = rows_a * 16, lbo_b = N * 16;
     uint8_t* a_tile = smem_raw;
     uint8_t* b_tile = a_tile + (K / 8) * lbo_a;
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = umma::warp_idx_sync();
 
     for (int i = tid; i < rows_a * (K / 8); i += 128) {
         int r = i / (K / 8), kg = i % (K / 8);
@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(const bf16* __restri
     umma::fence_after_sync();
     const uint32_t tmem = tmem_slot;
 
-    if (tid == 0) {
+    if (warp == 0) {
         const uint32_t idesc = umma::idesc_bf16(128, N);
         const uint32_t a0 = umma::smem_u32(a_tile) + row_shift * 16, b0 = umma::smem_u32(b_tile);
         for (int ks = 0; ks < K / 16; ++ks)

@@ -42,20 +42,41 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// ---------------------------------------------------------------- warp-uniform roles
+// Warp index as a value the compiler can prove warp-uniform (role branches then stay uniform and
+// descriptor arithmetic lives in uniform registers).
+__device__ __forceinline__ int warp_idx_sync() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+// elect.sync: exactly one lane of the (converged) warp gets true.  Issuing tcgen05.mma / commit /
+// bulk copies under this predicate (instead of `lane == 0`) lets ptxas emit a single predicated
+// UTCHMMA with uniform-register operands rather than a per-lane waterfall loop around every MMA.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ---------------------------------------------------------------- MMA issue / commit
-// D[tmem] (+)= A[smem] * B[smem]^T, M x N x 16, issued by ONE thread.
+// D[tmem] (+)= A[smem] * B[smem]^T, M x N x 16.  Called by ALL lanes of the (converged) MMA warp with
+// warp-uniform arguments; one elected lane issues the instruction.
 __device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                          bool accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
-        : "memory");
+    if (elect_one()) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
+            : "memory");
+    }
 }
-// Arrive on an mbarrier when all MMAs issued so far by this thread have completed.
+// Arrive on an mbarrier when all MMAs issued so far by this warp's elected lane have completed.
+// (elect.sync picks the same lane every time for a full mask, so commit tracks the MMAs above.)
 __device__ __forceinline__ void commit(uint64_t* mbar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(mbar))
-                 : "memory");
+    if (elect_one()) {
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(mbar))
+                     : "memory");
+    }
 }
 __device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
@@ -119,6 +140,14 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                      smem_u32(smem_dst)),
                  "l"(gmem_src), "r"(bytes), "r"(smem_u32(mbar))
                  : "memory");
+}
+
+// expect_tx + bulk copy by one elected lane; called by all lanes of the (converged) producer warp.
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* mbar) {
+    if (elect_one()) {
+        mbar_expect_tx(mbar, bytes);
+        bulk_g2s(smem_dst, gmem_src, bytes, mbar);
+    }
 }
 
 // ---------------------------------------------------------------- packing helpers
