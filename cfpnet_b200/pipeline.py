@@ -8,7 +8,7 @@ adds the host<->device staging used for the end-to-end measurement.
 """
 from __future__ import annotations
 
-from typing import Dict, List, Sequence
+from typing import Dict, Iterable, Iterator, List, Sequence, Tuple
 
 import torch
 import torch.nn as nn
@@ -56,3 +56,68 @@ class FusionPath(nn.Module):
             p.copy_(o, non_blocking=True)
         torch.cuda.current_stream(device).synchronize()
         return self._pinned_out
+
+    # ------------------------------------------------------------------ pipelined host-buffer entry
+    def stream_host(self, batches: Iterable[Dict[str, torch.Tensor]], patch_info, device, depth: int = 3,
+                    seeds: Iterable[int] | None = None) -> Iterator[Tuple[int, List[torch.Tensor]]]:
+        """Throughput form of :meth:`forward_host`: yields ``(index, [fused3, fused2, fused1])`` (pinned host
+        tensors, valid until ``depth`` more batches have been yielded) for every batch of pinned host inputs.
+
+        Three streams overlap the stages of consecutive batches: host->device copies of batch i+1 run
+        on a copy stream while batch i computes and the results of batch i-1 travel back on a third
+        stream.  Every batch still pays its full H2D + D2H; nothing is cached across batches.
+        ``seeds`` (one int per batch) seeds the positional-encoding crop before each forward."""
+        dev = torch.device(device)
+        comp = torch.cuda.current_stream(dev)
+        keys = ("x3", "x2", "x1", "hist_data", "mask")
+        # streams, device staging buffers and pinned result buffers persist across calls (pinned
+        # allocation costs tens of ms and synchronises the device; it must not sit in a hot loop)
+        cache = self.__dict__.setdefault("_stream_cache", {})
+        if (str(dev), depth) not in cache:
+            cache[(str(dev), depth)] = dict(
+                h2d=torch.cuda.Stream(dev), d2h=torch.cuda.Stream(dev),
+                slots=[dict(inp=None, out=None, in_ready=torch.cuda.Event(), comp_done=torch.cuda.Event(),
+                            out_ready=torch.cuda.Event(), busy=False) for _ in range(depth)])
+        st = cache[(str(dev), depth)]
+        h2d, d2h, slots = st["h2d"], st["d2h"], st["slots"]
+        for sl in slots:
+            sl["busy"] = False
+        pending: List[Tuple[int, int]] = []            # (batch index, slot)
+        seed_it = iter(seeds) if seeds is not None else None
+
+        def drain(idx_slot):
+            idx, si = idx_slot
+            slots[si]["out_ready"].synchronize()
+            return idx, slots[si]["out"]
+
+        for i, hb in enumerate(batches):
+            si = i % depth
+            sl = slots[si]
+            if sl["busy"]:                               # slot still owned by batch i-depth: hand it out first
+                yield drain(pending.pop(0))
+                sl["busy"] = False
+            if sl["inp"] is None or any(sl["inp"][k].shape != hb[k].shape or sl["inp"][k].dtype != hb[k].dtype for k in keys):
+                sl["inp"] = {k: torch.empty(hb[k].shape, dtype=hb[k].dtype, device=dev) for k in keys}
+            with torch.cuda.stream(h2d):
+                h2d.wait_event(sl["comp_done"])          # previous compute on these input buffers finished
+                for k in keys:
+                    sl["inp"][k].copy_(hb[k], non_blocking=True)
+                sl["in_ready"].record(h2d)
+            comp.wait_event(sl["in_ready"])
+            if seed_it is not None:
+                torch.manual_seed(next(seed_it))
+            d = sl["inp"]
+            outs = self.forward(d["x3"], d["x2"], d["x1"], d["hist_data"], d["mask"], patch_info)
+            sl["comp_done"].record(comp)
+            if sl["out"] is None or any(p.shape != o.shape or p.dtype != o.dtype for p, o in zip(sl["out"], outs)):
+                sl["out"] = [torch.empty(o.shape, dtype=o.dtype, pin_memory=True) for o in outs]
+            with torch.cuda.stream(d2h):
+                d2h.wait_event(sl["comp_done"])
+                for p, o in zip(sl["out"], outs):
+                    p.copy_(o, non_blocking=True)
+                    o.record_stream(d2h)
+                sl["out_ready"].record(d2h)
+            sl["busy"] = True
+            pending.append((i, si))
+        while pending:
+            yield drain(pending.pop(0))

@@ -217,3 +217,31 @@ def test_full_batch_properties():
             one = m(x[i:i + 1], feat1[i:i + 1], mask=inp["mask"][i:i + 1].to(DEV), patch_info=pi, **kw)
             # fp32 atomics in the attention state make the last bits order-dependent
             assert rel_l2(one, full[i:i + 1]) <= 1e-2
+
+
+def test_stream_host_equals_direct_forward():
+    """The pipelined host-buffer API (separate H2D / compute / D2H streams) returns, for every batch,
+    what a plain forward on device-resident copies of the same batch returns."""
+    from cfpnet_b200 import FusionPath
+    path = FusionPath(synth.COMBINE1_LAYERS)
+    path.hist_encoder.load_state_dict(synth.synthetic_state_dict(ref_keys()["hist_encoder"], seed=0))
+    for lv, name in ((3, "cross_atten3"), (2, "cross_atten2"), (1, "cross_atten1")):
+        getattr(path, name).load_state_dict(synth.synthetic_state_dict(ref_keys()[f"fusion_combine1_L{lv}"], seed=lv))
+    path = path.to(DEV).eval().set_dtype(torch.bfloat16)
+    batches, pi = [], None
+    for s in range(5):
+        inp = synth.make_inputs("G416", 2, seed=20 + s)
+        pi = inp["patch_info"]
+        batches.append({"x3": inp["x3"].bfloat16().pin_memory(), "x2": inp["x2"].bfloat16().pin_memory(),
+                        "x1": inp["x1"].bfloat16().pin_memory(), "hist_data": inp["hist_data"].pin_memory(),
+                        "mask": inp["mask"].pin_memory()})
+    got = {}
+    for idx, outs in path.stream_host(batches, pi, DEV, depth=2, seeds=range(100, 105)):
+        got[idx] = [o.clone() for o in outs]            # buffers are recycled after `depth` more batches
+    assert sorted(got) == list(range(5))
+    for i, hb in enumerate(batches):
+        torch.manual_seed(100 + i)
+        want = path(hb["x3"].to(DEV), hb["x2"].to(DEV), hb["x1"].to(DEV), hb["hist_data"].to(DEV), hb["mask"].to(DEV), pi)
+        torch.cuda.synchronize()
+        for g_, w_ in zip(got[i], want):
+            assert rel_l2(g_, w_) <= 1e-2
