@@ -313,42 +313,86 @@ def run_cfp(a):
         dist.destroy_process_group()
 
 
-# Per-frame algorithmic work of each kernel at G416 (derived in DESIGN.md §kernels):
-#   name -> (bound, units per frame) ; units = bytes/elem-size for "hbm" kernels, flops for "tensor"/"fma"
-def kernel_work(B, es):
-    N = {3: 884, 2: 3536, 1: 14144}
-    C = {3: 128, 2: 64, 1: 32}
-    K = {3: 7, 2: 15, 1: 31}
-    work = {}
-    # depthwise: FMA-pipe flops (2*N*C*k^2) and compulsory bytes (read + write the map once)
-    for lv in (3, 2, 1):
-        work[f"dwconv<{K[lv]}>"] = {"flops": 2.0 * N[lv] * C[lv] * K[lv] ** 2 * B, "bytes": 2.0 * N[lv] * C[lv] * es * B}
-    return work
+# Algorithmic work per LAUNCH of each kernel at G416 (derivations: DESIGN.md §4).
+#   flops  = useful multiply-adds x 2 of the op as the reference defines it (no padding / Toeplitz zeros)
+#   bytes  = compulsory HBM traffic: every activation the op reads + writes once, weights amortised
+LEVEL = {  # C: (N tokens, k, zone patch side p, window ws, inside Ni)
+    32: dict(N=14144, k=31, p=12, ws=12, Ni=9216, H=104, W=136),
+    64: dict(N=3536, k=15, p=6, ws=9, Ni=2304, H=52, W=68),
+    128: dict(N=884, k=7, p=3, ws=6, Ni=576, H=26, W=34),
+}
+
+
+def kernel_work(name, B, es):
+    import re
+    m = re.search(r"(\d+)>$", name)
+    if not m:
+        return None
+    v = int(m.group(1))
+    if name.startswith("dwconv"):                       # dwconv<k> / dwconv_tc<k>: v is the kernel size
+        C = {31: 32, 15: 64, 7: 128}[v]
+        g = LEVEL[C]
+        return dict(flops=2.0 * g["N"] * C * v * v * B, bytes=2.0 * g["N"] * C * es * B, bound="tensor" if "_tc" in name else "fma")
+    C = v
+    g = LEVEL[C]
+    N, Ni, p, ws = g["N"], g["Ni"], g["p"], g["ws"]
+    No = N - Ni
+    nwin = -(-g["H"] // ws) * -(-g["W"] // ws)
+    Ns = (g["H"] // ws) * (g["W"] // ws)
+    chain = 16.0 * C * C                                # q, merge, mlp0 (2Cx2C), mlp2 (2C->C): flops per query row
+    rows = {"hist2image": 64 * p * p, "lsa": nwin * ws * ws, "gsa": N, "dapm": No}
+    src = {"hist2image": 64 * 16, "lsa": nwin * ws * ws, "gsa": Ns, "dapm": Ni}
+    heads = {"hist2image": 4, "lsa": 8, "gsa": 8, "dapm": 4}
+    for kind in rows:
+        if f"<{kind}," in name:
+            dh = C // heads[kind]
+            if name.startswith("loftr_query"):
+                return dict(flops=(chain + 2.0 * C * dh) * rows[kind] * B, bytes=2.0 * rows[kind] * C * es * B, bound="tensor")
+            if name.startswith("attn_query"):
+                return dict(flops=(2.0 * C * C + 2.0 * C * dh) * rows[kind] * B, bytes=2.0 * rows[kind] * C * es * B, bound="tensor")
+            if name.startswith("kv_state"):
+                return dict(flops=(4.0 * C * C + 2.0 * C * dh) * src[kind] * B, bytes=src[kind] * C * es * B, bound="tensor")
+    if name.startswith("lkpm_mlp"):
+        return dict(flops=16.0 * N * C * C * B, bytes=3.0 * N * C * es * B, bound="tensor")
+    if name.startswith("conv3x3"):
+        cin = 2 * C if "2C->C" in name else C
+        return dict(flops=2.0 * N * cin * 9 * C * B, bytes=(cin + C + (C if cin == C else 0)) * N * es * B, bound="tensor")
+    if name.startswith("sr_conv"):
+        return dict(flops=2.0 * Ns * ws * ws * C * C * B, bytes=N * C * es * B, bound="tensor")
+    return None
+
+
+# dram bytes per launch of the top kernels from the committed `ncu --set full` captures (profiles/*.txt)
+NCU_TRAFFIC = {}
 
 
 def roofline_from_profile(prof, steps, B, es, peaks):
     total_ms = sum(v[1] for v in prof.values())
-    kernels = {k: {"launches_per_step": v[0] / steps, "ms_per_step": v[1] / steps,
-                   "share": v[1] / total_ms if total_ms else None} for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
-    top = max(prof.items(), key=lambda kv: kv[1][1])
-    name, (count, ms) = top
+    kernels = {}
+    for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+        rec = {"launches_per_step": v[0] / steps, "ms_per_step": v[1] / steps, "share": v[1] / total_ms if total_ms else None}
+        w = kernel_work(k, B, es)
+        if w:
+            avg_s = v[1] / v[0] * 1e-3
+            rec["TFLOPs"] = w["flops"] / avg_s / 1e12
+            rec["GBps"] = w["bytes"] / avg_s / 1e9
+        kernels[k] = rec
+    name, (count, ms) = max(prof.items(), key=lambda kv: kv[1][1])
     avg_s = ms / count * 1e-3
-    work = kernel_work(B, es)
-    if name in work:
-        # the large-kernel depthwise conv is FMA-pipe bound as a direct stencil; north_star asks
-        # for its HBM evidence, so report achieved compulsory GB/s against the measured copy bandwidth and give
-        # the FMA-pipe fraction beside it.
-        w = work[name]
+    w = kernel_work(name, B, es)
+    roof = {"kernel": name, "avg_launch_ms": avg_s * 1e3, "peak_source": peaks["source"], "traffic": NCU_TRAFFIC.get(name)}
+    if w and w["bound"] == "tensor":
+        ach = w["flops"] / avg_s / 1e12
+        roof.update(bound="tensor", achieved=ach, peak=peaks["bf16_tflops_sustained"], unit="TFLOP/s",
+                    frac=ach / peaks["bf16_tflops_sustained"],
+                    note="algorithmic (useful) flops of the op / CUDA-event time; peak = sustained cuBLAS bf16 (kernel timed inside a long step)",
+                    hbm={"achieved_GBps": w["bytes"] / avg_s / 1e9, "peak_GBps": peaks["hbm_gbs"],
+                         "frac": w["bytes"] / avg_s / 1e9 / peaks["hbm_gbs"]})
+    elif w:
         ach = w["bytes"] / avg_s / 1e9
-        fma_peak = 148 * 128 * 2 * 1.965e9 / 1e12
-        roof = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
-                "avg_launch_ms": avg_s * 1e3,
-                "fma_pipe": {"achieved_TFLOPs": w["flops"] / avg_s / 1e12, "peak_TFLOPs": fma_peak,
-                             "frac": w["flops"] / avg_s / 1e12 / fma_peak}}
+        roof.update(bound="hbm", achieved=ach, peak=peaks["hbm_gbs"], unit="GB/s", frac=ach / peaks["hbm_gbs"])
     else:
-        roof = {"kernel": name, "bound": "tensor", "achieved": None, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": None, "traffic": None, "peak_source": peaks["source"], "avg_launch_ms": avg_s * 1e3}
+        roof.update(bound="hbm", achieved=None, peak=peaks["hbm_gbs"], unit="GB/s", frac=None)
     return roof, kernels
 
 
