@@ -77,20 +77,160 @@ __device__ __forceinline__ void layernorm_reg(float (&v)[C], const float* __rest
     for (int i = 0; i < C; ++i) v[i] = v[i] * rstd * g[i] + b[i];
 }
 
+// ---------------------------------------------------------------------------------------
+// Row-thread stages of the chain (thread `tid` <-> token row0+tid <-> TMEM lane tid), shared by the
+// two kernel organisations below.
+template <int C, int NH, bool kAttnOnly, class Q>
+struct ChainStages {
+    using P = ChainTC<C>;
+    static constexpr int DH = C / NH, KG = P::KG, G = DH < 16 ? 16 : DH;
+    struct Row { typename Q::R ref; int g; };
+
+    // stage x: locate the row once, copy its C channels into a0[:, 0:C)
+    static __device__ __forceinline__ Row stage_x(const Q& q, int64_t row0, int tid, uint8_t* a0) {
+        const int64_t row = row0 + tid;
+        const bool live = row < q.rows;
+        Row r;
+        r.ref = q.locate(live ? row : 0);
+        r.g = live ? q.group(r.ref) : -1;
+        uint4 v[KG];
+#pragma unroll
+        for (int kg = 0; kg < KG; ++kg) v[kg] = live ? load8_bf16(q, r.ref, kg * 8) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int kg = 0; kg < KG; ++kg) *reinterpret_cast<uint4*>(a0 + (size_t)kg * P::LBO + tid * 16) = v[kg];
+        return r;
+    }
+    // epilogue 1: Q = elu(q)+1, msg = (Q KV) / (Q.Ksum + eps) -> a0[:, C:2C)  (or the message map)
+    static __device__ __forceinline__ void epi_attention(const Q& q, const Row& r, uint32_t tmem, int warp, int tid, uint8_t* a0,
+                                                         const float* __restrict__ kv, const float* __restrict__ ksum) {
+        const int g = r.g;
+#pragma unroll 1
+        for (int c0 = 0; c0 < C; c0 += G) {
+            float qv[G], out[G];
+#pragma unroll
+            for (int j = 0; j < G; j += 16) {
+                float t[16];
+                umma::tmem_ld16(umma::tmem_addr(tmem, warp * 32, c0 + j), t);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) qv[j + i] = elu1(t[i]);
+            }
+#pragma unroll
+            for (int hh = 0; hh < G / DH; ++hh) {
+                const int h0 = c0 + hh * DH;             // first channel of this head
+                float num[DH], den = kAttnEps;
+#pragma unroll
+                for (int v = 0; v < DH; ++v) num[v] = 0.f;
+                if (g >= 0) {
+                    const float* kvh = kv + (size_t)g * (C * DH) + (size_t)h0 * DH;
+                    const float* ksh = ksum + (size_t)g * C + h0;
+#pragma unroll
+                    for (int d = 0; d < DH; ++d) {
+                        const float qd = qv[hh * DH + d];
+                        den = fmaf(qd, ksh[d], den);
+#pragma unroll
+                        for (int v = 0; v < DH; v += 4) {
+                            const float4 k4 = *reinterpret_cast<const float4*>(kvh + d * DH + v);
+                            num[v] = fmaf(qd, k4.x, num[v]); num[v + 1] = fmaf(qd, k4.y, num[v + 1]);
+                            num[v + 2] = fmaf(qd, k4.z, num[v + 2]); num[v + 3] = fmaf(qd, k4.w, num[v + 3]);
+                        }
+                    }
+                }
+                const float inv = 1.f / den;
+#pragma unroll
+                for (int v = 0; v < DH; ++v) out[hh * DH + v] = num[v] * inv;
+            }
+#pragma unroll
+            for (int j = 0; j < G; j += 8) {
+                float o8[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o8[i] = out[j + i];
+                if (kAttnOnly) {
+                    if (g >= 0) store8(q, r.ref, c0 + j, o8);
+                } else {
+                    umma::store_chunk(a0, P::LBO, tid, KG + (c0 + j) / 8, o8);
+                }
+            }
+        }
+    }
+    // epilogue 2: LN1(merge) -> a0[:, C:2C)
+    static __device__ __forceinline__ void epi_ln1(const cfp_loftr_w& w, uint32_t tmem, int warp, int tid, uint8_t* a0) {
+        float v[C];
+        load_row<C>(tmem, warp, v);
+        layernorm_reg<C>(v, w.ln1_g, w.ln1_b);
+#pragma unroll
+        for (int j = 0; j < C; j += 8) {
+            float o8[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o8[i] = v[j + i];
+            umma::store_chunk(a0, P::LBO, tid, KG + j / 8, o8);
+        }
+    }
+    // epilogue 3: relu(W1 [x|msg]) -> a1 (2C columns)
+    static __device__ __forceinline__ void epi_relu(uint32_t tmem, int warp, int tid, uint8_t* a1) {
+#pragma unroll 1
+        for (int c0 = 0; c0 < 2 * C; c0 += 16) {
+            float t[16];
+            umma::tmem_ld16(umma::tmem_addr(tmem, warp * 32, c0), t);
+#pragma unroll
+            for (int j = 0; j < 16; j += 8) {
+                float o8[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o8[i] = fmaxf(t[j + i], 0.f);
+                umma::store_chunk(a1, P::LBO, tid, (c0 + j) / 8, o8);
+            }
+        }
+    }
+    // epilogue 4: x + LN2(W2 hidden) -> scatter through the provider
+    static __device__ __forceinline__ void epi_out(const Q& q, const Row& r, const cfp_loftr_w& w, uint32_t tmem, int warp, int tid,
+                                                   const uint8_t* a0) {
+        float v[C];
+        load_row<C>(tmem, warp, v);
+        layernorm_reg<C>(v, w.ln2_g, w.ln2_b);
+        if (r.g >= 0) {
+#pragma unroll
+            for (int j = 0; j < C; j += 8) {
+                float x8[8], o8[8];
+                unpack8(*reinterpret_cast<const uint4*>(a0 + (size_t)(j / 8) * P::LBO + tid * 16), x8);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o8[i] = x8[i] + v[j + i];
+                store8(q, r.ref, j, o8);
+            }
+        }
+    }
+};
+
+// D[:, dcol:dcol+C] (+)= A[:, kg0*8 : kg0*8+C] * Wblock^T   (called by a converged warp)
+template <int C>
+__device__ __forceinline__ void issue_block(uint32_t tmem_d, uint32_t a_addr, uint32_t w_addr, uint32_t idesc, bool acc_first) {
+    using P = ChainTC<C>;
+    uint64_t ad = umma::smem_desc(a_addr, P::LBO);
+    uint64_t wd = umma::smem_desc(w_addr, C * 16);
+#pragma unroll
+    for (int ks = 0; ks < C / 16; ++ks) {
+        umma::mma_bf16(tmem_d, ad, wd, idesc, acc_first || ks > 0);
+        ad = umma::desc_advance(ad, 2 * P::LBO);
+        wd = umma::desc_advance(wd, 2 * C * 16);
+    }
+}
+
 template <int C> struct ChainOcc { static constexpr int CTAS = C >= 128 ? 1 : (C == 64 ? 2 : 4); };
 
+// ---------------------------------------------------------------------------------------
+// Organisation A (C = 128): three warp roles.  warps 0-3 row threads, warp 4 streams weight blocks
+// through a ring (empty/full mbarriers), warp 5 issues the MMAs.
 template <int C, int NH, bool kAttnOnly, class Q>
 __global__ void __launch_bounds__(192, ChainOcc<C>::CTAS) loftr_query_tc_kernel(Q q, cfp_loftr_w w, const float* __restrict__ kv,
                                                              const float* __restrict__ ksum, int ntiles) {
     using P = ChainTC<C>;
-    constexpr int DH = C / NH, KG = P::KG, G = DH < 16 ? 16 : DH;
+    using S = ChainStages<C, NH, kAttnOnly, Q>;
+    constexpr int KG = P::KG;
     constexpr int NCHUNK = kAttnOnly ? 1 : 8;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ ChainBars bars;
-    uint8_t* a0 = smem;                  // [x | LN1(merge(msg))]  2C columns
-    uint8_t* a1 = a0 + P::ABUF;          // msg (C columns), later the MLP hidden (2C columns)
+    uint8_t* a0 = smem;                  // [x | msg, then LN1(merge(msg))]  2C columns
+    uint8_t* a1 = a0 + P::ABUF;          // the MLP hidden (2C columns)
     uint8_t* ring = a1 + P::ABUF;
-    const int tid = threadIdx.x, warp = umma::warp_idx_sync(), lane = tid & 31;
+    const int tid = threadIdx.x, warp = umma::warp_idx_sync();
 
     if (tid == 0) {
         for (int i = 0; i < P::NSLOT; ++i) { umma::mbar_init(&bars.full[i], 1); umma::mbar_init(&bars.empty[i], 1); }
@@ -105,205 +245,183 @@ __global__ void __launch_bounds__(192, ChainOcc<C>::CTAS) loftr_query_tc_kernel(
     const uint32_t tmem = bars.tmem_slot;
 
     if (warp < 4) {
-        // =============================================================== row threads
         uint32_t ph = 0;
+        auto hand_over = [&]() {          // operands staged / accumulator consumed -> MMA warp; then wait for its result
+            umma::fence_async_smem();
+            umma::fence_before_sync();
+            mbar_arrive(&bars.a_ready);
+            umma::mbar_wait(&bars.acc_ready, ph); ph ^= 1;
+            umma::fence_after_sync();
+        };
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const int64_t row0 = (int64_t)tile * 128;
-            // ---- stage x: thread = row; the row's geometry is located once and reused for the store
-            const int64_t row = row0 + tid;
-            const bool live = row < q.rows;
-            const typename Q::R ref = q.locate(live ? row : 0);
-            const int g = live ? q.group(ref) : -1;
-            {
-                uint4 v[KG];
-#pragma unroll
-                for (int kg = 0; kg < KG; ++kg) v[kg] = live ? load8_bf16(q, ref, kg * 8) : make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-                for (int kg = 0; kg < KG; ++kg) *reinterpret_cast<uint4*>(a0 + (size_t)kg * P::LBO + tid * 16) = v[kg];
-            }
-            umma::fence_async_smem();
-            mbar_arrive(&bars.a_ready);
-
-            // ---- epilogue 1: Q = elu(q)+1, msg = (Q KV) / (Q.Ksum + eps)
-            umma::mbar_wait(&bars.acc_ready, ph); ph ^= 1;
-            umma::fence_after_sync();
-            {
-#pragma unroll 1
-                for (int c0 = 0; c0 < C; c0 += G) {
-                    float qv[G], out[G];
-#pragma unroll
-                    for (int j = 0; j < G; j += 16) {
-                        float t[16];
-                        umma::tmem_ld16(umma::tmem_addr(tmem, warp * 32, c0 + j), t);
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) qv[j + i] = elu1(t[i]);
-                    }
-#pragma unroll
-                    for (int hh = 0; hh < G / DH; ++hh) {
-                        const int h0 = c0 + hh * DH;             // first channel of this head
-                        float num[DH], den = kAttnEps;
-#pragma unroll
-                        for (int v = 0; v < DH; ++v) num[v] = 0.f;
-                        if (g >= 0) {
-                            const float* kvh = kv + (size_t)g * (C * DH) + (size_t)h0 * DH;
-                            const float* ksh = ksum + (size_t)g * C + h0;
-#pragma unroll
-                            for (int d = 0; d < DH; ++d) {
-                                const float qd = qv[hh * DH + d];
-                                den = fmaf(qd, ksh[d], den);
-#pragma unroll
-                                for (int v = 0; v < DH; v += 4) {
-                                    const float4 k4 = *reinterpret_cast<const float4*>(kvh + d * DH + v);
-                                    num[v] = fmaf(qd, k4.x, num[v]); num[v + 1] = fmaf(qd, k4.y, num[v + 1]);
-                                    num[v + 2] = fmaf(qd, k4.z, num[v + 2]); num[v + 3] = fmaf(qd, k4.w, num[v + 3]);
-                                }
-                            }
-                        }
-                        const float inv = 1.f / den;
-#pragma unroll
-                        for (int v = 0; v < DH; ++v) out[hh * DH + v] = num[v] * inv;
-                    }
-#pragma unroll
-                    for (int j = 0; j < G; j += 8) {
-                        float o8[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) o8[i] = out[j + i];
-                        if (kAttnOnly) {
-                            if (g >= 0) store8(q, ref, c0 + j, o8);
-                        } else {
-                            umma::store_chunk(a0, P::LBO, tid, KG + (c0 + j) / 8, o8);
-                        }
-                    }
-                }
-            }
-            if (kAttnOnly) {
-                umma::fence_before_sync();
-                rows_sync();
-                continue;
-            }
-            umma::fence_async_smem();
-            umma::fence_before_sync();
-            mbar_arrive(&bars.a_ready);
-
-            // ---- epilogue 2: LN1(merge) -> second half of the cat tile
-            umma::mbar_wait(&bars.acc_ready, ph); ph ^= 1;
-            umma::fence_after_sync();
-            {
-                float v[C];
-                load_row<C>(tmem, warp, v);
-                layernorm_reg<C>(v, w.ln1_g, w.ln1_b);
-#pragma unroll
-                for (int j = 0; j < C; j += 8) {
-                    float o8[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) o8[i] = v[j + i];
-                    umma::store_chunk(a0, P::LBO, tid, KG + j / 8, o8);
-                }
-            }
-            umma::fence_async_smem();
-            umma::fence_before_sync();
-            mbar_arrive(&bars.a_ready);
-
-            // ---- epilogue 3: relu(W1 [x|msg]) -> hidden tile (2C columns)
-            umma::mbar_wait(&bars.acc_ready, ph); ph ^= 1;
-            umma::fence_after_sync();
-#pragma unroll 1
-            for (int c0 = 0; c0 < 2 * C; c0 += 16) {
-                float t[16];
-                umma::tmem_ld16(umma::tmem_addr(tmem, warp * 32, c0), t);
-#pragma unroll
-                for (int j = 0; j < 16; j += 8) {
-                    float o8[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) o8[i] = fmaxf(t[j + i], 0.f);
-                    umma::store_chunk(a1, P::LBO, tid, (c0 + j) / 8, o8);
-                }
-            }
-            umma::fence_async_smem();
-            umma::fence_before_sync();
-            mbar_arrive(&bars.a_ready);
-
-            // ---- epilogue 4: x + LN2(W2 hidden) -> scatter
-            umma::mbar_wait(&bars.acc_ready, ph); ph ^= 1;
-            umma::fence_after_sync();
-            {
-                float v[C];
-                load_row<C>(tmem, warp, v);
-                layernorm_reg<C>(v, w.ln2_g, w.ln2_b);
-                if (g >= 0) {
-#pragma unroll
-                    for (int j = 0; j < C; j += 8) {
-                        float x8[8], o8[8];
-                        unpack8(*reinterpret_cast<const uint4*>(a0 + (size_t)(j / 8) * P::LBO + tid * 16), x8);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) o8[i] = x8[i] + v[j + i];
-                        store8(q, ref, j, o8);
-                    }
-                }
+            const typename S::Row r = S::stage_x(q, (int64_t)tile * 128, tid, a0);
+            hand_over();
+            S::epi_attention(q, r, tmem, warp, tid, a0, kv, ksum);
+            if (!kAttnOnly) {
+                hand_over();
+                S::epi_ln1(w, tmem, warp, tid, a0);
+                hand_over();
+                S::epi_relu(tmem, warp, tid, a1);
+                hand_over();
+                S::epi_out(q, r, w, tmem, warp, tid, a0);
             }
             umma::fence_before_sync();
-            rows_sync();          // every row has read its x from a0 before the next tile is staged
+            rows_sync();          // every row is done with a0 / the accumulator before the next tile is staged
         }
     } else if (warp == 4) {
-        // =============================================================== weight producer
-        {
-            const bf16* wsrc = reinterpret_cast<const bf16*>(w.tc);
-            int cc = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
-                for (int c = 0; c < NCHUNK; ++c, ++cc) {
-                    const int slot = cc % P::NSLOT, round = cc / P::NSLOT;
-                    if (round > 0) umma::mbar_wait(&bars.empty[slot], (round - 1) & 1);
-                    umma::bulk_load(ring + (size_t)slot * P::SLOT, wsrc + (size_t)c * C * C, P::SLOT, &bars.full[slot]);
-                }
-        }
-    } else {
-        // =============================================================== MMA issuer (warp-uniform; elected lane issues)
-        {
-            const uint32_t idesc = umma::idesc_bf16(128, C);
-            const uint32_t a0s = umma::smem_u32(a0), a1s = umma::smem_u32(a1), rs = umma::smem_u32(ring);
-            constexpr uint32_t LBO_B = C * 16;
-            uint32_t ph = 0;
-            int cc = 0;
-            // one [C x C] block: D[:, dcol:dcol+C] (+)= A[:, kg0*8 : kg0*8+C] * Wblock^T
-            auto block = [&](uint32_t abase, int kg0, int dcol, bool acc_first) {
+        const bf16* wsrc = reinterpret_cast<const bf16*>(w.tc);
+        int cc = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+            for (int c = 0; c < NCHUNK; ++c, ++cc) {
                 const int slot = cc % P::NSLOT, round = cc / P::NSLOT;
-                umma::mbar_wait(&bars.full[slot], round & 1);
-                umma::fence_after_sync();
-                uint64_t ad = umma::smem_desc(abase + kg0 * P::LBO, P::LBO);
-                uint64_t wd = umma::smem_desc(rs + slot * P::SLOT, LBO_B);
-#pragma unroll
-                for (int ks = 0; ks < C / 16; ++ks) {
-                    umma::mma_bf16(tmem + dcol, ad, wd, idesc, acc_first || ks > 0);
-                    ad = umma::desc_advance(ad, 2 * P::LBO);
-                    wd = umma::desc_advance(wd, 2 * LBO_B);
-                }
-                umma::commit(&bars.empty[slot]);
-                ++cc;
-            };
-            auto wait_a = [&]() { umma::mbar_wait(&bars.a_ready, ph); ph ^= 1; umma::fence_after_sync(); };
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                wait_a();
-                block(a0s, 0, 0, false);                       // q
-                umma::commit(&bars.acc_ready);
-                if (kAttnOnly) continue;
-                wait_a();
-                block(a0s, KG, 0, false);                      // merge: msg sits in a0[:, C:2C)
-                umma::commit(&bars.acc_ready);
-                wait_a();
-                block(a0s, 0, 0, false);                       // W1 quadrants: (n0,k0) (n0,k1) (n1,k0) (n1,k1)
-                block(a0s, KG, 0, true);
-                block(a0s, 0, C, false);
-                block(a0s, KG, C, true);
-                umma::commit(&bars.acc_ready);
-                wait_a();
-                block(a1s, 0, 0, false);                       // W2 K-halves
-                block(a1s, KG, 0, true);
-                umma::commit(&bars.acc_ready);
+                if (round > 0) umma::mbar_wait(&bars.empty[slot], (round - 1) & 1);
+                umma::bulk_load(ring + (size_t)slot * P::SLOT, wsrc + (size_t)c * C * C, P::SLOT, &bars.full[slot]);
             }
+    } else {
+        const uint32_t idesc = umma::idesc_bf16(128, C);
+        const uint32_t a0s = umma::smem_u32(a0), a1s = umma::smem_u32(a1), rs = umma::smem_u32(ring);
+        uint32_t ph = 0;
+        int cc = 0;
+        auto block = [&](uint32_t abase, int kg0, int dcol, bool acc_first) {
+            const int slot = cc % P::NSLOT, round = cc / P::NSLOT;
+            umma::mbar_wait(&bars.full[slot], round & 1);
+            umma::fence_after_sync();
+            issue_block<C>(tmem + dcol, abase + kg0 * P::LBO, rs + slot * P::SLOT, idesc, acc_first);
+            umma::commit(&bars.empty[slot]);
+            ++cc;
+        };
+        auto wait_a = [&]() { umma::mbar_wait(&bars.a_ready, ph); ph ^= 1; umma::fence_after_sync(); };
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            wait_a();
+            block(a0s, 0, 0, false);                       // q
+            umma::commit(&bars.acc_ready);
+            if (kAttnOnly) continue;
+            wait_a();
+            block(a0s, KG, 0, false);                      // merge: msg sits in a0[:, C:2C)
+            umma::commit(&bars.acc_ready);
+            wait_a();
+            block(a0s, 0, 0, false);                       // W1 quadrants: (n0,k0) (n0,k1) (n1,k0) (n1,k1)
+            block(a0s, KG, 0, true);
+            block(a0s, 0, C, false);
+            block(a0s, KG, C, true);
+            umma::commit(&bars.acc_ready);
+            wait_a();
+            block(a1s, 0, 0, false);                       // W2 K-halves
+            block(a1s, KG, 0, true);
+            umma::commit(&bars.acc_ready);
         }
     }
     __syncthreads();
     if (warp == 4) {
+        umma::fence_after_sync();
+        umma::tmem_dealloc(tmem, P::TMEM_COLS);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Organisation B (C <= 64): one role.  The 128 row threads ARE the CTA; after a block barrier warp 0
+// issues the stage's MMAs itself and schedules the weight-block prefetches at the points where the
+// ring slots are known to be free (right after an accumulator wait), so there are no service warps
+// (their registers bought nothing), no empty-barriers and one mbarrier hand-off per stage instead
+// of two.  More CTAs fit per SM, which is what these latency-bound chains need.
+template <int C> struct MonoOcc { static constexpr int CTAS = C == 32 ? 5 : 2; };
+struct MonoBars {
+    uint64_t full[4], acc_ready;
+    uint32_t tmem_slot;
+};
+
+template <int C, int NH, bool kAttnOnly, class Q>
+__global__ void __launch_bounds__(128, MonoOcc<C>::CTAS) loftr_query_mono_kernel(Q q, cfp_loftr_w w, const float* __restrict__ kv,
+                                                                const float* __restrict__ ksum, int ntiles) {
+    using P = ChainTC<C>;
+    using S = ChainStages<C, NH, kAttnOnly, Q>;
+    constexpr int KG = P::KG, NB = kAttnOnly ? 1 : 8;      // weight blocks per tile
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ MonoBars bars;
+    uint8_t* a0 = smem;
+    uint8_t* a1 = a0 + P::ABUF;
+    uint8_t* ring = a1 + (kAttnOnly ? 0 : P::ABUF);        // 4 slots
+    const int tid = threadIdx.x, warp = umma::warp_idx_sync();
+
+    if (tid == 0) {
+        for (int i = 0; i < 4; ++i) umma::mbar_init(&bars.full[i], 1);
+        umma::mbar_init(&bars.acc_ready, 1);
+        umma::fence_mbar_init();
+    }
+    if (warp == 0) umma::tmem_alloc(&bars.tmem_slot, P::TMEM_COLS);
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = bars.tmem_slot;
+    const uint32_t idesc = umma::idesc_bf16(128, C);
+    const uint32_t a0s = umma::smem_u32(a0), a1s = umma::smem_u32(a1), rs = umma::smem_u32(ring);
+    const bf16* wsrc = reinterpret_cast<const bf16*>(w.tc);
+    const int my_tiles = blockIdx.x < ntiles ? (ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    const long total_blocks = (long)my_tiles * NB;
+
+    // weight block `seq` (running over this CTA's tiles) lives in slot seq % 4, parity (seq / 4) & 1
+    auto prefetch = [&](long seq) {                          // warp 0 only, converged
+        if (seq < total_blocks) {
+            const int slot = (int)(seq & 3);
+            umma::bulk_load(ring + (size_t)slot * P::SLOT, wsrc + (size_t)(seq % NB) * C * C, P::SLOT, &bars.full[slot]);
+        }
+    };
+    auto block = [&](long seq, uint32_t a_addr, int dcol, bool acc_first) {   // warp 0 only
+        const int slot = (int)(seq & 3);
+        umma::mbar_wait(&bars.full[slot], (uint32_t)((seq >> 2) & 1));
+        umma::fence_after_sync();
+        issue_block<C>(tmem + dcol, a_addr, rs + slot * P::SLOT, idesc, acc_first);
+    };
+    uint32_t ph = 0;
+    // operands staged by all rows -> barrier -> warp 0 issues `mmas` -> everyone waits for the accumulator
+    auto stage = [&](auto mmas) {
+        umma::fence_async_smem();
+        umma::fence_before_sync();
+        __syncthreads();
+        if (warp == 0) {
+            umma::fence_after_sync();
+            mmas();
+            umma::commit(&bars.acc_ready);
+        }
+        umma::mbar_wait(&bars.acc_ready, ph); ph ^= 1;
+        umma::fence_after_sync();
+    };
+
+    if (warp == 0)
+        for (long s0 = 0; s0 < 4; ++s0) prefetch(s0);
+    long base = 0;                                          // sequence number of this tile's first block
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, base += NB) {
+        const typename S::Row r = S::stage_x(q, (int64_t)tile * 128, tid, a0);
+        stage([&] { block(base + 0, a0s, 0, false); });                                   // q
+        if (kAttnOnly) {
+            if (warp == 0) prefetch(base + 4);               // slot of block `base` is free again
+            S::epi_attention(q, r, tmem, warp, tid, a0, kv, ksum);
+            continue;                                        // next stage() barrier orders a0 / TMEM reuse
+        }
+        S::epi_attention(q, r, tmem, warp, tid, a0, kv, ksum);
+        stage([&] { block(base + 1, a0s + KG * P::LBO, 0, false); });                     // merge
+        if (warp == 0) { prefetch(base + 4); prefetch(base + 5); }                        // blocks 0,1 consumed
+        S::epi_ln1(w, tmem, warp, tid, a0);
+        stage([&] {                                                                        // W1 quadrants
+            block(base + 2, a0s, 0, false);
+            block(base + 3, a0s + KG * P::LBO, 0, true);
+            block(base + 4, a0s, C, false);
+            block(base + 5, a0s + KG * P::LBO, C, true);
+        });
+        if (warp == 0) { prefetch(base + 6); prefetch(base + 7); prefetch(base + 8); prefetch(base + 9); }
+        S::epi_relu(tmem, warp, tid, a1);
+        stage([&] {                                                                        // W2 K-halves
+            block(base + 6, a1s, 0, false);
+            block(base + 7, a1s + KG * P::LBO, 0, true);
+        });
+        if (warp == 0) { prefetch(base + 10); prefetch(base + 11); }
+        S::epi_out(q, r, w, tmem, warp, tid, a0);
+        // the next tile's stage_x overwrites a0[:, 0:C), which epi_out of other rows may still read
+        __syncthreads();
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) {
         umma::fence_after_sync();
         umma::tmem_dealloc(tmem, P::TMEM_COLS);
     }
@@ -316,11 +434,20 @@ static int run_query_tc(const char* name, const Q& q, const cfp_loftr_w& w, cons
     CFP_REQUIRE(w.tc != nullptr, "%s: bf16 path needs the packed tensor-core weights (cfp_loftr_w.tc)", name);
     const int64_t ntiles = (q.rows + 127) / 128;
     CFP_REQUIRE(q.rows < ((int64_t)1 << 31), "%s: %lld rows exceed the 32-bit row index", name, (long long)q.rows);
-    const int per_sm = ChainOcc<C>::CTAS;
-    const int grid = (int)(ntiles < 148 * per_sm ? ntiles : 148 * per_sm);
-    auto k = loftr_query_tc_kernel<C, NH, kAttnOnly, Q>;
-    if (int e = set_smem(k, P::SMEM)) return e;
-    k<<<grid, 192, P::SMEM, st>>>(q, w, kv, ksum, (int)ntiles);
+    if constexpr (C <= 64) {
+        constexpr size_t smem = (kAttnOnly ? 1 : 2) * (size_t)P::ABUF + 4 * (size_t)P::SLOT;
+        const int per_sm = MonoOcc<C>::CTAS;
+        const int grid = (int)(ntiles < 148 * per_sm ? ntiles : 148 * per_sm);
+        auto k = loftr_query_mono_kernel<C, NH, kAttnOnly, Q>;
+        if (int e = set_smem(k, smem)) return e;
+        k<<<grid, 128, smem, st>>>(q, w, kv, ksum, (int)ntiles);
+    } else {
+        const int per_sm = ChainOcc<C>::CTAS;
+        const int grid = (int)(ntiles < 148 * per_sm ? ntiles : 148 * per_sm);
+        auto k = loftr_query_tc_kernel<C, NH, kAttnOnly, Q>;
+        if (int e = set_smem(k, P::SMEM)) return e;
+        k<<<grid, 192, P::SMEM, st>>>(q, w, kv, ksum, (int)ntiles);
+    }
     return check_launch(name);
 }
 
