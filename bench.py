@@ -223,12 +223,12 @@ def run_cfp(a):
             outs = step(i)
         d2h = sum(o.numel() * o.element_size() for o in outs)
         barrier()
-        if sampler:                         # let nvidia-smi finish its start-up before timing
+        if sampler:                         # let nvidia-smi finish its start-up before timing (rank 0 only)
             while not sampler.samples and sampler.is_alive() and time.perf_counter() - sampler_t < 5.0:
                 time.sleep(0.05)
-            for i in range(2):
-                step(i)
-            barrier()
+        for i in range(2):                  # every rank: same sequence of steps and collectives
+            step(i)
+        barrier()
         # ---- device-resident throughput ("value")
         if sampler:
             sampler.mark_begin()
