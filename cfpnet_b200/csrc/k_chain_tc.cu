@@ -22,6 +22,7 @@
 #include "cfp_internal.h"
 #include "providers.cuh"
 #include "umma.cuh"
+#include <cuda_fp16.h>
 
 namespace cfp {
 
@@ -74,7 +75,13 @@ __device__ __forceinline__ void layernorm_reg(float (&v)[C], const float* __rest
     for (int i = 0; i < C; ++i) { v[i] -= mean; q += v[i] * v[i]; }
     const float rstd = rsqrtf(q * (1.f / C) + kLnEps);
 #pragma unroll
-    for (int i = 0; i < C; ++i) v[i] = v[i] * rstd * g[i] + b[i];
+    for (int i = 0; i < C; i += 4) {                     // gamma / beta as 16-byte loads (warp-uniform addresses)
+        const float4 g4 = *reinterpret_cast<const float4*>(g + i), b4 = *reinterpret_cast<const float4*>(b + i);
+        v[i] = fmaf(v[i] * rstd, g4.x, b4.x);
+        v[i + 1] = fmaf(v[i + 1] * rstd, g4.y, b4.y);
+        v[i + 2] = fmaf(v[i + 2] * rstd, g4.z, b4.z);
+        v[i + 3] = fmaf(v[i + 3] * rstd, g4.w, b4.w);
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -454,30 +461,57 @@ static int run_query_tc(const char* name, const Q& q, const cfp_loftr_w& w, cons
 // =====================================================================================
 // LKPM pointwise half on tensor cores (convnext.py:49-58):
 //   out = x + W2 GELU(W1 LN(y) + b1) + b2,   W1: C -> 4C, W2: 4C -> C
-// The 4C hidden dimension is walked in four C-wide slices j: h_j = LN(y) W1_j^T (TMEM cols
-// [0,C)), GELU in registers -> bf16 A tile, out += h_j W2_j^T (TMEM cols [C,2C)); the out
-// accumulator stays in TMEM across the four slices.  MMA2_j and MMA1_{j+1} are issued back to
-// back, so the tensor pipe works on slice j+1 while the row threads apply GELU to slice j.
-// Weight blocks in consumption order: W1_0, W2_0, W1_1, W2_1, W1_2, W2_2, W1_3, W2_3.
+// The 4C hidden dimension is walked in 128-wide slices j (1, 2 or 4 of them): h_j = LN(y) W1_j^T
+// (TMEM cols [0,128)), GELU in registers -> bf16 A tile, out += h_j W2_j^T; the out accumulator stays
+// in TMEM across slices (for C = 32 there is a single slice and out reuses the h columns).  MMA2_j and
+// MMA1_{j+1} are issued back to back, so the tensor pipe works on slice j+1 while the row threads
+// apply GELU to slice j.  Weight blocks (all 256*C bytes) in consumption order: W1_0, W2_0, W1_1, ...
+// GELU: tanh form evaluated as packed fp16x2 (tanh.approx.f16x2): |dev| <= 5e-4 from the erf form,
+// i.e. below 1/8 bf16 ulp of the result for |y| >= 0.06; the epilogue is ALU-bound at small C and this
+// is ~3x fewer instructions than erff.
+__device__ __forceinline__ uint32_t gelu_tanh_bf16x2(float x0, float x1) {
+    const __half2 h = __floats2half2_rn(x0, x1);
+    const __half2 k0 = __float2half2_rn(0.7978845608f), k1 = __float2half2_rn(0.0356774081f);
+    const __half2 inner = __hmul2(h, __hfma2(__hmul2(h, h), k1, k0));
+    uint32_t ti = *reinterpret_cast<const uint32_t*>(&inner), to;
+    asm("tanh.approx.f16x2 %0, %1;\n" : "=r"(to) : "r"(ti));
+    const __half2 t = *reinterpret_cast<const __half2*>(&to);
+    const __half2 hh = __hmul2(h, __float2half2_rn(0.5f));
+    const float2 f = __half22float2(__hfma2(hh, t, hh));
+    return umma::pack_bf16(f.x, f.y);
+}
+
+template <int C> struct MlpTC {
+    static constexpr int NS = 128;                       // hidden slice width
+    static constexpr int NSL = 4 * C / NS;               // slices: 1, 2, 4
+    static constexpr int BLK = 256 * C;                  // bytes of one weight block
+    static constexpr int NBLK = 2 * NSL;                 // blocks per tile
+    static constexpr int NSLOT = C >= 128 ? 2 : (C == 64 ? 4 : 2);
+    static constexpr int OUT_COL = NSL == 1 ? 0 : NS;    // out accumulator columns
+    static constexpr int TMEM_COLS = NSL == 1 ? 128 : 256;
+    static constexpr size_t SMEM = (size_t)(C / 8 + 16) * ChainTC<C>::LBO + (size_t)NSLOT * BLK;
+};
+
 template <int C>
 __global__ void __launch_bounds__(192) lkpm_mlp_tc_kernel(bf16* __restrict__ feat0, const bf16* __restrict__ y,
                                                           int64_t rows, cfp_lkpm_w w, int ntiles) {
     using P = ChainTC<C>;
+    using M = MlpTC<C>;
     constexpr int KG = P::KG;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ ChainBars bars;
     uint8_t* a0 = smem;                          // LN(y)        [KG][129][16 B]
-    uint8_t* a1 = a0 + KG * P::LBO;              // GELU(h_j)    [KG][129][16 B]
-    uint8_t* ring = a1 + KG * P::LBO;
-    const int tid = threadIdx.x, warp = umma::warp_idx_sync(), lane = tid & 31;
+    uint8_t* a1 = a0 + KG * P::LBO;              // GELU(h_j)    [16][129][16 B]
+    uint8_t* ring = a1 + 16 * P::LBO;
+    const int tid = threadIdx.x, warp = umma::warp_idx_sync();
 
     if (tid == 0) {
-        for (int i = 0; i < P::NSLOT; ++i) { umma::mbar_init(&bars.full[i], 1); umma::mbar_init(&bars.empty[i], 1); }
+        for (int i = 0; i < M::NSLOT; ++i) { umma::mbar_init(&bars.full[i], 1); umma::mbar_init(&bars.empty[i], 1); }
         umma::mbar_init(&bars.a_ready, 128);
         umma::mbar_init(&bars.acc_ready, 1);
         umma::fence_mbar_init();
     }
-    if (warp == 4) umma::tmem_alloc(&bars.tmem_slot, P::TMEM_COLS);
+    if (warp == 4) umma::tmem_alloc(&bars.tmem_slot, M::TMEM_COLS);
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
@@ -486,20 +520,15 @@ __global__ void __launch_bounds__(192) lkpm_mlp_tc_kernel(bf16* __restrict__ fea
     if (warp < 4) {
         uint32_t ph = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const int64_t row0 = (int64_t)tile * 128;
-            for (int i = tid; i < 128 * KG; i += 128) {          // coalesced copy of the y tile
-                const int r = i / KG, kg = i % KG;
-                uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                if (row0 + r < rows) v = *reinterpret_cast<const uint4*>(y + (row0 + r) * C + kg * 8);
-                *reinterpret_cast<uint4*>(a0 + (size_t)kg * P::LBO + r * 16) = v;
-            }
-            rows_sync();
-            {   // channels-last LayerNorm (eps 1e-6) of row `tid`, in place
+            const int64_t row = (int64_t)tile * 128 + tid;
+            {   // channels-last LayerNorm (eps 1e-6) of row `tid` -> a0
                 float v[C];
 #pragma unroll
                 for (int j = 0; j < C; j += 8) {
                     float t[8];
-                    unpack8(*reinterpret_cast<const uint4*>(a0 + (size_t)(j / 8) * P::LBO + tid * 16), t);
+                    uint4 u = make_uint4(0u, 0u, 0u, 0u);
+                    if (row < rows) u = *reinterpret_cast<const uint4*>(y + row * C + j);
+                    unpack8(u, t);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) v[j + i] = t[i];
                 }
@@ -513,28 +542,35 @@ __global__ void __launch_bounds__(192) lkpm_mlp_tc_kernel(bf16* __restrict__ fea
                 const float rstd = rsqrtf(q * (1.f / C) + kLkpmLnEps);
 #pragma unroll
                 for (int j = 0; j < C; j += 8) {
-                    float o8[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) o8[i] = v[j + i] * rstd * w.ln_g[j + i] + w.ln_b[j + i];
+                    const float4 g0 = *reinterpret_cast<const float4*>(w.ln_g + j), g1 = *reinterpret_cast<const float4*>(w.ln_g + j + 4);
+                    const float4 b0 = *reinterpret_cast<const float4*>(w.ln_b + j), b1 = *reinterpret_cast<const float4*>(w.ln_b + j + 4);
+                    const float o8[8] = {fmaf(v[j] * rstd, g0.x, b0.x),     fmaf(v[j + 1] * rstd, g0.y, b0.y),
+                                         fmaf(v[j + 2] * rstd, g0.z, b0.z), fmaf(v[j + 3] * rstd, g0.w, b0.w),
+                                         fmaf(v[j + 4] * rstd, g1.x, b1.x), fmaf(v[j + 5] * rstd, g1.y, b1.y),
+                                         fmaf(v[j + 6] * rstd, g1.z, b1.z), fmaf(v[j + 7] * rstd, g1.w, b1.w)};
                     umma::store_chunk(a0, P::LBO, tid, j / 8, o8);
                 }
             }
             umma::fence_async_smem();
             mbar_arrive(&bars.a_ready);
 #pragma unroll 1
-            for (int js = 0; js < 4; ++js) {                     // hidden slice js: GELU(h + b1) -> a1
+            for (int js = 0; js < M::NSL; ++js) {                // hidden slice js: GELU(h + b1) -> a1
                 umma::mbar_wait(&bars.acc_ready, ph); ph ^= 1;
                 umma::fence_after_sync();
 #pragma unroll 1
-                for (int c0 = 0; c0 < C; c0 += 16) {
+                for (int c0 = 0; c0 < M::NS; c0 += 16) {
                     float t[16];
                     umma::tmem_ld16(umma::tmem_addr(tmem, warp * 32, c0), t);
+                    const float* bias = w.pw1_b + js * M::NS + c0;
 #pragma unroll
                     for (int j = 0; j < 16; j += 8) {
-                        float o8[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) o8[i] = gelu_erf_fast(t[j + i] + w.pw1_b[js * C + c0 + j + i]);
-                        umma::store_chunk(a1, P::LBO, tid, (c0 + j) / 8, o8);
+                        const float4 ba = *reinterpret_cast<const float4*>(bias + j), bb = *reinterpret_cast<const float4*>(bias + j + 4);
+                        uint4 u;
+                        u.x = gelu_tanh_bf16x2(t[j + 0] + ba.x, t[j + 1] + ba.y);
+                        u.y = gelu_tanh_bf16x2(t[j + 2] + ba.z, t[j + 3] + ba.w);
+                        u.z = gelu_tanh_bf16x2(t[j + 4] + bb.x, t[j + 5] + bb.y);
+                        u.w = gelu_tanh_bf16x2(t[j + 6] + bb.z, t[j + 7] + bb.w);
+                        *reinterpret_cast<uint4*>(a1 + (size_t)((c0 + j) / 8) * P::LBO + tid * 16) = u;
                     }
                 }
                 umma::fence_async_smem();
@@ -543,22 +579,22 @@ __global__ void __launch_bounds__(192) lkpm_mlp_tc_kernel(bf16* __restrict__ fea
             }
             umma::mbar_wait(&bars.acc_ready, ph); ph ^= 1;       // out accumulator complete
             umma::fence_after_sync();
-            const int64_t row = row0 + tid;
 #pragma unroll 1
             for (int c0 = 0; c0 < C; c0 += 16) {
                 float t[16];
-                umma::tmem_ld16(umma::tmem_addr(tmem, warp * 32, C + c0), t);
+                umma::tmem_ld16(umma::tmem_addr(tmem, warp * 32, M::OUT_COL + c0), t);
                 if (row < rows) {
 #pragma unroll
                     for (int j = 0; j < 16; j += 8) {
                         bf16* p = feat0 + row * C + c0 + j;
                         float x8[8];
                         unpack8(*reinterpret_cast<const uint4*>(p), x8);
+                        const float4 ba = *reinterpret_cast<const float4*>(w.pw2_b + c0 + j), bb = *reinterpret_cast<const float4*>(w.pw2_b + c0 + j + 4);
                         uint4 u;
-                        u.x = umma::pack_bf16(x8[0] + t[j + 0] + w.pw2_b[c0 + j + 0], x8[1] + t[j + 1] + w.pw2_b[c0 + j + 1]);
-                        u.y = umma::pack_bf16(x8[2] + t[j + 2] + w.pw2_b[c0 + j + 2], x8[3] + t[j + 3] + w.pw2_b[c0 + j + 3]);
-                        u.z = umma::pack_bf16(x8[4] + t[j + 4] + w.pw2_b[c0 + j + 4], x8[5] + t[j + 5] + w.pw2_b[c0 + j + 5]);
-                        u.w = umma::pack_bf16(x8[6] + t[j + 6] + w.pw2_b[c0 + j + 6], x8[7] + t[j + 7] + w.pw2_b[c0 + j + 7]);
+                        u.x = umma::pack_bf16(x8[0] + t[j + 0] + ba.x, x8[1] + t[j + 1] + ba.y);
+                        u.y = umma::pack_bf16(x8[2] + t[j + 2] + ba.z, x8[3] + t[j + 3] + ba.w);
+                        u.z = umma::pack_bf16(x8[4] + t[j + 4] + bb.x, x8[5] + t[j + 5] + bb.y);
+                        u.w = umma::pack_bf16(x8[6] + t[j + 6] + bb.z, x8[7] + t[j + 7] + bb.w);
                         *reinterpret_cast<uint4*>(p) = u;
                     }
                 }
@@ -567,70 +603,66 @@ __global__ void __launch_bounds__(192) lkpm_mlp_tc_kernel(bf16* __restrict__ fea
             rows_sync();
         }
     } else if (warp == 4) {
-        {
-            const bf16* wsrc = reinterpret_cast<const bf16*>(w.tc);
-            int cc = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
-                for (int c = 0; c < 8; ++c, ++cc) {
-                    const int slot = cc % P::NSLOT, round = cc / P::NSLOT;
-                    if (round > 0) umma::mbar_wait(&bars.empty[slot], (round - 1) & 1);
-                    umma::bulk_load(ring + (size_t)slot * P::SLOT, wsrc + (size_t)c * C * C, P::SLOT, &bars.full[slot]);
-                }
-        }
+        const bf16* wsrc = reinterpret_cast<const bf16*>(w.tc);
+        int cc = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+            for (int c = 0; c < M::NBLK; ++c, ++cc) {
+                const int slot = cc % M::NSLOT, round = cc / M::NSLOT;
+                if (round > 0) umma::mbar_wait(&bars.empty[slot], (round - 1) & 1);
+                umma::bulk_load(ring + (size_t)slot * M::BLK, wsrc + (size_t)c * (M::BLK / 2), M::BLK, &bars.full[slot]);
+            }
     } else {
-        {
-            const uint32_t idesc = umma::idesc_bf16(128, C);
-            const uint32_t a0s = umma::smem_u32(a0), a1s = umma::smem_u32(a1), rs = umma::smem_u32(ring);
-            constexpr uint32_t LBO_B = C * 16;
-            uint32_t ph = 0;
-            int cc = 0;
-            auto block = [&](uint32_t abase, int dcol, bool acc_first) {
-                const int slot = cc % P::NSLOT, round = cc / P::NSLOT;
-                umma::mbar_wait(&bars.full[slot], round & 1);
-                umma::fence_after_sync();
-                uint64_t ad = umma::smem_desc(abase, P::LBO);
-                uint64_t wd = umma::smem_desc(rs + slot * P::SLOT, LBO_B);
-#pragma unroll
-                for (int ks = 0; ks < C / 16; ++ks) {
-                    umma::mma_bf16(tmem + dcol, ad, wd, idesc, acc_first || ks > 0);
-                    ad = umma::desc_advance(ad, 2 * P::LBO);
-                    wd = umma::desc_advance(wd, 2 * LBO_B);
-                }
-                umma::commit(&bars.empty[slot]);
-                ++cc;
-            };
-            auto wait_a = [&]() { umma::mbar_wait(&bars.a_ready, ph); ph ^= 1; umma::fence_after_sync(); };
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                wait_a();
-                block(a0s, 0, false);                          // h_0
+        const uint32_t idesc1 = umma::idesc_bf16(128, M::NS), idesc2 = umma::idesc_bf16(128, C);
+        const uint32_t a0s = umma::smem_u32(a0), a1s = umma::smem_u32(a1), rs = umma::smem_u32(ring);
+        uint32_t ph = 0;
+        int cc = 0;
+        // h (+)= A0[128 x C] * W1_j^T (N = 128)   |   out (+)= A1[128 x 128] * W2_j^T (N = C)
+        auto block = [&](bool first_gemm, bool acc_first) {
+            const int slot = cc % M::NSLOT, round = cc / M::NSLOT;
+            umma::mbar_wait(&bars.full[slot], round & 1);
+            umma::fence_after_sync();
+            const uint32_t lbo_b = (first_gemm ? M::NS : C) * 16;
+            uint64_t ad = umma::smem_desc(first_gemm ? a0s : a1s, P::LBO);
+            uint64_t wd = umma::smem_desc(rs + slot * M::BLK, lbo_b);
+            const int nk = (first_gemm ? C : M::NS) / 16;
+            for (int ks = 0; ks < nk; ++ks) {
+                umma::mma_bf16(tmem + (first_gemm ? 0 : M::OUT_COL), ad, wd, first_gemm ? idesc1 : idesc2, acc_first || ks > 0);
+                ad = umma::desc_advance(ad, 2 * P::LBO);
+                wd = umma::desc_advance(wd, 2 * lbo_b);
+            }
+            umma::commit(&bars.empty[slot]);
+            ++cc;
+        };
+        auto wait_a = [&]() { umma::mbar_wait(&bars.a_ready, ph); ph ^= 1; umma::fence_after_sync(); };
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            wait_a();
+            block(true, false);                                // h_0
+            umma::commit(&bars.acc_ready);
+            for (int js = 0; js < M::NSL; ++js) {
+                wait_a();                                      // GELU(h_js) staged in a1, h columns free
+                block(false, js > 0);                          // out += GELU(h_js) W2_js^T
+                if (js + 1 < M::NSL) block(true, false);       // h_{js+1}
                 umma::commit(&bars.acc_ready);
-                for (int js = 0; js < 4; ++js) {
-                    wait_a();                                  // GELU(h_js) staged in a1, h columns free
-                    block(a1s, C, js > 0);                     // out += GELU(h_js) W2_js^T
-                    if (js < 3) block(a0s, 0, false);          // h_{js+1}
-                    umma::commit(&bars.acc_ready);
-                }
             }
         }
     }
     __syncthreads();
     if (warp == 4) {
         umma::fence_after_sync();
-        umma::tmem_dealloc(tmem, P::TMEM_COLS);
+        umma::tmem_dealloc(tmem, M::TMEM_COLS);
     }
 }
 
 template <int C>
 static int run_lkpm_mlp_tc(void* feat0, const void* y, int64_t rows, const cfp_lkpm_w& w, cudaStream_t st) {
-    using P = ChainTC<C>;
+    using M = MlpTC<C>;
     CFP_REQUIRE(w.tc != nullptr, "lkpm_mlp: bf16 path needs the packed tensor-core weights (cfp_lkpm_w.tc)");
-    constexpr size_t smem = 2 * (size_t)P::KG * P::LBO + (size_t)P::NSLOT * P::SLOT;
     auto k = lkpm_mlp_tc_kernel<C>;
-    if (int e = set_smem(k, smem)) return e;
+    if (int e = set_smem(k, M::SMEM)) return e;
     const int64_t ntiles = (rows + 127) / 128;
-    const int per_sm = C >= 128 ? 1 : (C == 64 ? 2 : 4);
+    const int per_sm = C >= 128 ? 1 : (C == 64 ? 2 : 3);
     const int grid = (int)(ntiles < 148 * per_sm ? ntiles : 148 * per_sm);
-    k<<<grid, 192, smem, st>>>((bf16*)feat0, (const bf16*)y, rows, w, (int)ntiles);
+    k<<<grid, 192, M::SMEM, st>>>((bf16*)feat0, (const bf16*)y, rows, w, (int)ntiles);
     return check_launch(C == 32 ? "lkpm_mlp_tc<32>" : C == 64 ? "lkpm_mlp_tc<64>" : "lkpm_mlp_tc<128>");
 }
 

@@ -76,6 +76,15 @@ struct WindowRows {            // LSA: ws x ws windows over the zero-padded map 
     __device__ void store4(const R& x, int c, float4 v) const {
         if (x.ok) IO<T>::st4(feat + x.off + c, v);
     }
+    // bf16 storage: one 16-byte access per 8 channels
+    __device__ uint4 raw8(const R& x, int c) const {
+        static_assert(sizeof(T) == 2, "raw8 is the bf16 fast path");
+        return x.ok ? *reinterpret_cast<const uint4*>(feat + x.off + c) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    __device__ void put8(const R& x, int c, uint4 v) const {
+        static_assert(sizeof(T) == 2, "put8 is the bf16 fast path");
+        if (x.ok) *reinterpret_cast<uint4*>(feat + x.off + c) = v;
+    }
 };
 
 template <typename T>
@@ -87,6 +96,14 @@ struct FrameRows {             // GSA queries: every token of a frame, group = f
     __device__ int group(const R& x) const { return x.g; }
     __device__ float4 load4(const R& x, int c) const { return IO<T>::ld4(feat + x.off + c); }
     __device__ void store4(const R& x, int c, float4 v) const { IO<T>::st4(feat + x.off + c, v); }
+    __device__ uint4 raw8(const R& x, int c) const {
+        static_assert(sizeof(T) == 2, "raw8 is the bf16 fast path");
+        return *reinterpret_cast<const uint4*>(feat + x.off + c);
+    }
+    __device__ void put8(const R& x, int c, uint4 v) const {
+        static_assert(sizeof(T) == 2, "put8 is the bf16 fast path");
+        *reinterpret_cast<uint4*>(feat + x.off + c) = v;
+    }
 };
 
 struct SrTokSrc {              // GSA keys/values: fp32 sub-sampled tokens [B][Ns][C]
@@ -112,6 +129,10 @@ struct InsideSrc {             // DAPM keys/values: tokens inside the zone recta
     }
     __device__ int group(const R& x) const { return x.g; }
     __device__ float4 load4(const R& x, int c) const { return IO<T>::ld4(feat + x.off + c); }
+    __device__ uint4 raw8(const R& x, int c) const {
+        static_assert(sizeof(T) == 2, "raw8 is the bf16 fast path");
+        return *reinterpret_cast<const uint4*>(feat + x.off + c);
+    }
 };
 
 template <typename T>
@@ -137,6 +158,14 @@ struct OutsideRows {           // DAPM queries: tokens outside the rectangle; me
     __device__ int group(const R& x) const { return x.g; }
     __device__ float4 load4(const R& x, int c) const { return IO<T>::ld4(feat + x.off + c); }
     __device__ void store4(const R& x, int c, float4 v) const { IO<T>::st4(msg + x.off + c, v); }
+    __device__ uint4 raw8(const R& x, int c) const {
+        static_assert(sizeof(T) == 2, "raw8 is the bf16 fast path");
+        return *reinterpret_cast<const uint4*>(feat + x.off + c);
+    }
+    __device__ void put8(const R& x, int c, uint4 v) const {
+        static_assert(sizeof(T) == 2, "put8 is the bf16 fast path");
+        *reinterpret_cast<uint4*>(msg + x.off + c) = v;
+    }
 };
 
 template <typename T>
@@ -197,12 +226,30 @@ struct ZonePatchRows {         // hist2image queries: cells of the zone canvas, 
     }
 };
 
-// 8 consecutive channels of a located row as packed bf16 (tensor-core path staging)
+// 8 consecutive channels of a located row as packed bf16 (tensor-core path staging).  Providers whose
+// storage already is bf16 expose raw8()/put8() (one 16-byte access, no conversion round trip).
+template <class P, class = void> struct HasRaw8 { static constexpr bool value = false; };
+template <class P> struct HasRaw8<P, decltype((void)&P::raw8)> { static constexpr bool value = true; };
+template <class P, class = void> struct HasPut8 { static constexpr bool value = false; };
+template <class P> struct HasPut8<P, decltype((void)&P::put8)> { static constexpr bool value = true; };
+
 template <class P>
 __device__ __forceinline__ uint4 load8_bf16(const P& p, const typename P::R& ref, int c) {
-    float4 a = p.load4(ref, c), b = p.load4(ref, c + 4);
-    __nv_bfloat162 t0 = __floats2bfloat162_rn(a.x, a.y), t1 = __floats2bfloat162_rn(a.z, a.w);
-    __nv_bfloat162 t2 = __floats2bfloat162_rn(b.x, b.y), t3 = __floats2bfloat162_rn(b.z, b.w);
+    if constexpr (HasRaw8<P>::value) {
+        return p.raw8(ref, c);
+    } else {
+        float4 a = p.load4(ref, c), b = p.load4(ref, c + 4);
+        __nv_bfloat162 t0 = __floats2bfloat162_rn(a.x, a.y), t1 = __floats2bfloat162_rn(a.z, a.w);
+        __nv_bfloat162 t2 = __floats2bfloat162_rn(b.x, b.y), t3 = __floats2bfloat162_rn(b.z, b.w);
+        uint4 u;
+        u.x = *reinterpret_cast<uint32_t*>(&t0); u.y = *reinterpret_cast<uint32_t*>(&t1);
+        u.z = *reinterpret_cast<uint32_t*>(&t2); u.w = *reinterpret_cast<uint32_t*>(&t3);
+        return u;
+    }
+}
+__device__ __forceinline__ uint4 pack8_bf16(const float (&v)[8]) {
+    __nv_bfloat162 t0 = __floats2bfloat162_rn(v[0], v[1]), t1 = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 t2 = __floats2bfloat162_rn(v[4], v[5]), t3 = __floats2bfloat162_rn(v[6], v[7]);
     uint4 u;
     u.x = *reinterpret_cast<uint32_t*>(&t0); u.y = *reinterpret_cast<uint32_t*>(&t1);
     u.z = *reinterpret_cast<uint32_t*>(&t2); u.w = *reinterpret_cast<uint32_t*>(&t3);
@@ -210,8 +257,12 @@ __device__ __forceinline__ uint4 load8_bf16(const P& p, const typename P::R& ref
 }
 template <class P>
 __device__ __forceinline__ void store8(const P& p, const typename P::R& ref, int c, const float (&v)[8]) {
-    p.store4(ref, c, make_float4(v[0], v[1], v[2], v[3]));
-    p.store4(ref, c + 4, make_float4(v[4], v[5], v[6], v[7]));
+    if constexpr (HasPut8<P>::value) {
+        p.put8(ref, c, pack8_bf16(v));
+    } else {
+        p.store4(ref, c, make_float4(v[0], v[1], v[2], v[3]));
+        p.store4(ref, c + 4, make_float4(v[4], v[5], v[6], v[7]));
+    }
 }
 
 // k_chain_tc.cu: the query chain on tcgen05 (bf16 activations only)

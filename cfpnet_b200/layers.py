@@ -226,9 +226,9 @@ class Block14(nn.Module):
         )
         w1, w2 = self.pwconv1.weight, self.pwconv2.weight
         blocks = []
-        for j in range(4):
-            blocks += [umma_block(w1[j * C:(j + 1) * C, :]), umma_block(w2[:, j * C:(j + 1) * C])]
-        t["tc"] = torch.stack(blocks).contiguous()
+        for j in range(4 * C // 128):                      # 128-wide hidden slices (csrc/k_chain_tc.cu: MlpTC)
+            blocks += [umma_block(w1[j * 128:(j + 1) * 128, :]).reshape(-1), umma_block(w2[:, j * 128:(j + 1) * 128]).reshape(-1)]
+        t["tc"] = torch.cat(blocks).contiguous()
         # banded-Toeplitz blocks of the depthwise taps for the tensor-core path (csrc/k_dwconv_tc.cu)
         ks = (32 + k - 1 + 15) // 16
         n = torch.arange(32, device=taps.device)[:, None]
