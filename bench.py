@@ -270,12 +270,13 @@ def run_cfp(a):
         # ---- per-kernel breakdown with CUDA events on the launch stream (roofline)
         prof = None
         if rank == 0:
-            barrier_local = torch.cuda.synchronize
-            barrier_local()
+            torch.cuda.synchronize()
+            path.concurrent_levels = False      # one stream: the gap between events is one kernel's time
             _lib.profile_start()
             for i in range(a.steps):
                 step(i)
             prof = _lib.profile_stop()
+            path.concurrent_levels = True
     if world > 1:
         dist.barrier()
 

@@ -36,12 +36,43 @@ class FusionPath(nn.Module):
         self.hist_encoder.out_dtype = dtype
         return self
 
+    concurrent_levels = True     # run the three (independent) fusion calls on three streams
+
     def forward(self, x3, x2, x1, hist_data, mask, patch_info, rect_data=None) -> List[torch.Tensor]:
         """x3/x2/x1: decoder features [B,128,h/16,w/16], [B,64,h/8,w/8], [B,32,h/4,w/4];
-        hist_data [B,Z,S]; mask [B,Z] bool.  Returns the fused maps in call order."""
+        hist_data [B,Z,S]; mask [B,Z] bool.  Returns the fused maps in call order.
+
+        The three TransformerFusion calls only share the histogram tokens, so after the encoder they
+        are enqueued on three streams: their (mostly latency-bound) kernels overlap on the GPU.  The
+        host-side order of the calls - and with it the order of the positional-encoding RNG draws -
+        stays L3, L2, L1 as in the reference decoder."""
         f32, f64, f128 = self.hist_encoder(hist_data.unsqueeze(-1))
         kw = dict(rect_data=rect_data, mask=mask, patch_info=patch_info, rgb=None)
-        return [self.cross_atten3(x3, f128, **kw), self.cross_atten2(x2, f64, **kw), self.cross_atten1(x1, f32, **kw)]
+        jobs = ((self.cross_atten3, x3, f128), (self.cross_atten2, x2, f64), (self.cross_atten1, x1, f32))
+        if not (self.concurrent_levels and x3.is_cuda):
+            return [m(x, f, **kw) for m, x, f in jobs]
+        dev = x3.device
+        cur = torch.cuda.current_stream(dev)
+        side = self.__dict__.setdefault("_level_streams", {}).setdefault(str(dev), [torch.cuda.Stream(dev) for _ in range(2)])
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        outs, joins = [], []
+        for i, (m, x, f) in enumerate(jobs):
+            if i == 2:                                   # the largest level stays on the caller's stream
+                outs.append(m(x, f, **kw))
+                continue
+            s = side[i]
+            s.wait_event(fork)
+            with torch.cuda.stream(s):
+                o = m(x, f, **kw)
+                e = torch.cuda.Event()
+                e.record(s)
+            o.record_stream(cur)
+            outs.append(o)
+            joins.append(e)
+        for e in joins:
+            cur.wait_event(e)
+        return outs
 
     # ------------------------------------------------------------------ host-buffer entry
     def forward_host(self, host: Dict[str, torch.Tensor], patch_info, device) -> List[torch.Tensor]:
