@@ -106,8 +106,17 @@ class TransformerFusion(nn.Module):
         with torch.cuda.device(dev):
             lib = _lib.load()
             ws_bytes = lib.cfp_workspace_bytes(B, H, W, D, self.ws, self.large_kernel or 0, code, C.byref(cg))
-            work = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
-            feat0 = torch.empty(B, H * W, D, device=dev, dtype=dt)
+            # scratch (workspace + token map) is owned by the module and reused across calls: stream order
+            # makes that safe for back-to-back forwards on one stream, and it keeps hundreds of MB of
+            # per-call allocations (cudaMalloc stalls once several streams are in play) off the hot path.
+            # One module instance must not run on two streams at once (replicas own their scratch).
+            key = (dev.index, dt, B, H, W)
+            scratch = self.__dict__.setdefault("_scratch", {})
+            if key not in scratch or scratch[key][0].numel() < ws_bytes:
+                scratch.clear()
+                scratch[key] = (torch.empty(ws_bytes, device=dev, dtype=torch.uint8),
+                                torch.empty(B, H * W, D, device=dev, dtype=dt))
+            work, feat0 = scratch[key]
             st = _lib.stream_ptr()
             _lib.call("cfp_posenc_tokens_fwd", x.data_ptr(), pos.data_ptr(), feat0.data_ptr(), B, D, H, W,
                       self.max_resolution[1], oy, ox, code, st)
@@ -128,6 +137,10 @@ class TransformerFusion(nn.Module):
                               work.data_ptr(), ws_bytes, code, st)
                     _lib.call("cfp_lkpm_fwd", feat0.data_ptr(), B, H, W, D, C.byref(lkpm_w), work.data_ptr(),
                               ws_bytes, code, st)
-            out = torch.empty(B, D, H, W, device=dev, dtype=dt)
+            out = kwargs.get("out")              # optional caller-provided result buffer (same shape/dtype)
+            if out is None:
+                out = torch.empty(B, D, H, W, device=dev, dtype=dt)
+            elif out.shape != x.shape or out.dtype != dt or out.device != dev or not out.is_contiguous():
+                raise ValueError("out= must be a contiguous tensor shaped and typed like x")
             _lib.call("cfp_tokens_to_nchw", feat0.data_ptr(), out.data_ptr(), B, D, H, W, code, st)
         return out

@@ -36,7 +36,8 @@ class FusionPath(nn.Module):
         self.hist_encoder.out_dtype = dtype
         return self
 
-    concurrent_levels = True     # run the three (independent) fusion calls on three streams
+    # run the three (independent) fusion calls on three streams (CFP_SEQUENTIAL_LEVELS=1 disables it)
+    concurrent_levels = not bool(__import__("os").environ.get("CFP_SEQUENTIAL_LEVELS"))
 
     def forward(self, x3, x2, x1, hist_data, mask, patch_info, rect_data=None) -> List[torch.Tensor]:
         """x3/x2/x1: decoder features [B,128,h/16,w/16], [B,64,h/8,w/8], [B,32,h/4,w/4];
@@ -54,21 +55,22 @@ class FusionPath(nn.Module):
         dev = x3.device
         cur = torch.cuda.current_stream(dev)
         side = self.__dict__.setdefault("_level_streams", {}).setdefault(str(dev), [torch.cuda.Stream(dev) for _ in range(2)])
+        # results are allocated on the caller's stream (no cross-stream allocator traffic: record_stream()
+        # on side-stream tensors turns into a cudaMalloc per step, and those occasionally stall for ~100 ms)
+        outs = [torch.empty_like(x) for _, x, _ in jobs]
         fork = torch.cuda.Event()
         fork.record(cur)
-        outs, joins = [], []
+        joins = []
         for i, (m, x, f) in enumerate(jobs):
             if i == 2:                                   # the largest level stays on the caller's stream
-                outs.append(m(x, f, **kw))
+                m(x, f, out=outs[i], **kw)
                 continue
             s = side[i]
             s.wait_event(fork)
             with torch.cuda.stream(s):
-                o = m(x, f, **kw)
+                m(x, f, out=outs[i], **kw)
                 e = torch.cuda.Event()
                 e.record(s)
-            o.record_stream(cur)
-            outs.append(o)
             joins.append(e)
         for e in joins:
             cur.wait_event(e)
@@ -146,8 +148,11 @@ class FusionPath(nn.Module):
                 d2h.wait_event(sl["comp_done"])
                 for p, o in zip(sl["out"], outs):
                     p.copy_(o, non_blocking=True)
-                    o.record_stream(d2h)
                 sl["out_ready"].record(d2h)
+            # keep the device results referenced until this slot is drained (host-synchronised on out_ready):
+            # record_stream() would instead park the blocks in the allocator until an event query succeeds,
+            # and the resulting occasional cudaMalloc stalls the device for ~100 ms
+            sl["dev_out"] = outs
             sl["busy"] = True
             pending.append((i, si))
         while pending:

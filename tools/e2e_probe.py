@@ -22,19 +22,14 @@ def batches(n):
 with torch.no_grad():
     for _ in path.stream_host(batches(4), pi, dev): pass
     torch.cuda.synchronize()
-    for depth in (2, 3, 4):
+    for trial in range(6):
+        ms0 = torch.cuda.memory_stats(dev)
         t0 = time.perf_counter(); stamps = []
-        for idx, outs in path.stream_host(batches(30), pi, dev, depth=depth):
+        for idx, outs in path.stream_host(batches(40), pi, dev):
             stamps.append(time.perf_counter() - t0)
         torch.cuda.synchronize()
         tot = time.perf_counter() - t0
+        ms1 = torch.cuda.memory_stats(dev)
         d = [b - a for a, b in zip(stamps, stamps[1:])]
-        print(f"depth {depth}: total {tot*1e3/30:.2f} ms/step; yield intervals (ms): " + " ".join(f"{x*1e3:.1f}" for x in d[:12]))
-    # enqueue cost alone
-    t0 = time.perf_counter()
-    for i in range(10):
-        d_ = sets[0]
-        outs = path(*(d_[k].to(dev, non_blocking=True) for k in ("x3", "x2", "x1", "hist_data", "mask")), pi)
-    t1 = time.perf_counter() - t0
-    torch.cuda.synchronize()
-    print(f"plain enqueue incl H2D: {t1*100:.2f} ms/step host time")
+        big = [(i, round(x * 1e3, 1)) for i, x in enumerate(d) if x > 0.012]
+        print(f"trial {trial}: {tot*1e3/40:.2f} ms/step; first yield {stamps[0]*1e3:.1f} ms; gaps>12ms: {big}; dev allocs {ms1['num_device_alloc']-ms0['num_device_alloc']}")
