@@ -76,31 +76,28 @@ __global__ void __launch_bounds__(192) conv3x3_tc_kernel(const bf16* __restrict_
         for (int s = 0; s < nsrc; ++s) {
             if (s > 0) umma::mbar_wait(&bars.a_free, 0);    // all MMAs reading source 0 have completed
             const bf16* src = s == 0 ? in0 : in1;
-            // 4 independent 16-byte loads in flight per thread (the staging is latency-bound otherwise)
+            // cp.async (LDGSTS) with zero-fill: every 16-byte chunk of the raster is one fire-and-forget copy, so
+            // all of a thread's ~40 copies are in flight at once (register staging made this phase latency-bound)
             const int total = cells * P::KG;
-            for (int i0 = tid; i0 < total; i0 += 4 * 128) {
-                uint4 v[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int i = i0 + u * 128;
-                    v[u] = make_uint4(0u, 0u, 0u, 0u);
-                    const int ci = i / P::KG, kg = i % P::KG;
-                    const int idx = ci - 1;                 // one slack cell in front (tap dx=0 of cell 0)
-                    if (i < total && idx >= 0) {
-                        const int pr = (int)__umulhi((unsigned)idx, wp_magic), px = idx - pr * WP;
-                        const int y = y0 - 1 + pr, x = px - 1;
-                        if (pr < R + 2 && y >= 0 && y < H && x >= 0 && x < W &&
-                            !(s == 1 && y >= zy0 && y < zy1 && x >= zx0 && x < zx1))
-                            v[u] = *reinterpret_cast<const uint4*>(src + (frame + (size_t)y * W + x) * C + kg * 8);
+            for (int i = tid; i < total; i += 128) {
+                const int ci = i / P::KG, kg = i % P::KG;
+                const int idx = ci - 1;                     // one slack cell in front (tap dx=0 of cell 0)
+                const bf16* g = src;                        // any valid address when the chunk is zero-filled
+                uint32_t nbytes = 0;
+                if (idx >= 0) {
+                    const int pr = (int)__umulhi((unsigned)idx, wp_magic), px = idx - pr * WP;
+                    const int y = y0 - 1 + pr, x = px - 1;
+                    if (pr < R + 2 && y >= 0 && y < H && x >= 0 && x < W &&
+                        !(s == 1 && y >= zy0 && y < zy1 && x >= zx0 && x < zx1)) {
+                        g = src + (frame + (size_t)y * W + x) * C + kg * 8;
+                        nbytes = 16;
                     }
                 }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int i = i0 + u * 128;
-                    if (i < total)
-                        *reinterpret_cast<uint4*>(a_buf + (size_t)(i % P::KG) * lbo_a + (size_t)(i / P::KG) * 16) = v[u];
-                }
+                const uint32_t dst = umma::smem_u32(a_buf + (size_t)kg * lbo_a + (size_t)ci * 16);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(g), "r"(nbytes) : "memory");
             }
+            asm volatile("cp.async.commit_group;\n" ::: "memory");
+            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
             umma::fence_async_smem();
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(umma::smem_u32(&bars.a_ready)) : "memory");
         }

@@ -50,9 +50,67 @@ __global__ void __launch_bounds__(256) layout_kernel(const T* __restrict__ src, 
     }
 }
 
+// bf16 fast path: 64 tokens x 64 channels per CTA, 4-byte accesses on both sides (two tokens of one channel on
+// the NCHW side, two channels of one token on the token side).  Requires H*W and C even.
+template <bool kToTokens>
+__global__ void __launch_bounds__(256) layout_bf16_kernel(const bf16* __restrict__ src_, const float* __restrict__ pos,
+                                                          bf16* __restrict__ dst_, int C, int H, int W, int pos_w, int oy, int ox) {
+    __shared__ uint16_t tile[64][66];                        // [channel][token]
+    const int b = blockIdx.z, n0 = blockIdx.x * 64, c0 = blockIdx.y * 64, N = H * W;
+    const uint16_t* src = reinterpret_cast<const uint16_t*>(src_);
+    uint16_t* dst = reinterpret_cast<uint16_t*>(dst_);
+    if (kToTokens) {
+        for (int i = threadIdx.x; i < 64 * 32; i += 256) {   // read (channel, token pair) from NCHW
+            const int cl = i / 32, nl = (i % 32) * 2, c = c0 + cl, n = n0 + nl;
+            if (c < C && n < N) {
+                const uint32_t v = *reinterpret_cast<const uint32_t*>(src + ((size_t)b * C + c) * N + n);
+                tile[cl][nl] = (uint16_t)(v & 0xffffu);
+                tile[cl][nl + 1] = (uint16_t)(v >> 16);
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < 64 * 32; i += 256) {   // write (token, channel pair) + positional encoding
+            const int nl = i / 32, cl = (i % 32) * 2, n = n0 + nl, c = c0 + cl;
+            if (n < N && c < C) {
+                const int y = n / W, x = n - y * W;
+                const float2 p = *reinterpret_cast<const float2*>(pos + ((size_t)(oy + y) * pos_w + (ox + x)) * C + c);
+                const float a = __uint_as_float((uint32_t)tile[cl][nl] << 16) + p.x;
+                const float d = __uint_as_float((uint32_t)tile[cl + 1][nl] << 16) + p.y;
+                __nv_bfloat162 o = __floats2bfloat162_rn(a, d);
+                *reinterpret_cast<uint32_t*>(dst + ((size_t)b * N + n) * C + c) = *reinterpret_cast<uint32_t*>(&o);
+            }
+        }
+    } else {
+        for (int i = threadIdx.x; i < 64 * 32; i += 256) {   // read (token, channel pair) from tokens
+            const int nl = i / 32, cl = (i % 32) * 2, n = n0 + nl, c = c0 + cl;
+            if (n < N && c < C) {
+                const uint32_t v = *reinterpret_cast<const uint32_t*>(src + ((size_t)b * N + n) * C + c);
+                tile[cl][nl] = (uint16_t)(v & 0xffffu);
+                tile[cl + 1][nl] = (uint16_t)(v >> 16);
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < 64 * 32; i += 256) {   // write (channel, token pair) to NCHW
+            const int cl = i / 32, nl = (i % 32) * 2, c = c0 + cl, n = n0 + nl;
+            if (c < C && n < N) {
+                const uint32_t v = (uint32_t)tile[cl][nl] | ((uint32_t)tile[cl][nl + 1] << 16);
+                *reinterpret_cast<uint32_t*>(dst + ((size_t)b * C + c) * N + n) = v;
+            }
+        }
+    }
+}
+
 template <typename T>
 static int launch_layout(bool to_tokens, const void* src, const float* pos, void* dst, int B, int C, int H,
                          int W, int pos_w, int oy, int ox, cudaStream_t st) {
+    if (sizeof(T) == 2 && (H * W) % 2 == 0 && C % 2 == 0) {
+        dim3 grid64((H * W + 63) / 64, (C + 63) / 64, B);
+        if (to_tokens)
+            layout_bf16_kernel<true><<<grid64, 256, 0, st>>>((const bf16*)src, pos, (bf16*)dst, C, H, W, pos_w, oy, ox);
+        else
+            layout_bf16_kernel<false><<<grid64, 256, 0, st>>>((const bf16*)src, pos, (bf16*)dst, C, H, W, pos_w, oy, ox);
+        return check_launch("layout_kernel");
+    }
     dim3 grid((H * W + 31) / 32, (C + 31) / 32, B);
     if (to_tokens)
         layout_kernel<T, true><<<grid, 256, 0, st>>>((const T*)src, pos, (T*)dst, C, H, W, pos_w, oy, ox);
