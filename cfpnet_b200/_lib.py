@@ -18,7 +18,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcfp.so")
 
 CFP_F32, CFP_BF16 = 0, 1
-ABI_VERSION = 7
+ABI_VERSION = 8
 _fp = C.POINTER(C.c_float)
 
 
@@ -53,7 +53,7 @@ class CfpTwinsW(C.Structure):
 
 
 class CfpHistW(C.Structure):
-    _fields_ = [("w_t", C.c_void_p * 9), ("b", C.c_void_p * 9)]
+    _fields_ = [("w_t", C.c_void_p * 9), ("b", C.c_void_p * 9), ("tc", C.c_void_p)]
 
 
 # name -> (restype, argtypes); must list every symbol include/cfp.h declares.

@@ -494,7 +494,7 @@ template <int C> struct MlpTC {
 
 template <int C>
 __global__ void __launch_bounds__(192) lkpm_mlp_tc_kernel(bf16* __restrict__ feat0, const bf16* __restrict__ y,
-                                                          int64_t rows, cfp_lkpm_w w, int ntiles) {
+                                                          int64_t rows, int planar_n, cfp_lkpm_w w, int ntiles) {
     using P = ChainTC<C>;
     using M = MlpTC<C>;
     constexpr int KG = P::KG;
@@ -523,14 +523,24 @@ __global__ void __launch_bounds__(192) lkpm_mlp_tc_kernel(bf16* __restrict__ fea
             const int64_t row = (int64_t)tile * 128 + tid;
             {   // channels-last LayerNorm (eps 1e-6) of row `tid` -> a0
                 float v[C];
+                if (planar_n > 0) {
+                    // planar dwconv output [frame][C][planar_n]: lanes are consecutive tokens, so each of the C
+                    // two-byte loads of a warp is one contiguous 64-byte segment
+                    const int64_t fr = row / planar_n;
+                    const uint16_t* p = reinterpret_cast<const uint16_t*>(y) + fr * C * planar_n + (row - fr * planar_n);
 #pragma unroll
-                for (int j = 0; j < C; j += 8) {
-                    float t[8];
-                    uint4 u = make_uint4(0u, 0u, 0u, 0u);
-                    if (row < rows) u = *reinterpret_cast<const uint4*>(y + row * C + j);
-                    unpack8(u, t);
+                    for (int c = 0; c < C; ++c)
+                        v[c] = row < rows ? __uint_as_float((uint32_t)__ldg(p + (size_t)c * planar_n) << 16) : 0.f;
+                } else {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) v[j + i] = t[i];
+                    for (int j = 0; j < C; j += 8) {
+                        float t[8];
+                        uint4 u = make_uint4(0u, 0u, 0u, 0u);
+                        if (row < rows) u = *reinterpret_cast<const uint4*>(y + row * C + j);
+                        unpack8(u, t);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[j + i] = t[i];
+                    }
                 }
                 float s = 0.f;
 #pragma unroll
@@ -654,7 +664,7 @@ __global__ void __launch_bounds__(192) lkpm_mlp_tc_kernel(bf16* __restrict__ fea
 }
 
 template <int C>
-static int run_lkpm_mlp_tc(void* feat0, const void* y, int64_t rows, const cfp_lkpm_w& w, cudaStream_t st) {
+static int run_lkpm_mlp_tc(void* feat0, const void* y, int64_t rows, int planar_n, const cfp_lkpm_w& w, cudaStream_t st) {
     using M = MlpTC<C>;
     CFP_REQUIRE(w.tc != nullptr, "lkpm_mlp: bf16 path needs the packed tensor-core weights (cfp_lkpm_w.tc)");
     auto k = lkpm_mlp_tc_kernel<C>;
@@ -662,14 +672,14 @@ static int run_lkpm_mlp_tc(void* feat0, const void* y, int64_t rows, const cfp_l
     const int64_t ntiles = (rows + 127) / 128;
     const int per_sm = C >= 128 ? 1 : (C == 64 ? 2 : 3);
     const int grid = (int)(ntiles < 148 * per_sm ? ntiles : 148 * per_sm);
-    k<<<grid, 192, M::SMEM, st>>>((bf16*)feat0, (const bf16*)y, rows, w, (int)ntiles);
+    k<<<grid, 192, M::SMEM, st>>>((bf16*)feat0, (const bf16*)y, rows, planar_n, w, (int)ntiles);
     return check_launch(C == 32 ? "lkpm_mlp_tc<32>" : C == 64 ? "lkpm_mlp_tc<64>" : "lkpm_mlp_tc<128>");
 }
 
-int lkpm_mlp_tc(void* feat0, const void* y, int64_t rows, int C, const cfp_lkpm_w& w, cudaStream_t st) {
-    if (C == 32) return run_lkpm_mlp_tc<32>(feat0, y, rows, w, st);
-    if (C == 64) return run_lkpm_mlp_tc<64>(feat0, y, rows, w, st);
-    if (C == 128) return run_lkpm_mlp_tc<128>(feat0, y, rows, w, st);
+int lkpm_mlp_tc(void* feat0, const void* y, int64_t rows, int planar_n, int C, const cfp_lkpm_w& w, cudaStream_t st) {
+    if (C == 32) return run_lkpm_mlp_tc<32>(feat0, y, rows, planar_n, w, st);
+    if (C == 64) return run_lkpm_mlp_tc<64>(feat0, y, rows, planar_n, w, st);
+    if (C == 128) return run_lkpm_mlp_tc<128>(feat0, y, rows, planar_n, w, st);
     return fail("unsupported C=%d", C);
 }
 

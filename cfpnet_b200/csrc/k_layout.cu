@@ -100,9 +100,95 @@ __global__ void __launch_bounds__(256) layout_bf16_kernel(const bf16* __restrict
     }
 }
 
+// bf16 main path: TC channels x TN tokens per CTA (TC * TN = 4096) with 16-byte global accesses on BOTH sides
+// (8 tokens of one channel on the NCHW side, 8 channels of one token on the token side); the transpose goes
+// through a [channel][token] shared tile of 65-word rows: the 2-byte column accesses are conflict-free, the
+// 4-byte row accesses 2-way.  Requires H*W % 8 == 0 (16-byte aligned channel rows) and C % TC == 0.
+template <bool kToTokens, int TC>
+__global__ void __launch_bounds__(256) layout_bf16_v8_kernel(const bf16* __restrict__ src_, const float* __restrict__ pos,
+                                                             bf16* __restrict__ dst_, int C, int H, int W, int pos_w, int oy, int ox) {
+    constexpr int TN = 4096 / TC, LD = TN + 2;               // halfwords per tile row (odd word count)
+    constexpr int NCH = TN / 8, CG = TC / 8;                 // 16-byte chunks per channel row / per token
+    __shared__ __align__(4) uint16_t tile[TC * LD];
+    const int b = blockIdx.z, n0 = blockIdx.x * TN, c0 = blockIdx.y * TC, N = H * W;
+    const uint16_t* src = reinterpret_cast<const uint16_t*>(src_);
+    uint16_t* dst = reinterpret_cast<uint16_t*>(dst_);
+    if (kToTokens) {
+#pragma unroll
+        for (int i = threadIdx.x; i < TC * NCH; i += 256) {  // NCHW side: (channel, 8 tokens)
+            const int cl = i / NCH, nl = (i % NCH) * 8, n = n0 + nl;
+            if (n < N) {
+                const uint4 v = *reinterpret_cast<const uint4*>(src + ((size_t)b * C + c0 + cl) * N + n);
+                uint32_t* t = reinterpret_cast<uint32_t*>(tile + cl * LD + nl);
+                t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = threadIdx.x; i < TN * CG; i += 256) {   // token side: (token, 8 channels) + positional encoding
+            const int nl = i / CG, cl = (i % CG) * 8, n = n0 + nl;
+            if (n < N) {
+                const int y = n / W, x = n - y * W;
+                const float* pp = pos + ((size_t)(oy + y) * pos_w + (ox + x)) * C + c0 + cl;
+                const float4 p0 = *reinterpret_cast<const float4*>(pp), p1 = *reinterpret_cast<const float4*>(pp + 4);
+                const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+                uint32_t o[4];
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) {
+                    const float a = __uint_as_float((uint32_t)tile[(cl + j) * LD + nl] << 16) + pv[j];
+                    const float d = __uint_as_float((uint32_t)tile[(cl + j + 1) * LD + nl] << 16) + pv[j + 1];
+                    __nv_bfloat162 t = __floats2bfloat162_rn(a, d);
+                    o[j / 2] = *reinterpret_cast<uint32_t*>(&t);
+                }
+                *reinterpret_cast<uint4*>(dst + ((size_t)b * N + n) * C + c0 + cl) = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = threadIdx.x; i < TN * CG; i += 256) {   // token side: (token, 8 channels)
+            const int nl = i / CG, cl = (i % CG) * 8, n = n0 + nl;
+            if (n < N) {
+                const uint4 v = *reinterpret_cast<const uint4*>(src + ((size_t)b * N + n) * C + c0 + cl);
+                const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) {
+                    tile[(cl + j) * LD + nl] = (uint16_t)(w4[j / 2] & 0xffffu);
+                    tile[(cl + j + 1) * LD + nl] = (uint16_t)(w4[j / 2] >> 16);
+                }
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = threadIdx.x; i < TC * NCH; i += 256) {  // NCHW side: (channel, 8 tokens)
+            const int cl = i / NCH, nl = (i % NCH) * 8, n = n0 + nl;
+            if (n < N) {
+                const uint32_t* t = reinterpret_cast<const uint32_t*>(tile + cl * LD + nl);
+                *reinterpret_cast<uint4*>(dst + ((size_t)b * C + c0 + cl) * N + n) = make_uint4(t[0], t[1], t[2], t[3]);
+            }
+        }
+    }
+}
+
+template <bool kToTokens, int TC>
+static void launch_v8(const void* src, const float* pos, void* dst, int B, int C, int H, int W, int pos_w, int oy, int ox,
+                      cudaStream_t st) {
+    dim3 grid((H * W + 4096 / TC - 1) / (4096 / TC), C / TC, B);
+    layout_bf16_v8_kernel<kToTokens, TC><<<grid, 256, 0, st>>>((const bf16*)src, pos, (bf16*)dst, C, H, W, pos_w, oy, ox);
+}
+
 template <typename T>
 static int launch_layout(bool to_tokens, const void* src, const float* pos, void* dst, int B, int C, int H,
                          int W, int pos_w, int oy, int ox, cudaStream_t st) {
+    if (sizeof(T) == 2 && (H * W) % 8 == 0 && C % 32 == 0 && (((uintptr_t)src | (uintptr_t)dst | (uintptr_t)pos) & 15) == 0) {
+        if (C % 64 == 0) {
+            if (to_tokens) launch_v8<true, 64>(src, pos, dst, B, C, H, W, pos_w, oy, ox, st);
+            else launch_v8<false, 64>(src, pos, dst, B, C, H, W, pos_w, oy, ox, st);
+        } else {
+            if (to_tokens) launch_v8<true, 32>(src, pos, dst, B, C, H, W, pos_w, oy, ox, st);
+            else launch_v8<false, 32>(src, pos, dst, B, C, H, W, pos_w, oy, ox, st);
+        }
+        return check_launch("layout_kernel");
+    }
     if (sizeof(T) == 2 && (H * W) % 2 == 0 && C % 2 == 0) {
         dim3 grid64((H * W + 63) / 64, (C + 63) / 64, B);
         if (to_tokens)

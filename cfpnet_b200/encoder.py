@@ -13,7 +13,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .packing import PackCache, fold_bn
+from .packing import PackCache, fold_bn, umma_block
 
 
 class PointNetEncoder(nn.Module):
@@ -61,7 +61,10 @@ class HistogramEncoder(nn.Module):
         w = _lib.CfpHistW()
         for i, (wt, b) in enumerate(stages):
             w.w_t[i], w.b[i] = wt.data_ptr(), b.data_ptr()
-        return w, stages
+        # tensor-core path: stages 1..8 as bf16 UMMA blocks ([Cout,Cin] weight -> [Cin/8][Cout][8]), concatenated
+        tc = torch.cat([umma_block(wt.t()).reshape(-1) for wt, _ in stages[1:]]).contiguous()
+        w.tc = tc.data_ptr()
+        return w, (stages, tc)
 
     def forward(self, hist_data):
         if self.training:

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define CFP_ABI_VERSION 7
+#define CFP_ABI_VERSION 8
 
 #if defined(__GNUC__)
 #define CFP_API __attribute__((visibility("default")))
@@ -88,9 +88,10 @@ typedef struct cfp_lkpm_w {
      * W1_j = pwconv1.weight[128j:128(j+1), :] as [C/8][128][8], W2_j = pwconv2.weight[:, 128j:128(j+1)]
      * as [16][C][8].  Required for CFP_BF16. */
     const void *tc;
-    /* bf16 tensor-core depthwise conv: per (channel, dy) one banded-Toeplitz block
-     * T[n][kk] = dw_t-tap(dy, kk-n) (0 outside 0 <= kk-n < k), n < 32, kk < 16*KS,
-     * KS = ceil((31+k)/16), stored as a bf16 UMMA block [2*KS][32][8]; order [C][k].
+    /* bf16 tensor-core depthwise conv: banded-Toeplitz blocks T_dy[n][kk] = dw_t-tap(dy, kk-n) (0 outside
+     * 0 <= kk-n < k), n < 32, kk < 16*KS, KS = ceil((31+k)/16).  Vertical taps are grouped dy = 8a + b
+     * (a < NA = ceil(k/8); zero blocks for dy >= k) with the eight b's side by side along N:
+     * bf16 [C][NA][KS][2][256 = b*32+n][8]  (per (a, k-step) one UMMA B block [2][256][8]).
      * Required for CFP_BF16 when k >= 15. */
     const void *dw_toep;
     int32_t ksize;
@@ -111,6 +112,9 @@ typedef struct cfp_twins_w {
 typedef struct cfp_hist_w {
     const float *w_t[9];
     const float *b[9];
+    /* bf16 tensor-core path: stages 1..8 as bf16 UMMA blocks [Cin/8][Cout][8], concatenated in stage order
+     * (106496 bytes); stage 0 (Cin = 1) uses w_t[0] / b[0]. */
+    const void *tc;
 } cfp_hist_w;
 
 CFP_API int cfp_version(void);

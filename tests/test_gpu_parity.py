@@ -53,7 +53,9 @@ def _restore_flags():
 
 
 # ------------------------------------------------------------------ a1
-@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 4e-3)])
+# bf16: the tensor-core kernel keeps bf16 activations between the nine stages (as the reference cast to bf16
+# does); measured 3e-3..6e-3, stated tolerance 1e-2 (the fused features downstream are held to 2e-2)
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 1e-2)])
 def test_hist_encoder(dtype, tol):
     enc, sd = build_hist(dtype)
     inp = synth.make_inputs("G416", 2, seed=1, levels=())
@@ -66,14 +68,15 @@ def test_hist_encoder(dtype, tol):
         assert rel_l2(o, t) <= tol                                     # fp64 oracle
 
 
-def test_hist_encoder_ragged_rows():
-    """Row counts that are not a multiple of the 64-row tile, and a single zone."""
-    enc, sd = build_hist()
-    for B, Z in ((1, 1), (3, 5), (1, 64)):
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 1e-2)])
+def test_hist_encoder_ragged_rows(dtype, tol):
+    """Row counts that are not a multiple of the 64 / 128-row tiles, a single zone, and more tiles than CTAs."""
+    enc, sd = build_hist(dtype)
+    for B, Z in ((1, 1), (3, 5), (1, 64), (41, 64)):
         h = torch.rand(B, Z, 16, generator=torch.Generator().manual_seed(B * 7 + Z)) * 4
         outs = enc(h.to(DEV).unsqueeze(-1))
         for o, t in zip(outs, O.hist_encoder(sd, h.double())):
-            assert rel_l2(o, t) <= 1e-5
+            assert rel_l2(o, t) <= tol
 
 
 # ------------------------------------------------------------------ a2/a3

@@ -41,7 +41,7 @@ def test_ctypes_structs_match_header_layout():
     assert ctypes.sizeof(_lib.CfpDapmW) == 17 * 8
     assert ctypes.sizeof(_lib.CfpLkpmW) == 11 * 8         # 10 pointers + int32 (+pad)
     assert ctypes.sizeof(_lib.CfpTwinsW) == 22 * 8 + 5 * 8 + 8
-    assert ctypes.sizeof(_lib.CfpHistW) == 18 * 8
+    assert ctypes.sizeof(_lib.CfpHistW) == 19 * 8
 
 
 def test_workspace_bytes_is_pure_host_arithmetic(lib):
