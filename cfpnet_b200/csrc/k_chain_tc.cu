@@ -23,6 +23,7 @@
 #include "providers.cuh"
 #include "umma.cuh"
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 namespace cfp {
 
@@ -108,8 +109,10 @@ struct ChainStages {
         return r;
     }
     // epilogue 1: Q = elu(q)+1, msg = (Q KV) / (Q.Ksum + eps) -> a0[:, C:2C)  (or the message map)
+    // kv / ksum hold the state of groups g_base, g_base + 1, ... (global arrays: g_base = 0; the shared-memory copy of the
+    // tile's groups: g_base = first group of the tile)
     static __device__ __forceinline__ void epi_attention(const Q& q, const Row& r, uint32_t tmem, int warp, int tid, uint8_t* a0,
-                                                         const float* __restrict__ kv, const float* __restrict__ ksum) {
+                                                         const float* __restrict__ kv, const float* __restrict__ ksum, int g_base = 0) {
         const int g = r.g;
 #pragma unroll 1
         for (int c0 = 0; c0 < C; c0 += G) {
@@ -128,8 +131,8 @@ struct ChainStages {
 #pragma unroll
                 for (int v = 0; v < DH; ++v) num[v] = 0.f;
                 if (g >= 0) {
-                    const float* kvh = kv + (size_t)g * (C * DH) + (size_t)h0 * DH;
-                    const float* ksh = ksum + (size_t)g * C + h0;
+                    const float* kvh = kv + (size_t)(g - g_base) * (C * DH) + (size_t)h0 * DH;
+                    const float* ksh = ksum + (size_t)(g - g_base) * C + h0;
 #pragma unroll
                     for (int d = 0; d < DH; ++d) {
                         const float qd = qv[hh * DH + d];
@@ -333,13 +336,13 @@ __global__ void __launch_bounds__(192, ChainOcc<C>::CTAS) loftr_query_tc_kernel(
 // of two.  More CTAs fit per SM, which is what these latency-bound chains need.
 template <int C> struct MonoOcc { static constexpr int CTAS = C == 32 ? 5 : 2; };
 struct MonoBars {
-    uint64_t full[4], acc_ready;
+    uint64_t full[4], acc_ready, kv_full;
     uint32_t tmem_slot;
 };
 
 template <int C, int NH, bool kAttnOnly, class Q>
 __global__ void __launch_bounds__(128, MonoOcc<C>::CTAS) loftr_query_mono_kernel(Q q, cfp_loftr_w w, const float* __restrict__ kv,
-                                                                const float* __restrict__ ksum, int ntiles) {
+                                                                const float* __restrict__ ksum, int ntiles, int kv_slots) {
     using P = ChainTC<C>;
     using S = ChainStages<C, NH, kAttnOnly, Q>;
     constexpr int KG = P::KG, NB = kAttnOnly ? 1 : 8;      // weight blocks per tile
@@ -348,11 +351,17 @@ __global__ void __launch_bounds__(128, MonoOcc<C>::CTAS) loftr_query_mono_kernel
     uint8_t* a0 = smem;
     uint8_t* a1 = a0 + P::ABUF;
     uint8_t* ring = a1 + (kAttnOnly ? 0 : P::ABUF);        // 4 slots
+    // attention state of the groups a tile touches (kv_slots of them; 0 = read it from global memory): brought in by two
+    // bulk copies while the q projection runs - the per-row loads of the attention epilogue then hit shared memory
+    // instead of stalling every FMA chain on an L2 round trip
+    float* kvs = reinterpret_cast<float*>(ring + 4 * (size_t)P::SLOT);
+    float* kss = kvs + (size_t)kv_slots * (C * S::DH);
     const int tid = threadIdx.x, warp = umma::warp_idx_sync();
 
     if (tid == 0) {
         for (int i = 0; i < 4; ++i) umma::mbar_init(&bars.full[i], 1);
         umma::mbar_init(&bars.acc_ready, 1);
+        umma::mbar_init(&bars.kv_full, 1);
         umma::fence_mbar_init();
     }
     if (warp == 0) umma::tmem_alloc(&bars.tmem_slot, P::TMEM_COLS);
@@ -397,15 +406,35 @@ __global__ void __launch_bounds__(128, MonoOcc<C>::CTAS) loftr_query_mono_kernel
     if (warp == 0)
         for (long s0 = 0; s0 < 4; ++s0) prefetch(s0);
     long base = 0;                                          // sequence number of this tile's first block
+    uint32_t kvph = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, base += NB) {
-        const typename S::Row r = S::stage_x(q, (int64_t)tile * 128, tid, a0);
-        stage([&] { block(base + 0, a0s, 0, false); });                                   // q
+        const int64_t row0 = (int64_t)tile * 128;
+        const typename S::Row r = S::stage_x(q, row0, tid, a0);
+        const int g_first = kv_slots > 0 ? q.group_of_row(row0) : 0;
+        stage([&] {                                                                        // q
+            if (kv_slots > 0) {            // every row is past the previous tile's attention epilogue (stage barrier)
+                const int64_t last = row0 + 127 < q.rows ? row0 + 127 : q.rows - 1;
+                const uint32_t ng = (uint32_t)(q.group_of_row(last) - g_first + 1);
+                if (umma::elect_one()) {
+                    umma::mbar_expect_tx(&bars.kv_full, ng * (uint32_t)((C * S::DH + C) * sizeof(float)));
+                    umma::bulk_g2s(kvs, kv + (size_t)g_first * (C * S::DH), ng * (uint32_t)(C * S::DH * sizeof(float)), &bars.kv_full);
+                    umma::bulk_g2s(kss, ksum + (size_t)g_first * C, ng * (uint32_t)(C * sizeof(float)), &bars.kv_full);
+                }
+            }
+            block(base + 0, a0s, 0, false);
+        });
+        const float* kv_t = kv;
+        const float* ks_t = ksum;
+        if (kv_slots > 0) {
+            umma::mbar_wait(&bars.kv_full, kvph); kvph ^= 1;
+            kv_t = kvs; ks_t = kss;
+        }
         if (kAttnOnly) {
             if (warp == 0) prefetch(base + 4);               // slot of block `base` is free again
-            S::epi_attention(q, r, tmem, warp, tid, a0, kv, ksum);
+            S::epi_attention(q, r, tmem, warp, tid, a0, kv_t, ks_t, g_first);
             continue;                                        // next stage() barrier orders a0 / TMEM reuse
         }
-        S::epi_attention(q, r, tmem, warp, tid, a0, kv, ksum);
+        S::epi_attention(q, r, tmem, warp, tid, a0, kv_t, ks_t, g_first);
         stage([&] { block(base + 1, a0s + KG * P::LBO, 0, false); });                     // merge
         if (warp == 0) { prefetch(base + 4); prefetch(base + 5); }                        // blocks 0,1 consumed
         S::epi_ln1(w, tmem, warp, tid, a0);
@@ -442,12 +471,19 @@ static int run_query_tc(const char* name, const Q& q, const cfp_loftr_w& w, cons
     const int64_t ntiles = (q.rows + 127) / 128;
     CFP_REQUIRE(q.rows < ((int64_t)1 << 31), "%s: %lld rows exceed the 32-bit row index", name, (long long)q.rows);
     if constexpr (C <= 64) {
-        constexpr size_t smem = (kAttnOnly ? 1 : 2) * (size_t)P::ABUF + 4 * (size_t)P::SLOT;
+        constexpr size_t smem0 = (kAttnOnly ? 1 : 2) * (size_t)P::ABUF + 4 * (size_t)P::SLOT;
         const int per_sm = MonoOcc<C>::CTAS;
+        // shared-memory copy of the attention state of one tile's groups, if it fits beside the occupancy target
+        constexpr int DH = C / NH;
+        const uint32_t rpg = q.rows_per_group();
+        int kv_slots = (int)((128 + rpg - 2) / rpg + 1);
+        const size_t kv_bytes = (size_t)kv_slots * (C * DH + C) * sizeof(float);
+        if ((smem0 + kv_bytes + 1024) * per_sm > 227 * 1024 || getenv("CFP_NO_KV_SMEM")) kv_slots = 0;
+        const size_t smem = smem0 + (kv_slots > 0 ? kv_bytes : 0);
         const int grid = (int)(ntiles < 148 * per_sm ? ntiles : 148 * per_sm);
         auto k = loftr_query_mono_kernel<C, NH, kAttnOnly, Q>;
         if (int e = set_smem(k, smem)) return e;
-        k<<<grid, 128, smem, st>>>(q, w, kv, ksum, (int)ntiles);
+        k<<<grid, 128, smem, st>>>(q, w, kv, ksum, (int)ntiles, kv_slots);
     } else {
         const int per_sm = ChainOcc<C>::CTAS;
         const int grid = (int)(ntiles < 148 * per_sm ? ntiles : 148 * per_sm);

@@ -24,11 +24,12 @@
 #include "cfp_common.cuh"
 #include "cfp_internal.h"
 #include "umma.cuh"
+#include <stdlib.h>
 
 namespace cfp {
 
-template <int C> struct ConvTC {
-    static constexpr int T = 256 / C;                 // M-tiles per CTA: T*C = 256 TMEM columns
+template <int C, int TCOLS> struct ConvTC {
+    static constexpr int T = TCOLS / C;               // M-tiles per CTA: T*C = TCOLS TMEM columns (256 or 128)
     static constexpr int NSLOT = C >= 128 ? 2 : 3;    // weight ring depth
     static constexpr int SLOT_BYTES = C * C * 2;      // one [C x C] bf16 block
     static constexpr int KG = C / 8;                  // 16-byte channel groups per source
@@ -39,14 +40,14 @@ struct ConvTCBars {
     uint32_t tmem_slot;
 };
 
-template <int C>
+template <int C, int TCOLS>
 __global__ void __launch_bounds__(192) conv3x3_tc_kernel(const bf16* __restrict__ in0, const bf16* __restrict__ in1,
                                                          const bf16* __restrict__ wpk,
                                                          const float* __restrict__ shift,
                                                          const bf16* __restrict__ residual, bf16* __restrict__ out,
                                                          int H, int W, int R, int cells, unsigned wp_magic, int zy0,
                                                          int zy1, int zx0, int zx1) {
-    using P = ConvTC<C>;
+    using P = ConvTC<C, TCOLS>;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ ConvTCBars bars;
     const int WP = W + 2;
@@ -65,7 +66,7 @@ __global__ void __launch_bounds__(192) conv3x3_tc_kernel(const bf16* __restrict_
         umma::mbar_init(&bars.acc_ready, 1);
         umma::fence_mbar_init();
     }
-    if (warp == 4) umma::tmem_alloc(&bars.tmem_slot, 256);
+    if (warp == 4) umma::tmem_alloc(&bars.tmem_slot, TCOLS);
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
@@ -184,14 +185,14 @@ __global__ void __launch_bounds__(192) conv3x3_tc_kernel(const bf16* __restrict_
     __syncthreads();
     if (warp == 4) {
         umma::fence_after_sync();
-        umma::tmem_dealloc(tmem, 256);
+        umma::tmem_dealloc(tmem, TCOLS);
     }
 }
 
-template <int C>
+template <int C, int TCOLS>
 static int conv_tc_launch(const void* in0, const void* in1, const void* wpk, const float* shift, const void* residual,
                           void* out, int B, int H, int W, int zy0, int zy1, int zx0, int zx1, cudaStream_t st) {
-    using P = ConvTC<C>;
+    using P = ConvTC<C, TCOLS>;
     const int WP = W + 2;
     const int R = (P::T * 128) / WP;
     CFP_REQUIRE(R >= 1, "conv3x3 (tensor-core path): map width %d exceeds %d", W, P::T * 128 - 2);
@@ -199,7 +200,7 @@ static int conv_tc_launch(const void* in0, const void* in1, const void* wpk, con
     while (cells % 8 != 1) ++cells;              // LBO/16 = 1 (mod 8): conflict-free staging stores
     const size_t smem = (size_t)P::KG * cells * 16 + (size_t)P::NSLOT * P::SLOT_BYTES;
     CFP_REQUIRE(smem <= 220 * 1024, "conv3x3 (tensor-core path): %zu B shared memory", smem);
-    auto k = conv3x3_tc_kernel<C>;
+    auto k = conv3x3_tc_kernel<C, TCOLS>;
     if (int e = set_smem(k, smem)) return e;
     dim3 grid((H + R - 1) / R, B);
     const unsigned wp_magic = (unsigned)((((uint64_t)1 << 32) + WP - 1) / WP);   // umulhi(i, magic) == i / WP for i*WP < 2^32
@@ -212,9 +213,22 @@ static int conv_tc_launch(const void* in0, const void* in1, const void* wpk, con
 int conv3x3_tc(const void* in0, const void* in1, const void* wpk, const float* shift, const void* residual, void* out,
                int B, int H, int W, int C, int zy0, int zy1, int zx0, int zx1, cudaStream_t st) {
     CFP_REQUIRE(B <= 65535, "B too large for grid.y");
-    if (C == 32) return conv_tc_launch<32>(in0, in1, wpk, shift, residual, out, B, H, W, zy0, zy1, zx0, zx1, st);
-    if (C == 64) return conv_tc_launch<64>(in0, in1, wpk, shift, residual, out, B, H, W, zy0, zy1, zx0, zx1, st);
-    if (C == 128) return conv_tc_launch<128>(in0, in1, wpk, shift, residual, out, B, H, W, zy0, zy1, zx0, zx1, st);
+    // CTA size: 256 accumulator columns (T = 256/C M-tiles, one or two CTAs per SM) or 128 (half the raster, twice the
+    // CTAs per SM: the stage -> MMA -> epilogue phases of a CTA are serial, co-resident CTAs are what overlaps them)
+    // measured (B200, 64 frames): 128 columns win for C = 32 / 64 (0.84x / 0.93x the time), 256 for C = 128
+    static const int tcols_env = getenv("CFP_CONV_TCOLS") ? atoi(getenv("CFP_CONV_TCOLS")) : 0;
+    const int tcols = tcols_env ? tcols_env : (C <= 64 ? 128 : 256);
+#define CFP_CONV_ARGS in0, in1, wpk, shift, residual, out, B, H, W, zy0, zy1, zx0, zx1, st
+    if (tcols == 128) {
+        if (C == 32) return conv_tc_launch<32, 128>(CFP_CONV_ARGS);
+        if (C == 64) return conv_tc_launch<64, 128>(CFP_CONV_ARGS);
+        if (C == 128) return conv_tc_launch<128, 128>(CFP_CONV_ARGS);
+    } else {
+        if (C == 32) return conv_tc_launch<32, 256>(CFP_CONV_ARGS);
+        if (C == 64) return conv_tc_launch<64, 256>(CFP_CONV_ARGS);
+        if (C == 128) return conv_tc_launch<128, 256>(CFP_CONV_ARGS);
+    }
+#undef CFP_CONV_ARGS
     return fail("unsupported C=%d", C);
 }
 

@@ -20,7 +20,9 @@
 //
 // One A read now feeds 256 accumulator columns (the MMA runs at the tensor pipe's rate) and a 31 x 31 tile costs
 // 16 MMAs instead of 124.  The epilogue thread of accumulator row m gets E[m + b] from lane m + b with warp
-// shuffles; the rows that live in the next warp's TMEM quarter travel through a small shared-memory exchange.
+// shuffles; the rows that live in the next TMEM lane quarter travel through a small shared-memory exchange.
+// Sixteen epilogue warps (four per lane quarter, 8 output columns each) keep four warps on every scheduler: with one
+// warp per scheduler the (latency-bound) epilogue, not the tensor pipe, paced the kernel.
 // About half of every T_dy is structural zeros; the tensor pipe is still >10x faster than the FMA pipe on this op.
 //
 // Data flow: dw_plane_pack_kernel rewrites the token-major map into zero-padded channel planes stored
@@ -93,41 +95,54 @@ __global__ void __launch_bounds__(256) dw_plane_pack_kernel(const bf16* __restri
     // every plane row an A view can touch (HP >= PAD + F x (H + PAD)): the rows below the last frame's halo are only
     // multiplied by all-zero Toeplitz blocks (taps dy >= K of the last group of eight), but a stale NaN would survive that
     const int rows = min(8, g.HP - pr0);
-    // plane row pr -> (stacked frame f, image row y) or halo
-    int fy[8];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        const int q = pr0 + r - g.PAD;                         // row relative to the first frame's first row
-        const int f = q >= 0 ? q / g.RS : -1, y = q - f * g.RS;
+    // plane row pr -> (stacked frame f, image row y) -> source row index, or -1 for a zero row
+    auto src_row = [&](int r) {
+        const int qr = pr0 + r - g.PAD;                        // row relative to the first frame's first row
+        const int f = qr >= 0 ? qr / g.RS : -1, y = qr - f * g.RS;
         const int frame = stack * g.F + f;
-        fy[r] = (r < rows && q >= 0 && f < g.F && y < g.H && frame < B) ? frame * g.H + y : -1;
-    }
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(in);
-    for (int i = threadIdx.x; i < 8 * W * C2; i += 256) {
-        const int r = i / (W * C2), j = i - r * (W * C2);
-        if (fy[r] >= 0) slab[(r * W) * LD + (j / C2) * LD + (j % C2)] = src[(size_t)fy[r] * W * C2 + j];
+        return (r < rows && qr >= 0 && f < g.F && y < g.H && frame < B) ? frame * g.H + y : -1;
+    };
+    // phase 1: the image rows among the 8, 16-byte loads (8 channels), rows one after the other
+    {
+        const int V = C2 / 4, nvec = W * V;                   // uint4 per pixel (C % 8 == 0), per row
+        for (int r = 0; r < 8; ++r) {
+            const int sr = src_row(r);
+            if (sr < 0) continue;                             // block-uniform
+            const uint4* src = reinterpret_cast<const uint4*>(in) + (size_t)sr * nvec;
+            for (int i = threadIdx.x; i < nvec; i += 256) {
+                const uint4 v = src[i];
+                uint32_t* d = slab + (r * W + i / V) * LD + (i % V) * 4;
+                d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+            }
+        }
     }
     __syncthreads();
-    // one thread = (channel pair, x-group, row): 8 four-byte reads -> two 16-byte chunks (channels 2*c2, 2*c2+1);
-    // r fastest so that 8 consecutive threads write 128 contiguous bytes of a plane
-    const int nxg = g.WG;      // every x-group an A operand covers (a stale NaN times a structural zero of T would poison the row)
-    for (int i = threadIdx.x; i < C2 * nxg * 8; i += 256) {
-        const int r = i & 7, xg = (i >> 3) % nxg, c2 = (i >> 3) / nxg;
-        if (r >= rows) continue;
-        uint32_t v[8];
+    // phase 2: thread = (plane row r, slot); a slot walks over the (channel pair, x-group) chunks.  8 consecutive threads
+    // (r = 0..7) write 128 contiguous bytes of a plane.  Chunks without image cells are plain zero stores.
+    const int r = threadIdx.x & 7;
+    if (r >= rows) return;
+    const bool img_row = src_row(r) >= 0;
+    const int npair = C2 * g.WG;
+    int pair = threadIdx.x >> 3, c2 = pair / g.WG, xg = pair - c2 * g.WG;
+    const size_t plane_stride = (size_t)g.WG * g.HP * 8;       // elements per channel plane
+    for (; pair < npair; pair += 32) {
+        const int xb = xg * 8 - g.PAD;                         // image column of the chunk's first element
+        uint4 lo = make_uint4(0u, 0u, 0u, 0u), hi = lo;
+        if (img_row && xb + 7 >= 0 && xb < W) {
+            uint32_t v[8];
+            const uint32_t* sp = slab + (r * W + xb) * LD + c2;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int x = xg * 8 + j - g.PAD;
-            v[j] = (fy[r] >= 0 && x >= 0 && x < W) ? slab[(r * W + x) * LD + c2] : 0u;
+            for (int j = 0; j < 8; ++j) v[j] = (xb + j >= 0 && xb + j < W) ? sp[j * LD] : 0u;
+            lo.x = __byte_perm(v[0], v[1], 0x5410); hi.x = __byte_perm(v[0], v[1], 0x7632);
+            lo.y = __byte_perm(v[2], v[3], 0x5410); hi.y = __byte_perm(v[2], v[3], 0x7632);
+            lo.z = __byte_perm(v[4], v[5], 0x5410); hi.z = __byte_perm(v[4], v[5], 0x7632);
+            lo.w = __byte_perm(v[6], v[7], 0x5410); hi.w = __byte_perm(v[6], v[7], 0x7632);
         }
-        uint4 lo, hi;
-        lo.x = __byte_perm(v[0], v[1], 0x5410); hi.x = __byte_perm(v[0], v[1], 0x7632);
-        lo.y = __byte_perm(v[2], v[3], 0x5410); hi.y = __byte_perm(v[2], v[3], 0x7632);
-        lo.z = __byte_perm(v[4], v[5], 0x5410); hi.z = __byte_perm(v[4], v[5], 0x7632);
-        lo.w = __byte_perm(v[6], v[7], 0x5410); hi.w = __byte_perm(v[6], v[7], 0x7632);
         const size_t off = ((((size_t)stack * C + 2 * c2) * g.WG + xg) * g.HP + (pr0 + r)) * 8;
         *reinterpret_cast<uint4*>(planes + off) = lo;
-        *reinterpret_cast<uint4*>(planes + off + (size_t)g.WG * g.HP * 8) = hi;
+        *reinterpret_cast<uint4*>(planes + off + plane_stride) = hi;
+        xg += 32;
+        while (xg >= g.WG) { xg -= g.WG; ++c2; }
     }
 }
 
@@ -169,8 +184,26 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 constexpr int kXchLd = 36;                                 // floats per exchanged row (16-byte aligned, bank-staggered)
 constexpr int kXchRows = 28;                               // rows a warp publishes per item: sum_{b=1..7} b
 constexpr size_t kXchBytes = 2 * 3 * kXchRows * kXchLd * sizeof(float);
+constexpr int kDwParts = 4;                                // epilogue warps per TMEM lane quarter
+constexpr int kDwCols = 32 / kDwParts;                     // output columns per epilogue thread
+constexpr int kDwEpiWarps = 4 * kDwParts;
+constexpr int kDwThreads = (kDwEpiWarps + 2) * 32;         // + bulk-copy producer warp + MMA issuer warp
+constexpr size_t kBndBytes = 2 * kDwEpiWarps * 7 * kDwCols * sizeof(float);   // per (item parity, warp): 7 boundary rows
 
-__global__ void __launch_bounds__(192) dwconv_tc_kernel(const bf16* __restrict__ planes, const bf16* __restrict__ toep,
+template <int NC> __device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[NC]);
+template <> __device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, float (&v)[16]) { umma::tmem_ld16(taddr, v); }
+template <> __device__ __forceinline__ void tmem_ld<8>(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__global__ void __launch_bounds__(kDwThreads) dwconv_tc_kernel(const bf16* __restrict__ planes, const bf16* __restrict__ toep,
                                                         const float* __restrict__ shift, bf16* __restrict__ planar_out,
                                                         int B, DwGeom g, int items_per_cta, int total_items) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -183,73 +216,92 @@ __global__ void __launch_bounds__(192) dwconv_tc_kernel(const bf16* __restrict__
     uint8_t* t_sm = smem;
     uint8_t* a_sm = smem + t_bytes;                            // [3][a_stride]
     const uint32_t a_stride = (a_bytes + 127) & ~127u;
-    float* xch = reinterpret_cast<float*>(a_sm + 3 * (size_t)a_stride);   // [2][3 warps][28 rows][kXchLd]
+    float* xch = reinterpret_cast<float*>(a_sm + 3 * (size_t)a_stride);   // [2][3 quarters][28 rows][kXchLd]
+    float* bnd = xch + kXchBytes / sizeof(float);                         // [2][epilogue warps][7 rows][kDwCols]
     const int i0 = blockIdx.x * items_per_cta, i1 = min(i0 + items_per_cta, total_items);
 
     if (tid == 0) {
         umma::mbar_init(&bars.t_full, 1);
         umma::mbar_init(&bars.t_empty, 1);
         for (int i = 0; i < 3; ++i) { umma::mbar_init(&bars.a_full[i], 1); umma::mbar_init(&bars.a_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { umma::mbar_init(&bars.acc_full[i], 1); umma::mbar_init(&bars.acc_empty[i], 128); }
+        for (int i = 0; i < 2; ++i) { umma::mbar_init(&bars.acc_full[i], 1); umma::mbar_init(&bars.acc_empty[i], kDwEpiWarps * 32); }
         umma::fence_mbar_init();
     }
-    if (warp == 4) umma::tmem_alloc(&bars.tmem_slot, 512);
+    if (warp == kDwEpiWarps) umma::tmem_alloc(&bars.tmem_slot, 512);
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
     const uint32_t tmem = bars.tmem_slot;
 
-    if (warp < 4) {
-        // ---------------- epilogue: thread = accumulator row m; out[m][n] = sum_b E_b[m + b][n]
+    if (warp < kDwEpiWarps) {
+        // ---------------- epilogue: kDwParts warps per TMEM lane quarter.  Thread = (accumulator row m, kDwCols of the
+        // 32 output columns):  out[m][n] = sum_b E_b[m + b][n]
+        constexpr int NC = kDwCols;
+        const int q = warp & 3, part = warp >> 2, row = q * 32 + lane;
         for (int i = i0; i < i1; ++i) {
             const int n = i - i0, ab = n & 1;
             const DwItem it = dw_item(i, g);
             const float sh = shift[it.c];
-            float* xw = xch + (size_t)ab * (3 * kXchRows * kXchLd);
+            float* xw = xch + (size_t)ab * (3 * kXchRows * kXchLd) + part * NC;
+            float* bw = bnd + ((size_t)ab * kDwEpiWarps + warp) * (7 * NC);
             umma::mbar_wait(&bars.acc_full[ab], (n >> 1) & 1);
             umma::fence_after_sync();
-            float acc[32];
+            float acc[NC];
 #pragma unroll
             for (int b = 0; b < 8; ++b) {
-                float e[32];
-                tmem_ld32(umma::tmem_addr(tmem, warp * 32, ab * 256 + b * 32), e);
+                float e[NC];
+                tmem_ld<NC>(umma::tmem_addr(tmem, q * 32, ab * 256 + b * 32 + part * NC), e);
                 if (b == 0) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) acc[j] = e[j];
+                    for (int j = 0; j < NC; ++j) acc[j] = e[j];
                 } else {
-                    if (warp > 0 && lane < b) {                // rows the warp below needs: E_b[32 w + lane]
-                        float* dst = xw + ((size_t)(warp - 1) * kXchRows + b * (b - 1) / 2 + lane) * kXchLd;
+                    if (q > 0 && lane < b) {                   // rows the quarter below needs: E_b[32 q + lane]
+                        float* dst = xw + ((size_t)(q - 1) * kXchRows + b * (b - 1) / 2 + lane) * kXchLd;
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(e[j], e[j + 1], e[j + 2], e[j + 3]);
+                        for (int j = 0; j < NC; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(e[j], e[j + 1], e[j + 2], e[j + 3]);
                     }
-                    const bool in_warp = lane + b < 32;
+                    float sv[NC];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float sv = __shfl_down_sync(0xffffffffu, e[j], b);
-                        acc[j] += in_warp ? sv : 0.f;
+                    for (int j = 0; j < NC; ++j) sv[j] = __shfl_down_sync(0xffffffffu, e[j], b);
+                    if (lane + b < 32) {
+#pragma unroll
+                        for (int j = 0; j < NC; ++j) acc[j] += sv[j];
                     }
                 }
             }
             umma::fence_before_sync();
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(umma::smem_u32(&bars.acc_empty[ab])) : "memory");
-            asm volatile("bar.sync 1, 128;\n" ::: "memory");  // boundary rows of this item are published
-            if (warp < 3 && lane >= 25) {
-                for (int b = 32 - lane; b < 8; ++b) {
-                    const float* src = xw + ((size_t)warp * kXchRows + b * (b - 1) / 2 + (lane + b - 32)) * kXchLd;
+            asm volatile("bar.sync 1, %0;\n" ::"n"(kDwEpiWarps * 32) : "memory");   // boundary rows of this item are published
+            if (q < 3) {
+                // rows 25..31 of the quarter take E_b[m + b] for m + b >= 32 from the exchange: lane -> (target row 25 + t,
+                // four of the NC columns) sums its b's, then hands the partial row over through `bw`
+                constexpr int QPR = NC / 4;                    // float4 per row
+                const int t = lane / QPR, cq = (lane % QPR) * 4;
+                if (t < 7) {
+                    float4 sacc = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int b = 7 - t; b < 8; ++b) {
+                        const float4 v = *reinterpret_cast<const float4*>(xw + ((size_t)q * kXchRows + b * (b - 1) / 2 + (t + b - 7)) * kXchLd + cq);
+                        sacc.x += v.x; sacc.y += v.y; sacc.z += v.z; sacc.w += v.w;
+                    }
+                    *reinterpret_cast<float4*>(bw + t * NC + cq) = sacc;
+                }
+                __syncwarp();
+                if (lane >= 25) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 q = *reinterpret_cast<const float4*>(src + j);
-                        acc[j] += q.x; acc[j + 1] += q.y; acc[j + 2] += q.z; acc[j + 3] += q.w;
+                    for (int j = 0; j < NC; j += 4) {
+                        const float4 v = *reinterpret_cast<const float4*>(bw + (lane - 25) * NC + j);
+                        acc[j] += v.x; acc[j + 1] += v.y; acc[j + 2] += v.z; acc[j + 3] += v.w;
                     }
                 }
+                __syncwarp();                                  // `bw` is rewritten two items later (ab parity) - cheap insurance
             }
-            const int m = it.mt * kDwMS + tid, x0 = it.xt * 32;
+            const int m = it.mt * kDwMS + row, x0 = it.xt * 32 + part * NC;
             const int f = m / g.RS, y = m - f * g.RS, frame = it.b * g.F + f;      // stacked frame and its row
-            if (tid < kDwMS && f < g.F && y < g.H && frame < B) {
+            if (row < kDwMS && f < g.F && y < g.H && frame < B) {
                 bf16* dst = planar_out + (((size_t)frame * g.C + it.c) * g.H + y) * g.W + x0;
                 const bool aligned = (((size_t)(dst - planar_out)) & 7) == 0;
 #pragma unroll
-                for (int j = 0; j < 32; j += 8) {
+                for (int j = 0; j < NC; j += 8) {
                     if (x0 + j + 8 <= g.W && aligned) {
                         uint4 u;
                         u.x = umma::pack_bf16(fmaxf(acc[j + 0] + sh, 0.f), fmaxf(acc[j + 1] + sh, 0.f));
@@ -259,13 +311,13 @@ __global__ void __launch_bounds__(192) dwconv_tc_kernel(const bf16* __restrict__
                         *reinterpret_cast<uint4*>(dst + j) = u;
                     } else {
 #pragma unroll
-                        for (int q = 0; q < 8; ++q)
-                            if (x0 + j + q < g.W) dst[j + q] = __float2bfloat16_rn(fmaxf(acc[j + q] + sh, 0.f));
+                        for (int qq = 0; qq < 8; ++qq)
+                            if (x0 + j + qq < g.W) dst[j + qq] = __float2bfloat16_rn(fmaxf(acc[j + qq] + sh, 0.f));
                     }
                 }
             }
         }
-    } else if (warp == 4) {
+    } else if (warp == kDwEpiWarps) {
         // ---------------- producer: Toeplitz blocks per channel, one bulk copy per work item
         {
             int cur_c = -1, nt = 0;
@@ -328,7 +380,7 @@ __global__ void __launch_bounds__(192) dwconv_tc_kernel(const bf16* __restrict__
         }
     }
     __syncthreads();
-    if (warp == 4) {
+    if (warp == kDwEpiWarps) {
         umma::fence_after_sync();
         umma::tmem_dealloc(tmem, 512);
     }
@@ -352,13 +404,13 @@ int dwconv_tc(const void* in, const void** planar_out_p, int B, int H, int W, in
     }
     {
         const uint32_t t_bytes = g.NA * g.KS * 2 * 256 * 16, a_bytes = 2 * g.KS * g.HP * 16;
-        const size_t smem = t_bytes + 3 * (size_t)((a_bytes + 127) & ~127u) + kXchBytes;
+        const size_t smem = t_bytes + 3 * (size_t)((a_bytes + 127) & ~127u) + kXchBytes + kBndBytes;
         CFP_REQUIRE(smem <= 225 * 1024, "dwconv (tensor-core path): %zu B shared memory (H=%d too tall)", smem, H);
         if (int err = set_smem(dwconv_tc_kernel, smem)) return err;
         const int total = C * g.nX * g.NB * g.nM;
         const int grid = total < 148 ? total : 148;
         const int per = (total + grid - 1) / grid;
-        dwconv_tc_kernel<<<(total + per - 1) / per, 192, smem, st>>>(planes, (const bf16*)toep, shift, planar_out, B, g, per, total);
+        dwconv_tc_kernel<<<(total + per - 1) / per, kDwThreads, smem, st>>>(planes, (const bf16*)toep, shift, planar_out, B, g, per, total);
         if (int err = check_launch(K == 31 ? "dwconv_tc<31>" : K == 15 ? "dwconv_tc<15>" : "dwconv_tc<7>")) return err;
     }
     return 0;

@@ -60,6 +60,8 @@ struct WindowRows {            // LSA: ws x ws windows over the zero-padded map 
     WindowRows(T* f, int H_, int W_, int C_, int ws_, int nwx_, int nwin_, int64_t n)
         : feat(f), H(H_), W(W_), C(C_), ws(ws_), nwx(nwx_), nwin(nwin_), rows(n), dL(ws_ * ws_), dWin(nwin_), dNwx(nwx_), dWs(ws_) {}
     typedef RowRef R;
+    __host__ __device__ uint32_t rows_per_group() const { return dL.d; }
+    __device__ int group_of_row(int64_t r) const { return (int)dL.div((uint32_t)r); }
     __device__ R locate(int64_t r) const {
         uint32_t g, l, b, wi, wy, wx, iy, ix;
         dL.divmod((uint32_t)r, g, l);
@@ -92,6 +94,8 @@ struct FrameRows {             // GSA queries: every token of a frame, group = f
     T* feat; int N, C; int64_t rows; FastDiv dN;
     FrameRows(T* f, int N_, int C_, int64_t n) : feat(f), N(N_), C(C_), rows(n), dN(N_) {}
     typedef RowRef R;
+    __host__ __device__ uint32_t rows_per_group() const { return dN.d; }
+    __device__ int group_of_row(int64_t r) const { return (int)dN.div((uint32_t)r); }
     __device__ R locate(int64_t r) const { return R{r * C, (int)dN.div((uint32_t)r), true}; }
     __device__ int group(const R& x) const { return x.g; }
     __device__ float4 load4(const R& x, int c) const { return IO<T>::ld4(feat + x.off + c); }
@@ -142,6 +146,8 @@ struct OutsideRows {           // DAPM queries: tokens outside the rectangle; me
         : feat(f), msg(m), H(H_), W(W_), C(C_), ry0(ry0_), ry1(ry1_), rx0(rx0_), rx1(rx1_), No(No_), rows(n), dNo(No_),
           dOut(W_ - (rx1_ - rx0_) > 0 ? W_ - (rx1_ - rx0_) : 1) {}
     typedef RowRef R;
+    __host__ __device__ uint32_t rows_per_group() const { return dNo.d; }
+    __device__ int group_of_row(int64_t r) const { return (int)dNo.div((uint32_t)r); }
     __device__ R locate(int64_t r) const {
         uint32_t b, o;
         dNo.divmod((uint32_t)r, b, o);
@@ -178,6 +184,8 @@ struct ZonePatchRows {         // hist2image queries: cells of the zone canvas, 
         : feat0(f), emb(e), canvas(cv), mask(m), H(H_), W(W_), C(C_), zn(zn_), p1(p1_), p2(p2_), sy_wo(sy), sx_wo(sx),
           tzh(tzh_), tzw(tzw_), interpolate(interp), assign(assign_), rows(n), dP(p1_ * p2_), dZ(zn_ * zn_), dZn(zn_), dP2(p2_) {}
     struct R { int b, cy, cx, g; bool valid; };
+    __host__ __device__ uint32_t rows_per_group() const { return dP.d; }
+    __device__ int group_of_row(int64_t r) const { return (int)dP.div((uint32_t)r); }
     __device__ R locate(int64_t r) const {
         uint32_t g, l, b, z, zy, zx, py, px;
         dP.divmod((uint32_t)r, g, l);
