@@ -190,7 +190,9 @@ struct ChainStages {
             }
         }
     }
-    // epilogue 4: x + LN2(W2 hidden) -> scatter through the provider
+    // epilogue 4: x + LN2(W2 hidden) -> scatter through the provider.  x comes from a0[:, 0:C) (kReloadX = false) or is
+    // read again through the provider when the MLP hidden has overwritten a0 in place (two-group kernel).
+    template <bool kReloadX = false>
     static __device__ __forceinline__ void epi_out(const Q& q, const Row& r, const cfp_loftr_w& w, uint32_t tmem, int warp, int tid,
                                                    const uint8_t* a0) {
         float v[C];
@@ -200,7 +202,8 @@ struct ChainStages {
 #pragma unroll
             for (int j = 0; j < C; j += 8) {
                 float x8[8], o8[8];
-                unpack8(*reinterpret_cast<const uint4*>(a0 + (size_t)(j / 8) * P::LBO + tid * 16), x8);
+                if (kReloadX) unpack8(load8_bf16(q, r.ref, j), x8);
+                else unpack8(*reinterpret_cast<const uint4*>(a0 + (size_t)(j / 8) * P::LBO + tid * 16), x8);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) o8[i] = x8[i] + v[j + i];
                 store8(q, r.ref, j, o8);
@@ -226,10 +229,16 @@ __device__ __forceinline__ void issue_block(uint32_t tmem_d, uint32_t a_addr, ui
 template <int C> struct ChainOcc { static constexpr int CTAS = C >= 128 ? 1 : (C == 64 ? 2 : 4); };
 
 // ---------------------------------------------------------------------------------------
-// Organisation A (C = 128): three warp roles.  warps 0-3 row threads, warp 4 streams weight blocks
-// through a ring (empty/full mbarriers), warp 5 issues the MMAs.
+// Organisation A (C = 128): three warp roles, TWO 128-token tiles per CTA.  At C = 128 the eight [C x C] weight
+// blocks of the chain are 256 KB per tile pass - more than shared memory holds and the dominant cost of a tile when
+// they are streamed for 128 rows only.  So a CTA runs two row groups (warps 0-3 and 4-7, thread <-> token <-> TMEM
+// lane, one tile each) in lockstep: every weight block brought in by the producer (warp 8) is used by the MMA issuer
+// (warp 9) for both tiles back to back (two accumulators of 2C TMEM columns), and the eight row warps run the
+// epilogues of the two tiles side by side (two warps per scheduler instead of one).  Each group owns ONE operand
+// buffer: the MLP hidden overwrites [x | msg] in place once its MMAs have completed, and the residual x is read again
+// through the provider (L2-hot) in the last epilogue.
 template <int C, int NH, bool kAttnOnly, class Q>
-__global__ void __launch_bounds__(192, ChainOcc<C>::CTAS) loftr_query_tc_kernel(Q q, cfp_loftr_w w, const float* __restrict__ kv,
+__global__ void __launch_bounds__(320, 1) loftr_query_tc_kernel(Q q, cfp_loftr_w w, const float* __restrict__ kv,
                                                              const float* __restrict__ ksum, int ntiles) {
     using P = ChainTC<C>;
     using S = ChainStages<C, NH, kAttnOnly, Q>;
@@ -237,24 +246,25 @@ __global__ void __launch_bounds__(192, ChainOcc<C>::CTAS) loftr_query_tc_kernel(
     constexpr int NCHUNK = kAttnOnly ? 1 : 8;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ ChainBars bars;
-    uint8_t* a0 = smem;                  // [x | msg, then LN1(merge(msg))]  2C columns
-    uint8_t* a1 = a0 + P::ABUF;          // the MLP hidden (2C columns)
-    uint8_t* ring = a1 + P::ABUF;
+    uint8_t* ring = smem + 2 * (size_t)P::ABUF;
     const int tid = threadIdx.x, warp = umma::warp_idx_sync();
+    const int npairs = (ntiles + 1) / 2;
 
     if (tid == 0) {
         for (int i = 0; i < P::NSLOT; ++i) { umma::mbar_init(&bars.full[i], 1); umma::mbar_init(&bars.empty[i], 1); }
-        umma::mbar_init(&bars.a_ready, 128);
+        umma::mbar_init(&bars.a_ready, 256);
         umma::mbar_init(&bars.acc_ready, 1);
         umma::fence_mbar_init();
     }
-    if (warp == 4) umma::tmem_alloc(&bars.tmem_slot, P::TMEM_COLS);
+    if (warp == 8) umma::tmem_alloc(&bars.tmem_slot, 512);
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
-    const uint32_t tmem = bars.tmem_slot;
 
-    if (warp < 4) {
+    if (warp < 8) {
+        const int grp = warp >> 2, wq = warp & 3, tid_g = tid & 127;
+        uint8_t* a0 = smem + (size_t)grp * P::ABUF;          // [x | msg, then LN1(merge(msg))], then the MLP hidden
+        const uint32_t tmem = bars.tmem_slot + grp * 256;
         uint32_t ph = 0;
         auto hand_over = [&]() {          // operands staged / accumulator consumed -> MMA warp; then wait for its result
             umma::fence_async_smem();
@@ -263,25 +273,27 @@ __global__ void __launch_bounds__(192, ChainOcc<C>::CTAS) loftr_query_tc_kernel(
             umma::mbar_wait(&bars.acc_ready, ph); ph ^= 1;
             umma::fence_after_sync();
         };
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const typename S::Row r = S::stage_x(q, (int64_t)tile * 128, tid, a0);
+        for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+            const int tile = 2 * pair + grp;                 // an odd tile count leaves group 1 of the last pair with dead rows
+            const int64_t row0 = tile < ntiles ? (int64_t)tile * 128 : q.rows;
+            const typename S::Row r = S::stage_x(q, row0, tid_g, a0);
             hand_over();
-            S::epi_attention(q, r, tmem, warp, tid, a0, kv, ksum);
+            S::epi_attention(q, r, tmem, wq, tid_g, a0, kv, ksum);
             if (!kAttnOnly) {
                 hand_over();
-                S::epi_ln1(w, tmem, warp, tid, a0);
+                S::epi_ln1(w, tmem, wq, tid_g, a0);
                 hand_over();
-                S::epi_relu(tmem, warp, tid, a1);
+                S::epi_relu(tmem, wq, tid_g, a0);             // in place: the W1 MMAs have consumed [x | LN1]
                 hand_over();
-                S::epi_out(q, r, w, tmem, warp, tid, a0);
+                S::template epi_out<true>(q, r, w, tmem, wq, tid_g, a0);
             }
             umma::fence_before_sync();
-            rows_sync();          // every row is done with a0 / the accumulator before the next tile is staged
+            asm volatile("bar.sync 1, 256;\n" ::: "memory");  // every row is done with a0 / the accumulators before the next pair
         }
-    } else if (warp == 4) {
+    } else if (warp == 8) {
         const bf16* wsrc = reinterpret_cast<const bf16*>(w.tc);
         int cc = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+        for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x)
             for (int c = 0; c < NCHUNK; ++c, ++cc) {
                 const int slot = cc % P::NSLOT, round = cc / P::NSLOT;
                 if (round > 0) umma::mbar_wait(&bars.empty[slot], (round - 1) & 1);
@@ -289,42 +301,46 @@ __global__ void __launch_bounds__(192, ChainOcc<C>::CTAS) loftr_query_tc_kernel(
             }
     } else {
         const uint32_t idesc = umma::idesc_bf16(128, C);
-        const uint32_t a0s = umma::smem_u32(a0), a1s = umma::smem_u32(a1), rs = umma::smem_u32(ring);
+        const uint32_t a0s = umma::smem_u32(smem), rs = umma::smem_u32(ring);
+        const uint32_t tmem = bars.tmem_slot;
         uint32_t ph = 0;
         int cc = 0;
-        auto block = [&](uint32_t abase, int kg0, int dcol, bool acc_first) {
+        // one weight block, both tiles: D_g[:, dcol:dcol+C] (+)= A_g[:, kg0*8 : kg0*8+C] * W^T
+        auto block = [&](int kg0, int dcol, bool acc_first) {
             const int slot = cc % P::NSLOT, round = cc / P::NSLOT;
             umma::mbar_wait(&bars.full[slot], round & 1);
             umma::fence_after_sync();
-            issue_block<C>(tmem + dcol, abase + kg0 * P::LBO, rs + slot * P::SLOT, idesc, acc_first);
+#pragma unroll
+            for (int g2 = 0; g2 < 2; ++g2)
+                issue_block<C>(tmem + g2 * 256 + dcol, a0s + g2 * P::ABUF + kg0 * P::LBO, rs + slot * P::SLOT, idesc, acc_first);
             umma::commit(&bars.empty[slot]);
             ++cc;
         };
         auto wait_a = [&]() { umma::mbar_wait(&bars.a_ready, ph); ph ^= 1; umma::fence_after_sync(); };
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
             wait_a();
-            block(a0s, 0, 0, false);                       // q
+            block(0, 0, false);                            // q
             umma::commit(&bars.acc_ready);
             if (kAttnOnly) continue;
             wait_a();
-            block(a0s, KG, 0, false);                      // merge: msg sits in a0[:, C:2C)
+            block(KG, 0, false);                           // merge: msg sits in a0[:, C:2C)
             umma::commit(&bars.acc_ready);
             wait_a();
-            block(a0s, 0, 0, false);                       // W1 quadrants: (n0,k0) (n0,k1) (n1,k0) (n1,k1)
-            block(a0s, KG, 0, true);
-            block(a0s, 0, C, false);
-            block(a0s, KG, C, true);
+            block(0, 0, false);                            // W1 quadrants: (n0,k0) (n0,k1) (n1,k0) (n1,k1)
+            block(KG, 0, true);
+            block(0, C, false);
+            block(KG, C, true);
             umma::commit(&bars.acc_ready);
             wait_a();
-            block(a1s, 0, 0, false);                       // W2 K-halves
-            block(a1s, KG, 0, true);
+            block(0, 0, false);                            // W2 K-halves (hidden sits in a0[:, 0:2C))
+            block(KG, 0, true);
             umma::commit(&bars.acc_ready);
         }
     }
     __syncthreads();
-    if (warp == 4) {
+    if (warp == 8) {
         umma::fence_after_sync();
-        umma::tmem_dealloc(tmem, P::TMEM_COLS);
+        umma::tmem_dealloc(bars.tmem_slot, 512);
     }
 }
 
@@ -334,6 +350,8 @@ __global__ void __launch_bounds__(192, ChainOcc<C>::CTAS) loftr_query_tc_kernel(
 // ring slots are known to be free (right after an accumulator wait), so there are no service warps
 // (their registers bought nothing), no empty-barriers and one mbarrier hand-off per stage instead
 // of two.  More CTAs fit per SM, which is what these latency-bound chains need.
+// (measured: an in-place hidden buffer + register caps for 8 / 3 CTAs per SM made these kernels 5-25 % SLOWER - they
+// are not occupancy-bound)
 template <int C> struct MonoOcc { static constexpr int CTAS = C == 32 ? 5 : 2; };
 struct MonoBars {
     uint64_t full[4], acc_ready, kv_full;
@@ -485,11 +503,11 @@ static int run_query_tc(const char* name, const Q& q, const cfp_loftr_w& w, cons
         if (int e = set_smem(k, smem)) return e;
         k<<<grid, 128, smem, st>>>(q, w, kv, ksum, (int)ntiles, kv_slots);
     } else {
-        const int per_sm = ChainOcc<C>::CTAS;
-        const int grid = (int)(ntiles < 148 * per_sm ? ntiles : 148 * per_sm);
+        const int64_t npairs = (ntiles + 1) / 2;
+        const int grid = (int)(npairs < 148 ? npairs : 148);
         auto k = loftr_query_tc_kernel<C, NH, kAttnOnly, Q>;
         if (int e = set_smem(k, P::SMEM)) return e;
-        k<<<grid, 192, P::SMEM, st>>>(q, w, kv, ksum, (int)ntiles);
+        k<<<grid, 320, P::SMEM, st>>>(q, w, kv, ksum, (int)ntiles);
     }
     return check_launch(name);
 }

@@ -12,17 +12,18 @@
 // The banded Toeplitz matrix T_dy carries the horizontal taps; the vertical tap is a row shift.  A row-shifted
 // A view (start address + 16 B * dy in the canonical K-major layout, umma.cuh) would work, but with N = 32 every
 // MMA is bound by the shared-memory read of its 4 KB A tile (twice that when the shift is not a multiple of
-// 8 rows).  So the vertical taps are split as dy = 8 a + b: the eight b's of one a use the SAME 8-row-aligned A
-// view and their Toeplitz blocks sit side by side along N:
+// 8 rows).  So the vertical taps are split as dy = NB a + b (NB = kDwNB = 4): the NB b's of one a use the SAME A view
+// (rows m + NB a) and their Toeplitz blocks sit side by side along N:
 //
-//   E[m][(b, n)] = sum_a sum_kk plane[m + 8 a][x0 + kk] * T_{8a+b}[n][kk]        one M=128 x N=256 x K=16 MMA per (a, kk/16)
-//   out[r][n]    = sum_b E[r + b][(b, n)]                                        row shift b applied by the epilogue
+//   E[m][(b, n)] = sum_a sum_kk plane[m + NB a][x0 + kk] * T_{NB a+b}[n][kk]      one M=128 x N=128 x K=16 MMA per (a, kk/16)
+//   out[r][n]    = sum_b E[r + b][(b, n)]                                         row shift b applied by the epilogue
 //
-// One A read now feeds 256 accumulator columns (the MMA runs at the tensor pipe's rate) and a 31 x 31 tile costs
-// 16 MMAs instead of 124.  The epilogue thread of accumulator row m gets E[m + b] from lane m + b with warp
-// shuffles; the rows that live in the next TMEM lane quarter travel through a small shared-memory exchange.
-// Sixteen epilogue warps (four per lane quarter, 8 output columns each) keep four warps on every scheduler: with one
-// warp per scheduler the (latency-bound) epilogue, not the tensor pipe, paced the kernel.
+// One A read feeds NB x 32 accumulator columns, so the MMA runs at the tensor pipe's rate instead of the operand
+// fetch rate.  NB is a balance: the epilogue has to read NB x 32 accumulator columns per output row through
+// tcgen05.ld (64 B/clk/SM) - at NB = 8 that alone took as long as the MMAs - and needs NB - 1 shuffles per column.
+// The epilogue thread of accumulator row m gets E[m + b] from lane m + b with warp shuffles; the rows that live in
+// the next TMEM lane quarter travel through a small shared-memory exchange.  Eight epilogue warps (two per lane
+// quarter, 16 output columns each) keep two warps on every scheduler.
 // About half of every T_dy is structural zeros; the tensor pipe is still >10x faster than the FMA pipe on this op.
 //
 // Data flow: dw_plane_pack_kernel rewrites the token-major map into zero-padded channel planes stored
@@ -39,7 +40,9 @@
 
 namespace cfp {
 
-constexpr int kDwMS = 120;     // output rows per 128-row M block: the epilogue reads accumulator rows m .. m+7
+constexpr int kDwNB = 4;       // vertical taps stacked along the MMA's N dimension (dy = kDwNB * a + b)
+constexpr int kDwN = kDwNB * 32;
+constexpr int kDwMS = 120;     // output rows per 128-row M block: the epilogue reads accumulator rows m .. m + kDwNB - 1
 
 struct DwGeom {
     int H, W, C, K, PAD;
@@ -50,7 +53,7 @@ struct DwGeom {
     int nM;        // M blocks (kDwMS output rows each) per stack
     int HP;        // padded plane rows
     int KS;        // 16-column K-steps per tap group = ceil((32 + K - 1) / 16)
-    int NA;        // groups of eight vertical taps = ceil(K / 8)
+    int NA;        // groups of kDwNB vertical taps = ceil(K / kDwNB)
     int nX;        // 32-column output tiles
     int WG;        // 8-column groups per plane = 4*nX + 2*KS - 4
 };
@@ -65,10 +68,10 @@ static DwGeom dw_geom(int B, int H, int W, int C, int K) {
     const int rows = g.F * H + (g.F - 1) * g.PAD;      // output rows of one stack
     g.nM = (rows + kDwMS - 1) / kDwMS;
     g.KS = (32 + K - 1 + 15) / 16;
-    g.NA = (K + 7) / 8;
+    g.NA = (K + kDwNB - 1) / kDwNB;
     // rows an A view can touch: last block start + 128 accumulator rows + 8 rows per further tap group;
     // and every row that feeds a stored output (PAD + F x (H + PAD)) must exist for the pack kernel
-    g.HP = (g.nM - 1) * kDwMS + 128 + 8 * (g.NA - 1);
+    g.HP = (g.nM - 1) * kDwMS + 128 + kDwNB * (g.NA - 1);
     if (g.HP < g.F * g.RS + g.PAD) g.HP = g.F * g.RS + g.PAD;
     g.nX = (W + 31) / 32;
     g.WG = 4 * g.nX + 2 * g.KS - 4;
@@ -182,13 +185,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 }
 
 constexpr int kXchLd = 36;                                 // floats per exchanged row (16-byte aligned, bank-staggered)
-constexpr int kXchRows = 28;                               // rows a warp publishes per item: sum_{b=1..7} b
+constexpr int kXchRows = kDwNB * (kDwNB - 1) / 2;           // rows a quarter publishes per item: sum_{b=1..NB-1} b
 constexpr size_t kXchBytes = 2 * 3 * kXchRows * kXchLd * sizeof(float);
-constexpr int kDwParts = 4;                                // epilogue warps per TMEM lane quarter
+constexpr int kDwParts = 2;                                // epilogue warps per TMEM lane quarter
 constexpr int kDwCols = 32 / kDwParts;                     // output columns per epilogue thread
 constexpr int kDwEpiWarps = 4 * kDwParts;
 constexpr int kDwThreads = (kDwEpiWarps + 2) * 32;         // + bulk-copy producer warp + MMA issuer warp
-constexpr size_t kBndBytes = 2 * kDwEpiWarps * 7 * kDwCols * sizeof(float);   // per (item parity, warp): 7 boundary rows
+constexpr size_t kBndBytes = 2 * kDwEpiWarps * (kDwNB - 1) * kDwCols * sizeof(float);   // per (item parity, warp): boundary rows
 
 template <int NC> __device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[NC]);
 template <> __device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, float (&v)[16]) { umma::tmem_ld16(taddr, v); }
@@ -209,7 +212,7 @@ __global__ void __launch_bounds__(kDwThreads) dwconv_tc_kernel(const bf16* __res
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ DwBars bars;
     const int tid = threadIdx.x, warp = umma::warp_idx_sync(), lane = tid & 31;
-    constexpr uint32_t t_blk = 2 * 256 * 16;                   // bytes of one (a, ks) block  [2 k-groups][256 = (b, n)][8]
+    constexpr uint32_t t_blk = 2 * kDwN * 16;                  // bytes of one (a, ks) block  [2 k-groups][kDwN = (b, n)][8]
     const uint32_t t_bytes = g.NA * g.KS * t_blk;
     const uint32_t lbo_a = g.HP * 16;
     const uint32_t a_bytes = 2 * g.KS * lbo_a;
@@ -227,7 +230,7 @@ __global__ void __launch_bounds__(kDwThreads) dwconv_tc_kernel(const bf16* __res
         for (int i = 0; i < 2; ++i) { umma::mbar_init(&bars.acc_full[i], 1); umma::mbar_init(&bars.acc_empty[i], kDwEpiWarps * 32); }
         umma::fence_mbar_init();
     }
-    if (warp == kDwEpiWarps) umma::tmem_alloc(&bars.tmem_slot, 512);
+    if (warp == kDwEpiWarps) umma::tmem_alloc(&bars.tmem_slot, 2 * kDwN);
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
@@ -243,14 +246,14 @@ __global__ void __launch_bounds__(kDwThreads) dwconv_tc_kernel(const bf16* __res
             const DwItem it = dw_item(i, g);
             const float sh = shift[it.c];
             float* xw = xch + (size_t)ab * (3 * kXchRows * kXchLd) + part * NC;
-            float* bw = bnd + ((size_t)ab * kDwEpiWarps + warp) * (7 * NC);
+            float* bw = bnd + ((size_t)ab * kDwEpiWarps + warp) * ((kDwNB - 1) * NC);
             umma::mbar_wait(&bars.acc_full[ab], (n >> 1) & 1);
             umma::fence_after_sync();
             float acc[NC];
 #pragma unroll
-            for (int b = 0; b < 8; ++b) {
+            for (int b = 0; b < kDwNB; ++b) {
                 float e[NC];
-                tmem_ld<NC>(umma::tmem_addr(tmem, q * 32, ab * 256 + b * 32 + part * NC), e);
+                tmem_ld<NC>(umma::tmem_addr(tmem, q * 32, ab * kDwN + b * 32 + part * NC), e);
                 if (b == 0) {
 #pragma unroll
                     for (int j = 0; j < NC; ++j) acc[j] = e[j];
@@ -277,19 +280,19 @@ __global__ void __launch_bounds__(kDwThreads) dwconv_tc_kernel(const bf16* __res
                 // four of the NC columns) sums its b's, then hands the partial row over through `bw`
                 constexpr int QPR = NC / 4;                    // float4 per row
                 const int t = lane / QPR, cq = (lane % QPR) * 4;
-                if (t < 7) {
+                if (t < kDwNB - 1) {
                     float4 sacc = make_float4(0.f, 0.f, 0.f, 0.f);
-                    for (int b = 7 - t; b < 8; ++b) {
-                        const float4 v = *reinterpret_cast<const float4*>(xw + ((size_t)q * kXchRows + b * (b - 1) / 2 + (t + b - 7)) * kXchLd + cq);
+                    for (int b = kDwNB - 1 - t; b < kDwNB; ++b) {
+                        const float4 v = *reinterpret_cast<const float4*>(xw + ((size_t)q * kXchRows + b * (b - 1) / 2 + (t + b - (kDwNB - 1))) * kXchLd + cq);
                         sacc.x += v.x; sacc.y += v.y; sacc.z += v.z; sacc.w += v.w;
                     }
                     *reinterpret_cast<float4*>(bw + t * NC + cq) = sacc;
                 }
                 __syncwarp();
-                if (lane >= 25) {
+                if (lane >= 33 - kDwNB) {
 #pragma unroll
                     for (int j = 0; j < NC; j += 4) {
-                        const float4 v = *reinterpret_cast<const float4*>(bw + (lane - 25) * NC + j);
+                        const float4 v = *reinterpret_cast<const float4*>(bw + (lane - (33 - kDwNB)) * NC + j);
                         acc[j] += v.x; acc[j + 1] += v.y; acc[j + 2] += v.z; acc[j + 3] += v.w;
                     }
                 }
@@ -344,8 +347,8 @@ __global__ void __launch_bounds__(kDwThreads) dwconv_tc_kernel(const bf16* __res
     } else {
         // ---------------- MMA issuer (warp-uniform control flow; one elected lane issues)
         {
-            const uint32_t idesc = umma::idesc_bf16(128, 256);
-            const uint64_t tdesc0 = umma::smem_desc(umma::smem_u32(t_sm), 256 * 16);
+            const uint32_t idesc = umma::idesc_bf16(128, kDwN);
+            const uint64_t tdesc0 = umma::smem_desc(umma::smem_u32(t_sm), kDwN * 16);
             const uint32_t as0 = umma::smem_u32(a_sm);
             int cur_c = -1, nt = 0;
             for (int i = i0; i < i1; ++i) {
@@ -364,7 +367,7 @@ __global__ void __launch_bounds__(kDwThreads) dwconv_tc_kernel(const bf16* __res
                 // side along N (256 = 8 x 32 columns); their row shift b is applied by the epilogue
                 uint64_t ad = umma::smem_desc(as0 + s * a_stride + (uint32_t)(it.mt * kDwMS) * 16, lbo_a);
                 uint64_t td = tdesc0;
-                const uint32_t dcol = tmem + ab * 256;
+                const uint32_t dcol = tmem + ab * kDwN;
                 for (int a = 0; a < g.NA; ++a) {
                     uint64_t adj = ad;
                     for (int j = 0; j < g.KS; ++j) {
@@ -372,7 +375,8 @@ __global__ void __launch_bounds__(kDwThreads) dwconv_tc_kernel(const bf16* __res
                         adj = umma::desc_advance(adj, 2 * lbo_a);
                         td = umma::desc_advance(td, t_blk);
                     }
-                    ad = umma::desc_advance(ad, 8 * 16);       // next group of eight vertical taps: eight rows down
+                    ad = umma::desc_advance(ad, kDwNB * 16);   // next group of vertical taps: kDwNB rows down (any 16-byte
+                                                               // aligned start is a legal operand view; measured: no penalty)
                 }
                 umma::commit(&bars.a_empty[s]);
                 umma::commit(&bars.acc_full[ab]);
@@ -382,7 +386,7 @@ __global__ void __launch_bounds__(kDwThreads) dwconv_tc_kernel(const bf16* __res
     __syncthreads();
     if (warp == kDwEpiWarps) {
         umma::fence_after_sync();
-        umma::tmem_dealloc(tmem, 512);
+        umma::tmem_dealloc(tmem, 2 * kDwN);
     }
 }
 
@@ -403,7 +407,7 @@ int dwconv_tc(const void* in, const void** planar_out_p, int B, int H, int W, in
         if (int err = check_launch("dw_plane_pack")) return err;
     }
     {
-        const uint32_t t_bytes = g.NA * g.KS * 2 * 256 * 16, a_bytes = 2 * g.KS * g.HP * 16;
+        const uint32_t t_bytes = g.NA * g.KS * 2 * kDwN * 16, a_bytes = 2 * g.KS * g.HP * 16;
         const size_t smem = t_bytes + 3 * (size_t)((a_bytes + 127) & ~127u) + kXchBytes + kBndBytes;
         CFP_REQUIRE(smem <= 225 * 1024, "dwconv (tensor-core path): %zu B shared memory (H=%d too tall)", smem, H);
         if (int err = set_smem(dwconv_tc_kernel, smem)) return err;

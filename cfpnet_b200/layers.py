@@ -230,17 +230,18 @@ class Block14(nn.Module):
             blocks += [umma_block(w1[j * 128:(j + 1) * 128, :]).reshape(-1), umma_block(w2[:, j * 128:(j + 1) * 128]).reshape(-1)]
         t["tc"] = torch.cat(blocks).contiguous()
         # banded-Toeplitz blocks of the depthwise taps for the tensor-core path (csrc/k_dwconv_tc.cu):
-        # T_dy[n][kk] = w[dy][kk - n]; vertical taps grouped as dy = 8 a + b with the eight b's side by side along
-        # the MMA's N dimension -> [C][a][k-step][k-group (2)][b*32 + n (256)][8] bf16 (UMMA K-major B blocks)
+        # T_dy[n][kk] = w[dy][kk - n]; vertical taps grouped as dy = 4 a + b with the four b's side by side along
+        # the MMA's N dimension -> [C][a][k-step][k-group (2)][b*32 + n (128)][8] bf16 (UMMA K-major B blocks)
+        nb = 4                                              # kDwNB in csrc/k_dwconv_tc.cu
         ks = (32 + k - 1 + 15) // 16
-        na = (k + 7) // 8
+        na = (k + nb - 1) // nb
         n = torch.arange(32, device=taps.device)[:, None]
         kk = torch.arange(16 * ks, device=taps.device)[None, :]
         dx = kk - n
         band = ((dx >= 0) & (dx < k)).to(taps.dtype)
         toep = taps[:, :, dx.clamp(0, k - 1)] * band                      # [C, k(dy), 32, 16*ks]
-        toep = torch.cat([toep, toep.new_zeros(C, 8 * na - k, 32, 16 * ks)], dim=1)
-        t["dw_toep"] = (toep.to(torch.bfloat16).view(C, na, 8, 32, ks, 2, 8).permute(0, 1, 4, 5, 2, 3, 6).contiguous())
+        toep = torch.cat([toep, toep.new_zeros(C, nb * na - k, 32, 16 * ks)], dim=1)
+        t["dw_toep"] = (toep.to(torch.bfloat16).view(C, na, nb, 32, ks, 2, 8).permute(0, 1, 4, 5, 2, 3, 6).contiguous())
         keep.extend(t.values())
         w = _lib.CfpLkpmW(**{n: v.data_ptr() for n, v in t.items()})
         w.ksize = k

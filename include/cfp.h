@@ -89,9 +89,9 @@ typedef struct cfp_lkpm_w {
      * as [16][C][8].  Required for CFP_BF16. */
     const void *tc;
     /* bf16 tensor-core depthwise conv: banded-Toeplitz blocks T_dy[n][kk] = dw_t-tap(dy, kk-n) (0 outside
-     * 0 <= kk-n < k), n < 32, kk < 16*KS, KS = ceil((31+k)/16).  Vertical taps are grouped dy = 8a + b
-     * (a < NA = ceil(k/8); zero blocks for dy >= k) with the eight b's side by side along N:
-     * bf16 [C][NA][KS][2][256 = b*32+n][8]  (per (a, k-step) one UMMA B block [2][256][8]).
+     * 0 <= kk-n < k), n < 32, kk < 16*KS, KS = ceil((31+k)/16).  Vertical taps are grouped dy = 4a + b
+     * (a < NA = ceil(k/4); zero blocks for dy >= k) with the four b's side by side along N:
+     * bf16 [C][NA][KS][2][128 = b*32+n][8]  (per (a, k-step) one UMMA B block [2][128][8]).
      * Required for CFP_BF16 when k >= 15. */
     const void *dw_toep;
     int32_t ksize;
