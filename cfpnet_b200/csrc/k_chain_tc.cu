@@ -760,7 +760,10 @@ template <int C> struct KvTC {
     static constexpr size_t SMEM = (size_t)(KG + A1G) * ChainTC<C>::LBO + 4 * (size_t)C * C;
 };
 
-template <int C, int NH, bool kComplete, class Src>
+// kZone16 (groups of exactly one 16-row MMA step: the hist2image zones): the per-group reduction is done by the row
+// threads themselves with FMAs straight from the bf16 K | V tile - 16 rows x dh products per (channel, group) - instead
+// of one MMA + accumulator read-back + flush round trip per group (eight serial round trips per tile).
+template <int C, int NH, bool kComplete, class Src, bool kZone16 = false>
 __global__ void __launch_bounds__(192) kv_state_tc_kernel(Src src, int S, int S_pad, int groups, const bf16* __restrict__ wkv_tc,
                                                           float* __restrict__ kv, float* __restrict__ ksum, int ntiles) {
     using P = ChainTC<C>;
@@ -822,6 +825,41 @@ __global__ void __launch_bounds__(192) kv_state_tc_kernel(Src src, int S, int S_
                     for (int i = 0; i < 8; ++i) o8[i] = !real ? 0.f : (c0 < C ? elu1(t[j + i]) : t[j + i]);
                     umma::store_chunk(a1, P::LBO, tid, (c0 + j) / 8, o8);
                 }
+            }
+            if constexpr (kZone16) {
+                umma::fence_before_sync();
+                rows_sync();                                   // K | V of all 128 rows staged; accumulator consumed
+                constexpr int ZPT = 8 / (128 / C);             // zones per thread: thread = (channel c1, zone subset)
+                const int c1 = tid % C, h0 = (c1 / DH) * DH;
+                const uint8_t* kp = a1 + (size_t)(c1 / 8) * P::LBO + (c1 % 8) * 2;
+                const uint8_t* vp = a1 + (size_t)(KG + h0 / 8) * P::LBO;
+                for (int z = (tid / C) * ZPT; z < (tid / C) * ZPT + ZPT; ++z) {
+                    float acc[DH], ks = 0.f;
+#pragma unroll
+                    for (int v = 0; v < DH; ++v) acc[v] = 0.f;
+#pragma unroll 4
+                    for (int rr = 0; rr < 16; ++rr) {
+                        const int rw = z * 16 + rr;
+                        const float kval = __uint_as_float((uint32_t)*reinterpret_cast<const uint16_t*>(kp + rw * 16) << 16);
+                        ks += kval;
+#pragma unroll
+                        for (int v8 = 0; v8 < DH / 8; ++v8) {
+                            float vv[8];
+                            unpack8(*reinterpret_cast<const uint4*>(vp + (size_t)v8 * P::LBO + rw * 16), vv);
+#pragma unroll
+                            for (int i2 = 0; i2 < 8; ++i2) acc[v8 * 8 + i2] = fmaf(kval, vv[i2], acc[v8 * 8 + i2]);
+                        }
+                    }
+                    const int64_t g = (int64_t)tile * 8 + z;
+                    if (g < groups) {
+                        float* dst = kv + (size_t)g * (C * DH) + (size_t)c1 * DH;
+#pragma unroll
+                        for (int v = 0; v < DH; v += 4) *reinterpret_cast<float4*>(dst + v) = make_float4(acc[v], acc[v + 1], acc[v + 2], acc[v + 3]);
+                        ksum[(size_t)g * C + c1] = ks;
+                    }
+                }
+                rows_sync();                                   // a1 is rewritten by the next tile's epilogue
+                continue;
             }
             {
                 const float one8[8] = {real ? 1.f : 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -891,6 +929,7 @@ __global__ void __launch_bounds__(192) kv_state_tc_kernel(Src src, int S, int S_
                         umma::mma_bf16(tmem + half * C, umma::smem_desc(a0s + 2 * ks * P::LBO, P::LBO),
                                        umma::smem_desc(ws + half * 2 * C * C + ks * 2 * LBO_B, LBO_B), idesc, ks > 0);
                 umma::commit(&bars.acc_ready);
+                if constexpr (kZone16) continue;              // the row threads reduce the groups themselves
                 wait_a();                                     // K | V | ones staged
                 int ks = 0;
                 bool first = true;
@@ -931,7 +970,11 @@ static int run_kv_state_tc(const char* name, const Src& src, int S, int groups, 
     const int64_t ntiles = ((int64_t)groups * S_pad + 127) / 128;
     const int per_sm = C >= 128 ? 1 : (C == 64 ? 2 : 4);
     const int grid = (int)(ntiles < 148 * per_sm ? ntiles : 148 * per_sm);
-    if (complete) {
+    if (S_pad == 16 && NH == 4) {                     // hist2image zones (dh = C/4 is a multiple of 8)
+        auto k = kv_state_tc_kernel<C, NH, true, Src, (NH == 4)>;
+        if (int e = set_smem(k, K::SMEM)) return e;
+        k<<<grid, 192, K::SMEM, st>>>(src, S, S_pad, groups, (const bf16*)wkv_tc, kv, ksum, (int)ntiles);
+    } else if (complete) {
         auto k = kv_state_tc_kernel<C, NH, true, Src>;
         if (int e = set_smem(k, K::SMEM)) return e;
         k<<<grid, 192, K::SMEM, st>>>(src, S, S_pad, groups, (const bf16*)wkv_tc, kv, ksum, (int)ntiles);

@@ -42,6 +42,7 @@ namespace cfp {
 
 constexpr int kDwNB = 4;       // vertical taps stacked along the MMA's N dimension (dy = kDwNB * a + b)
 constexpr int kDwN = kDwNB * 32;
+constexpr int kDwAcc = kDwN <= 128 ? 128 : 256;   // TMEM columns reserved per accumulator (two accumulators)
 constexpr int kDwMS = 120;     // output rows per 128-row M block: the epilogue reads accumulator rows m .. m + kDwNB - 1
 
 struct DwGeom {
@@ -230,7 +231,7 @@ __global__ void __launch_bounds__(kDwThreads) dwconv_tc_kernel(const bf16* __res
         for (int i = 0; i < 2; ++i) { umma::mbar_init(&bars.acc_full[i], 1); umma::mbar_init(&bars.acc_empty[i], kDwEpiWarps * 32); }
         umma::fence_mbar_init();
     }
-    if (warp == kDwEpiWarps) umma::tmem_alloc(&bars.tmem_slot, 2 * kDwN);
+    if (warp == kDwEpiWarps) umma::tmem_alloc(&bars.tmem_slot, 2 * kDwAcc);
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
@@ -253,7 +254,7 @@ __global__ void __launch_bounds__(kDwThreads) dwconv_tc_kernel(const bf16* __res
 #pragma unroll
             for (int b = 0; b < kDwNB; ++b) {
                 float e[NC];
-                tmem_ld<NC>(umma::tmem_addr(tmem, q * 32, ab * kDwN + b * 32 + part * NC), e);
+                tmem_ld<NC>(umma::tmem_addr(tmem, q * 32, ab * kDwAcc + b * 32 + part * NC), e);
                 if (b == 0) {
 #pragma unroll
                     for (int j = 0; j < NC; ++j) acc[j] = e[j];
@@ -367,7 +368,7 @@ __global__ void __launch_bounds__(kDwThreads) dwconv_tc_kernel(const bf16* __res
                 // side along N (256 = 8 x 32 columns); their row shift b is applied by the epilogue
                 uint64_t ad = umma::smem_desc(as0 + s * a_stride + (uint32_t)(it.mt * kDwMS) * 16, lbo_a);
                 uint64_t td = tdesc0;
-                const uint32_t dcol = tmem + ab * kDwN;
+                const uint32_t dcol = tmem + ab * kDwAcc;
                 for (int a = 0; a < g.NA; ++a) {
                     uint64_t adj = ad;
                     for (int j = 0; j < g.KS; ++j) {
@@ -386,7 +387,7 @@ __global__ void __launch_bounds__(kDwThreads) dwconv_tc_kernel(const bf16* __res
     __syncthreads();
     if (warp == kDwEpiWarps) {
         umma::fence_after_sync();
-        umma::tmem_dealloc(tmem, 2 * kDwN);
+        umma::tmem_dealloc(tmem, 2 * kDwAcc);
     }
 }
 
