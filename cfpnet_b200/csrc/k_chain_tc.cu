@@ -575,13 +575,21 @@ __global__ void __launch_bounds__(192) lkpm_mlp_tc_kernel(bf16* __restrict__ fea
         uint32_t ph = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int64_t row = (int64_t)tile * 128 + tid;
+            // residual x of the row, fetched now so that the last epilogue does not stall on it (registers permitting)
+            constexpr bool kPrefetchX = C <= 64;
+            uint4 xres[kPrefetchX ? C / 8 : 1];
+            if constexpr (kPrefetchX) {
+#pragma unroll
+                for (int j = 0; j < C / 8; ++j)
+                    xres[j] = row < rows ? *reinterpret_cast<const uint4*>(feat0 + row * C + j * 8) : make_uint4(0u, 0u, 0u, 0u);
+            }
             {   // channels-last LayerNorm (eps 1e-6) of row `tid` -> a0
                 float v[C];
                 if (planar_n > 0) {
                     // planar dwconv output [frame][C][planar_n]: lanes are consecutive tokens, so each of the C
                     // two-byte loads of a warp is one contiguous 64-byte segment
-                    const int64_t fr = row / planar_n;
-                    const uint16_t* p = reinterpret_cast<const uint16_t*>(y) + fr * C * planar_n + (row - fr * planar_n);
+                    const uint32_t fr = (uint32_t)row / (uint32_t)planar_n;      // rows < 2^31: 32-bit divide
+                    const uint16_t* p = reinterpret_cast<const uint16_t*>(y) + (size_t)fr * C * planar_n + ((uint32_t)row - fr * (uint32_t)planar_n);
 #pragma unroll
                     for (int c = 0; c < C; ++c)
                         v[c] = row < rows ? __uint_as_float((uint32_t)__ldg(p + (size_t)c * planar_n) << 16) : 0.f;
@@ -643,7 +651,7 @@ __global__ void __launch_bounds__(192) lkpm_mlp_tc_kernel(bf16* __restrict__ fea
             }
             umma::mbar_wait(&bars.acc_ready, ph); ph ^= 1;       // out accumulator complete
             umma::fence_after_sync();
-#pragma unroll 1
+#pragma unroll
             for (int c0 = 0; c0 < C; c0 += 16) {
                 float t[16];
                 umma::tmem_ld16(umma::tmem_addr(tmem, warp * 32, M::OUT_COL + c0), t);
@@ -652,7 +660,8 @@ __global__ void __launch_bounds__(192) lkpm_mlp_tc_kernel(bf16* __restrict__ fea
                     for (int j = 0; j < 16; j += 8) {
                         bf16* p = feat0 + row * C + c0 + j;
                         float x8[8];
-                        unpack8(*reinterpret_cast<const uint4*>(p), x8);
+                        if constexpr (kPrefetchX) unpack8(xres[(c0 + j) / 8], x8);
+                        else unpack8(*reinterpret_cast<const uint4*>(p), x8);
                         const float4 ba = *reinterpret_cast<const float4*>(w.pw2_b + c0 + j), bb = *reinterpret_cast<const float4*>(w.pw2_b + c0 + j + 4);
                         uint4 u;
                         u.x = umma::pack_bf16(x8[0] + t[j + 0] + ba.x, x8[1] + t[j + 1] + ba.y);
@@ -764,7 +773,7 @@ template <int C> struct KvTC {
 // threads themselves with FMAs straight from the bf16 K | V tile - 16 rows x dh products per (channel, group) - instead
 // of one MMA + accumulator read-back + flush round trip per group (eight serial round trips per tile).
 template <int C, int NH, bool kComplete, class Src, bool kZone16 = false>
-__global__ void __launch_bounds__(192) kv_state_tc_kernel(Src src, int S, int S_pad, int groups, const bf16* __restrict__ wkv_tc,
+__global__ void __launch_bounds__(192) kv_state_tc_kernel(Src src, int S, int S_pad, FastDiv dSp, int groups, const bf16* __restrict__ wkv_tc,
                                                           float* __restrict__ kv, float* __restrict__ ksum, int ntiles) {
     using P = ChainTC<C>;
     using K = KvTC<C>;
@@ -791,14 +800,15 @@ __global__ void __launch_bounds__(192) kv_state_tc_kernel(Src src, int S, int S_
     __syncthreads();
     umma::fence_after_sync();
     const uint32_t tmem = bars.tmem_slot;
-    const int64_t total = (int64_t)groups * S_pad;
+    const uint32_t total = (uint32_t)groups * (uint32_t)S_pad;      // < 2^31 (checked by the launcher): 32-bit index math and
+                                                                      // multiply-high division (a 64-bit divide per run used to cost ~25 % here)
 
     if (warp < 4) {
         uint32_t ph = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const int64_t row0 = (int64_t)tile * 128;
-            const int64_t myp = row0 + tid;
-            const int myg = (int)(myp / S_pad), mys = (int)(myp - (int64_t)myg * S_pad);
+            const uint32_t row0 = (uint32_t)tile * 128u;
+            const uint32_t myp = row0 + tid;
+            const int myg = (int)dSp.div(myp), mys = (int)(myp - (uint32_t)myg * (uint32_t)S_pad);
             const bool real = myp < total && mys < S;
             {
                 const typename Src::R ref = src.locate(real ? (int64_t)myg * S + mys : 0);
@@ -872,9 +882,9 @@ __global__ void __launch_bounds__(192) kv_state_tc_kernel(Src src, int S, int S_
             // ---- flush the runs: lane c1 adds D[c1][head(c1) block] and D[c1][ones] to the state
             int ks = 0;
             while (ks < 8 && row0 + 16 * ks < total) {
-                const int g = (int)((row0 + 16 * ks) / S_pad);
+                const int g = (int)dSp.div(row0 + 16 * ks);
                 int ke = ks + 1;
-                while (ke < 8 && row0 + 16 * ke < total && (int)((row0 + 16 * ke) / S_pad) == g) ++ke;
+                while (ke < 8 && row0 + 16 * ke < total && (int)dSp.div(row0 + 16 * ke) == g) ++ke;
                 umma::mbar_wait(&bars.acc_ready, ph); ph ^= 1;
                 umma::fence_after_sync();
                 if (warp * 32 < C) {
@@ -920,7 +930,7 @@ __global__ void __launch_bounds__(192) kv_state_tc_kernel(Src src, int S, int S_
             umma::mbar_wait(&bars.full[0], 0);
             umma::fence_after_sync();
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                const int64_t row0 = (int64_t)tile * 128;
+                const uint32_t row0 = (uint32_t)tile * 128u;
                 wait_a();
 #pragma unroll
                 for (int half = 0; half < 2; ++half)          // k -> cols [0,C), v -> cols [C,2C)
@@ -934,9 +944,9 @@ __global__ void __launch_bounds__(192) kv_state_tc_kernel(Src src, int S, int S_
                 int ks = 0;
                 bool first = true;
                 while (ks < 8 && row0 + 16 * ks < total) {
-                    const int g = (int)((row0 + 16 * ks) / S_pad);
+                    const int g = (int)dSp.div(row0 + 16 * ks);
                     int ke = ks + 1;
-                    while (ke < 8 && row0 + 16 * ke < total && (int)((row0 + 16 * ke) / S_pad) == g) ++ke;
+                    while (ke < 8 && row0 + 16 * ke < total && (int)dSp.div(row0 + 16 * ke) == g) ++ke;
                     if (!first) wait_a();                     // previous run's accumulator has been read
                     first = false;
                     for (int k = ks; k < ke; ++k)             // MN-major views: SBO = group stride, LBO = 8 rows
@@ -968,20 +978,21 @@ static int run_kv_state_tc(const char* name, const Src& src, int S, int groups, 
         if (e != cudaSuccess) return fail("cudaMemsetAsync(kv state): %s", cudaGetErrorString(e));
     }
     const int64_t ntiles = ((int64_t)groups * S_pad + 127) / 128;
+    CFP_REQUIRE((int64_t)groups * S_pad < ((int64_t)1 << 31), "%s: %lld padded rows exceed the 32-bit row index", name, (long long)groups * S_pad);
     const int per_sm = C >= 128 ? 1 : (C == 64 ? 2 : 4);
     const int grid = (int)(ntiles < 148 * per_sm ? ntiles : 148 * per_sm);
     if (S_pad == 16 && NH == 4) {                     // hist2image zones (dh = C/4 is a multiple of 8)
         auto k = kv_state_tc_kernel<C, NH, true, Src, (NH == 4)>;
         if (int e = set_smem(k, K::SMEM)) return e;
-        k<<<grid, 192, K::SMEM, st>>>(src, S, S_pad, groups, (const bf16*)wkv_tc, kv, ksum, (int)ntiles);
+        k<<<grid, 192, K::SMEM, st>>>(src, S, S_pad, FastDiv((uint32_t)S_pad), groups, (const bf16*)wkv_tc, kv, ksum, (int)ntiles);
     } else if (complete) {
         auto k = kv_state_tc_kernel<C, NH, true, Src>;
         if (int e = set_smem(k, K::SMEM)) return e;
-        k<<<grid, 192, K::SMEM, st>>>(src, S, S_pad, groups, (const bf16*)wkv_tc, kv, ksum, (int)ntiles);
+        k<<<grid, 192, K::SMEM, st>>>(src, S, S_pad, FastDiv((uint32_t)S_pad), groups, (const bf16*)wkv_tc, kv, ksum, (int)ntiles);
     } else {
         auto k = kv_state_tc_kernel<C, NH, false, Src>;
         if (int e = set_smem(k, K::SMEM)) return e;
-        k<<<grid, 192, K::SMEM, st>>>(src, S, S_pad, groups, (const bf16*)wkv_tc, kv, ksum, (int)ntiles);
+        k<<<grid, 192, K::SMEM, st>>>(src, S, S_pad, FastDiv((uint32_t)S_pad), groups, (const bf16*)wkv_tc, kv, ksum, (int)ntiles);
     }
     return check_launch(name);
 }
@@ -1006,10 +1017,13 @@ int kv_tc_dapm(int C, const InsideSrc<bf16>& src, int S, int groups, const void*
 // GEMM with K = ws*ws*C whose A rows are gathered per tap.  Only B*Ns (a few thousand) rows exist,
 // so the K dimension (taps) is split across CTAs (grid = row tiles x tap splits) and partial sums
 // are added atomically into an fp32 accumulator; sr_bias_ln_kernel then applies bias + LayerNorm.
-// Per tap: the 128 row threads gather the [128 x C] A slice into a 2-stage ring while the bulk-copy
-// engine brings the [C x C] weight block; the MMA lane consumes both and frees the stage by commit.
+// Per tap the 128 row threads copy the [128 x C] A slice into a ring stage with zero-fill cp.async (every 16-byte chunk
+// is one fire-and-forget copy; each thread's chunk addresses are tap-independent up to a common offset and are located
+// once) while the bulk-copy engine brings the [C x C] weight block; SrTC::NST taps are in flight, the MMA lane consumes
+// a stage and frees it by commit.  (With a 2-stage register-staged gather every tap paid a full global-load round trip.)
+template <int C> struct SrTC { static constexpr int NST = C >= 128 ? 3 : (C == 64 ? 4 : 6); };
 struct SrBars {
-    uint64_t a_full[2], w_full[2], empty[2], acc_ready;
+    uint64_t a_full[6], w_full[6], empty[6], acc_ready;
     uint32_t tmem_slot;
 };
 
@@ -1018,18 +1032,18 @@ __global__ void __launch_bounds__(192) sr_conv_tc_kernel(const bf16* __restrict_
                                                          int64_t rows, int H, int W, int ws, int nsx, int Ns,
                                                          const bf16* __restrict__ sr_tc, int taps_per_cta) {
     using P = ChainTC<C>;
-    constexpr int KG = P::KG, TCOLS = C < 32 ? 32 : C;
+    constexpr int KG = P::KG, TCOLS = C < 32 ? 32 : C, NST = SrTC<C>::NST;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ SrBars bars;
-    uint8_t* a_st = smem;                                // [2][KG][129][16 B]
-    uint8_t* w_st = a_st + 2 * KG * P::LBO;              // [2][C x C]
-    const int tid = threadIdx.x, warp = umma::warp_idx_sync(), lane = tid & 31;
+    uint8_t* a_st = smem;                                // [NST][KG][129][16 B]
+    uint8_t* w_st = a_st + (size_t)NST * KG * P::LBO;    // [NST][C x C]
+    const int tid = threadIdx.x, warp = umma::warp_idx_sync();
     const int ntap = ws * ws;
     const int t0 = blockIdx.y * taps_per_cta, t1 = min(t0 + taps_per_cta, ntap);
     const int64_t row0 = (int64_t)blockIdx.x * 128;
 
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < NST; ++i) {
             umma::mbar_init(&bars.a_full[i], 128);
             umma::mbar_init(&bars.w_full[i], 1);
             umma::mbar_init(&bars.empty[i], 1);
@@ -1044,24 +1058,44 @@ __global__ void __launch_bounds__(192) sr_conv_tc_kernel(const bf16* __restrict_
     const uint32_t tmem = bars.tmem_slot;
 
     if (warp < 4) {
-        for (int t = t0; t < t1; ++t) {
-            const int n = t - t0, st = n & 1;
-            if (n >= 2) umma::mbar_wait(&bars.empty[st], ((n >> 1) - 1) & 1);
-            const int dy = t / ws, dx = t % ws;
-            uint8_t* a = a_st + (size_t)st * KG * P::LBO;
-            for (int i = tid; i < 128 * KG; i += 128) {
-                const int r = i / KG, kg = i % KG;
-                const int64_t row = row0 + r;
-                uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                if (row < rows) {
-                    const int b = (int)(row / Ns), sidx = (int)(row % Ns);
-                    const int y = (sidx / nsx) * ws + dy, x = (sidx % nsx) * ws + dx;
-                    v = *reinterpret_cast<const uint4*>(feat + (((int64_t)b * H + y) * W + x) * C + kg * 8);
-                }
-                *reinterpret_cast<uint4*>(a + (size_t)kg * P::LBO + r * 16) = v;
+        // chunk k of this thread: (row r_k, channel group kg_k) with r_k * KG + kg_k = tid + 128 k; source element offset of
+        // the row's window origin (tap (0,0)) or -1 for rows past the end (zero-filled)
+        int64_t base[KG];
+        uint32_t dst[KG];
+#pragma unroll
+        for (int k = 0; k < KG; ++k) {
+            const int i = tid + 128 * k, r = i / KG, kg = i % KG;
+            const int64_t row = row0 + r;
+            base[k] = -1;
+            if (row < rows) {
+                const uint32_t b = (uint32_t)row / (uint32_t)Ns, sidx = (uint32_t)row - b * (uint32_t)Ns;
+                const int y = (int)(sidx / (uint32_t)nsx) * ws, x = (int)(sidx % (uint32_t)nsx) * ws;
+                base[k] = (((int64_t)b * H + y) * W + x) * C + kg * 8;
             }
+            dst[k] = (uint32_t)(kg * P::LBO + r * 16);
+        }
+        const uint32_t a_base = umma::smem_u32(a_st);
+        auto issue = [&](int t) {                        // copies of tap t into stage (t - t0) % NST
+            const int n = t - t0, st = n % NST;
+            if (n >= NST) umma::mbar_wait(&bars.empty[st], ((n / NST) - 1) & 1);
+            const int64_t toff = ((int64_t)(t / ws) * W + (t % ws)) * C;
+#pragma unroll
+            for (int k = 0; k < KG; ++k) {
+                const bf16* g = base[k] >= 0 ? feat + base[k] + toff : feat;
+                const uint32_t nbytes = base[k] >= 0 ? 16u : 0u;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(a_base + st * (uint32_t)(KG * P::LBO) + dst[k]), "l"(g), "r"(nbytes) : "memory");
+            }
+        };
+        for (int t = t0; t < t0 + NST - 1; ++t) {        // prologue: NST - 1 taps in flight
+            if (t < t1) issue(t);
+            asm volatile("cp.async.commit_group;\n" ::: "memory");
+        }
+        for (int t = t0; t < t1; ++t) {
+            if (t + NST - 1 < t1) issue(t + NST - 1);
+            asm volatile("cp.async.commit_group;\n" ::: "memory");
+            asm volatile("cp.async.wait_group %0;\n" ::"n"(NST - 1) : "memory");    // tap t has landed
             umma::fence_async_smem();
-            mbar_arrive(&bars.a_full[st]);
+            mbar_arrive(&bars.a_full[(t - t0) % NST]);
         }
         umma::mbar_wait(&bars.acc_ready, 0);
         umma::fence_after_sync();
@@ -1078,8 +1112,8 @@ __global__ void __launch_bounds__(192) sr_conv_tc_kernel(const bf16* __restrict_
         umma::fence_before_sync();
     } else if (warp == 4) {
         for (int t = t0; t < t1; ++t) {
-            const int n = t - t0, st = n & 1;
-            if (n >= 2) umma::mbar_wait(&bars.empty[st], ((n >> 1) - 1) & 1);
+            const int n = t - t0, st = n % NST;
+            if (n >= NST) umma::mbar_wait(&bars.empty[st], ((n / NST) - 1) & 1);
             umma::bulk_load(w_st + (size_t)st * P::SLOT, sr_tc + (size_t)t * C * C, P::SLOT, &bars.w_full[st]);
         }
     } else {
@@ -1087,9 +1121,9 @@ __global__ void __launch_bounds__(192) sr_conv_tc_kernel(const bf16* __restrict_
             const uint32_t idesc = umma::idesc_bf16(128, C);
             constexpr uint32_t LBO_B = C * 16;
             for (int t = t0; t < t1; ++t) {
-                const int n = t - t0, st = n & 1;
-                umma::mbar_wait(&bars.a_full[st], (n >> 1) & 1);
-                umma::mbar_wait(&bars.w_full[st], (n >> 1) & 1);
+                const int n = t - t0, st = n % NST;
+                umma::mbar_wait(&bars.a_full[st], (n / NST) & 1);
+                umma::mbar_wait(&bars.w_full[st], (n / NST) & 1);
                 umma::fence_after_sync();
                 const uint32_t ab = umma::smem_u32(a_st) + st * KG * P::LBO, wb = umma::smem_u32(w_st) + st * P::SLOT;
 #pragma unroll
@@ -1143,7 +1177,8 @@ static int run_sr_conv_tc(const void* feat0, float* sr_tok, int B, int H, int W,
     if (splits > ntap) splits = ntap;
     const int taps_per_cta = (ntap + splits - 1) / splits;
     splits = (ntap + taps_per_cta - 1) / taps_per_cta;
-    constexpr size_t smem = 2 * (size_t)P::KG * P::LBO + 2 * (size_t)P::SLOT;
+    constexpr size_t smem = SrTC<C>::NST * ((size_t)P::KG * P::LBO + (size_t)P::SLOT);
+    CFP_REQUIRE(rows < ((int64_t)1 << 31), "sr conv: %lld rows exceed the 32-bit row index", (long long)rows);
     auto k = sr_conv_tc_kernel<C>;
     if (int err = set_smem(k, smem)) return err;
     k<<<dim3(tiles, splits), 192, smem, st>>>((const bf16*)feat0, sr_tok, rows, H, W, ws, nsx, Ns, (const bf16*)sr_tc,
