@@ -211,11 +211,12 @@ CFP_API int cfp_lkpm_fwd(void* feat0, int B, int H, int W, int C, const cfp_lkpm
     if (dtype == CFP_BF16) {
         if (w->ksize >= 15) {      // Toeplitz GEMM on the tensor pipe (k_dwconv_tc.cu); its planar output feeds the MLP directly
             const void* planar = nullptr;
-            if (int e = dwconv_tc(feat0, &planar, B, H, W, C, w->ksize, w->dw_toep, w->dw_shift, ws + L.planes, st)) return e;
-            return lkpm_mlp_tc(feat0, planar, (int64_t)B * H * W, H * W, C, *w, st);
+            int pitch = 0;
+            if (int e = dwconv_tc(feat0, &planar, &pitch, B, H, W, C, w->ksize, w->dw_toep, w->dw_shift, ws + L.planes, st)) return e;
+            return lkpm_mlp_tc(feat0, planar, (int64_t)B * H * W, H * W, W, pitch, C, *w, st);
         }
         if (int e = dwconv_bn_relu(feat0, y, B, H, W, C, w->ksize, w->dw_t, w->dw_shift, dtype, st)) return e;
-        return lkpm_mlp_tc(feat0, y, (int64_t)B * H * W, 0, C, *w, st);
+        return lkpm_mlp_tc(feat0, y, (int64_t)B * H * W, 0, 0, 0, C, *w, st);
     }
     if (int e = dwconv_bn_relu(feat0, y, B, H, W, C, w->ksize, w->dw_t, w->dw_shift, dtype, st)) return e;
     return lkpm_mlp(feat0, y, (int64_t)B * H * W, C, *w, dtype, st);

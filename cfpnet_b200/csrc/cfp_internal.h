@@ -61,14 +61,16 @@ int conv3x3_tc(const void* in0, const void* in1, const void* wpk, const float* s
                int B, int H, int W, int C, int zy0, int zy1, int zx0, int zx1, cudaStream_t st);
 
 // k_chain_tc.cu  (bf16, tcgen05)
-// y: dwconv output, token-major [rows][C] when planar_n == 0, else planar [rows / planar_n][C][planar_n]
-int lkpm_mlp_tc(void* feat0, const void* y, int64_t rows, int planar_n, int C, const cfp_lkpm_w& w, cudaStream_t st);
+// y: dwconv output, token-major [rows][C] when planar_w == 0, else planar [frames][C][H][planar_pitch] of frames with
+// planar_n = H * planar_w tokens
+int lkpm_mlp_tc(void* feat0, const void* y, int64_t rows, int planar_n, int planar_w, int planar_pitch, int C, const cfp_lkpm_w& w,
+                cudaStream_t st);
 int sr_conv_ln_tc(const void* feat0, float* sr_tok, int B, int H, int W, int C, int ws, const void* sr_tc,
                   const float* sr_b, const float* g, const float* b, cudaStream_t st);
 
 // k_dwconv_tc.cu  (bf16, tcgen05)
 size_t dwconv_tc_plane_bytes(int B, int H, int W, int C, int K);
-int dwconv_tc(const void* in, const void** planar_out, int B, int H, int W, int C, int K, const void* toep, const float* shift,
+int dwconv_tc(const void* in, const void** planar_out, int* planar_pitch, int B, int H, int W, int C, int K, const void* toep, const float* shift,
               char* plane_ws, cudaStream_t st);
 
 // k_selftest.cu

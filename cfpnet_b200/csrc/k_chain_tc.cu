@@ -548,7 +548,7 @@ template <int C> struct MlpTC {
 
 template <int C>
 __global__ void __launch_bounds__(192) lkpm_mlp_tc_kernel(bf16* __restrict__ feat0, const bf16* __restrict__ y,
-                                                          int64_t rows, int planar_n, cfp_lkpm_w w, int ntiles) {
+                                                          int64_t rows, int planar_n, int planar_w, int planar_pitch, cfp_lkpm_w w, int ntiles) {
     using P = ChainTC<C>;
     using M = MlpTC<C>;
     constexpr int KG = P::KG;
@@ -586,13 +586,15 @@ __global__ void __launch_bounds__(192) lkpm_mlp_tc_kernel(bf16* __restrict__ fea
             {   // channels-last LayerNorm (eps 1e-6) of row `tid` -> a0
                 float v[C];
                 if (planar_n > 0) {
-                    // planar dwconv output [frame][C][planar_n]: lanes are consecutive tokens, so each of the C
-                    // two-byte loads of a warp is one contiguous 64-byte segment
-                    const uint32_t fr = (uint32_t)row / (uint32_t)planar_n;      // rows < 2^31: 32-bit divide
-                    const uint16_t* p = reinterpret_cast<const uint16_t*>(y) + (size_t)fr * C * planar_n + ((uint32_t)row - fr * (uint32_t)planar_n);
+                    // planar dwconv output [frame][C][H][pitch]: lanes are consecutive tokens, so each of the C two-byte
+                    // loads of a warp is (mostly) one contiguous 64-byte segment
+                    const uint32_t fr = (uint32_t)row / (uint32_t)planar_n, n = (uint32_t)row - fr * (uint32_t)planar_n;   // rows < 2^31
+                    const uint32_t yy = n / (uint32_t)planar_w, xx = n - yy * (uint32_t)planar_w;
+                    const size_t cstride = (size_t)(planar_n / planar_w) * planar_pitch;
+                    const uint16_t* p = reinterpret_cast<const uint16_t*>(y) + (size_t)fr * C * cstride + (size_t)yy * planar_pitch + xx;
 #pragma unroll
                     for (int c = 0; c < C; ++c)
-                        v[c] = row < rows ? __uint_as_float((uint32_t)__ldg(p + (size_t)c * planar_n) << 16) : 0.f;
+                        v[c] = row < rows ? __uint_as_float((uint32_t)__ldg(p + (size_t)c * cstride) << 16) : 0.f;
                 } else {
 #pragma unroll
                     for (int j = 0; j < C; j += 8) {
@@ -727,7 +729,9 @@ __global__ void __launch_bounds__(192) lkpm_mlp_tc_kernel(bf16* __restrict__ fea
 }
 
 template <int C>
-static int run_lkpm_mlp_tc(void* feat0, const void* y, int64_t rows, int planar_n, const cfp_lkpm_w& w, cudaStream_t st) {
+static int run_lkpm_mlp_tc(void* feat0, const void* y, int64_t rows, int planar_n, int planar_w, int planar_pitch, const cfp_lkpm_w& w,
+                           cudaStream_t st) {
+    CFP_REQUIRE(rows < ((int64_t)1 << 31), "lkpm_mlp: %lld rows exceed the 32-bit row index", (long long)rows);
     using M = MlpTC<C>;
     CFP_REQUIRE(w.tc != nullptr, "lkpm_mlp: bf16 path needs the packed tensor-core weights (cfp_lkpm_w.tc)");
     auto k = lkpm_mlp_tc_kernel<C>;
@@ -735,14 +739,15 @@ static int run_lkpm_mlp_tc(void* feat0, const void* y, int64_t rows, int planar_
     const int64_t ntiles = (rows + 127) / 128;
     const int per_sm = C >= 128 ? 1 : (C == 64 ? 2 : 3);
     const int grid = (int)(ntiles < 148 * per_sm ? ntiles : 148 * per_sm);
-    k<<<grid, 192, M::SMEM, st>>>((bf16*)feat0, (const bf16*)y, rows, planar_n, w, (int)ntiles);
+    k<<<grid, 192, M::SMEM, st>>>((bf16*)feat0, (const bf16*)y, rows, planar_n, planar_w, planar_pitch, w, (int)ntiles);
     return check_launch(C == 32 ? "lkpm_mlp_tc<32>" : C == 64 ? "lkpm_mlp_tc<64>" : "lkpm_mlp_tc<128>");
 }
 
-int lkpm_mlp_tc(void* feat0, const void* y, int64_t rows, int planar_n, int C, const cfp_lkpm_w& w, cudaStream_t st) {
-    if (C == 32) return run_lkpm_mlp_tc<32>(feat0, y, rows, planar_n, w, st);
-    if (C == 64) return run_lkpm_mlp_tc<64>(feat0, y, rows, planar_n, w, st);
-    if (C == 128) return run_lkpm_mlp_tc<128>(feat0, y, rows, planar_n, w, st);
+int lkpm_mlp_tc(void* feat0, const void* y, int64_t rows, int planar_n, int planar_w, int planar_pitch, int C, const cfp_lkpm_w& w,
+                cudaStream_t st) {
+    if (C == 32) return run_lkpm_mlp_tc<32>(feat0, y, rows, planar_n, planar_w, planar_pitch, w, st);
+    if (C == 64) return run_lkpm_mlp_tc<64>(feat0, y, rows, planar_n, planar_w, planar_pitch, w, st);
+    if (C == 128) return run_lkpm_mlp_tc<128>(feat0, y, rows, planar_n, planar_w, planar_pitch, w, st);
     return fail("unsupported C=%d", C);
 }
 

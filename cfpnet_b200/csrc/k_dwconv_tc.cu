@@ -57,6 +57,7 @@ struct DwGeom {
     int NA;        // groups of kDwNB vertical taps = ceil(K / kDwNB)
     int nX;        // 32-column output tiles
     int WG;        // 8-column groups per plane = 4*nX + 2*KS - 4
+    int WO;        // row pitch of the planar output = W rounded up to 8 (every row and every 8-column chunk 16-byte aligned)
 };
 static DwGeom dw_geom(int B, int H, int W, int C, int K) {
     DwGeom g;
@@ -76,12 +77,13 @@ static DwGeom dw_geom(int B, int H, int W, int C, int K) {
     if (g.HP < g.F * g.RS + g.PAD) g.HP = g.F * g.RS + g.PAD;
     g.nX = (W + 31) / 32;
     g.WG = 4 * g.nX + 2 * g.KS - 4;
+    g.WO = (W + 7) & ~7;
     return g;
 }
 size_t dwconv_tc_plane_bytes(int B, int H, int W, int C, int K) {
     DwGeom g = dw_geom(B, H, W, C, K);
     const size_t in_bytes = (size_t)g.NB * C * g.WG * g.HP * 16;
-    const size_t out_bytes = (size_t)B * C * H * W * 2;
+    const size_t out_bytes = (size_t)B * C * H * g.WO * 2;
     return ((in_bytes + 255) & ~(size_t)255) + ((out_bytes + 255) & ~(size_t)255);
 }
 
@@ -302,21 +304,16 @@ __global__ void __launch_bounds__(kDwThreads) dwconv_tc_kernel(const bf16* __res
             const int m = it.mt * kDwMS + row, x0 = it.xt * 32 + part * NC;
             const int f = m / g.RS, y = m - f * g.RS, frame = it.b * g.F + f;      // stacked frame and its row
             if (row < kDwMS && f < g.F && y < g.H && frame < B) {
-                bf16* dst = planar_out + (((size_t)frame * g.C + it.c) * g.H + y) * g.W + x0;
-                const bool aligned = (((size_t)(dst - planar_out)) & 7) == 0;
+                bf16* dst = planar_out + (((size_t)frame * g.C + it.c) * g.H + y) * g.WO + x0;
 #pragma unroll
                 for (int j = 0; j < NC; j += 8) {
-                    if (x0 + j + 8 <= g.W && aligned) {
+                    if (x0 + j < g.WO) {                       // WO % 8 == 0: a chunk is inside the (padded) row or not at all
                         uint4 u;
                         u.x = umma::pack_bf16(fmaxf(acc[j + 0] + sh, 0.f), fmaxf(acc[j + 1] + sh, 0.f));
                         u.y = umma::pack_bf16(fmaxf(acc[j + 2] + sh, 0.f), fmaxf(acc[j + 3] + sh, 0.f));
                         u.z = umma::pack_bf16(fmaxf(acc[j + 4] + sh, 0.f), fmaxf(acc[j + 5] + sh, 0.f));
                         u.w = umma::pack_bf16(fmaxf(acc[j + 6] + sh, 0.f), fmaxf(acc[j + 7] + sh, 0.f));
                         *reinterpret_cast<uint4*>(dst + j) = u;
-                    } else {
-#pragma unroll
-                        for (int qq = 0; qq < 8; ++qq)
-                            if (x0 + j + qq < g.W) dst[j + qq] = __float2bfloat16_rn(fmaxf(acc[j + qq] + sh, 0.f));
                     }
                 }
             }
@@ -391,7 +388,7 @@ __global__ void __launch_bounds__(kDwThreads) dwconv_tc_kernel(const bf16* __res
     }
 }
 
-int dwconv_tc(const void* in, const void** planar_out_p, int B, int H, int W, int C, int K, const void* toep, const float* shift,
+int dwconv_tc(const void* in, const void** planar_out_p, int* planar_pitch, int B, int H, int W, int C, int K, const void* toep, const float* shift,
               char* plane_ws, cudaStream_t st) {
     CFP_REQUIRE(toep != nullptr, "dwconv: bf16 path needs the packed Toeplitz blocks (cfp_lkpm_w.dw_toep)");
     CFP_REQUIRE(B <= 65535 && C <= 65535, "grid limits");
@@ -399,7 +396,8 @@ int dwconv_tc(const void* in, const void** planar_out_p, int B, int H, int W, in
     const size_t in_bytes = ((size_t)g.NB * C * g.WG * g.HP * 16 + 255) & ~(size_t)255;
     bf16* planes = reinterpret_cast<bf16*>(plane_ws);
     bf16* planar_out = reinterpret_cast<bf16*>(plane_ws + in_bytes);
-    *planar_out_p = planar_out;          // [B][C][H][W]; lkpm_mlp_tc reads it in place (no transpose back)
+    *planar_out_p = planar_out;          // [B][C][H][WO]; lkpm_mlp_tc reads it in place (no transpose back)
+    *planar_pitch = g.WO;
     {
         const size_t smem = (size_t)8 * W * (C / 2 + 1) * 4;
         CFP_REQUIRE(smem <= 200 * 1024, "dw_plane_pack: %zu B shared memory", smem);

@@ -29,9 +29,10 @@ x = torch.randn(B, H * W, C, device="cuda").bfloat16()
 x0 = x.clone()
 _lib.call("cfp_lkpm_fwd", x.data_ptr(), B, H, W, C, ctypes.byref(packed[1][1]), work.data_ptr(), nbytes, code, _lib.stream_ptr())
 torch.cuda.synchronize()
-out_bytes = (B * C * H * W * 2 + 255) // 256 * 256
+WO = (W + 7) // 8 * 8                      # row pitch of the planar output
+out_bytes = (B * C * H * WO * 2 + 255) // 256 * 256
 end = lib.cfp_workspace_bytes(B, H, W, C, 0, m.large_kernel, code, None)     # cfp_lkpm_fwd's own layout (no zones, no sr)
-y = work[end - out_bytes: end - out_bytes + B * C * H * W * 2].view(torch.bfloat16).view(B, C, H, W).float().cpu()
+y = work[end - out_bytes: end - out_bytes + B * C * H * WO * 2].view(torch.bfloat16).view(B, C, H, WO)[..., :W].float().cpu()
 blk = m.layers[1].large_kernel_path
 scale, shift = fold_bn(blk.bn1)
 taps = (blk.dwconv2.weight.detach().float()[:, 0] * scale[:, None, None]).to(torch.bfloat16).float().cpu()
