@@ -206,6 +206,9 @@ struct ChainStages {
                 else unpack8(*reinterpret_cast<const uint4*>(a0 + (size_t)(j / 8) * P::LBO + tid * 16), x8);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) o8[i] = x8[i] + v[j + i];
+                if constexpr (HasPutSum<Q>::value && sizeof(typename Q::R) > 0) {
+                    if (q.sums_in_place()) { q.put8_sum(r.ref, j, o8, x8); continue; }
+                }
                 store8(q, r.ref, j, o8);
             }
         }

@@ -21,6 +21,15 @@ namespace cfp {
 
 template <int C> struct Tile { static constexpr int BM = C >= 128 ? 32 : 64; };
 
+__device__ __forceinline__ uint4 pack8_bf16_fwd(const float (&v)[8]) {
+    __nv_bfloat162 t0 = __floats2bfloat162_rn(v[0], v[1]), t1 = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 t2 = __floats2bfloat162_rn(v[4], v[5]), t3 = __floats2bfloat162_rn(v[6], v[7]);
+    uint4 u;
+    u.x = *reinterpret_cast<uint32_t*>(&t0); u.y = *reinterpret_cast<uint32_t*>(&t1);
+    u.z = *reinterpret_cast<uint32_t*>(&t2); u.w = *reinterpret_cast<uint32_t*>(&t3);
+    return u;
+}
+
 struct FastDiv {               // exact n / d for 0 <= n < 2^32, 1 <= d < 2^32
     uint64_t m;
     uint32_t d;
@@ -218,6 +227,18 @@ struct ZonePatchRows {         // hist2image queries: cells of the zone canvas, 
                            w00 * a.z + w01 * bq.z + w10 * cq.z + w11 * d.z,
                            w00 * a.w + w01 * bq.w + w10 * cq.w + w11 * d.w);
     }
+    // feat0[zone] += out with out = x + msg: when the canvas is cut from feat0 itself (change_embedding, fusion.py:134),
+    // no resize and no --no_skip_inside, the cell's current value IS the x the row was staged from, so the sum is
+    // 2x + msg from registers: one 16-byte store instead of a read-modify-write whose load latency ends every tile.
+    __device__ bool sums_in_place() const { return !interpolate && !assign && emb == feat0; }
+    __device__ void put8_sum(const R& q, int c, const float (&o8)[8], const float (&x8)[8]) const {
+        const int y = sy_wo + q.cy, x = sx_wo + q.cx;
+        if (!q.valid || y < 0 || y >= H || x < 0 || x >= W) return;      // hist_mask / pad_mask (fusion.py:144,112-118)
+        float s8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s8[i] = o8[i] + x8[i];
+        *reinterpret_cast<uint4*>(feat0 + ((int64_t)q.b * H * W + (int64_t)y * W + x) * C + c) = pack8_bf16_fwd(s8);
+    }
     __device__ void store4(const R& q, int c, float4 v) const {
         if (!q.valid) v = make_float4(0.f, 0.f, 0.f, 0.f);   // zone_feature[~hist_mask] = 0  (fusion.py:144)
         if (interpolate) {                                // resized back by canvas_resize_add_kernel
@@ -238,6 +259,8 @@ struct ZonePatchRows {         // hist2image queries: cells of the zone canvas, 
 // storage already is bf16 expose raw8()/put8() (one 16-byte access, no conversion round trip).
 template <class P, class = void> struct HasRaw8 { static constexpr bool value = false; };
 template <class P> struct HasRaw8<P, decltype((void)&P::raw8)> { static constexpr bool value = true; };
+template <class P, class = void> struct HasPutSum { static constexpr bool value = false; };
+template <class P> struct HasPutSum<P, decltype((void)&P::put8_sum)> { static constexpr bool value = true; };
 template <class P, class = void> struct HasPut8 { static constexpr bool value = false; };
 template <class P> struct HasPut8<P, decltype((void)&P::put8)> { static constexpr bool value = true; };
 
