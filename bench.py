@@ -400,6 +400,13 @@ LEVEL = {  # C: (N tokens, k, zone patch side p, window ws, inside Ni)
 
 def kernel_work(name, B, es):
     import re
+    # kernels launched once per level under one name: average per launch over the levels that use them
+    if name == "layout_kernel":          # pos-enc + NCHW -> tokens and tokens -> NCHW, each level: read + write the map
+        return dict(flops=0.0, bytes=sum(2.0 * g["N"] * C * es * B for C, g in LEVEL.items()) / 3, bound="hbm")
+    if name == "dw_plane_pack":          # levels with k >= 15: read the token map, write the planes (>= the same size)
+        return dict(flops=0.0, bytes=sum(2.0 * LEVEL[C]["N"] * C * es * B for C in (32, 64)) / 2, bound="hbm")
+    if name.startswith("hist_encoder"):  # 1024 samples per frame: 4 B in, (32+64+128) elements out; 109 MFLOP per frame
+        return dict(flops=109e6 * B, bytes=1024.0 * B * (4 + 224 * es), bound="tensor" if name.endswith("_tc") else "fma")
     m = re.search(r"(\d+)>$", name)
     if not m:
         return None
@@ -437,37 +444,54 @@ def kernel_work(name, B, es):
     return None
 
 
-# dram bytes per launch of the top kernels from the committed `ncu --set full` captures (profiles/*.txt)
-NCU_TRAFFIC = {}
+# dram bytes (read + write) per launch from the committed ncu capture of this workload (tools/ncu_traffic.py ->
+# profiles/ncu_traffic.json: {bench kernel name: bytes per launch}); null when the kernel was not captured
+def load_ncu_traffic():
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+            return {k: float(v) for k, v in json.load(fh).get("bytes_per_launch", {}).items()}
+    except Exception:
+        return {}
+
+
+def roofline_of(name, avg_s, B, es, peaks):
+    """Roofline of one kernel: the bound is whichever of (algorithmic bytes / HBM peak) and (useful flops / tensor
+    peak) takes longer; `achieved` is the algorithmic quantity of that bound / measured launch time."""
+    w = kernel_work(name, B, es)
+    if not w:
+        return dict(bound="hbm", achieved=None, peak=peaks["hbm_gbs"], unit="GB/s", frac=None)
+    t_hbm = w["bytes"] / (peaks["hbm_gbs"] * 1e9)
+    t_tc = w["flops"] / (peaks["bf16_tflops_sustained"] * 1e12) if w["bound"] == "tensor" else 0.0
+    gbps, tflops = w["bytes"] / avg_s / 1e9, w["flops"] / avg_s / 1e12
+    if t_tc >= t_hbm:
+        return dict(bound="tensor", achieved=tflops, peak=peaks["bf16_tflops_sustained"], unit="TFLOP/s",
+                    frac=tflops / peaks["bf16_tflops_sustained"],
+                    note="useful flops of the op (no padding / Toeplitz zeros) / CUDA-event time; peak = sustained cuBLAS bf16",
+                    other={"hbm_GBps": gbps, "hbm_frac": gbps / peaks["hbm_gbs"]})
+    return dict(bound="hbm", achieved=gbps, peak=peaks["hbm_gbs"], unit="GB/s", frac=gbps / peaks["hbm_gbs"],
+                note="algorithmic bytes (activations read + written once) / CUDA-event time; peak = measured copy bandwidth",
+                other={"TFLOPs": tflops, "tensor_frac": tflops / peaks["bf16_tflops_sustained"]} if w["bound"] == "tensor" else
+                      {"fp32_TFLOPs": tflops})
 
 
 def roofline_from_profile(prof, steps, B, es, peaks):
     total_ms = sum(v[1] for v in prof.values())
+    traffic = load_ncu_traffic()
     kernels = {}
     for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1]):
         rec = {"launches_per_step": v[0] / steps, "ms_per_step": v[1] / steps, "share": v[1] / total_ms if total_ms else None}
         w = kernel_work(k, B, es)
         if w:
             avg_s = v[1] / v[0] * 1e-3
+            r = roofline_of(k, avg_s, B, es, peaks)
             rec["TFLOPs"] = w["flops"] / avg_s / 1e12
             rec["GBps"] = w["bytes"] / avg_s / 1e9
+            rec["bound"], rec["roofline_frac"] = r["bound"], r["frac"]
         kernels[k] = rec
     name, (count, ms) = max(prof.items(), key=lambda kv: kv[1][1])
     avg_s = ms / count * 1e-3
-    w = kernel_work(name, B, es)
-    roof = {"kernel": name, "avg_launch_ms": avg_s * 1e3, "peak_source": peaks["source"], "traffic": NCU_TRAFFIC.get(name)}
-    if w and w["bound"] == "tensor":
-        ach = w["flops"] / avg_s / 1e12
-        roof.update(bound="tensor", achieved=ach, peak=peaks["bf16_tflops_sustained"], unit="TFLOP/s",
-                    frac=ach / peaks["bf16_tflops_sustained"],
-                    note="algorithmic (useful) flops of the op / CUDA-event time; peak = sustained cuBLAS bf16 (kernel timed inside a long step)",
-                    hbm={"achieved_GBps": w["bytes"] / avg_s / 1e9, "peak_GBps": peaks["hbm_gbs"],
-                         "frac": w["bytes"] / avg_s / 1e9 / peaks["hbm_gbs"]})
-    elif w:
-        ach = w["bytes"] / avg_s / 1e9
-        roof.update(bound="hbm", achieved=ach, peak=peaks["hbm_gbs"], unit="GB/s", frac=ach / peaks["hbm_gbs"])
-    else:
-        roof.update(bound="hbm", achieved=None, peak=peaks["hbm_gbs"], unit="GB/s", frac=None)
+    roof = {"kernel": name, "avg_launch_ms": avg_s * 1e3, "peak_source": peaks["source"], "traffic": traffic.get(name)}
+    roof.update(roofline_of(name, avg_s, B, es, peaks))
     return roof, kernels
 
 

@@ -24,7 +24,7 @@ def module_for(level):
     return m.to(DEV).eval(), sd
 
 
-def layer_call(m, name, layer_idx, feat0, geom_name="G416", level=3, mask=None, feat1=None):
+def layer_call(m, name, layer_idx, feat0, geom_name="G416", level=3, mask=None, feat1=None, poison=False):
     """Run ONE layer entry point in place on a copy of feat0 [B,N,C]; returns the result."""
     C = m.embedding_dim
     H, W = synth.level_hw(geom_name, level)
@@ -37,6 +37,8 @@ def layer_call(m, name, layer_idx, feat0, geom_name="G416", level=3, mask=None, 
     lib = _lib.load()
     nbytes = lib.cfp_workspace_bytes(B, H, W, C, m.ws, m.large_kernel, code, ctypes.byref(cg))
     work = torch.empty(nbytes, device=DEV, dtype=torch.uint8)
+    if poison:
+        work.fill_(0xFF)
     x = feat0.clone()
     st = _lib.stream_ptr()
     w = packed[layer_idx]
@@ -83,6 +85,23 @@ def test_bf16_layer_matches_fp32_layer(level, name, idx):
     fast, _ = layer_call(m.to(torch.bfloat16), name, idx, bf, level=level, **kw)
     err = rel_l2(fast, exact)
     assert err <= 1.5e-2, f"{name} L{level}: bf16 vs fp32 rel-L2 {err:.3e}"
+
+
+@pytest.mark.parametrize("geom,level,B", [("G480", 1, 1), ("G480", 2, 3), ("G480", 3, 2), ("G416", 2, 5), ("G416", 1, 2)])
+def test_lkpm_bf16_other_shapes(geom, level, B):
+    """LKPM on the tensor-core depthwise path at the shapes the golden cases do not reach: a map that fills the
+    120-row M block exactly (480x640 at 1/4), two frames stacked in one plane with an odd batch, row pitches that are
+    not a multiple of 8; the workspace is pre-filled with NaN bit patterns (stale bytes must not enter an MMA)."""
+    m, sd = module_for(level)
+    C = m.embedding_dim
+    H, W = synth.level_hw(geom, level)
+    f32 = torch.randn(B, H * W, C, generator=torch.Generator().manual_seed(7 * level + B)).to(DEV)
+    bf = f32.to(torch.bfloat16)
+    exact, _ = layer_call(m, "lkpm", 1, bf.float(), geom_name=geom, level=level)
+    fast, _ = layer_call(m.to(torch.bfloat16), "lkpm", 1, bf, geom_name=geom, level=level, poison=True)
+    err = rel_l2(fast, exact)
+    assert torch.isfinite(fast.float()).all()
+    assert err <= 1.5e-2, f"lkpm {geom} L{level} B={B}: bf16 vs fp32 rel-L2 {err:.3e}"
 
 
 @pytest.mark.parametrize("level", [3, 2, 1])
