@@ -541,13 +541,34 @@ __device__ __forceinline__ uint32_t gelu_tanh_bf16x2(float x0, float x1) {
 template <int C> struct MlpTC {
     static constexpr int NS = 128;                       // hidden slice width
     static constexpr int NSL = 4 * C / NS;               // slices: 1, 2, 4
-    static constexpr int BLK = 256 * C;                  // bytes of one weight block
+    // Both GEMMs carry their bias inside the contraction: the A operands have one extra 16-column K step whose first
+    // column is 1 (written once per CTA), the weight blocks one extra K step whose first column is the bias.  The
+    // LayerNorm affine is folded into W1 / b1 by the host.  So the epilogues are pure: normalise | GELU | + residual.
+    static constexpr int K1 = C + 16;                    // GEMM1: [128 x K1] x W1_j^T (N = 128), bf16
+    static constexpr int K2 = NS + 16;                   // GEMM2: [128 x K2] x W2_j^T (N = C), fp16
+    static constexpr int BLK1 = NS * K1 * 2, BLK2 = C * K2 * 2;
+    static constexpr int BLK = BLK1 > BLK2 ? BLK1 : BLK2;   // ring slot / packed block stride (bytes)
     static constexpr int NBLK = 2 * NSL;                 // blocks per tile
     static constexpr int NSLOT = C >= 128 ? 2 : (C == 64 ? 4 : 2);
     static constexpr int OUT_COL = NSL == 1 ? 0 : NS;    // out accumulator columns
     static constexpr int TMEM_COLS = NSL == 1 ? 128 : 256;
-    static constexpr size_t SMEM = (size_t)(C / 8 + 16) * ChainTC<C>::LBO + (size_t)NSLOT * BLK;
+    static constexpr int G0 = K1 / 8, G1 = K2 / 8;       // 16-byte k-groups of the two A buffers
+    static constexpr size_t SMEM = (size_t)(G0 + G1) * ChainTC<C>::LBO + (size_t)NSLOT * BLK;
 };
+
+// GELU (tanh form) of two fp32 values as packed fp16: the second GEMM consumes fp16 (more mantissa than bf16, and no
+// conversion back through fp32).
+__device__ __forceinline__ uint32_t gelu_tanh_h2(float x0, float x1) {
+    const __half2 h = __floats2half2_rn(x0, x1);
+    const __half2 k0 = __float2half2_rn(0.7978845608f), k1 = __float2half2_rn(0.0356774081f);
+    const __half2 inner = __hmul2(h, __hfma2(__hmul2(h, h), k1, k0));
+    uint32_t ti = *reinterpret_cast<const uint32_t*>(&inner), to;
+    asm("tanh.approx.f16x2 %0, %1;\n" : "=r"(to) : "r"(ti));
+    const __half2 t = *reinterpret_cast<const __half2*>(&to);
+    const __half2 hh = __hmul2(h, __float2half2_rn(0.5f));
+    const __half2 r = __hfma2(hh, t, hh);
+    return *reinterpret_cast<const uint32_t*>(&r);
+}
 
 template <int C>
 __global__ void __launch_bounds__(192) lkpm_mlp_tc_kernel(bf16* __restrict__ feat0, const bf16* __restrict__ y,
@@ -557,9 +578,9 @@ __global__ void __launch_bounds__(192) lkpm_mlp_tc_kernel(bf16* __restrict__ fea
     constexpr int KG = P::KG;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ ChainBars bars;
-    uint8_t* a0 = smem;                          // LN(y)        [KG][129][16 B]
-    uint8_t* a1 = a0 + KG * P::LBO;              // GELU(h_j)    [16][129][16 B]
-    uint8_t* ring = a1 + 16 * P::LBO;
+    uint8_t* a0 = smem;                          // [LNhat(y) | 1 0..0]   [G0][129][16 B]  bf16
+    uint8_t* a1 = a0 + M::G0 * P::LBO;           // [GELU(h_j) | 1 0..0]  [G1][129][16 B]  fp16
+    uint8_t* ring = a1 + M::G1 * P::LBO;
     const int tid = threadIdx.x, warp = umma::warp_idx_sync();
 
     if (tid == 0) {
@@ -569,6 +590,13 @@ __global__ void __launch_bounds__(192) lkpm_mlp_tc_kernel(bf16* __restrict__ fea
         umma::fence_mbar_init();
     }
     if (warp == 4) umma::tmem_alloc(&bars.tmem_slot, M::TMEM_COLS);
+    if (warp < 4) {                              // the constant bias columns of the two A operands (row `tid`)
+        *reinterpret_cast<uint4*>(a0 + (size_t)KG * P::LBO + tid * 16) = make_uint4(0x3F80u, 0u, 0u, 0u);        // bf16 1.0
+        *reinterpret_cast<uint4*>(a0 + (size_t)(KG + 1) * P::LBO + tid * 16) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(a1 + (size_t)(M::NS / 8) * P::LBO + tid * 16) = make_uint4(0x3C00u, 0u, 0u, 0u);  // fp16 1.0
+        *reinterpret_cast<uint4*>(a1 + (size_t)(M::NS / 8 + 1) * P::LBO + tid * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    umma::fence_async_smem();
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
@@ -618,13 +646,9 @@ __global__ void __launch_bounds__(192) lkpm_mlp_tc_kernel(bf16* __restrict__ fea
                 for (int i = 0; i < C; ++i) { v[i] -= mean; q += v[i] * v[i]; }
                 const float rstd = rsqrtf(q * (1.f / C) + kLkpmLnEps);
 #pragma unroll
-                for (int j = 0; j < C; j += 8) {
-                    const float4 g0 = *reinterpret_cast<const float4*>(w.ln_g + j), g1 = *reinterpret_cast<const float4*>(w.ln_g + j + 4);
-                    const float4 b0 = *reinterpret_cast<const float4*>(w.ln_b + j), b1 = *reinterpret_cast<const float4*>(w.ln_b + j + 4);
-                    const float o8[8] = {fmaf(v[j] * rstd, g0.x, b0.x),     fmaf(v[j + 1] * rstd, g0.y, b0.y),
-                                         fmaf(v[j + 2] * rstd, g0.z, b0.z), fmaf(v[j + 3] * rstd, g0.w, b0.w),
-                                         fmaf(v[j + 4] * rstd, g1.x, b1.x), fmaf(v[j + 5] * rstd, g1.y, b1.y),
-                                         fmaf(v[j + 6] * rstd, g1.z, b1.z), fmaf(v[j + 7] * rstd, g1.w, b1.w)};
+                for (int j = 0; j < C; j += 8) {                 // gamma / beta live in W1 / b1 (host fold)
+                    const float o8[8] = {v[j] * rstd,     v[j + 1] * rstd, v[j + 2] * rstd, v[j + 3] * rstd,
+                                         v[j + 4] * rstd, v[j + 5] * rstd, v[j + 6] * rstd, v[j + 7] * rstd};
                     umma::store_chunk(a0, P::LBO, tid, j / 8, o8);
                 }
             }
@@ -638,15 +662,13 @@ __global__ void __launch_bounds__(192) lkpm_mlp_tc_kernel(bf16* __restrict__ fea
                 for (int c0 = 0; c0 < M::NS; c0 += 16) {
                     float t[16];
                     umma::tmem_ld16(umma::tmem_addr(tmem, warp * 32, c0), t);
-                    const float* bias = w.pw1_b + js * M::NS + c0;
 #pragma unroll
                     for (int j = 0; j < 16; j += 8) {
-                        const float4 ba = *reinterpret_cast<const float4*>(bias + j), bb = *reinterpret_cast<const float4*>(bias + j + 4);
                         uint4 u;
-                        u.x = gelu_tanh_bf16x2(t[j + 0] + ba.x, t[j + 1] + ba.y);
-                        u.y = gelu_tanh_bf16x2(t[j + 2] + ba.z, t[j + 3] + ba.w);
-                        u.z = gelu_tanh_bf16x2(t[j + 4] + bb.x, t[j + 5] + bb.y);
-                        u.w = gelu_tanh_bf16x2(t[j + 6] + bb.z, t[j + 7] + bb.w);
+                        u.x = gelu_tanh_h2(t[j + 0], t[j + 1]);
+                        u.y = gelu_tanh_h2(t[j + 2], t[j + 3]);
+                        u.z = gelu_tanh_h2(t[j + 4], t[j + 5]);
+                        u.w = gelu_tanh_h2(t[j + 6], t[j + 7]);
                         *reinterpret_cast<uint4*>(a1 + (size_t)((c0 + j) / 8) * P::LBO + tid * 16) = u;
                     }
                 }
@@ -667,12 +689,11 @@ __global__ void __launch_bounds__(192) lkpm_mlp_tc_kernel(bf16* __restrict__ fea
                         float x8[8];
                         if constexpr (kPrefetchX) unpack8(xres[(c0 + j) / 8], x8);
                         else unpack8(*reinterpret_cast<const uint4*>(p), x8);
-                        const float4 ba = *reinterpret_cast<const float4*>(w.pw2_b + c0 + j), bb = *reinterpret_cast<const float4*>(w.pw2_b + c0 + j + 4);
                         uint4 u;
-                        u.x = umma::pack_bf16(x8[0] + t[j + 0] + ba.x, x8[1] + t[j + 1] + ba.y);
-                        u.y = umma::pack_bf16(x8[2] + t[j + 2] + ba.z, x8[3] + t[j + 3] + ba.w);
-                        u.z = umma::pack_bf16(x8[4] + t[j + 4] + bb.x, x8[5] + t[j + 5] + bb.y);
-                        u.w = umma::pack_bf16(x8[6] + t[j + 6] + bb.z, x8[7] + t[j + 7] + bb.w);
+                        u.x = umma::pack_bf16(x8[0] + t[j + 0], x8[1] + t[j + 1]);
+                        u.y = umma::pack_bf16(x8[2] + t[j + 2], x8[3] + t[j + 3]);
+                        u.z = umma::pack_bf16(x8[4] + t[j + 4], x8[5] + t[j + 5]);
+                        u.w = umma::pack_bf16(x8[6] + t[j + 6], x8[7] + t[j + 7]);
                         *reinterpret_cast<uint4*>(p) = u;
                     }
                 }
@@ -690,11 +711,13 @@ __global__ void __launch_bounds__(192) lkpm_mlp_tc_kernel(bf16* __restrict__ fea
                 umma::bulk_load(ring + (size_t)slot * M::BLK, wsrc + (size_t)c * (M::BLK / 2), M::BLK, &bars.full[slot]);
             }
     } else {
-        const uint32_t idesc1 = umma::idesc_bf16(128, M::NS), idesc2 = umma::idesc_bf16(128, C);
+        // GEMM1: bf16 x bf16; GEMM2: fp16 x fp16 (a_format = b_format = 0 in the instruction descriptor)
+        const uint32_t idesc1 = umma::idesc_bf16(128, M::NS);
+        const uint32_t idesc2 = umma::idesc_bf16(128, C) & ~((7u << 7) | (7u << 10));
         const uint32_t a0s = umma::smem_u32(a0), a1s = umma::smem_u32(a1), rs = umma::smem_u32(ring);
         uint32_t ph = 0;
         int cc = 0;
-        // h (+)= A0[128 x C] * W1_j^T (N = 128)   |   out (+)= A1[128 x 128] * W2_j^T (N = C)
+        // h (+)= A0[128 x K1] * W1_j^T (N = 128)   |   out (+)= A1[128 x K2] * W2_j^T (N = C)
         auto block = [&](bool first_gemm, bool acc_first) {
             const int slot = cc % M::NSLOT, round = cc / M::NSLOT;
             umma::mbar_wait(&bars.full[slot], round & 1);
@@ -702,7 +725,7 @@ __global__ void __launch_bounds__(192) lkpm_mlp_tc_kernel(bf16* __restrict__ fea
             const uint32_t lbo_b = (first_gemm ? M::NS : C) * 16;
             uint64_t ad = umma::smem_desc(first_gemm ? a0s : a1s, P::LBO);
             uint64_t wd = umma::smem_desc(rs + slot * M::BLK, lbo_b);
-            const int nk = (first_gemm ? C : M::NS) / 16;
+            const int nk = (first_gemm ? M::K1 : M::K2) / 16;
             for (int ks = 0; ks < nk; ++ks) {
                 umma::mma_bf16(tmem + (first_gemm ? 0 : M::OUT_COL), ad, wd, first_gemm ? idesc1 : idesc2, acc_first || ks > 0);
                 ad = umma::desc_advance(ad, 2 * P::LBO);

@@ -224,10 +224,25 @@ class Block14(nn.Module):
             pw2_t=linear_t(self.pwconv2.weight),
             pw2_b=self.pwconv2.bias.detach().float().contiguous(),
         )
-        w1, w2 = self.pwconv1.weight, self.pwconv2.weight
+        # tensor-core MLP (csrc/k_chain_tc.cu: MlpTC): per 128-wide hidden slice j two blocks, W1_j then W2_j, each padded
+        # to the ring-slot size.  The LayerNorm affine is folded into W1 / b1, and both biases ride in one extra 16-column
+        # K step (first column = bias) that meets a constant ones-column of the A operand.  W1_j: bf16 [128][C+16];
+        # W2_j: fp16 [C][128+16] (the GELU output feeds the second GEMM as fp16).
+        g_ln, b_ln = self.norm.weight.detach().float(), self.norm.bias.detach().float()
+        w1 = self.pwconv1.weight.detach().float()
+        w2 = self.pwconv2.weight.detach().float()
+        b1 = self.pwconv1.bias.detach().float() + w1 @ b_ln
+        w1 = w1 * g_ln[None, :]
+        b2 = self.pwconv2.bias.detach().float()
+        blk = max(128 * (C + 16) * 2, C * 144 * 2)          # bytes (MlpTC::BLK)
         blocks = []
-        for j in range(4 * C // 128):                      # 128-wide hidden slices (csrc/k_chain_tc.cu: MlpTC)
-            blocks += [umma_block(w1[j * 128:(j + 1) * 128, :]).reshape(-1), umma_block(w2[:, j * 128:(j + 1) * 128]).reshape(-1)]
+        for j in range(4 * C // 128):
+            sl = slice(j * 128, (j + 1) * 128)
+            w1j = torch.cat([w1[sl, :], b1[sl, None], w1.new_zeros(128, 15)], dim=1)
+            w2j = torch.cat([w2[:, sl], (b2 if j == 0 else torch.zeros_like(b2))[:, None], w2.new_zeros(C, 15)], dim=1)
+            for blkw, dt in ((w1j, torch.bfloat16), (w2j, torch.float16)):
+                raw = umma_block(blkw, dt).reshape(-1).view(torch.uint8)
+                blocks.append(torch.cat([raw, raw.new_zeros(blk - raw.numel())]))
         t["tc"] = torch.cat(blocks).contiguous()
         # banded-Toeplitz blocks of the depthwise taps for the tensor-core path (csrc/k_dwconv_tc.cu):
         # T_dy[n][kk] = w[dy][kk - n]; vertical taps grouped as dy = 4 a + b with the four b's side by side along

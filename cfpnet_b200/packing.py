@@ -46,9 +46,9 @@ class PackCache:
         return self._value
 
 
-def umma_block(w: torch.Tensor) -> torch.Tensor:
-    """[N,K] weight -> bf16 block in the canonical K-major no-swizzle UMMA layout
+def umma_block(w: torch.Tensor, dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    """[N,K] weight -> 16-bit block in the canonical K-major no-swizzle UMMA layout
     [K/8][N][8] (csrc/umma.cuh): element (n,k) at ((k//8)*N + n)*8 + k%8."""
     n, k = w.shape
     assert k % 8 == 0
-    return w.detach().to(torch.bfloat16).view(n, k // 8, 8).permute(1, 0, 2).contiguous()
+    return w.detach().to(dtype).contiguous().view(n, k // 8, 8).permute(1, 0, 2).contiguous()

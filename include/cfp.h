@@ -83,10 +83,14 @@ typedef struct cfp_dapm_w {
  *   ln_g/b [C]; pw1_t [C][4C], pw1_b [4C]; pw2_t [4C][C], pw2_b [C]. */
 typedef struct cfp_lkpm_w {
     const float *dw_t, *dw_shift, *ln_g, *ln_b, *pw1_t, *pw1_b, *pw2_t, *pw2_b;
-    /* bf16 tensor-core path: the 4C hidden dim in 128-wide slices j (4C/128 of them); per slice two
-     * bf16 blocks in the canonical K-major UMMA layout, in consumption order W1_0, W2_0, W1_1, ...:
-     * W1_j = pwconv1.weight[128j:128(j+1), :] as [C/8][128][8], W2_j = pwconv2.weight[:, 128j:128(j+1)]
-     * as [16][C][8].  Required for CFP_BF16. */
+    /* bf16 tensor-core path: the 4C hidden dim in 128-wide slices j (4C/128 of them); per slice two 16-bit blocks in
+     * the canonical K-major UMMA layout ([K/8][N][8]), in consumption order W1_0, W2_0, W1_1, ..., each padded to
+     * max(128*(C+16), C*144)*2 bytes:
+     *   W1_j  bf16 [N=128][K=C+16]: (pwconv1.weight * ln_g)[128j:128(j+1), :], then one K step whose first column is
+     *         (pwconv1.bias + pwconv1.weight @ ln_b)[128j:128(j+1)] (LayerNorm affine and bias folded in);
+     *   W2_j  fp16 [N=C][K=128+16]: pwconv2.weight[:, 128j:128(j+1)], then one K step whose first column is
+     *         pwconv2.bias for j = 0 and zero otherwise.
+     * Required for CFP_BF16. */
     const void *tc;
     /* bf16 tensor-core depthwise conv: banded-Toeplitz blocks T_dy[n][kk] = dw_t-tap(dy, kk-n) (0 outside
      * 0 <= kk-n < k), n < 32, kk < 16*KS, KS = ceil((31+k)/16).  Vertical taps are grouped dy = 4a + b
