@@ -86,6 +86,17 @@ def make_inputs(geometry: str, batch: int, seed: int = 1, levels: Sequence[int] 
     return out
 
 
+ENCODER_CHANNELS = (16, 40, 56, 136, 232)          # x_block0..4 at strides 2..32 (decoder.py:100-104)
+
+
+def encoder_features(geometry: str, batch: int, seed: int = 1) -> list:
+    """Synthetic stand-ins for the five image-encoder feature maps the decoder consumes (the timm backbone is
+    third-party and out of scope): ``[B, c, H/s, W/s]`` ~ N(0, 1) for s = 2, 4, 8, 16, 32."""
+    img_h, img_w, _ = GEOMETRIES[geometry]
+    g = _gen(seed, "encoder_features")
+    return [torch.randn(batch, c, img_h // s, img_w // s, generator=g) for c, s in zip(ENCODER_CHANNELS, (2, 4, 8, 16, 32))]
+
+
 def synthetic_state_dict(shapes: Mapping[str, Sequence[int]], seed: int = 0) -> Dict[str, torch.Tensor]:
     """Deterministic weights for any module given its state_dict shapes.
 
@@ -110,7 +121,7 @@ def synthetic_state_dict(shapes: Mapping[str, Sequence[int]], seed: int = 0) -> 
             t = torch.randn(shape, generator=g) * 0.2
         elif leaf == "running_var":
             t = torch.rand(shape, generator=g) + 0.5
-        elif is_norm and leaf == "weight":
+        elif leaf == "weight" and (is_norm or len(shape) == 1):     # norm layers, also unnamed ones in nn.Sequential
             t = torch.rand(shape, generator=g) + 0.5
         elif leaf == "bias":
             t = torch.randn(shape, generator=g) * 0.1

@@ -439,3 +439,60 @@ def fusion_path(sds: Mapping[str, Mapping], layer_names, xs: Sequence[Tensor], h
         outs.append(transformer_fusion(sds[name], layer_names, max_res, xs[li], toks[C], mask,
                                        patch_info, off))
     return outs
+
+
+# --------------------------------------------------------------------------
+# the caller of the path: decoder shell + adaptive-bins head (test harness for the end-to-end depth check;
+# SURVEY.md §8 f1/f2 - these ops are NOT part of the product, they wrap it the way the reference's Decoder / Deltar do)
+# --------------------------------------------------------------------------
+def _conv(p: Mapping, name: str, x: Tensor, padding: int) -> Tensor:
+    b = p[name + ".bias"].to(x.dtype) if (name + ".bias") in p else None
+    return F.conv2d(x, p[name + ".weight"].to(x.dtype), b, padding=padding)
+
+
+def upsample_bn(p: Mapping, x: Tensor, concat_with: Tensor) -> Tensor:
+    """``UpSampleBN.forward`` (src/models/decoder.py:40-58): bilinear(align_corners) resize to the skip map, concat,
+    2 x [conv3x3 + BN(eval) + LeakyReLU(0.01)]."""
+    up = F.interpolate(x, size=[concat_with.size(2), concat_with.size(3)], mode="bilinear", align_corners=True)
+    f = torch.cat([up, concat_with], dim=1)
+    f = F.leaky_relu(_bn_eval(_conv(p, "_net.0", f, 1), p, "_net.1", 1), 0.01)
+    return F.leaky_relu(_bn_eval(_conv(p, "_net.3", f, 1), p, "_net.4", 1), 0.01)
+
+
+def decoder_shell(p: Mapping, img_features: Sequence[Tensor], hist_features: Sequence[Tensor], fuse) -> Tensor:
+    """``Decoder.forward`` (src/models/decoder.py:96-128).  ``fuse(name, x, depth_feat)`` runs one TransformerFusion
+    call (``name`` in cross_atten3 / 2 / 1): the oracle's, or the CUDA module under test."""
+    x0, x1, x2, x3, x4 = img_features
+    f1, f2, f3 = hist_features
+    d4 = _conv(p, "conv4", x4, 0)
+    d3 = _conv(p, "conv3", upsample_bn(sub(p, "up1."), d4, x3), 0)
+    d3 = torch.cat([d3, fuse("cross_atten3", d3, f3)], dim=1)
+    d2 = _conv(p, "conv2", upsample_bn(sub(p, "up2."), d3, x2), 0)
+    d2 = torch.cat([d2, fuse("cross_atten2", d2, f2)], dim=1)
+    d1 = _conv(p, "conv1", upsample_bn(sub(p, "up3."), d2, x1), 0)
+    d1 = torch.cat([d1, fuse("cross_atten1", d1, f1)], dim=1)
+    d0 = upsample_bn(sub(p, "up4."), d1, x0)
+    return _conv(p, "conv0", d0, 1)
+
+
+def depth_tail(sd: Mapping, unet_out: Tensor, min_val: float, max_val: float) -> Tuple[Tensor, Tensor]:
+    """``DepthRegression.forward`` with norm='linear' (decoder.py:21-37), the ``conv_out`` softmax over the bins and the
+    bin-centre expectation (deltar.py:18-19, 50-61).  Returns (bin_edges [B, n_bins+1], pred [B,1,H,W])."""
+    h = sub(sd, "depth_head.")
+    ram = _conv(h, "conv3x3", unet_out, 1)
+    r = F.conv2d(unet_out, h["conv1x1.weight"].to(unet_out.dtype)).mean([2, 3])
+    r = F.leaky_relu(F.linear(r, h["regressor.0.weight"].to(r.dtype), h["regressor.0.bias"].to(r.dtype)), 0.01)
+    r = F.leaky_relu(F.linear(r, h["regressor.2.weight"].to(r.dtype), h["regressor.2.bias"].to(r.dtype)), 0.01)
+    y = torch.relu(F.linear(r, h["regressor.4.weight"].to(r.dtype), h["regressor.4.bias"].to(r.dtype))) + 0.1
+    widths = (max_val - min_val) * (y / y.sum(dim=1, keepdim=True))
+    widths = F.pad(widths, (1, 0), mode="constant", value=min_val)
+    edges = torch.cumsum(widths, dim=1)
+    centers = 0.5 * (edges[:, :-1] + edges[:, 1:])
+    prob = torch.softmax(_conv(sub(sd, "conv_out."), "0", ram, 0), dim=1)
+    pred = torch.sum(prob * centers.view(*centers.shape, 1, 1), dim=1, keepdim=True)
+    return edges, pred
+
+
+def abs_rel(pred: Tensor, gt: Tensor) -> float:
+    """``compute_errors``' abs_rel (src/utils/metrics.py:10)."""
+    return float(((pred.double() - gt.double()).abs() / gt.double()).mean())
