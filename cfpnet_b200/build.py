@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(HERE, "libcfp.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "--expt-extended-lambda", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC",
-         "-Xcompiler", "-fvisibility=hidden", "-Xptxas", "-v"]
+         "-Xcompiler", "-fvisibility=hidden", "-Xptxas", "-v"] + os.environ.get("CFP_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _sources():

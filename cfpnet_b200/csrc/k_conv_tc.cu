@@ -25,12 +25,23 @@
 #include "cfp_internal.h"
 #include "umma.cuh"
 #include <stdlib.h>
+#include <stdio.h>
 
 namespace cfp {
 
+#ifdef CFP_DEBUG_TIMING
+// phase timestamps (globaltimer ns) of CTA (0,0): [0] start, [1] source-0 raster landed, [2] source-1 (or last) raster
+// landed, [3] accumulators ready, [4] epilogue done; row thread 0 writes them.  Debug builds only.
+__device__ unsigned long long g_conv_dbg[8];
+__device__ __forceinline__ unsigned long long dbg_now() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define CFP_DBG_MARK(i) do { if (blockIdx.x == 1 && blockIdx.y == 1 && threadIdx.x == 0) g_conv_dbg[i] = dbg_now(); } while (0)
+#else
+#define CFP_DBG_MARK(i) do { } while (0)
+#endif
+
 template <int C, int TCOLS> struct ConvTC {
     static constexpr int T = TCOLS / C;               // M-tiles per CTA: T*C = TCOLS TMEM columns (256 or 128)
-    static constexpr int NSLOT = C >= 128 ? 2 : 3;    // weight ring depth
+    static constexpr int NSLOT = C >= 128 ? 2 : 3;    // weight ring depth (measured: 9 / 4 slots for C = 32 / 64 cost more occupancy than they buy)
     static constexpr int SLOT_BYTES = C * C * 2;      // one [C x C] bf16 block
     static constexpr int KG = C / 8;                  // 16-byte channel groups per source
 };
@@ -72,6 +83,7 @@ __global__ void __launch_bounds__(192) conv3x3_tc_kernel(const bf16* __restrict_
     umma::fence_after_sync();
     const uint32_t tmem = bars.tmem_slot;
 
+    CFP_DBG_MARK(0);
     if (warp < 4) {
         // ---------------- stage the raster, one source at a time
         for (int s = 0; s < nsrc; ++s) {
@@ -99,46 +111,67 @@ __global__ void __launch_bounds__(192) conv3x3_tc_kernel(const bf16* __restrict_
             }
             asm volatile("cp.async.commit_group;\n" ::: "memory");
             asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+            CFP_DBG_MARK(1 + s);
             umma::fence_async_smem();
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(umma::smem_u32(&bars.a_ready)) : "memory");
         }
-        // ---------------- epilogue: thread = accumulator row = output cell of the padded raster
-        umma::mbar_wait(&bars.acc_ready, 0);
-        umma::fence_after_sync();
-#pragma unroll 1
-        for (int t = 0; t < P::T; ++t) {
+        // ---------------- epilogue: thread = accumulator row = output cell of the padded raster.  The residual row of tile
+        // t + 1 is fetched while tile t is processed (and tile 0's while the MMAs still run): its load latency used to be
+        // paid eight times per CTA.
+        auto cell_of = [&](int t, bool& live) -> size_t {
             const int o = t * 128 + warp * 32 + lane;
             const int r = (int)__umulhi((unsigned)o, wp_magic), px = o - r * WP;   // o / WP (exact: o*WP < 2^32)
             const int y = y0 + r, x = px - 1;
-            const bool live = r < R && y < H && x >= 0 && x < W;
-            const size_t off = (frame + (size_t)y * W + x) * C;
+            live = r < R && y < H && x >= 0 && x < W;
+            return (frame + (size_t)y * W + x) * C;
+        };
+        constexpr int NCH = C / 8;
+        uint4 res_next[NCH];
+        auto fetch_res = [&](int t) {
+            bool live;
+            const size_t off = cell_of(t, live);
+#pragma unroll
+            for (int k = 0; k < NCH; ++k)
+                res_next[k] = (residual && live) ? *reinterpret_cast<const uint4*>(residual + off + k * 8) : make_uint4(0u, 0u, 0u, 0u);
+        };
+        fetch_res(0);
+        umma::mbar_wait(&bars.acc_ready, 0);
+        CFP_DBG_MARK(3);
+        umma::fence_after_sync();
 #pragma unroll 1
+        for (int t = 0; t < P::T; ++t) {
+            bool live;
+            const size_t off = cell_of(t, live);
+            uint4 res[NCH];
+#pragma unroll
+            for (int k = 0; k < NCH; ++k) res[k] = res_next[k];
+            if (t + 1 < P::T) fetch_res(t + 1);
+#pragma unroll
             for (int c0 = 0; c0 < C; c0 += 16) {
                 float v[16];
                 umma::tmem_ld16(umma::tmem_addr(tmem, warp * 32, t * C + c0), v);   // warp-collective
                 if (live) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] += shift[c0 + j];
-                    if (residual) {
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            float4 a = IO<bf16>::ld4(residual + off + c0 + 8 * h), c = IO<bf16>::ld4(residual + off + c0 + 8 * h + 4);
-                            v[8 * h + 0] += a.x; v[8 * h + 1] += a.y; v[8 * h + 2] += a.z; v[8 * h + 3] += a.w;
-                            v[8 * h + 4] += c.x; v[8 * h + 5] += c.y; v[8 * h + 6] += c.z; v[8 * h + 7] += c.w;
-                        }
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 sh = *reinterpret_cast<const float4*>(shift + c0 + j);
+                        v[j] += sh.x; v[j + 1] += sh.y; v[j + 2] += sh.z; v[j + 3] += sh.w;
                     }
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
+                        const uint4 rr = res[(c0 >> 3) + h];
+                        const uint32_t w4[4] = {rr.x, rr.y, rr.z, rr.w};
                         uint4 u;
-                        u.x = umma::pack_bf16(v[8 * h + 0], v[8 * h + 1]);
-                        u.y = umma::pack_bf16(v[8 * h + 2], v[8 * h + 3]);
-                        u.z = umma::pack_bf16(v[8 * h + 4], v[8 * h + 5]);
-                        u.w = umma::pack_bf16(v[8 * h + 6], v[8 * h + 7]);
+                        uint32_t* up = &u.x;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            up[k] = umma::pack_bf16(v[8 * h + 2 * k] + __uint_as_float(w4[k] << 16),
+                                                    v[8 * h + 2 * k + 1] + __uint_as_float(w4[k] & 0xffff0000u));
                         *reinterpret_cast<uint4*>(out + off + c0 + 8 * h) = u;
                     }
                 }
             }
         }
+        CFP_DBG_MARK(4);
         umma::fence_before_sync();
     } else if (warp == 4) {
         // ---------------- weight producer (bulk async copies, L2 -> shared)
@@ -206,6 +239,15 @@ static int conv_tc_launch(const void* in0, const void* in1, const void* wpk, con
     const unsigned wp_magic = (unsigned)((((uint64_t)1 << 32) + WP - 1) / WP);   // umulhi(i, magic) == i / WP for i*WP < 2^32
     k<<<grid, 192, smem, st>>>((const bf16*)in0, (const bf16*)in1, (const bf16*)wpk, shift, (const bf16*)residual,
                                (bf16*)out, H, W, R, cells, wp_magic, zy0, zy1, zx0, zx1);
+#ifdef CFP_DEBUG_TIMING
+    {
+        cudaStreamSynchronize(st);
+        unsigned long long h[8] = {0};
+        cudaMemcpyFromSymbol(h, g_conv_dbg, sizeof(h));
+        fprintf(stderr, "conv3x3_tc<C=%d,%s> CTA(1,1) ns: stage0 %llu  stage1 %llu  mma-done %llu  epilogue %llu  (grid %d x %d)\n", C,
+                in1 ? "2C->C" : "C->C", h[1] - h[0], h[2] - h[0], h[3] - h[0], h[4] - h[0], grid.x, grid.y);
+    }
+#endif
     return check_launch(in1 ? (C == 32 ? "conv3x3_tc<2C->C,32>" : C == 64 ? "conv3x3_tc<2C->C,64>" : "conv3x3_tc<2C->C,128>")
                             : (C == 32 ? "conv3x3_tc<C->C,32>" : C == 64 ? "conv3x3_tc<C->C,64>" : "conv3x3_tc<C->C,128>"));
 }
