@@ -24,8 +24,18 @@
 #include "umma.cuh"
 #include <cuda_fp16.h>
 #include <stdlib.h>
+#include <stdio.h>
 
 namespace cfp {
+
+#ifdef CFP_DEBUG_TIMING
+// phase timestamps (globaltimer ns) of the second tile of CTA 5 of a query-chain launch.  Debug builds only.
+__device__ unsigned long long g_chain_dbg[16];
+__device__ __forceinline__ unsigned long long chain_now() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define CFP_CHAIN_MARK(i, it) do { if (blockIdx.x == 5 && threadIdx.x == 0 && (it) == 1) g_chain_dbg[i] = chain_now(); } while (0)
+#else
+#define CFP_CHAIN_MARK(i, it) do { } while (0)
+#endif
 
 template <int C> struct ChainTC {
     static constexpr int KG = C / 8;                       // 16-byte k-groups per C columns
@@ -145,7 +155,7 @@ struct ChainStages {
                         }
                     }
                 }
-                const float inv = 1.f / den;
+                const float inv = __fdividef(1.f, den);     // MUFU.RCP: the bf16 path does not need the IEEE divide
 #pragma unroll
                 for (int v = 0; v < DH; ++v) out[hh * DH + v] = num[v] * inv;
             }
@@ -430,7 +440,10 @@ __global__ void __launch_bounds__(128, MonoOcc<C>::CTAS) loftr_query_mono_kernel
     uint32_t kvph = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, base += NB) {
         const int64_t row0 = (int64_t)tile * 128;
+        const int dbg_it = (tile - (int)blockIdx.x) / (int)gridDim.x;
+        CFP_CHAIN_MARK(0, dbg_it);
         const typename S::Row r = S::stage_x(q, row0, tid, a0);
+        CFP_CHAIN_MARK(1, dbg_it);
         const int g_first = kv_slots > 0 ? q.group_of_row(row0) : 0;
         stage([&] {                                                                        // q
             if (kv_slots > 0) {            // every row is past the previous tile's attention epilogue (stage barrier)
@@ -455,10 +468,14 @@ __global__ void __launch_bounds__(128, MonoOcc<C>::CTAS) loftr_query_mono_kernel
             S::epi_attention(q, r, tmem, warp, tid, a0, kv_t, ks_t, g_first);
             continue;                                        // next stage() barrier orders a0 / TMEM reuse
         }
+        CFP_CHAIN_MARK(2, dbg_it);
         S::epi_attention(q, r, tmem, warp, tid, a0, kv_t, ks_t, g_first);
+        CFP_CHAIN_MARK(3, dbg_it);
         stage([&] { block(base + 1, a0s + KG * P::LBO, 0, false); });                     // merge
+        CFP_CHAIN_MARK(4, dbg_it);
         if (warp == 0) { prefetch(base + 4); prefetch(base + 5); }                        // blocks 0,1 consumed
         S::epi_ln1(w, tmem, warp, tid, a0);
+        CFP_CHAIN_MARK(5, dbg_it);
         stage([&] {                                                                        // W1 quadrants
             block(base + 2, a0s, 0, false);
             block(base + 3, a0s + KG * P::LBO, 0, true);
@@ -466,13 +483,17 @@ __global__ void __launch_bounds__(128, MonoOcc<C>::CTAS) loftr_query_mono_kernel
             block(base + 5, a0s + KG * P::LBO, C, true);
         });
         if (warp == 0) { prefetch(base + 6); prefetch(base + 7); prefetch(base + 8); prefetch(base + 9); }
+        CFP_CHAIN_MARK(6, dbg_it);
         S::epi_relu(tmem, warp, tid, a1);
+        CFP_CHAIN_MARK(7, dbg_it);
         stage([&] {                                                                        // W2 K-halves
             block(base + 6, a1s, 0, false);
             block(base + 7, a1s + KG * P::LBO, 0, true);
         });
         if (warp == 0) { prefetch(base + 10); prefetch(base + 11); }
+        CFP_CHAIN_MARK(8, dbg_it);
         S::epi_out(q, r, w, tmem, warp, tid, a0);
+        CFP_CHAIN_MARK(9, dbg_it);
         // the next tile's stage_x overwrites a0[:, 0:C), which epi_out of other rows may still read
         __syncthreads();
     }
@@ -505,6 +526,15 @@ static int run_query_tc(const char* name, const Q& q, const cfp_loftr_w& w, cons
         auto k = loftr_query_mono_kernel<C, NH, kAttnOnly, Q>;
         if (int e = set_smem(k, smem)) return e;
         k<<<grid, 128, smem, st>>>(q, w, kv, ksum, (int)ntiles, kv_slots);
+#ifdef CFP_DEBUG_TIMING
+        {
+            cudaStreamSynchronize(st);
+            unsigned long long h[16] = {0};
+            cudaMemcpyFromSymbol(h, g_chain_dbg, sizeof(h));
+            fprintf(stderr, "%s (C=%d, %d CTAs, %lld tiles) 2nd tile of CTA 5, ns since tile start: stage_x %llu | q-acc %llu | attn %llu | merge-acc %llu | ln1 %llu | W1-acc %llu | relu %llu | W2-acc %llu | out %llu\n",
+                    name, C, grid, (long long)ntiles, h[1] - h[0], h[2] - h[0], h[3] - h[0], h[4] - h[0], h[5] - h[0], h[6] - h[0], h[7] - h[0], h[8] - h[0], h[9] - h[0]);
+        }
+#endif
     } else {
         const int64_t npairs = (ntiles + 1) / 2;
         const int grid = (int)(npairs < 148 ? npairs : 148);
@@ -803,28 +833,33 @@ template <int C> struct KvTC {
 // kZone16 (groups of exactly one 16-row MMA step: the hist2image zones): the per-group reduction is done by the row
 // threads themselves with FMAs straight from the bf16 K | V tile - 16 rows x dh products per (channel, group) - instead
 // of one MMA + accumulator read-back + flush round trip per group (eight serial round trips per tile).
+// NT = threads per row (KvNT<C>): at C = 128 a CTA per SM with four row warps left every scheduler with one warp of long
+// serial epilogues; two threads share a row (x chunks, then K columns | V columns, then half of the zones each).
+template <int C> struct KvNT { static constexpr int NT = C >= 128 ? 2 : 1; };
 template <int C, int NH, bool kComplete, class Src, bool kZone16 = false>
-__global__ void __launch_bounds__(192) kv_state_tc_kernel(Src src, int S, int S_pad, FastDiv dSp, int groups, const bf16* __restrict__ wkv_tc,
+__global__ void __launch_bounds__((4 * KvNT<C>::NT + 2) * 32) kv_state_tc_kernel(Src src, int S, int S_pad, FastDiv dSp, int groups, const bf16* __restrict__ wkv_tc,
                                                           float* __restrict__ kv, float* __restrict__ ksum, int ntiles) {
     using P = ChainTC<C>;
     using K = KvTC<C>;
-    constexpr int DH = C / NH, KG = P::KG;
+    constexpr int DH = C / NH, KG = P::KG, NT = KvNT<C>::NT, ROWT = 128 * NT;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ ChainBars bars;
     uint8_t* a0 = smem;                            // x tile                [KG][129][16 B]
     uint8_t* a1 = a0 + KG * P::LBO;                // K | V | ones | zeros  [A1G][129][16 B]
     uint8_t* wsm = a1 + K::A1G * P::LBO;           // Wk, Wv blocks
-    const int tid = threadIdx.x, warp = umma::warp_idx_sync(), lane = tid & 31;
+    const int tid_all = threadIdx.x, warp = umma::warp_idx_sync(), lane = tid_all & 31;
+    const int tid = tid_all & 127, half = warp >> 2, wq = warp & 3;       // row, which of the row's NT threads, TMEM lane quarter
+    auto rows_barrier = [&]() { asm volatile("bar.sync 1, %0;\n" ::"n"(ROWT) : "memory"); };
 
-    if (tid == 0) {
+    if (tid_all == 0) {
         umma::mbar_init(&bars.full[0], 1);
-        umma::mbar_init(&bars.a_ready, 128);
+        umma::mbar_init(&bars.a_ready, ROWT);
         umma::mbar_init(&bars.acc_ready, 1);
         umma::fence_mbar_init();
     }
-    if (warp == 4) umma::tmem_alloc(&bars.tmem_slot, K::TMEM_COLS);
-    if (warp < 4)                                   // zero the groups no one writes later
-        for (int i = tid; i < (K::A1G - 2 * KG) * 129; i += 128)
+    if (warp == 4 * NT) umma::tmem_alloc(&bars.tmem_slot, K::TMEM_COLS);
+    if (warp < 4 * NT)                              // zero the groups no one writes later
+        for (int i = tid_all; i < (K::A1G - 2 * KG) * 129; i += ROWT)
             *reinterpret_cast<uint4*>(a1 + (size_t)(2 * KG) * P::LBO + (size_t)i * 16) = make_uint4(0u, 0u, 0u, 0u);
     umma::fence_async_smem();
     umma::fence_before_sync();
@@ -834,7 +869,7 @@ __global__ void __launch_bounds__(192) kv_state_tc_kernel(Src src, int S, int S_
     const uint32_t total = (uint32_t)groups * (uint32_t)S_pad;      // < 2^31 (checked by the launcher): 32-bit index math and
                                                                       // multiply-high division (a 64-bit divide per run used to cost ~25 % here)
 
-    if (warp < 4) {
+    if (warp < 4 * NT) {
         uint32_t ph = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const uint32_t row0 = (uint32_t)tile * 128u;
@@ -843,11 +878,12 @@ __global__ void __launch_bounds__(192) kv_state_tc_kernel(Src src, int S, int S_
             const bool real = myp < total && mys < S;
             {
                 const typename Src::R ref = src.locate(real ? (int64_t)myg * S + mys : 0);
-                uint4 v[KG];
+                constexpr int KGT = KG / NT;                   // this thread's share of the row's 16-byte chunks
+                uint4 v[KGT];
 #pragma unroll
-                for (int kg = 0; kg < KG; ++kg) v[kg] = real ? load8_bf16(src, ref, kg * 8) : make_uint4(0u, 0u, 0u, 0u);
+                for (int k = 0; k < KGT; ++k) v[k] = real ? load8_bf16(src, ref, (half * KGT + k) * 8) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-                for (int kg = 0; kg < KG; ++kg) *reinterpret_cast<uint4*>(a0 + (size_t)kg * P::LBO + tid * 16) = v[kg];
+                for (int k = 0; k < KGT; ++k) *reinterpret_cast<uint4*>(a0 + (size_t)(half * KGT + k) * P::LBO + tid * 16) = v[k];
             }
             umma::fence_async_smem();
             mbar_arrive(&bars.a_ready);
@@ -856,9 +892,9 @@ __global__ void __launch_bounds__(192) kv_state_tc_kernel(Src src, int S, int S_
             umma::mbar_wait(&bars.acc_ready, ph); ph ^= 1;
             umma::fence_after_sync();
 #pragma unroll 1
-            for (int c0 = 0; c0 < 2 * C; c0 += 16) {
+            for (int c0 = half * (2 * C / NT); c0 < (half + 1) * (2 * C / NT); c0 += 16) {   // NT = 2: K columns | V columns
                 float t[16];
-                umma::tmem_ld16(umma::tmem_addr(tmem, warp * 32, c0), t);
+                umma::tmem_ld16(umma::tmem_addr(tmem, wq * 32, c0), t);
 #pragma unroll
                 for (int j = 0; j < 16; j += 8) {
                     float o8[8];
@@ -869,12 +905,12 @@ __global__ void __launch_bounds__(192) kv_state_tc_kernel(Src src, int S, int S_
             }
             if constexpr (kZone16) {
                 umma::fence_before_sync();
-                rows_sync();                                   // K | V of all 128 rows staged; accumulator consumed
-                constexpr int ZPT = 8 / (128 / C);             // zones per thread: thread = (channel c1, zone subset)
-                const int c1 = tid % C, h0 = (c1 / DH) * DH;
+                rows_barrier();                                // K | V of all 128 rows staged; accumulator consumed
+                constexpr int ZPT = 8 / (ROWT / C);            // zones per thread: thread = (channel c1, zone subset)
+                const int c1 = tid_all % C, h0 = (c1 / DH) * DH;
                 const uint8_t* kp = a1 + (size_t)(c1 / 8) * P::LBO + (c1 % 8) * 2;
                 const uint8_t* vp = a1 + (size_t)(KG + h0 / 8) * P::LBO;
-                for (int z = (tid / C) * ZPT; z < (tid / C) * ZPT + ZPT; ++z) {
+                for (int z = (tid_all / C) * ZPT; z < (tid_all / C) * ZPT + ZPT; ++z) {
                     float acc[DH], ks = 0.f;
 #pragma unroll
                     for (int v = 0; v < DH; ++v) acc[v] = 0.f;
@@ -899,10 +935,10 @@ __global__ void __launch_bounds__(192) kv_state_tc_kernel(Src src, int S, int S_
                         ksum[(size_t)g * C + c1] = ks;
                     }
                 }
-                rows_sync();                                   // a1 is rewritten by the next tile's epilogue
+                rows_barrier();                                // a1 is rewritten by the next tile's epilogue
                 continue;
             }
-            {
+            if (half == 0) {
                 const float one8[8] = {real ? 1.f : 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                 umma::store_chunk(a1, P::LBO, tid, 2 * KG, one8);
             }
@@ -918,12 +954,12 @@ __global__ void __launch_bounds__(192) kv_state_tc_kernel(Src src, int S, int S_
                 while (ke < 8 && row0 + 16 * ke < total && (int)dSp.div(row0 + 16 * ke) == g) ++ke;
                 umma::mbar_wait(&bars.acc_ready, ph); ph ^= 1;
                 umma::fence_after_sync();
-                if (warp * 32 < C) {
-                    const int m = warp * 32 + lane;
+                if (half == 0 && wq * 32 < C) {
+                    const int m = wq * 32 + lane;
                     float t0[16], t1[16], o[16];
-                    umma::tmem_ld16(umma::tmem_addr(tmem, warp * 32, 2 * C + warp * 32), t0);
-                    umma::tmem_ld16(umma::tmem_addr(tmem, warp * 32, 2 * C + warp * 32 + 16), t1);
-                    umma::tmem_ld16(umma::tmem_addr(tmem, warp * 32, 3 * C), o);
+                    umma::tmem_ld16(umma::tmem_addr(tmem, wq * 32, 2 * C + wq * 32), t0);
+                    umma::tmem_ld16(umma::tmem_addr(tmem, wq * 32, 2 * C + wq * 32 + 16), t1);
+                    umma::tmem_ld16(umma::tmem_addr(tmem, wq * 32, 3 * C), o);
                     float* dst = kv + (size_t)g * (C * DH) + (size_t)m * DH;
 #pragma unroll
                     for (int sb = 0; sb < 32 / DH; ++sb)
@@ -948,7 +984,7 @@ __global__ void __launch_bounds__(192) kv_state_tc_kernel(Src src, int S, int S_
             }
             umma::fence_before_sync();
         }
-    } else if (warp == 4) {
+    } else if (warp == 4 * NT) {
         umma::bulk_load(wsm, wkv_tc, 4 * C * C, &bars.full[0]);
     } else {
         {
@@ -990,7 +1026,7 @@ __global__ void __launch_bounds__(192) kv_state_tc_kernel(Src src, int S, int S_
         }
     }
     __syncthreads();
-    if (warp == 4) {
+    if (warp == 4 * NT) {
         umma::fence_after_sync();
         umma::tmem_dealloc(tmem, K::TMEM_COLS);
     }
@@ -1015,15 +1051,15 @@ static int run_kv_state_tc(const char* name, const Src& src, int S, int groups, 
     if (S_pad == 16 && NH == 4) {                     // hist2image zones (dh = C/4 is a multiple of 8)
         auto k = kv_state_tc_kernel<C, NH, true, Src, (NH == 4)>;
         if (int e = set_smem(k, K::SMEM)) return e;
-        k<<<grid, 192, K::SMEM, st>>>(src, S, S_pad, FastDiv((uint32_t)S_pad), groups, (const bf16*)wkv_tc, kv, ksum, (int)ntiles);
+        k<<<grid, (4 * KvNT<C>::NT + 2) * 32, K::SMEM, st>>>(src, S, S_pad, FastDiv((uint32_t)S_pad), groups, (const bf16*)wkv_tc, kv, ksum, (int)ntiles);
     } else if (complete) {
         auto k = kv_state_tc_kernel<C, NH, true, Src>;
         if (int e = set_smem(k, K::SMEM)) return e;
-        k<<<grid, 192, K::SMEM, st>>>(src, S, S_pad, FastDiv((uint32_t)S_pad), groups, (const bf16*)wkv_tc, kv, ksum, (int)ntiles);
+        k<<<grid, (4 * KvNT<C>::NT + 2) * 32, K::SMEM, st>>>(src, S, S_pad, FastDiv((uint32_t)S_pad), groups, (const bf16*)wkv_tc, kv, ksum, (int)ntiles);
     } else {
         auto k = kv_state_tc_kernel<C, NH, false, Src>;
         if (int e = set_smem(k, K::SMEM)) return e;
-        k<<<grid, 192, K::SMEM, st>>>(src, S, S_pad, FastDiv((uint32_t)S_pad), groups, (const bf16*)wkv_tc, kv, ksum, (int)ntiles);
+        k<<<grid, (4 * KvNT<C>::NT + 2) * 32, K::SMEM, st>>>(src, S, S_pad, FastDiv((uint32_t)S_pad), groups, (const bf16*)wkv_tc, kv, ksum, (int)ntiles);
     }
     return check_launch(name);
 }
