@@ -54,6 +54,8 @@ class FusionPath(nn.Module):
             return [m(x, f, **kw) for m, x, f in jobs]
         dev = x3.device
         cur = torch.cuda.current_stream(dev)
+        # (measured: stream priorities do not help - higher priority for the two smaller levels costs 2.5 %, for the
+        # largest level nothing changes)
         side = self.__dict__.setdefault("_level_streams", {}).setdefault(str(dev), [torch.cuda.Stream(dev) for _ in range(2)])
         # results are allocated on the caller's stream (no cross-stream allocator traffic: record_stream()
         # on side-stream tensors turns into a cudaMalloc per step, and those occasionally stall for ~100 ms)
