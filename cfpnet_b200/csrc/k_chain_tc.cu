@@ -77,21 +77,29 @@ __device__ __forceinline__ void load_row(uint32_t tmem, int warp, float (&v)[C])
 }
 template <int C>
 __device__ __forceinline__ void layernorm_reg(float (&v)[C], const float* __restrict__ g, const float* __restrict__ b) {
-    float s = 0.f;
+    using namespace umma;
+    f32x2 p[C / 2];                                      // the row as C/2 register pairs: every step is one packed op per pair
+    f32x2 s2 = pack2(0.f, 0.f);
 #pragma unroll
-    for (int i = 0; i < C; ++i) s += v[i];
-    const float mean = s * (1.f / C);
-    float q = 0.f;
+    for (int i = 0; i < C / 2; ++i) { p[i] = pack2(v[2 * i], v[2 * i + 1]); s2 = add2(s2, p[i]); }
+    float s_lo, s_hi;
+    unpack2(s2, s_lo, s_hi);
+    const float mean = (s_lo + s_hi) * (1.f / C);
+    const f32x2 nm = pack2(-mean, -mean);
+    f32x2 q2 = pack2(0.f, 0.f);
 #pragma unroll
-    for (int i = 0; i < C; ++i) { v[i] -= mean; q += v[i] * v[i]; }
-    const float rstd = rsqrtf(q * (1.f / C) + kLnEps);
+    for (int i = 0; i < C / 2; ++i) { p[i] = add2(p[i], nm); q2 = fma2(p[i], p[i], q2); }
+    float q_lo, q_hi;
+    unpack2(q2, q_lo, q_hi);
+    const float rstd = rsqrtf((q_lo + q_hi) * (1.f / C) + kLnEps);
+    const f32x2 r2 = pack2(rstd, rstd);
 #pragma unroll
-    for (int i = 0; i < C; i += 4) {                     // gamma / beta as 16-byte loads (warp-uniform addresses)
-        const float4 g4 = *reinterpret_cast<const float4*>(g + i), b4 = *reinterpret_cast<const float4*>(b + i);
-        v[i] = fmaf(v[i] * rstd, g4.x, b4.x);
-        v[i + 1] = fmaf(v[i + 1] * rstd, g4.y, b4.y);
-        v[i + 2] = fmaf(v[i + 2] * rstd, g4.z, b4.z);
-        v[i + 3] = fmaf(v[i + 3] * rstd, g4.w, b4.w);
+    for (int i = 0; i < C / 2; i += 2) {                 // gamma / beta as 16-byte loads (warp-uniform addresses)
+        const float4 g4 = *reinterpret_cast<const float4*>(g + 2 * i), b4 = *reinterpret_cast<const float4*>(b + 2 * i);
+        const f32x2 o0 = fma2(mul2(p[i], r2), pack2(g4.x, g4.y), pack2(b4.x, b4.y));
+        const f32x2 o1 = fma2(mul2(p[i + 1], r2), pack2(g4.z, g4.w), pack2(b4.z, b4.w));
+        unpack2(o0, v[2 * i], v[2 * i + 1]);
+        unpack2(o1, v[2 * i + 2], v[2 * i + 3]);
     }
 }
 
@@ -143,17 +151,23 @@ struct ChainStages {
                 if (g >= 0) {
                     const float* kvh = kv + (size_t)(g - g_base) * (C * DH) + (size_t)h0 * DH;
                     const float* ksh = ksum + (size_t)(g - g_base) * C + h0;
+                    umma::f32x2 n2[DH / 2];                  // num as register pairs: one FFMA2 per two outputs
+#pragma unroll
+                    for (int v = 0; v < DH / 2; ++v) n2[v] = umma::pack2(0.f, 0.f);
 #pragma unroll
                     for (int d = 0; d < DH; ++d) {
                         const float qd = qv[hh * DH + d];
                         den = fmaf(qd, ksh[d], den);
+                        const umma::f32x2 q2 = umma::pack2(qd, qd);
 #pragma unroll
                         for (int v = 0; v < DH; v += 4) {
                             const float4 k4 = *reinterpret_cast<const float4*>(kvh + d * DH + v);
-                            num[v] = fmaf(qd, k4.x, num[v]); num[v + 1] = fmaf(qd, k4.y, num[v + 1]);
-                            num[v + 2] = fmaf(qd, k4.z, num[v + 2]); num[v + 3] = fmaf(qd, k4.w, num[v + 3]);
+                            n2[v / 2] = umma::fma2(q2, umma::pack2(k4.x, k4.y), n2[v / 2]);
+                            n2[v / 2 + 1] = umma::fma2(q2, umma::pack2(k4.z, k4.w), n2[v / 2 + 1]);
                         }
                     }
+#pragma unroll
+                    for (int v = 0; v < DH / 2; ++v) umma::unpack2(n2[v], num[2 * v], num[2 * v + 1]);
                 }
                 const float inv = __fdividef(1.f, den);     // MUFU.RCP: the bf16 path does not need the IEEE divide
 #pragma unroll
@@ -655,18 +669,27 @@ __global__ void __launch_bounds__(192) lkpm_mlp_tc_kernel(bf16* __restrict__ fea
                         for (int i = 0; i < 8; ++i) v[j + i] = t[i];
                     }
                 }
-                float s = 0.f;
+                using namespace umma;                            // packed fp32x2: one instruction per channel pair
+                f32x2 p2[C / 2];
+                f32x2 s2 = pack2(0.f, 0.f);
 #pragma unroll
-                for (int i = 0; i < C; ++i) s += v[i];
-                const float mean = s * (1.f / C);
-                float q = 0.f;
+                for (int i = 0; i < C / 2; ++i) { p2[i] = pack2(v[2 * i], v[2 * i + 1]); s2 = add2(s2, p2[i]); }
+                float s_lo, s_hi;
+                unpack2(s2, s_lo, s_hi);
+                const float mean = (s_lo + s_hi) * (1.f / C);
+                const f32x2 nm = pack2(-mean, -mean);
+                f32x2 q2 = pack2(0.f, 0.f);
 #pragma unroll
-                for (int i = 0; i < C; ++i) { v[i] -= mean; q += v[i] * v[i]; }
-                const float rstd = rsqrtf(q * (1.f / C) + kLkpmLnEps);
+                for (int i = 0; i < C / 2; ++i) { p2[i] = add2(p2[i], nm); q2 = fma2(p2[i], p2[i], q2); }
+                float q_lo, q_hi;
+                unpack2(q2, q_lo, q_hi);
+                const float rstd = rsqrtf((q_lo + q_hi) * (1.f / C) + kLkpmLnEps);
+                const f32x2 r2 = pack2(rstd, rstd);
 #pragma unroll
                 for (int j = 0; j < C; j += 8) {                 // gamma / beta live in W1 / b1 (host fold)
-                    const float o8[8] = {v[j] * rstd,     v[j + 1] * rstd, v[j + 2] * rstd, v[j + 3] * rstd,
-                                         v[j + 4] * rstd, v[j + 5] * rstd, v[j + 6] * rstd, v[j + 7] * rstd};
+                    float o8[8];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) unpack2(mul2(p2[j / 2 + k], r2), o8[2 * k], o8[2 * k + 1]);
                     umma::store_chunk(a0, P::LBO, tid, j / 8, o8);
                 }
             }
