@@ -495,6 +495,97 @@ def roofline_from_profile(prof, steps, B, es, peaks):
     return roof, kernels
 
 
+# ---------------------------------------------------------------------------------- other BASELINE.json configs
+def run_aux(a):
+    """The two single-GPU side configurations of BASELINE.json (not the headline line):
+      --workload baseline_b16   configs[1]: DELTAR-style layer list (hist2image image x2, no cross-zone propagation),
+                                batch 16, 416x544 - frames/s, device-resident, K timed steps;
+      --workload latency_480    configs[3]: combine1, ZJUL5-shaped 480x640 (8x8 zones of 56 px: the bilinear-resize
+                                branch at 1/16), batch 1, evaluate_time.py's protocol (evaluate_time.py:56-82): 100
+                                warm-up forwards, 500 timed ones each bracketed by a device synchronise, trimmed mean
+                                sum(sorted(dt)[1:-2]) / (n - 3) in ms."""
+    from cfpnet_b200 import FusionPath, shard
+    from cfpnet_b200.build import build
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the fusion path has no CPU fallback")
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    build()
+    dtype = {"bf16": torch.bfloat16, "f32": torch.float32}[a.dtype]
+    latency = a.workload == "latency_480"
+    layers = synth.COMBINE1_LAYERS if latency else ("hist2image", "image", "hist2image", "image")
+    geom, B = ("G480", 1) if latency else ("G416", 16)
+    path = FusionPath(layers)
+    path.hist_encoder.load_state_dict(synth.synthetic_state_dict({k: v.shape for k, v in path.hist_encoder.state_dict().items()}, 0))
+    for lv, name in ((3, "cross_atten3"), (2, "cross_atten2"), (1, "cross_atten1")):
+        m = getattr(path, name)
+        m.load_state_dict(synth.synthetic_state_dict({k: v.shape for k, v in m.state_dict().items()}, lv))
+    path = path.to(dev).eval().set_dtype(dtype)
+    sets = []
+    for s_ in range(3):
+        inp = synth.make_inputs(geom, B, seed=100 + s_)
+        sets.append({k: (inp[k].to(dtype) if k.startswith("x") else inp[k]).to(dev) for k in ("x3", "x2", "x1", "hist_data", "mask")})
+    patch_info = inp["patch_info"]
+
+    def step(i):
+        d = sets[i % 3]
+        shard.seed_posenc(i)
+        return path(d["x3"], d["x2"], d["x1"], d["hist_data"], d["mask"], patch_info)
+
+    with torch.no_grad():
+        if latency:
+            for i in range(100):
+                step(i)
+            dts = []
+            for i in range(500):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                step(i)
+                torch.cuda.synchronize()
+                dts.append(time.perf_counter() - t0)
+            ms_eager = 1e3 * sum(sorted(dts)[1:-2]) / (len(dts) - 3)
+            # the same protocol through a CUDA-graph replay of the forward (the maps fill the positional-encoding tables
+            # at 480x640, so nothing random is frozen): removes the ~95 host-side launches per forward
+            d0 = sets[0]
+            run = path.make_graphed(d0["x3"], d0["x2"], d0["x1"], d0["hist_data"], d0["mask"], patch_info)
+            for i in range(100):
+                d = sets[i % 3]
+                run(d["x3"], d["x2"], d["x1"], d["hist_data"], d["mask"])
+            dts = []
+            for i in range(500):
+                d = sets[i % 3]
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                run(d["x3"], d["x2"], d["x1"], d["hist_data"], d["mask"])
+                torch.cuda.synchronize()
+                dts.append(time.perf_counter() - t0)
+            ms = 1e3 * sum(sorted(dts)[1:-2]) / (len(dts) - 3)
+            line = {"metric": "CFP fusion path latency @480x640, 8x8 zones, batch 1 (evaluate_time.py protocol)", "value": ms,
+                    "unit": "ms", "higher_is_better": False, "n_gpus": 1, "steps": 500, "warmup": 100, "ms_per_step": ms,
+                    "dtype": a.dtype, "data": "synthetic", "vs_baseline": None,
+                    "config": {"workload": "CFPNet combine1 fusion path, ZJUL5-shaped 480x640, 8x8 zones of 56 px, batch 1 "
+                                           "(BASELINE.json configs[3]); hot path only (hist encoder + three TransformerFusion calls)",
+                               "layers": list(layers), "median_ms": 1e3 * statistics.median(dts), "min_ms": 1e3 * min(dts),
+                               "mode": "CUDA-graph replay (FusionPath.make_graphed)", "eager_ms": ms_eager}}
+        else:
+            for i in range(max(a.warmup, 3)):
+                step(i)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(a.steps):
+                step(i)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / a.steps
+            line = {"metric": "DELTAR-style fusion (no cross-zone propagation) frames/s @416x544, 8x8 zones, batch 16", "value": B * 1e3 / ms,
+                    "unit": "frames/s", "higher_is_better": True, "n_gpus": 1, "steps": a.steps, "warmup": max(a.warmup, 3),
+                    "ms_per_step": ms, "dtype": a.dtype, "data": "synthetic", "vs_baseline": None,
+                    "config": {"workload": "DELTAR-style baseline layer list (..._10x config), 416x544, batch 16, 1 GPU "
+                                           "(BASELINE.json configs[1])", "layers": list(layers), "per_gpu_batch": B}}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -504,7 +595,11 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="frames per GPU per step")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="combine1_b64", choices=["combine1_b64", "baseline_b16", "latency_480"],
+                    help="combine1_b64 = the headline (BASELINE.json configs[2]); the other two are side configurations")
     a = ap.parse_args()
+    if a.workload != "combine1_b64":
+        return run_aux(a)
     a.warmup = max(a.warmup, 3) if a.impl == "cfp" else a.warmup
     if a.impl == "reference":
         run_reference(a)

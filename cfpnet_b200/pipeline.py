@@ -78,6 +78,41 @@ class FusionPath(nn.Module):
             cur.wait_event(e)
         return outs
 
+    # ------------------------------------------------------------------ CUDA-graph replay (latency mode)
+    def make_graphed(self, x3, x2, x1, hist_data, mask, patch_info):
+        """Capture one forward (all ~95 launches on the three level streams) into a CUDA graph over static input
+        buffers and return ``run(x3, x2, x1, hist_data, mask) -> [fused3, fused2, fused1]`` that copies the inputs in
+        and replays it: at batch 1 the eager path is bound by the ~95 host-side launches, not by the GPU.
+
+        A replay re-runs the captured kernels with the captured arguments, so the positional-encoding crop offsets
+        (``fusion.py:88-91``, drawn per forward when the map is smaller than the table) would be frozen: capture is
+        only offered when every level's map fills its table (the 480x640 evaluation geometry), where the reference
+        draws nothing either."""
+        for m, x in ((self.cross_atten3, x3), (self.cross_atten2, x2), (self.cross_atten1, x1)):
+            if list(x.shape[2:]) != list(m.max_resolution):
+                raise ValueError(f"make_graphed: a {tuple(x.shape[2:])} map draws a random positional-encoding crop from the "
+                                 f"{m.max_resolution} table on every forward; replaying a graph would freeze it")
+        static = [t.clone() for t in (x3, x2, x1, hist_data, mask)]
+        dev = x3.device
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), torch.no_grad():          # warm-up off the capture: packing, scratch, smem attributes
+            for _ in range(2):
+                self.forward(*static, patch_info)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph), torch.no_grad():
+            outs = self.forward(*static, patch_info)
+
+        def run(x3, x2, x1, hist_data, mask):
+            for dst, src in zip(static, (x3, x2, x1, hist_data, mask)):
+                dst.copy_(src, non_blocking=True)
+            graph.replay()
+            return outs
+
+        run.graph = graph
+        return run
+
     # ------------------------------------------------------------------ host-buffer entry
     def forward_host(self, host: Dict[str, torch.Tensor], patch_info, device) -> List[torch.Tensor]:
         """End-to-end call with HOST buffers: pinned inputs are copied to the device, the path

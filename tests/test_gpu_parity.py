@@ -248,3 +248,31 @@ def test_stream_host_equals_direct_forward():
         torch.cuda.synchronize()
         for g_, w_ in zip(got[i], want):
             assert rel_l2(g_, w_) <= 1e-2
+
+
+def test_graph_replay_equals_eager_forward():
+    """FusionPath.make_graphed at the 480x640 geometry (no positional-encoding crop is drawn there): a replay on new
+    inputs equals the eager forward on them; at 416x544 capture is refused (the crop offsets would be frozen)."""
+    path = cfpnet_b200.FusionPath(synth.COMBINE1_LAYERS)
+    path.hist_encoder.load_state_dict(synth.synthetic_state_dict({k: v.shape for k, v in path.hist_encoder.state_dict().items()}, 0))
+    for lv, name in ((3, "cross_atten3"), (2, "cross_atten2"), (1, "cross_atten1")):
+        m = getattr(path, name)
+        m.load_state_dict(synth.synthetic_state_dict({k: v.shape for k, v in m.state_dict().items()}, lv))
+    path = path.to(DEV).eval().set_dtype(torch.bfloat16)
+
+    def dev_inputs(geom, seed):
+        inp = synth.make_inputs(geom, 1, seed=seed)
+        return [inp[k].to(torch.bfloat16).to(DEV) for k in ("x3", "x2", "x1")] + [inp["hist_data"].to(DEV), inp["mask"].to(DEV)], inp["patch_info"]
+
+    a, pi = dev_inputs("G480", 3)
+    b, _ = dev_inputs("G480", 4)
+    with torch.no_grad():
+        run = path.make_graphed(*a, pi)
+        got = [o.clone() for o in run(*b)]
+        torch.cuda.synchronize()
+        want = path(*b, pi)
+    for g_, w_ in zip(got, want):      # not bit-equal: the split-K / straddling-group fp32 atomics are order-dependent
+        assert rel_l2(g_, w_) <= 5e-3
+    c, pi416 = dev_inputs("G416", 3)
+    with pytest.raises(ValueError, match="positional-encoding"):
+        path.make_graphed(*c, pi416)
