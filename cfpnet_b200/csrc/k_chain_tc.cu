@@ -219,6 +219,57 @@ struct ChainStages {
     template <bool kReloadX = false>
     static __device__ __forceinline__ void epi_out(const Q& q, const Row& r, const cfp_loftr_w& w, uint32_t tmem, int warp, int tid,
                                                    const uint8_t* a0) {
+        if constexpr (kReloadX) {
+            // C = 128, two-tile kernel: the residual row is fetched through the provider FIRST (all KG 16-byte loads in
+            // flight at once - issued one by one between the stores they used to serialise on each other, 12-38 us per
+            // tile), and LayerNorm walks the accumulator three times in 16-column pieces instead of holding all C
+            // values in registers next to them (mean, then centred sum of squares, then normalise + residual + store).
+            uint4 xr[KG];
+#pragma unroll
+            for (int k = 0; k < KG; ++k) xr[k] = r.g >= 0 ? load8_bf16(q, r.ref, k * 8) : make_uint4(0u, 0u, 0u, 0u);
+            float s = 0.f;
+#pragma unroll 1
+            for (int c0 = 0; c0 < C; c0 += 16) {
+                float t[16];
+                umma::tmem_ld16(umma::tmem_addr(tmem, warp * 32, c0), t);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) s += t[i];
+            }
+            const float mean = s * (1.f / C);
+            float qs = 0.f;
+#pragma unroll 1
+            for (int c0 = 0; c0 < C; c0 += 16) {
+                float t[16];
+                umma::tmem_ld16(umma::tmem_addr(tmem, warp * 32, c0), t);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { const float d = t[i] - mean; qs = fmaf(d, d, qs); }
+            }
+            const float rstd = rsqrtf(qs * (1.f / C) + kLnEps);
+#pragma unroll
+            for (int c0 = 0; c0 < C; c0 += 16) {
+                float t[16];
+                umma::tmem_ld16(umma::tmem_addr(tmem, warp * 32, c0), t);
+                if (r.g >= 0) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int j = c0 + 8 * h;
+                        const float4 g0 = *reinterpret_cast<const float4*>(w.ln2_g + j), g1 = *reinterpret_cast<const float4*>(w.ln2_g + j + 4);
+                        const float4 b0 = *reinterpret_cast<const float4*>(w.ln2_b + j), b1 = *reinterpret_cast<const float4*>(w.ln2_b + j + 4);
+                        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                        float x8[8], o8[8];
+                        unpack8(xr[j / 8], x8);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) o8[i] = x8[i] + fmaf((t[8 * h + i] - mean) * rstd, gg[i], bb[i]);
+                        if constexpr (HasPutSum<Q>::value) {
+                            if (q.sums_in_place()) { q.put8_sum(r.ref, j, o8, x8); continue; }
+                        }
+                        store8(q, r.ref, j, o8);
+                    }
+                }
+            }
+            return;
+        }
         float v[C];
         load_row<C>(tmem, warp, v);
         layernorm_reg<C>(v, w.ln2_g, w.ln2_b);
@@ -226,8 +277,7 @@ struct ChainStages {
 #pragma unroll
             for (int j = 0; j < C; j += 8) {
                 float x8[8], o8[8];
-                if (kReloadX) unpack8(load8_bf16(q, r.ref, j), x8);
-                else unpack8(*reinterpret_cast<const uint4*>(a0 + (size_t)(j / 8) * P::LBO + tid * 16), x8);
+                unpack8(*reinterpret_cast<const uint4*>(a0 + (size_t)(j / 8) * P::LBO + tid * 16), x8);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) o8[i] = x8[i] + v[j + i];
                 if constexpr (HasPutSum<Q>::value && sizeof(typename Q::R) > 0) {
@@ -303,16 +353,27 @@ __global__ void __launch_bounds__(320, 1) loftr_query_tc_kernel(Q q, cfp_loftr_w
         for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
             const int tile = 2 * pair + grp;                 // an odd tile count leaves group 1 of the last pair with dead rows
             const int64_t row0 = tile < ntiles ? (int64_t)tile * 128 : q.rows;
+            const int dbg_it = 1 - (pair - (int)blockIdx.x) / (int)gridDim.x;      // marks on the FIRST pair of CTA 5
+            CFP_CHAIN_MARK(0, dbg_it);
             const typename S::Row r = S::stage_x(q, row0, tid_g, a0);
+            CFP_CHAIN_MARK(1, dbg_it);
             hand_over();
+            CFP_CHAIN_MARK(2, dbg_it);
             S::epi_attention(q, r, tmem, wq, tid_g, a0, kv, ksum);
+            CFP_CHAIN_MARK(3, dbg_it);
             if (!kAttnOnly) {
                 hand_over();
+                CFP_CHAIN_MARK(4, dbg_it);
                 S::epi_ln1(w, tmem, wq, tid_g, a0);
+                CFP_CHAIN_MARK(5, dbg_it);
                 hand_over();
+                CFP_CHAIN_MARK(6, dbg_it);
                 S::epi_relu(tmem, wq, tid_g, a0);             // in place: the W1 MMAs have consumed [x | LN1]
+                CFP_CHAIN_MARK(7, dbg_it);
                 hand_over();
+                CFP_CHAIN_MARK(8, dbg_it);
                 S::template epi_out<true>(q, r, w, tmem, wq, tid_g, a0);
+                CFP_CHAIN_MARK(9, dbg_it);
             }
             umma::fence_before_sync();
             asm volatile("bar.sync 1, 256;\n" ::: "memory");  // every row is done with a0 / the accumulators before the next pair
@@ -555,6 +616,15 @@ static int run_query_tc(const char* name, const Q& q, const cfp_loftr_w& w, cons
         auto k = loftr_query_tc_kernel<C, NH, kAttnOnly, Q>;
         if (int e = set_smem(k, P::SMEM)) return e;
         k<<<grid, 320, P::SMEM, st>>>(q, w, kv, ksum, (int)ntiles);
+#ifdef CFP_DEBUG_TIMING
+        {
+            cudaStreamSynchronize(st);
+            unsigned long long h[16] = {0};
+            cudaMemcpyFromSymbol(h, g_chain_dbg, sizeof(h));
+            fprintf(stderr, "%s (C=%d, %d CTAs, %lld tiles, two per CTA) 1st pair of CTA 5, ns since start: stage_x %llu | q-acc %llu | attn %llu | merge-acc %llu | ln1 %llu | W1-acc %llu | relu %llu | W2-acc %llu | out %llu\n",
+                    name, C, grid, (long long)ntiles, h[1] - h[0], h[2] - h[0], h[3] - h[0], h[4] - h[0], h[5] - h[0], h[6] - h[0], h[7] - h[0], h[8] - h[0], h[9] - h[0]);
+        }
+#endif
     }
     return check_launch(name);
 }

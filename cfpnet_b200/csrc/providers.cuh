@@ -210,6 +210,19 @@ struct ZonePatchRows {         // hist2image queries: cells of the zone canvas, 
         if (y < 0 || y >= H || x < 0 || x >= W) return make_float4(0.f, 0.f, 0.f, 0.f);
         return IO<T>::ld4(emb + ((int64_t)b * H * W + (int64_t)y * W + x) * C + c);
     }
+    // bf16 storage, no resize: the canvas cell is one 16-byte load (zeros outside the map); the resize branch goes through
+    // the fp32 bilinear blend
+    __device__ uint4 raw8(const R& q, int c) const {
+        static_assert(sizeof(T) == 2, "raw8 is the bf16 fast path");
+        if (!interpolate) {
+            const int y = sy_wo + q.cy, x = sx_wo + q.cx;
+            if (y < 0 || y >= H || x < 0 || x >= W) return make_uint4(0u, 0u, 0u, 0u);
+            return *reinterpret_cast<const uint4*>(emb + ((int64_t)q.b * H * W + (int64_t)y * W + x) * C + c);
+        }
+        const float4 a = load4(q, c), b = load4(q, c + 4);
+        const float v8[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        return pack8_bf16_fwd(v8);
+    }
     __device__ float4 load4(const R& q, int c) const {
         if (!interpolate) return canvas_at(q.b, q.cy, q.cx, c);
         // F.interpolate(bilinear, align_corners=True) from [tzh,tzw] to [zn*p1, zn*p2]  (fusion.py:141)
