@@ -108,10 +108,7 @@ __device__ __forceinline__ void hist_tc_stage(uint8_t* a, const uint8_t* wsm, co
     }
     umma::mbar_wait(acc_ready, ph); ph ^= 1;
     umma::fence_after_sync();
-#pragma unroll 1
-    for (int c0 = 0; c0 < N; c0 += 16) {
-        float t[16];
-        umma::tmem_ld16(umma::tmem_addr(tmem, wq * 32, c0), t);
+    umma::tmem_for_each16<N>(umma::tmem_addr(tmem, wq * 32, 0), [&](int c0, const float (&t)[16]) {
 #pragma unroll
         for (int j = 0; j < 16; j += 8) {
             const float4 b0 = *reinterpret_cast<const float4*>(bias + c0 + j), b1 = *reinterpret_cast<const float4*>(bias + c0 + j + 4);
@@ -123,7 +120,7 @@ __device__ __forceinline__ void hist_tc_stage(uint8_t* a, const uint8_t* wsm, co
             *reinterpret_cast<uint4*>(a + (size_t)((c0 + j) / 8) * HistTC::LBO + tid_g * 16) = u;
             if (kStore && row < rows) *reinterpret_cast<uint4*>(out + row * N + c0 + j) = u;
         }
-    }
+    });
 }
 
 __global__ void __launch_bounds__(256, 1) hist_encoder_tc_kernel(const float* __restrict__ hist, bf16* __restrict__ o32,

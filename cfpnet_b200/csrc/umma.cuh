@@ -107,6 +107,42 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+// Asynchronous form: the load is only issued; the registers are valid after tmem_wait_ld16() on the SAME array (the wait
+// names them as read-write operands, so the compiler cannot move a use above it).
+__device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld16(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+}
+// Walk NCOLS accumulator columns of this thread's TMEM lane in 16-column pieces, f(c0, v[16]) on each, with the load of
+// piece i+1 in flight while piece i is processed (a tcgen05.ld + wait per piece exposes ~100 cycles of TMEM latency
+// every 16 columns - every epilogue used to pay that).
+template <int NCOLS, class F>
+__device__ __forceinline__ void tmem_for_each16(uint32_t taddr, F&& f) {
+    static_assert(NCOLS % 16 == 0, "16-column pieces");
+    uint32_t buf[2][16];
+    tmem_ld16_async(taddr, buf[0]);
+    tmem_wait_ld16(buf[0]);
+#pragma unroll
+    for (int i = 0; i < NCOLS / 16; ++i) {
+        if (i + 1 < NCOLS / 16) tmem_ld16_async(taddr + (uint32_t)((i + 1) * 16), buf[(i + 1) & 1]);
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(buf[i & 1][j]);
+        f(i * 16, v);
+        if (i + 1 < NCOLS / 16) tmem_wait_ld16(buf[(i + 1) & 1]);
+    }
+}
 __device__ __forceinline__ uint32_t tmem_addr(uint32_t base, int lane, int col) {
     return base + ((uint32_t)lane << 16) + (uint32_t)col;
 }
