@@ -645,7 +645,7 @@ template <int C> struct MlpTC {
     static constexpr int BLK1 = NS * K1 * 2, BLK2 = C * K2 * 2;
     static constexpr int BLK = BLK1 > BLK2 ? BLK1 : BLK2;   // ring slot / packed block stride (bytes)
     static constexpr int NBLK = 2 * NSL;                 // blocks per tile
-    static constexpr int NSLOT = C >= 128 ? 2 : (C == 64 ? 4 : 2);
+    static constexpr int NSLOT = 2;                      // (4 slots at C = 64 cost the second CTA per SM: 140 KB of shared memory)
     static constexpr int OUT_COL = NSL == 1 ? 0 : NS;    // out accumulator columns
     static constexpr int TMEM_COLS = NSL == 1 ? 128 : 256;
     static constexpr int G0 = K1 / 8, G1 = K2 / 8;       // 16-byte k-groups of the two A buffers
