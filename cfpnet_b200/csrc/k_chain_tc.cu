@@ -898,7 +898,11 @@ template <int C> struct KvTC {
     static constexpr int KG = C / 8;
     static constexpr int A1G = 2 * KG + 2 < 16 ? 16 : 2 * KG + 2;   // K | V | ones | zeros (>= 16 groups: M = 128)
     static constexpr int NRED = C + 16;
-    static constexpr int TMEM_COLS = 3 * C + 16 <= 128 ? 128 : (3 * C + 16 <= 256 ? 256 : 512);
+    // the reduction accumulator (C + 16 columns) reuses the projection's 2C columns: the reduce MMAs are issued only after
+    // every row thread has read its K | V row (a_ready), so the kernel needs max(2C, C + 16) columns - 64 / 128 / 256 -
+    // and TMEM stops being what limits the co-resident CTAs at C = 32 / 64
+    static constexpr int RED_COL = 0;
+    static constexpr int TMEM_COLS = 2 * C <= 64 ? 64 : (2 * C <= 128 ? 128 : 256);
     static constexpr size_t SMEM = (size_t)(KG + A1G) * ChainTC<C>::LBO + 4 * (size_t)C * C;
 };
 
@@ -1049,9 +1053,9 @@ __global__ void __launch_bounds__((4 * KvNT<C>::NT + 2) * 32) kv_state_tc_kernel
                 if (half == 0 && wq * 32 < C) {
                     const int m = wq * 32 + lane;
                     float t0[16], t1[16], o[16];
-                    umma::tmem_ld16(umma::tmem_addr(tmem, wq * 32, 2 * C + wq * 32), t0);
-                    umma::tmem_ld16(umma::tmem_addr(tmem, wq * 32, 2 * C + wq * 32 + 16), t1);
-                    umma::tmem_ld16(umma::tmem_addr(tmem, wq * 32, 3 * C), o);
+                    umma::tmem_ld16(umma::tmem_addr(tmem, wq * 32, K::RED_COL + wq * 32), t0);
+                    umma::tmem_ld16(umma::tmem_addr(tmem, wq * 32, K::RED_COL + wq * 32 + 16), t1);
+                    umma::tmem_ld16(umma::tmem_addr(tmem, wq * 32, K::RED_COL + C), o);
                     float* dst = kv + (size_t)g * (C * DH) + (size_t)m * DH;
 #pragma unroll
                     for (int sb = 0; sb < 32 / DH; ++sb)
@@ -1110,7 +1114,7 @@ __global__ void __launch_bounds__((4 * KvNT<C>::NT + 2) * 32) kv_state_tc_kernel
                     if (!first) wait_a();                     // previous run's accumulator has been read
                     first = false;
                     for (int k = ks; k < ke; ++k)             // MN-major views: SBO = group stride, LBO = 8 rows
-                        umma::mma_bf16(tmem + 2 * C, umma::smem_desc(a1s + k * 256, 128, P::LBO),
+                        umma::mma_bf16(tmem + K::RED_COL, umma::smem_desc(a1s + k * 256, 128, P::LBO),
                                        umma::smem_desc(a1s + KG * P::LBO + k * 256, 128, P::LBO), idesc_red, k > ks);
                     umma::commit(&bars.acc_ready);
                     ks = ke;
@@ -1139,7 +1143,7 @@ static int run_kv_state_tc(const char* name, const Src& src, int S, int groups, 
     }
     const int64_t ntiles = ((int64_t)groups * S_pad + 127) / 128;
     CFP_REQUIRE((int64_t)groups * S_pad < ((int64_t)1 << 31), "%s: %lld padded rows exceed the 32-bit row index", name, (long long)groups * S_pad);
-    const int per_sm = C >= 128 ? 1 : (C == 64 ? 2 : 4);
+    const int per_sm = C >= 128 ? 1 : (C == 64 ? 3 : 5);          // shared memory: 169 / 70 / 45 KB per CTA
     const int grid = (int)(ntiles < 148 * per_sm ? ntiles : 148 * per_sm);
     if (S_pad == 16 && NH == 4) {                     // hist2image zones (dh = C/4 is a multiple of 8)
         auto k = kv_state_tc_kernel<C, NH, true, Src, (NH == 4)>;
