@@ -41,7 +41,7 @@ __device__ __forceinline__ unsigned long long dbg_now() { unsigned long long t; 
 
 template <int C, int TCOLS> struct ConvTC {
     static constexpr int T = TCOLS / C;               // M-tiles per CTA: T*C = TCOLS TMEM columns (256 or 128)
-    static constexpr int NSLOT = C >= 128 ? 2 : 3;    // weight ring depth (measured: 9 / 4 slots for C = 32 / 64 cost more occupancy than they buy)
+    static constexpr int NSLOT = C >= 128 ? 2 : 3;    // weight ring depth (measured: 2 slots and 9 / 4 slots change nothing or cost occupancy)
     static constexpr int SLOT_BYTES = C * C * 2;      // one [C x C] bf16 block
     static constexpr int KG = C / 8;                  // 16-byte channel groups per source
 };
