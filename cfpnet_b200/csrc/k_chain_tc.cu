@@ -1346,7 +1346,11 @@ static int run_sr_conv_tc(const void* feat0, float* sr_tok, int B, int H, int W,
     cudaError_t e = cudaMemsetAsync(sr_tok, 0, (size_t)rows * C * sizeof(float), st);
     if (e != cudaSuccess) return fail("cudaMemsetAsync(sr accumulator): %s", cudaGetErrorString(e));
     const int tiles = (int)((rows + 127) / 128), ntap = ws * ws;
-    int splits = (2 * 148 + tiles - 1) / tiles;                 // ~2 CTAs per SM
+    // split the taps so that the grid is ONE wave of co-resident CTAs (shared memory: 3 / 2 / 1 CTAs per SM at C = 32 / 64 /
+    // 128): a second, partial wave of tap slices costs a whole slice latency
+    constexpr int per_sm = C >= 128 ? 1 : (C == 64 ? 2 : 3);
+    int splits = (148 * per_sm) / tiles;
+    if (splits < 1) splits = 1;
     if (splits > ntap) splits = ntap;
     const int taps_per_cta = (ntap + splits - 1) / splits;
     splits = (ntap + taps_per_cta - 1) / taps_per_cta;
