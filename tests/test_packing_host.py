@@ -83,7 +83,7 @@ def test_mlp_fold_reproduces_layernorm_mlp(C):
         out += a1 @ w2.t()
     with torch.no_grad():
         ln = F.layer_norm(y, (C,), blk.norm.weight.double(), blk.norm.bias.double(), eps=1e-6)
-    F.gelu(F.linear(ln, blk.pwconv1.weight.double(), blk.pwconv1.bias.double())),
+        ref = F.linear(F.gelu(F.linear(ln, blk.pwconv1.weight.double(), blk.pwconv1.bias.double())),
                        blk.pwconv2.weight.double(), blk.pwconv2.bias.double())
     assert float((out - ref).norm() / ref.norm()) <= 1e-2          # bf16 / fp16 weight rounding only
 
