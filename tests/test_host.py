@@ -164,3 +164,24 @@ def test_synthetic_inputs_are_deterministic():
     assert torch.equal(a["mask"], b["mask"])
     assert (a["hist_data"][~a["mask"]] == 0).all()
     assert 0.6 < a["mask"].float().mean() < 0.95
+
+
+def test_fastdiv_multiply_high_formula_is_exact():
+    """providers.cuh: FastDiv::div(n) = umul64hi(n, ~0ull / d + 1) for 0 <= n < 2^32 - the kernels' only division.
+    Checked against Python integers on the divisors the path uses (window / zone / frame sizes) and random ones."""
+    import random
+    rng = random.Random(0)
+    divisors = [1, 2, 3, 9, 16, 36, 48, 81, 96, 136, 138, 144, 308, 576, 884, 1232, 2304, 3536, 4928, 9216, 14144] + \
+               [rng.randrange(1, 1 << 20) for _ in range(200)]
+    for d in divisors:
+        m = ((1 << 64) - 1) // d + 1 if d > 1 else 0
+        ns = [0, 1, d - 1, d, d + 1, 2 * d - 1, (1 << 32) - 1, (1 << 31), (1 << 31) - 1] + [rng.randrange(0, 1 << 32) for _ in range(300)]
+        for n in ns:
+            n &= (1 << 32) - 1
+            q = n if d == 1 else (n * m) >> 64
+            assert q == n // d, (n, d)
+    # conv3x3_tc's 32-bit magic: umulhi(i, ceil(2^32 / WP)) == i / WP whenever i * WP < 2^32
+    for WP in (36, 70, 138, 162, 642):
+        magic = ((1 << 32) + WP - 1) // WP
+        for i in list(range(0, 5000)) + [rng.randrange(0, (1 << 32) // WP) for _ in range(2000)]:
+            assert (i * magic) >> 32 == i // WP, (i, WP)
