@@ -26,7 +26,9 @@ GEOMETRIES = {
     "G416": (416, 544, 48),
     "G480": (480, 640, 56),      # L3 takes the bilinear-resize branch
     "G480pad": (480, 640, 64),   # zones reach outside the image: pad_mask path
+    "G416z6": (416, 544, 64),    # 6x6 zones of 64 px: the reference's training layout (--train_zone_num 6)
 }
+ZONE_NUM = {"G416z6": 6}         # zones per side where it is not 8
 # level -> (C, downscale, max_resolution, large_kernel)   (decoder.py:82-94)
 LEVELS = {
     3: (128, 16, (30, 40), 7),
@@ -62,10 +64,11 @@ def level_hw(geometry: str, level: int) -> Tuple[int, int]:
 
 
 def make_inputs(geometry: str, batch: int, seed: int = 1, levels: Sequence[int] = (3, 2, 1),
-                dtype=torch.float32, zone_num: int = 8, p_valid: float = 0.8) -> dict:
+                dtype=torch.float32, zone_num: int | None = None, p_valid: float = 0.8) -> dict:
     """One synthetic batch: ``x{level}`` [B,C,h,w], ``hist_data`` [B,Z,16],
     ``mask`` [B,Z] bool, ``rect_data`` [B,Z,4], ``patch_info`` (collated)."""
     img_h, img_w, zone_px = GEOMETRIES[geometry]
+    zone_num = ZONE_NUM.get(geometry, 8) if zone_num is None else zone_num
     Z = zone_num * zone_num
     out = {}
     for lv in levels:

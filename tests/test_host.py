@@ -11,7 +11,9 @@ import torch
 import cfpnet_b200
 from cfpnet_b200 import _lib, geometry, synth
 from cfpnet_b200.config import args
-from helpers import FUSION_CASES, FusionCase, ref_keys
+from helpers import FUSION_CASES as _BASE_CASES, FUSION_CASES_Z6, FusionCase, ref_keys
+
+FUSION_CASES = _BASE_CASES + FUSION_CASES_Z6
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 

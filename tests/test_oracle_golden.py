@@ -8,7 +8,9 @@ import pytest
 import torch
 
 from cfpnet_b200 import synth
-from helpers import FUSION_CASES, FusionCase, GOLDEN, ref_keys, rel_l2
+from helpers import FUSION_CASES as _BASE_CASES, FUSION_CASES_Z6, FusionCase, GOLDEN, ref_keys, rel_l2
+
+FUSION_CASES = _BASE_CASES + FUSION_CASES_Z6
 from oracle import cfp_oracle as O
 
 

@@ -135,7 +135,7 @@ def fusion_case(tag, geometry, level, batch, layers, change_embedding=True, no_s
     rec["geo_vals"] = np.array([cap[k] for k in GEO_KEYS], dtype=np.int64)
     B, H, W = out.shape[0], out.shape[2], out.shape[3]
     zm = channel_const(cap["zone_mask"], C).reshape(B, H * W)
-    hm = channel_const(cap["hist_mask"], C).reshape(B * 64, cap["p1"] * cap["p2"])
+    hm = channel_const(cap["hist_mask"], C).reshape(B * cap["zone_num"] ** 2, cap["p1"] * cap["p2"])
     pm = channel_const(cap["pad_mask"], C).reshape(B, cap["tzh"], cap["tzw"])
     rec["zone_mask_bits"], rec["zone_mask_shape"] = np.packbits(zm), np.array(zm.shape)
     rec["hist_mask_bits"], rec["hist_mask_shape"] = np.packbits(hm), np.array(hm.shape)
@@ -177,3 +177,5 @@ if __name__ == "__main__":
     fusion_case("G416_L3_B1_baseline", "G416", 3, 1, BL)
     fusion_case("G416_L3_B1_noskip", "G416", 3, 1, C1, no_skip_inside=True)
     fusion_case("G416_L3_B1_keepemb", "G416", 3, 1, C1, change_embedding=False)
+    fusion_case("G416z6_L3_B2", "G416z6", 3, 2, C1)      # 6x6 zones of 64 px: the reference's training layout
+    fusion_case("G416z6_L2_B1", "G416z6", 2, 1, C1)
