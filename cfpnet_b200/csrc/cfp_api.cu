@@ -113,8 +113,14 @@ extern "C" {
 CFP_API int cfp_version(void) { return CFP_ABI_VERSION; }
 CFP_API const char* cfp_last_error(void) { return tls_error().msg; }
 
+// One workspace serves every entry point of a level.  cfp_twins_fwd / cfp_lkpm_fwd take no geometry and lay the
+// workspace out for the default 64 zones, cfp_d2i_fwd / cfp_dapm_fwd for zone_num^2: the size handed out covers both
+// (with fewer than 64 zones - the reference's 6x6 training layout - the geometry-less layout is the larger one and
+// those two calls used to refuse the workspace).
 CFP_API size_t cfp_workspace_bytes(int B, int H, int W, int C, int ws, int large_kernel, int dtype, const cfp_geom* g) {
-    return ws_layout(B, H, W, C, ws, large_kernel, dtype, g).total;
+    const size_t with_g = ws_layout(B, H, W, C, ws, large_kernel, dtype, g).total;
+    const size_t without = ws_layout(B, H, W, C, ws, large_kernel, dtype, nullptr).total;
+    return with_g > without ? with_g : without;
 }
 
 CFP_API int cfp_hist_encoder_fwd(const float* hist, void* out32, void* out64, void* out128, int64_t rows,

@@ -126,7 +126,9 @@ CFP_API int cfp_version(void);
 CFP_API const char *cfp_last_error(void);
 
 /* Scratch bytes (fp32 attention state + token scratch) one fusion call needs;
- * the caller allocates it (torch.empty) and passes it to the layer calls. */
+ * the caller allocates it (torch.empty) and passes it to the layer calls.  The
+ * size covers every entry point of the level: those that take the geometry
+ * (zone_num^2 zones) and those that do not (laid out for 64 zones). */
 CFP_API size_t cfp_workspace_bytes(int B, int H, int W, int C, int ws, int large_kernel, int dtype,
                                    const cfp_geom *g);
 

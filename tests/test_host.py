@@ -54,6 +54,58 @@ def test_workspace_bytes_is_pure_host_arithmetic(lib):
     assert 0 < small < big and half < big
 
 
+def _centred_geom(zn, p, H, W):
+    t = zn * p
+    y0, x0 = (H - t) // 2, (W - t) // 2
+    return _lib.CfpGeom(zone_num=zn, p1=p, p2=p, sy_wo=y0, sx_wo=x0, ey_wo=y0 + t, ex_wo=x0 + t, tzh=t, tzw=t,
+                        ry0=y0, ry1=y0 + t, rx0=x0, rx1=x0 + t)
+
+
+@pytest.mark.parametrize("zn,p", [(8, 3), (6, 4), (4, 6), (1, 24), (12, 2)])
+@pytest.mark.parametrize("dtype", [_lib.CFP_F32, _lib.CFP_BF16])
+def test_workspace_covers_every_entry_point(lib, zn, p, dtype):
+    """One workspace serves all layer calls of a level.  cfp_twins_fwd / cfp_lkpm_fwd get no geometry and lay it out
+    for 64 zones: with the reference's 6x6 training layout the size computed from the geometry alone was smaller and
+    both calls refused it (the round-1 6x6 failure).  Pure host arithmetic - no device work."""
+    B, H, W, C, ws, lk = 2, 26, 34, 128, 6, 7
+    g = _centred_geom(zn, p, H, W)
+    n = lib.cfp_workspace_bytes(B, H, W, C, ws, lk, dtype, ctypes.byref(g))
+    assert n >= lib.cfp_workspace_bytes(B, H, W, C, ws, lk, dtype, None)        # twins / lkpm layouts (subsets of it)
+    assert n >= lib.cfp_workspace_bytes(B, H, W, C, ws, 0, dtype, None)
+    assert n >= lib.cfp_workspace_bytes(B, H, W, C, 0, lk, dtype, None)
+    if zn <= 8:
+        assert n == lib.cfp_workspace_bytes(B, H, W, C, ws, lk, dtype, ctypes.byref(_centred_geom(8, 3, H, W)))
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="calls the layer entry points with fake device pointers: only "
+                                                      "safe where the first launch fails (no CUDA driver)")
+@pytest.mark.parametrize("zn,p", [(8, 3), (6, 4)])
+@pytest.mark.parametrize("dtype", [_lib.CFP_F32, _lib.CFP_BF16])
+def test_layer_calls_accept_the_advertised_workspace(lib, zn, p, dtype):
+    """Argument validation of the layer calls happens before any CUDA call: with the size cfp_workspace_bytes hands out
+    none of them may answer 'workspace too small' (they go on and fail at the first launch - there is no GPU here)."""
+    B, H, W, C, ws, lk = 2, 26, 34, 128, 6, 7
+    g = _centred_geom(zn, p, H, W)
+    n = lib.cfp_workspace_bytes(B, H, W, C, ws, lk, dtype, ctypes.byref(g))
+    fake = ctypes.c_void_p(0x1000)
+    tw, lkw, dw, lw = _lib.CfpTwinsW(), _lib.CfpLkpmW(), _lib.CfpDapmW(), _lib.CfpLoftrW()
+    tw.ws, lkw.ksize = ws, lk
+    calls = {
+        "twins": lambda: lib.cfp_twins_fwd(fake, B, H, W, C, ctypes.byref(tw), fake, n, dtype, None),
+        "lkpm": lambda: lib.cfp_lkpm_fwd(fake, B, H, W, C, ctypes.byref(lkw), fake, n, dtype, None),
+        "dapm": lambda: lib.cfp_dapm_fwd(fake, B, H, W, C, ctypes.byref(g), ctypes.byref(dw), fake, n, dtype, None),
+        "d2i": lambda: lib.cfp_d2i_fwd(fake, fake, fake, fake, fake, B, H, W, C, 16, ctypes.byref(g), ctypes.byref(lw),
+                                       0, fake, n, dtype, None),
+    }
+    for name, fn in calls.items():
+        assert fn() != 0, name                                     # no device: the call cannot succeed ...
+        assert b"workspace too small" not in lib.cfp_last_error(), (name, lib.cfp_last_error())   # ... but not for this
+    # and one byte less than the geometry-less layout needs is still refused, with the sizes in the message
+    assert lib.cfp_lkpm_fwd(fake, B, H, W, C, ctypes.byref(lkw), fake,
+                            lib.cfp_workspace_bytes(B, H, W, C, 0, lk, dtype, None) - 1, dtype, None) != 0
+    assert b"workspace too small" in lib.cfp_last_error()
+
+
 def test_rejected_call_sets_thread_local_message(lib):
     rc = lib.cfp_lkpm_fwd(None, 1, 8, 8, 48, None, None, 0, 0, None)
     assert rc != 0 and b"null" in lib.cfp_last_error().lower()
