@@ -12,7 +12,11 @@ Parity pinning: the reference has no tests or golden vectors of its own
 (SURVEY.md §4), so this restatement is pinned against outputs of the reference
 modules themselves, imported in the build container and stored under
 ``tests/golden/`` by ``tools/make_golden.py`` (committed).  ``tests/test_oracle_golden.py``
-checks every function here against those fixtures.
+checks every function here against those fixtures.  TRAIN mode (BatchNorm batch
+statistics, ``bn_stats=`` dict; gradients = autograd over this file) is pinned the
+same way on one forward + backward of the reference modules in ``.train()`` mode
+(``tools/make_golden_train.py`` -> ``tests/golden/train_*.npz``,
+``tests/test_oracle_train_golden.py``).
 
 Every function cites the reference file:line it follows (paths relative to the
 reference root).  All functions are dtype-agnostic: run them in float32 for
@@ -45,6 +49,10 @@ class _Sub(Mapping):
 
     def __getitem__(self, k):
         return self.sd[self.prefix + k]
+
+    @property
+    def full_prefix(self):
+        return getattr(self.sd, "full_prefix", "") + self.prefix
 
     def __iter__(self):
         n = len(self.prefix)
@@ -158,15 +166,38 @@ def zone_masks(g: Mapping[str, int], mask: Tensor, B: int, H: int, W: int, D: in
 # --------------------------------------------------------------------------
 # a1: histogram encoder
 # --------------------------------------------------------------------------
-def _bn_eval(x: Tensor, p: Mapping, name: str, dim: int) -> Tensor:
+BN_MOMENTUM = 0.1      # nn.BatchNorm{1,2}d default
+
+
+def _bn(x: Tensor, p: Mapping, name: str, dim: int, bn_stats: Optional[dict] = None) -> Tensor:
+    """nn.BatchNorm{1,2}d over dim ``dim``.  ``bn_stats is None``: eval mode (running statistics).  A dict: TRAIN mode
+    (``model.train()``, train.py:75) - normalise with the batch mean / biased variance over every other dim and record
+    the module's updated buffers under its full state_dict name: running = (1 - 0.1) * running + 0.1 * batch, with the
+    UNBIASED batch variance, ``num_batches_tracked + 1`` (torch semantics; the reference uses the module defaults)."""
     shape = [1] * x.dim()
     shape[dim] = -1
-    inv = torch.rsqrt(p[name + ".running_var"].to(x.dtype) + BN_EPS)
-    return ((x - p[name + ".running_mean"].to(x.dtype).view(shape)) * (inv * p[name + ".weight"].to(x.dtype)).view(shape)
-            + p[name + ".bias"].to(x.dtype).view(shape))
+    w, b = p[name + ".weight"].to(x.dtype).view(shape), p[name + ".bias"].to(x.dtype).view(shape)
+    if bn_stats is None:
+        inv = torch.rsqrt(p[name + ".running_var"].to(x.dtype) + BN_EPS)
+        return (x - p[name + ".running_mean"].to(x.dtype).view(shape)) * (inv.view(shape) * w) + b
+    dims = [d for d in range(x.dim()) if d != dim]
+    n = x.numel() // x.shape[dim]
+    mean = x.mean(dims)
+    var = x.var(dims, unbiased=False)
+    full = getattr(p, "full_prefix", "") + name
+    with torch.no_grad():
+        bn_stats[full + ".running_mean"] = (1 - BN_MOMENTUM) * p[name + ".running_mean"].to(x.dtype) + BN_MOMENTUM * mean
+        bn_stats[full + ".running_var"] = ((1 - BN_MOMENTUM) * p[name + ".running_var"].to(x.dtype)
+                                           + BN_MOMENTUM * var * (n / max(n - 1, 1)))
+        bn_stats[full + ".num_batches_tracked"] = p[name + ".num_batches_tracked"] + 1
+    return (x - mean.view(shape)) * (torch.rsqrt(var + BN_EPS).view(shape) * w) + b
 
 
-def pointnet_block(p: Mapping, x: Tensor) -> Tensor:
+def _bn_eval(x: Tensor, p: Mapping, name: str, dim: int) -> Tensor:
+    return _bn(x, p, name, dim, None)
+
+
+def pointnet_block(p: Mapping, x: Tensor, bn_stats: Optional[dict] = None) -> Tensor:
     """3 x [pointwise conv + BN(eval) + ReLU] on the last dim.
 
     Follows src/models/encoder.py:17-24 (Conv1d k=1 == per-sample linear).
@@ -175,11 +206,11 @@ def pointnet_block(p: Mapping, x: Tensor) -> Tensor:
     for i in (1, 2, 3):
         w = p[f"conv{i}.weight"].to(x.dtype)[:, :, 0]
         x = F.linear(x, w, p[f"conv{i}.bias"].to(x.dtype))
-        x = torch.relu(_bn_eval(x, p, f"bn{i}", x.dim() - 1))
+        x = torch.relu(_bn(x, p, f"bn{i}", x.dim() - 1, bn_stats))
     return x
 
 
-def hist_encoder(sd: Mapping, hist: Tensor) -> List[Tensor]:
+def hist_encoder(sd: Mapping, hist: Tensor, bn_stats: Optional[dict] = None) -> List[Tensor]:
     """``hist``: [B,Z,N] zone depth samples -> 3 token tensors [B,Z,N,{32,64,128}].
 
     Follows src/models/encoder.py:45-50 (the three extractors are chained and
@@ -188,7 +219,7 @@ def hist_encoder(sd: Mapping, hist: Tensor) -> List[Tensor]:
     x = hist.unsqueeze(-1)
     outs = []
     for i in (1, 2, 3):
-        x = pointnet_block(sub(sd, f"hist_extractor{i}.pointnet_encoder."), x)
+        x = pointnet_block(sub(sd, f"hist_extractor{i}.pointnet_encoder."), x, bn_stats)
         outs.append(x)
     return outs
 
@@ -275,7 +306,8 @@ def twins_layer(p: Mapping, x: Tensor, H: int, W: int, ws: int) -> Tensor:
 # --------------------------------------------------------------------------
 # a6: DAPM (direct-attention propagation)
 # --------------------------------------------------------------------------
-def dapm(p: Mapping, feat0: Tensor, g: Mapping[str, int], H: int, W: int, nhead: int = 4) -> Tensor:
+def dapm(p: Mapping, feat0: Tensor, g: Mapping[str, int], H: int, W: int, nhead: int = 4,
+         bn_stats: Optional[dict] = None) -> Tensor:
     """Follows src/models/transformer.py:204-248.  Outside-zone tokens query
     inside-zone tokens (raster order), the message map is zero inside the zone,
     then conv3x3(2C->C) -> BN -> conv3x3(C->C) -> BN (no activation, :242) and a
@@ -293,15 +325,15 @@ def dapm(p: Mapping, feat0: Tensor, g: Mapping[str, int], H: int, W: int, nhead:
     tmp = torch.zeros_like(feat0)
     tmp[:, ~inside] = msg
     m = torch.cat([feat0, tmp], dim=2).transpose(1, 2).reshape(B, 2 * C, H, W)
-    m = _bn_eval(F.conv2d(m, p["conv1.weight"].to(dt), padding=1), p, "bn1", 1)
-    m = _bn_eval(F.conv2d(m, p["conv2.weight"].to(dt), padding=1), p, "bn2", 1)
+    m = _bn(F.conv2d(m, p["conv1.weight"].to(dt), padding=1), p, "bn1", 1, bn_stats)
+    m = _bn(F.conv2d(m, p["conv2.weight"].to(dt), padding=1), p, "bn2", 1, bn_stats)
     return m.reshape(B, C, N).transpose(1, 2) + feat0
 
 
 # --------------------------------------------------------------------------
 # a7: LKPM (large-kernel depthwise propagation)
 # --------------------------------------------------------------------------
-def lkpm(p: Mapping, feat0: Tensor, H: int, W: int) -> Tensor:
+def lkpm(p: Mapping, feat0: Tensor, H: int, W: int, bn_stats: Optional[dict] = None) -> Tensor:
     """Follows src/models/convnext.py:42-58: depthwise kxk (+bias) -> BN ->
     ReLU -> channels-last LayerNorm(eps 1e-6) -> Linear C->4C -> GELU(erf) ->
     Linear 4C->C -> residual.  gamma is None (layer_scale_init_value=0, :28-36);
@@ -312,7 +344,7 @@ def lkpm(p: Mapping, feat0: Tensor, H: int, W: int) -> Tensor:
     k = w.shape[-1]
     m = feat0.transpose(1, 2).reshape(B, C, H, W)
     y = F.conv2d(m, w, p["dwconv2.bias"].to(dt), padding=(k - 1) // 2, groups=C)
-    y = torch.relu(_bn_eval(y, p, "bn1", 1))
+    y = torch.relu(_bn(y, p, "bn1", 1, bn_stats))
     y = y.reshape(B, C, N).transpose(1, 2)
     y = F.layer_norm(y, (C,), p["norm.weight"].to(dt), p["norm.bias"].to(dt), LKPM_LN_EPS)
     y = F.gelu(F.linear(y, p["pwconv1.weight"].to(dt), p["pwconv1.bias"].to(dt)))
@@ -320,9 +352,10 @@ def lkpm(p: Mapping, feat0: Tensor, H: int, W: int) -> Tensor:
     return feat0 + y
 
 
-def combine1(p: Mapping, feat0: Tensor, g, H: int, W: int) -> Tensor:
+def combine1(p: Mapping, feat0: Tensor, g, H: int, W: int, bn_stats: Optional[dict] = None) -> Tensor:
     """transformer.py:261-275: LKPM(DAPM(feat0))"""
-    return lkpm(sub(p, "large_kernel_path."), dapm(sub(p, "transformer_path."), feat0, g, H, W), H, W)
+    return lkpm(sub(p, "large_kernel_path."), dapm(sub(p, "transformer_path."), feat0, g, H, W, bn_stats=bn_stats), H, W,
+                bn_stats)
 
 
 # --------------------------------------------------------------------------
@@ -386,12 +419,15 @@ def draw_posenc_offsets(max_res: Sequence[int], H: int, W: int) -> Tuple[int, in
 def transformer_fusion(sd: Mapping, layer_names: Sequence[str], max_res: Sequence[int],
                        x: Tensor, feat1: Tensor, mask: Tensor, patch_info: dict,
                        offsets: Optional[Tuple[int, int]] = None,
-                       change_embedding: bool = True, no_skip_inside: bool = False) -> Tensor:
+                       change_embedding: bool = True, no_skip_inside: bool = False,
+                       bn_stats: Optional[dict] = None) -> Tensor:
     """Whole ``TransformerFusion.forward`` (src/models/fusion.py:52-188).
 
     ``x`` [B,C,H,W], ``feat1`` [B,Z,S,C], ``mask`` [B,Z] bool -> [B,C,H,W].
     ``offsets`` = (oy, ox) of the positional-encoding crop; drawn from the
-    global CPU RNG exactly like the reference when None.
+    global CPU RNG exactly like the reference when None.  ``bn_stats``: None = eval
+    mode; a dict = train mode (batch statistics, updated buffers recorded in it -
+    see ``_bn``).  Gradients come from autograd over this restatement.
     """
     B, C, H, W = x.shape
     dt = x.dtype
@@ -410,7 +446,7 @@ def transformer_fusion(sd: Mapping, layer_names: Sequence[str], max_res: Sequenc
             feat0 = hist2image(p, feat0, feat0 if change_embedding else emb0, ztok, mask, g, H, W,
                                no_skip_inside)
         elif name == "combine1":
-            feat0 = combine1(p, feat0, g, H, W)
+            feat0 = combine1(p, feat0, g, H, W, bn_stats)
         else:
             raise NotImplementedError(name)
     return feat0.view(B, H, W, C).permute(0, 3, 1, 2).contiguous()
