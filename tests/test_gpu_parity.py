@@ -92,7 +92,8 @@ def test_hist_encoder_ragged_rows(dtype, tol):
 
 
 # ------------------------------------------------------------------ a2/a3
-@pytest.mark.parametrize("tag", ["G416_L3_B2", "G480_L3_B1", "G480pad_L3_B1", "G480pad_L2_B1", "G416_L1_B1"])
+@pytest.mark.parametrize("tag", ["G416_L3_B2", "G480_L3_B1", "G480pad_L3_B1", "G480pad_L2_B1", "G416_L1_B1"]
+                         + [pytest.param(t, marks=_Z6_MARKS) for t in FUSION_CASES_Z6])
 def test_masks_bit_exact(tag):
     case = FusionCase(tag)
     inp = case.inputs()
@@ -102,7 +103,7 @@ def test_masks_bit_exact(tag):
     B, P = case.batch, g.p1 * g.p2
     mask = inp["mask"].to(DEV, torch.uint8).contiguous()
     zm = torch.empty(B, H * W, dtype=torch.uint8, device=DEV)
-    hm = torch.empty(B * 64, P, dtype=torch.uint8, device=DEV)
+    hm = torch.empty(B * g.zone_num ** 2, P, dtype=torch.uint8, device=DEV)
     pm = torch.empty(B, g.tzh, g.tzw, dtype=torch.uint8, device=DEV)
     _lib.call("cfp_zone_masks", mask.data_ptr(), zm.data_ptr(), hm.data_ptr(), pm.data_ptr(), B, H, W,
               ctypes.byref(cg), _lib.stream_ptr())

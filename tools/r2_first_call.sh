@@ -1,0 +1,15 @@
+#!/bin/bash
+# First GPU call of round 2 (nothing of this could be run in round 1: the GPU budget was spent).
+#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/r2_first_call.sh'
+# 1. the 6x6-zone cases as HARD failures (round-1 fix of cfp_workspace_bytes, confirmed only on the CPU);
+# 2. the whole GPU suite (the 6x6 cases run last, non-strict xfail: XPASS = fixed);
+# 3. the default bench line;
+# Everything lands in gpurun_out/ so it comes back.
+mkdir -p gpurun_out
+CFP_TEST_Z6=1 timeout 300 python -m pytest tests/test_gpu_parity.py -k z6 -q -x > gpurun_out/r2_z6.log 2>&1
+echo "z6 rc=$?" | tee -a gpurun_out/r2_z6.log
+timeout 600 python -m pytest tests -m gpu -q -x -rxX > gpurun_out/r2_gpu_tests.log 2>&1
+echo "suite rc=$?" | tee -a gpurun_out/r2_gpu_tests.log
+timeout 300 python bench.py > gpurun_out/r2_bench.json 2> gpurun_out/r2_bench.err
+tail -3 gpurun_out/r2_z6.log gpurun_out/r2_gpu_tests.log
+head -c 600 gpurun_out/r2_bench.json
