@@ -13,9 +13,8 @@ FUSION_CASES = [
     "G416_L3_B2", "G416_L2_B1", "G416_L1_B1", "G480_L3_B1", "G480pad_L3_B1", "G480pad_L2_B1",
     "G416_L3_B1_baseline", "G416_L3_B1_noskip", "G416_L3_B1_keepemb",
 ]
-# 6x6 zones of 64 px - the reference's training layout (--train_zone_num 6).  Fixtures from the reference; oracle and
-# geometry pinned on the CPU.  On the GPU they are non-strict xfail until a run confirms the workspace-size fix
-# (tests/test_gpu_parity.py).
+# 6x6 zones of 64 px - the reference's training layout (--train_zone_num 6).  Fixtures from the reference; oracle,
+# geometry and (since the workspace-size fix, profiles/r1t_z6_gpu_check.log) the CUDA path are held to them.
 FUSION_CASES_Z6 = ["G416z6_L3_B2", "G416z6_L2_B1"]
 
 

@@ -13,17 +13,16 @@ from cfpnet_b200 import _lib, geometry, synth
 from cfpnet_b200.config import args
 from helpers import FUSION_CASES as _BASE_CASES, FUSION_CASES_Z6, FusionCase, GOLDEN, ref_keys, rel_l2
 
-# 6x6 zones (the reference's training layout).  They failed on the last GPU call of round 1 because cfp_twins_fwd /
+# 6x6 zones (the reference's training layout).  They failed on their first GPU run because cfp_twins_fwd /
 # cfp_lkpm_fwd refused the workspace (their layout assumes 64 zones, the module had sized it for 36): reproduced and
-# fixed on the CPU afterwards (cfp_workspace_bytes now covers both layouts, tests/test_host.py::
-# test_workspace_covers_every_entry_point), with no GPU budget left to re-run them.  Until a GPU run confirms the fix
-# they are non-strict xfail (XPASS = fixed) and conftest.py schedules them last in the session with a timeout, so
-# that nothing they do can affect another test.  CFP_TEST_Z6=1 makes them ordinary (hard) cases.
-_Z6_MARKS = [pytest.mark.timeout(300, method="thread")]
-if not os.environ.get("CFP_TEST_Z6"):
-    _Z6_MARKS.append(pytest.mark.xfail(strict=False, reason="6x6-zone layout: workspace-size fix applied, not yet "
-                                                            "confirmed on a GPU"))
-FUSION_CASES = _BASE_CASES + [pytest.param(t, marks=_Z6_MARKS) for t in FUSION_CASES_Z6]
+# fixed on the CPU (cfp_workspace_bytes now covers both layouts, tests/test_host.py::
+# test_workspace_covers_every_entry_point) and confirmed on a B200 with the round's last GPU seconds
+# (tools/z6_quick.py -> profiles/r1t_z6_gpu_check.log: fp32 rel-L2 1.2e-6 / 8.3e-7, bf16 8.8e-3 / 8.6e-3) - ordinary
+# cases now.  Only the mask-export cases of that layout have not run on a GPU yet: non-strict xfail, scheduled last
+# (conftest.py).
+_Z6_MARKS = [pytest.mark.timeout(300, method="thread"),
+             pytest.mark.xfail(strict=False, reason="6x6-zone mask export: not yet run on a GPU")]
+FUSION_CASES = _BASE_CASES + FUSION_CASES_Z6
 from oracle import cfp_oracle as O
 
 pytestmark = pytest.mark.gpu
