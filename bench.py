@@ -138,12 +138,14 @@ class ClockSampler(threading.Thread):
 
 # ---------------------------------------------------------------------------------- reference arm
 def oracle_modules():
+    """The CPU arm's weights: shapes from the dump of the REFERENCE modules' own state_dict
+    (tests/golden/state_dict_keys.json) - nothing of the product (modules, kernels, library) is on this path."""
     from oracle import cfp_oracle as O
-    from cfpnet_b200 import FusionPath
-    path = FusionPath(synth.COMBINE1_LAYERS)
-    sds = {"hist_encoder": synth.synthetic_state_dict({k: v.shape for k, v in path.hist_encoder.state_dict().items()}, 0)}
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests", "golden", "state_dict_keys.json")) as fh:
+        keys = json.load(fh)
+    sds = {"hist_encoder": synth.synthetic_state_dict(keys["hist_encoder"], 0)}
     for lv, name in ((3, "cross_atten3"), (2, "cross_atten2"), (1, "cross_atten1")):
-        sds[name] = synth.synthetic_state_dict({k: v.shape for k, v in getattr(path, name).state_dict().items()}, lv)
+        sds[name] = synth.synthetic_state_dict(keys[f"fusion_combine1_L{lv}"], lv)
     return O, sds
 
 
