@@ -379,7 +379,7 @@ def run_cfp(a):
                     "hbm_peak_GBps": peaks["hbm_gbs"], "bf16_peak_TFLOPs": peaks["bf16_tflops_sustained"]}
     if prof:
         line["roofline"], line["kernels"] = roofline_from_profile(prof, a.steps, B, es, peaks)
-    if not a.no_cpu:
+    if not a.no_cpu and world == 1:          # the CPU baseline is reported at N = 1 only (rank 0's host cores)
         cores = os.cpu_count() or 1
         t = time_cpu_frames(1, 10, 3)
         med = statistics.median(t)
