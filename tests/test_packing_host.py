@@ -103,3 +103,111 @@ def test_hist_encoder_tc_blocks_decode_to_the_folded_stages():
 
 def ctypes_ptr_ok(w):
     return bool(w.tc) and all(bool(w.w_t[i]) and bool(w.b[i]) for i in range(9))
+
+
+# ------------------------------------------------------------------ DAPM 3x3 convs, LoFTR chain, GSA sub-sampling conv
+def _loaded(mod, seed):
+    mod.load_state_dict(synth.synthetic_state_dict({n: v.shape for n, v in mod.state_dict().items()}, seed=seed))
+    return mod.eval()
+
+
+@pytest.mark.parametrize("C", [32, 64])
+def test_dapm_conv_blocks_reproduce_conv_bn(C):
+    """conv{1,2}_pk: one [Cout x Cout] block per (source, tap), eval-mode BN scale folded into the weights, shift
+    added by the epilogue (k_conv_tc.cu walks source-major, tap = ky*3+kx, over the zero-padded raster) - and the
+    fp32 engine's [(tap, cin)][Cout] layout - both against conv2d + batch_norm."""
+    m = _loaded(cfpnet_b200.layers.LoFTREncoderLayer_newcross9(C, 4), seed=5).double()
+    keep = []
+    m.pack(keep)
+    attn, convs = keep[:4], keep[4:]
+    assert len(convs) == 6
+    H, W, B = 7, 9, 2
+    g = torch.Generator().manual_seed(0)
+    for i, (conv, bn, cin) in enumerate(((m.conv1, m.bn1, 2 * C), (m.conv2, m.bn2, C))):
+        wt, shift, pk = convs[3 * i:3 * i + 3]
+        x = torch.randn(B, cin, H, W, generator=g, dtype=torch.float64)
+        want = F.batch_norm(F.conv2d(x, conv.weight, padding=1), bn.running_mean, bn.running_var, bn.weight, bn.bias,
+                            False, 0.0, bn.eps)
+        xp = F.pad(x, (1, 1, 1, 1))
+        # tensor-core blocks (bf16 storage: decode, then compare at bf16 weight precision)
+        assert pk.shape[0] == (cin // C) * 9 and pk.dtype == torch.bfloat16
+        got = torch.zeros(B, C, H, W, dtype=torch.float64)
+        exact = torch.zeros_like(got)
+        scale, _ = fold_bn(bn)
+        for s in range(cin // C):
+            for ky in range(3):
+                for kx in range(3):
+                    blk = from_umma(pk[s * 9 + ky * 3 + kx].reshape(-1), C, C).double()        # [Cout, K = C inputs of source s]
+                    tap = xp[:, s * C:(s + 1) * C, ky:ky + H, kx:kx + W]
+                    got += torch.einsum("ok,bkhw->bohw", blk, tap)
+                    exact += torch.einsum("ok,bkhw->bohw", conv.weight[:, s * C:(s + 1) * C, ky, kx] * scale[:, None].double(), tap)
+        got += shift.double().view(1, C, 1, 1)
+        exact += shift.double().view(1, C, 1, 1)
+        assert (exact - want).abs().max() <= 1e-5 * want.abs().max()               # fold is exact (fp32 scale / shift)
+        assert (got - want).norm() / want.norm() <= 4e-3                           # + bf16 rounding of the weights
+        # fp32 engine layout: row (tap*cin + c) of wt, column = output channel
+        got32 = torch.zeros(B, C, H, W, dtype=torch.float64)
+        for ky in range(3):
+            for kx in range(3):
+                rows = wt[(ky * 3 + kx) * cin:(ky * 3 + kx + 1) * cin].double()                # [cin, Cout]
+                got32 += torch.einsum("ko,bkhw->bohw", rows, xp[:, :, ky:ky + H, kx:kx + W])
+        got32 += shift.double().view(1, C, 1, 1)
+        assert (got32 - want).abs().max() <= 1e-5 * want.abs().max()
+    # the attention half: q block and k | v blocks are the plain projection weights
+    assert torch.equal(from_umma(attn[2].reshape(-1), C, C), m.q_proj.weight.to(torch.bfloat16))
+    assert torch.equal(from_umma(attn[3][1].reshape(-1), C, C), m.v_proj.weight.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("C,nhead", [(32, 4), (64, 8), (128, 8)])
+def test_loftr_chain_blocks_follow_the_consumption_order(C, nhead):
+    """cfp_loftr_w.tc: eight [C x C] blocks in the order the chain consumes them (k_chain_tc.cu): Wq | Wm |
+    W1 quadrants accumulated as  hidden[:, :C] = x B2^T + msg B3^T,  hidden[:, C:] = x B4^T + msg B5^T  |
+    out = hidden[:, :C] B6^T + hidden[:, C:] B7^T.  Emulated in float64 against the nn.Linear layers."""
+    m = _loaded(cfpnet_b200.layers.LoFTREncoderLayer(C, nhead), seed=9)
+    keep = []
+    m.pack(keep)
+    names = ["wq_t", "wkv_t", "wm_t", "w1_t", "w2_t", "ln1_g", "ln1_b", "ln2_g", "ln2_b", "tc", "kv_tc"]
+    t = dict(zip(names, keep))
+    blocks = [from_umma(t["tc"][i].reshape(-1), C, C).double() for i in range(8)]
+    bf = lambda w: w.detach().to(torch.bfloat16).double()      # noqa: E731  (the blocks store bf16)
+    g = torch.Generator().manual_seed(1)
+    x, msg = torch.randn(11, C, generator=g, dtype=torch.float64), torch.randn(11, C, generator=g, dtype=torch.float64)
+    assert torch.allclose(x @ blocks[0].t(), F.linear(x, bf(m.q_proj.weight)))
+    assert torch.allclose(msg @ blocks[1].t(), F.linear(msg, bf(m.merge.weight)))
+    hidden = torch.cat([x @ blocks[2].t() + msg @ blocks[3].t(), x @ blocks[4].t() + msg @ blocks[5].t()], dim=1)
+    assert torch.allclose(hidden, F.linear(torch.cat([x, msg], dim=1), bf(m.mlp[0].weight)))
+    hidden = torch.relu(hidden)
+    out = hidden[:, :C] @ blocks[6].t() + hidden[:, C:] @ blocks[7].t()
+    assert torch.allclose(out, F.linear(hidden, bf(m.mlp[2].weight)))
+    kvb = [from_umma(t["kv_tc"][i].reshape(-1), C, C).double() for i in range(2)]
+    assert torch.allclose(x @ kvb[0].t(), F.linear(x, bf(m.k_proj.weight))) and \
+        torch.allclose(x @ kvb[1].t(), F.linear(x, bf(m.v_proj.weight)))
+    # fp32 engine: [in][out] transposes, k | v side by side
+    assert torch.equal(t["wkv_t"], torch.cat([m.k_proj.weight.t(), m.v_proj.weight.t()], dim=1))
+    assert torch.equal(t["w1_t"], m.mlp[0].weight.t()) and torch.equal(t["w2_t"], m.mlp[2].weight.t())
+
+
+@pytest.mark.parametrize("C,ws", [(32, 12), (128, 6)])
+def test_gsa_subsampling_blocks_reproduce_the_strided_conv(C, ws):
+    """sr_tc: one [C x C] block per tap (dy, dx) of the stride-ws, ws x ws conv (transformer.py:144-147): the kernel
+    accumulates  out[token] = sum_taps x[token*ws + (dy,dx)] B_tap^T  over a split of the taps; sr_t is the fp32
+    engine's [(dy, dx, cin)][Cout] layout."""
+    m = _loaded(cfpnet_b200.layers.TwinsTransformer(C, ws=ws), seed=2)
+    keep = []
+    m.pack(keep)
+    sr_t, sr_b, _, _, sr_tc = keep[-5:]
+    H, W = 2 * ws, 3 * ws
+    x = torch.randn(1, C, H, W, generator=torch.Generator().manual_seed(3), dtype=torch.float64)
+    w64 = m.gsa.sr.weight.detach().double()
+    want = F.conv2d(x, w64, m.gsa.sr.bias.detach().double(), stride=ws)
+    want_bf = F.conv2d(x, w64.to(torch.bfloat16).double(), m.gsa.sr.bias.detach().double(), stride=ws)
+    got = torch.zeros_like(want)
+    got32 = torch.zeros_like(want)
+    for dy in range(ws):
+        for dx in range(ws):
+            tap = x[:, :, dy::ws, dx::ws]                                   # [1, C, H/ws, W/ws]
+            got += torch.einsum("ok,bkhw->bohw", from_umma(sr_tc[dy * ws + dx].reshape(-1), C, C).double(), tap)
+            got32 += torch.einsum("ko,bkhw->bohw", sr_t[(dy * ws + dx) * C:(dy * ws + dx + 1) * C].double(), tap)
+    bias = sr_b.double().view(1, C, 1, 1)
+    assert torch.allclose(got + bias, want_bf, rtol=1e-9, atol=1e-9)
+    assert torch.allclose(got32 + bias, want, rtol=1e-5, atol=1e-5)
