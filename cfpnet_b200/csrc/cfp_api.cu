@@ -235,6 +235,8 @@ CFP_API int cfp_twins_fwd(void* feat0, int B, int H, int W, int C, const cfp_twi
     CFP_REQUIRE(w && workspace, "null pointer");
     CFP_REQUIRE(w->ws > 1, "window size must be > 1 (transformer.py:79)");
     CFP_REQUIRE(C % 8 == 0, "dim %d should be divided by num_heads 8 (transformer.py:81)", C);
+    CFP_REQUIRE(H >= w->ws && W >= w->ws, "%dx%d map smaller than the %dx%d sub-sampling kernel (the reference's sr conv "
+                "fails here too, transformer.py:144)", H, W, w->ws, w->ws);
     WsLayout L = ws_layout(B, H, W, C, w->ws, 0, dtype, nullptr);
     CFP_REQUIRE(workspace_bytes >= L.total, "workspace too small: %zu < %zu", workspace_bytes, L.total);
     return twins(feat0, B, H, W, C, *w, (char*)workspace, L, dtype, (cudaStream_t)stream);

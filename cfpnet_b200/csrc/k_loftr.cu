@@ -208,6 +208,7 @@ template <int C, int NH, class Src>
 static int run_kv_state(const char* name, const Src& src, int groups, const float* wkv_t, float* kv, float* ksum,
                         cudaStream_t st) {
     constexpr int DH = C / NH;
+    CFP_REQUIRE(src.rows < ((int64_t)1 << 31), "%s: %lld rows exceed the 32-bit row index", name, (long long)src.rows);
     cudaError_t e = cudaMemsetAsync(kv, 0, (size_t)groups * (C * DH + C) * sizeof(float), st);
     if (e != cudaSuccess) return fail("cudaMemsetAsync(kv state): %s", cudaGetErrorString(e));
     auto k = kv_state_kernel<C, NH, Src>;
@@ -219,6 +220,7 @@ static int run_kv_state(const char* name, const Src& src, int groups, const floa
 template <int C, int NH, bool kAttnOnly, class Q>
 static int run_query(const char* name, const Q& q, const cfp_loftr_w& w, const float* kv, const float* ksum,
                      cudaStream_t st) {
+    CFP_REQUIRE(q.rows < ((int64_t)1 << 31), "%s: %lld rows exceed the 32-bit row index", name, (long long)q.rows);
     auto k = loftr_query_kernel<C, NH, kAttnOnly, Q>;
     if (int err = set_smem(k, query_smem<C>())) return err;
     const unsigned grid = (unsigned)((q.rows + Tile<C>::BM - 1) / Tile<C>::BM);
@@ -277,7 +279,8 @@ static int dapm_impl(const void* feat0, void* msg_map, int B, int H, int W, cons
             if (int e = run_kv_state<C, 4>("kv_state<dapm>", src, B, w.wkv_t, kv, ksum, st)) return e;
         }
     } else {
-        cudaMemsetAsync(kv, 0, (size_t)B * (C * (C / 4) + C) * sizeof(float), st);
+        cudaError_t e = cudaMemsetAsync(kv, 0, (size_t)B * (C * (C / 4) + C) * sizeof(float), st);
+        if (e != cudaSuccess) return fail("cudaMemsetAsync(kv state): %s", cudaGetErrorString(e));
     }
     if (No == 0) return 0;
     OutsideRows<T> q((const T*)feat0, (T*)msg_map, H, W, C, g.ry0, g.ry1, g.rx0, g.rx1, No, (int64_t)B * No);

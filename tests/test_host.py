@@ -111,6 +111,11 @@ def test_rejected_call_sets_thread_local_message(lib):
     assert rc != 0 and b"null" in lib.cfp_last_error().lower()
     rc = lib.cfp_lkpm_fwd(ctypes.c_void_p(256), 1, 8, 8, 48, None, None, 0, 0, None)
     assert rc != 0 and b"embedding_dim" in lib.cfp_last_error()
+    # a map smaller than the GSA sub-sampling kernel: the reference's strided conv raises, the library refuses
+    tw = _lib.CfpTwinsW()
+    tw.ws = 6
+    rc = lib.cfp_twins_fwd(ctypes.c_void_p(256), 1, 4, 40, 32, ctypes.byref(tw), ctypes.c_void_p(256), 1 << 30, 0, None)
+    assert rc != 0 and b"sub-sampling kernel" in lib.cfp_last_error()
 
 
 @pytest.mark.parametrize("tag", FUSION_CASES)
