@@ -190,3 +190,238 @@ def lkpm_bwd(p: Mapping, feat0: Tensor, H: int, W: int, dout: Tensor) -> Tuple[T
     dy0, g["bn1.weight"], g["bn1.bias"] = bn_train_bwd(y0, p["bn1.weight"], dy1, 1)
     dm, g["dwconv2.weight"], g["dwconv2.bias"] = depthwise_conv_bwd(m, w, dy0)
     return dout + dm.reshape(B, C, N).transpose(1, 2), g
+
+
+# ----------------------------------------------------------------------------------------------
+# Whole layers and the whole TransformerFusion call, TRAIN mode (batch-statistics BN).  Each function recomputes the
+# forward internals it needs from the layer's input (what a fused backward kernel does too) and returns the gradient
+# of the layer input plus {parameter name: gradient} with names relative to the layer's prefix.
+# ----------------------------------------------------------------------------------------------
+from torch.nn.grad import conv2d_input, conv2d_weight  # noqa: E402  (explicit adjoints of conv2d, no autograd graph)
+
+from .cfp_oracle import dapm as _dapm_fwd, hist2image as _h2i_fwd, loftr_layer, lkpm as _lkpm_fwd, lsa as _lsa_fwd  # noqa: E402
+from .cfp_oracle import gsa as _gsa_fwd, sub, twins_window_size, zone_geometry  # noqa: E402
+
+
+def _prefixed(prefix: str, grads: Mapping[str, Tensor]) -> Dict[str, Tensor]:
+    return {prefix + k: v for k, v in grads.items()}
+
+
+def _conv_bn_train(x: Tensor, w: Tensor, p: Mapping, bn: str, stride: int = 1, padding: int = 1):
+    y0 = F.conv2d(x, w, padding=padding, stride=stride)
+    dims = (0, 2, 3)
+    rstd = torch.rsqrt(y0.var(dims, unbiased=False, keepdim=True) + BN_EPS)
+    C = y0.shape[1]
+    return y0, (y0 - y0.mean(dims, keepdim=True)) * rstd * p[bn + ".weight"].view(1, C, 1, 1) + p[bn + ".bias"].view(1, C, 1, 1)
+
+
+def lsa_bwd(p: Mapping, x: Tensor, H: int, W: int, ws: int, dout: Tensor):
+    """LSA (transformer.py:89-116): the window regroup is a permutation of the zero-padded map, its adjoint the inverse
+    permutation followed by the crop; queries and keys are the same tokens, so both gradients land on the windows."""
+    B, N, C = x.shape
+    pb, pr = (ws - H % ws) % ws, (ws - W % ws) % ws
+    Hp, Wp = H + pb, W + pr
+    nh, nw = Hp // ws, Wp // ws
+
+    def to_win(t):
+        t = F.pad(t.view(B, H, W, C), (0, 0, 0, pr, 0, pb))
+        return t.view(B, nh, ws, nw, ws, C).permute(0, 1, 3, 2, 4, 5).reshape(B * nh * nw, ws * ws, C)
+
+    def from_win(t):
+        t = t.view(B, nh, nw, ws, ws, C).permute(0, 1, 3, 2, 4, 5).reshape(B, Hp, Wp, C)
+        return t[:, :H, :W].reshape(B, N, C)
+
+    win = to_win(x)
+    dq, dsrc, g = loftr_layer_bwd(sub(p, "encoder_layer."), win, win, 8, to_win(dout))   # padded output cells: zero cotangent
+    return from_win(dq + dsrc), _prefixed("encoder_layer.", g)
+
+
+def gsa_bwd(p: Mapping, x: Tensor, H: int, W: int, ws: int, dout: Tensor):
+    """GSA (transformer.py:138-150): source = LN(sr(x)); the strided conv's adjoints are conv2d_input / conv2d_weight."""
+    B, N, C = x.shape
+    m = x.transpose(1, 2).reshape(B, C, H, W)
+    s0 = F.conv2d(m, p["sr.weight"], p["sr.bias"], stride=ws)
+    hs, wsz = s0.shape[2], s0.shape[3]
+    s0t = s0.reshape(B, C, -1).transpose(1, 2)
+    s1 = F.layer_norm(s0t, (C,), p["norm.weight"], p["norm.bias"], LN_EPS)
+    dx, ds1, g = loftr_layer_bwd(sub(p, "encoder_layer."), x, s1, 8, dout)
+    grads = _prefixed("encoder_layer.", g)
+    ds0t, grads["norm.weight"], grads["norm.bias"] = layer_norm_bwd(s0t, p["norm.weight"], ds1)
+    ds0 = ds0t.transpose(1, 2).reshape(B, C, hs, wsz)
+    grads["sr.bias"] = ds0.sum(dim=(0, 2, 3))
+    grads["sr.weight"] = conv2d_weight(m, p["sr.weight"].shape, ds0, stride=ws)
+    dm = conv2d_input(m.shape, p["sr.weight"], ds0, stride=ws)
+    return dx + dm.reshape(B, C, N).transpose(1, 2), grads
+
+
+def twins_bwd(p: Mapping, x: Tensor, H: int, W: int, ws: int, dout: Tensor):
+    y = _lsa_fwd(sub(p, "lga."), x, H, W, ws)
+    dy, g2 = gsa_bwd(sub(p, "gsa."), y, H, W, ws, dout)
+    dx, g1 = lsa_bwd(sub(p, "lga."), x, H, W, ws, dy)
+    return dx, {**_prefixed("lga.", g1), **_prefixed("gsa.", g2)}
+
+
+def dapm_bwd(p: Mapping, feat0: Tensor, g: Mapping[str, int], H: int, W: int, dout: Tensor, nhead: int = 4):
+    """DAPM (transformer.py:204-248), train-mode BN: out = feat0 + BN2(conv2(BN1(conv1([feat0 | msg map])))), msg map =
+    attention of the outside tokens over the inside tokens, zero inside the zone rectangle."""
+    B, N, C = feat0.shape
+    inside = torch.zeros(H, W, dtype=torch.bool)
+    inside[g["ry0"]:g["ry1"], g["rx0"]:g["rx1"]] = True
+    inside = inside.reshape(-1)
+    fin, fout = feat0[:, inside], feat0[:, ~inside]
+    Wq, Wk, Wv = p["q_proj.weight"], p["k_proj.weight"], p["v_proj.weight"]
+    q, k, v = fout @ Wq.t(), fin @ Wk.t(), fin @ Wv.t()
+    tmp = torch.zeros_like(feat0)
+    tmp[:, ~inside] = linear_attention(q, k, v, nhead)
+    m0 = torch.cat([feat0, tmp], dim=2).transpose(1, 2).reshape(B, 2 * C, H, W)
+    c1, m1 = _conv_bn_train(m0, p["conv1.weight"], p, "bn1")
+    c2, _ = _conv_bn_train(m1, p["conv2.weight"], p, "bn2")
+    grads: Dict[str, Tensor] = {}
+    dy = dout.transpose(1, 2).reshape(B, C, H, W)
+    dc2, grads["bn2.weight"], grads["bn2.bias"] = bn_train_bwd(c2, p["bn2.weight"], dy, 1)
+    grads["conv2.weight"] = conv2d_weight(m1, p["conv2.weight"].shape, dc2, padding=1)
+    dm1 = conv2d_input(m1.shape, p["conv2.weight"], dc2, padding=1)
+    dc1, grads["bn1.weight"], grads["bn1.bias"] = bn_train_bwd(c1, p["bn1.weight"], dm1, 1)
+    grads["conv1.weight"] = conv2d_weight(m0, p["conv1.weight"].shape, dc1, padding=1)
+    dm0 = conv2d_input(m0.shape, p["conv1.weight"], dc1, padding=1).reshape(B, 2 * C, N).transpose(1, 2)
+    dfeat = dout + dm0[..., :C]
+    dq, dk, dv = linear_attention_bwd(q, k, v, nhead, dm0[..., C:][:, ~inside])       # only outside cells carry a message
+    flat = lambda t: t.reshape(-1, t.shape[-1])          # noqa: E731
+    grads["q_proj.weight"] = flat(dq).t() @ flat(fout)
+    grads["k_proj.weight"] = flat(dk).t() @ flat(fin)
+    grads["v_proj.weight"] = flat(dv).t() @ flat(fin)
+    dfeat = dfeat.clone()
+    dfeat[:, ~inside] += dq @ Wq
+    dfeat[:, inside] += dk @ Wk + dv @ Wv
+    return dfeat, grads
+
+
+def combine1_bwd(p: Mapping, feat0: Tensor, g, H: int, W: int, dout: Tensor):
+    y = _dapm_fwd(sub(p, "transformer_path."), feat0, g, H, W, bn_stats={})
+    dy, g2 = lkpm_bwd(sub(p, "large_kernel_path."), y, H, W, dout)
+    dx, g1 = dapm_bwd(sub(p, "transformer_path."), feat0, g, H, W, dy)
+    return dx, {**_prefixed("transformer_path.", g1), **_prefixed("large_kernel_path.", g2)}
+
+
+def hist2image_bwd(p: Mapping, feat0: Tensor, ztok: Tensor, mask: Tensor, g: Mapping[str, int], H: int, W: int, dout: Tensor):
+    """hist2image (fusion.py:132-157) with change_embedding, without the resize branch (the training layout):
+    out = feat0, and on the zone rectangle  out += mask * loftr(canvas cells, zone tokens)  where the canvas is cut from
+    feat0 itself.  Returns (dfeat0, dztok, grads)."""
+    if g["interpolate"]:
+        raise NotImplementedError("explicit backward is stated for the no-resize branch (training layout) only")
+    B, N, C = feat0.shape
+    zn, p1, p2 = g["zone_num"], g["p1"], g["p2"]
+    top, left = max(-g["sy_wo"], 0), max(-g["sx_wo"], 0)
+    hh, ww = g["ry1"] - g["ry0"], g["rx1"] - g["rx0"]
+    rect = (slice(None), slice(g["ry0"], g["ry1"]), slice(g["rx0"], g["rx1"]))
+    cv = (slice(None), slice(top, top + hh), slice(left, left + ww))
+
+    def to_zone(t_rect):                      # [B,hh,ww,C] (in-image part) -> zero-padded canvas -> [(B zn zn), p1 p2, C]
+        canvas = t_rect.new_zeros(B, zn * p1, zn * p2, C)
+        canvas[cv] = t_rect
+        return canvas.view(B, zn, p1, zn, p2, C).permute(0, 1, 3, 2, 4, 5).reshape(B * zn * zn, p1 * p2, C)
+
+    def from_zone(t):                         # adjoint: back to the in-image rectangle
+        return t.view(B, zn, zn, p1, p2, C).permute(0, 1, 3, 2, 4, 5).reshape(B, zn * p1, zn * p2, C)[cv]
+
+    f = feat0.view(B, H, W, C)
+    xz = to_zone(f[rect])
+    mz = mask.reshape(B * zn * zn, 1, 1).to(feat0.dtype)
+    dt = to_zone(dout.view(B, H, W, C)[rect]) * mz              # rows of invalid zones are zeroed, residual included
+    dxz, dztok, grads = loftr_layer_bwd(p, xz, ztok, 4, dt)
+    dfeat = dout.clone().view(B, H, W, C)
+    dfeat[rect] += from_zone(dxz)
+    return dfeat.view(B, N, C), dztok, grads
+
+
+def pointnet_block_bwd(p: Mapping, x: Tensor, dout: Tensor):
+    """3 x [pointwise linear + train-mode BN + ReLU] (encoder.py:17-24)."""
+    acts = [x]
+    pre = []
+    for i in (1, 2, 3):
+        y0 = F.linear(acts[-1], p[f"conv{i}.weight"][:, :, 0], p[f"conv{i}.bias"])
+        dims = list(range(y0.dim() - 1))
+        y1 = (y0 - y0.mean(dims)) * torch.rsqrt(y0.var(dims, unbiased=False) + BN_EPS) * p[f"bn{i}.weight"] + p[f"bn{i}.bias"]
+        pre.append((y0, y1))
+        acts.append(torch.relu(y1))
+    grads: Dict[str, Tensor] = {}
+    d = dout
+    flat = lambda t: t.reshape(-1, t.shape[-1])          # noqa: E731
+    for i in (3, 2, 1):
+        y0, y1 = pre[i - 1]
+        d = d * (y1 > 0)
+        d, grads[f"bn{i}.weight"], grads[f"bn{i}.bias"] = bn_train_bwd(y0, p[f"bn{i}.weight"], d, y0.dim() - 1)
+        grads[f"conv{i}.bias"] = flat(d).sum(0)
+        grads[f"conv{i}.weight"] = (flat(d).t() @ flat(acts[i - 1])).unsqueeze(-1)
+        d = d @ p[f"conv{i}.weight"][:, :, 0]
+    return d, grads
+
+
+def hist_encoder_bwd(sd: Mapping, hist: Tensor, douts):
+    """Backward of ``cfp_oracle.hist_encoder`` in train mode; ``douts`` = cotangents of the three outputs (None = unused)."""
+    x = hist.unsqueeze(-1)
+    ins = []
+    for i in (1, 2, 3):
+        ins.append(x)
+        x = _pointnet_fwd_train(sub(sd, f"hist_extractor{i}.pointnet_encoder."), x)
+    grads: Dict[str, Tensor] = {}
+    d = None
+    for i in (3, 2, 1):
+        if douts[i - 1] is not None:
+            d = douts[i - 1] if d is None else d + douts[i - 1]
+        if d is None:
+            continue
+        d, g = pointnet_block_bwd(sub(sd, f"hist_extractor{i}.pointnet_encoder."), ins[i - 1], d)
+        grads.update(_prefixed(f"hist_extractor{i}.pointnet_encoder.", g))
+    return d.squeeze(-1), grads
+
+
+def _pointnet_fwd_train(p: Mapping, x: Tensor) -> Tensor:
+    from .cfp_oracle import pointnet_block
+    return pointnet_block(p, x, bn_stats={})
+
+
+def transformer_fusion_bwd(sd: Mapping, layer_names, max_res, x: Tensor, feat1: Tensor, mask: Tensor, patch_info: dict,
+                           offsets, dout: Tensor):
+    """Backward of one ``TransformerFusion`` call in train mode (fusion.py:52-188; change_embedding, no resize branch).
+    Returns (dx [B,C,H,W], dfeat1 [B,Z,S,C], {state_dict name: gradient})."""
+    B, C, H, W = x.shape
+    g = zone_geometry(patch_info, max_res[1], H, W)
+    oy, ox = offsets
+    pos = sd["positional_encodings"].view(max_res[0], max_res[1], C)[oy:oy + H, ox:ox + W]
+    feat = (x.permute(0, 2, 3, 1) + pos).reshape(B, H * W, C)
+    ztok = (feat1 + sd["positional_encodings2"]).reshape(-1, feat1.shape[2], C)
+    ws = twins_window_size(max_res)
+    inputs = []
+    for i, name in enumerate(layer_names):                                   # forward, keeping every layer's input
+        p = sub(sd, f"layers.{i}.")
+        inputs.append(feat)
+        if name == "image":
+            feat = _gsa_fwd(sub(p, "gsa."), _lsa_fwd(sub(p, "lga."), feat, H, W, ws), H, W, ws)
+        elif name == "hist2image":
+            feat = _h2i_fwd(p, feat, feat, ztok, mask, g, H, W)
+        elif name == "combine1":
+            feat = _lkpm_fwd(sub(p, "large_kernel_path."),
+                             _dapm_fwd(sub(p, "transformer_path."), feat, g, H, W, bn_stats={}), H, W, bn_stats={})
+        else:
+            raise NotImplementedError(name)
+    grads: Dict[str, Tensor] = {}
+    d = dout.permute(0, 2, 3, 1).reshape(B, H * W, C)
+    dztok = torch.zeros_like(ztok)
+    for i in reversed(range(len(layer_names))):
+        p, name = sub(sd, f"layers.{i}."), layer_names[i]
+        if name == "image":
+            d, gl = twins_bwd(p, inputs[i], H, W, ws, d)
+        elif name == "hist2image":
+            d, dz, gl = hist2image_bwd(p, inputs[i], ztok, mask, g, H, W, d)
+            dztok = dztok + dz
+        else:
+            d, gl = combine1_bwd(p, inputs[i], g, H, W, d)
+        grads.update(_prefixed(f"layers.{i}.", gl))
+    dmap = d.view(B, H, W, C)
+    dpos = torch.zeros(max_res[0], max_res[1], C, dtype=x.dtype)
+    dpos[oy:oy + H, ox:ox + W] = dmap.sum(0)
+    grads["positional_encodings"] = dpos.view(max_res[0] * max_res[1], C)
+    dfeat1 = dztok.view(feat1.shape)
+    grads["positional_encodings2"] = dfeat1.sum(dim=(0, 1))
+    return dmap.permute(0, 3, 1, 2).contiguous(), dfeat1, grads

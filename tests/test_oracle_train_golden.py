@@ -122,3 +122,48 @@ def test_batchnorm_buffers_after_the_step_match_reference(step):
         else:
             assert int(got) == int(want), full
     assert touched >= 3 * 6            # at least DAPM bn1/bn2 + LKPM bn1 of both combine1 layers... and the encoder's
+
+
+def test_explicit_backward_chain_matches_reference(step):
+    """The closed-form backward of the WHOLE call (oracle/cfp_oracle_bwd.py: posenc, hist2image, DAPM, LKPM, LSA, GSA,
+    histogram encoder - no autograd anywhere) against the gradients the REFERENCE computed in .train() mode."""
+    from oracle import cfp_oracle_bwd as OB
+    z = step["z"]
+    geometry, level, batch, layers = [str(v) for v in z["meta"]]
+    level, batch, layers = int(level), int(batch), tuple(layers.split(","))
+    C, _, max_res, _ = synth.LEVELS[level]
+    sd = {k: (v.double() if v.is_floating_point() else v)
+          for k, v in synth.synthetic_state_dict(ref_keys()[f"fusion_combine1_L{level}"], seed=level).items()}
+    hsd = {k: (v.double() if v.is_floating_point() else v)
+           for k, v in synth.synthetic_state_dict(ref_keys()["hist_encoder"], seed=0).items()}
+    inp = synth.make_inputs(geometry, batch, seed=1, levels=(level,))
+    x, hist = inp[f"x{level}"].double(), inp["hist_data"].double()
+    H, W = x.shape[2], x.shape[3]
+    torch.manual_seed(2)
+    offsets = O.draw_posenc_offsets(max_res, H, W)
+    ct = torch.randn(x.shape, generator=torch.Generator().manual_seed(77), dtype=torch.float64)
+    with torch.no_grad():
+        feats = O.hist_encoder(hsd, hist, bn_stats={})
+        slot = {32: 0, 64: 1, 128: 2}[C]
+        dx, dfeat1, grads = OB.transformer_fusion_bwd(sd, layers, max_res, x, feats[slot], inp["mask"], inp["patch_info"],
+                                                      offsets, ct)
+        douts = [None, None, None]
+        douts[slot] = dfeat1
+        dhist, hgrads = OB.hist_encoder_bwd(hsd, hist, douts)
+    _check_map(z, "grad_x", dx, step["tag"] + " explicit grad_x")
+    assert rel_l2(dhist, torch.from_numpy(z["grad_hist"])) <= TOL
+    checked = 0
+    for i, full in enumerate(str(n) for n in z["param_names"]):
+        scope, name = full.split(".", 1)
+        got = (grads if scope == "fusion" else hgrads).get(name)
+        if not bool(z["param_has_grad"][i]):
+            assert got is None, full                         # never used by the forward: no gradient is produced
+            continue
+        assert got is not None, full
+        norm = float(z["param_grad_norm"][i])
+        tol = RTOL * norm + ATOL
+        assert abs(float(got.norm()) - norm) <= tol, full
+        probe = got.reshape(-1)[_probe_index(full, got.numel())]
+        assert float((probe - torch.from_numpy(z["param_grad_probe"][i])).norm()) <= tol, full
+        checked += 1
+    assert checked == int(z["param_has_grad"].sum())
