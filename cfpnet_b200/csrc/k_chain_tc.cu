@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(320, 1) loftr_query_tc_kernel(Q q, cfp_loftr_w
         for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
             const int tile = 2 * pair + grp;                 // an odd tile count leaves group 1 of the last pair with dead rows
             const int64_t row0 = tile < ntiles ? (int64_t)tile * 128 : q.rows;
-            const int dbg_it = 1 - (pair - (int)blockIdx.x) / (int)gridDim.x;      // marks on the FIRST pair of CTA 5
+            [[maybe_unused]] const int dbg_it = 1 - (pair - (int)blockIdx.x) / (int)gridDim.x;      // marks on the FIRST pair of CTA 5
             CFP_CHAIN_MARK(0, dbg_it);
             const typename S::Row r = S::stage_x(q, row0, tid_g, a0);
             CFP_CHAIN_MARK(1, dbg_it);
@@ -509,7 +509,7 @@ __global__ void __launch_bounds__(128, MonoOcc<C>::CTAS) loftr_query_mono_kernel
     uint32_t kvph = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, base += NB) {
         const int64_t row0 = (int64_t)tile * 128;
-        const int dbg_it = (tile - (int)blockIdx.x) / (int)gridDim.x;
+        [[maybe_unused]] const int dbg_it = (tile - (int)blockIdx.x) / (int)gridDim.x;
         CFP_CHAIN_MARK(0, dbg_it);
         const typename S::Row r = S::stage_x(q, row0, tid, a0);
         CFP_CHAIN_MARK(1, dbg_it);
@@ -952,7 +952,7 @@ __global__ void __launch_bounds__((4 * KvNT<C>::NT + 2) * 32) kv_state_tc_kernel
             const uint32_t myp = row0 + tid;
             const int myg = (int)dSp.div(myp), mys = (int)(myp - (uint32_t)myg * (uint32_t)S_pad);
             const bool real = myp < total && mys < S;
-            const int dbg_it = (tile - (int)blockIdx.x) / (int)gridDim.x;
+            [[maybe_unused]] const int dbg_it = (tile - (int)blockIdx.x) / (int)gridDim.x;
             CFP_CHAIN_MARK(0, dbg_it);
             {
                 const typename Src::R ref = src.locate(real ? (int64_t)myg * S + mys : 0);
