@@ -120,3 +120,4 @@ if __name__ == "__main__":
     C1 = synth.COMBINE1_LAYERS
     train_case("G416z6_L3_B2", "G416z6", 3, 2, C1)      # the reference's training layout: 6x6 zones of 64 px
     train_case("G416_L2_B2", "G416", 2, 2, C1)
+    train_case("G416z6_L1_B1", "G416z6", 1, 1, C1)      # the heavy level: 31x31 depthwise, 12x12 windows
