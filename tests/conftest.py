@@ -14,8 +14,6 @@ def pytest_configure(config):
 
 def pytest_collection_modifyitems(config, items):
     import torch
-    # GPU cases that have not run on a GPU yet (non-strict xfail) go after everything else
-    items.sort(key=lambda it: "gpu" in it.keywords and it.get_closest_marker("xfail") is not None)
     if torch.cuda.is_available():
         return
     skip = pytest.mark.skip(reason="no CUDA device")

@@ -17,11 +17,7 @@ from helpers import FUSION_CASES as _BASE_CASES, FUSION_CASES_Z6, FusionCase, GO
 # cfp_lkpm_fwd refused the workspace (their layout assumes 64 zones, the module had sized it for 36): reproduced and
 # fixed on the CPU (cfp_workspace_bytes now covers both layouts, tests/test_host.py::
 # test_workspace_covers_every_entry_point) and confirmed on a B200 with the round's last GPU seconds
-# (tools/z6_quick.py -> profiles/r1t_z6_gpu_check.log: fp32 rel-L2 1.2e-6 / 8.3e-7, bf16 8.8e-3 / 8.6e-3) - ordinary
-# cases now.  Only the mask-export cases of that layout have not run on a GPU yet: non-strict xfail, scheduled last
-# (conftest.py).
-_Z6_MARKS = [pytest.mark.timeout(300, method="thread"),
-             pytest.mark.xfail(strict=False, reason="6x6-zone mask export: not yet run on a GPU")]
+# (tools/z6_quick.py -> profiles/r1t_z6_gpu_check.log: fp32 rel-L2 1.2e-6 / 8.3e-7, bf16 8.8e-3 / 8.6e-3).
 FUSION_CASES = _BASE_CASES + FUSION_CASES_Z6
 from oracle import cfp_oracle as O
 
@@ -91,8 +87,7 @@ def test_hist_encoder_ragged_rows(dtype, tol):
 
 
 # ------------------------------------------------------------------ a2/a3
-@pytest.mark.parametrize("tag", ["G416_L3_B2", "G480_L3_B1", "G480pad_L3_B1", "G480pad_L2_B1", "G416_L1_B1"]
-                         + [pytest.param(t, marks=_Z6_MARKS) for t in FUSION_CASES_Z6])
+@pytest.mark.parametrize("tag", ["G416_L3_B2", "G480_L3_B1", "G480pad_L3_B1", "G480pad_L2_B1", "G416_L1_B1"] + FUSION_CASES_Z6)
 def test_masks_bit_exact(tag):
     case = FusionCase(tag)
     inp = case.inputs()

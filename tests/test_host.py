@@ -244,3 +244,29 @@ def test_fastdiv_multiply_high_formula_is_exact():
         magic = ((1 << 32) + WP - 1) // WP
         for i in list(range(0, 5000)) + [rng.randrange(0, (1 << 32) // WP) for _ in range(2000)]:
             assert (i * magic) >> 32 == i // WP, (i, WP)
+
+
+@pytest.mark.parametrize("tag", FUSION_CASES)
+def test_zone_masks_kernel_formula_matches_reference_masks(tag):
+    """csrc/k_layout.cu::zone_masks_kernel restated index by index in numpy (zone_mask: rectangle test per cell;
+    hist_mask[j] = mask[j // (p1 p2)]; pad_mask: in-image part of the canvas) against the masks the reference
+    materialised - the kernel's arithmetic checked without a GPU, for the 8x8 and the 6x6 zone layouts."""
+    case = FusionCase(tag)
+    inp = case.inputs()
+    H, W = synth.level_hw(case.geometry, case.level)
+    g = geometry.zone_geometry(inp["patch_info"], case.max_res[1], H, W)
+    B, Z, P = case.batch, g.zone_num ** 2, g.p1 * g.p2
+    n = np.arange(B * H * W) % (H * W)
+    y, x = n // W, n % W
+    zone = (y >= g.ry0) & (y < g.ry1) & (x >= g.rx0) & (x < g.rx1)
+    hist = inp["mask"].numpy().reshape(-1).astype(bool)[np.arange(B * Z * P) // P]
+    j = np.arange(B * g.tzh * g.tzw)
+    cx, cy = j % g.tzw, (j // g.tzw) % g.tzh
+    pad = np.ones_like(j, dtype=bool)
+    if g.pad_h > 0 or g.pad_w > 0:
+        top, left = max(-g.sy_wo, 0), max(-g.sx_wo, 0)
+        bot, right = max(g.ey_wo - H, 0), max(g.ex_wo - W, 0)
+        pad = ~((cy < top) | (cy >= g.tzh - bot) | (cx < left) | (cx >= g.tzw - right))
+    assert np.array_equal(zone.reshape(B, H * W), case.mask_bits("zone_mask"))
+    assert np.array_equal(hist.reshape(B * Z, P), case.mask_bits("hist_mask"))
+    assert np.array_equal(pad.reshape(B, g.tzh, g.tzw), case.mask_bits("pad_mask"))

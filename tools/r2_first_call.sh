@@ -2,7 +2,7 @@
 # First GPU call of round 2 (nothing of this could be run in round 1: the GPU budget was spent).
 #   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/r2_first_call.sh'
 # 1. the 6x6-zone cases alone (fusion cases confirmed by tools/z6_quick.py at the end of round 1; the mask-export
-#    cases never ran on a GPU and are non-strict xfail: XPASS = fine);
+#    cases of that layout run here for the first time);
 # 2. the whole GPU suite;
 # 3. the default bench line;
 # Everything lands in gpurun_out/ so it comes back.
