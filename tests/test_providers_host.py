@@ -159,3 +159,51 @@ def test_lsa_window_rows(level, geom):
     t = F.pad(idx, (0, 0, 0, pr, 0, pb))
     want = t.view(1, nwy, ws, nwx, ws, 1).permute(0, 1, 3, 2, 4, 5).reshape(-1).numpy().astype(np.int64) - 1
     assert np.array_equal(tok, want)
+
+
+@pytest.mark.parametrize("H,W", [(26, 34), (52, 68), (104, 136), (30, 40), (120, 160), (7, 5)])
+@pytest.mark.parametrize("T", [1, 2, 4])
+def test_conv3x3_padded_raster_scheme(H, W, T):
+    """csrc/k_conv_tc.cu restated: a CTA stages the zero-padded raster of R rows (+halo) with one slack cell in front,
+    output cell o of the SAME raster reads tap (dy, dx) at staged cell o + dy*WP + dx, junk columns / rows are dropped
+    (`live`).  Checked against F.conv2d (float64, 3 channels) for every CTA of the grid, incl. the staging bound."""
+    Cc = 3
+    gen = torch.Generator().manual_seed(H * 1000 + W + T)
+    x = torch.randn(1, Cc, H, W, generator=gen, dtype=torch.float64)
+    w = torch.randn(Cc, Cc, 3, 3, generator=gen, dtype=torch.float64)
+    zy0, zy1, zx0, zx1 = H // 4, H // 2 + 1, W // 3, W // 2          # second source: cells inside the zone are never read
+    want = F.conv2d(x, w, padding=1)[0].numpy()
+    xz = x.clone()
+    xz[:, :, zy0:zy1, zx0:zx1] = 0
+    want_z = F.conv2d(xz, w, padding=1)[0].numpy()
+    WP = W + 2
+    R = (T * 128) // WP
+    if R < 1:
+        pytest.skip("map wider than the CTA's raster: the launcher refuses it (CFP_REQUIRE R >= 1)")
+    cells = T * 128 + 2 * WP + 2
+    while cells % 8 != 1:
+        cells += 1
+    xn, wn = x[0].numpy(), w.numpy()
+    got = np.full((2, Cc, H, W), np.nan)
+    for y0 in range(0, H, R):
+        for src in range(2):
+            ci = np.arange(cells)
+            idx = ci - 1
+            pr, px = idx // WP, idx % WP
+            y, xx = y0 - 1 + pr, px - 1
+            ok = (idx >= 0) & (pr < R + 2) & (y >= 0) & (y < H) & (xx >= 0) & (xx < W)
+            if src == 1:
+                ok &= ~((y >= zy0) & (y < zy1) & (xx >= zx0) & (xx < zx1))
+            a = np.where(ok[None, :], xn[:, np.clip(y, 0, H - 1), np.clip(xx, 0, W - 1)], 0.0)       # [Cc, cells]
+            o = np.arange(T * 128)
+            acc = np.zeros((Cc, T * 128))
+            for tap in range(9):
+                at = o + (tap // 3) * WP + tap % 3
+                assert at.max() < cells                                    # staged buffer covers every operand view
+                acc += wn[:, :, tap // 3, tap % 3] @ a[:, at]
+            r, pxo = o // WP, o % WP
+            yy, xo = y0 + r, pxo - 1
+            live = (r < R) & (yy < H) & (xo >= 0) & (xo < W)
+            got[src][:, yy[live], xo[live]] = acc[:, live]
+    assert not np.isnan(got).any()                                         # every output cell written by exactly one CTA row
+    assert np.abs(got[0] - want).max() <= 1e-10 and np.abs(got[1] - want_z).max() <= 1e-10
