@@ -207,3 +207,48 @@ def test_conv3x3_padded_raster_scheme(H, W, T):
             got[src][:, yy[live], xo[live]] = acc[:, live]
     assert not np.isnan(got).any()                                         # every output cell written by exactly one CTA row
     assert np.abs(got[0] - want).max() <= 1e-10 and np.abs(got[1] - want_z).max() <= 1e-10
+
+
+@pytest.mark.parametrize("S,groups", [(16, 72), (16, 36), (36, 60), (81, 48), (144, 108), (20, 3), (35, 2), (88, 5),
+                                      (576, 2), (2304, 1), (9216, 2), (1, 7)])
+def test_kv_state_padded_runs(S, groups):
+    """csrc/k_chain_tc.cu::kv_state_tc_kernel's row enumeration restated: group sizes padded to a multiple of 16 so that
+    every 16-row MMA step belongs to one group; consecutive steps of a group inside a 128-row tile form a run that is
+    flushed once - with a plain store when groups never straddle tiles (128 % S_pad == 0: no memset), with an atomic add
+    otherwise.  The emulation must reproduce sum_s K_s^T V_s per group (float64) and, in the plain-store case, write
+    every group exactly once."""
+    d = 4
+    gen = np.random.default_rng(S * 131 + groups)
+    K, V = gen.standard_normal((groups, S, d)), gen.standard_normal((groups, S, d))
+    want = np.einsum("gsd,gsv->gdv", K, V)
+    S_pad = (S + 15) // 16 * 16
+    complete = 128 % S_pad == 0
+    total = groups * S_pad
+    ntiles = (total + 127) // 128
+    kv = np.zeros((groups, d, d)) if not complete else np.full((groups, d, d), np.nan)
+    writes = np.zeros(groups, dtype=int)
+    for tile in range(ntiles):
+        row0 = tile * 128
+        p = row0 + np.arange(128)
+        g_of, s_of = p // S_pad, p % S_pad
+        real = (p < total) & (s_of < S)
+        Kt = np.where(real[:, None], K[np.minimum(g_of, groups - 1), np.minimum(s_of, S - 1)], 0.0)   # padding rows are zeros
+        Vt = np.where(real[:, None], V[np.minimum(g_of, groups - 1), np.minimum(s_of, S - 1)], 0.0)
+        ks = 0
+        while ks < 8 and row0 + 16 * ks < total:
+            g = (row0 + 16 * ks) // S_pad
+            ke = ks + 1
+            while ke < 8 and row0 + 16 * ke < total and (row0 + 16 * ke) // S_pad == g:
+                ke += 1
+            rows = slice(16 * ks, 16 * ke)
+            assert set(g_of[rows][real[rows]]) <= {g}                       # a run never mixes groups
+            acc = Kt[rows].T @ Vt[rows]
+            if complete:
+                kv[g] = acc
+            else:
+                kv[g] += acc
+            writes[g] += 1
+            ks = ke
+    assert np.abs(kv - want).max() <= 1e-9 * max(1.0, np.abs(want).max())
+    if complete:
+        assert (writes == 1).all()
