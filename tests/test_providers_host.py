@@ -252,3 +252,15 @@ def test_kv_state_padded_runs(S, groups):
     assert np.abs(kv - want).max() <= 1e-9 * max(1.0, np.abs(want).max())
     if complete:
         assert (writes == 1).all()
+
+
+def test_query_chain_state_slots_cover_every_tile():
+    """run_query_tc sizes the shared-memory copy of the attention state for kv_slots = (128 + rpg - 2) / rpg + 1 groups;
+    a 128-row tile starting at any multiple of 128 must never touch more (the bulk copies would overrun the buffer)."""
+    for rpg in list(range(1, 300)) + [576, 884, 3536, 14144]:
+        kv_slots = (128 + rpg - 2) // rpg + 1
+        rows = rpg * 37
+        row0 = np.arange(0, rows, 128)
+        last = np.minimum(row0 + 127, rows - 1)
+        ng = last // rpg - row0 // rpg + 1
+        assert ng.max() <= kv_slots, (rpg, int(ng.max()), kv_slots)
