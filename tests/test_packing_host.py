@@ -61,7 +61,7 @@ def test_toeplitz_pack_reproduces_the_depthwise_conv(C, k, H, W, B):
     assert float((out - ref).abs().max()) <= 1e-9 * float(ref.abs().max() + 1)
 
 
-@pytest.mark.parametrize("C", [32, 64])
+@pytest.mark.parametrize("C", [32, 64, 128])
 def test_mlp_fold_reproduces_layernorm_mlp(C):
     """W1' = W1 diag(g), b1' = b1 + W1 b ride in [LNhat(y) | 1]; b2 rides in [GELU(h) | 1] of slice 0 (MlpTC)."""
     blk = make_block(C, 7)
