@@ -18,7 +18,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcfp.so")
 
 CFP_F32, CFP_BF16 = 0, 1
-ABI_VERSION = 8
+ABI_VERSION = 9
 _fp = C.POINTER(C.c_float)
 
 
@@ -62,6 +62,7 @@ SIGNATURES = {
     "cfp_version": (_i, []),
     "cfp_last_error": (C.c_char_p, []),
     "cfp_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i, C.POINTER(CfpGeom)]),
+    "cfp_geometry_from_rects": (_i, [_fp, _i, _i, _i, _i, _i, C.POINTER(CfpGeom)]),
     "cfp_hist_encoder_fwd": (_i, [_p, _p, _p, _p, _i64, C.POINTER(CfpHistW), _i, _p]),
     "cfp_zone_masks": (_i, [_p, _p, _p, _p, _i, _i, _i, C.POINTER(CfpGeom), _p]),
     "cfp_posenc_tokens_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),

@@ -1,6 +1,9 @@
 // extern "C" surface of libcfp (declared in include/cfp.h): argument validation, workspace
 // partitioning and the per-layer launch sequences.  No device allocation, no synchronisation,
 // no global mutable state (the error message is thread-local).
+#include <algorithm>
+#include <climits>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -121,6 +124,68 @@ CFP_API size_t cfp_workspace_bytes(int B, int H, int W, int C, int ws, int large
     const size_t with_g = ws_layout(B, H, W, C, ws, large_kernel, dtype, g).total;
     const size_t without = ws_layout(B, H, W, C, ws, large_kernel, dtype, nullptr).total;
     return with_g > without ? with_g : without;
+}
+
+CFP_API int cfp_geometry_from_rects(const float* rects, int B, int Z, int max_width, int H, int W, cfp_geom* out) {
+    CFP_REQUIRE(rects && out, "null pointer");
+    CFP_REQUIRE(B > 0 && Z > 0 && H > 0 && W > 0, "bad shape B=%d Z=%d H=%d W=%d", B, Z, H, W);
+    CFP_REQUIRE(max_width > 0 && 640 % max_width == 0, "max_resolution[1]=%d does not divide 640 (fusion.py:41)", max_width);
+    const int cps = 640 / max_width;                        // conv_patch_size: 4 / 8 / 16
+    CFP_REQUIRE(cps == 4 || cps == 8 || cps == 16, "patch_info has no entry for cell size %d (utils/dataloader.py:25)", cps);
+    int zn = (int)std::sqrt((double)Z);                     // int(math.sqrt(Z)), utils/dataloader.py:14
+    while ((zn + 1) * (zn + 1) <= Z) ++zn;
+    while (zn * zn > Z) --zn;
+    int pad_h = INT_MIN, pad_w = INT_MIN, p1 = INT_MIN, p2 = INT_MIN;
+    int sy_wo = INT_MAX, sx_wo = INT_MAX, ey_wo = INT_MIN, ex_wo = INT_MIN;
+    const float fc = (float)cps;
+    for (int b = 0; b < B; ++b) {                           // per frame (dataloader.py:15-38), then max / min over the batch
+        const float* r = rects + (size_t)b * Z * 4;
+        float hgt = -INFINITY, wid = -INFINITY, up = 0.f, left = 0.f, down = 0.f, right = 0.f;
+        float y0min = INFINITY, x0min = INFINITY, y1max = -INFINITY, x1max = -INFINITY;
+        for (int z = 0; z < Z; ++z) {
+            const float y0 = r[4 * z], x0 = r[4 * z + 1], y1 = r[4 * z + 2], x1 = r[4 * z + 3];
+            hgt = fmaxf(hgt, y1 - y0);
+            wid = fmaxf(wid, x1 - x0);
+            up = fmaxf(up, fabsf(fminf(y0, 0.f)));
+            left = fmaxf(left, fabsf(fminf(x0, 0.f)));
+            down = fmaxf(down, fmaxf(y1, 480.f) - 480.f);   // the canvas is hard-coded 480 x 640 (dataloader.py:20-23)
+            right = fmaxf(right, fmaxf(x1, 640.f) - 640.f);
+            y0min = fminf(y0min, y0 / fc);                  // float32 divisions, truncated toward zero below
+            x0min = fminf(x0min, x0 / fc);
+            y1max = fmaxf(y1max, y1 / fc);
+            x1max = fmaxf(x1max, x1 / fc);
+        }
+        const int over_h = (int)fmaxf(up, down), over_w = (int)fmaxf(left, right);
+        const int ih = (int)hgt, iw = (int)wid;
+        auto ceil_div = [](int a, int d) { return a >= 0 ? (a + d - 1) / d : -((-a) / d); };   // math.ceil(a / d)
+        pad_h = std::max(pad_h, ceil_div(over_h, cps));
+        pad_w = std::max(pad_w, ceil_div(over_w, cps));
+        p1 = std::max(p1, ceil_div(ih, cps));
+        p2 = std::max(p2, ceil_div(iw, cps));
+        sy_wo = std::min(sy_wo, (int)y0min);
+        sx_wo = std::min(sx_wo, (int)x0min);
+        ey_wo = std::max(ey_wo, (int)y1max);
+        ex_wo = std::max(ex_wo, (int)x1max);
+    }
+    cfp_geom g{};
+    g.zone_num = zn; g.pad_h = pad_h; g.pad_w = pad_w; g.p1 = p1; g.p2 = p2;
+    g.sy_wo = sy_wo; g.sx_wo = sx_wo; g.ey_wo = ey_wo; g.ex_wo = ex_wo;
+    const int sy = sy_wo + pad_h, ey = ey_wo + pad_h, sx = sx_wo + pad_w, ex = ex_wo + pad_w;   // fusion.py:79-82
+    g.tzh = ey - sy; g.tzw = ex - sx;
+    g.interpolate = (g.tzh != p1 * zn || g.tzw != p2 * zn) ? 1 : 0;                               // fusion.py:83-84
+    auto clip = [](int v, int top) { return v < 0 ? 0 : (v > top ? top : v); };
+    g.ry0 = clip(sy_wo, H); g.ry1 = clip(ey_wo, H); g.rx0 = clip(sx_wo, W); g.rx1 = clip(ex_wo, W);   // fusion.py:104
+    *out = g;
+    // what the reference's own forward needs to be well defined (fusion.py:136-138,157)
+    CFP_REQUIRE(sy >= 0 && sx >= 0 && ey <= H + 2 * pad_h && ex <= W + 2 * pad_w,
+                "zone canvas [%d:%d,%d:%d] leaves the padded %dx%d map", sy, ey, sx, ex, H + 2 * pad_h, W + 2 * pad_w);
+    CFP_REQUIRE(g.tzh > 0 && g.tzw > 0, "empty zone canvas");
+    int top = sy_wo < 0 ? -sy_wo : 0, lft = sx_wo < 0 ? -sx_wo : 0;
+    int bot = ey_wo > H ? ey_wo - H : 0, rgt = ex_wo > W ? ex_wo - W : 0;
+    if (pad_h == 0 && pad_w == 0) top = lft = bot = rgt = 0;
+    CFP_REQUIRE(g.tzh - top - bot == g.ry1 - g.ry0 && g.tzw - lft - rgt == g.rx1 - g.rx0,
+                "in-image canvas cells do not match the zone rectangle");
+    return 0;
 }
 
 CFP_API int cfp_hist_encoder_fwd(const float* hist, void* out32, void* out64, void* out128, int64_t rows,

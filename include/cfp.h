@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define CFP_ABI_VERSION 8
+#define CFP_ABI_VERSION 9
 
 #if defined(__GNUC__)
 #define CFP_API __attribute__((visibility("default")))
@@ -131,6 +131,17 @@ CFP_API const char *cfp_last_error(void);
  * (zone_num^2 zones) and those that do not (laid out for 64 zones). */
 CFP_API size_t cfp_workspace_bytes(int B, int H, int W, int C, int ws, int large_kernel, int dtype,
                                    const cfp_geom *g);
+
+/* a2. Zone geometry of one TransformerFusion call, host arithmetic only (no device work, no stream).
+ * Replaces patch_info_from_rect_data (src/utils/dataloader.py:13-40: per-frame pad / patch / index
+ * integers, hard-coded 480x640 canvas, float32 divisions truncated toward zero), the batch-wise max / min
+ * of fusion.py:75-78 and the integer block of fusion.py:67-84,104.  rects [B][Z][4] float rows
+ * (y0,x0,y1,x1) in pixels (host memory); max_width = max_resolution[1] of the level (160 / 80 / 40:
+ * cell size 640/max_width px); H, W = the level's map.  Fills *out; non-zero return (+ message) for
+ * layouts on which the reference's own forward is undefined (canvas slice outside the padded map,
+ * in-image canvas cells != zone rectangle cells).  Bit-exact with the reference's integers on the 216
+ * layouts of tests/golden/geometry_cases.json (tests/test_host.py). */
+CFP_API int cfp_geometry_from_rects(const float *rects, int B, int Z, int max_width, int H, int W, cfp_geom *out);
 
 /* a1. HistogramEncoder.forward (encoder.py:45-50; deltar.py:40).
  * hist [rows] fp32 zone depth samples (rows = B*Z*S) -> out32 [rows][32],

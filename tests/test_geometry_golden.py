@@ -79,3 +79,75 @@ def test_geometry_and_masks_bit_exact(i):
     zm, _hm, pm = O.zone_masks(g.asdict(), torch.ones(1, Z, dtype=torch.bool), 1, H, W, 1)
     assert int(zm.sum()) == c["zone_mask_sum"] and sha(zm.reshape(H, W).numpy()) == c["zone_mask_sha1"]
     assert int(pm.sum()) == c["pad_mask_sum"] and sha(pm.reshape(g.tzh, g.tzw).numpy()) == c["pad_mask_sha1"]
+
+
+# ------------------------------------------------------------------ the same integers through the C ABI
+import ctypes  # noqa: E402
+
+from cfpnet_b200 import _lib  # noqa: E402
+
+
+def c_geometry(rects, max_width, H, W):
+    """cfp_geometry_from_rects on a [B,Z,4] float32 array -> (return code, CfpGeom, message)"""
+    from cfpnet_b200.build import build
+    build()
+    lib = _lib.load()
+    r = np.ascontiguousarray(np.asarray(rects, dtype=np.float32))
+    if r.ndim == 2:
+        r = r[None]
+    out = _lib.CfpGeom()
+    rc = lib.cfp_geometry_from_rects(r.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), r.shape[0], r.shape[1], max_width, H, W,
+                                     ctypes.byref(out))
+    return rc, out, lib.cfp_last_error().decode()
+
+
+C_FIELDS = {"pad_height": "pad_h", "pad_width": "pad_w", "p1": "p1", "p2": "p2", "sy_wo_pad": "sy_wo", "sx_wo_pad": "sx_wo",
+            "ey_wo_pad": "ey_wo", "ex_wo_pad": "ex_wo", "tzh": "tzh", "tzw": "tzw", "interpolate": "interpolate",
+            "zone_num": "zone_num"}
+
+
+@pytest.mark.parametrize("i", range(len(CASES)))
+def test_c_abi_geometry_bit_exact(i):
+    """include/cfp.h::cfp_geometry_from_rects (plain C, host only) against the integers the REFERENCE computed, and its
+    verdict (accept / refuse) against the Python host logic, on all 216 layouts."""
+    c = CASES[i]
+    _, stride, max_res, _ = synth.LEVELS[c["level"]]
+    H, W = c["img"][0] // stride, c["img"][1] // stride
+    rect = grid_rects(c)
+    rc, out, msg = c_geometry(rect.numpy(), max_res[1], H, W)
+    g = geometry.zone_geometry(geometry.collate_patch_info([geometry.patch_info_from_rect_data(rect)]), max_res[1], H, W)
+    for name, _t in _lib.CfpGeom._fields_:                       # the C struct equals the Python dataclass field by field
+        assert getattr(out, name) == getattr(g, name), name
+    if "geo" in c:
+        for ref_name, mine in C_FIELDS.items():
+            assert getattr(out, mine) == c["geo"][ref_name], ref_name
+    try:
+        geometry.check_geometry(g, H, W)
+        accepted = True
+    except ValueError:
+        accepted = False
+    assert (rc == 0) == accepted, msg
+    if "reference_raises" in c:
+        assert rc != 0
+
+
+def test_c_abi_geometry_takes_the_batch_extremes():
+    """fusion.py:75-78: pads / patch sizes are the batch maximum, the canvas the union over the batch"""
+    a = grid_rects({"zone_num": 8, "px": 48, "y0": 16, "x0": 80}).numpy()
+    b = grid_rects({"zone_num": 8, "px": 40, "y0": 48, "x0": 112}).numpy()
+    rc, both, _ = c_geometry(np.stack([a, b]), 40, 26, 34)
+    _, ga, _ = c_geometry(a, 40, 26, 34)
+    _, gb, _ = c_geometry(b, 40, 26, 34)
+    assert both.p1 == max(ga.p1, gb.p1) and both.sy_wo == min(ga.sy_wo, gb.sy_wo) and both.ey_wo == max(ga.ey_wo, gb.ey_wo)
+    pi = geometry.collate_patch_info([geometry.patch_info_from_rect_data(torch.from_numpy(r)) for r in (a, b)])
+    g = geometry.zone_geometry(pi, 40, 26, 34)
+    for name, _t in _lib.CfpGeom._fields_:
+        assert getattr(both, name) == getattr(g, name), name
+
+
+def test_c_abi_geometry_rejects_bad_arguments():
+    a = grid_rects({"zone_num": 8, "px": 48, "y0": 16, "x0": 80}).numpy()
+    rc, _, msg = c_geometry(a, 48, 26, 34)
+    assert rc != 0 and "640" in msg
+    rc, _, msg = c_geometry(a, 640, 26, 34)                      # cell size 1: no patch_info entry in the reference either
+    assert rc != 0 and "cell size" in msg
