@@ -51,3 +51,30 @@ def test_committed_traffic_file_names_bench_kernels():
 def test_peaks_file_or_fallback():
     p = bench.load_peaks()
     assert p["hbm_gbs"] > 1000 and p["bf16_tflops_sustained"] > 100 and p["source"]
+
+
+def test_committed_bench_line_carries_the_whole_contract():
+    """The driver's contract for the JSON line (keys and their meaning), checked on the committed final line of the
+    round; bench.py prints the same dict."""
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    d = json.load(open(os.path.join(root, "profiles", "r1s_bench_final.json")))
+    baseline = json.load(open(os.path.join(root, "BASELINE.json")))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert baseline["metric"].startswith(d["metric"]) and d["unit"] == "frames/s"
+    assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None and d["data"] == "synthetic"
+    assert d["warmup"] >= 3 and d["n_gpus"] == 1 and d["dtype"] == "bf16"
+    assert "workload" in d["config"] and "model" not in d["config"] and "l2_policy" in d["config"]
+    assert abs(d["value"] - d["config"]["global_batch"] * d["steps"] / (d["ms_per_step"] * d["steps"] * 1e-3)) <= 1e-6 * d["value"]
+    e = d["e2e"]
+    assert e["unit"] == d["unit"] and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and 0 < e["value"] < d["value"]
+    assert d["gpu_launches"] > 0 and d["gpu_launches"] % d["steps"] == 0
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
+    r = d["roofline"]
+    assert r["bound"] in ("hbm", "tensor") and r["unit"] in ("GB/s", "TFLOP/s")
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) <= 1e-9 and 0 < r["frac"] <= 1 and r["traffic"] is None or r["traffic"] > 0
+    c = d["cpu_baseline"]
+    assert c["kind"] in ("port", "reference") and c["cores"] >= 1 and c["value"] > 0 and c["unit"] == d["unit"] and c["sample"]
