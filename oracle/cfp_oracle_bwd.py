@@ -303,34 +303,60 @@ def combine1_bwd(p: Mapping, feat0: Tensor, g, H: int, W: int, dout: Tensor):
     return dx, {**_prefixed("transformer_path.", g1), **_prefixed("large_kernel_path.", g2)}
 
 
+def bilinear_matrix(n_in: int, n_out: int, dtype=torch.float64) -> Tensor:
+    """[n_out, n_in] matrix of F.interpolate(mode="bilinear", align_corners=True) along one axis: the resize is
+    separable, out = Wy in Wx^T per channel, so its adjoint is Wy^T dout Wx - the same two small GEMMs transposed."""
+    m = torch.zeros(n_out, n_in, dtype=dtype)
+    for o in range(n_out):
+        f = o * ((n_in - 1) / (n_out - 1)) if n_out > 1 else 0.0
+        i0 = min(int(f), n_in - 1)
+        i1 = min(i0 + 1, n_in - 1)
+        m[o, i0] += 1.0 - (f - i0)
+        m[o, i1] += f - i0
+    return m
+
+
 def hist2image_bwd(p: Mapping, feat0: Tensor, ztok: Tensor, mask: Tensor, g: Mapping[str, int], H: int, W: int, dout: Tensor):
-    """hist2image (fusion.py:132-157) with change_embedding, without the resize branch (the training layout):
-    out = feat0, and on the zone rectangle  out += mask * loftr(canvas cells, zone tokens)  where the canvas is cut from
-    feat0 itself.  Returns (dfeat0, dztok, grads)."""
-    if g["interpolate"]:
-        raise NotImplementedError("explicit backward is stated for the no-resize branch (training layout) only")
+    """hist2image (fusion.py:132-157) with change_embedding:  out = feat0, and on the zone rectangle
+    out += crop(resize_back(mask * loftr(resize(canvas cells), zone tokens)))  where the canvas is cut from feat0 itself
+    and the two resizes exist only in the resize branch (fusion.py:140-141,146-149).  Returns (dfeat0, dztok, grads)."""
     B, N, C = feat0.shape
     zn, p1, p2 = g["zone_num"], g["p1"], g["p2"]
+    tzh, tzw = g["tzh"], g["tzw"]
+    oh, ow = zn * p1, zn * p2
     top, left = max(-g["sy_wo"], 0), max(-g["sx_wo"], 0)
     hh, ww = g["ry1"] - g["ry0"], g["rx1"] - g["rx0"]
     rect = (slice(None), slice(g["ry0"], g["ry1"]), slice(g["rx0"], g["rx1"]))
     cv = (slice(None), slice(top, top + hh), slice(left, left + ww))
+    interp = bool(g["interpolate"])
+    if interp:
+        Wy, Wx = bilinear_matrix(tzh, oh, feat0.dtype), bilinear_matrix(tzw, ow, feat0.dtype)        # canvas -> zones
+        Vy, Vx = bilinear_matrix(oh, tzh, feat0.dtype), bilinear_matrix(ow, tzw, feat0.dtype)        # zones -> canvas
 
-    def to_zone(t_rect):                      # [B,hh,ww,C] (in-image part) -> zero-padded canvas -> [(B zn zn), p1 p2, C]
-        canvas = t_rect.new_zeros(B, zn * p1, zn * p2, C)
+    def to_canvas(t_rect):                    # in-image rectangle -> zero-padded [B,tzh,tzw,C] canvas
+        canvas = t_rect.new_zeros(B, tzh, tzw, C)
         canvas[cv] = t_rect
-        return canvas.view(B, zn, p1, zn, p2, C).permute(0, 1, 3, 2, 4, 5).reshape(B * zn * zn, p1 * p2, C)
+        return canvas
 
-    def from_zone(t):                         # adjoint: back to the in-image rectangle
-        return t.view(B, zn, zn, p1, p2, C).permute(0, 1, 3, 2, 4, 5).reshape(B, zn * p1, zn * p2, C)[cv]
+    def zones(canvas_oh_ow):                  # [B,oh,ow,C] -> [(B zn zn), p1 p2, C]
+        return canvas_oh_ow.view(B, zn, p1, zn, p2, C).permute(0, 1, 3, 2, 4, 5).reshape(B * zn * zn, p1 * p2, C)
+
+    def unzones(t):
+        return t.view(B, zn, zn, p1, p2, C).permute(0, 1, 3, 2, 4, 5).reshape(B, oh, ow, C)
 
     f = feat0.view(B, H, W, C)
-    xz = to_zone(f[rect])
+    canvas = to_canvas(f[rect])
+    xz = zones(torch.einsum("oy,byxc,px->bopc", Wy, canvas, Wx) if interp else canvas)
     mz = mask.reshape(B * zn * zn, 1, 1).to(feat0.dtype)
-    dt = to_zone(dout.view(B, H, W, C)[rect]) * mz              # rows of invalid zones are zeroed, residual included
+    # cotangent of the layer output: rectangle -> canvas (zero outside the image) -> adjoint of the resize back -> zones
+    dcan = to_canvas(dout.view(B, H, W, C)[rect])
+    dt = zones(torch.einsum("yo,byxc,xp->bopc", Vy, dcan, Vx) if interp else dcan) * mz    # invalid zones: zeroed, residual included
     dxz, dztok, grads = loftr_layer_bwd(p, xz, ztok, 4, dt)
+    dcv = unzones(dxz)
+    if interp:
+        dcv = torch.einsum("oy,bopc,px->byxc", Wy, dcv, Wx)                                   # adjoint of the resize to zones
     dfeat = dout.clone().view(B, H, W, C)
-    dfeat[rect] += from_zone(dxz)
+    dfeat[rect] += dcv[cv]
     return dfeat.view(B, N, C), dztok, grads
 
 
@@ -383,7 +409,7 @@ def _pointnet_fwd_train(p: Mapping, x: Tensor) -> Tensor:
 
 def transformer_fusion_bwd(sd: Mapping, layer_names, max_res, x: Tensor, feat1: Tensor, mask: Tensor, patch_info: dict,
                            offsets, dout: Tensor):
-    """Backward of one ``TransformerFusion`` call in train mode (fusion.py:52-188; change_embedding, no resize branch).
+    """Backward of one ``TransformerFusion`` call in train mode (fusion.py:52-188; change_embedding, every geometry branch).
     Returns (dx [B,C,H,W], dfeat1 [B,Z,S,C], {state_dict name: gradient})."""
     B, C, H, W = x.shape
     g = zone_geometry(patch_info, max_res[1], H, W)

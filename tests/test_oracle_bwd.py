@@ -102,3 +102,39 @@ def test_lkpm_train_backward(C, k, H, W):
             assert float(g.abs().max()) <= 1e-9 and float(p[name].grad.abs().max()) <= 1e-9
             continue
         assert g.shape == p[name].grad.shape and _close(g, p[name].grad), name
+
+
+@pytest.mark.parametrize("geom,level", [("G416z6", 3), ("G480", 3), ("G480pad", 3), ("G480pad", 2)])
+def test_hist2image_backward_all_branches(geom, level):
+    """explicit hist2image backward (gather / scatter adjoints, invalid-zone zeroing, and in the resize branch the two
+    separable bilinear resizes as matrices) against autograd over the forward restatement: no-resize, resize, pad"""
+    from cfpnet_b200 import synth
+    C, _, max_res, _ = synth.LEVELS[level]
+    inp = synth.make_inputs(geom, 2, seed=3, levels=(level,))
+    H, W = synth.level_hw(geom, level)
+    g = O.zone_geometry(inp["patch_info"], max_res[1], H, W)
+    Z = g["zone_num"] ** 2
+    names = {"q_proj.weight": (C, C), "k_proj.weight": (C, C), "v_proj.weight": (C, C), "merge.weight": (C, C),
+             "mlp.0.weight": (2 * C, 2 * C), "mlp.2.weight": (C, 2 * C), "norm1.weight": (C,), "norm1.bias": (C,),
+             "norm2.weight": (C,), "norm2.bias": (C,)}
+    p = {}
+    for i, (k, shp) in enumerate(names.items()):
+        t = _rand(*shp, seed=60 + i, scale=0.2)
+        p[k] = (t + 1.0 if k in ("norm1.weight", "norm2.weight") else t).requires_grad_(True)
+    feat0 = _rand(2, H * W, C, seed=1).requires_grad_(True)
+    ztok = _rand(2 * Z, 16, C, seed=2).requires_grad_(True)
+    dout = _rand(2, H * W, C, seed=3)
+    O.hist2image(p, feat0, feat0, ztok, inp["mask"], g, H, W).backward(dout)
+    with torch.no_grad():
+        dfeat, dz, grads = OB.hist2image_bwd({k: v.detach() for k, v in p.items()}, feat0.detach(), ztok.detach(),
+                                             inp["mask"], g, H, W, dout)
+    assert _close(dfeat, feat0.grad) and _close(dz, ztok.grad)
+    for k, gr in grads.items():
+        assert _close(gr, p[k].grad), k
+
+
+def test_bilinear_matrix_is_the_align_corners_resize():
+    x = _rand(1, 3, 28, 28, seed=1)
+    Wy, Wx = OB.bilinear_matrix(28, 32), OB.bilinear_matrix(28, 32)
+    want = F.interpolate(x, size=[32, 32], mode="bilinear", align_corners=True)
+    assert _close(torch.einsum("oy,bcyx,px->bcop", Wy, x, Wx), want)
