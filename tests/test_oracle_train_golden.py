@@ -12,7 +12,7 @@ from cfpnet_b200 import synth
 from helpers import GOLDEN, ref_keys, rel_l2
 from oracle import cfp_oracle as O
 
-CASES = ["G416z6_L3_B2", "G416_L2_B2", "G416z6_L1_B1"]
+CASES = ["G416z6_L3_B2", "G416_L2_B2", "G416z6_L1_B1", "G480_L3_B1"]
 TOL = 2e-6          # float64 restatement vs float32 copy of the float64 reference run
 RTOL, ATOL = 1e-8, 1e-9     # parameter gradients are stored in float64: |diff| <= RTOL * |grad| + ATOL
 

@@ -8,7 +8,7 @@ exists, pin what one training step of the path computes.  The reference's ``Hist
 (BatchNorm batch statistics, train.py:75) in float64, and run forward + backward on the synthetic inputs with the
 scalar ``L = sum(out * cotangent)`` (cotangent = seeded N(0,1), so every output element gets its own weight).  Stored:
 
-  * the forward output (float32 copy of the float64 run; maps above 300k elements as a seeded sample + channel sums);
+  * the forward output (float32 copy of the float64 run; maps above 100k elements as a seeded sample + channel sums);
   * d L / d x and d L / d hist_data - the gradients that leave the path on the input side;
   * for every parameter: whether it received a gradient at all (the reference registers parameters it never uses;
     SURVEY.md section 8e: they must stay out of the gradient allreduce), its gradient's L2 norm, sum, and the
@@ -34,7 +34,7 @@ from cfpnet_b200 import synth  # noqa: E402
 OUT = os.path.join(ROOT, "tests", "golden")
 N_PROBE = 48
 SAMPLE_N = 32768
-FULL_LIMIT = 300_000        # elements; larger maps are stored sampled
+FULL_LIMIT = 100_000        # elements; larger maps are stored sampled
 
 ref = import_reference()
 args = ref["args"]
@@ -120,4 +120,5 @@ if __name__ == "__main__":
     C1 = synth.COMBINE1_LAYERS
     train_case("G416z6_L3_B2", "G416z6", 3, 2, C1)      # the reference's training layout: 6x6 zones of 64 px
     train_case("G416_L2_B2", "G416", 2, 2, C1)
-    train_case("G416z6_L1_B1", "G416z6", 1, 1, C1)      # the heavy level: 31x31 depthwise, 12x12 windows
+    train_case("G416z6_L1_B1", "G416z6", 1, 1, C1)
+    train_case("G480_L3_B1", "G480", 3, 1, C1)           # bilinear-resize branch of hist2image (480x640, 8x8 zones of 56 px)      # the heavy level: 31x31 depthwise, 12x12 windows
