@@ -532,3 +532,29 @@ def depth_tail(sd: Mapping, unet_out: Tensor, min_val: float, max_val: float) ->
 def abs_rel(pred: Tensor, gt: Tensor) -> float:
     """``compute_errors``' abs_rel (src/utils/metrics.py:10)."""
     return float(((pred.double() - gt.double()).abs() / gt.double()).mean())
+
+
+# --------------------------------------------------------------------------
+# f3 (input side, SURVEY.md section 8f - "next" row, oracle step only): zone distribution -> zone depth samples
+# --------------------------------------------------------------------------
+def sample_points_from_hist(hist_data: Tensor, mask: Tensor, zone_sample_num: int = 16, sample_uniform: bool = True) -> Tensor:
+    """``hist_data`` [Z,2] (mu, sigma) per zone, ``mask`` [Z] bool -> [Z, zone_sample_num] float32 depth samples, zeros
+    for invalid zones.  Follows src/utils/dataloader.py:65-81 (``sample_point_from_hist_parallel``): with
+    ``sample_uniform`` an even grid over mu +- 3 sigma built as ``w * start + (1 - w) * end`` from two float32
+    ``linspace`` ramps (``tensor_linspace``, :43-58 - the blend, not ``torch.linspace(start, end)``, fixes the rounding);
+    otherwise the normal quantiles at ppf = arange(delta, 1, (1 - 2 delta) / (n - 1)), delta = 1e-3."""
+    Z = mask.numel()
+    fh = torch.zeros(Z, zone_sample_num, dtype=torch.float32)
+    mu, sigma = hist_data[mask, 0], hist_data[mask, 1]
+    if sample_uniform:
+        start, end = mu - 3.0 * sigma, mu + 3.0 * sigma
+        w0 = torch.linspace(1, 0, steps=zone_sample_num).to(start)
+        w1 = torch.linspace(0, 1, steps=zone_sample_num).to(start)
+        fh[mask] = (w0 * start.unsqueeze(-1) + w1 * end.unsqueeze(-1)).to(torch.float32)
+    else:
+        import numpy as np
+        delta = 1e-3
+        ppf = torch.Tensor(np.arange(delta, 1, (1 - 2 * delta) / (zone_sample_num - 1)).tolist()).unsqueeze(0)
+        q = mu.unsqueeze(-1) + sigma.unsqueeze(-1) * math.sqrt(2.0) * torch.erfinv(2 * ppf - 1)      # Normal(mu, sigma).icdf
+        fh[mask] = q.to(torch.float32)
+    return fh

@@ -75,3 +75,30 @@ def test_oracle_draws_offsets_like_reference():
     before = torch.get_rng_state()
     assert O.draw_posenc_offsets(case.max_res, 30, 40) == (0, 0)
     assert torch.equal(before, torch.get_rng_state())      # nothing drawn
+
+
+@pytest.mark.parametrize("zn", [8, 6])
+def test_zone_depth_samples_match_reference(zn):
+    """f3 (input side, oracle step): (mu, sigma, mask) -> 16 depth samples per zone, bit-exact in the uniform mode the
+    configs use (--sample_uniform), 1e-6 in the quantile mode (erfinv vs Normal.icdf)."""
+    z = np.load(os.path.join(GOLDEN, "input_side.npz"))
+    hist, mask = torch.from_numpy(z[f"hist_z{zn}"]), torch.from_numpy(z[f"mask_z{zn}"])
+    got = O.sample_points_from_hist(hist, mask, 16, True)
+    assert got.dtype == torch.float32 and np.array_equal(got.numpy(), z[f"samples_z{zn}_uniform"])
+    assert float(got[~mask].abs().max()) == 0.0
+    got = O.sample_points_from_hist(hist, mask, 16, False)
+    assert np.allclose(got.numpy(), z[f"samples_z{zn}_icdf"], rtol=1e-6, atol=1e-6)
+
+
+def test_synthetic_histograms_follow_the_sampling_rule():
+    """cfpnet_b200.synth builds hist_data as the reference's uniform sampling of (mu, sigma): even grid over mu +- 3 sigma,
+    zeros for invalid zones (what the bench and every fixture feed the histogram encoder)."""
+    inp = synth.make_inputs("G416", 2, seed=1, levels=())
+    h, m = inp["hist_data"], inp["mask"]
+    assert h.shape == (2, 64, 16) and float(h[~m].abs().max()) == 0.0
+    v = h[m]
+    step = v[:, 1:] - v[:, :-1]
+    assert float((step - step.mean(dim=1, keepdim=True)).abs().max()) <= 1e-5            # even grid
+    mu, sigma = v.mean(dim=1), (v[:, -1] - v[:, 0]) / 6.0
+    assert float(mu.min()) >= 0.3 - 1e-4 and float(mu.max()) <= 4.0 + 1e-4 and float(sigma.min()) >= 0.01 - 1e-4 \
+        and float(sigma.max()) <= 0.2 + 1e-4
