@@ -558,3 +558,18 @@ def sample_points_from_hist(hist_data: Tensor, mask: Tensor, zone_sample_num: in
         q = mu.unsqueeze(-1) + sigma.unsqueeze(-1) * math.sqrt(2.0) * torch.erfinv(2 * ppf - 1)      # Normal(mu, sigma).icdf
         fh[mask] = q.to(torch.float32)
     return fh
+
+
+# --------------------------------------------------------------------------
+# f4 (loss, SURVEY.md section 8f - "next" row, oracle step only)
+# --------------------------------------------------------------------------
+def silog_loss(pred: Tensor, target: Tensor, mask: Optional[Tensor] = None, interpolate: bool = True) -> Tensor:
+    """Scale-invariant log loss of the training step (src/loss.py:9-19): the prediction is resized to the target
+    (bilinear, align_corners), masked, g = log(pred) - log(target), 10 * sqrt(var(g) + 0.15 * mean(g)^2) with the
+    UNBIASED variance (torch.var default)."""
+    if interpolate:
+        pred = F.interpolate(pred, target.shape[-2:], mode="bilinear", align_corners=True)
+    if mask is not None:
+        pred, target = pred[mask], target[mask]
+    g = torch.log(pred) - torch.log(target)
+    return 10 * torch.sqrt(torch.var(g) + 0.15 * torch.pow(torch.mean(g), 2))

@@ -451,3 +451,22 @@ def transformer_fusion_bwd(sd: Mapping, layer_names, max_res, x: Tensor, feat1: 
     dfeat1 = dztok.view(feat1.shape)
     grads["positional_encodings2"] = dfeat1.sum(dim=(0, 1))
     return dmap.permute(0, 3, 1, 2).contiguous(), dfeat1, grads
+
+
+def silog_loss_bwd(pred: Tensor, target: Tensor, mask: Tensor) -> Tensor:
+    """d silog_loss / d pred in closed form (src/loss.py:9-19; pred [B,1,h,w], target / mask [B,1,H,W]):
+    with n masked elements, g = log(up(pred)) - log(target), D = var_unbiased(g) + 0.15 mean(g)^2, L = 10 sqrt(D):
+        dL/dg_i = (5 / sqrt(D)) * ( 2 (g_i - mean) / (n - 1) + 0.3 mean / n ),   dL/dup_i = dL/dg_i / up_i,
+    scattered through the mask and pulled back through the separable bilinear resize (Wy^T . Wx)."""
+    B, _, h, w = pred.shape
+    H, W = target.shape[-2:]
+    Wy, Wx = bilinear_matrix(h, H, pred.dtype), bilinear_matrix(w, W, pred.dtype)
+    up = torch.einsum("oy,bcyx,px->bcop", Wy, pred, Wx)
+    g = torch.log(up[mask]) - torch.log(target[mask])
+    n = g.numel()
+    mean = g.mean()
+    D = g.var() + 0.15 * mean * mean
+    dg = (5.0 / torch.sqrt(D)) * (2.0 * (g - mean) / (n - 1) + 0.3 * mean / n)
+    dup = torch.zeros_like(up)
+    dup[mask] = dg / up[mask]
+    return torch.einsum("oy,bcop,px->bcyx", Wy, dup, Wx)

@@ -138,3 +138,15 @@ def test_bilinear_matrix_is_the_align_corners_resize():
     Wy, Wx = OB.bilinear_matrix(28, 32), OB.bilinear_matrix(28, 32)
     want = F.interpolate(x, size=[32, 32], mode="bilinear", align_corners=True)
     assert _close(torch.einsum("oy,bcyx,px->bcop", Wy, x, Wx), want)
+
+
+def test_silog_loss_and_gradient_match_reference():
+    """f4 oracle step: the training loss (src/loss.py:9-19) and its closed-form gradient against the reference's value
+    and autograd gradient (tests/golden/silog_loss.npz, tools/make_golden_loss.py)"""
+    import os
+    import numpy as np
+    from helpers import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "silog_loss.npz"))
+    pred, target, mask = (torch.from_numpy(z[k]) for k in ("pred", "target", "mask"))
+    assert abs(float(O.silog_loss(pred, target, mask)) - float(z["loss"])) <= 1e-12
+    assert _close(OB.silog_loss_bwd(pred, target, mask), torch.from_numpy(z["grad"]))
