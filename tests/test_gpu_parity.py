@@ -141,13 +141,20 @@ def test_fusion_bf16_vs_reference(tag):
     case.check_output(out, BF16_TOL, f"cuda bf16 {tag}")
 
 
+# the 6x6 training layout at every level against the oracle: L3 / L2 are also covered by the fixtures above and were
+# confirmed on a B200 (profiles/r1t_z6_gpu_check.log); L1 (256 cells per zone) has not run on a GPU yet - opt-in until
+# the first GPU call of the next round (tools/r2_first_call.sh sets CFP_TEST_EXTRA=1)
+_EXTRA = pytest.mark.skipif(not os.environ.get("CFP_TEST_EXTRA"), reason="not yet run on a GPU; CFP_TEST_EXTRA=1 to run")
+
+
+@pytest.mark.parametrize("geom", ["G416", pytest.param("G416z6", marks=_EXTRA)])
 @pytest.mark.parametrize("level", [3, 2, 1])
-def test_fusion_vs_oracle_batch3(level):
+def test_fusion_vs_oracle_batch3(level, geom):
     """Batch > 1 with per-frame masks, against the fp64 oracle on the same seeded inputs."""
     m, sd = build_fusion(level)
     enc, hsd = build_hist()
     C, _, max_res, _ = synth.LEVELS[level]
-    inp = synth.make_inputs("G416", 3, seed=5, levels=(level,))
+    inp = synth.make_inputs(geom, 3, seed=5, levels=(level,))
     feats = enc(inp["hist_data"].to(DEV).unsqueeze(-1))
     feat1 = {32: feats[0], 64: feats[1], 128: feats[2]}[C]
     torch.manual_seed(11)

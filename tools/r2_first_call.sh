@@ -7,7 +7,7 @@
 # 3. the default bench line;
 # Everything lands in gpurun_out/ so it comes back.
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_parity.py -k z6 -q -x > gpurun_out/r2_z6.log 2>&1
+CFP_TEST_EXTRA=1 timeout 300 python -m pytest tests/test_gpu_parity.py -k z6 -q > gpurun_out/r2_z6.log 2>&1
 echo "z6 rc=$?" | tee -a gpurun_out/r2_z6.log
 timeout 600 python -m pytest tests -m gpu -q -x -rxX > gpurun_out/r2_gpu_tests.log 2>&1
 echo "suite rc=$?" | tee -a gpurun_out/r2_gpu_tests.log
