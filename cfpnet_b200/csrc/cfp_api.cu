@@ -144,6 +144,9 @@ CFP_API int cfp_geometry_from_rects(const float* rects, int B, int Z, int max_wi
         float y0min = INFINITY, x0min = INFINITY, y1max = -INFINITY, x1max = -INFINITY;
         for (int z = 0; z < Z; ++z) {
             const float y0 = r[4 * z], x0 = r[4 * z + 1], y1 = r[4 * z + 2], x1 = r[4 * z + 3];
+            CFP_REQUIRE(std::isfinite(y0) && std::isfinite(x0) && std::isfinite(y1) && std::isfinite(x1) &&
+                        fabsf(y0) < 1e6f && fabsf(x0) < 1e6f && fabsf(y1) < 1e6f && fabsf(x1) < 1e6f,
+                        "rect_data[%d][%d] is not a finite pixel rectangle", b, z);
             hgt = fmaxf(hgt, y1 - y0);
             wid = fmaxf(wid, x1 - x0);
             up = fmaxf(up, fabsf(fminf(y0, 0.f)));

@@ -151,3 +151,7 @@ def test_c_abi_geometry_rejects_bad_arguments():
     assert rc != 0 and "640" in msg
     rc, _, msg = c_geometry(a, 640, 26, 34)                      # cell size 1: no patch_info entry in the reference either
     assert rc != 0 and "cell size" in msg
+    bad = a.copy()
+    bad[5, 2] = np.nan
+    rc, _, msg = c_geometry(bad, 40, 26, 34)
+    assert rc != 0 and "rect_data[0][5]" in msg
