@@ -12,10 +12,12 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 FUSION_CASES = [
     "G416_L3_B2", "G416_L2_B1", "G416_L1_B1", "G480_L3_B1", "G480pad_L3_B1", "G480pad_L2_B1",
     "G416_L3_B1_baseline", "G416_L3_B1_noskip", "G416_L3_B1_keepemb",
+    # round 2: every shape a bench configuration runs (BASELINE.json configs[1] / [3]) at every level it touches
+    "G480_L2_B1", "G480_L1_B1", "G480pad_L1_B1", "G416_L2_B1_baseline", "G416_L1_B1_baseline", "G416_L3_B16_baseline",
 ]
 # 6x6 zones of 64 px - the reference's training layout (--train_zone_num 6).  Fixtures from the reference; oracle,
 # geometry and (since the workspace-size fix, profiles/r1t_z6_gpu_check.log) the CUDA path are held to them.
-FUSION_CASES_Z6 = ["G416z6_L3_B2", "G416z6_L2_B1"]
+FUSION_CASES_Z6 = ["G416z6_L3_B2", "G416z6_L2_B1", "G416z6_L1_B1"]
 
 
 def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:

@@ -87,7 +87,8 @@ def test_hist_encoder_ragged_rows(dtype, tol):
 
 
 # ------------------------------------------------------------------ a2/a3
-@pytest.mark.parametrize("tag", ["G416_L3_B2", "G480_L3_B1", "G480pad_L3_B1", "G480pad_L2_B1", "G416_L1_B1"] + FUSION_CASES_Z6)
+@pytest.mark.parametrize("tag", ["G416_L3_B2", "G480_L3_B1", "G480pad_L3_B1", "G480pad_L2_B1", "G416_L1_B1", "G480_L2_B1", "G480_L1_B1",
+                                 "G480pad_L1_B1", "G416_L3_B16_baseline"] + FUSION_CASES_Z6)
 def test_masks_bit_exact(tag):
     case = FusionCase(tag)
     inp = case.inputs()
@@ -141,13 +142,8 @@ def test_fusion_bf16_vs_reference(tag):
     case.check_output(out, BF16_TOL, f"cuda bf16 {tag}")
 
 
-# the 6x6 training layout at every level against the oracle: L3 / L2 are also covered by the fixtures above and were
-# confirmed on a B200 (profiles/r1t_z6_gpu_check.log); L1 (256 cells per zone) has not run on a GPU yet - opt-in until
-# the first GPU call of the next round (tools/r2_first_call.sh sets CFP_TEST_EXTRA=1)
-_EXTRA = pytest.mark.skipif(not os.environ.get("CFP_TEST_EXTRA"), reason="not yet run on a GPU; CFP_TEST_EXTRA=1 to run")
-
-
-@pytest.mark.parametrize("geom", ["G416", pytest.param("G416z6", marks=_EXTRA)])
+# the 6x6 training layout at every level against the oracle (L1 = 256 cells per zone)
+@pytest.mark.parametrize("geom", ["G416", "G416z6"])
 @pytest.mark.parametrize("level", [3, 2, 1])
 def test_fusion_vs_oracle_batch3(level, geom):
     """Batch > 1 with per-frame masks, against the fp64 oracle on the same seeded inputs."""

@@ -165,9 +165,17 @@ def dump_keys():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    dump_keys()
-    hist_case()
+    only = [a for a in sys.argv[1:] if not a.startswith("-")]      # optional: regenerate just these fixture tags
     C1, BL = synth.COMBINE1_LAYERS, synth.BASELINE_LAYERS
+    _all_cases = fusion_case
+
+    def fusion_case(tag, *a, **kw):                                  # noqa: F811  (tag filter around the generator)
+        if not only or tag in only:
+            _all_cases(tag, *a, **kw)
+
+    if not only:
+        dump_keys()
+        hist_case()
     fusion_case("G416_L3_B2", "G416", 3, 2, C1)
     fusion_case("G416_L2_B1", "G416", 2, 1, C1)
     fusion_case("G416_L1_B1", "G416", 1, 1, C1)
@@ -179,3 +187,11 @@ if __name__ == "__main__":
     fusion_case("G416_L3_B1_keepemb", "G416", 3, 1, C1, change_embedding=False)
     fusion_case("G416z6_L3_B2", "G416z6", 3, 2, C1)      # 6x6 zones of 64 px: the reference's training layout
     fusion_case("G416z6_L2_B1", "G416z6", 2, 1, C1)
+    # round 2: every shape a bench configuration runs has a reference fixture at each level it touches
+    fusion_case("G480_L2_B1", "G480", 2, 1, C1)          # BASELINE configs[3] (latency_480): p = 7, 60 x 80
+    fusion_case("G480_L1_B1", "G480", 1, 1, C1)          # p = 14, 120 x 160: the map fills the table (no crop draw)
+    fusion_case("G480pad_L1_B1", "G480pad", 1, 1, C1)
+    fusion_case("G416_L2_B1_baseline", "G416", 2, 1, BL)  # BASELINE configs[1] (baseline_b16) at the other two levels
+    fusion_case("G416_L1_B1_baseline", "G416", 1, 1, BL)
+    fusion_case("G416_L3_B16_baseline", "G416", 3, 16, BL)  # ... and at its batch size
+    fusion_case("G416z6_L1_B1", "G416z6", 1, 1, C1)      # 6x6 training layout, 256 cells per zone
