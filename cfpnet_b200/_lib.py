@@ -18,7 +18,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcfp.so")
 
 CFP_F32, CFP_BF16 = 0, 1
-ABI_VERSION = 9
+ABI_VERSION = 10
 _fp = C.POINTER(C.c_float)
 
 
@@ -65,7 +65,7 @@ SIGNATURES = {
     "cfp_geometry_from_rects": (_i, [_fp, _i, _i, _i, _i, _i, C.POINTER(CfpGeom)]),
     "cfp_hist_encoder_fwd": (_i, [_p, _p, _p, _p, _i64, C.POINTER(CfpHistW), _i, _p]),
     "cfp_zone_masks": (_i, [_p, _p, _p, _p, _i, _i, _i, C.POINTER(CfpGeom), _p]),
-    "cfp_posenc_tokens_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "cfp_posenc_tokens_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "cfp_tokens_to_nchw": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "cfp_d2i_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, C.POINTER(CfpGeom),
                          C.POINTER(CfpLoftrW), _i, _p, _sz, _i, _p]),

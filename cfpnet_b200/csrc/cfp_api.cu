@@ -97,6 +97,16 @@ static int check_common(const void* p, int B, int H, int W, int C, int dtype) {
     CFP_REQUIRE(dtype == CFP_F32 || dtype == CFP_BF16, "unsupported dtype %d", dtype);
     return 0;
 }
+// Rows of the zone canvas must map one-to-one onto the zone rectangle (fusion.py:112-120,157): with no padding the
+// reference's pad_mask is all ones (fusion.py:119-120), so nothing of the canvas may overhang the map.
+static int check_canvas(const cfp_geom* g, int H, int W) {
+    int top = g->sy_wo < 0 ? -g->sy_wo : 0, left = g->sx_wo < 0 ? -g->sx_wo : 0;
+    int bot = g->ey_wo > H ? g->ey_wo - H : 0, right = g->ex_wo > W ? g->ex_wo - W : 0;
+    if (g->pad_h == 0 && g->pad_w == 0) top = left = bot = right = 0;
+    CFP_REQUIRE(g->tzh - top - bot == g->ry1 - g->ry0 && g->tzw - left - right == g->rx1 - g->rx0,
+                "in-image canvas cells do not match the zone rectangle (the reference's index_put fails here too)");
+    return 0;
+}
 static int check_geom(const cfp_geom* g, int H, int W) {
     CFP_REQUIRE(g != nullptr, "null geometry");
     CFP_REQUIRE(g->zone_num > 0 && g->p1 > 0 && g->p2 > 0 && g->tzh > 0 && g->tzw > 0, "degenerate zone geometry");
@@ -183,12 +193,7 @@ CFP_API int cfp_geometry_from_rects(const float* rects, int B, int Z, int max_wi
     CFP_REQUIRE(sy >= 0 && sx >= 0 && ey <= H + 2 * pad_h && ex <= W + 2 * pad_w,
                 "zone canvas [%d:%d,%d:%d] leaves the padded %dx%d map", sy, ey, sx, ex, H + 2 * pad_h, W + 2 * pad_w);
     CFP_REQUIRE(g.tzh > 0 && g.tzw > 0, "empty zone canvas");
-    int top = sy_wo < 0 ? -sy_wo : 0, lft = sx_wo < 0 ? -sx_wo : 0;
-    int bot = ey_wo > H ? ey_wo - H : 0, rgt = ex_wo > W ? ex_wo - W : 0;
-    if (pad_h == 0 && pad_w == 0) top = lft = bot = rgt = 0;
-    CFP_REQUIRE(g.tzh - top - bot == g.ry1 - g.ry0 && g.tzw - lft - rgt == g.rx1 - g.rx0,
-                "in-image canvas cells do not match the zone rectangle");
-    return 0;
+    return check_canvas(&g, H, W);
 }
 
 CFP_API int cfp_hist_encoder_fwd(const float* hist, void* out32, void* out64, void* out128, int64_t rows,
@@ -209,12 +214,13 @@ CFP_API int cfp_zone_masks(const uint8_t* mask, uint8_t* zone_mask, uint8_t* his
     return zone_masks(mask, zone_mask, hist_mask, pad_mask, B, H, W, *g, (cudaStream_t)stream);
 }
 
-CFP_API int cfp_posenc_tokens_fwd(const void* x_nchw, const float* pos, void* tokens, int B, int C, int H, int W, int pos_w,
-                          int oy, int ox, int dtype, void* stream) {
+CFP_API int cfp_posenc_tokens_fwd(const void* x_nchw, const float* pos, void* tokens, int B, int C, int H, int W, int pos_h,
+                          int pos_w, int oy, int ox, int dtype, void* stream) {
     begin_call(stream);
     CFP_REQUIRE(x_nchw && pos && tokens, "null pointer");
     CFP_REQUIRE(B > 0 && B <= 65535 && C > 0 && H > 0 && W > 0, "bad shape");
-    CFP_REQUIRE(oy >= 0 && ox >= 0 && ox + W <= pos_w, "positional-encoding crop out of range");
+    CFP_REQUIRE(oy >= 0 && ox >= 0 && ox + W <= pos_w && oy + H <= pos_h,
+                "positional-encoding crop [%d:%d,%d:%d] outside the %dx%d table", oy, oy + H, ox, ox + W, pos_h, pos_w);
     CFP_REQUIRE(dtype == CFP_F32 || dtype == CFP_BF16, "unsupported dtype %d", dtype);
     return posenc_tokens(x_nchw, pos, tokens, B, C, H, W, pos_w, oy, ox, dtype, (cudaStream_t)stream);
 }
@@ -235,11 +241,7 @@ CFP_API int cfp_d2i_fwd(void* feat0, const void* emb, const void* zone_tok, cons
     if (int e = check_geom(g, H, W)) return e;
     CFP_REQUIRE(emb && zone_tok && pos2 && mask && w && workspace, "null pointer");
     CFP_REQUIRE(S > 0, "zone_sample_num must be positive");
-    // rows of the zone canvas must map one-to-one onto the zone rectangle (fusion.py:157)
-    const int top = g->sy_wo < 0 ? -g->sy_wo : 0, left = g->sx_wo < 0 ? -g->sx_wo : 0;
-    const int bot = g->ey_wo > H ? g->ey_wo - H : 0, right = g->ex_wo > W ? g->ex_wo - W : 0;
-    CFP_REQUIRE(g->tzh - top - bot == g->ry1 - g->ry0 && g->tzw - left - right == g->rx1 - g->rx0,
-                "zone canvas does not match the zone rectangle (the reference's index_put fails here too)");
+    if (int e = check_canvas(g, H, W)) return e;
     WsLayout L = ws_layout(B, H, W, C, 0, 0, dtype, g);
     CFP_REQUIRE(workspace_bytes >= L.total, "workspace too small: %zu < %zu", workspace_bytes, L.total);
     return d2i(feat0, emb, zone_tok, pos2, mask, B, H, W, C, S, *g, *w, assign, (char*)workspace, L, dtype,

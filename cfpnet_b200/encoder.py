@@ -13,7 +13,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .packing import PackCache, fold_bn, umma_block
+from .packing import PackCache, Packer, fold_bn, host, relocate, umma_block
 
 
 class PointNetEncoder(nn.Module):
@@ -33,8 +33,8 @@ class PointNetEncoder(nn.Module):
         out = []
         for conv, bn in ((self.conv1, self.bn1), (self.conv2, self.bn2), (self.conv3, self.bn3)):
             scale, shift = fold_bn(bn)
-            w = conv.weight.detach().float()[:, :, 0] * scale[:, None]
-            out.append((w.t().contiguous(), (conv.bias.detach().float() * scale + shift).contiguous()))
+            w = host(conv.weight)[:, :, 0] * scale[:, None]
+            out.append((w.t().contiguous(), (host(conv.bias) * scale + shift).contiguous()))
         return out
 
 
@@ -52,19 +52,27 @@ class HistogramEncoder(nn.Module):
         self.hist_extractor2 = HistExtractor(in_channel=channels[0], out_channel=channels[1])
         self.hist_extractor3 = HistExtractor(in_channel=channels[1], out_channel=channels[2])
         self.out_dtype = None            # None -> float32; set to torch.bfloat16 for the bf16 path
-        self._cache = PackCache(self)
+        self._cache = PackCache()
+
+    def _replicate_for_data_parallel(self):
+        replica = super()._replicate_for_data_parallel()      # replicas own their pack cache (see TransformerFusion)
+        replica._cache = PackCache()
+        return replica
 
     def _pack(self):
         stages = []
         for ex in (self.hist_extractor1, self.hist_extractor2, self.hist_extractor3):
             stages += ex.pointnet_encoder.packed_stages()
+        keep = Packer()
         w = _lib.CfpHistW()
         for i, (wt, b) in enumerate(stages):
-            w.w_t[i], w.b[i] = wt.data_ptr(), b.data_ptr()
+            w.w_t[i], w.b[i] = keep.ref(wt), keep.ref(b)
         # tensor-core path: stages 1..8 as bf16 UMMA blocks ([Cout,Cin] weight -> [Cin/8][Cout][8]), concatenated
         tc = torch.cat([umma_block(wt.t()).reshape(-1) for wt, _ in stages[1:]]).contiguous()
-        w.tc = tc.data_ptr()
-        return w, (stages, tc)
+        w.tc = keep.ref(tc)
+        buf = keep.upload(self.hist_extractor1.pointnet_encoder.conv1.weight.device)    # one host->device copy
+        relocate(w, buf.data_ptr())
+        return w, (stages, tc, buf)
 
     def forward(self, hist_data):
         if self.training:
@@ -75,7 +83,7 @@ class HistogramEncoder(nn.Module):
         if D != 1:
             raise ValueError("hist_data must be [B,Z,N,1] (deltar.py:40)")
         dt = self.out_dtype or (hist_data.dtype if hist_data.dtype == torch.bfloat16 else torch.float32)
-        w, _keep = self._cache.get(self._pack)
+        w, _keep = self._cache.get(self, self._pack)
         x = hist_data.detach().reshape(-1).float().contiguous()
         rows = x.numel()
         outs = [torch.empty(B, Z, N, c, device=x.device, dtype=dt) for c in (32, 64, 128)]

@@ -19,7 +19,7 @@ from . import _lib
 from .config import args
 from .geometry import check_geometry, zone_geometry
 from .layers import Combine1, LoFTREncoderLayer, TwinsTransformer
-from .packing import PackCache
+from .packing import PackCache, Packer, Scratch, host, relocate
 
 
 class TransformerFusion(nn.Module):
@@ -52,21 +52,36 @@ class TransformerFusion(nn.Module):
                 raise NotImplementedError(name)           # fusion.py:37
         self.layers = nn.ModuleList(layers)
         self.conv_patch_size = 640 / self.max_resolution[1]
-        self._cache = PackCache(self)
+        self._cache = PackCache()
+        self._scratch = Scratch()
+
+    def _replicate_for_data_parallel(self):
+        """``nn.DataParallel`` replicas copy ``__dict__`` shallowly: give each its own pack cache and scratch (the
+        original's hold device-0 pointers) - replicas run concurrently, one thread per GPU (train.py:45)."""
+        replica = super()._replicate_for_data_parallel()
+        replica._cache = PackCache()
+        replica._scratch = Scratch()
+        return replica
 
     # ------------------------------------------------------------------ packing
     def _pack(self):
-        keep = []
+        """Weight structs of every layer + the two positional tables: packed on the host, one flat device buffer
+        (``buf``), struct fields relocated to device pointers.  Returns (structs, pos ptr, pos2 ptr, buf)."""
+        keep = Packer()
         packed = []
         for layer, name in zip(self.layers, self.layer_names):
             if name == "combine1":
                 packed.append((layer.transformer_path.pack(keep), layer.large_kernel_path.pack(keep)))
             else:
                 packed.append(layer.pack(keep))
-        pos = self.positional_encodings.detach().float().contiguous()
-        pos2 = self.positional_encodings2.detach().float().contiguous()
-        keep += [pos, pos2]
-        return packed, pos, pos2, keep
+        pos = keep.ref(host(self.positional_encodings).contiguous())
+        pos2 = keep.ref(host(self.positional_encodings2).contiguous())
+        buf = keep.upload(self.positional_encodings.device)
+        base = buf.data_ptr()
+        for w in packed:
+            for s_ in (w if isinstance(w, tuple) else (w,)):
+                relocate(s_, base)
+        return packed, base + pos, base + pos2, buf
 
     # ------------------------------------------------------------------ forward
     def forward(self, x, feat1, **kwargs):
@@ -86,6 +101,14 @@ class TransformerFusion(nn.Module):
             check_geometry(g, H, W)
         if feat1.shape[0] != B or feat1.shape[1] != g.zone_num ** 2 or feat1.shape[3] != D:
             raise ValueError(f"feat1 {tuple(feat1.shape)} does not match B={B}, zones={g.zone_num ** 2}, D={D}")
+        if S != self.positional_encodings2.shape[0]:     # the reference's `feat1 + positional_encodings2` fails to broadcast
+            raise ValueError(f"feat1 carries {S} samples per zone, positional_encodings2 has {self.positional_encodings2.shape[0]}")
+        if tuple(kwargs["mask"].shape) != (B, g.zone_num ** 2):
+            raise ValueError(f"mask {tuple(kwargs['mask'].shape)} is not [B={B}, zones={g.zone_num ** 2}]")
+        if torch.is_grad_enabled() and (x.requires_grad or feat1.requires_grad):
+            raise RuntimeError("TransformerFusion (libcfp, eval mode) returns a tensor without autograd history: an input "
+                               "that requires grad would have its gradient cut silently; call under torch.no_grad() or "
+                               "detach the inputs")
 
         # positional-encoding crop: same draws, same order as fusion.py:87-91
         oy = ox = 0
@@ -96,7 +119,7 @@ class TransformerFusion(nn.Module):
         if H > self.max_resolution[0] or W > self.max_resolution[1]:
             raise ValueError("feature map larger than the positional-encoding table")
 
-        packed, pos, pos2, _keep = self._cache.get(self._pack)
+        packed, pos, pos2, _buf = self._cache.get(self, self._pack)
         dev = x.device
         x = x.detach().contiguous()
         feat1 = feat1.detach().to(dt).contiguous()
@@ -110,16 +133,13 @@ class TransformerFusion(nn.Module):
             # makes that safe for back-to-back forwards on one stream, and it keeps hundreds of MB of
             # per-call allocations (cudaMalloc stalls once several streams are in play) off the hot path.
             # One module instance must not run on two streams at once (replicas own their scratch).
-            key = (dev.index, dt, B, H, W)
-            scratch = self.__dict__.setdefault("_scratch", {})
-            if key not in scratch or scratch[key][0].numel() < ws_bytes:
-                scratch.clear()
-                scratch[key] = (torch.empty(ws_bytes, device=dev, dtype=torch.uint8),
-                                torch.empty(B, H * W, D, device=dev, dtype=dt))
-            work, feat0 = scratch[key]
+            work, feat0 = self._scratch.get(
+                dev.index, (dt, B, H, W), lambda t: t[0].numel() >= ws_bytes,
+                lambda: (torch.empty(ws_bytes, device=dev, dtype=torch.uint8),
+                         torch.empty(B, H * W, D, device=dev, dtype=dt)))
             st = _lib.stream_ptr()
-            _lib.call("cfp_posenc_tokens_fwd", x.data_ptr(), pos.data_ptr(), feat0.data_ptr(), B, D, H, W,
-                      self.max_resolution[1], oy, ox, code, st)
+            _lib.call("cfp_posenc_tokens_fwd", x.data_ptr(), pos, feat0.data_ptr(), B, D, H, W,
+                      self.max_resolution[0], self.max_resolution[1], oy, ox, code, st)
             emb = feat0
             if not args.change_embedding and "hist2image" in self.layer_names:
                 emb = feat0.clone()                          # fusion.py:134-136: canvas cut from the first map
@@ -128,7 +148,7 @@ class TransformerFusion(nn.Module):
                     _lib.call("cfp_twins_fwd", feat0.data_ptr(), B, H, W, D, C.byref(w), work.data_ptr(),
                               ws_bytes, code, st)
                 elif name == "hist2image":
-                    _lib.call("cfp_d2i_fwd", feat0.data_ptr(), emb.data_ptr(), feat1.data_ptr(), pos2.data_ptr(),
+                    _lib.call("cfp_d2i_fwd", feat0.data_ptr(), emb.data_ptr(), feat1.data_ptr(), pos2,
                               mask.data_ptr(), B, H, W, D, S, C.byref(cg), C.byref(w),
                               int(bool(args.no_skip_inside)), work.data_ptr(), ws_bytes, code, st)
                 else:   # combine1: DAPM then LKPM (transformer.py:270-273)

@@ -13,7 +13,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .packing import fold_bn, linear_t, umma_block
+from .packing import Packer, fold_bn, host, linear_t, umma_block
 
 
 class LinearAttention(nn.Module):
@@ -44,26 +44,26 @@ class LoFTREncoderLayer(nn.Module):
         self.norm1 = nn.LayerNorm(d_model)
         self.norm2 = nn.LayerNorm(d_model)
 
-    def pack(self, keep: list) -> _lib.CfpLoftrW:
+    def pack(self, keep: Packer) -> _lib.CfpLoftrW:
         t = dict(
             wq_t=linear_t(self.q_proj.weight),
             wkv_t=torch.cat([linear_t(self.k_proj.weight), linear_t(self.v_proj.weight)], dim=1).contiguous(),
             wm_t=linear_t(self.merge.weight),
             w1_t=linear_t(self.mlp[0].weight),
             w2_t=linear_t(self.mlp[2].weight),
-            ln1_g=self.norm1.weight.detach().float().contiguous(),
-            ln1_b=self.norm1.bias.detach().float().contiguous(),
-            ln2_g=self.norm2.weight.detach().float().contiguous(),
-            ln2_b=self.norm2.bias.detach().float().contiguous(),
+            ln1_g=host(self.norm1.weight).contiguous(),
+            ln1_b=host(self.norm1.bias).contiguous(),
+            ln2_g=host(self.norm2.weight).contiguous(),
+            ln2_b=host(self.norm2.bias).contiguous(),
         )
         C = self.q_proj.weight.shape[0]
-        w1, w2 = self.mlp[0].weight, self.mlp[2].weight
+        w1, w2 = self.mlp[0].weight.detach().cpu(), self.mlp[2].weight.detach().cpu()
         t["tc"] = torch.stack([umma_block(b) for b in (
             self.q_proj.weight, self.merge.weight, w1[:C, :C], w1[:C, C:], w1[C:, :C], w1[C:, C:],
             w2[:, :C], w2[:, C:])]).contiguous()
         t["kv_tc"] = torch.stack([umma_block(self.k_proj.weight), umma_block(self.v_proj.weight)]).contiguous()
         keep.extend(t.values())
-        return _lib.CfpLoftrW(**{k: v.data_ptr() for k, v in t.items()})
+        return _lib.CfpLoftrW(**{k: keep.ref(v) for k, v in t.items()})
 
 
 class LocallyGroupedAttn(nn.Module):
@@ -102,7 +102,7 @@ class TwinsTransformer(nn.Module):
         self.lga = LocallyGroupedAttn(dim=dim, ws=ws)
         self.gsa = GlobalSubSampleAttn(dim=dim, sr_ratio=ws)
 
-    def pack(self, keep: list) -> _lib.CfpTwinsW:
+    def pack(self, keep: Packer) -> _lib.CfpTwinsW:
         if self.gsa.sr is None:
             raise _lib.CfpError("libcfp serves GSA with sr_ratio > 1 only")
         C, ws = self.gsa.dim, self.gsa.sr_ratio
@@ -110,15 +110,16 @@ class TwinsTransformer(nn.Module):
         w.lsa = self.lga.encoder_layer.pack(keep)
         w.gsa = self.gsa.encoder_layer.pack(keep)
         # [Cout,Cin,ws,ws] -> [(dy,dx,cin)][Cout]
-        sr_t = self.gsa.sr.weight.detach().float().permute(2, 3, 1, 0).reshape(ws * ws * C, C).contiguous()
-        t = dict(sr_t=sr_t, sr_b=self.gsa.sr.bias.detach().float().contiguous(),
-                 srln_g=self.gsa.norm.weight.detach().float().contiguous(),
-                 srln_b=self.gsa.norm.bias.detach().float().contiguous(),
-                 sr_tc=torch.stack([umma_block(self.gsa.sr.weight[:, :, dy, dx])
+        srw = self.gsa.sr.weight.detach().cpu()
+        sr_t = srw.float().permute(2, 3, 1, 0).reshape(ws * ws * C, C).contiguous()
+        t = dict(sr_t=sr_t, sr_b=host(self.gsa.sr.bias).contiguous(),
+                 srln_g=host(self.gsa.norm.weight).contiguous(),
+                 srln_b=host(self.gsa.norm.bias).contiguous(),
+                 sr_tc=torch.stack([umma_block(srw[:, :, dy, dx])
                                     for dy in range(ws) for dx in range(ws)]).contiguous())
         keep.extend(t.values())
         for k, v in t.items():
-            setattr(w, k, v.data_ptr())
+            setattr(w, k, keep.ref(v))
         w.ws = ws
         return w
 
@@ -149,7 +150,7 @@ class LoFTREncoderLayer_newcross9(nn.Module):
         self.bn2 = nn.BatchNorm2d(d_model)
         self.relu = nn.ReLU()
 
-    def pack(self, keep: list) -> _lib.CfpDapmW:
+    def pack(self, keep: Packer) -> _lib.CfpDapmW:
         if self.nhead != 4:
             raise _lib.CfpError("libcfp serves DAPM with 4 heads (fusion.py:13)")
         w = _lib.CfpDapmW()
@@ -160,10 +161,10 @@ class LoFTREncoderLayer_newcross9(nn.Module):
             kv_tc=torch.stack([umma_block(self.k_proj.weight), umma_block(self.v_proj.weight)]).contiguous(),
         )
         keep.extend(t.values())
-        w.attn = _lib.CfpLoftrW(**{k: v.data_ptr() for k, v in t.items()})
+        w.attn = _lib.CfpLoftrW(**{k: keep.ref(v) for k, v in t.items()})
         for i, (conv, bn) in enumerate(((self.conv1, self.bn1), (self.conv2, self.bn2)), start=1):
             scale, shift = fold_bn(bn)
-            ws = conv.weight.detach().float() * scale[:, None, None, None]          # [Cout,Cin,3,3]
+            ws = host(conv.weight) * scale[:, None, None, None]                     # [Cout,Cin,3,3]
             cout, cin = ws.shape[0], ws.shape[1]
             wt = ws.permute(2, 3, 1, 0).reshape(9 * cin, cout).contiguous()
             # tensor-core blocks: one [Cout x Cout-wide K] block per (source, tap)
@@ -171,9 +172,9 @@ class LoFTREncoderLayer_newcross9(nn.Module):
                               for s0 in range(0, cin, cout) for ky in range(3) for kx in range(3)]).contiguous()
             shift = shift.contiguous()
             keep.extend((wt, shift, pk))
-            setattr(w, f"conv{i}_t", wt.data_ptr())
-            setattr(w, f"shift{i}", shift.data_ptr())
-            setattr(w, f"conv{i}_pk", pk.data_ptr())
+            setattr(w, f"conv{i}_t", keep.ref(wt))
+            setattr(w, f"shift{i}", keep.ref(shift))
+            setattr(w, f"conv{i}_pk", keep.ref(pk))
         return w
 
 
@@ -209,31 +210,31 @@ class Block14(nn.Module):
         self.bn1 = nn.BatchNorm2d(dim)
         self.relu = nn.ReLU()
 
-    def pack(self, keep: list) -> _lib.CfpLkpmW:
+    def pack(self, keep: Packer) -> _lib.CfpLkpmW:
         k = self.dwconv2.kernel_size[0]
         scale, shift = fold_bn(self.bn1)
         C = scale.numel()
-        taps = self.dwconv2.weight.detach().float()[:, 0] * scale[:, None, None]        # [C,k,k]
+        taps = host(self.dwconv2.weight)[:, 0] * scale[:, None, None]                   # [C,k,k]
         t = dict(
             dw_t=taps.permute(1, 2, 0).reshape(k * k, C).contiguous(),
-            dw_shift=(self.dwconv2.bias.detach().float() * scale + shift).contiguous(),
-            ln_g=self.norm.weight.detach().float().contiguous(),
-            ln_b=self.norm.bias.detach().float().contiguous(),
+            dw_shift=(host(self.dwconv2.bias) * scale + shift).contiguous(),
+            ln_g=host(self.norm.weight).contiguous(),
+            ln_b=host(self.norm.bias).contiguous(),
             pw1_t=linear_t(self.pwconv1.weight),
-            pw1_b=self.pwconv1.bias.detach().float().contiguous(),
+            pw1_b=host(self.pwconv1.bias).contiguous(),
             pw2_t=linear_t(self.pwconv2.weight),
-            pw2_b=self.pwconv2.bias.detach().float().contiguous(),
+            pw2_b=host(self.pwconv2.bias).contiguous(),
         )
         # tensor-core MLP (csrc/k_chain_tc.cu: MlpTC): per 128-wide hidden slice j two blocks, W1_j then W2_j, each padded
         # to the ring-slot size.  The LayerNorm affine is folded into W1 / b1, and both biases ride in one extra 16-column
         # K step (first column = bias) that meets a constant ones-column of the A operand.  W1_j: bf16 [128][C+16];
         # W2_j: fp16 [C][128+16] (the GELU output feeds the second GEMM as fp16).
-        g_ln, b_ln = self.norm.weight.detach().float(), self.norm.bias.detach().float()
-        w1 = self.pwconv1.weight.detach().float()
-        w2 = self.pwconv2.weight.detach().float()
-        b1 = self.pwconv1.bias.detach().float() + w1 @ b_ln
+        g_ln, b_ln = host(self.norm.weight), host(self.norm.bias)
+        w1 = host(self.pwconv1.weight)
+        w2 = host(self.pwconv2.weight)
+        b1 = host(self.pwconv1.bias) + w1 @ b_ln
         w1 = w1 * g_ln[None, :]
-        b2 = self.pwconv2.bias.detach().float()
+        b2 = host(self.pwconv2.bias)
         blk = max(128 * (C + 16) * 2, C * 144 * 2)          # bytes (MlpTC::BLK)
         blocks = []
         for j in range(4 * C // 128):
@@ -258,7 +259,7 @@ class Block14(nn.Module):
         toep = torch.cat([toep, toep.new_zeros(C, nb * na - k, 32, 16 * ks)], dim=1)
         t["dw_toep"] = (toep.to(torch.bfloat16).view(C, na, nb, 32, ks, 2, 8).permute(0, 1, 4, 5, 2, 3, 6).contiguous())
         keep.extend(t.values())
-        w = _lib.CfpLkpmW(**{n: v.data_ptr() for n, v in t.items()})
+        w = _lib.CfpLkpmW(**{n: keep.ref(v) for n, v in t.items()})
         w.ksize = k
         return w
 

@@ -59,7 +59,7 @@ class FusionPath(nn.Module):
         side = self.__dict__.setdefault("_level_streams", {}).setdefault(str(dev), [torch.cuda.Stream(dev) for _ in range(2)])
         # results are allocated on the caller's stream (no cross-stream allocator traffic: record_stream()
         # on side-stream tensors turns into a cudaMalloc per step, and those occasionally stall for ~100 ms)
-        outs = [torch.empty_like(x) for _, x, _ in jobs]
+        outs = [torch.empty_like(x, memory_format=torch.contiguous_format) for _, x, _ in jobs]
         fork = torch.cuda.Event()
         fork.record(cur)
         joins = []

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define CFP_ABI_VERSION 9
+#define CFP_ABI_VERSION 10
 
 #if defined(__GNUC__)
 #define CFP_API __attribute__((visibility("default")))
@@ -157,9 +157,10 @@ CFP_API int cfp_zone_masks(const uint8_t *mask, uint8_t *zone_mask, uint8_t *his
                    int B, int H, int W, const cfp_geom *g, void *stream);
 
 /* a4. Positional-encoding add + NCHW -> token-major (fusion.py:92-97):
- * tokens[b][y*W+x][c] = x[b][c][y][x] + pos[(oy+y)*pos_w + ox+x][c]. */
+ * tokens[b][y*W+x][c] = x[b][c][y][x] + pos[(oy+y)*pos_w + ox+x][c]; pos is the
+ * [pos_h*pos_w][C] table (max_resolution), the crop must lie inside it. */
 CFP_API int cfp_posenc_tokens_fwd(const void *x_nchw, const float *pos, void *tokens, int B, int C, int H,
-                          int W, int pos_w, int oy, int ox, int dtype, void *stream);
+                          int W, int pos_h, int pos_w, int oy, int ox, int dtype, void *stream);
 /* fusion.py:186: token-major -> contiguous NCHW. */
 CFP_API int cfp_tokens_to_nchw(const void *tokens, void *out_nchw, int B, int C, int H, int W, int dtype,
                        void *stream);

@@ -33,7 +33,7 @@ def layer_call(m, name, layer_idx, feat0, geom_name="G416", level=3, mask=None, 
     g = geometry.zone_geometry(inp["patch_info"], m.max_resolution[1], H, W)
     cg = _lib.CfpGeom.from_geometry(g)
     code = _lib.dtype_code(feat0.dtype)
-    packed, pos, pos2, _keep = m._cache.get(m._pack)
+    packed, pos, pos2, _keep = m._cache.get(m, m._pack)
     lib = _lib.load()
     nbytes = lib.cfp_workspace_bytes(B, H, W, C, m.ws, m.large_kernel, code, ctypes.byref(cg))
     work = torch.empty(nbytes, device=DEV, dtype=torch.uint8)
@@ -50,7 +50,7 @@ def layer_call(m, name, layer_idx, feat0, geom_name="G416", level=3, mask=None, 
     elif name == "twins":
         _lib.call("cfp_twins_fwd", x.data_ptr(), B, H, W, C, ctypes.byref(w), work.data_ptr(), nbytes, code, st)
     elif name == "d2i":
-        _lib.call("cfp_d2i_fwd", x.data_ptr(), x.data_ptr(), feat1.data_ptr(), pos2.data_ptr(), mask.data_ptr(),
+        _lib.call("cfp_d2i_fwd", x.data_ptr(), x.data_ptr(), feat1.data_ptr(), pos2, mask.data_ptr(),
                   B, H, W, C, feat1.shape[2], ctypes.byref(cg), ctypes.byref(w), 0, work.data_ptr(), nbytes, code, st)
     torch.cuda.synchronize()
     return x, g

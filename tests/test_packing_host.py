@@ -8,7 +8,7 @@ import torch.nn.functional as F
 import cfpnet_b200
 from cfpnet_b200 import _lib, synth
 from cfpnet_b200.config import args
-from cfpnet_b200.packing import fold_bn, umma_block
+from cfpnet_b200.packing import Packer, fold_bn, umma_block
 
 
 def from_umma(block, n, k):
@@ -35,7 +35,7 @@ def make_block(C, k):
 def test_toeplitz_pack_reproduces_the_depthwise_conv(C, k, H, W, B):
     """Emulates dwconv_tc: vertical taps dy = 4a + b stacked along N, out[r] = sum_b E_b[r + b], on zero-padded planes."""
     blk = make_block(C, k)
-    keep = []
+    keep = Packer()
     w = blk.pack(keep)
     toep = next(t for t in keep if t.dtype == torch.bfloat16 and t.dim() == 7)      # [C][NA][KS][2][NB][32][8]
     nb, pad = 4, (k - 1) // 2
@@ -65,7 +65,7 @@ def test_toeplitz_pack_reproduces_the_depthwise_conv(C, k, H, W, B):
 def test_mlp_fold_reproduces_layernorm_mlp(C):
     """W1' = W1 diag(g), b1' = b1 + W1 b ride in [LNhat(y) | 1]; b2 rides in [GELU(h) | 1] of slice 0 (MlpTC)."""
     blk = make_block(C, 7)
-    keep = []
+    keep = Packer()
     blk.pack(keep)
     tc = next(t for t in keep if t.dtype == torch.uint8)
     bsz = max(128 * (C + 16) * 2, C * 144 * 2)
@@ -91,7 +91,7 @@ def test_mlp_fold_reproduces_layernorm_mlp(C):
 def test_hist_encoder_tc_blocks_decode_to_the_folded_stages():
     enc = cfpnet_b200.HistogramEncoder()
     enc.load_state_dict(synth.synthetic_state_dict({k: v.shape for k, v in enc.state_dict().items()}, 0))
-    w, (stages, tc) = enc.eval()._pack()
+    w, (stages, tc, _buf) = enc.eval()._pack()
     off = 0
     for wt, _b in stages[1:]:                                   # stage i: wt [Cin, Cout] -> block [Cin/8][Cout][8]
         cin, cout = wt.shape
@@ -117,7 +117,7 @@ def test_dapm_conv_blocks_reproduce_conv_bn(C):
     added by the epilogue (k_conv_tc.cu walks source-major, tap = ky*3+kx, over the zero-padded raster) - and the
     fp32 engine's [(tap, cin)][Cout] layout - both against conv2d + batch_norm."""
     m = _loaded(cfpnet_b200.layers.LoFTREncoderLayer_newcross9(C, 4), seed=5).double()
-    keep = []
+    keep = Packer()
     m.pack(keep)
     attn, convs = keep[:4], keep[4:]
     assert len(convs) == 6
@@ -164,7 +164,7 @@ def test_loftr_chain_blocks_follow_the_consumption_order(C, nhead):
     W1 quadrants accumulated as  hidden[:, :C] = x B2^T + msg B3^T,  hidden[:, C:] = x B4^T + msg B5^T  |
     out = hidden[:, :C] B6^T + hidden[:, C:] B7^T.  Emulated in float64 against the nn.Linear layers."""
     m = _loaded(cfpnet_b200.layers.LoFTREncoderLayer(C, nhead), seed=9)
-    keep = []
+    keep = Packer()
     m.pack(keep)
     names = ["wq_t", "wkv_t", "wm_t", "w1_t", "w2_t", "ln1_g", "ln1_b", "ln2_g", "ln2_b", "tc", "kv_tc"]
     t = dict(zip(names, keep))
@@ -193,7 +193,7 @@ def test_gsa_subsampling_blocks_reproduce_the_strided_conv(C, ws):
     accumulates  out[token] = sum_taps x[token*ws + (dy,dx)] B_tap^T  over a split of the taps; sr_t is the fp32
     engine's [(dy, dx, cin)][Cout] layout."""
     m = _loaded(cfpnet_b200.layers.TwinsTransformer(C, ws=ws), seed=2)
-    keep = []
+    keep = Packer()
     m.pack(keep)
     sr_t, sr_b, _, _, sr_tc = keep[-5:]
     H, W = 2 * ws, 3 * ws
@@ -211,3 +211,44 @@ def test_gsa_subsampling_blocks_reproduce_the_strided_conv(C, ws):
     bias = sr_b.double().view(1, C, 1, 1)
     assert torch.allclose(got + bias, want_bf, rtol=1e-9, atol=1e-9)
     assert torch.allclose(got32 + bias, want, rtol=1e-5, atol=1e-5)
+
+
+# ------------------------------------------------------------------ pack cache / flat buffer plumbing
+def test_packer_lays_tensors_out_in_one_flat_buffer_and_relocate_turns_offsets_into_pointers():
+    from cfpnet_b200.packing import relocate
+    keep = Packer()
+    a, b = torch.arange(5, dtype=torch.float32), torch.arange(7, dtype=torch.int16).to(torch.bfloat16)
+    oa, ob = keep.ref(a), keep.ref(b)
+    assert oa == Packer.ALIGN and ob == 2 * Packer.ALIGN and keep.ref(a) == oa         # 0 stays the null pointer
+    flat = keep.upload("cpu")
+    assert torch.equal(flat[oa:oa + 20].view(torch.float32), a) and torch.equal(flat[ob:ob + 14].view(torch.bfloat16), b)
+    w = _lib.CfpTwinsW()
+    w.lsa.wq_t, w.sr_b, w.ws = oa, ob, 6
+    relocate(w, 1 << 20)
+    assert w.lsa.wq_t == (1 << 20) + oa and w.sr_b == (1 << 20) + ob and w.ws == 6 and not w.gsa.wq_t and not w.sr_t
+    h = _lib.CfpHistW()
+    h.w_t[3] = oa
+    relocate(h, 4096)
+    assert h.w_t[3] == 4096 + oa and not h.w_t[0] and not h.tc
+
+
+def test_data_parallel_replicas_own_their_pack_cache_and_scratch():
+    """nn.DataParallel replicas share the original's __dict__ entries: a shared cache would publish device-0
+    weight pointers to every replica.  Replicas get fresh caches, are never cached (their parameters are re-broadcast
+    on every forward), and the original's cache is keyed by the caller's own tensors."""
+    import copy
+    args.attention_layer = list(synth.COMBINE1_LAYERS)
+    m = cfpnet_b200.TransformerFusion(32, [120, 160], large_kernel=31, patch_size=16).eval()
+    r = m._replicate_for_data_parallel()
+    assert r._cache is not m._cache and r._scratch is not m._scratch and r._is_replica
+    enc = cfpnet_b200.HistogramEncoder().eval()
+    assert enc._replicate_for_data_parallel()._cache is not enc._cache
+    calls = []
+    build = lambda: calls.append(1) or len(calls)                                      # noqa: E731
+    assert m._cache.get(m, build) == 1 and m._cache.get(m, build) == 1                 # cached for the original
+    with torch.no_grad():
+        m.positional_encodings.add_(1.0)                                               # version bump -> re-pack
+    assert m._cache.get(m, build) == 2
+    assert r._cache.get(r, build) == 3 and r._cache.get(r, build) == 4                 # replicas: never cached
+    m2 = copy.deepcopy(m)                                                              # locks inside do not break deepcopy
+    assert m2._cache is not m._cache and m2._cache.get(m2, build) == 5

@@ -19,7 +19,7 @@ from cfpnet_b200 import geometry
 g = geometry.zone_geometry(inp["patch_info"], max_res[1], H, W)
 cg = _lib.CfpGeom.from_geometry(g)
 code = _lib.CFP_BF16
-packed, pos, pos2, keep = m._cache.get(m._pack)
+packed, pos, pos2, keep = m._cache.get(m, m._pack)
 lib = _lib.load()
 nbytes = lib.cfp_workspace_bytes(B, H, W, C, m.ws, m.large_kernel, code, ctypes.byref(cg))
 work = torch.zeros(nbytes, device="cuda", dtype=torch.uint8)

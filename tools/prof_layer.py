@@ -22,7 +22,7 @@ inp = synth.make_inputs("G416", B, levels=())
 g = geometry.zone_geometry(inp["patch_info"], max_res[1], H, W)
 cg = _lib.CfpGeom.from_geometry(g)
 code = _lib.CFP_BF16
-packed, pos, pos2, keep = m._cache.get(m._pack)
+packed, pos, pos2, keep = m._cache.get(m, m._pack)
 lib = _lib.load()
 nbytes = lib.cfp_workspace_bytes(B, H, W, C, m.ws, m.large_kernel, code, ctypes.byref(cg))
 work = torch.empty(nbytes, device="cuda", dtype=torch.uint8)
@@ -38,7 +38,7 @@ for it in range(3):
     elif name == "twins":
         _lib.call("cfp_twins_fwd", x.data_ptr(), B, H, W, C, ctypes.byref(packed[2]), work.data_ptr(), nbytes, code, st)
     elif name == "d2i":
-        _lib.call("cfp_d2i_fwd", x.data_ptr(), x.data_ptr(), feat1.data_ptr(), pos2.data_ptr(), mask.data_ptr(), B, H, W, C, 16,
+        _lib.call("cfp_d2i_fwd", x.data_ptr(), x.data_ptr(), feat1.data_ptr(), pos2, mask.data_ptr(), B, H, W, C, 16,
                   ctypes.byref(cg), ctypes.byref(packed[0]), 0, work.data_ptr(), nbytes, code, st)
 torch.cuda.synchronize()
 print("done")
