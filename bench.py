@@ -51,6 +51,56 @@ def load_peaks():
                 "source": "fallback (B200_PROFILING.md)"}
 
 
+def bind_host_to_gpu(index):
+    """Pin this process to the CPU cores NVML reports as local to GPU `index` (its NUMA node) BEFORE the pinned host
+    buffers are allocated, so that first-touch places them on that node and the copy engine does not cross the socket
+    interconnect.  Returns a short description for the JSON line (or why nothing was done)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [w * 64 + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1 and w * 64 + b < ncpu]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return "nvml affinity empty / outside the cgroup: not bound"
+        os.sched_setaffinity(0, allowed)
+        try:
+            numa = pynvml.nvmlDeviceGetNumaNodeId(h)
+        except Exception:
+            numa = None
+        return f"bound to {len(allowed)} cpus [{allowed[0]}..{allowed[-1]}] (NVML affinity of GPU {index}, numa {numa})"
+    except Exception as e:                                  # noqa: BLE001
+        return f"not bound ({type(e).__name__}: {e})"
+
+
+def probe_host_link(dev, nbytes_in, nbytes_out, barrier, reps=6):
+    """Host<->device copy ceiling of THIS run: every rank copies `nbytes_in` host->device and `nbytes_out` device->host
+    concurrently (two streams, pinned buffers), all ranks at once - the traffic pattern of the e2e loop without any
+    compute.  Returns seconds per (in + out) pair on this rank."""
+    h_in = torch.empty(nbytes_in, dtype=torch.uint8).pin_memory()
+    h_out = torch.empty(nbytes_out, dtype=torch.uint8).pin_memory()
+    d_in = torch.empty(nbytes_in, dtype=torch.uint8, device=dev)
+    d_out = torch.empty(nbytes_out, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def both():
+        with torch.cuda.stream(s1):
+            d_in.copy_(h_in, non_blocking=True)
+        with torch.cuda.stream(s2):
+            h_out.copy_(d_out, non_blocking=True)
+    both()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        both()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / reps
+    barrier()
+    return dt
+
+
 class ClockSampler(threading.Thread):
     """SM clock and throttle reasons during the timed region, read in-process through NVML
     (nvidia_ml_py) every 200 ms plus one explicit sample in the middle of the timed loop.  Clock queries
@@ -215,6 +265,7 @@ def run_cfp(a):
     build()
     dtype = {"bf16": torch.bfloat16, "f32": torch.float32}[a.dtype]
     B = a.batch
+    host_binding = bind_host_to_gpu(local) if not os.environ.get("CFP_BENCH_NO_BIND") else "off (CFP_BENCH_NO_BIND)"
 
     path = FusionPath(synth.COMBINE1_LAYERS)
     path.hist_encoder.load_state_dict(synth.synthetic_state_dict(
@@ -341,6 +392,9 @@ def run_cfp(a):
             if not perturbed:
                 break
 
+        # ---- what the host link gives this run: the e2e loop's copies alone (no compute), all ranks at once
+        link_s = max_over_ranks(probe_host_link(dev, h2d, d2h, barrier) * 1e3) * 1e-3
+
         # ---- per-kernel breakdown with CUDA events on the launch stream (roofline)
         prof = None
         if rank == 0:
@@ -367,7 +421,12 @@ def run_cfp(a):
         "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": a.dtype, "data": "synthetic", "config": workload_config(a, B),
         "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h},
+                "d2h_bytes_per_step": d2h,
+                # the copies of one step alone, every rank at once (slowest rank): the host link's ceiling for this metric
+                "host_link": {"copy_only_ms_per_step": link_s * 1e3, "ceiling_frames_per_s": B * world / link_s,
+                              "GBps_each_way_per_gpu": [h2d / link_s / 1e9, d2h / link_s / 1e9],
+                              "e2e_frac_of_ceiling": (frames / (ms_e2e * 1e-3)) / (B * world / link_s),
+                              "host_binding": host_binding}},
         "gpu_launches": int(launches), "clocks": clocks,
         "step_ms": {"min": min(step_ms), "median": statistics.median(step_ms), "max": max(step_ms)},
         "timed_attempts_ms": attempts, "e2e_attempts_ms": e2e_attempts, "allocator_in_timed_region": alloc_delta,
@@ -413,7 +472,7 @@ def kernel_work(name, B, es):
     if not m:
         return None
     v = int(m.group(1))
-    if name.startswith("dwconv"):                       # dwconv<k> / dwconv_tc<k>: v is the kernel size
+    if name.startswith(("dwconv", "tr_dwconv_wgrad")):  # dwconv<k> / dwconv_tc<k> / weight gradient: v is the kernel size
         C = {31: 32, 15: 64, 7: 128}[v]
         g = LEVEL[C]
         return dict(flops=2.0 * g["N"] * C * v * v * B, bytes=2.0 * g["N"] * C * es * B, bound="tensor" if "_tc" in name else "fma")
@@ -588,18 +647,248 @@ def run_aux(a):
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------------- training step (BASELINE.json configs[4])
+def run_train(a):
+    """--workload train_b32: the training step of the part of the path whose train-mode forward + backward exists as
+    CUDA (histogram encoder + the LKPM block of each decoder level; the attention layers and DAPM convs are not built
+    yet - DESIGN.md section 8), 32 frames per GPU, fp32 as the reference trains (train.py:96-135):
+
+        zero_grad -> forward (BatchNorm on per-replica batch statistics) -> backward -> NCCL all-reduce of the flat
+        gradient bucket -> clip_grad_norm_(0.1) -> AdamW
+
+    `value` = frames/s of that step with inputs resident in HBM; `e2e` = the same with the step's inputs copied from
+    pinned host memory and the gradient norm read back.  `collective` reports the all-reduce inside the step (bytes,
+    CUDA-event time, share of the step, bus bandwidth) and, separately, the same NCCL all-reduce on a bucket of the
+    size the COMPLETE path's gradients have (26.6 MB fp32)."""
+    import torch.distributed as dist
+    import cfpnet_b200
+    from cfpnet_b200 import _lib
+    from cfpnet_b200.build import build
+    from cfpnet_b200.layers import Block14
+    from cfpnet_b200.train import FlatTrainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    build()
+    B = a.batch
+    enc = cfpnet_b200.HistogramEncoder()
+    enc.load_state_dict(synth.synthetic_state_dict({k: v.shape for k, v in enc.state_dict().items()}, 0))
+    blocks = {}
+    for lv in (3, 2, 1):
+        C, _, _, k = synth.LEVELS[lv]
+        blk = Block14(C, large_kernel=k)
+        blk.load_state_dict(synth.synthetic_state_dict({kk: v.shape for kk, v in blk.state_dict().items()}, 3))
+        blocks[lv] = blk
+    mods = [enc.to(dev).train()] + [blocks[lv].to(dev).train() for lv in (3, 2, 1)]
+    trainer = FlatTrainer(mods, lr=1e-4, weight_decay=0.1, max_norm=0.1)
+
+    NSETS = 3
+    host_sets, dev_sets = [], []
+    for s_ in range(NSETS):
+        inp = synth.make_inputs(GEOMETRY, B, seed=300 + rank * NSETS + s_)
+        h = {"hist": inp["hist_data"].unsqueeze(-1).contiguous().pin_memory()}
+        for lv in (3, 2, 1):
+            h[f"x{lv}"] = inp[f"x{lv}"].float().contiguous().pin_memory()
+        host_sets.append(h)
+        dev_sets.append({k: v.to(dev) for k, v in h.items()})
+    h2d = sum(v.numel() * v.element_size() for v in host_sets[0].values())
+    g = torch.Generator().manual_seed(11 + rank)
+    # cotangents of the slice's outputs (what the rest of the network would send back), scaled like a mean loss
+    cts = {}
+    for lv in (3, 2, 1):
+        x = host_sets[0][f"x{lv}"]
+        cts[f"x{lv}"] = (torch.randn(x.shape, generator=g) / x.numel()).to(dev)
+    for c_ in (32, 64, 128):
+        cts[f"h{c_}"] = (torch.randn(B, 64, 16, c_, generator=g) / (B * 64 * 16 * c_)).to(dev)
+
+    ev_a = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+
+    def step(d, timed_exchange=False):
+        trainer.zero_grad()
+        hist = d["hist"]
+        outs, grads = [], []
+        ho = enc(hist)
+        for o, c_ in zip(ho, (32, 64, 128)):
+            outs.append(o)
+            grads.append(cts[f"h{c_}"])
+        for lv in (3, 2, 1):
+            x = d[f"x{lv}"].requires_grad_(True)            # the decoder upstream needs dx: the full backward runs
+            x.grad = None
+            outs.append(blocks[lv](x))
+            grads.append(cts[f"x{lv}"])
+        torch.autograd.backward(outs, grads)
+        if trainer.flat_g is None:
+            trainer.adopt()
+        if timed_exchange:
+            ev_a[0].record()
+        trainer.exchange()
+        if timed_exchange:
+            ev_a[1].record()
+        trainer.update()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sampler = ClockSampler(local) if rank == 0 and not os.environ.get("CFP_BENCH_NO_SAMPLER") else None
+    if sampler:
+        sampler.start()
+    for i in range(max(a.warmup, 3)):
+        step(dev_sets[i % NSETS])
+    barrier()
+    if sampler:
+        t_s = time.perf_counter()
+        while not sampler.samples and sampler.is_alive() and time.perf_counter() - t_s < 5.0:
+            time.sleep(0.05)
+        sampler.mark_begin()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0 = _lib.launch_count()
+    e0.record()
+    for i in range(a.steps):
+        step(dev_sets[i % NSETS])
+        if sampler and i == a.steps // 2:
+            sampler.sample_now()
+    e1.record()
+    barrier()
+    launches = _lib.launch_count() - n0
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    if sampler:
+        sampler.mark_end()
+    clocks = sampler.finish() if sampler else None
+
+    # all-reduce inside the step, CUDA events on the launch stream (separate instrumented pass)
+    ar_ms = []
+    for i in range(a.steps):
+        step(dev_sets[i % NSETS], timed_exchange=True)
+        torch.cuda.synchronize()
+        ar_ms.append(ev_a[0].elapsed_time(ev_a[1]))
+    ar_med = max_over_ranks(statistics.median(ar_ms))
+    # the same collective on a bucket of the complete path's gradient size (6.65 M parameters)
+    full_ms = None
+    if world > 1:
+        big = torch.zeros(6_650_000, device=dev, dtype=torch.float32)
+        for _ in range(5):
+            dist.all_reduce(big)
+        torch.cuda.synchronize()
+        t_ = []
+        for _ in range(20):
+            ev_a[0].record()
+            dist.all_reduce(big)
+            ev_a[1].record()
+            torch.cuda.synchronize()
+            t_.append(ev_a[0].elapsed_time(ev_a[1]))
+        full_ms = max_over_ranks(statistics.median(t_))
+
+    # end to end: inputs from pinned host memory every step, the gradient norm read back
+    side = torch.cuda.Stream(device=dev)
+    norm_host = torch.zeros(1).pin_memory()
+
+    def e2e_run(n):
+        cur = torch.cuda.current_stream()
+        staged = None
+        for i in range(n + 1):
+            nxt = None
+            if i < n:
+                with torch.cuda.stream(side):
+                    nxt = {k: v.to(dev, non_blocking=True) for k, v in host_sets[i % NSETS].items()}
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+            if staged is not None:
+                cur.wait_event(staged[1])
+                step(staged[0])
+                norm_host.copy_(trainer.sumsq[:1], non_blocking=True)
+                for t in staged[0].values():
+                    t.record_stream(cur)
+            staged = (nxt, ev) if nxt is not None else None
+        torch.cuda.synchronize()
+
+    e2e_run(3)
+    barrier()
+    t_wall = time.perf_counter()
+    e0.record()
+    e2e_run(a.steps)
+    e1.record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), t_wall * 1e3))
+
+    prof = None
+    torch.cuda.synchronize()
+    if rank == 0:
+        _lib.profile_start()
+    for i in range(a.steps):                # every rank: the step contains a collective
+        step(dev_sets[i % NSETS])
+    if rank == 0:
+        prof = _lib.profile_stop()
+    barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = load_peaks()
+    frames = B * world * a.steps
+    nparams = int(trainer.flat_g.numel())
+    bus = lambda nbytes, ms: (2.0 * (world - 1) / world * nbytes / (ms * 1e-3) / 1e9) if world > 1 and ms else None   # noqa: E731
+    line = {
+        "metric": "CFP path training step (hist encoder + LKPM blocks) frames/s @416x544, 8x8 zones", "value": frames / (ms_total * 1e-3),
+        "unit": "frames/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_total / a.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "training step of the CUDA-built part of the path: HistogramEncoder + Block14 (LKPM) of the three "
+                               f"decoder levels in .train() mode, fp32, {B} frames per GPU, 416x544 (BASELINE.json configs[4]; "
+                               "attention layers / DAPM convs have no backward kernels yet)",
+                   "per_gpu_batch": B, "global_batch": B * world, "optimizer": "clip_grad_norm_(0.1) + AdamW on the flat bucket",
+                   "l2_policy": "inputs rotate over 3 distinct batches; activations of a step (> 1 GB) exceed the 126 MB L2"},
+        "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "collective": {"op": "NCCL all-reduce (sum) of one flat fp32 gradient bucket", "parameters": nparams, "bytes": nparams * 4,
+                       "ms": ar_med, "share_of_step": ar_med / (ms_total / a.steps) if world > 1 else 0.0,
+                       "busbw_GBps": bus(nparams * 4, ar_med),
+                       "full_path_bucket": {"bytes": 6_650_000 * 4, "ms": full_ms, "busbw_GBps": bus(6_650_000 * 4, full_ms)}},
+    }
+    if prof:
+        line["roofline"], line["kernels"] = roofline_from_profile(prof, a.steps, B, 4, peaks)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cfp", choices=["cfp", "reference"])
-    ap.add_argument("--batch", type=int, default=64, help="frames per GPU per step")
+    ap.add_argument("--batch", type=int, default=None, help="frames per GPU per step (default 64; train_b32: 32)")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--workload", default="combine1_b64", choices=["combine1_b64", "baseline_b16", "latency_480"],
+    ap.add_argument("--workload", default="combine1_b64", choices=["combine1_b64", "baseline_b16", "latency_480", "train_b32"],
                     help="combine1_b64 = the headline (BASELINE.json configs[2]); the other two are side configurations")
     a = ap.parse_args()
+    if a.batch is None:
+        a.batch = 32 if a.workload == "train_b32" else 64
+    if a.workload == "train_b32":
+        if a.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "the training-step workload has no CPU arm; --impl reference "
+                              "serves the headline workload"}))
+            return None
+        return run_train(a)
     if a.workload != "combine1_b64":
         return run_aux(a)
     a.warmup = max(a.warmup, 3) if a.impl == "cfp" else a.warmup

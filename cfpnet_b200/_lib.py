@@ -18,7 +18,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcfp.so")
 
 CFP_F32, CFP_BF16 = 0, 1
-ABI_VERSION = 10
+ABI_VERSION = 11
 _fp = C.POINTER(C.c_float)
 
 
@@ -72,7 +72,20 @@ SIGNATURES = {
     "cfp_dapm_fwd": (_i, [_p, _i, _i, _i, _i, C.POINTER(CfpGeom), C.POINTER(CfpDapmW), _p, _sz, _i, _p]),
     "cfp_lkpm_fwd": (_i, [_p, _i, _i, _i, _i, C.POINTER(CfpLkpmW), _p, _sz, _i, _p]),
     "cfp_twins_fwd": (_i, [_p, _i, _i, _i, _i, C.POINTER(CfpTwinsW), _p, _sz, _i, _p]),
+    "cfp_tr_gemm": (_i, [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i, _i, _i, _p, _i, _p]),
+    "cfp_tr_colsum": (_i, [_p, _p, _i64, _i, _p]),
+    "cfp_tr_bn_stats": (_i, [_p, _i64, _i, C.c_float, C.c_float, _p, _p, _p, _p, _p, _p]),
+    "cfp_tr_bn_apply": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i, _i, _p]),
+    "cfp_tr_bn_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _p]),
+    "cfp_tr_ln_fwd": (_i, [_p, _p, _p, _p, _i64, _i, C.c_float, _p]),
+    "cfp_tr_ln_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i, C.c_float, _p]),
+    "cfp_tr_ew": (_i, [_p, _p, _p, _i64, _i, _p]),
+    "cfp_tr_dwconv": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _p]),
+    "cfp_tr_dwconv_wgrad": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "cfp_tr_sumsq": (_i, [_p, _i64, C.c_float, _p, _p]),
+    "cfp_tr_adamw": (_i, [_p, _p, _p, _p, _i64, _p, _p, _i] + [C.c_float] * 4 + [_i, C.c_float, _p, C.c_float, _p]),
     "cfp_launch_count": (_i64, []),
+    "cfp_set_pdl": (_i, [_i]),
     "cfp_selftest_umma": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),
     "cfp_profile_start": (_i, []),
     "cfp_profile_stop": (_i, [C.c_char_p, _sz]),
@@ -132,6 +145,11 @@ def ptr(t) -> int:
 
 def stream_ptr() -> int:
     return torch.cuda.current_stream().cuda_stream
+
+
+def set_pdl(on) -> int:
+    """Programmatic dependent launch for this thread's calls (True / False / None = default); returns the previous setting."""
+    return int(load().cfp_set_pdl(-1 if on is None else int(bool(on))))
 
 
 def launch_count() -> int:

@@ -7,6 +7,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
+#include <atomic>
+#include <mutex>
 #include <string>
 #include <vector>
 #include "cfp_common.cuh"
@@ -25,38 +28,61 @@ int fail(const char* fmt, ...) {
     va_end(ap);
     return 1;
 }
-// Per-thread launch accounting and the optional event profiler (cfp_profile_*): when on, one
-// CUDA event is recorded on the call's stream after every kernel launch, so a kernel's time is
-// the gap to the previous event on that (in-order) stream.
-struct ThreadState {
-    cudaStream_t stream = nullptr;
-    int64_t launches = 0;
-    bool profiling = false;
+static thread_local int tl_pdl = -1;      // -1: default (on unless CFP_NO_PDL is set); 0 / 1: cfp_set_pdl
+bool pdl_enabled() {
+    static const bool env_on = getenv("CFP_NO_PDL") == nullptr;
+    return tl_pdl < 0 ? env_on : (tl_pdl != 0 && env_on);
+}
+int sm_count() {
+    static thread_local int cached_dev = -1, cached = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev != cached_dev) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached_dev = dev;
+        cached = n;
+    }
+    return cached;
+}
+// Launch accounting and the optional event profiler (cfp_profile_*), process-wide: a training step enqueues its forward
+// from the caller's thread and its backward from autograd's device thread, and both belong in one count / one profile.
+// When profiling is on, one CUDA event is recorded on the call's stream after every kernel launch, so a kernel's time
+// is the gap to the previous event (meaningful when the profiled calls share one in-order stream).
+struct ProfileState {
+    std::mutex mu;
+    std::atomic<int64_t> launches{0};
+    std::atomic<bool> profiling{false};
     cudaEvent_t first = nullptr;
     std::vector<std::pair<const char*, cudaEvent_t>> events;
 };
-static ThreadState& tstate() {
-    static thread_local ThreadState t;
-    return t;
+static ProfileState& pstate() {
+    static ProfileState p;
+    return p;
 }
+static thread_local cudaStream_t tl_stream = nullptr;
 static void begin_call(void* stream) {
-    ThreadState& t = tstate();
-    t.stream = (cudaStream_t)stream;
-    if (t.profiling && !t.first) {
-        cudaEventCreate(&t.first);
-        cudaEventRecord(t.first, t.stream);
+    tl_stream = (cudaStream_t)stream;
+    ProfileState& p = pstate();
+    if (p.profiling.load(std::memory_order_relaxed)) {
+        std::lock_guard<std::mutex> lk(p.mu);
+        if (!p.first) {
+            cudaEventCreate(&p.first);
+            cudaEventRecord(p.first, tl_stream);
+        }
     }
 }
 int check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail("%s launch failed: %s", what, cudaGetErrorString(e));
-    ThreadState& t = tstate();
-    ++t.launches;
-    if (t.profiling) {
+    ProfileState& p = pstate();
+    p.launches.fetch_add(1, std::memory_order_relaxed);
+    if (p.profiling.load(std::memory_order_relaxed)) {
         cudaEvent_t ev;
         cudaEventCreate(&ev);
-        cudaEventRecord(ev, t.stream);
-        t.events.emplace_back(what, ev);
+        cudaEventRecord(ev, tl_stream);
+        std::lock_guard<std::mutex> lk(p.mu);
+        p.events.emplace_back(what, ev);
     }
     return 0;
 }
@@ -312,6 +338,80 @@ CFP_API int cfp_twins_fwd(void* feat0, int B, int H, int W, int C, const cfp_twi
     return twins(feat0, B, H, W, C, *w, (char*)workspace, L, dtype, (cudaStream_t)stream);
 }
 
+// ---------------------------------------------------------------- training-step building blocks (fp32)
+CFP_API int cfp_tr_gemm(const float* a, int64_t a_rs, int64_t a_cs, const float* b, int64_t b_rs, int64_t b_cs, float* c,
+                        int64_t c_rs, int M, int N, int K, const float* bias, int accumulate, void* stream) {
+    begin_call(stream);
+    CFP_REQUIRE(a && b && c, "null pointer");
+    return tr_gemm(a, a_rs, a_cs, b, b_rs, b_cs, c, c_rs, M, N, K, bias, accumulate, (cudaStream_t)stream);
+}
+CFP_API int cfp_tr_colsum(const float* x, float* out, int64_t rows, int C, void* stream) {
+    begin_call(stream);
+    CFP_REQUIRE(x && out && rows > 0 && C > 0, "bad arguments");
+    return tr_colsum(x, out, rows, C, (cudaStream_t)stream);
+}
+CFP_API int cfp_tr_bn_stats(const float* x, int64_t rows, int C, float eps, float momentum, float* mean, float* rstd,
+                            float* running_mean, float* running_var, float* scratch, void* stream) {
+    begin_call(stream);
+    CFP_REQUIRE(x && mean && rstd && scratch, "null pointer");
+    return tr_bn_stats(x, rows, C, eps, momentum, mean, rstd, running_mean, running_var, scratch, (cudaStream_t)stream);
+}
+CFP_API int cfp_tr_bn_apply(const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                            float* y, int64_t rows, int C, int relu, void* stream) {
+    begin_call(stream);
+    CFP_REQUIRE(x && mean && rstd && gamma && beta && y, "null pointer");
+    return tr_bn_apply(x, mean, rstd, gamma, beta, y, rows, C, relu, (cudaStream_t)stream);
+}
+CFP_API int cfp_tr_bn_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                          const float* beta, float* dx, float* dgamma, float* dbeta, int64_t rows, int C, int relu, void* stream) {
+    begin_call(stream);
+    CFP_REQUIRE(dy && x && mean && rstd && gamma && beta && dx && dgamma && dbeta, "null pointer");
+    return tr_bn_bwd(dy, x, mean, rstd, gamma, beta, dx, dgamma, dbeta, rows, C, relu, (cudaStream_t)stream);
+}
+CFP_API int cfp_tr_ln_fwd(const float* x, const float* g, const float* b, float* y, int64_t rows, int C, float eps, void* stream) {
+    begin_call(stream);
+    CFP_REQUIRE(x && g && b && y, "null pointer");
+    return tr_ln_fwd(x, g, b, y, rows, C, eps, (cudaStream_t)stream);
+}
+CFP_API int cfp_tr_ln_bwd(const float* x, const float* g, const float* dy, float* dx, float* dg, float* db, int64_t rows, int C,
+                          float eps, void* stream) {
+    begin_call(stream);
+    CFP_REQUIRE(x && g && dy && dx && dg && db, "null pointer");
+    return tr_ln_bwd(x, g, dy, dx, dg, db, rows, C, eps, (cudaStream_t)stream);
+}
+CFP_API int cfp_tr_ew(const float* a, const float* b, float* out, int64_t n, int op, void* stream) {
+    begin_call(stream);
+    CFP_REQUIRE(a && out, "null pointer");
+    return tr_ew(a, b, out, n, op, (cudaStream_t)stream);
+}
+CFP_API int cfp_tr_dwconv(const float* in, float* out, int B, int H, int W, int C, int ksize, const float* taps_t,
+                          const float* shift, int relu, void* stream) {
+    begin_call(stream);
+    CFP_REQUIRE(in && out && taps_t && shift, "null pointer");
+    CFP_REQUIRE(B > 0 && H > 0 && W > 0, "bad shape");
+    return dwconv_bn_relu(in, out, B, H, W, C, ksize, taps_t, shift, CFP_F32, (cudaStream_t)stream, relu);
+}
+CFP_API int cfp_tr_dwconv_wgrad(const float* x, const float* dy, float* dw, int B, int H, int W, int C, int ksize, void* stream) {
+    begin_call(stream);
+    CFP_REQUIRE(x && dy && dw, "null pointer");
+    CFP_REQUIRE(B > 0 && H > 0 && W > 0, "bad shape");
+    return tr_dwconv_wgrad(x, dy, dw, B, H, W, C, ksize, (cudaStream_t)stream);
+}
+
+CFP_API int cfp_tr_sumsq(const float* x, int64_t n, float scale, float* out, void* stream) {
+    begin_call(stream);
+    CFP_REQUIRE(out && (x || n == 0) && n >= 0, "bad arguments");
+    return tr_sumsq(x, n, scale, out, (cudaStream_t)stream);
+}
+CFP_API int cfp_tr_adamw(float* p, const float* g, float* m, float* v, int64_t n, const int64_t* seg_end, const float* seg_lr,
+                         int nseg, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                         const float* sumsq, float max_norm, void* stream) {
+    begin_call(stream);
+    CFP_REQUIRE(p && g && m && v && seg_end && seg_lr && n >= 0, "bad arguments");
+    return tr_adamw(p, g, m, v, n, seg_end, seg_lr, nseg, beta1, beta2, eps, weight_decay, step, grad_scale, sumsq, max_norm,
+                    (cudaStream_t)stream);
+}
+
 CFP_API int cfp_selftest_umma(const void* a, const void* b, float* d, int rows_a, int n, int k, int row_shift,
                               void* stream) {
     begin_call(stream);
@@ -319,10 +419,17 @@ CFP_API int cfp_selftest_umma(const void* a, const void* b, float* d, int rows_a
     return umma_selftest(a, b, d, rows_a, n, k, row_shift, (cudaStream_t)stream);
 }
 
-CFP_API int64_t cfp_launch_count(void) { return tstate().launches; }
+CFP_API int64_t cfp_launch_count(void) { return pstate().launches.load(); }
+
+CFP_API int cfp_set_pdl(int on) {
+    const int prev = pdl_enabled() ? 1 : 0;
+    tl_pdl = on < 0 ? -1 : (on ? 1 : 0);
+    return prev;
+}
 
 CFP_API int cfp_profile_start(void) {
-    ThreadState& t = tstate();
+    ProfileState& t = pstate();
+    std::lock_guard<std::mutex> lk(t.mu);
     for (auto& e : t.events) cudaEventDestroy(e.second);
     t.events.clear();
     if (t.first) cudaEventDestroy(t.first);
@@ -332,8 +439,9 @@ CFP_API int cfp_profile_start(void) {
 }
 
 CFP_API int cfp_profile_stop(char* out, size_t cap) {
-    ThreadState& t = tstate();
+    ProfileState& t = pstate();
     t.profiling = false;
+    std::lock_guard<std::mutex> lk(t.mu);
     CFP_REQUIRE(out && cap > 2, "null output buffer");
     struct Acc { const char* name; int count; double ms; };
     std::vector<Acc> acc;

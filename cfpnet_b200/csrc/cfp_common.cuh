@@ -232,6 +232,20 @@ __device__ __forceinline__ void layernorm_rows(float* buf, int ld, const float* 
     }
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Every kernel of the bf16 path is launched with cudaLaunchAttributeProgrammaticStreamSerialization: its CTAs may
+// become resident while the previous kernel of the stream is still draining, run their prologue (barrier init, TMEM
+// allocation, constant shared-memory columns, first weight copies - nothing the previous kernel produced) and block
+// in pdl_wait() until the previous grid has completed and its writes are visible.  Rules followed everywhere:
+//   * pdl_trigger() right after the prologue, so the next kernel can be scheduled as soon as the last wave of this
+//     grid is resident;
+//   * every thread that reads or writes an activation / workspace buffer calls pdl_wait() first (weights and packed
+//     constants may be fetched before it);
+//   * at least the row / epilogue threads of every kernel wait, so grid N cannot finish before grid N-1 and the
+//     ordering stays transitive along the stream.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+
 // ---------------------------------------------------------------- host side
 struct ErrorState {
     char msg[512];
@@ -244,6 +258,25 @@ int check_launch(const char* what);
     do {                                       \
         if (!(cond)) return ::cfp::fail(__VA_ARGS__); \
     } while (0)
+
+bool pdl_enabled();      // CFP_NO_PDL=1 launches everything fully serialised (A/B measurements)
+int sm_count();          // multiprocessors of the current device (cached per device)
+
+// k<<<grid, block, smem, st>>>(args...) with the programmatic-stream-serialization attribute
+template <class... P, class... A>
+inline void launch_pdl(void (*k)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    (void)cudaLaunchKernelEx(&cfg, k, P(args)...);      // a failure is picked up by check_launch (cudaGetLastError)
+}
 
 template <typename K>
 inline int set_smem(K kernel, size_t bytes) {

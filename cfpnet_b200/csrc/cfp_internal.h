@@ -52,7 +52,7 @@ int sr_conv_ln(const void* feat0, float* sr_tok, int B, int H, int W, int C, int
 
 // k_lkpm.cu
 int dwconv_bn_relu(const void* in, void* out, int B, int H, int W, int C, int ksize, const float* dw_t,
-                   const float* dw_shift, int dtype, cudaStream_t st);
+                   const float* dw_shift, int dtype, cudaStream_t st, int relu = 1);
 int lkpm_mlp(void* feat0, const void* y, int64_t rows, int C, const cfp_lkpm_w& w, int dtype,
              cudaStream_t st);
 
@@ -72,6 +72,26 @@ int sr_conv_ln_tc(const void* feat0, float* sr_tok, int B, int H, int W, int C, 
 size_t dwconv_tc_plane_bytes(int B, int H, int W, int C, int K);
 int dwconv_tc(const void* in, const void** planar_out, int* planar_pitch, int B, int H, int W, int C, int K, const void* toep, const float* shift,
               char* plane_ws, cudaStream_t st);
+
+// k_train.cu  (fp32 training-step building blocks)
+int tr_gemm(const float* A, int64_t a_rs, int64_t a_cs, const float* B, int64_t b_rs, int64_t b_cs, float* C, int64_t c_rs,
+            int M, int N, int K, const float* bias, int accumulate, cudaStream_t st);
+int tr_colsum(const float* x, float* out, int64_t rows, int C, cudaStream_t st);
+int tr_bn_stats(const float* x, int64_t rows, int C, float eps, float momentum, float* mean, float* rstd, float* running_mean,
+                float* running_var, float* scratch, cudaStream_t st);
+int tr_bn_apply(const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta, float* y,
+                int64_t rows, int C, int relu, cudaStream_t st);
+int tr_bn_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
+              float* dx, float* dgamma, float* dbeta, int64_t rows, int C, int relu, cudaStream_t st);
+int tr_ln_fwd(const float* x, const float* g, const float* b, float* y, int64_t rows, int C, float eps, cudaStream_t st);
+int tr_ln_bwd(const float* x, const float* g, const float* dy, float* dx, float* dg, float* db, int64_t rows, int C, float eps,
+              cudaStream_t st);
+int tr_ew(const float* a, const float* b, float* out, int64_t n, int op, cudaStream_t st);
+int tr_sumsq(const float* x, int64_t n, float scale, float* out, cudaStream_t st);
+int tr_adamw(float* p, const float* g, float* m, float* v, int64_t n, const int64_t* seg_end, const float* seg_lr, int nseg,
+             float beta1, float beta2, float eps, float wd, int step, float grad_scale, const float* sumsq, float max_norm,
+             cudaStream_t st);
+int tr_dwconv_wgrad(const float* x, const float* dy, float* dw, int B, int H, int W, int C, int K, cudaStream_t st);
 
 // k_selftest.cu
 int umma_selftest(const void* A, const void* B, float* D, int rows_a, int N, int K, int row_shift, cudaStream_t st);

@@ -333,6 +333,7 @@ __global__ void __launch_bounds__(320, 1) loftr_query_tc_kernel(Q q, cfp_loftr_w
     umma::fence_after_sync();
 
     if (warp < 8) {
+        pdl_wait();                       // rows and attention state come from the previous kernels of the stream
         const int grp = warp >> 2, wq = warp & 3, tid_g = tid & 127;
         uint8_t* a0 = smem + (size_t)grp * P::ABUF;          // [x | msg, then LN1(merge(msg))], then the MLP hidden
         const uint32_t tmem = bars.tmem_slot + grp * 256;
@@ -419,6 +420,7 @@ __global__ void __launch_bounds__(320, 1) loftr_query_tc_kernel(Q q, cfp_loftr_w
             umma::commit(&bars.acc_ready);
         }
     }
+    pdl_trigger();                         // this CTA's work is done: the next kernel of the stream may start its prologue
     __syncthreads();
     if (warp == 8) {
         umma::fence_after_sync();
@@ -504,7 +506,8 @@ __global__ void __launch_bounds__(128, MonoOcc<C>::CTAS) loftr_query_mono_kernel
     };
 
     if (warp == 0)
-        for (long s0 = 0; s0 < 4; ++s0) prefetch(s0);
+        for (long s0 = 0; s0 < 4; ++s0) prefetch(s0);       // weights: not produced by the previous kernel
+    pdl_wait();
     long base = 0;                                          // sequence number of this tile's first block
     uint32_t kvph = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, base += NB) {
@@ -566,6 +569,7 @@ __global__ void __launch_bounds__(128, MonoOcc<C>::CTAS) loftr_query_mono_kernel
         // the next tile's stage_x overwrites a0[:, 0:C), which epi_out of other rows may still read
         __syncthreads();
     }
+    pdl_trigger();                         // this CTA's work is done: the next kernel of the stream may start its prologue
     umma::fence_before_sync();
     __syncthreads();
     if (warp == 0) {
@@ -591,10 +595,10 @@ static int run_query_tc(const char* name, const Q& q, const cfp_loftr_w& w, cons
         const size_t kv_bytes = (size_t)kv_slots * (C * DH + C) * sizeof(float);
         if ((smem0 + kv_bytes + 1024) * per_sm > 227 * 1024 || getenv("CFP_NO_KV_SMEM")) kv_slots = 0;
         const size_t smem = smem0 + (kv_slots > 0 ? kv_bytes : 0);
-        const int grid = (int)(ntiles < 148 * per_sm ? ntiles : 148 * per_sm);
+        const int grid = (int)(ntiles < sm_count() * per_sm ? ntiles : sm_count() * per_sm);
         auto k = loftr_query_mono_kernel<C, NH, kAttnOnly, Q>;
         if (int e = set_smem(k, smem)) return e;
-        k<<<grid, 128, smem, st>>>(q, w, kv, ksum, (int)ntiles, kv_slots);
+        launch_pdl(k, grid, 128, smem, st, q, w, kv, ksum, (int)ntiles, kv_slots);
 #ifdef CFP_DEBUG_TIMING
         {
             cudaStreamSynchronize(st);
@@ -606,10 +610,10 @@ static int run_query_tc(const char* name, const Q& q, const cfp_loftr_w& w, cons
 #endif
     } else {
         const int64_t npairs = (ntiles + 1) / 2;
-        const int grid = (int)(npairs < 148 ? npairs : 148);
+        const int grid = (int)(npairs < sm_count() ? npairs : sm_count());
         auto k = loftr_query_tc_kernel<C, NH, kAttnOnly, Q>;
         if (int e = set_smem(k, P::SMEM)) return e;
-        k<<<grid, 320, P::SMEM, st>>>(q, w, kv, ksum, (int)ntiles);
+        launch_pdl(k, grid, 320, P::SMEM, st, q, w, kv, ksum, (int)ntiles);
 #ifdef CFP_DEBUG_TIMING
         {
             cudaStreamSynchronize(st);
@@ -699,6 +703,7 @@ __global__ void __launch_bounds__(192) lkpm_mlp_tc_kernel(bf16* __restrict__ fea
     const uint32_t tmem = bars.tmem_slot;
 
     if (warp < 4) {
+        pdl_wait();
         uint32_t ph = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int64_t row = (int64_t)tile * 128 + tid;
@@ -849,6 +854,7 @@ __global__ void __launch_bounds__(192) lkpm_mlp_tc_kernel(bf16* __restrict__ fea
             }
         }
     }
+    pdl_trigger();                         // this CTA's work is done: the next kernel of the stream may start its prologue
     __syncthreads();
     if (warp == 4) {
         umma::fence_after_sync();
@@ -866,8 +872,8 @@ static int run_lkpm_mlp_tc(void* feat0, const void* y, int64_t rows, int planar_
     if (int e = set_smem(k, M::SMEM)) return e;
     const int64_t ntiles = (rows + 127) / 128;
     const int per_sm = C >= 128 ? 1 : (C == 64 ? 2 : 3);
-    const int grid = (int)(ntiles < 148 * per_sm ? ntiles : 148 * per_sm);
-    k<<<grid, 192, M::SMEM, st>>>((bf16*)feat0, (const bf16*)y, rows, planar_n, planar_w, planar_pitch, w, (int)ntiles);
+    const int grid = (int)(ntiles < sm_count() * per_sm ? ntiles : sm_count() * per_sm);
+    launch_pdl(k, grid, 192, M::SMEM, st, (bf16*)feat0, (const bf16*)y, rows, planar_n, planar_w, planar_pitch, w, (int)ntiles);
     return check_launch(C == 32 ? "lkpm_mlp_tc<32>" : C == 64 ? "lkpm_mlp_tc<64>" : "lkpm_mlp_tc<128>");
 }
 
@@ -946,6 +952,7 @@ __global__ void __launch_bounds__((4 * KvNT<C>::NT + 2) * 32) kv_state_tc_kernel
                                                                       // multiply-high division (a 64-bit divide per run used to cost ~25 % here)
 
     if (warp < 4 * NT) {
+        pdl_wait();
         uint32_t ph = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const uint32_t row0 = (uint32_t)tile * 128u;
@@ -1122,6 +1129,7 @@ __global__ void __launch_bounds__((4 * KvNT<C>::NT + 2) * 32) kv_state_tc_kernel
             }
         }
     }
+    pdl_trigger();                         // this CTA's work is done: the next kernel of the stream may start its prologue
     __syncthreads();
     if (warp == 4 * NT) {
         umma::fence_after_sync();
@@ -1144,19 +1152,19 @@ static int run_kv_state_tc(const char* name, const Src& src, int S, int groups, 
     const int64_t ntiles = ((int64_t)groups * S_pad + 127) / 128;
     CFP_REQUIRE((int64_t)groups * S_pad < ((int64_t)1 << 31), "%s: %lld padded rows exceed the 32-bit row index", name, (long long)groups * S_pad);
     const int per_sm = C >= 128 ? 1 : (C == 64 ? 3 : 5);          // shared memory: 169 / 70 / 45 KB per CTA
-    const int grid = (int)(ntiles < 148 * per_sm ? ntiles : 148 * per_sm);
+    const int grid = (int)(ntiles < sm_count() * per_sm ? ntiles : sm_count() * per_sm);
     if (S_pad == 16 && NH == 4) {                     // hist2image zones (dh = C/4 is a multiple of 8)
         auto k = kv_state_tc_kernel<C, NH, true, Src, (NH == 4)>;
         if (int e = set_smem(k, K::SMEM)) return e;
-        k<<<grid, (4 * KvNT<C>::NT + 2) * 32, K::SMEM, st>>>(src, S, S_pad, FastDiv((uint32_t)S_pad), groups, (const bf16*)wkv_tc, kv, ksum, (int)ntiles);
+        launch_pdl(k, grid, (4 * KvNT<C>::NT + 2) * 32, K::SMEM, st, src, S, S_pad, FastDiv((uint32_t)S_pad), groups, (const bf16*)wkv_tc, kv, ksum, (int)ntiles);
     } else if (complete) {
         auto k = kv_state_tc_kernel<C, NH, true, Src>;
         if (int e = set_smem(k, K::SMEM)) return e;
-        k<<<grid, (4 * KvNT<C>::NT + 2) * 32, K::SMEM, st>>>(src, S, S_pad, FastDiv((uint32_t)S_pad), groups, (const bf16*)wkv_tc, kv, ksum, (int)ntiles);
+        launch_pdl(k, grid, (4 * KvNT<C>::NT + 2) * 32, K::SMEM, st, src, S, S_pad, FastDiv((uint32_t)S_pad), groups, (const bf16*)wkv_tc, kv, ksum, (int)ntiles);
     } else {
         auto k = kv_state_tc_kernel<C, NH, false, Src>;
         if (int e = set_smem(k, K::SMEM)) return e;
-        k<<<grid, (4 * KvNT<C>::NT + 2) * 32, K::SMEM, st>>>(src, S, S_pad, FastDiv((uint32_t)S_pad), groups, (const bf16*)wkv_tc, kv, ksum, (int)ntiles);
+        launch_pdl(k, grid, (4 * KvNT<C>::NT + 2) * 32, K::SMEM, st, src, S, S_pad, FastDiv((uint32_t)S_pad), groups, (const bf16*)wkv_tc, kv, ksum, (int)ntiles);
     }
 #ifdef CFP_DEBUG_TIMING
     {
@@ -1231,6 +1239,7 @@ __global__ void __launch_bounds__(192) sr_conv_tc_kernel(const bf16* __restrict_
     const uint32_t tmem = bars.tmem_slot;
 
     if (warp < 4) {
+        pdl_wait();
         // chunk k of this thread: (row r_k, channel group kg_k) with r_k * KG + kg_k = tid + 128 k; source element offset of
         // the row's window origin (tap (0,0)) or -1 for rows past the end (zero-filled)
         int64_t base[KG];
@@ -1308,6 +1317,7 @@ __global__ void __launch_bounds__(192) sr_conv_tc_kernel(const bf16* __restrict_
             umma::commit(&bars.acc_ready);
         }
     }
+    pdl_trigger();                         // this CTA's work is done: the next kernel of the stream may start its prologue
     __syncthreads();
     if (warp == 4) {
         umma::fence_after_sync();
@@ -1321,6 +1331,8 @@ __global__ void sr_bias_ln_kernel(float* __restrict__ sr_tok, int64_t rows, cons
                                   const float* __restrict__ gamma, const float* __restrict__ beta) {
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    pdl_trigger();                         // tiny kernel: let the next one come in right away
+    pdl_wait();
     if (row >= rows) return;
     constexpr int PER = C / 32;
     float v[PER], s = 0.f;
@@ -1349,7 +1361,7 @@ static int run_sr_conv_tc(const void* feat0, float* sr_tok, int B, int H, int W,
     // split the taps so that the grid is ONE wave of co-resident CTAs (shared memory: 3 / 2 / 1 CTAs per SM at C = 32 / 64 /
     // 128): a second, partial wave of tap slices costs a whole slice latency
     constexpr int per_sm = C >= 128 ? 1 : (C == 64 ? 2 : 3);
-    int splits = (148 * per_sm) / tiles;
+    int splits = (sm_count() * per_sm) / tiles;
     if (splits < 1) splits = 1;
     if (splits > ntap) splits = ntap;
     const int taps_per_cta = (ntap + splits - 1) / splits;
@@ -1358,10 +1370,10 @@ static int run_sr_conv_tc(const void* feat0, float* sr_tok, int B, int H, int W,
     CFP_REQUIRE(rows < ((int64_t)1 << 31), "sr conv: %lld rows exceed the 32-bit row index", (long long)rows);
     auto k = sr_conv_tc_kernel<C>;
     if (int err = set_smem(k, smem)) return err;
-    k<<<dim3(tiles, splits), 192, smem, st>>>((const bf16*)feat0, sr_tok, rows, H, W, ws, nsx, Ns, (const bf16*)sr_tc,
-                                               taps_per_cta);
+    launch_pdl(k, dim3(tiles, splits), 192, smem, st, (const bf16*)feat0, sr_tok, rows, H, W, ws, nsx, Ns, (const bf16*)sr_tc,
+               taps_per_cta);
     if (int err = check_launch(C == 32 ? "sr_conv_tc<32>" : C == 64 ? "sr_conv_tc<64>" : "sr_conv_tc<128>")) return err;
-    sr_bias_ln_kernel<C><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(sr_tok, rows, sr_b, g, b);
+    launch_pdl(sr_bias_ln_kernel<C>, (unsigned)((rows + 7) / 8), 256, 0, st, sr_tok, rows, sr_b, g, b);
     return check_launch("sr_bias_ln");
 }
 

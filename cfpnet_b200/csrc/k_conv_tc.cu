@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(192) conv3x3_tc_kernel(const bf16* __restrict_
 
     CFP_DBG_MARK(0);
     if (warp < 4) {
+        pdl_wait();                       // the maps come from the previous kernels of the stream (weights do not)
         // ---------------- stage the raster, one source at a time
         for (int s = 0; s < nsrc; ++s) {
             if (s > 0) umma::mbar_wait(&bars.a_free, 0);    // all MMAs reading source 0 have completed
@@ -215,6 +216,7 @@ __global__ void __launch_bounds__(192) conv3x3_tc_kernel(const bf16* __restrict_
             }
         }
     }
+    pdl_trigger();                         // this CTA's work is done: the next kernel of the stream may start its prologue
     __syncthreads();
     if (warp == 4) {
         umma::fence_after_sync();
@@ -237,8 +239,8 @@ static int conv_tc_launch(const void* in0, const void* in1, const void* wpk, con
     if (int e = set_smem(k, smem)) return e;
     dim3 grid((H + R - 1) / R, B);
     const unsigned wp_magic = (unsigned)((((uint64_t)1 << 32) + WP - 1) / WP);   // umulhi(i, magic) == i / WP for i*WP < 2^32
-    k<<<grid, 192, smem, st>>>((const bf16*)in0, (const bf16*)in1, (const bf16*)wpk, shift, (const bf16*)residual,
-                               (bf16*)out, H, W, R, cells, wp_magic, zy0, zy1, zx0, zx1);
+    launch_pdl(k, grid, 192, smem, st, (const bf16*)in0, (const bf16*)in1, (const bf16*)wpk, shift, (const bf16*)residual,
+               (bf16*)out, H, W, R, cells, wp_magic, zy0, zy1, zx0, zx1);
 #ifdef CFP_DEBUG_TIMING
     {
         cudaStreamSynchronize(st);

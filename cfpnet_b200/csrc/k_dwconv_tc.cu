@@ -98,6 +98,7 @@ __global__ void __launch_bounds__(256) dw_plane_pack_kernel(const bf16* __restri
     extern __shared__ __align__(16) uint32_t slab[];          // [8 rows][W][C/2 + 1] channel pairs (odd stride: no conflicts)
     const int stack = blockIdx.y, pr0 = blockIdx.x * 8;
     const int C = g.C, W = g.W, C2 = C / 2, LD = C2 + 1;
+    pdl_wait();
     // every plane row an A view can touch (HP >= PAD + F x (H + PAD)): the rows below the last frame's halo are only
     // multiplied by all-zero Toeplitz blocks (taps dy >= K of the last group of eight), but a stale NaN would survive that
     const int rows = min(8, g.HP - pr0);
@@ -123,6 +124,7 @@ __global__ void __launch_bounds__(256) dw_plane_pack_kernel(const bf16* __restri
         }
     }
     __syncthreads();
+    pdl_trigger();
     // phase 2: thread = (plane row r, slot); a slot walks over the (channel pair, x-group) chunks.  8 consecutive threads
     // (r = 0..7) write 128 contiguous bytes of a plane.  Chunks without image cells are plain zero stores.
     const int r = threadIdx.x & 7;
@@ -224,6 +226,7 @@ __global__ void __launch_bounds__(kDwThreads) dwconv_tc_kernel(const bf16* __res
     const uint32_t tmem = bars.tmem_slot;
 
     if (warp < kDwEpiWarps) {
+        pdl_wait();                       // the planar output may still be read by the previous kernels of the stream
         // ---------------- epilogue: kDwParts warps per TMEM lane quarter.  Thread = (accumulator row m, kDwCols of the
         // 32 output columns):  out[m][n] = sum_b E_b[m + b][n]
         constexpr int NC = kDwCols;
@@ -321,6 +324,7 @@ __global__ void __launch_bounds__(kDwThreads) dwconv_tc_kernel(const bf16* __res
                     cur_c = it.c;
                     ++nt;
                 }
+                if (i == i0) pdl_wait();  // the first Toeplitz blocks (weights) are on their way; the planes are the previous kernel's
                 if (n >= 3) umma::mbar_wait(&bars.a_empty[s], ((n / 3) - 1) & 1);
                 const bf16* src = planes + ((((size_t)it.b * g.C + it.c) * g.WG + 4 * it.xt) * g.HP) * 8;
                 umma::bulk_load(a_sm + (size_t)s * a_stride, src, a_bytes, &bars.a_full[s]);
@@ -365,6 +369,7 @@ __global__ void __launch_bounds__(kDwThreads) dwconv_tc_kernel(const bf16* __res
             }
         }
     }
+    pdl_trigger();                         // this CTA's work is done: the next kernel of the stream may start its prologue
     __syncthreads();
     if (warp == kDwEpiWarps) {
         umma::fence_after_sync();
@@ -386,7 +391,7 @@ int dwconv_tc(const void* in, const void** planar_out_p, int* planar_pitch, int 
         const size_t smem = (size_t)8 * W * (C / 2 + 1) * 4;
         CFP_REQUIRE(smem <= 200 * 1024, "dw_plane_pack: %zu B shared memory", smem);
         if (int err = set_smem(dw_plane_pack_kernel, smem)) return err;
-        dw_plane_pack_kernel<<<dim3((g.HP + 7) / 8, g.NB), 256, smem, st>>>((const bf16*)in, planes, g, B);
+        launch_pdl(dw_plane_pack_kernel, dim3((g.HP + 7) / 8, g.NB), 256, smem, st, (const bf16*)in, planes, g, B);
         if (int err = check_launch("dw_plane_pack")) return err;
     }
     {
@@ -395,9 +400,9 @@ int dwconv_tc(const void* in, const void** planar_out_p, int* planar_pitch, int 
         CFP_REQUIRE(smem <= 225 * 1024, "dwconv (tensor-core path): %zu B shared memory (H=%d too tall)", smem, H);
         if (int err = set_smem(dwconv_tc_kernel, smem)) return err;
         const int total = C * g.nX * g.NB * g.nM;
-        const int grid = total < 148 ? total : 148;
+        const int grid = total < sm_count() ? total : sm_count();
         const int per = (total + grid - 1) / grid;
-        dwconv_tc_kernel<<<(total + per - 1) / per, kDwThreads, smem, st>>>(planes, (const bf16*)toep, shift, planar_out, B, g, per, total);
+        launch_pdl(dwconv_tc_kernel, (total + per - 1) / per, kDwThreads, smem, st, planes, (const bf16*)toep, shift, planar_out, B, g, per, total);
         if (int err = check_launch(K == 31 ? "dwconv_tc<31>" : K == 15 ? "dwconv_tc<15>" : "dwconv_tc<7>")) return err;
     }
     return 0;

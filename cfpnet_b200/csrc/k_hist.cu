@@ -150,6 +150,7 @@ __global__ void __launch_bounds__(256, 1) hist_encoder_tc_kernel(const float* __
             umma::bulk_g2s(wsm + off, reinterpret_cast<const uint8_t*>(w.tc) + off,
                            min(16384, HistTC::WBYTES - off), &bars.w_full);
     }
+    pdl_wait();                            // the token tensors may still be read by the previous forward's kernels
     uint32_t ph = 0;
     bool w_ready = false;
     for (int tile = blockIdx.x * 2 + grp; tile < ntiles; tile += gridDim.x * 2) {
@@ -176,6 +177,7 @@ __global__ void __launch_bounds__(256, 1) hist_encoder_tc_kernel(const float* __
         hist_tc_stage<128, 128, O7, false>(a, wsm, w.b[7], tmem, bar, ph, grp, wq, tid_g, nullptr, row, rows);
         hist_tc_stage<128, 128, O8, true>(a, wsm, w.b[8], tmem, bar, ph, grp, wq, tid_g, o128, row, rows);
     }
+    pdl_trigger();
     if (!w_ready) umma::mbar_wait(&bars.w_full, 0);           // never leave with a bulk copy in flight
     umma::fence_before_sync();
     __syncthreads();
@@ -190,8 +192,8 @@ static int launch_tc(const float* hist, void* o32, void* o64, void* o128, int64_
     if (int e = set_smem(hist_encoder_tc_kernel, HistTC::SMEM)) return e;
     const int64_t ntiles = (rows + 127) / 128;
     CFP_REQUIRE(ntiles < ((int64_t)1 << 30), "hist_encoder: too many rows");
-    const int grid = (int)((ntiles + 1) / 2 < 148 ? (ntiles + 1) / 2 : 148);
-    hist_encoder_tc_kernel<<<grid, 256, HistTC::SMEM, st>>>(hist, (bf16*)o32, (bf16*)o64, (bf16*)o128, rows, w, (int)ntiles);
+    const int grid = (int)((ntiles + 1) / 2 < sm_count() ? (ntiles + 1) / 2 : sm_count());
+    launch_pdl(hist_encoder_tc_kernel, grid, 256, HistTC::SMEM, st, hist, (bf16*)o32, (bf16*)o64, (bf16*)o128, rows, w, (int)ntiles);
     return check_launch("hist_encoder_tc");
 }
 

@@ -113,6 +113,8 @@ __global__ void __launch_bounds__(256) layout_bf16_v8_kernel(const bf16* __restr
     const int b = blockIdx.z, n0 = blockIdx.x * TN, c0 = blockIdx.y * TC, N = H * W;
     const uint16_t* src = reinterpret_cast<const uint16_t*>(src_);
     uint16_t* dst = reinterpret_cast<uint16_t*>(dst_);
+    pdl_trigger();                         // short, bandwidth-bound kernel: the next one may queue up behind it at once
+    pdl_wait();
     if (kToTokens) {
 #pragma unroll
         for (int i = threadIdx.x; i < TC * NCH; i += 256) {  // NCHW side: (channel, 8 tokens)
@@ -173,7 +175,7 @@ template <bool kToTokens, int TC>
 static void launch_v8(const void* src, const float* pos, void* dst, int B, int C, int H, int W, int pos_w, int oy, int ox,
                       cudaStream_t st) {
     dim3 grid((H * W + 4096 / TC - 1) / (4096 / TC), C / TC, B);
-    layout_bf16_v8_kernel<kToTokens, TC><<<grid, 256, 0, st>>>((const bf16*)src, pos, (bf16*)dst, C, H, W, pos_w, oy, ox);
+    launch_pdl(layout_bf16_v8_kernel<kToTokens, TC>, grid, 256, 0, st, (const bf16*)src, pos, (bf16*)dst, C, H, W, pos_w, oy, ox);
 }
 
 template <typename T>
@@ -245,7 +247,7 @@ __global__ void zone_masks_kernel(const uint8_t* __restrict__ mask, uint8_t* __r
 
 int zone_masks(const uint8_t* mask, uint8_t* zm, uint8_t* hm, uint8_t* pm, int B, int H, int W,
                const cfp_geom& g, cudaStream_t st) {
-    zone_masks_kernel<<<148 * 4, 256, 0, st>>>(mask, zm, hm, pm, B, H, W, g);
+    zone_masks_kernel<<<sm_count() * 4, 256, 0, st>>>(mask, zm, hm, pm, B, H, W, g);
     return check_launch("zone_masks_kernel");
 }
 

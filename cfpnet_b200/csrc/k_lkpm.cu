@@ -20,7 +20,7 @@ template <int K, typename T>
 __global__ void __launch_bounds__(kThreads) dwconv_bn_relu_kernel(const T* __restrict__ in, T* __restrict__ out,
                                                                   int H, int W, int C,
                                                                   const float* __restrict__ dw_t,
-                                                                  const float* __restrict__ dw_shift) {
+                                                                  const float* __restrict__ dw_shift, int relu) {
     constexpr int HP = kDwTile + K - 1, PADK = (K - 1) / 2, Q = 8, NIN = 2 * (Q - 1) + K;
     extern __shared__ __align__(16) float smem[];
     float* halo = smem;                         // [HP][HP][16]
@@ -30,16 +30,17 @@ __global__ void __launch_bounds__(kThreads) dwconv_bn_relu_kernel(const T* __res
     const int y0 = blockIdx.y * kDwTile, x0 = blockIdx.x * kDwTile;
     const size_t frame = (size_t)b * H * W;
 
+    for (int i = threadIdx.x; i < K * K * (kDwCh / 4); i += kThreads) {          // taps: weights, before the wait
+        const int tap = i / (kDwCh / 4), c = (i % (kDwCh / 4)) * 4;
+        *reinterpret_cast<float4*>(wsm + tap * kDwCh + c) = *reinterpret_cast<const float4*>(dw_t + (size_t)tap * C + c0 + c);
+    }
+    pdl_wait();
     for (int i = threadIdx.x; i < HP * HP * (kDwCh / 4); i += kThreads) {
         const int cell = i / (kDwCh / 4), c = (i % (kDwCh / 4)) * 4;
         const int y = y0 - PADK + cell / HP, x = x0 - PADK + cell % HP;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (y >= 0 && y < H && x >= 0 && x < W) v = IO<T>::ld4(in + (frame + (size_t)y * W + x) * C + c0 + c);
         *reinterpret_cast<float4*>(halo + cell * kDwCh + c) = v;
-    }
-    for (int i = threadIdx.x; i < K * K * (kDwCh / 4); i += kThreads) {
-        const int tap = i / (kDwCh / 4), c = (i % (kDwCh / 4)) * 4;
-        *reinterpret_cast<float4*>(wsm + tap * kDwCh + c) = *reinterpret_cast<const float4*>(dw_t + (size_t)tap * C + c0 + c);
     }
     __syncthreads();
 
@@ -74,6 +75,7 @@ __global__ void __launch_bounds__(kThreads) dwconv_bn_relu_kernel(const T* __res
             }
         }
     }
+    pdl_trigger();
     const float sh = dw_shift[c0 + c];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -82,31 +84,33 @@ __global__ void __launch_bounds__(kThreads) dwconv_bn_relu_kernel(const T* __res
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
             const int x = x0 + 2 * q + xh;
-            if (x < W) IO<T>::st(out + (frame + (size_t)y * W + x) * C + c0 + c, fmaxf(acc[r][q] + sh, 0.f));
+            if (x < W) IO<T>::st(out + (frame + (size_t)y * W + x) * C + c0 + c, relu ? fmaxf(acc[r][q] + sh, 0.f) : acc[r][q] + sh);
         }
     }
 }
 
 template <int K, typename T>
 static int dw_launch(const void* in, void* out, int B, int H, int W, int C, const float* dw_t, const float* dw_shift,
-                     cudaStream_t st) {
+                     int relu, cudaStream_t st) {
     constexpr int HP = kDwTile + K - 1;
     const size_t smem = (size_t)(HP * HP * kDwCh + K * K * kDwCh) * sizeof(float);
     auto k = dwconv_bn_relu_kernel<K, T>;
     if (int e = set_smem(k, smem)) return e;
     dim3 grid((W + kDwTile - 1) / kDwTile, (H + kDwTile - 1) / kDwTile, B * (C / kDwCh));
-    k<<<grid, kThreads, smem, st>>>((const T*)in, (T*)out, H, W, C, dw_t, dw_shift);
+    launch_pdl(k, grid, kThreads, smem, st, (const T*)in, (T*)out, H, W, C, dw_t, dw_shift, relu);
     return check_launch(K == 31 ? "dwconv<31>" : K == 15 ? "dwconv<15>" : "dwconv<7>");
 }
 
+// relu = 0: the plain depthwise conv + per-channel shift (train mode: shift = the conv bias, BatchNorm follows as its
+// own kernels; with the taps flipped in both axes and shift = 0 it is the conv's input gradient)
 int dwconv_bn_relu(const void* in, void* out, int B, int H, int W, int C, int ksize, const float* dw_t,
-                   const float* dw_shift, int dtype, cudaStream_t st) {
+                   const float* dw_shift, int dtype, cudaStream_t st, int relu) {
     CFP_REQUIRE(C % kDwCh == 0, "dwconv: C=%d not a multiple of %d", C, kDwCh);
     CFP_REQUIRE((size_t)B * (C / kDwCh) <= 65535, "dwconv: B*C/16=%zu exceeds grid.z", (size_t)B * (C / kDwCh));
 #define CFP_DW(KS)                                                                                       \
     if (ksize == KS)                                                                                     \
-        return dtype == CFP_F32 ? dw_launch<KS, float>(in, out, B, H, W, C, dw_t, dw_shift, st)          \
-                                : dw_launch<KS, bf16>(in, out, B, H, W, C, dw_t, dw_shift, st);
+        return dtype == CFP_F32 ? dw_launch<KS, float>(in, out, B, H, W, C, dw_t, dw_shift, relu, st)    \
+                                : dw_launch<KS, bf16>(in, out, B, H, W, C, dw_t, dw_shift, relu, st);
     CFP_DW(7) CFP_DW(15) CFP_DW(31)
 #undef CFP_DW
     return fail("unsupported large_kernel=%d: libcfp serves 7, 15, 31 (decoder.py:92-94)", ksize);

@@ -258,7 +258,7 @@ static int d2i_impl(void* feat0, const void* emb, const void* zone_tok, const fl
     if (g.interpolate) {
         const int64_t total = (int64_t)B * (g.ry1 - g.ry0) * (g.rx1 - g.rx0) * (C / 4);
         const int64_t want = (total + 255) / 256;
-        const unsigned grid = (unsigned)(want < 148 * 8 ? want : 148 * 8);
+        const unsigned grid = (unsigned)(want < sm_count() * 8 ? want : sm_count() * 8);
         canvas_resize_add_kernel<T><<<grid, 256, 0, st>>>((const T*)(ws + L.canvas), (T*)feat0, B, H, W, C, g, assign);
         return check_launch("canvas_resize_add_kernel");
     }

@@ -75,13 +75,15 @@ class HistogramEncoder(nn.Module):
         return w, (stages, tc, buf)
 
     def forward(self, hist_data):
-        if self.training:
-            raise NotImplementedError("libcfp serves eval-mode BatchNorm only (running statistics folded); "
-                                      "the training step is a later row of the scope table")
         _lib.require_cuda(hist_data, "hist_data")
         B, Z, N, D = hist_data.shape
         if D != 1:
             raise ValueError("hist_data must be [B,Z,N,1] (deltar.py:40)")
+        if self.training:
+            # train mode (train.py:75): BatchNorm on batch statistics, differentiable - fp32 training kernels behind an
+            # autograd Function (cfpnet_b200/train.py); returns the three token tensors as a list like the eval path
+            from .train import HistEncoderTrainFn
+            return list(HistEncoderTrainFn.apply(self, hist_data, *self.parameters()))
         dt = self.out_dtype or (hist_data.dtype if hist_data.dtype == torch.bfloat16 else torch.float32)
         w, _keep = self._cache.get(self, self._pack)
         x = hist_data.detach().reshape(-1).float().contiguous()

@@ -264,6 +264,18 @@ class Block14(nn.Module):
         return w
 
 
+    def forward(self, x):
+        """Block14.forward (convnext.py:42-58) on an NCHW map, as a stand-alone module: train mode (BatchNorm on batch
+        statistics, differentiable) through the fp32 training kernels of cfpnet_b200/train.py.  Inside
+        ``TransformerFusion`` the eval-mode block is driven through ``cfp_lkpm_fwd`` on token-major maps instead."""
+        _lib.require_cuda(x, "x")
+        if not self.training:
+            raise NotImplementedError("stand-alone Block14.forward serves train mode; eval mode runs inside "
+                                      "TransformerFusion.forward (cfp_lkpm_fwd)")
+        from .train import LkpmTrainFn
+        return LkpmTrainFn.apply(self, x, *self.parameters())
+
+
 class Combine1(nn.Module):
     """DAPM -> LKPM, transformer.py:251-259."""
 

@@ -113,6 +113,12 @@ class PackCache:
     def __reduce__(self):
         return (PackCache, ())
 
+    def invalidate(self):
+        """Drop every packed copy: for writers that update parameters through raw pointers (the libcfp optimizer step,
+        cfpnet_b200/train.py), which torch's version counters do not see."""
+        with self._lock:
+            self._entries.clear()
+
     @staticmethod
     def _key(module: nn.Module):
         return tuple((t.data_ptr(), t._version, str(t.device)) for t in

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define CFP_ABI_VERSION 10
+#define CFP_ABI_VERSION 11
 
 #if defined(__GNUC__)
 #define CFP_API __attribute__((visibility("default")))
@@ -188,12 +188,75 @@ CFP_API int cfp_lkpm_fwd(void *feat0, int B, int H, int W, int C, const cfp_lkpm
 CFP_API int cfp_twins_fwd(void *feat0, int B, int H, int W, int C, const cfp_twins_w *w, void *workspace,
                   size_t workspace_bytes, int dtype, void *stream);
 
+/* ---- Training step (BASELINE config 5; reference train.py:96-135 with the modules in .train() mode, BatchNorm on
+ * batch statistics per replica as under nn.DataParallel, train.py:45).  The reference differentiates its modules with
+ * autograd; here the step is a sequence of these fp32 building blocks (token-major [rows][C] maps), ordered by
+ * cfpnet_b200/train.py exactly as oracle/cfp_oracle_bwd.py states the backward.  Each names the reference op it serves.
+ *
+ * cfp_tr_gemm: C[M][N] (+)= A . B (+ bias[N]); element (i,k) of A at a[i*a_rs + k*a_cs], (k,j) of B at b[k*b_rs + j*b_cs].
+ *   nn.Linear / Conv1d(k=1) forward x W^T + b (encoder.py:19-23, convnext.py:51-53), its input gradient dy W and its
+ *   weight gradient dy^T x (a reduction over every row of the batch: split over K across CTAs, fp32 atomics).
+ *   accumulate != 0 adds to the existing C. */
+CFP_API int cfp_tr_gemm(const float *a, int64_t a_rs, int64_t a_cs, const float *b, int64_t b_rs, int64_t b_cs, float *c,
+                        int64_t c_rs, int M, int N, int K, const float *bias, int accumulate, void *stream);
+/* out[c] = sum_r x[r][c]: bias gradients. */
+CFP_API int cfp_tr_colsum(const float *x, float *out, int64_t rows, int C, void *stream);
+/* Train-mode BatchNorm (encoder.py:21-23, convnext.py:45-46, transformer.py:239-244): batch mean and biased variance
+ * over the rows (two passes), rstd = rsqrt(var + eps); running_mean / running_var (nullable) updated in place with
+ * `momentum` and the unbiased variance, as torch.nn.functional.batch_norm does.  scratch: 2*C floats. */
+CFP_API int cfp_tr_bn_stats(const float *x, int64_t rows, int C, float eps, float momentum, float *mean, float *rstd,
+                            float *running_mean, float *running_var, float *scratch, void *stream);
+/* y = (x - mean) * rstd * gamma + beta, then ReLU when relu != 0. */
+CFP_API int cfp_tr_bn_apply(const float *x, const float *mean, const float *rstd, const float *gamma, const float *beta,
+                            float *y, int64_t rows, int C, int relu, void *stream);
+/* Backward of cfp_tr_bn_apply (+ the ReLU behind it when relu != 0) with batch statistics:
+ * dx = gamma*rstd/n * (n g - sum g - xhat sum(g xhat)); dgamma = sum g xhat, dbeta = sum g. */
+CFP_API int cfp_tr_bn_bwd(const float *dy, const float *x, const float *mean, const float *rstd, const float *gamma,
+                          const float *beta, float *dx, float *dgamma, float *dbeta, int64_t rows, int C, int relu,
+                          void *stream);
+/* LayerNorm over the channel dim (convnext.py:60-85 channels_last, nn.LayerNorm of transformer.py:36-37) and its
+ * backward (dx, dgamma, dbeta). */
+CFP_API int cfp_tr_ln_fwd(const float *x, const float *g, const float *b, float *y, int64_t rows, int C, float eps,
+                          void *stream);
+CFP_API int cfp_tr_ln_bwd(const float *x, const float *g, const float *dy, float *dx, float *dg, float *db, int64_t rows,
+                          int C, float eps, void *stream);
+/* Elementwise: op 0 out = a + b | 1 out = a * (b > 0) | 2 out = gelu_erf(a) | 3 out = a * gelu_erf'(b) | 4 out = relu(a)
+ * | 5 out = a * d/db(elu(b) + 1). */
+CFP_API int cfp_tr_ew(const float *a, const float *b, float *out, int64_t n, int op, void *stream);
+/* k x k depthwise conv on a token-major map, out = conv(in) + shift[c] (ReLU when relu != 0): Block14.dwconv2 in train
+ * mode (convnext.py:45; shift = the conv bias) and, with the taps flipped in both axes and shift = 0, its input
+ * gradient.  taps_t [k*k][C]. */
+CFP_API int cfp_tr_dwconv(const float *in, float *out, int B, int H, int W, int C, int ksize, const float *taps_t,
+                          const float *shift, int relu, void *stream);
+/* dw[c][i][j] = sum_{b,y,x} dy[b][y][x][c] * x[b][y+i-p][x+j-p][c]: weight gradient of that conv, [C][k][k]. */
+CFP_API int cfp_tr_dwconv_wgrad(const float *x, const float *dy, float *dw, int B, int H, int W, int C, int ksize,
+                                void *stream);
+
+/* Optimizer step on the flat gradient bucket (train.py:124-129: clip_grad_norm_(parameters, 0.1), AdamW.step()).
+ * cfp_tr_sumsq: out[0] = sum_i (x[i] * scale)^2 (the squared global gradient norm; scale = 1 / world after a sum
+ * all-reduce).  `out` is CFP_SUMSQ_FLOATS floats, zero-initialised once by the caller (result, per-CTA partials, a
+ * ticket): the sum is formed in a fixed order, so replicas that hold the same bucket get the same bits.  cfp_tr_adamw: torch.optim.AdamW's update of p / m / v [n] with gradient g * grad_scale * min(1, max_norm /
+ * (sqrt(*sumsq) + 1e-6)) (max_norm <= 0: no clipping, sumsq may be NULL); `step` >= 1 is the bias-correction step count;
+ * element i uses the learning rate seg_lr[s] of the segment with seg_end[s-1] <= i < seg_end[s] (device arrays [nseg]: the
+ * reference's 1x / 10x parameter groups, train.py:75-76).  Nothing here synchronises with the host. */
+#define CFP_SUMSQ_FLOATS 1026
+CFP_API int cfp_tr_sumsq(const float *x, int64_t n, float scale, float *out, void *stream);
+CFP_API int cfp_tr_adamw(float *p, const float *g, float *m, float *v, int64_t n, const int64_t *seg_end, const float *seg_lr,
+                         int nseg, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                         const float *sumsq, float max_norm, void *stream);
+
 /* Accounting / tracing (no reference counterpart: the reference has no profiling hooks,
- * SURVEY.md §5).  cfp_launch_count: kernels this thread has enqueued since load.
- * cfp_profile_start: from now on this thread records one CUDA event per kernel launch on the
- * call's stream.  cfp_profile_stop: waits for the recorded events (the one place the library
+ * SURVEY.md §5).  cfp_launch_count: kernels this process has enqueued since load (all threads: a training
+ * step's backward is enqueued from autograd's thread).
+ * cfp_profile_start: from now on one CUDA event is recorded per kernel launch on the call's stream (all threads).  cfp_profile_stop: waits for the recorded events (the one place the library
  * blocks), writes {"kernel_name": [launches, total_ms], ...} as JSON into out[cap]. */
 CFP_API int64_t cfp_launch_count(void);
+/* Programmatic dependent launch of the bf16-path kernels for the calling thread: 1 = on (the default: a kernel's
+ * prologue overlaps the previous kernel's drain; measured -3.5 % on a single stream), 0 = off (what FusionPath selects
+ * while it runs the three levels on three streams: pre-launched CTAs then only take slots from the other streams'
+ * kernels, measured +1.5 %), -1 = back to the default.  Returns the previous setting.  CFP_NO_PDL=1 in the
+ * environment disables it process-wide. */
+CFP_API int cfp_set_pdl(int on);
 /* Known-answer self-test of the tcgen05 engine (tests only): d[m][j] = sum_k a[m+row_shift][k] *
  * b[j][k] for m < 128; a [rows_a][k] and b [n][k] are bf16 row-major, d [128][n] fp32. */
 CFP_API int cfp_selftest_umma(const void *a, const void *b, float *d, int rows_a, int n, int k, int row_shift,

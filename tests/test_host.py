@@ -204,7 +204,7 @@ def test_product_path_has_no_cpu_fallback():
     enc = cfpnet_b200.HistogramEncoder().eval()
     with pytest.raises(_lib.CfpError, match="no CPU implementation"):
         enc(inp["hist_data"].unsqueeze(-1))
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(_lib.CfpError, match="no CPU implementation"):          # train mode is CUDA-only too
         enc.train()(inp["hist_data"].unsqueeze(-1))
 
 
