@@ -412,6 +412,39 @@ CFP_API int cfp_tr_adamw(float* p, const float* g, float* m, float* v, int64_t n
                     (cudaStream_t)stream);
 }
 
+// ---------------------------------------------------------------- input side (f3) and loss / metrics (f4)
+CFP_API int cfp_zone_hist(const float* dep, int B, int H, int W, int sy, int sx, int ph, int pw, int zone_num, int nbins,
+                          float max_distance, const double* centres, float* fh, uint8_t* mask, int* hist_out, void* stream) {
+    begin_call(stream);
+    CFP_REQUIRE(dep && centres && fh && mask, "null pointer");
+    CFP_REQUIRE(B > 0 && H > 0 && W > 0, "bad shape");
+    return zone_hist(dep, B, H, W, sy, sx, ph, pw, zone_num, nbins, max_distance, centres, fh, mask, hist_out, (cudaStream_t)stream);
+}
+CFP_API int cfp_zone_samples(const float* fh, const uint8_t* mask, float* out, int64_t zones, int S, const float* w0,
+                             const float* w1, int mode, void* stream) {
+    begin_call(stream);
+    CFP_REQUIRE(fh && mask && out, "null pointer");
+    return zone_samples(fh, mask, out, zones, S, w0, w1, mode, (cudaStream_t)stream);
+}
+CFP_API int cfp_silog_fwd(const float* pred, const float* target, const uint8_t* mask, int B, int h, int w, int H, int W,
+                          int interpolate, double* scratch, float* loss, void* stream) {
+    begin_call(stream);
+    CFP_REQUIRE(pred && target && scratch && loss, "null pointer");
+    return silog_fwd(pred, target, mask, B, h, w, H, W, interpolate, scratch, loss, (cudaStream_t)stream);
+}
+CFP_API int cfp_silog_bwd(const float* pred, const float* target, const uint8_t* mask, int B, int h, int w, int H, int W,
+                          int interpolate, const double* scratch, float grad_out, float* grad_pred, void* stream) {
+    begin_call(stream);
+    CFP_REQUIRE(pred && target && scratch && grad_pred, "null pointer");
+    return silog_bwd(pred, target, mask, B, h, w, H, W, interpolate, scratch, grad_out, grad_pred, (cudaStream_t)stream);
+}
+CFP_API int cfp_depth_metrics(const float* gt, const float* pred, const uint8_t* valid, int64_t n, double* scratch, double* out,
+                              void* stream) {
+    begin_call(stream);
+    CFP_REQUIRE(gt && pred && scratch && out, "null pointer");
+    return depth_metrics(gt, pred, valid, n, scratch, out, (cudaStream_t)stream);
+}
+
 CFP_API int cfp_selftest_umma(const void* a, const void* b, float* d, int rows_a, int n, int k, int row_shift,
                               void* stream) {
     begin_call(stream);

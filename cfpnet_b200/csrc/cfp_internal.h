@@ -93,6 +93,17 @@ int tr_adamw(float* p, const float* g, float* m, float* v, int64_t n, const int6
              cudaStream_t st);
 int tr_dwconv_wgrad(const float* x, const float* dy, float* dw, int B, int H, int W, int C, int K, cudaStream_t st);
 
+// k_io.cu  (input side f3, loss / metrics f4)
+int zone_hist(const float* dep, int B, int H, int W, int sy, int sx, int ph, int pw, int zn, int nbins, float max_distance,
+              const double* centres, float* fh, uint8_t* mask, int* hist_out, cudaStream_t st);
+int zone_samples(const float* fh, const uint8_t* mask, float* out, int64_t zones, int S, const float* w0, const float* w1, int mode,
+                 cudaStream_t st);
+int silog_fwd(const float* pred, const float* target, const uint8_t* mask, int B, int h, int w, int H, int W, int interpolate,
+              double* scratch, float* loss, cudaStream_t st);
+int silog_bwd(const float* pred, const float* target, const uint8_t* mask, int B, int h, int w, int H, int W, int interpolate,
+              const double* scratch, float gout, float* grad_pred, cudaStream_t st);
+int depth_metrics(const float* gt, const float* pred, const uint8_t* valid, int64_t n, double* scratch, double* out, cudaStream_t st);
+
 // k_selftest.cu
 int umma_selftest(const void* A, const void* B, float* D, int rows_a, int N, int K, int row_shift, cudaStream_t st);
 

@@ -22,6 +22,19 @@ from .layers import Combine1, LoFTREncoderLayer, TwinsTransformer
 from .packing import PackCache, Packer, Scratch, host, relocate
 
 
+MICRO_DEFAULT = {128: 1, 64: 1, 32: 1}
+
+
+def _micro_default(dim: int) -> int:
+    import os
+    table = dict(MICRO_DEFAULT)
+    for item in os.environ.get("CFP_MICRO", "").split(","):
+        if ":" in item:
+            k, v = item.split(":")
+            table[int(k)] = int(v)
+    return max(1, table.get(dim, 1))
+
+
 class TransformerFusion(nn.Module):
     def __init__(self, embedding_dim, max_resolution, num_heads=4, large_kernel=None, patch_size=None):
         super().__init__()
@@ -54,6 +67,8 @@ class TransformerFusion(nn.Module):
         self.conv_patch_size = 640 / self.max_resolution[1]
         self._cache = PackCache()
         self._scratch = Scratch()
+        # batch slices run on separate streams inside one forward (see forward()); CFP_MICRO="128:4,64:2,32:1" overrides
+        self.micro_batches = _micro_default(embedding_dim)
 
     def _replicate_for_data_parallel(self):
         """``nn.DataParallel`` replicas copy ``__dict__`` shallowly: give each its own pack cache and scratch (the
@@ -125,42 +140,77 @@ class TransformerFusion(nn.Module):
         feat1 = feat1.detach().to(dt).contiguous()
         mask = kwargs["mask"].to(device=dev, dtype=torch.uint8).contiguous()
         cg = _lib.CfpGeom.from_geometry(g)
-        st = None
-        with torch.cuda.device(dev):
+        out = kwargs.get("out")                  # optional caller-provided result buffer (same shape/dtype)
+        if out is None:
+            out = torch.empty(B, D, H, W, device=dev, dtype=dt)
+        elif out.shape != x.shape or out.dtype != dt or out.device != dev or not out.is_contiguous():
+            raise ValueError("out= must be a contiguous tensor shaped and typed like x")
+        emb_copy = (not args.change_embedding) and "hist2image" in self.layer_names
+
+        def run(part, b0, b1):
+            """Frames [b0, b1) through the layer list on the current stream (scratch slot `part`)."""
+            Bp = b1 - b0
             lib = _lib.load()
-            ws_bytes = lib.cfp_workspace_bytes(B, H, W, D, self.ws, self.large_kernel or 0, code, C.byref(cg))
+            ws_bytes = lib.cfp_workspace_bytes(Bp, H, W, D, self.ws, self.large_kernel or 0, code, C.byref(cg))
             # scratch (workspace + token map) is owned by the module and reused across calls: stream order
             # makes that safe for back-to-back forwards on one stream, and it keeps hundreds of MB of
             # per-call allocations (cudaMalloc stalls once several streams are in play) off the hot path.
             # One module instance must not run on two streams at once (replicas own their scratch).
             work, feat0 = self._scratch.get(
-                dev.index, (dt, B, H, W), lambda t: t[0].numel() >= ws_bytes,
+                dev.index, (dt, Bp, H, W, part), lambda t: t[0].numel() >= ws_bytes,
                 lambda: (torch.empty(ws_bytes, device=dev, dtype=torch.uint8),
-                         torch.empty(B, H * W, D, device=dev, dtype=dt)))
+                         torch.empty(Bp, H * W, D, device=dev, dtype=dt)))
             st = _lib.stream_ptr()
-            _lib.call("cfp_posenc_tokens_fwd", x.data_ptr(), pos, feat0.data_ptr(), B, D, H, W,
+            xp, f1p, mp, op = x[b0:b1], feat1[b0:b1], mask[b0:b1], out[b0:b1]
+            _lib.call("cfp_posenc_tokens_fwd", xp.data_ptr(), pos, feat0.data_ptr(), Bp, D, H, W,
                       self.max_resolution[0], self.max_resolution[1], oy, ox, code, st)
-            emb = feat0
-            if not args.change_embedding and "hist2image" in self.layer_names:
-                emb = feat0.clone()                          # fusion.py:134-136: canvas cut from the first map
+            emb = feat0.clone() if emb_copy else feat0       # fusion.py:134-136: canvas cut from the first map
             for w, name in zip(packed, self.layer_names):
                 if name == "image":
-                    _lib.call("cfp_twins_fwd", feat0.data_ptr(), B, H, W, D, C.byref(w), work.data_ptr(),
+                    _lib.call("cfp_twins_fwd", feat0.data_ptr(), Bp, H, W, D, C.byref(w), work.data_ptr(),
                               ws_bytes, code, st)
                 elif name == "hist2image":
-                    _lib.call("cfp_d2i_fwd", feat0.data_ptr(), emb.data_ptr(), feat1.data_ptr(), pos2,
-                              mask.data_ptr(), B, H, W, D, S, C.byref(cg), C.byref(w),
+                    _lib.call("cfp_d2i_fwd", feat0.data_ptr(), emb.data_ptr(), f1p.data_ptr(), pos2,
+                              mp.data_ptr(), Bp, H, W, D, S, C.byref(cg), C.byref(w),
                               int(bool(args.no_skip_inside)), work.data_ptr(), ws_bytes, code, st)
                 else:   # combine1: DAPM then LKPM (transformer.py:270-273)
                     dapm_w, lkpm_w = w
-                    _lib.call("cfp_dapm_fwd", feat0.data_ptr(), B, H, W, D, C.byref(cg), C.byref(dapm_w),
+                    _lib.call("cfp_dapm_fwd", feat0.data_ptr(), Bp, H, W, D, C.byref(cg), C.byref(dapm_w),
                               work.data_ptr(), ws_bytes, code, st)
-                    _lib.call("cfp_lkpm_fwd", feat0.data_ptr(), B, H, W, D, C.byref(lkpm_w), work.data_ptr(),
+                    _lib.call("cfp_lkpm_fwd", feat0.data_ptr(), Bp, H, W, D, C.byref(lkpm_w), work.data_ptr(),
                               ws_bytes, code, st)
-            out = kwargs.get("out")              # optional caller-provided result buffer (same shape/dtype)
-            if out is None:
-                out = torch.empty(B, D, H, W, device=dev, dtype=dt)
-            elif out.shape != x.shape or out.dtype != dt or out.device != dev or not out.is_contiguous():
-                raise ValueError("out= must be a contiguous tensor shaped and typed like x")
-            _lib.call("cfp_tokens_to_nchw", feat0.data_ptr(), out.data_ptr(), B, D, H, W, code, st)
+            _lib.call("cfp_tokens_to_nchw", feat0.data_ptr(), op.data_ptr(), Bp, D, H, W, code, st)
+
+        parts = max(1, min(int(self.micro_batches), B))
+        with torch.cuda.device(dev):
+            if parts == 1:
+                run(0, 0, B)
+                return out
+            # Frames are independent in eval mode: the batch is cut into `parts` slices that run the layer list on
+            # separate streams.  The kernels of the small maps (1/16 scale: one or two waves of long serial tile
+            # chains, one CTA per SM) are latency-bound; two half-batches keep twice as many chains in flight.
+            cur = torch.cuda.current_stream(dev)
+            side = self.__dict__.setdefault("_part_streams", {}).setdefault(
+                dev.index, [torch.cuda.Stream(dev) for _ in range(8)])
+            fork = torch.cuda.Event()
+            fork.record(cur)
+            joins = []
+            prev_pdl = _lib.set_pdl(False)       # pre-launched CTAs would only take slots from the other slices' kernels
+            try:
+                for i in range(parts):
+                    b0, b1 = i * B // parts, (i + 1) * B // parts
+                    if i == parts - 1:
+                        run(i, b0, b1)           # the last slice stays on the caller's stream
+                        continue
+                    s_ = side[i % len(side)]
+                    s_.wait_event(fork)
+                    with torch.cuda.stream(s_):
+                        run(i, b0, b1)
+                        e = torch.cuda.Event()
+                        e.record(s_)
+                    joins.append(e)
+            finally:
+                _lib.set_pdl(bool(prev_pdl))
+            for e in joins:
+                cur.wait_event(e)
         return out

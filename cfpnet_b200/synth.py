@@ -135,3 +135,19 @@ def synthetic_state_dict(shapes: Mapping[str, Sequence[int]], seed: int = 0) -> 
             raise KeyError(f"no synthetic rule for {name} {shape}")
         sd[name] = t
     return sd
+
+
+def synthetic_depth_map(h: int, w: int, seed: int) -> torch.Tensor:
+    """Piecewise-smooth synthetic depth map [h,w] in metres for the input-side fixtures: a tilted plane with noise, boxes
+    at other depths (zones with two clusters), a band of invalid (zero) pixels and a far corner beyond the sensor range
+    (zones with no signal)."""
+    g = torch.Generator().manual_seed(seed)
+    yy, xx = torch.meshgrid(torch.linspace(0, 1, h), torch.linspace(0, 1, w), indexing="ij")
+    d = 0.6 + 2.8 * yy + 0.5 * xx + 0.02 * torch.randn(h, w, generator=g)
+    for _ in range(14):
+        y0, x0 = int(torch.randint(0, h - 40, [1], generator=g)), int(torch.randint(0, w - 40, [1], generator=g))
+        hh, ww = int(torch.randint(20, 90, [1], generator=g)), int(torch.randint(20, 90, [1], generator=g))
+        d[y0:y0 + hh, x0:x0 + ww] = float(torch.rand(1, generator=g) * 5.0 + 0.2)
+    d[h // 3: h // 3 + 60, : w // 2] = 0.0
+    d[:130, w - 200:] = 7.5
+    return d.float()

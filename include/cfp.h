@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define CFP_ABI_VERSION 11
+#define CFP_ABI_VERSION 12
 
 #if defined(__GNUC__)
 #define CFP_API __attribute__((visibility("default")))
@@ -244,6 +244,42 @@ CFP_API int cfp_tr_sumsq(const float *x, int64_t n, float scale, float *out, voi
 CFP_API int cfp_tr_adamw(float *p, const float *g, float *m, float *v, int64_t n, const int64_t *seg_end, const float *seg_lr,
                          int nseg, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
                          const float *sumsq, float max_norm, void *stream);
+
+/* ---- Input side (the reference runs these on the host CPU inside its dataloader, one frame at a time).
+ *
+ * cfp_zone_hist: get_hist_parallel (src/utils/dataloader.py:84-134) for a batch of depth maps dep [B][H][W] (metres):
+ *   zone (zy, zx) of the zone_num x zone_num grid is the ph x pw patch at (sy + zy ph, sx + zx pw); its depths are binned
+ *   like torch.histc(bins = nbins, min = 0, max = max_distance), bin 0 is cleared, 20 is subtracted from every count
+ *   (clipped at 0), only the contiguous run of non-zero bins with the largest sum survives, and in float64
+ *   mu = sum(centre count) / (n + 1e-9), sigma = sqrt(sum(count (centre - mu)^2) / (n + 1e-9)) + 1e-9.
+ *   centres [nbins] (device, double) are the bin centres as the reference forms them (:120).  Outputs: fh [B][Z][2] =
+ *   (mu, sigma) fp32, mask [B][Z] = n > 0, hist_out [B][Z][nbins] int32 (nullable) = the surviving counts.
+ * cfp_zone_samples: sample_point_from_hist_parallel (:65-81): fh [zones][2], mask [zones] -> out [zones][S]; mode 0
+ *   (sample_uniform): out = w0[s] (mu - 3 sigma) + w1[s] (mu + 3 sigma) with w0 / w1 [S] = the reference's two linspace
+ *   ramps, every operation rounded to fp32 as the reference's (bit-identical results); mode 1: normal quantiles
+ *   mu + sigma w0[s] sqrt(2), w0[s] = erfinv(2 ppf_s - 1).  Zones with mask == 0 give zeros. */
+CFP_API int cfp_zone_hist(const float *dep, int B, int H, int W, int sy, int sx, int ph, int pw, int zone_num, int nbins,
+                          float max_distance, const double *centres, float *fh, uint8_t *mask, int *hist_out, void *stream);
+CFP_API int cfp_zone_samples(const float *fh, const uint8_t *mask, float *out, int64_t zones, int S, const float *w0,
+                             const float *w1, int mode, void *stream);
+
+/* ---- Loss and metrics.
+ * cfp_silog_fwd: SILogLoss.forward (src/loss.py:9-19): pred [B][1][h][w] is resized to the target [B][1][H][W] (bilinear,
+ *   align_corners; interpolate == 0: same size, no resize), g = log(up) - log(target) over the pixels with mask != 0 (NULL:
+ *   all), loss = 10 sqrt(var_unbiased(g) + 0.15 mean(g)^2).  Sums are accumulated in float64 in a fixed order.  scratch:
+ *   CFP_SILOG_SCRATCH_DOUBLES doubles, zeroed once by the caller; afterwards scratch[0..3] = n, mean, D, loss (what
+ *   cfp_silog_bwd reads).  cfp_silog_bwd: grad_pred [B][1][h][w] = grad_out * dloss/dpred (zeroed inside).
+ * cfp_depth_metrics: compute_errors (src/utils/metrics.py:4-24) over the n-element maps gt / pred where valid != 0 (NULL:
+ *   all): out[0..8] = a1 a2 a3 abs_rel rmse log_10 rmse_log silog sq_rel, out[9] = number of valid pixels (device doubles).
+ *   scratch: CFP_METRICS_SCRATCH_DOUBLES doubles, zeroed once by the caller. */
+#define CFP_SILOG_SCRATCH_DOUBLES 1544
+#define CFP_METRICS_SCRATCH_DOUBLES 5634
+CFP_API int cfp_silog_fwd(const float *pred, const float *target, const uint8_t *mask, int B, int h, int w, int H, int W,
+                          int interpolate, double *scratch, float *loss, void *stream);
+CFP_API int cfp_silog_bwd(const float *pred, const float *target, const uint8_t *mask, int B, int h, int w, int H, int W,
+                          int interpolate, const double *scratch, float grad_out, float *grad_pred, void *stream);
+CFP_API int cfp_depth_metrics(const float *gt, const float *pred, const uint8_t *valid, int64_t n, double *scratch, double *out,
+                              void *stream);
 
 /* Accounting / tracing (no reference counterpart: the reference has no profiling hooks,
  * SURVEY.md §5).  cfp_launch_count: kernels this process has enqueued since load (all threads: a training

@@ -573,3 +573,62 @@ def silog_loss(pred: Tensor, target: Tensor, mask: Optional[Tensor] = None, inte
         pred, target = pred[mask], target[mask]
     g = torch.log(pred) - torch.log(target)
     return 10 * torch.sqrt(torch.var(g) + 0.15 * torch.pow(torch.mean(g), 2))
+
+
+# --------------------------------------------------------------------------
+# f3 (input side): depth map -> per-zone (mu, sigma, validity)
+# --------------------------------------------------------------------------
+def zone_hist_params(dep: Tensor, sy: int, sx: int, ph: int, pw: int, zone_num: int, max_distance: float):
+    """One frame of ``get_hist_parallel`` (src/utils/dataloader.py:84-134) with the random draws already made:
+    ``dep`` [H,W] metres; zones of ph x pw px from (sy, sx).  Returns (fh [Z,2] float64 (mu, sigma), mask [Z] bool,
+    hist [Z,bins] float32 - the surviving cluster's counts).  :103-106 histogram per zone (torch.histc, 4 cm bins),
+    :110-111 bin 0 cleared and 20 subtracted, :112-118 strongest contiguous cluster, :120 bin centres through a float32
+    tensor of the upper edges, :126-131 moments in float64."""
+    import numpy as np
+    range_margin = list(np.arange(0, max_distance + 1e-9, 0.04))
+    bins = int(max_distance / 0.04)
+    Z = zone_num * zone_num
+    hist = torch.zeros(Z, bins, dtype=torch.float32)
+    for z in range(Z):
+        zy, zx = divmod(z, zone_num)
+        patch = dep[sy + zy * ph: sy + (zy + 1) * ph, sx + zx * pw: sx + (zx + 1) * pw].contiguous().float()
+        hist[z] = torch.histc(patch, bins=bins, min=0, max=max_distance)
+    hist[:, 0] = 0
+    hist = torch.clip(hist - 20, 0, None)
+    for z in range(Z):
+        row = hist[z].clone()
+        best, lo, hi, i = -1.0, 0, 0, 0
+        while i < bins:
+            if row[i] == 0:
+                i += 1
+                continue
+            j = i
+            while j < bins and row[j] != 0:
+                j += 1
+            s = float(row[i:j].sum())
+            if s > best:
+                best, lo, hi = s, i, j
+            i = j
+        hist[z] = 0
+        hist[z, lo:hi] = row[lo:hi]
+    dist = ((torch.Tensor(range_margin[1:]).double() + torch.tensor(range_margin[:-1], dtype=torch.float64)) / 2).unsqueeze(0)
+    n = torch.sum(hist, dim=1)
+    mask = n > 0
+    mu = torch.sum(dist * hist, dim=1) / (n + 1e-9)
+    std = torch.sqrt(torch.sum(hist * torch.pow(dist - mu.unsqueeze(-1), 2), dim=1) / (n + 1e-9)) + 1e-9
+    return torch.stack([mu, std], dim=1), mask, hist
+
+
+# --------------------------------------------------------------------------
+# f4 (metrics)
+# --------------------------------------------------------------------------
+def depth_metrics(gt: Tensor, pred: Tensor) -> dict:
+    """``compute_errors`` (src/utils/metrics.py:4-24) on 1-d tensors of valid pixels, float64."""
+    gt, pred = gt.double(), pred.double()
+    thresh = torch.maximum(gt / pred, pred / gt)
+    err = torch.log(pred) - torch.log(gt)
+    return dict(a1=float((thresh < 1.25).double().mean()), a2=float((thresh < 1.25 ** 2).double().mean()),
+                a3=float((thresh < 1.25 ** 3).double().mean()), abs_rel=float(((gt - pred).abs() / gt).mean()),
+                rmse=float(((gt - pred) ** 2).mean().sqrt()), log_10=float((torch.log10(gt) - torch.log10(pred)).abs().mean()),
+                rmse_log=float(((torch.log(gt) - torch.log(pred)) ** 2).mean().sqrt()),
+                silog=float(((err ** 2).mean() - err.mean() ** 2).sqrt() * 100), sq_rel=float((((gt - pred) ** 2) / gt).mean()))

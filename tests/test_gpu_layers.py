@@ -113,3 +113,30 @@ def test_dapm_layer_vs_oracle(level):
     out, g = layer_call(m, "dapm", 1, f, level=level)
     truth = O.dapm(O.sub(sd, "layers.1.transformer_path."), f.double().cpu(), g.asdict(), H, W)
     assert rel_l2(out, truth) <= 1e-4
+
+
+@pytest.mark.parametrize("parts", [2, 3])
+def test_micro_batched_forward_equals_whole_batch(parts):
+    """TransformerFusion.micro_batches: the batch cut into slices on separate streams gives the whole-batch result
+    (fp32: bit-identical except for the fp32 atomics of straddling attention groups)."""
+    import cfpnet_b200
+    from cfpnet_b200 import synth
+    from helpers import ref_keys, rel_l2
+    dev = "cuda:0"
+    inp = synth.make_inputs("G416", 5, seed=9, levels=(3,))
+    enc = cfpnet_b200.HistogramEncoder()
+    enc.load_state_dict(synth.synthetic_state_dict(ref_keys()["hist_encoder"], seed=0))
+    enc = enc.to(dev).eval()
+    args.attention_layer = list(synth.COMBINE1_LAYERS)
+    m = cfpnet_b200.TransformerFusion(128, [30, 40], large_kernel=7, patch_size=4)
+    m.load_state_dict(synth.synthetic_state_dict(ref_keys()["fusion_combine1_L3"], seed=3))
+    m = m.to(dev).eval()
+    outs = []
+    with torch.no_grad():
+        f128 = enc(inp["hist_data"].to(dev).unsqueeze(-1))[2]
+        for p in (1, parts):
+            m.micro_batches = p
+            torch.manual_seed(5)
+            outs.append(m(inp["x3"].to(dev), f128, mask=inp["mask"].to(dev), patch_info=inp["patch_info"], rect_data=None, rgb=None).float().cpu())
+    torch.cuda.synchronize()
+    assert rel_l2(outs[1], outs[0]) <= 1e-5

@@ -270,3 +270,12 @@ def test_zone_masks_kernel_formula_matches_reference_masks(tag):
     assert np.array_equal(zone.reshape(B, H * W), case.mask_bits("zone_mask"))
     assert np.array_equal(hist.reshape(B * Z, P), case.mask_bits("hist_mask"))
     assert np.array_equal(pad.reshape(B, g.tzh, g.tzw), case.mask_bits("pad_mask"))
+
+
+def test_header_constants_match_the_host_side():
+    from cfpnet_b200 import headers
+    src = open(os.path.join(ROOT, "include", "cfp.h")).read()
+    for name, val in (("CFP_SUMSQ_FLOATS", headers.SUMSQ_FLOATS), ("CFP_SILOG_SCRATCH_DOUBLES", headers.SILOG_SCRATCH_DOUBLES),
+                      ("CFP_METRICS_SCRATCH_DOUBLES", headers.METRICS_SCRATCH_DOUBLES)):
+        m = re.search(r"#define\s+%s\s+(\d+)" % name, src)
+        assert m and int(m.group(1)) == val, name
