@@ -18,7 +18,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcfp.so")
 
 CFP_F32, CFP_BF16 = 0, 1
-ABI_VERSION = 12
+ABI_VERSION = 13
 _fp = C.POINTER(C.c_float)
 
 
@@ -84,6 +84,12 @@ SIGNATURES = {
     "cfp_tr_dwconv_wgrad": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "cfp_tr_sumsq": (_i, [_p, _i64, C.c_float, _p, _p]),
     "cfp_tr_adamw": (_i, [_p, _p, _p, _p, _i64, _p, _p, _i] + [C.c_float] * 4 + [_i, C.c_float, _p, C.c_float, _p]),
+    "cfp_conv_fwd": (_i, [_p] + [_i] * 7 + [_p, _p, C.c_float, _p, _i, _i, _p]),
+    "cfp_upsample_concat": (_i, [_p, _i, _i, _i, _i, _p, _i, _p, _i, _i, _i, _i, _p]),
+    "cfp_posenc_tokens_nhwc_fwd": (_i, [_p, _i, _p, _p] + [_i] * 8 + [_p]),
+    "cfp_copy_channels": (_i, [_p, _i, _p, _i, _i, _i, _i64, _p]),
+    "cfp_head_bins": (_i, [_p, _i, _i, _i, _i] + [_p] * 7 + [_i, _i, C.c_float, C.c_float, _p, _p, _p, _p]),
+    "cfp_head_expect": (_i, [_p, _i, _i, _i, _p, _p, _p, _i, _p, _p, _p]),
     "cfp_zone_hist": (_i, [_p] + [_i] * 9 + [C.c_float, _p, _p, _p, _p, _p]),
     "cfp_zone_samples": (_i, [_p, _p, _p, _i64, _i, _p, _p, _i, _p]),
     "cfp_silog_fwd": (_i, [_p, _p, _p] + [_i] * 6 + [_p, _p, _p]),

@@ -104,6 +104,21 @@ int silog_bwd(const float* pred, const float* target, const uint8_t* mask, int B
               const double* scratch, float gout, float* grad_pred, cudaStream_t st);
 int depth_metrics(const float* gt, const float* pred, const uint8_t* valid, int64_t n, double* scratch, double* out, cudaStream_t st);
 
+// k_dec_tc.cu  (decoder shell f1, adaptive-bins head f2; bf16, channels-last)
+int conv_gen_tc(const void* in, int cin, int kc, int taps, const void* wpk, const float* shift, float slope, void* out, int out_pitch,
+                int out_coff, int B, int H, int W, int cout, cudaStream_t st);
+int upsample_concat(const void* lo, int h, int w, int c_lo, int lo_pitch, const float* skip, int c_skip, void* out, int B, int H, int W,
+                    int c_out, cudaStream_t st);
+int copy_channels(const void* src, int src_pitch, void* dst, int dst_pitch, int coff, int C, int64_t rows, cudaStream_t st);
+int posenc_tokens_nhwc(const void* x, int x_pitch, const float* pos, void* tokens, int B, int C, int H, int W, int pos_w, int oy, int ox,
+                       cudaStream_t st);
+int channel_mean(const void* x, int pitch, int C, int B, int npix, float* mean, cudaStream_t st);
+int head_regressor(const float* mean, const float* wc, const float* w0, const float* b0, const float* w2, const float* b2, const float* w4,
+                   const float* b4, int B, int E, int Hd, int nb, float min_val, float max_val, float* edges, float* centres,
+                   cudaStream_t st);
+int head_expect_tc(const void* x, int pitch, int B, int npix, const void* w_tc, const float* bias, const float* centres, int nb, float* pred,
+                   float* prob, cudaStream_t st);
+
 // k_selftest.cu
 int umma_selftest(const void* A, const void* B, float* D, int rows_a, int N, int K, int row_shift, cudaStream_t st);
 

@@ -98,6 +98,71 @@ class TransformerFusion(nn.Module):
                 relocate(s_, base)
         return packed, base + pos, base + pos2, buf
 
+
+    def _run_layers(self, packed, pos2, feat0, feat1, mask, B, H, W, D, S, cg, work, ws_bytes, code, st, emb_copy):
+        """The layer list on the token-major map ``feat0`` [B, H*W, D] (in place), current stream."""
+        emb = feat0.clone() if emb_copy else feat0           # fusion.py:134-136: canvas cut from the first map
+        for w, name in zip(packed, self.layer_names):
+            if name == "image":
+                _lib.call("cfp_twins_fwd", feat0.data_ptr(), B, H, W, D, C.byref(w), work.data_ptr(), ws_bytes, code, st)
+            elif name == "hist2image":
+                _lib.call("cfp_d2i_fwd", feat0.data_ptr(), emb.data_ptr(), feat1.data_ptr(), pos2, mask.data_ptr(), B, H, W, D, S,
+                          C.byref(cg), C.byref(w), int(bool(args.no_skip_inside)), work.data_ptr(), ws_bytes, code, st)
+            else:   # combine1: DAPM then LKPM (transformer.py:270-273)
+                dapm_w, lkpm_w = w
+                _lib.call("cfp_dapm_fwd", feat0.data_ptr(), B, H, W, D, C.byref(cg), C.byref(dapm_w), work.data_ptr(), ws_bytes,
+                          code, st)
+                _lib.call("cfp_lkpm_fwd", feat0.data_ptr(), B, H, W, D, C.byref(lkpm_w), work.data_ptr(), ws_bytes, code, st)
+
+    def forward_tokens(self, x_tok, x_pitch, B, H, W, feat1, out_tok, out_pitch, out_coff, **kwargs):
+        """The same call for a caller that holds its maps channels-last in bf16 (cfpnet_b200.decoder): ``x_tok`` is a
+        [B, H, W, x_pitch] buffer whose first ``embedding_dim`` channels are x; the result is written into channels
+        [out_coff, out_coff + embedding_dim) of ``out_tok`` [B, H, W, out_pitch] - the ``torch.cat([x_d, x_d_fused])`` of
+        decoder.py:112,117,122 without a transposed or concatenated copy.  Same positional-encoding draws as forward()."""
+        if self.training:
+            raise NotImplementedError("libcfp serves eval-mode BatchNorm only for the attention layers")
+        _lib.require_cuda(x_tok, "x_tok")
+        D = self.embedding_dim
+        if x_tok.dtype != torch.bfloat16 or out_tok.dtype != torch.bfloat16:
+            raise ValueError("forward_tokens serves the bf16 engine")
+        S = feat1.size(2)
+        g = zone_geometry(kwargs["patch_info"], self.max_resolution[1], H, W)
+        if any(n in ("hist2image", "combine1") for n in self.layer_names):
+            check_geometry(g, H, W)
+        if feat1.shape[0] != B or feat1.shape[1] != g.zone_num ** 2 or feat1.shape[3] != D:
+            raise ValueError(f"feat1 {tuple(feat1.shape)} does not match B={B}, zones={g.zone_num ** 2}, D={D}")
+        if S != self.positional_encodings2.shape[0]:
+            raise ValueError(f"feat1 carries {S} samples per zone, positional_encodings2 has {self.positional_encodings2.shape[0]}")
+        if tuple(kwargs["mask"].shape) != (B, g.zone_num ** 2):
+            raise ValueError(f"mask {tuple(kwargs['mask'].shape)} is not [B={B}, zones={g.zone_num ** 2}]")
+        oy = ox = 0
+        if H < self.max_resolution[0]:
+            oy = int(torch.randint(0, self.max_resolution[0] - H + 1, [1]))
+        if W < self.max_resolution[1]:
+            ox = int(torch.randint(0, self.max_resolution[1] - W + 1, [1]))
+        if H > self.max_resolution[0] or W > self.max_resolution[1]:
+            raise ValueError("feature map larger than the positional-encoding table")
+        packed, pos, pos2, _buf = self._cache.get(self, self._pack)
+        dev = x_tok.device
+        dt = torch.bfloat16
+        code = _lib.CFP_BF16
+        feat1 = feat1.detach().to(dt).contiguous()
+        mask = kwargs["mask"].to(device=dev, dtype=torch.uint8).contiguous()
+        cg = _lib.CfpGeom.from_geometry(g)
+        emb_copy = (not args.change_embedding) and "hist2image" in self.layer_names
+        with torch.cuda.device(dev):
+            lib = _lib.load()
+            ws_bytes = lib.cfp_workspace_bytes(B, H, W, D, self.ws, self.large_kernel or 0, code, C.byref(cg))
+            work, feat0 = self._scratch.get(
+                dev.index, (dt, B, H, W, 0), lambda t: t[0].numel() >= ws_bytes,
+                lambda: (torch.empty(ws_bytes, device=dev, dtype=torch.uint8), torch.empty(B, H * W, D, device=dev, dtype=dt)))
+            st = _lib.stream_ptr()
+            _lib.call("cfp_posenc_tokens_nhwc_fwd", x_tok.data_ptr(), x_pitch, pos, feat0.data_ptr(), B, D, H, W,
+                      self.max_resolution[0], self.max_resolution[1], oy, ox, st)
+            self._run_layers(packed, pos2, feat0, feat1, mask, B, H, W, D, S, cg, work, ws_bytes, code, st, emb_copy)
+            _lib.call("cfp_copy_channels", feat0.data_ptr(), D, out_tok.data_ptr(), out_pitch, out_coff, D, B * H * W, st)
+        return out_tok
+
     # ------------------------------------------------------------------ forward
     def forward(self, x, feat1, **kwargs):
         if self.training:
@@ -164,21 +229,7 @@ class TransformerFusion(nn.Module):
             xp, f1p, mp, op = x[b0:b1], feat1[b0:b1], mask[b0:b1], out[b0:b1]
             _lib.call("cfp_posenc_tokens_fwd", xp.data_ptr(), pos, feat0.data_ptr(), Bp, D, H, W,
                       self.max_resolution[0], self.max_resolution[1], oy, ox, code, st)
-            emb = feat0.clone() if emb_copy else feat0       # fusion.py:134-136: canvas cut from the first map
-            for w, name in zip(packed, self.layer_names):
-                if name == "image":
-                    _lib.call("cfp_twins_fwd", feat0.data_ptr(), Bp, H, W, D, C.byref(w), work.data_ptr(),
-                              ws_bytes, code, st)
-                elif name == "hist2image":
-                    _lib.call("cfp_d2i_fwd", feat0.data_ptr(), emb.data_ptr(), f1p.data_ptr(), pos2,
-                              mp.data_ptr(), Bp, H, W, D, S, C.byref(cg), C.byref(w),
-                              int(bool(args.no_skip_inside)), work.data_ptr(), ws_bytes, code, st)
-                else:   # combine1: DAPM then LKPM (transformer.py:270-273)
-                    dapm_w, lkpm_w = w
-                    _lib.call("cfp_dapm_fwd", feat0.data_ptr(), Bp, H, W, D, C.byref(cg), C.byref(dapm_w),
-                              work.data_ptr(), ws_bytes, code, st)
-                    _lib.call("cfp_lkpm_fwd", feat0.data_ptr(), Bp, H, W, D, C.byref(lkpm_w), work.data_ptr(),
-                              ws_bytes, code, st)
+            self._run_layers(packed, pos2, feat0, f1p, mp, Bp, H, W, D, S, cg, work, ws_bytes, code, st, emb_copy)
             _lib.call("cfp_tokens_to_nchw", feat0.data_ptr(), op.data_ptr(), Bp, D, H, W, code, st)
 
         parts = max(1, min(int(self.micro_batches), B))

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define CFP_ABI_VERSION 12
+#define CFP_ABI_VERSION 13
 
 #if defined(__GNUC__)
 #define CFP_API __attribute__((visibility("default")))
@@ -244,6 +244,40 @@ CFP_API int cfp_tr_sumsq(const float *x, int64_t n, float scale, float *out, voi
 CFP_API int cfp_tr_adamw(float *p, const float *g, float *m, float *v, int64_t n, const int64_t *seg_end, const float *seg_lr,
                          int nseg, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
                          const float *sumsq, float max_norm, void *stream);
+
+/* ---- Decoder shell and adaptive-bins head (f2): bf16, channels-last maps [B][H][W][pitch] - the token-major
+ * layout of the fusion path.
+ *
+ * cfp_conv_fwd: k x k convolution (k = 1, 3; stride 1, zero padding (k-1)/2) as an implicit GEMM on tcgen05:
+ *   out[b][y][x][out_coff + o] = act(sum_{taps, c} in[b][y+dy][x+dx][c] w[o][c][dy][dx] + shift[o]), act = LeakyReLU with
+ *   `leaky_slope` (1.0 = none).  Serves decoder.py:43-48 (conv3x3 + BatchNorm2d folded by the host + LeakyReLU, twice per
+ *   UpSampleBN), :70,76-80 (1x1 / 3x3 convs with bias) and DepthRegression.conv3x3 (:13).  cin: input channels, zero-padded to
+ *   a multiple of 16 (= the input's pitch); cout in {32, 64, 128, 256}; kchunk (multiple of 16, divides cin, cout * kchunk <=
+ *   20480): channels per staged K-chunk; w_tc: bf16 blocks [cin / kchunk][k * k][kchunk / 8][cout][8] (canonical K-major UMMA
+ *   layout per (chunk, tap)); shift [cout] fp32; out: bf16, pitch out_pitch (write into a slice of a wider buffer: torch.cat).
+ * cfp_upsample_concat: UpSampleBN's input (decoder.py:51-58): out [B][H][W][c_out] = [ bilinear(align_corners) resize of
+ *   lo [B][h][w][c_lo] (pitch lo_pitch) | skip [B][c_skip][H][W] (fp32 NCHW, the image encoder's feature) | zeros ].
+ * cfp_copy_channels: dst[row][coff : coff + C] = src[row][0 : C] (bf16, pitches in elements).
+ * cfp_head_bins: DepthRegression's regressor branch (decoder.py:24-36, norm 'linear') + the bin geometry of deltar.py:52-57:
+ *   per-frame channel mean of x [B][npix][pitch] (E channels) -> conv1x1 (wc [E][E], no bias) -> Linear(E, hidden) ->
+ *   LeakyReLU -> Linear(hidden, hidden) -> LeakyReLU -> Linear(hidden, n_bins) -> relu + 0.1 -> / sum -> edges [B][n_bins + 1]
+ *   = cumsum([min_val, (max_val - min_val) y]), centres [B][n_bins].  Weights fp32 row-major [out][in]; mean_scratch [B][E].
+ * cfp_head_expect: conv_out (1x1, E = 128 -> n_bins, bias) + softmax over the bins + sum_j p_j centre_j in one kernel:
+ *   x [B][npix][pitch] bf16 (the range-attention maps), w_tc = canonical UMMA block of the [n_bins][128] weight, pred
+ *   [B][npix] fp32; prob (nullable) [B][n_bins][npix] fp32 is the probability volume the reference returns in eval mode. */
+CFP_API int cfp_conv_fwd(const void *in, int B, int H, int W, int cin, int cout, int ksize, int kchunk, const void *w_tc,
+                         const float *shift, float leaky_slope, void *out, int out_pitch, int out_coff, void *stream);
+CFP_API int cfp_upsample_concat(const void *lo, int h, int w, int c_lo, int lo_pitch, const float *skip, int c_skip, void *out,
+                                int B, int H, int W, int c_out, void *stream);
+/* cfp_posenc_tokens_fwd for a caller that already holds the map channels-last (bf16, pitch x_pitch): tokens = x + pos crop. */
+CFP_API int cfp_posenc_tokens_nhwc_fwd(const void *x, int x_pitch, const float *pos, void *tokens, int B, int C, int H, int W,
+                                       int pos_h, int pos_w, int oy, int ox, void *stream);
+CFP_API int cfp_copy_channels(const void *src, int src_pitch, void *dst, int dst_pitch, int coff, int C, int64_t rows, void *stream);
+CFP_API int cfp_head_bins(const void *x, int pitch, int B, int npix, int E, const float *wc, const float *w0, const float *b0,
+                          const float *w2, const float *b2, const float *w4, const float *b4, int hidden, int n_bins, float min_val,
+                          float max_val, float *mean_scratch, float *edges, float *centres, void *stream);
+CFP_API int cfp_head_expect(const void *x, int pitch, int B, int npix, const void *w_tc, const float *bias, const float *centres,
+                            int n_bins, float *pred, float *prob, void *stream);
 
 /* ---- Input side (the reference runs these on the host CPU inside its dataloader, one frame at a time).
  *
