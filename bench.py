@@ -244,7 +244,13 @@ def workload_config(a, per_gpu_batch):
     return {"workload": "CFPNet combine1 fusion path (hist encoder + cross_atten3/2/1), 416x544, 8x8 zones of 48 px, "
                         f"{per_gpu_batch} frames per GPU, batch-sharded (BASELINE.json configs[2])",
             "layers": list(synth.COMBINE1_LAYERS), "per_gpu_batch": per_gpu_batch, "global_batch": per_gpu_batch * a.gpus,
-            "l2_policy": "inputs rotate over 3 distinct batches + workspace > 126 MB L2 between reuse"}
+            "l2_policy": "inputs rotate over 3 distinct batches + workspace > 126 MB L2 between reuse",
+            "launch_mode": "CUDA-graph replay per step (FusionPath.make_graphed; positional-encoding crops drawn per replay)"
+                           if os.environ.get("CFP_GRAPH", "1") != "0" else "eager launches",
+            "levels": "sequential (one stream)" if os.environ.get("CFP_SEQUENTIAL_LEVELS") else
+                      "the three levels on three streams (valid for the synthetic harness, whose level inputs are independent; "
+                      "inside the reference decoder the levels are serially dependent - see drop_in_sequential)",
+            "micro_batches": os.environ.get("CFP_MICRO", "default")}
 
 
 # ---------------------------------------------------------------------------------- product arm
@@ -288,9 +294,21 @@ def run_cfp(a):
         patch_info = inp["patch_info"]
     h2d = sum(v.numel() * v.element_size() for v in host_sets[0].values())
 
+    # CUDA-graph replay of the forward (one graph per rotating input set, the set's tensors are the captured inputs; the
+    # positional-encoding crops are drawn per replay and read from device memory): CFP_GRAPH=0 runs eager launches
+    use_graph = os.environ.get("CFP_GRAPH", "1") != "0"
+    graphs = []
+    if use_graph:
+        with torch.no_grad():
+            for d in dev_sets:
+                graphs.append(path.make_graphed(d["x3"], d["x2"], d["x1"], d["hist_data"], d["mask"], patch_info, copy_inputs=False))
+    launches_per_forward = [0]
+
     def step(i):
         d = dev_sets[i % NSETS]
         shard.seed_posenc(i)                # same positional-encoding crop on every rank
+        if use_graph:
+            return graphs[i % NSETS]()
         return path(d["x3"], d["x2"], d["x1"], d["hist_data"], d["mask"], patch_info)
 
     def barrier():
@@ -340,6 +358,11 @@ def run_cfp(a):
             barrier()
             step_ms = [(e0 if i == 0 else marks[i - 1]).elapsed_time(marks[i]) for i in range(a.steps)]
             launches = _lib.launch_count() - n0
+            if use_graph:                   # replays do not pass through the library's launch counter: one eager forward does
+                n1 = _lib.launch_count()
+                path(dev_sets[0]["x3"], dev_sets[0]["x2"], dev_sets[0]["x1"], dev_sets[0]["hist_data"], dev_sets[0]["mask"], patch_info)
+                torch.cuda.synchronize()
+                launches = (_lib.launch_count() - n1) * a.steps
             ms_total = max_over_ranks(e0.elapsed_time(e1))
             attempts.append(ms_total)
             ms1 = torch.cuda.memory_stats(dev)
@@ -353,6 +376,32 @@ def run_cfp(a):
             sampler.mark_end()
         clocks = sampler.finish() if sampler else None
 
+        # ---- the same K steps with the three levels on ONE stream: what a drop-in into the reference's decoder can use
+        # (there x_d2 depends on the fused x_d3, decoder.py:109-121, so the levels cannot overlap)
+        seq_ms = None
+        if path.concurrent_levels:
+            path.concurrent_levels = False
+            seq_graphs = []
+            if use_graph:
+                for d in dev_sets:
+                    seq_graphs.append(path.make_graphed(d["x3"], d["x2"], d["x1"], d["hist_data"], d["mask"], patch_info, copy_inputs=False))
+
+            def seq_step(i):
+                d = dev_sets[i % NSETS]
+                shard.seed_posenc(i)
+                return seq_graphs[i % NSETS]() if use_graph else path(d["x3"], d["x2"], d["x1"], d["hist_data"], d["mask"], patch_info)
+            for i in range(3):
+                seq_step(i)
+            barrier()
+            e0.record()
+            for i in range(a.steps):
+                seq_step(i)
+            e1.record()
+            barrier()
+            seq_ms = max_over_ranks(e0.elapsed_time(e1))
+            del seq_graphs
+            path.concurrent_levels = True
+
         # ---- end-to-end through the public host-buffer API ("e2e"): pinned host inputs in, pinned host
         # outputs back, every step; FusionPath.stream_host overlaps the copies of neighbouring steps
         # with compute on separate streams (each step still pays its own H2D + D2H).
@@ -360,7 +409,7 @@ def run_cfp(a):
             for i in range(n):
                 yield host_sets[i % NSETS]
 
-        for _ in path.stream_host(host_batches(max(a.warmup, 3)), patch_info, dev, seeds=range(2, 2 + max(a.warmup, 3))):
+        for _ in path.stream_host(host_batches(max(a.warmup, 3)), patch_info, dev, seeds=range(2, 2 + max(a.warmup, 3)), graph=use_graph):
             pass
         e2e_attempts = []
         for attempt in range(2):
@@ -368,7 +417,7 @@ def run_cfp(a):
             t_wall = time.perf_counter()
             e0.record()
             stamps = []
-            for _idx, _outs in path.stream_host(host_batches(a.steps), patch_info, dev, seeds=range(2, 2 + a.steps)):
+            for _idx, _outs in path.stream_host(host_batches(a.steps), patch_info, dev, seeds=range(2, 2 + a.steps), graph=use_graph):
                 stamps.append(time.perf_counter())
             e1.record()
             barrier()
@@ -401,8 +450,10 @@ def run_cfp(a):
             torch.cuda.synchronize()
             path.concurrent_levels = False      # one stream: the gap between events is one kernel's time
             _lib.profile_start()
-            for i in range(a.steps):
-                step(i)
+            for i in range(a.steps):            # eager launches (the profiler records an event per launch)
+                d = dev_sets[i % NSETS]
+                shard.seed_posenc(i)
+                path(d["x3"], d["x2"], d["x1"], d["hist_data"], d["mask"], patch_info)
             prof = _lib.profile_stop()
             path.concurrent_levels = not bool(os.environ.get("CFP_SEQUENTIAL_LEVELS"))
     if world > 1:
@@ -431,6 +482,9 @@ def run_cfp(a):
         "step_ms": {"min": min(step_ms), "median": statistics.median(step_ms), "max": max(step_ms)},
         "timed_attempts_ms": attempts, "e2e_attempts_ms": e2e_attempts, "allocator_in_timed_region": alloc_delta,
     }
+    if seq_ms:
+        line["drop_in_sequential"] = {"ms_per_step": seq_ms / a.steps, "value": frames / (seq_ms * 1e-3), "unit": "frames/s",
+                                      "note": "levels L3, L2, L1 on one stream, as inside the reference decoder (decoder.py:109-121)"}
     # whole-path roofline view (algorithmic bytes / dense flops per frame x measured frames/s)
     per_gpu_fps = value / world
     line["path"] = {"algorithmic_GBps": ELEMS_PER_FRAME * es * per_gpu_fps / 1e9,
@@ -459,6 +513,32 @@ LEVEL = {  # C: (N tokens, k, zone patch side p, window ws, inside Ni)
 }
 
 
+def _decoder_work():
+    """Per-frame, per-LAUNCH averages (useful flops, algorithmic bf16 bytes) of the decoder / head kernels at 416x544:
+    every conv of decoder.py:70-80 + DepthRegression.conv3x3 grouped by its output width (= the kernel instantiation)."""
+    px = {2: 208 * 272, 4: 104 * 136, 8: 52 * 68, 16: 26 * 34, 32: 13 * 17}
+    convs = [  # (pixels, cin, cout, taps)
+        (px[32], 232, 256, 1), (px[16], 392, 256, 9), (px[16], 256, 256, 9), (px[16], 256, 128, 1),
+        (px[8], 312, 128, 9), (px[8], 128, 128, 9), (px[8], 128, 64, 1),
+        (px[4], 168, 64, 9), (px[4], 64, 64, 9), (px[4], 64, 32, 1),
+        (px[2], 80, 32, 9), (px[2], 32, 32, 9), (px[2], 32, 128, 9), (px[2], 128, 128, 9)]
+    work = {}
+    for cout in (256, 128, 64, 32):
+        sel = [c for c in convs if c[2] == cout]
+        work[f"conv_gen_tc<{cout}>"] = (sum(2.0 * p * ci * co * t for p, ci, co, t in sel) / len(sel),
+                                        sum(2.0 * p * (ci + co) for p, ci, co, t in sel) / len(sel))
+    ups = [(px[32], 232, 0), (px[16], 392, 256), (px[8], 312, 256), (px[4], 168, 128), (px[2], 80, 64)]
+    work["upsample_concat"] = (0.0, sum(2.0 * p * c + 2.0 * (p // 4) * lo for p, c, lo in ups) / len(ups))
+    work["head_expect_tc<256>"] = (2.0 * px[2] * 128 * 256, 2.0 * px[2] * 128 + 4.0 * px[2])
+    work["channel_mean"] = (0.0, 2.0 * px[2] * 128)
+    work["copy_channels"] = (0.0, sum(4.0 * p * c for p, c in ((px[16], 128), (px[8], 64), (px[4], 32))) / 3)
+    work["posenc_tokens_nhwc"] = work["copy_channels"]
+    return work
+
+
+DECODER_WORK = _decoder_work()
+
+
 def kernel_work(name, B, es):
     import re
     # kernels launched once per level under one name: average per launch over the levels that use them
@@ -468,6 +548,9 @@ def kernel_work(name, B, es):
         return dict(flops=0.0, bytes=sum(2.0 * LEVEL[C]["N"] * C * es * B for C in (32, 64)) / 2, bound="hbm")
     if name.startswith("hist_encoder"):  # 1024 samples per frame: 4 B in, (32+64+128) elements out; 109 MFLOP per frame
         return dict(flops=109e6 * B, bytes=1024.0 * B * (4 + 224 * es), bound="tensor" if name.endswith("_tc") else "fma")
+    if name in DECODER_WORK:
+        f, by = DECODER_WORK[name]
+        return dict(flops=f * B, bytes=by * B * es / 2.0, bound="tensor" if f > 0 else "hbm")
     m = re.search(r"(\d+)>$", name)
     if not m:
         return None
@@ -869,6 +952,134 @@ def run_train(a):
 
 
 
+# ---------------------------------------------------------------------------------- decoder + fusion + head
+def run_tail(a):
+    """--workload tail_b16: everything of the reference model below the third-party image encoder - histogram encoder,
+    Decoder (UpSampleBN blocks, 1x1 convs, the three TransformerFusion calls in their true serial order) and the
+    adaptive-bins head - as libcfp kernels, bf16, channels-last: five encoder feature maps + zone histograms in, depth out.
+    `value`: frames/s with the inputs resident in HBM; `e2e`: inputs from pinned host memory, depth maps read back."""
+    import cfpnet_b200
+    from cfpnet_b200 import _lib, decoder as D, shard
+    from cfpnet_b200.build import build
+    from cfpnet_b200.config import args as cargs
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the path has no CPU fallback")
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    build()
+    B = a.batch
+    cargs.attention_layer = list(synth.COMBINE1_LAYERS)
+    with open(os.path.join(ROOT, "tests", "golden", "depth_tail_keys.json")) as fh:
+        sd = synth.synthetic_state_dict(json.load(fh), seed=11)
+    dec = D.Decoder(num_classes=128)
+    dec.load_state_dict({k[len("decoder."):]: v for k, v in sd.items() if k.startswith("decoder.")}, strict=True)
+    dec = dec.to(dev).eval()
+    for m in (dec.cross_atten1, dec.cross_atten2, dec.cross_atten3):
+        m.to(torch.bfloat16)
+    head = D.DepthHead(n_bins=256, min_val=1e-3, max_val=10.0)
+    head.load_state_dict({k: v for k, v in sd.items() if k.startswith(("depth_head.", "conv_out."))}, strict=True)
+    head = head.to(dev).eval()
+    enc = cfpnet_b200.HistogramEncoder()
+    enc.load_state_dict({k[len("hist_encoder."):]: v for k, v in sd.items() if k.startswith("hist_encoder.")}, strict=True)
+    enc = enc.to(dev).eval()
+    enc.out_dtype = torch.bfloat16
+    NSETS = 3
+    host_sets, dev_sets = [], []
+    for s_ in range(NSETS):
+        inp = synth.make_inputs(GEOMETRY, B, seed=200 + s_, levels=())
+        h = {f"f{i}": t.contiguous().pin_memory() for i, t in enumerate(synth.encoder_features(GEOMETRY, B, seed=200 + s_))}
+        h["hist_data"] = inp["hist_data"].pin_memory()
+        h["mask"] = inp["mask"].pin_memory()
+        host_sets.append(h)
+        dev_sets.append({k: v.to(dev) for k, v in h.items()})
+    patch_info = inp["patch_info"]
+    h2d = sum(v.numel() * v.element_size() for v in host_sets[0].values())
+
+    def step(d, i):
+        shard.seed_posenc(i)
+        hist = enc(d["hist_data"].unsqueeze(-1))
+        unet, H, W = dec.forward_nhwc([d[f"f{j}"] for j in range(5)], hist, rect_data=None, mask=d["mask"], patch_info=patch_info, rgb=None)
+        return head.forward_nhwc(unet, H, W)
+
+    sampler = ClockSampler(0) if not os.environ.get("CFP_BENCH_NO_SAMPLER") else None
+    if sampler:
+        sampler.start()
+    with torch.no_grad():
+        for i in range(max(a.warmup, 3)):
+            edges, pred = step(dev_sets[i % NSETS], i)
+        torch.cuda.synchronize()
+        d2h = pred.numel() * pred.element_size() + edges.numel() * edges.element_size()
+        if sampler:
+            t_s = time.perf_counter()
+            while not sampler.samples and sampler.is_alive() and time.perf_counter() - t_s < 5.0:
+                time.sleep(0.05)
+            sampler.mark_begin()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = _lib.launch_count()
+        e0.record()
+        for i in range(a.steps):
+            step(dev_sets[i % NSETS], i)
+            if sampler and i == a.steps // 2:
+                sampler.sample_now()
+        e1.record()
+        torch.cuda.synchronize()
+        launches = _lib.launch_count() - n0
+        ms_total = e0.elapsed_time(e1)
+        if sampler:
+            sampler.mark_end()
+        clocks = sampler.finish() if sampler else None
+        # end to end: inputs copied from pinned host memory on a side stream one step ahead, depth read back
+        side = torch.cuda.Stream(dev)
+        pred_host = torch.empty(pred.shape, dtype=pred.dtype).pin_memory()
+        edges_host = torch.empty(edges.shape, dtype=edges.dtype).pin_memory()
+
+        def e2e_run(n):
+            cur = torch.cuda.current_stream()
+            staged = None
+            for i in range(n + 1):
+                nxt = None
+                if i < n:
+                    with torch.cuda.stream(side):
+                        nxt = {k: v.to(dev, non_blocking=True) for k, v in host_sets[i % NSETS].items()}
+                        ev = torch.cuda.Event()
+                        ev.record(side)
+                if staged is not None:
+                    cur.wait_event(staged[1])
+                    ed, pr = step(staged[0], i)
+                    pred_host.copy_(pr, non_blocking=True)
+                    edges_host.copy_(ed, non_blocking=True)
+                    for t in staged[0].values():
+                        t.record_stream(cur)
+                staged = (nxt, ev) if nxt is not None else None
+            torch.cuda.synchronize()
+
+        e2e_run(3)
+        t_wall = time.perf_counter()
+        e0.record()
+        e2e_run(a.steps)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_e2e = max(e0.elapsed_time(e1), (time.perf_counter() - t_wall) * 1e3)
+        _lib.profile_start()
+        for i in range(a.steps):
+            step(dev_sets[i % NSETS], i)
+        prof = _lib.profile_stop()
+    peaks = load_peaks()
+    frames = B * a.steps
+    line = {"metric": "CFPNet below the image encoder (hist encoder + decoder + fusion + adaptive-bins head) frames/s @416x544, 8x8 zones",
+            "value": frames / (ms_total * 1e-3), "unit": "frames/s", "n_gpus": 1, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": "histogram encoder + Decoder (UpSampleBN x4, 1x1 convs, cross_atten3/2/1 in their serial order) + "
+                                   f"DepthRegression / conv_out head, combine1 layer list, 416x544, {B} frames, 1 GPU (SURVEY.md 8 f1 / f2 "
+                                   "around the hot path); the image encoder's five feature maps are synthetic inputs",
+                       "per_gpu_batch": B, "l2_policy": "inputs rotate over 3 distinct batches; a step's activations exceed the 126 MB L2"},
+            "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches), "clocks": clocks}
+    line["roofline"], line["kernels"] = roofline_from_profile(prof, a.steps, B, 2, peaks)
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -878,11 +1089,16 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="frames per GPU per step (default 64; train_b32: 32)")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--workload", default="combine1_b64", choices=["combine1_b64", "baseline_b16", "latency_480", "train_b32"],
+    ap.add_argument("--workload", default="combine1_b64", choices=["combine1_b64", "baseline_b16", "latency_480", "train_b32", "tail_b16"],
                     help="combine1_b64 = the headline (BASELINE.json configs[2]); the other two are side configurations")
     a = ap.parse_args()
     if a.batch is None:
-        a.batch = 32 if a.workload == "train_b32" else 64
+        a.batch = {"train_b32": 32, "tail_b16": 16}.get(a.workload, 64)
+    if a.workload == "tail_b16":
+        if a.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "--impl reference serves the headline workload"}))
+            return None
+        return run_tail(a)
     if a.workload == "train_b32":
         if a.impl == "reference":
             print(json.dumps({"impl": "reference", "unavailable": "the training-step workload has no CPU arm; --impl reference "

@@ -86,6 +86,7 @@ SIGNATURES = {
     "cfp_tr_adamw": (_i, [_p, _p, _p, _p, _i64, _p, _p, _i] + [C.c_float] * 4 + [_i, C.c_float, _p, C.c_float, _p]),
     "cfp_conv_fwd": (_i, [_p] + [_i] * 7 + [_p, _p, C.c_float, _p, _i, _i, _p]),
     "cfp_upsample_concat": (_i, [_p, _i, _i, _i, _i, _p, _i, _p, _i, _i, _i, _i, _p]),
+    "cfp_posenc_tokens_crop_fwd": (_i, [_p, _p, _p] + [_i] * 6 + [_p, _i, _p]),
     "cfp_posenc_tokens_nhwc_fwd": (_i, [_p, _i, _p, _p] + [_i] * 8 + [_p]),
     "cfp_copy_channels": (_i, [_p, _i, _p, _i, _i, _i, _i64, _p]),
     "cfp_head_bins": (_i, [_p, _i, _i, _i, _i] + [_p] * 7 + [_i, _i, C.c_float, C.c_float, _p, _p, _p, _p]),

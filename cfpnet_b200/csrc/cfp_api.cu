@@ -251,6 +251,16 @@ CFP_API int cfp_posenc_tokens_fwd(const void* x_nchw, const float* pos, void* to
     return posenc_tokens(x_nchw, pos, tokens, B, C, H, W, pos_w, oy, ox, dtype, (cudaStream_t)stream);
 }
 
+CFP_API int cfp_posenc_tokens_crop_fwd(const void* x_nchw, const float* pos, void* tokens, int B, int C, int H, int W, int pos_h,
+                                       int pos_w, const int* crop, int dtype, void* stream) {
+    begin_call(stream);
+    CFP_REQUIRE(x_nchw && pos && tokens && crop, "null pointer");
+    CFP_REQUIRE(B > 0 && B <= 65535 && C > 0 && H > 0 && W > 0, "bad shape");
+    CFP_REQUIRE(W <= pos_w && H <= pos_h, "feature map %dx%d larger than the %dx%d positional-encoding table", H, W, pos_h, pos_w);
+    CFP_REQUIRE(dtype == CFP_F32 || dtype == CFP_BF16, "unsupported dtype %d", dtype);
+    return posenc_tokens(x_nchw, pos, tokens, B, C, H, W, pos_w, 0, 0, dtype, (cudaStream_t)stream, crop);
+}
+
 CFP_API int cfp_tokens_to_nchw(const void* tokens, void* out_nchw, int B, int C, int H, int W, int dtype, void* stream) {
     begin_call(stream);
     CFP_REQUIRE(tokens && out_nchw, "null pointer");

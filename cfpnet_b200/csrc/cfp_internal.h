@@ -23,7 +23,7 @@ inline size_t elem_size(int dtype) { return dtype == CFP_F32 ? 4 : 2; }
 
 // k_layout.cu
 int posenc_tokens(const void* x, const float* pos, void* tokens, int B, int C, int H, int W, int pos_w,
-                  int oy, int ox, int dtype, cudaStream_t st);
+                  int oy, int ox, int dtype, cudaStream_t st, const int* crop = nullptr);
 int tokens_to_nchw(const void* tokens, void* out, int B, int C, int H, int W, int dtype, cudaStream_t st);
 int zone_masks(const uint8_t* mask, uint8_t* zm, uint8_t* hm, uint8_t* pm, int B, int H, int W,
                const cfp_geom& g, cudaStream_t st);

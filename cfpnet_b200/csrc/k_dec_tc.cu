@@ -227,21 +227,24 @@ int conv_gen_tc(const void* in, int cin, int kc, int taps, const void* wpk, cons
 // ------------------------------------------------------------------------------------------------ upsample + concat
 // out[b][y][x][:] = [ bilinear_align_corners(lo [B][h][w][c_lo] (pitch lo_pitch))(y, x) | skip [B][c_skip][H][W] (fp32, NCHW: the
 // image encoder's layout) | zeros up to c_out ]      (decoder.py:51-58; F.interpolate index arithmetic as in k_io.cu)
-// thread = (pixel, 8-channel group); consecutive threads take consecutive pixels, so the NCHW reads of the skip feature
-// are coalesced.
+// Two thread -> element maps in one launch: the resized part walks (pixel, 8-channel group) with the GROUP fastest - a warp reads
+// and writes whole contiguous runs of a pixel's channels; the skip part walks it with the PIXEL fastest, so its NCHW fp32
+// reads are coalesced along x (its 16-byte channels-last stores are the strided side).
 __global__ void __launch_bounds__(256) upsample_concat_kernel(const bf16* __restrict__ lo, int h, int w, int c_lo, int lo_pitch,
                                                               const float* __restrict__ skip, int c_skip, bf16* __restrict__ out, int B,
                                                               int H, int W, int c_out) {
     pdl_wait();
-    const int groups = c_out / 8;
-    const int64_t npix = (int64_t)B * H * W, total = npix * groups;
+    const int g_lo = c_lo / 8, g_rest = (c_out - c_lo) / 8;
+    const int64_t npix = (int64_t)B * H * W, n_lo = npix * g_lo, total = n_lo + npix * g_rest;
     const float sy = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f, sx = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t pix = i % npix;
-        const int g = (int)(i / npix), c0 = g * 8;
-        const int x = (int)(pix % W), y = (int)((pix / W) % H), b = (int)(pix / ((int64_t)W * H));
         float v[8];
-        if (c0 + 8 <= c_lo) {
+        int64_t pix;
+        int c0;
+        if (i < n_lo) {
+            pix = i / g_lo;
+            c0 = (int)(i - pix * g_lo) * 8;
+            const int x = (int)(pix % W), y = (int)((pix / W) % H), b = (int)(pix / ((int64_t)W * H));
             const float fy = sy * y, fx = sx * x;
             int y0 = (int)fy, x0i = (int)fx;
             if (y0 > h - 1) y0 = h - 1;
@@ -263,10 +266,14 @@ __global__ void __launch_bounds__(256) upsample_concat_kernel(const bf16* __rest
                                w10 * __uint_as_float(cq[k] & 0xffff0000u) + w11 * __uint_as_float(d[k] & 0xffff0000u);
             }
         } else {
+            const int64_t j = i - n_lo;
+            pix = j % npix;
+            c0 = c_lo + (int)(j / npix) * 8;
+            const int x = (int)(pix % W), y = (int)((pix / W) % H), b = (int)(pix / ((int64_t)W * H));
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const int c = c0 + k - c_lo;
-                v[k] = (c >= 0 && c < c_skip) ? skip[(((size_t)b * c_skip + c) * H + y) * W + x] : 0.f;
+                v[k] = c < c_skip ? skip[(((size_t)b * c_skip + c) * H + y) * W + x] : 0.f;
             }
         }
         uint4 u;
@@ -389,10 +396,10 @@ int channel_mean(const void* x, int pitch, int C, int B, int npix, float* mean, 
 }
 
 // ------------------------------------------------------------------------------------------------ head: bin regressor
-// One CTA per frame (decoder.py:24-36 with norm = 'linear', deltar.py:52-57): v = Wc mean, h1 = lrelu(W0 v + b0),
+// One CTA of 32 warps per frame (tiny, latency-bound: every warp keeps a weight row's loads in flight) (decoder.py:24-36 with norm = 'linear', deltar.py:52-57): v = Wc mean, h1 = lrelu(W0 v + b0),
 // h2 = lrelu(W2 h1 + b2), y = relu(W4 h2 + b4) + 0.1, y /= sum(y), widths = (max - min) y, edges = cumsum([min, widths]),
 // centres = (edges[:-1] + edges[1:]) / 2.  Weights row-major [out][in] fp32 as nn.Linear / the squeezed conv keep them.
-__global__ void __launch_bounds__(256) head_regressor_kernel(const float* __restrict__ mean, const float* __restrict__ wc,
+__global__ void __launch_bounds__(1024) head_regressor_kernel(const float* __restrict__ mean, const float* __restrict__ wc,
                                                              const float* __restrict__ w0, const float* __restrict__ b0,
                                                              const float* __restrict__ w2, const float* __restrict__ b2,
                                                              const float* __restrict__ w4, const float* __restrict__ b4, int E, int Hd,
@@ -401,16 +408,21 @@ __global__ void __launch_bounds__(256) head_regressor_kernel(const float* __rest
     extern __shared__ float rs[];                        // [E] mean | [E] v | [Hd] h1 | [Hd] h2 | [nb] y | [nb + 1] edges
     float* m = rs; float* v = m + E; float* h1 = v + E; float* h2 = h1 + Hd; float* y = h2 + Hd; float* ed = y + nb;
     const int b = blockIdx.x;
-    for (int i = threadIdx.x; i < E; i += 256) m[i] = mean[(size_t)b * E + i];
+    for (int i = threadIdx.x; i < E; i += blockDim.x) m[i] = mean[(size_t)b * E + i];
     __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     auto dense = [&](const float* W, const float* bias, const float* xin, float* out, int n_out, int n_in, int act) {
-        for (int o = threadIdx.x; o < n_out; o += 256) {
-            float s = bias ? bias[o] : 0.f;
+        for (int o = wid; o < n_out; o += nwarp) {           // a warp per output: the weight row is read in coalesced segments
             const float* wr = W + (size_t)o * n_in;
-            for (int k = 0; k < n_in; ++k) s = fmaf(wr[k], xin[k], s);
-            if (act == 1) s = s > 0.f ? s : 0.01f * s;              // nn.LeakyReLU() default slope
-            if (act == 2) s = fmaxf(s, 0.f) + 0.1f;
-            out[o] = s;
+            float s = 0.f;
+            for (int k = lane; k < n_in; k += 32) s = fmaf(wr[k], xin[k], s);
+            s = warp_sum(s);
+            if (lane == 0) {
+                if (bias) s += bias[o];
+                if (act == 1) s = s > 0.f ? s : 0.01f * s;          // nn.LeakyReLU() default slope
+                if (act == 2) s = fmaxf(s, 0.f) + 0.1f;
+                out[o] = s;
+            }
         }
         __syncthreads();
     };
@@ -426,8 +438,8 @@ __global__ void __launch_bounds__(256) head_regressor_kernel(const float* __rest
         for (int i = 0; i < nb; ++i) { e += (max_val - min_val) * (y[i] / s); ed[i + 1] = e; }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i <= nb; i += 256) edges[(size_t)b * (nb + 1) + i] = ed[i];
-    for (int i = threadIdx.x; i < nb; i += 256) centres[(size_t)b * nb + i] = 0.5f * (ed[i] + ed[i + 1]);
+    for (int i = threadIdx.x; i <= nb; i += blockDim.x) edges[(size_t)b * (nb + 1) + i] = ed[i];
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) centres[(size_t)b * nb + i] = 0.5f * (ed[i] + ed[i + 1]);
 }
 int head_regressor(const float* mean, const float* wc, const float* w0, const float* b0, const float* w2, const float* b2, const float* w4,
                    const float* b4, int B, int E, int Hd, int nb, float min_val, float max_val, float* edges, float* centres,
@@ -435,7 +447,7 @@ int head_regressor(const float* mean, const float* wc, const float* w0, const fl
     CFP_REQUIRE(B > 0 && E > 0 && Hd > 0 && nb > 0, "head_regressor: bad shape");
     const size_t smem = (size_t)(2 * E + 2 * Hd + 2 * nb + 1) * sizeof(float);
     CFP_REQUIRE(smem <= 48 * 1024, "head_regressor: %zu B of shared memory", smem);
-    head_regressor_kernel<<<B, 256, smem, st>>>(mean, wc, w0, b0, w2, b2, w4, b4, E, Hd, nb, min_val, max_val, edges, centres);
+    head_regressor_kernel<<<B, 1024, smem, st>>>(mean, wc, w0, b0, w2, b2, w4, b4, E, Hd, nb, min_val, max_val, edges, centres);
     return check_launch("head_regressor");
 }
 
@@ -489,26 +501,23 @@ __global__ void __launch_bounds__(192) head_expect_tc_kernel(const bf16* __restr
             umma::fence_after_sync();
             const int fr = (int)((row < rows ? row : 0) / npix);
             const float* cen = centres + (size_t)fr * NB;
-            float mx = -3.0e38f;
-#pragma unroll 1
-            for (int c0 = 0; c0 < NB; c0 += 16) {
-                float v[16];
-                umma::tmem_ld16(umma::tmem_addr(tmem, warp * 32, c0), v);
+            // one walk over the logits (pipelined TMEM loads), online softmax: running maximum, sums rescaled per 16-bin piece
+            float mx = -3.0e38f, se = 0.f, sc = 0.f;
+            umma::tmem_for_each16<NB>(umma::tmem_addr(tmem, warp * 32, 0), [&](int c0, const float (&t)[16]) {
+                float l[16], cm = -3.0e38f;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) mx = fmaxf(mx, v[j] + __ldg(bias + c0 + j));
-            }
-            float se = 0.f, sc = 0.f;
-#pragma unroll 1
-            for (int c0 = 0; c0 < NB; c0 += 16) {
-                float v[16];
-                umma::tmem_ld16(umma::tmem_addr(tmem, warp * 32, c0), v);
+                for (int j = 0; j < 16; ++j) { l[j] = t[j] + __ldg(bias + c0 + j); cm = fmaxf(cm, l[j]); }
+                if (cm > mx) {
+                    const float r = __expf(mx - cm);
+                    se *= r; sc *= r; mx = cm;
+                }
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    const float e = __expf(v[j] + __ldg(bias + c0 + j) - mx);
+                    const float e = __expf(l[j] - mx);
                     se += e;
                     sc = fmaf(e, __ldg(cen + c0 + j), sc);
                 }
-            }
+            });
             if (row < rows) pred[row] = sc / se;
             if (prob) {
                 const float inv = 1.f / se;

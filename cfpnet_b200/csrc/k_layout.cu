@@ -13,8 +13,9 @@ namespace cfp {
 template <typename T, bool kToTokens>
 __global__ void __launch_bounds__(256) layout_kernel(const T* __restrict__ src, const float* __restrict__ pos,
                                                      T* __restrict__ dst, int C, int H, int W, int pos_w,
-                                                     int oy, int ox) {
+                                                     int oy, int ox, const int* __restrict__ crop) {
     __shared__ float tile[32][33];
+    if (crop) { oy = crop[0]; ox = crop[1]; }
     const int N = H * W;
     const int b = blockIdx.z;
     const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -54,8 +55,10 @@ __global__ void __launch_bounds__(256) layout_kernel(const T* __restrict__ src, 
 // the NCHW side, two channels of one token on the token side).  Requires H*W and C even.
 template <bool kToTokens>
 __global__ void __launch_bounds__(256) layout_bf16_kernel(const bf16* __restrict__ src_, const float* __restrict__ pos,
-                                                          bf16* __restrict__ dst_, int C, int H, int W, int pos_w, int oy, int ox) {
+                                                          bf16* __restrict__ dst_, int C, int H, int W, int pos_w, int oy, int ox,
+                                                          const int* __restrict__ crop) {
     __shared__ uint16_t tile[64][66];                        // [channel][token]
+    if (crop) { oy = crop[0]; ox = crop[1]; }
     const int b = blockIdx.z, n0 = blockIdx.x * 64, c0 = blockIdx.y * 64, N = H * W;
     const uint16_t* src = reinterpret_cast<const uint16_t*>(src_);
     uint16_t* dst = reinterpret_cast<uint16_t*>(dst_);
@@ -106,7 +109,8 @@ __global__ void __launch_bounds__(256) layout_bf16_kernel(const bf16* __restrict
 // 4-byte row accesses 2-way.  Requires H*W % 8 == 0 (16-byte aligned channel rows) and C % TC == 0.
 template <bool kToTokens, int TC>
 __global__ void __launch_bounds__(256) layout_bf16_v8_kernel(const bf16* __restrict__ src_, const float* __restrict__ pos,
-                                                             bf16* __restrict__ dst_, int C, int H, int W, int pos_w, int oy, int ox) {
+                                                             bf16* __restrict__ dst_, int C, int H, int W, int pos_w, int oy, int ox,
+                                                             const int* __restrict__ crop) {
     constexpr int TN = 4096 / TC, LD = TN + 2;               // halfwords per tile row (odd word count)
     constexpr int NCH = TN / 8, CG = TC / 8;                 // 16-byte chunks per channel row / per token
     __shared__ __align__(4) uint16_t tile[TC * LD];
@@ -115,6 +119,7 @@ __global__ void __launch_bounds__(256) layout_bf16_v8_kernel(const bf16* __restr
     uint16_t* dst = reinterpret_cast<uint16_t*>(dst_);
     pdl_trigger();                         // short, bandwidth-bound kernel: the next one may queue up behind it at once
     pdl_wait();
+    if (crop) { oy = crop[0]; ox = crop[1]; }  // crop offsets from device memory (CUDA-graph replays: nothing random is frozen)
     if (kToTokens) {
 #pragma unroll
         for (int i = threadIdx.x; i < TC * NCH; i += 256) {  // NCHW side: (channel, 8 tokens)
@@ -173,48 +178,48 @@ __global__ void __launch_bounds__(256) layout_bf16_v8_kernel(const bf16* __restr
 
 template <bool kToTokens, int TC>
 static void launch_v8(const void* src, const float* pos, void* dst, int B, int C, int H, int W, int pos_w, int oy, int ox,
-                      cudaStream_t st) {
+                      const int* crop, cudaStream_t st) {
     dim3 grid((H * W + 4096 / TC - 1) / (4096 / TC), C / TC, B);
-    launch_pdl(layout_bf16_v8_kernel<kToTokens, TC>, grid, 256, 0, st, (const bf16*)src, pos, (bf16*)dst, C, H, W, pos_w, oy, ox);
+    launch_pdl(layout_bf16_v8_kernel<kToTokens, TC>, grid, 256, 0, st, (const bf16*)src, pos, (bf16*)dst, C, H, W, pos_w, oy, ox, crop);
 }
 
 template <typename T>
 static int launch_layout(bool to_tokens, const void* src, const float* pos, void* dst, int B, int C, int H,
-                         int W, int pos_w, int oy, int ox, cudaStream_t st) {
+                         int W, int pos_w, int oy, int ox, const int* crop, cudaStream_t st) {
     if (sizeof(T) == 2 && (H * W) % 8 == 0 && C % 32 == 0 && (((uintptr_t)src | (uintptr_t)dst | (uintptr_t)pos) & 15) == 0) {
         if (C % 64 == 0) {
-            if (to_tokens) launch_v8<true, 64>(src, pos, dst, B, C, H, W, pos_w, oy, ox, st);
-            else launch_v8<false, 64>(src, pos, dst, B, C, H, W, pos_w, oy, ox, st);
+            if (to_tokens) launch_v8<true, 64>(src, pos, dst, B, C, H, W, pos_w, oy, ox, crop, st);
+            else launch_v8<false, 64>(src, pos, dst, B, C, H, W, pos_w, oy, ox, crop, st);
         } else {
-            if (to_tokens) launch_v8<true, 32>(src, pos, dst, B, C, H, W, pos_w, oy, ox, st);
-            else launch_v8<false, 32>(src, pos, dst, B, C, H, W, pos_w, oy, ox, st);
+            if (to_tokens) launch_v8<true, 32>(src, pos, dst, B, C, H, W, pos_w, oy, ox, crop, st);
+            else launch_v8<false, 32>(src, pos, dst, B, C, H, W, pos_w, oy, ox, crop, st);
         }
         return check_launch("layout_kernel");
     }
     if (sizeof(T) == 2 && (H * W) % 2 == 0 && C % 2 == 0) {
         dim3 grid64((H * W + 63) / 64, (C + 63) / 64, B);
         if (to_tokens)
-            layout_bf16_kernel<true><<<grid64, 256, 0, st>>>((const bf16*)src, pos, (bf16*)dst, C, H, W, pos_w, oy, ox);
+            layout_bf16_kernel<true><<<grid64, 256, 0, st>>>((const bf16*)src, pos, (bf16*)dst, C, H, W, pos_w, oy, ox, crop);
         else
-            layout_bf16_kernel<false><<<grid64, 256, 0, st>>>((const bf16*)src, pos, (bf16*)dst, C, H, W, pos_w, oy, ox);
+            layout_bf16_kernel<false><<<grid64, 256, 0, st>>>((const bf16*)src, pos, (bf16*)dst, C, H, W, pos_w, oy, ox, crop);
         return check_launch("layout_kernel");
     }
     dim3 grid((H * W + 31) / 32, (C + 31) / 32, B);
     if (to_tokens)
-        layout_kernel<T, true><<<grid, 256, 0, st>>>((const T*)src, pos, (T*)dst, C, H, W, pos_w, oy, ox);
+        layout_kernel<T, true><<<grid, 256, 0, st>>>((const T*)src, pos, (T*)dst, C, H, W, pos_w, oy, ox, crop);
     else
-        layout_kernel<T, false><<<grid, 256, 0, st>>>((const T*)src, pos, (T*)dst, C, H, W, pos_w, oy, ox);
+        layout_kernel<T, false><<<grid, 256, 0, st>>>((const T*)src, pos, (T*)dst, C, H, W, pos_w, oy, ox, crop);
     return check_launch("layout_kernel");
 }
 
 int posenc_tokens(const void* x, const float* pos, void* tokens, int B, int C, int H, int W, int pos_w,
-                  int oy, int ox, int dtype, cudaStream_t st) {
-    return dtype == CFP_F32 ? launch_layout<float>(true, x, pos, tokens, B, C, H, W, pos_w, oy, ox, st)
-                            : launch_layout<bf16>(true, x, pos, tokens, B, C, H, W, pos_w, oy, ox, st);
+                  int oy, int ox, int dtype, cudaStream_t st, const int* crop) {
+    return dtype == CFP_F32 ? launch_layout<float>(true, x, pos, tokens, B, C, H, W, pos_w, oy, ox, crop, st)
+                            : launch_layout<bf16>(true, x, pos, tokens, B, C, H, W, pos_w, oy, ox, crop, st);
 }
 int tokens_to_nchw(const void* tokens, void* out, int B, int C, int H, int W, int dtype, cudaStream_t st) {
-    return dtype == CFP_F32 ? launch_layout<float>(false, tokens, nullptr, out, B, C, H, W, 0, 0, 0, st)
-                            : launch_layout<bf16>(false, tokens, nullptr, out, B, C, H, W, 0, 0, 0, st);
+    return dtype == CFP_F32 ? launch_layout<float>(false, tokens, nullptr, out, B, C, H, W, 0, 0, 0, nullptr, st)
+                            : launch_layout<bf16>(false, tokens, nullptr, out, B, C, H, W, 0, 0, 0, nullptr, st);
 }
 
 // ---------------------------------------------------------------- masks

@@ -99,6 +99,18 @@ class TransformerFusion(nn.Module):
         return packed, base + pos, base + pos2, buf
 
 
+    def draw_crop(self, H: int, W: int):
+        """(oy, ox) of the positional-encoding crop: the reference's draws from torch's global CPU generator, in its
+        order (fusion.py:87-91); nothing is drawn along an axis the map fills."""
+        if H > self.max_resolution[0] or W > self.max_resolution[1]:
+            raise ValueError("feature map larger than the positional-encoding table")
+        oy = ox = 0
+        if H < self.max_resolution[0]:
+            oy = int(torch.randint(0, self.max_resolution[0] - H + 1, [1]))
+        if W < self.max_resolution[1]:
+            ox = int(torch.randint(0, self.max_resolution[1] - W + 1, [1]))
+        return oy, ox
+
     def _run_layers(self, packed, pos2, feat0, feat1, mask, B, H, W, D, S, cg, work, ws_bytes, code, st, emb_copy):
         """The layer list on the token-major map ``feat0`` [B, H*W, D] (in place), current stream."""
         emb = feat0.clone() if emb_copy else feat0           # fusion.py:134-136: canvas cut from the first map
@@ -135,13 +147,7 @@ class TransformerFusion(nn.Module):
             raise ValueError(f"feat1 carries {S} samples per zone, positional_encodings2 has {self.positional_encodings2.shape[0]}")
         if tuple(kwargs["mask"].shape) != (B, g.zone_num ** 2):
             raise ValueError(f"mask {tuple(kwargs['mask'].shape)} is not [B={B}, zones={g.zone_num ** 2}]")
-        oy = ox = 0
-        if H < self.max_resolution[0]:
-            oy = int(torch.randint(0, self.max_resolution[0] - H + 1, [1]))
-        if W < self.max_resolution[1]:
-            ox = int(torch.randint(0, self.max_resolution[1] - W + 1, [1]))
-        if H > self.max_resolution[0] or W > self.max_resolution[1]:
-            raise ValueError("feature map larger than the positional-encoding table")
+        oy, ox = self.draw_crop(H, W)
         packed, pos, pos2, _buf = self._cache.get(self, self._pack)
         dev = x_tok.device
         dt = torch.bfloat16
@@ -190,14 +196,10 @@ class TransformerFusion(nn.Module):
                                "that requires grad would have its gradient cut silently; call under torch.no_grad() or "
                                "detach the inputs")
 
-        # positional-encoding crop: same draws, same order as fusion.py:87-91
-        oy = ox = 0
-        if H < self.max_resolution[0]:
-            oy = int(torch.randint(0, self.max_resolution[0] - H + 1, [1]))
-        if W < self.max_resolution[1]:
-            ox = int(torch.randint(0, self.max_resolution[1] - W + 1, [1]))
-        if H > self.max_resolution[0] or W > self.max_resolution[1]:
-            raise ValueError("feature map larger than the positional-encoding table")
+        # positional-encoding crop: same draws, same order as fusion.py:87-91 (under a CUDA-graph capture the offsets
+        # live in device memory and the replay wrapper makes the draws: FusionPath.make_graphed)
+        crop_dev = self.__dict__.get("_crop_dev")
+        oy, ox = (0, 0) if crop_dev is not None else self.draw_crop(H, W)
 
         packed, pos, pos2, _buf = self._cache.get(self, self._pack)
         dev = x.device
@@ -227,8 +229,12 @@ class TransformerFusion(nn.Module):
                          torch.empty(Bp, H * W, D, device=dev, dtype=dt)))
             st = _lib.stream_ptr()
             xp, f1p, mp, op = x[b0:b1], feat1[b0:b1], mask[b0:b1], out[b0:b1]
-            _lib.call("cfp_posenc_tokens_fwd", xp.data_ptr(), pos, feat0.data_ptr(), Bp, D, H, W,
-                      self.max_resolution[0], self.max_resolution[1], oy, ox, code, st)
+            if crop_dev is not None:
+                _lib.call("cfp_posenc_tokens_crop_fwd", xp.data_ptr(), pos, feat0.data_ptr(), Bp, D, H, W,
+                          self.max_resolution[0], self.max_resolution[1], crop_dev.data_ptr(), code, st)
+            else:
+                _lib.call("cfp_posenc_tokens_fwd", xp.data_ptr(), pos, feat0.data_ptr(), Bp, D, H, W,
+                          self.max_resolution[0], self.max_resolution[1], oy, ox, code, st)
             self._run_layers(packed, pos2, feat0, f1p, mp, Bp, H, W, D, S, cg, work, ws_bytes, code, st, emb_copy)
             _lib.call("cfp_tokens_to_nchw", feat0.data_ptr(), op.data_ptr(), Bp, D, H, W, code, st)
 

@@ -36,17 +36,21 @@ class FusionPath(nn.Module):
         self.hist_encoder.out_dtype = dtype
         return self
 
-    # run the three (independent) fusion calls on three streams (CFP_SEQUENTIAL_LEVELS=1 disables it)
+    # run the three fusion calls of the synthetic harness on three streams (CFP_SEQUENTIAL_LEVELS=1: one stream, the drop-in order)
     concurrent_levels = not bool(__import__("os").environ.get("CFP_SEQUENTIAL_LEVELS"))
 
     def forward(self, x3, x2, x1, hist_data, mask, patch_info, rect_data=None) -> List[torch.Tensor]:
         """x3/x2/x1: decoder features [B,128,h/16,w/16], [B,64,h/8,w/8], [B,32,h/4,w/4];
         hist_data [B,Z,S]; mask [B,Z] bool.  Returns the fused maps in call order.
 
-        The three TransformerFusion calls only share the histogram tokens, so after the encoder they
-        are enqueued on three streams: their (mostly latency-bound) kernels overlap on the GPU.  The
-        host-side order of the calls - and with it the order of the positional-encoding RNG draws -
-        stays L3, L2, L1 as in the reference decoder."""
+        In THIS harness the three level inputs are given up front (synthetic decoder features), so the three
+        TransformerFusion calls are independent and are enqueued on three streams: their (mostly latency-bound) kernels
+        overlap on the GPU.  Inside the reference's ``Decoder`` they are NOT independent - ``x_d2`` is computed from the
+        fused ``x_d3`` and ``x_d1`` from the fused ``x_d2`` (``decoder.py:109-121``) - so a drop-in there runs them one
+        after the other: ``concurrent_levels = False`` (or ``CFP_SEQUENTIAL_LEVELS=1``) is that configuration, and
+        ``bench.py`` reports it next to the headline as ``drop_in_sequential``; ``cfpnet_b200.decoder.Decoder`` is the
+        integrated form.  The host-side order of the calls - and with it the order of the positional-encoding RNG
+        draws - stays L3, L2, L1 as in the reference decoder."""
         f32, f64, f128 = self.hist_encoder(hist_data.unsqueeze(-1))
         kw = dict(rect_data=rect_data, mask=mask, patch_info=patch_info, rgb=None)
         jobs = ((self.cross_atten3, x3, f128), (self.cross_atten2, x2, f64), (self.cross_atten1, x1, f32))
@@ -86,38 +90,52 @@ class FusionPath(nn.Module):
         return outs
 
     # ------------------------------------------------------------------ CUDA-graph replay (latency mode)
-    def make_graphed(self, x3, x2, x1, hist_data, mask, patch_info):
-        """Capture one forward (all ~95 launches on the three level streams) into a CUDA graph over static input
-        buffers and return ``run(x3, x2, x1, hist_data, mask) -> [fused3, fused2, fused1]`` that copies the inputs in
-        and replays it: at batch 1 the eager path is bound by the ~95 host-side launches, not by the GPU.
+    def make_graphed(self, x3, x2, x1, hist_data, mask, patch_info, copy_inputs: bool = True):
+        """Capture one forward (every launch of the three levels, on all their streams) into a CUDA graph and return
+        ``run(x3, x2, x1, hist_data, mask) -> [fused3, fused2, fused1]`` that replays it: the ~95 host-side launches of
+        a forward (~20 us each through Python + ctypes) become one graph launch.  ``copy_inputs``: the arguments of
+        ``run`` are copied into the captured static buffers first; with ``copy_inputs=False`` the captured tensors ARE the
+        inputs (``run()`` takes no arguments; the caller refills them in place).
 
-        A replay re-runs the captured kernels with the captured arguments, so the positional-encoding crop offsets
-        (``fusion.py:88-91``, drawn per forward when the map is smaller than the table) would be frozen: capture is
-        only offered when every level's map fills its table (the 480x640 evaluation geometry), where the reference
-        draws nothing either."""
-        for m, x in ((self.cross_atten3, x3), (self.cross_atten2, x2), (self.cross_atten1, x1)):
-            if list(x.shape[2:]) != list(m.max_resolution):
-                raise ValueError(f"make_graphed: a {tuple(x.shape[2:])} map draws a random positional-encoding crop from the "
-                                 f"{m.max_resolution} table on every forward; replaying a graph would freeze it")
-        static = [t.clone() for t in (x3, x2, x1, hist_data, mask)]
+        The positional-encoding crop offsets (``fusion.py:88-91``, drawn per forward when a map is smaller than its
+        table) are not frozen into the graph: while capturing, the modules read them from a small device buffer
+        (``cfp_posenc_tokens_crop_fwd``), and every replay first makes the reference's draws - same generator, same
+        order L3, L2, L1 - and uploads them."""
+        mods = ((self.cross_atten3, x3), (self.cross_atten2, x2), (self.cross_atten1, x1))
+        static = [t.clone() for t in (x3, x2, x1, hist_data, mask)] if copy_inputs else [x3, x2, x1, hist_data, mask]
         dev = x3.device
+        crop_dev = torch.zeros(3, 2, device=dev, dtype=torch.int32)
+        shapes = [(m, int(x.shape[2]), int(x.shape[3])) for m, x in mods]
+
+        def upload_crops():
+            vals = [list(m.draw_crop(H, W)) for m, H, W in shapes]
+            crop_dev.copy_(torch.tensor(vals, dtype=torch.int32))       # stream-ordered before the replay
+
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side), torch.no_grad():          # warm-up off the capture: packing, scratch, smem attributes
-            for _ in range(2):
-                self.forward(*static, patch_info)
-        torch.cuda.current_stream(dev).wait_stream(side)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph), torch.no_grad():
-            outs = self.forward(*static, patch_info)
+        try:
+            for i, (m, _x) in enumerate(mods):
+                m.__dict__["_crop_dev"] = crop_dev[i]
+            with torch.cuda.stream(side), torch.no_grad():          # warm-up off the capture: packing, scratch, smem attributes
+                for _ in range(2):
+                    self.forward(*static, patch_info)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph), torch.no_grad():
+                outs = self.forward(*static, patch_info)
+        finally:
+            for m, _x in mods:
+                m.__dict__.pop("_crop_dev", None)
 
-        def run(x3, x2, x1, hist_data, mask):
-            for dst, src in zip(static, (x3, x2, x1, hist_data, mask)):
-                dst.copy_(src, non_blocking=True)
+        def run(*inputs):
+            if copy_inputs:
+                for dst, src in zip(static, inputs):
+                    dst.copy_(src, non_blocking=True)
+            upload_crops()
             graph.replay()
             return outs
 
-        run.graph = graph
+        run.graph, run.crop_dev, run.static = graph, crop_dev, static
         return run
 
     # ------------------------------------------------------------------ host-buffer entry
@@ -136,7 +154,7 @@ class FusionPath(nn.Module):
 
     # ------------------------------------------------------------------ pipelined host-buffer entry
     def stream_host(self, batches: Iterable[Dict[str, torch.Tensor]], patch_info, device, depth: int = 3,
-                    seeds: Iterable[int] | None = None) -> Iterator[Tuple[int, List[torch.Tensor]]]:
+                    seeds: Iterable[int] | None = None, graph: bool = False) -> Iterator[Tuple[int, List[torch.Tensor]]]:
         """Throughput form of :meth:`forward_host`: yields ``(index, [fused3, fused2, fused1])`` (pinned host
         tensors, valid until ``depth`` more batches have been yielded) for every batch of pinned host inputs.
 
@@ -154,7 +172,7 @@ class FusionPath(nn.Module):
             cache[(str(dev), depth)] = dict(
                 h2d=torch.cuda.Stream(dev), d2h=torch.cuda.Stream(dev),
                 slots=[dict(inp=None, out=None, in_ready=torch.cuda.Event(), comp_done=torch.cuda.Event(),
-                            out_ready=torch.cuda.Event(), busy=False) for _ in range(depth)])
+                            out_ready=torch.cuda.Event(), busy=False, graph=None) for _ in range(depth)])
         st = cache[(str(dev), depth)]
         h2d, d2h, slots = st["h2d"], st["d2h"], st["slots"]
         for sl in slots:
@@ -175,6 +193,7 @@ class FusionPath(nn.Module):
                 sl["busy"] = False
             if sl["inp"] is None or any(sl["inp"][k].shape != hb[k].shape or sl["inp"][k].dtype != hb[k].dtype for k in keys):
                 sl["inp"] = {k: torch.empty(hb[k].shape, dtype=hb[k].dtype, device=dev) for k in keys}
+                sl["graph"] = None
             with torch.cuda.stream(h2d):
                 h2d.wait_event(sl["comp_done"])          # previous compute on these input buffers finished
                 for k in keys:
@@ -184,7 +203,13 @@ class FusionPath(nn.Module):
             if seed_it is not None:
                 torch.manual_seed(next(seed_it))
             d = sl["inp"]
-            outs = self.forward(d["x3"], d["x2"], d["x1"], d["hist_data"], d["mask"], patch_info)
+            if graph:                                    # one captured forward per slot (its device buffers are the static inputs)
+                if sl.get("graph") is None:
+                    comp.synchronize()                   # capture replays the forward: the slot's first inputs must have landed
+                    sl["graph"] = self.make_graphed(d["x3"], d["x2"], d["x1"], d["hist_data"], d["mask"], patch_info, copy_inputs=False)
+                outs = sl["graph"]()
+            else:
+                outs = self.forward(d["x3"], d["x2"], d["x1"], d["hist_data"], d["mask"], patch_info)
             sl["comp_done"].record(comp)
             if sl["out"] is None or any(p.shape != o.shape or p.dtype != o.dtype for p, o in zip(sl["out"], outs)):
                 sl["out"] = [torch.empty(o.shape, dtype=o.dtype, pin_memory=True) for o in outs]

@@ -162,6 +162,11 @@ CFP_API int cfp_zone_masks(const uint8_t *mask, uint8_t *zone_mask, uint8_t *his
 CFP_API int cfp_posenc_tokens_fwd(const void *x_nchw, const float *pos, void *tokens, int B, int C, int H,
                           int W, int pos_h, int pos_w, int oy, int ox, int dtype, void *stream);
 /* fusion.py:186: token-major -> contiguous NCHW. */
+/* cfp_posenc_tokens_fwd with the crop offsets (oy, ox) read from DEVICE memory (crop [2], int32) when the kernel runs: a
+ * CUDA-graph replay of a forward then takes fresh offsets from the buffer instead of freezing the captured ones (the
+ * reference draws them per call, fusion.py:88-91).  The caller keeps 0 <= oy <= pos_h - H, 0 <= ox <= pos_w - W. */
+CFP_API int cfp_posenc_tokens_crop_fwd(const void *x_nchw, const float *pos, void *tokens, int B, int C, int H, int W, int pos_h,
+                                       int pos_w, const int *crop, int dtype, void *stream);
 CFP_API int cfp_tokens_to_nchw(const void *tokens, void *out_nchw, int B, int C, int H, int W, int dtype,
                        void *stream);
 

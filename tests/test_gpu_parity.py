@@ -262,7 +262,7 @@ def test_stream_host_equals_direct_forward():
 
 def test_graph_replay_equals_eager_forward():
     """FusionPath.make_graphed at the 480x640 geometry (no positional-encoding crop is drawn there): a replay on new
-    inputs equals the eager forward on them; at 416x544 capture is refused (the crop offsets would be frozen)."""
+    inputs equals the eager forward on them; at 416x544 the crop offsets are drawn per replay and read from device memory."""
     path = cfpnet_b200.FusionPath(synth.COMBINE1_LAYERS)
     path.hist_encoder.load_state_dict(synth.synthetic_state_dict({k: v.shape for k, v in path.hist_encoder.state_dict().items()}, 0))
     for lv, name in ((3, "cross_atten3"), (2, "cross_atten2"), (1, "cross_atten1")):
@@ -283,6 +283,23 @@ def test_graph_replay_equals_eager_forward():
         want = path(*b, pi)
     for g_, w_ in zip(got, want):      # not bit-equal: the split-K / straddling-group fp32 atomics are order-dependent
         assert rel_l2(g_, w_) <= 5e-3
+    # 416x544: the maps are smaller than the positional-encoding tables, so every forward draws crop offsets; a replay
+    # takes them from device memory (same generator, same order) - nothing random is frozen into the graph
     c, pi416 = dev_inputs("G416", 3)
-    with pytest.raises(ValueError, match="positional-encoding"):
-        path.make_graphed(*c, pi416)
+    d, _ = dev_inputs("G416", 4)
+    with torch.no_grad():
+        run416 = path.make_graphed(*c, pi416)
+        for seed, inputs in ((11, d), (12, c), (13, d)):
+            torch.manual_seed(seed)
+            got = [o.clone() for o in run416(*inputs)]
+            torch.cuda.synchronize()
+            torch.manual_seed(seed)
+            want = path(*inputs, pi416)
+            for g_, w_ in zip(got, want):
+                assert rel_l2(g_, w_) <= 5e-3, seed
+        torch.manual_seed(11)
+        first = [o.clone() for o in run416(*d)]
+        torch.manual_seed(12)
+        other = [o.clone() for o in run416(*d)]
+        torch.cuda.synchronize()
+        assert rel_l2(first[0], other[0]) > 1e-3, "different seeds must give different crops (hence outputs) on replay"

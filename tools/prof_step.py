@@ -21,7 +21,7 @@ path.hist_encoder.load_state_dict(synth.synthetic_state_dict({k: v.shape for k, 
 for lv, name in ((3, "cross_atten3"), (2, "cross_atten2"), (1, "cross_atten1")):
     m = getattr(path, name)
     m.load_state_dict(synth.synthetic_state_dict({k: v.shape for k, v in m.state_dict().items()}, lv))
-path = path.to(dev).eval().set_dtype(torch.bfloat16)
+path = path.eval().set_dtype(torch.bfloat16).to(dev)       # cast on the host: no ATen cast kernels in front of the capture window
 inp = synth.make_inputs("G416", B, seed=100)
 d = {k: (inp[k].to(torch.bfloat16) if k.startswith("x") else inp[k]).to(dev) for k in ("x3", "x2", "x1", "hist_data", "mask")}
 with torch.no_grad():
