@@ -15,7 +15,7 @@ import torch
 from .geometry import ZoneGeometry
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcfp.so")
+LIB_PATH = os.environ.get("CFP_LIB_PATH") or os.path.join(_HERE, "libcfp.so")   # override: debug builds (tools/)
 
 CFP_F32, CFP_BF16 = 0, 1
 ABI_VERSION = 13

@@ -64,10 +64,10 @@ __device__ __forceinline__ void unpack8(uint4 u, float (&v)[8]) {
     v[6] = __uint_as_float(u.w << 16); v[7] = __uint_as_float(u.w & 0xffff0000u);
 }
 
-// Row r's accumulator columns [0, C) -> registers.
-template <int C>
-__device__ __forceinline__ void load_row(uint32_t tmem, int warp, float (&v)[C]) {
-    umma::tmem_for_each16<C>(umma::tmem_addr(tmem, warp * 32, 0), [&](int c0, const float (&t)[16]) {
+// Row r's accumulator columns [col0, col0 + N) -> registers.
+template <int N>
+__device__ __forceinline__ void load_cols(uint32_t tmem, int wq, int col0, float (&v)[N]) {
+    umma::tmem_for_each16<N>(umma::tmem_addr(tmem, wq * 32, col0), [&](int c0, const float (&t)[16]) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[c0 + j] = t[j];
     });
@@ -99,38 +99,91 @@ __device__ __forceinline__ void layernorm_reg(float (&v)[C], const float* __rest
         unpack2(o1, v[2 * i + 2], v[2 * i + 3]);
     }
 }
+// Statistics of a row whose C columns are split over two threads (CH = C / 2 each): every thread brings the mean of its
+// half and the sum of squares centred on THAT mean; one exchange through shared memory (xch[half][row]) and Chan's
+// pairwise combination give the row's mean and 1 / std.  `sync` is a barrier over all threads that share rows.
+// Returns {shift, rstd}: (v - mean) = (v - mean_half) + shift.
+template <int C, class Sync>
+__device__ __forceinline__ float2 ln_combine_halves(float mean_h, float m2_h, float2* xch, int row, int half, float eps, Sync&& sync) {
+    constexpr int CH = C / 2;
+    xch[half * 128 + row] = make_float2(mean_h, m2_h);
+    sync();
+    const float2 o = xch[(half ^ 1) * 128 + row];
+    const float mean = 0.5f * (mean_h + o.x), d = mean_h - o.x;
+    const float var = (m2_h + o.y + d * d * (0.5f * CH)) * (1.f / C);
+    return make_float2(mean_h - mean, rsqrtf(var + eps));
+}
+// LayerNorm of the CH = C / 2 columns this thread holds of a split row (g, b already offset to those columns)
+template <int C, class Sync>
+__device__ __forceinline__ void layernorm_half(float (&v)[C / 2], const float* __restrict__ g, const float* __restrict__ b,
+                                               float2* xch, int row, int half, Sync&& sync) {
+    using namespace umma;
+    constexpr int CH = C / 2;
+    f32x2 p[CH / 2];
+    f32x2 s2 = pack2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < CH / 2; ++i) { p[i] = pack2(v[2 * i], v[2 * i + 1]); s2 = add2(s2, p[i]); }
+    float s_lo, s_hi;
+    unpack2(s2, s_lo, s_hi);
+    const float mean_h = (s_lo + s_hi) * (1.f / CH);
+    const f32x2 nm = pack2(-mean_h, -mean_h);
+    f32x2 q2 = pack2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < CH / 2; ++i) { p[i] = add2(p[i], nm); q2 = fma2(p[i], p[i], q2); }
+    float q_lo, q_hi;
+    unpack2(q2, q_lo, q_hi);
+    const float2 st = ln_combine_halves<C>(mean_h, q_lo + q_hi, xch, row, half, kLnEps, sync);
+    const f32x2 sh2 = pack2(st.x, st.x), r2 = pack2(st.y, st.y);
+#pragma unroll
+    for (int i = 0; i < CH / 2; i += 2) {
+        const float4 g4 = *reinterpret_cast<const float4*>(g + 2 * i), b4 = *reinterpret_cast<const float4*>(b + 2 * i);
+        const f32x2 o0 = fma2(mul2(add2(p[i], sh2), r2), pack2(g4.x, g4.y), pack2(b4.x, b4.y));
+        const f32x2 o1 = fma2(mul2(add2(p[i + 1], sh2), r2), pack2(g4.z, g4.w), pack2(b4.z, b4.w));
+        unpack2(o0, v[2 * i], v[2 * i + 1]);
+        unpack2(o1, v[2 * i + 2], v[2 * i + 3]);
+    }
+}
 
 // ---------------------------------------------------------------------------------------
-// Row-thread stages of the chain (thread `tid` <-> token row0+tid <-> TMEM lane tid), shared by the
-// two kernel organisations below.
-template <int C, int NH, bool kAttnOnly, class Q>
+// Row-thread stages of the chain, shared by the two kernel organisations below.  A token row is owned by NT threads
+// (NT = 1: thread `tid` <-> token row0 + tid <-> TMEM lane tid; NT = 2: two threads of different warps with the same
+// TMEM lane quarter share a row, `half` selects which CH = C / NT columns - i.e. which heads, which 16-byte chunks -
+// are this thread's).  At C >= 64 a thread per row meant 4-8 warps per SM walking 64-256 accumulator columns each in
+// one long dependent instruction stream (issue-slot utilisation 0.11-0.26); two threads per row halve every epilogue
+// and double the warps the schedulers can pick from.  Only the two LayerNorms need the other half: one exchange of
+// (mean, centred sum of squares) through shared memory each.
+template <int C, int NH, bool kAttnOnly, class Q, int NT = 1>
 struct ChainStages {
     using P = ChainTC<C>;
     static constexpr int DH = C / NH, KG = P::KG, G = DH < 16 ? 16 : DH;
+    static constexpr int CH = C / NT, KGT = KG / NT;
+    static_assert(NT == 1 || NT == 2, "one or two threads per row");
+    static_assert(CH % G == 0 && CH % 16 == 0, "a thread owns whole heads and whole 16-column pieces");
     struct Row { typename Q::R ref; int g; };
 
-    // stage x: locate the row once, copy its C channels into a0[:, 0:C)
-    static __device__ __forceinline__ Row stage_x(const Q& q, int64_t row0, int tid, uint8_t* a0) {
+    // stage x: locate the row once, copy this thread's chunks of its C channels into a0[:, 0:C)
+    static __device__ __forceinline__ Row stage_x(const Q& q, int64_t row0, int tid, uint8_t* a0, int half = 0) {
         const int64_t row = row0 + tid;
         const bool live = row < q.rows;
         Row r;
         r.ref = q.locate(live ? row : 0);
         r.g = live ? q.group(r.ref) : -1;
-        uint4 v[KG];
+        uint4 v[KGT];
 #pragma unroll
-        for (int kg = 0; kg < KG; ++kg) v[kg] = live ? load8_bf16(q, r.ref, kg * 8) : make_uint4(0u, 0u, 0u, 0u);
+        for (int kg = 0; kg < KGT; ++kg) v[kg] = live ? load8_bf16(q, r.ref, (half * KGT + kg) * 8) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-        for (int kg = 0; kg < KG; ++kg) *reinterpret_cast<uint4*>(a0 + (size_t)kg * P::LBO + tid * 16) = v[kg];
+        for (int kg = 0; kg < KGT; ++kg) *reinterpret_cast<uint4*>(a0 + (size_t)(half * KGT + kg) * P::LBO + tid * 16) = v[kg];
         return r;
     }
     // epilogue 1: Q = elu(q)+1, msg = (Q KV) / (Q.Ksum + eps) -> a0[:, C:2C)  (or the message map)
     // kv / ksum hold the state of groups g_base, g_base + 1, ... (global arrays: g_base = 0; the shared-memory copy of the
     // tile's groups: g_base = first group of the tile)
     static __device__ __forceinline__ void epi_attention(const Q& q, const Row& r, uint32_t tmem, int warp, int tid, uint8_t* a0,
-                                                         const float* __restrict__ kv, const float* __restrict__ ksum, int g_base = 0) {
+                                                         const float* __restrict__ kv, const float* __restrict__ ksum, int g_base = 0,
+                                                         int half = 0) {
         const int g = r.g;
 #pragma unroll 1
-        for (int c0 = 0; c0 < C; c0 += G) {
+        for (int c0 = half * CH; c0 < half * CH + CH; c0 += G) {
             float qv[G], out[G];
 #pragma unroll
             for (int j = 0; j < G; j += 16) {
@@ -184,75 +237,87 @@ struct ChainStages {
         }
     }
     // epilogue 2: LN1(merge) -> a0[:, C:2C)
-    static __device__ __forceinline__ void epi_ln1(const cfp_loftr_w& w, uint32_t tmem, int warp, int tid, uint8_t* a0) {
-        float v[C];
-        load_row<C>(tmem, warp, v);
-        layernorm_reg<C>(v, w.ln1_g, w.ln1_b);
+    template <class Sync>
+    static __device__ __forceinline__ void epi_ln1(const cfp_loftr_w& w, uint32_t tmem, int warp, int tid, uint8_t* a0, int half,
+                                                   float2* xch, Sync&& sync) {
+        float v[CH];
+        load_cols<CH>(tmem, warp, half * CH, v);
+        if constexpr (NT == 1) layernorm_reg<C>(v, w.ln1_g, w.ln1_b);
+        else layernorm_half<C>(v, w.ln1_g + half * CH, w.ln1_b + half * CH, xch, tid, half, sync);
 #pragma unroll
-        for (int j = 0; j < C; j += 8) {
+        for (int j = 0; j < CH; j += 8) {
             float o8[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) o8[i] = v[j + i];
-            umma::store_chunk(a0, P::LBO, tid, KG + j / 8, o8);
+            umma::store_chunk(a0, P::LBO, tid, KG + (half * CH + j) / 8, o8);
         }
     }
     // epilogue 3: relu(W1 [x|msg]) -> a1 (2C columns)
-    static __device__ __forceinline__ void epi_relu(uint32_t tmem, int warp, int tid, uint8_t* a1) {
-        umma::tmem_for_each16<2 * C>(umma::tmem_addr(tmem, warp * 32, 0), [&](int c0, const float (&t)[16]) {
+    static __device__ __forceinline__ void epi_relu(uint32_t tmem, int warp, int tid, uint8_t* a1, int half = 0) {
+        constexpr int N = 2 * C / NT;
+        umma::tmem_for_each16<N>(umma::tmem_addr(tmem, warp * 32, half * N), [&](int c0, const float (&t)[16]) {
 #pragma unroll
             for (int j = 0; j < 16; j += 8) {
                 float o8[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) o8[i] = fmaxf(t[j + i], 0.f);
-                umma::store_chunk(a1, P::LBO, tid, (c0 + j) / 8, o8);
+                umma::store_chunk(a1, P::LBO, tid, (half * N + c0 + j) / 8, o8);
             }
         });
     }
     // epilogue 4: x + LN2(W2 hidden) -> scatter through the provider.  x comes from a0[:, 0:C) (kReloadX = false) or is
     // read again through the provider when the MLP hidden has overwritten a0 in place (two-group kernel).
-    template <bool kReloadX = false>
+    template <bool kReloadX, class Sync>
     static __device__ __forceinline__ void epi_out(const Q& q, const Row& r, const cfp_loftr_w& w, uint32_t tmem, int warp, int tid,
-                                                   const uint8_t* a0) {
+                                                   const uint8_t* a0, int half, float2* xch, Sync&& sync) {
+        const int cb = half * CH;                          // this thread's first column
         if constexpr (kReloadX) {
-            // C = 128, two-tile kernel: the residual row is fetched through the provider FIRST (all KG 16-byte loads in
+            // C = 128, two-tile kernel: the residual row is fetched through the provider FIRST (all 16-byte loads in
             // flight at once - issued one by one between the stores they used to serialise on each other, 12-38 us per
-            // tile), and LayerNorm walks the accumulator three times in 16-column pieces instead of holding all C
+            // tile), and LayerNorm walks the accumulator three times in 16-column pieces instead of holding all the
             // values in registers next to them (mean, then centred sum of squares, then normalise + residual + store).
-            uint4 xr[KG];
+            uint4 xr[KGT];
 #pragma unroll
-            for (int k = 0; k < KG; ++k) xr[k] = r.g >= 0 ? load8_bf16(q, r.ref, k * 8) : make_uint4(0u, 0u, 0u, 0u);
+            for (int k = 0; k < KGT; ++k) xr[k] = r.g >= 0 ? load8_bf16(q, r.ref, cb + k * 8) : make_uint4(0u, 0u, 0u, 0u);
             float s = 0.f;
 #pragma unroll 1
-            for (int c0 = 0; c0 < C; c0 += 16) {
+            for (int c0 = 0; c0 < CH; c0 += 16) {
                 float t[16];
-                umma::tmem_ld16(umma::tmem_addr(tmem, warp * 32, c0), t);
+                umma::tmem_ld16(umma::tmem_addr(tmem, warp * 32, cb + c0), t);
 #pragma unroll
                 for (int i = 0; i < 16; ++i) s += t[i];
             }
-            const float mean = s * (1.f / C);
+            float mean = s * (1.f / CH);
             float qs = 0.f;
 #pragma unroll 1
-            for (int c0 = 0; c0 < C; c0 += 16) {
+            for (int c0 = 0; c0 < CH; c0 += 16) {
                 float t[16];
-                umma::tmem_ld16(umma::tmem_addr(tmem, warp * 32, c0), t);
+                umma::tmem_ld16(umma::tmem_addr(tmem, warp * 32, cb + c0), t);
 #pragma unroll
                 for (int i = 0; i < 16; ++i) { const float d = t[i] - mean; qs = fmaf(d, d, qs); }
             }
-            const float rstd = rsqrtf(qs * (1.f / C) + kLnEps);
+            float rstd;
+            if constexpr (NT == 1) {
+                rstd = rsqrtf(qs * (1.f / C) + kLnEps);
+            } else {
+                const float2 st = ln_combine_halves<C>(mean, qs, xch, tid, half, kLnEps, sync);
+                mean -= st.x;
+                rstd = st.y;
+            }
 #pragma unroll
-            for (int c0 = 0; c0 < C; c0 += 16) {
+            for (int c0 = 0; c0 < CH; c0 += 16) {
                 float t[16];
-                umma::tmem_ld16(umma::tmem_addr(tmem, warp * 32, c0), t);
+                umma::tmem_ld16(umma::tmem_addr(tmem, warp * 32, cb + c0), t);
                 if (r.g >= 0) {
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        const int j = c0 + 8 * h;
+                        const int jl = c0 + 8 * h, j = cb + jl;
                         const float4 g0 = *reinterpret_cast<const float4*>(w.ln2_g + j), g1 = *reinterpret_cast<const float4*>(w.ln2_g + j + 4);
                         const float4 b0 = *reinterpret_cast<const float4*>(w.ln2_b + j), b1 = *reinterpret_cast<const float4*>(w.ln2_b + j + 4);
                         const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
                         const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
                         float x8[8], o8[8];
-                        unpack8(xr[j / 8], x8);
+                        unpack8(xr[jl / 8], x8);
 #pragma unroll
                         for (int i = 0; i < 8; ++i) o8[i] = x8[i] + fmaf((t[8 * h + i] - mean) * rstd, gg[i], bb[i]);
                         if constexpr (HasPutSum<Q>::value) {
@@ -264,16 +329,18 @@ struct ChainStages {
             }
             return;
         }
-        float v[C];
-        load_row<C>(tmem, warp, v);
-        layernorm_reg<C>(v, w.ln2_g, w.ln2_b);
+        float v[CH];
+        load_cols<CH>(tmem, warp, cb, v);
+        if constexpr (NT == 1) layernorm_reg<C>(v, w.ln2_g, w.ln2_b);
+        else layernorm_half<C>(v, w.ln2_g + cb, w.ln2_b + cb, xch, tid, half, sync);
         if (r.g >= 0) {
 #pragma unroll
-            for (int j = 0; j < C; j += 8) {
+            for (int jl = 0; jl < CH; jl += 8) {
+                const int j = cb + jl;
                 float x8[8], o8[8];
                 unpack8(*reinterpret_cast<const uint4*>(a0 + (size_t)(j / 8) * P::LBO + tid * 16), x8);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) o8[i] = x8[i] + v[j + i];
+                for (int i = 0; i < 8; ++i) o8[i] = x8[i] + v[jl + i];
                 if constexpr (HasPutSum<Q>::value && sizeof(typename Q::R) > 0) {
                     if (q.sums_in_place()) { q.put8_sum(r.ref, j, o8, x8); continue; }
                 }
@@ -308,35 +375,39 @@ template <int C> struct ChainOcc { static constexpr int CTAS = C >= 128 ? 1 : (C
 // epilogues of the two tiles side by side (two warps per scheduler instead of one).  Each group owns ONE operand
 // buffer: the MLP hidden overwrites [x | msg] in place once its MMAs have completed, and the residual x is read again
 // through the provider (L2-hot) in the last epilogue.
-template <int C, int NH, bool kAttnOnly, class Q>
-__global__ void __launch_bounds__(320, 1) loftr_query_tc_kernel(Q q, cfp_loftr_w w, const float* __restrict__ kv,
+template <int C, int NH, bool kAttnOnly, class Q, int NT>
+__global__ void __launch_bounds__((8 * NT + 2) * 32, 1) loftr_query_tc_kernel(Q q, cfp_loftr_w w, const float* __restrict__ kv,
                                                              const float* __restrict__ ksum, int ntiles) {
     using P = ChainTC<C>;
-    using S = ChainStages<C, NH, kAttnOnly, Q>;
+    using S = ChainStages<C, NH, kAttnOnly, Q, NT>;
     constexpr int KG = P::KG;
     constexpr int NCHUNK = kAttnOnly ? 1 : 8;
+    constexpr int RW = 4 * NT, NRW = 2 * RW;                 // row warps per tile group / per CTA; then producer, MMA issuer
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ ChainBars bars;
+    __shared__ float2 ln_xch[2][NT][128];                    // LayerNorm statistics of split rows, per tile group
     uint8_t* ring = smem + 2 * (size_t)P::ABUF;
     const int tid = threadIdx.x, warp = umma::warp_idx_sync();
     const int npairs = (ntiles + 1) / 2;
 
     if (tid == 0) {
         for (int i = 0; i < P::NSLOT; ++i) { umma::mbar_init(&bars.full[i], 1); umma::mbar_init(&bars.empty[i], 1); }
-        umma::mbar_init(&bars.a_ready, 256);
+        umma::mbar_init(&bars.a_ready, NRW * 32);
         umma::mbar_init(&bars.acc_ready, 1);
         umma::fence_mbar_init();
     }
-    if (warp == 8) umma::tmem_alloc(&bars.tmem_slot, 512);
+    if (warp == NRW) umma::tmem_alloc(&bars.tmem_slot, 512);
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
 
-    if (warp < 8) {
+    if (warp < NRW) {
         pdl_wait();                       // rows and attention state come from the previous kernels of the stream
-        const int grp = warp >> 2, wq = warp & 3, tid_g = tid & 127;
+        const int grp = warp / RW, half = (warp % RW) >> 2, wq = warp & 3, tid_g = tid & 127;
         uint8_t* a0 = smem + (size_t)grp * P::ABUF;          // [x | msg, then LN1(merge(msg))], then the MLP hidden
         const uint32_t tmem = bars.tmem_slot + grp * 256;
+        float2* xch = &ln_xch[grp][0][0];
+        auto group_sync = [&]() { asm volatile("bar.sync %0, %1;\n" ::"r"(2 + grp), "n"(RW * 32) : "memory"); };
         uint32_t ph = 0;
         auto hand_over = [&]() {          // operands staged / accumulator consumed -> MMA warp; then wait for its result
             umma::fence_async_smem();
@@ -350,30 +421,30 @@ __global__ void __launch_bounds__(320, 1) loftr_query_tc_kernel(Q q, cfp_loftr_w
             const int64_t row0 = tile < ntiles ? (int64_t)tile * 128 : q.rows;
             [[maybe_unused]] const int dbg_it = 1 - (pair - (int)blockIdx.x) / (int)gridDim.x;      // marks on the FIRST pair of CTA 5
             CFP_CHAIN_MARK(0, dbg_it);
-            const typename S::Row r = S::stage_x(q, row0, tid_g, a0);
+            const typename S::Row r = S::stage_x(q, row0, tid_g, a0, half);
             CFP_CHAIN_MARK(1, dbg_it);
             hand_over();
             CFP_CHAIN_MARK(2, dbg_it);
-            S::epi_attention(q, r, tmem, wq, tid_g, a0, kv, ksum);
+            S::epi_attention(q, r, tmem, wq, tid_g, a0, kv, ksum, 0, half);
             CFP_CHAIN_MARK(3, dbg_it);
             if (!kAttnOnly) {
                 hand_over();
                 CFP_CHAIN_MARK(4, dbg_it);
-                S::epi_ln1(w, tmem, wq, tid_g, a0);
+                S::epi_ln1(w, tmem, wq, tid_g, a0, half, xch, group_sync);
                 CFP_CHAIN_MARK(5, dbg_it);
                 hand_over();
                 CFP_CHAIN_MARK(6, dbg_it);
-                S::epi_relu(tmem, wq, tid_g, a0);             // in place: the W1 MMAs have consumed [x | LN1]
+                S::epi_relu(tmem, wq, tid_g, a0, half);       // in place: the W1 MMAs have consumed [x | LN1]
                 CFP_CHAIN_MARK(7, dbg_it);
                 hand_over();
                 CFP_CHAIN_MARK(8, dbg_it);
-                S::template epi_out<true>(q, r, w, tmem, wq, tid_g, a0);
+                S::template epi_out<true>(q, r, w, tmem, wq, tid_g, a0, half, xch, group_sync);
                 CFP_CHAIN_MARK(9, dbg_it);
             }
             umma::fence_before_sync();
-            asm volatile("bar.sync 1, 256;\n" ::: "memory");  // every row is done with a0 / the accumulators before the next pair
+            asm volatile("bar.sync 1, %0;\n" ::"n"(NRW * 32) : "memory");  // every row is done with a0 / the accumulators before the next pair
         }
-    } else if (warp == 8) {
+    } else if (warp == NRW) {
         const bf16* wsrc = reinterpret_cast<const bf16*>(w.tc);
         int cc = 0;
         for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x)
@@ -422,7 +493,7 @@ __global__ void __launch_bounds__(320, 1) loftr_query_tc_kernel(Q q, cfp_loftr_w
     }
     pdl_trigger();                         // this CTA's work is done: the next kernel of the stream may start its prologue
     __syncthreads();
-    if (warp == 8) {
+    if (warp == NRW) {
         umma::fence_after_sync();
         umma::tmem_dealloc(bars.tmem_slot, 512);
     }
@@ -442,14 +513,15 @@ struct MonoBars {
     uint32_t tmem_slot;
 };
 
-template <int C, int NH, bool kAttnOnly, class Q>
-__global__ void __launch_bounds__(128, MonoOcc<C>::CTAS) loftr_query_mono_kernel(Q q, cfp_loftr_w w, const float* __restrict__ kv,
+template <int C, int NH, bool kAttnOnly, class Q, int NT>
+__global__ void __launch_bounds__(128 * NT, MonoOcc<C>::CTAS) loftr_query_mono_kernel(Q q, cfp_loftr_w w, const float* __restrict__ kv,
                                                                 const float* __restrict__ ksum, int ntiles, int kv_slots) {
     using P = ChainTC<C>;
-    using S = ChainStages<C, NH, kAttnOnly, Q>;
+    using S = ChainStages<C, NH, kAttnOnly, Q, NT>;
     constexpr int KG = P::KG, NB = kAttnOnly ? 1 : 8;      // weight blocks per tile
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ MonoBars bars;
+    __shared__ float2 ln_xch[NT][128];                      // LayerNorm statistics of split rows
     uint8_t* a0 = smem;
     uint8_t* a1 = a0 + P::ABUF;
     uint8_t* ring = a1 + (kAttnOnly ? 0 : P::ABUF);        // 4 slots
@@ -458,9 +530,12 @@ __global__ void __launch_bounds__(128, MonoOcc<C>::CTAS) loftr_query_mono_kernel
     // instead of stalling every FMA chain on an L2 round trip
     float* kvs = reinterpret_cast<float*>(ring + 4 * (size_t)P::SLOT);
     float* kss = kvs + (size_t)kv_slots * (C * S::DH);
-    const int tid = threadIdx.x, warp = umma::warp_idx_sync();
+    const int warp = umma::warp_idx_sync();
+    const int tid = threadIdx.x & 127, half = warp >> 2, wq = warp & 3;   // row of the tile (= TMEM lane), which of its NT threads
+    float2* xch = &ln_xch[0][0];
+    auto cta_sync = [&]() { __syncthreads(); };
 
-    if (tid == 0) {
+    if (threadIdx.x == 0) {
         for (int i = 0; i < 4; ++i) umma::mbar_init(&bars.full[i], 1);
         umma::mbar_init(&bars.acc_ready, 1);
         umma::mbar_init(&bars.kv_full, 1);
@@ -514,7 +589,7 @@ __global__ void __launch_bounds__(128, MonoOcc<C>::CTAS) loftr_query_mono_kernel
         const int64_t row0 = (int64_t)tile * 128;
         [[maybe_unused]] const int dbg_it = (tile - (int)blockIdx.x) / (int)gridDim.x;
         CFP_CHAIN_MARK(0, dbg_it);
-        const typename S::Row r = S::stage_x(q, row0, tid, a0);
+        const typename S::Row r = S::stage_x(q, row0, tid, a0, half);
         CFP_CHAIN_MARK(1, dbg_it);
         const int g_first = kv_slots > 0 ? q.group_of_row(row0) : 0;
         stage([&] {                                                                        // q
@@ -537,16 +612,16 @@ __global__ void __launch_bounds__(128, MonoOcc<C>::CTAS) loftr_query_mono_kernel
         }
         if (kAttnOnly) {
             if (warp == 0) prefetch(base + 4);               // slot of block `base` is free again
-            S::epi_attention(q, r, tmem, warp, tid, a0, kv_t, ks_t, g_first);
+            S::epi_attention(q, r, tmem, wq, tid, a0, kv_t, ks_t, g_first, half);
             continue;                                        // next stage() barrier orders a0 / TMEM reuse
         }
         CFP_CHAIN_MARK(2, dbg_it);
-        S::epi_attention(q, r, tmem, warp, tid, a0, kv_t, ks_t, g_first);
+        S::epi_attention(q, r, tmem, wq, tid, a0, kv_t, ks_t, g_first, half);
         CFP_CHAIN_MARK(3, dbg_it);
         stage([&] { block(base + 1, a0s + KG * P::LBO, 0, false); });                     // merge
         CFP_CHAIN_MARK(4, dbg_it);
         if (warp == 0) { prefetch(base + 4); prefetch(base + 5); }                        // blocks 0,1 consumed
-        S::epi_ln1(w, tmem, warp, tid, a0);
+        S::epi_ln1(w, tmem, wq, tid, a0, half, xch, cta_sync);
         CFP_CHAIN_MARK(5, dbg_it);
         stage([&] {                                                                        // W1 quadrants
             block(base + 2, a0s, 0, false);
@@ -556,7 +631,7 @@ __global__ void __launch_bounds__(128, MonoOcc<C>::CTAS) loftr_query_mono_kernel
         });
         if (warp == 0) { prefetch(base + 6); prefetch(base + 7); prefetch(base + 8); prefetch(base + 9); }
         CFP_CHAIN_MARK(6, dbg_it);
-        S::epi_relu(tmem, warp, tid, a1);
+        S::epi_relu(tmem, wq, tid, a1, half);
         CFP_CHAIN_MARK(7, dbg_it);
         stage([&] {                                                                        // W2 K-halves
             block(base + 6, a1s, 0, false);
@@ -564,7 +639,7 @@ __global__ void __launch_bounds__(128, MonoOcc<C>::CTAS) loftr_query_mono_kernel
         });
         if (warp == 0) { prefetch(base + 10); prefetch(base + 11); }
         CFP_CHAIN_MARK(8, dbg_it);
-        S::epi_out(q, r, w, tmem, warp, tid, a0);
+        S::template epi_out<false>(q, r, w, tmem, wq, tid, a0, half, xch, cta_sync);
         CFP_CHAIN_MARK(9, dbg_it);
         // the next tile's stage_x overwrites a0[:, 0:C), which epi_out of other rows may still read
         __syncthreads();
@@ -578,9 +653,16 @@ __global__ void __launch_bounds__(128, MonoOcc<C>::CTAS) loftr_query_mono_kernel
     }
 }
 
-template <int C, int NH, bool kAttnOnly, class Q>
-static int run_query_tc(const char* name, const Q& q, const cfp_loftr_w& w, const float* kv, const float* ksum,
-                        cudaStream_t st) {
+// threads per token row: two at C >= 64 (see ChainStages); CFP_CHAIN_NT=1 forces the thread-per-row kernels (A/B measurements)
+template <int C> struct ChainNT { static constexpr int NT = C >= 64 ? 2 : 1; };
+static bool chain_split_rows() {
+    static const bool v = [] { const char* e = getenv("CFP_CHAIN_NT"); return !(e && e[0] == '1'); }();
+    return v;
+}
+
+template <int C, int NH, bool kAttnOnly, class Q, int NT>
+static int run_query_tc_nt(const char* name, const Q& q, const cfp_loftr_w& w, const float* kv, const float* ksum,
+                           cudaStream_t st) {
     using P = ChainTC<C>;
     CFP_REQUIRE(w.tc != nullptr, "%s: bf16 path needs the packed tensor-core weights (cfp_loftr_w.tc)", name);
     const int64_t ntiles = (q.rows + 127) / 128;
@@ -596,9 +678,9 @@ static int run_query_tc(const char* name, const Q& q, const cfp_loftr_w& w, cons
         if ((smem0 + kv_bytes + 1024) * per_sm > 227 * 1024 || getenv("CFP_NO_KV_SMEM")) kv_slots = 0;
         const size_t smem = smem0 + (kv_slots > 0 ? kv_bytes : 0);
         const int grid = (int)(ntiles < sm_count() * per_sm ? ntiles : sm_count() * per_sm);
-        auto k = loftr_query_mono_kernel<C, NH, kAttnOnly, Q>;
+        auto k = loftr_query_mono_kernel<C, NH, kAttnOnly, Q, NT>;
         if (int e = set_smem(k, smem)) return e;
-        launch_pdl(k, grid, 128, smem, st, q, w, kv, ksum, (int)ntiles, kv_slots);
+        launch_pdl(k, grid, 128 * NT, smem, st, q, w, kv, ksum, (int)ntiles, kv_slots);
 #ifdef CFP_DEBUG_TIMING
         {
             cudaStreamSynchronize(st);
@@ -611,9 +693,9 @@ static int run_query_tc(const char* name, const Q& q, const cfp_loftr_w& w, cons
     } else {
         const int64_t npairs = (ntiles + 1) / 2;
         const int grid = (int)(npairs < sm_count() ? npairs : sm_count());
-        auto k = loftr_query_tc_kernel<C, NH, kAttnOnly, Q>;
+        auto k = loftr_query_tc_kernel<C, NH, kAttnOnly, Q, NT>;
         if (int e = set_smem(k, P::SMEM)) return e;
-        launch_pdl(k, grid, 320, P::SMEM, st, q, w, kv, ksum, (int)ntiles);
+        launch_pdl(k, grid, (8 * NT + 2) * 32, P::SMEM, st, q, w, kv, ksum, (int)ntiles);
 #ifdef CFP_DEBUG_TIMING
         {
             cudaStreamSynchronize(st);
@@ -625,6 +707,15 @@ static int run_query_tc(const char* name, const Q& q, const cfp_loftr_w& w, cons
 #endif
     }
     return check_launch(name);
+}
+
+template <int C, int NH, bool kAttnOnly, class Q>
+static int run_query_tc(const char* name, const Q& q, const cfp_loftr_w& w, const float* kv, const float* ksum,
+                        cudaStream_t st) {
+    if constexpr (ChainNT<C>::NT == 2) {
+        if (chain_split_rows()) return run_query_tc_nt<C, NH, kAttnOnly, Q, 2>(name, q, w, kv, ksum, st);
+    }
+    return run_query_tc_nt<C, NH, kAttnOnly, Q, 1>(name, q, w, kv, ksum, st);
 }
 
 // =====================================================================================
@@ -917,7 +1008,7 @@ template <int C> struct KvTC {
 // of one MMA + accumulator read-back + flush round trip per group (eight serial round trips per tile).
 // NT = threads per row (KvNT<C>): at C = 128 a CTA per SM with four row warps left every scheduler with one warp of long
 // serial epilogues; two threads share a row (x chunks, then K columns | V columns, then half of the zones each).
-template <int C> struct KvNT { static constexpr int NT = C >= 128 ? 2 : 1; };
+template <int C> struct KvNT { static constexpr int NT = C >= 64 ? 2 : 1; };
 template <int C, int NH, bool kComplete, class Src, bool kZone16 = false>
 __global__ void __launch_bounds__((4 * KvNT<C>::NT + 2) * 32) kv_state_tc_kernel(Src src, int S, int S_pad, FastDiv dSp, int groups, const bf16* __restrict__ wkv_tc,
                                                           float* __restrict__ kv, float* __restrict__ ksum, int ntiles) {
@@ -1392,9 +1483,14 @@ int sr_conv_ln_tc(const void* feat0, float* sr_tok, int B, int H, int W, int C, 
     if (C == 128) return run_query_tc<128, NH, ATTN>(NAME ",128>", q, w, kv, ksum, st);  \
     return fail("unsupported C=%d", C);
 
+template <class Q>
+static int query_tc_h2i_impl(int C, const Q& q, const cfp_loftr_w& w, const float* kv, const float* ksum, cudaStream_t st) {
+    CFP_TC_DISPATCH(4, false, "loftr_query_tc<hist2image")
+}
 int query_tc_h2i(int C, const ZonePatchRows<bf16>& q, const cfp_loftr_w& w, const float* kv, const float* ksum,
                  cudaStream_t st) {
-    CFP_TC_DISPATCH(4, false, "loftr_query_tc<hist2image")
+    if (q.fast_eligible()) return query_tc_h2i_impl(C, ZonePatchRows<bf16, true>(q), w, kv, ksum, st);
+    return query_tc_h2i_impl(C, q, w, kv, ksum, st);
 }
 int query_tc_lsa(int C, const WindowRows<bf16>& q, const cfp_loftr_w& w, const float* kv, const float* ksum,
                  cudaStream_t st) {

@@ -183,11 +183,21 @@ struct OutsideRows {           // DAPM queries: tokens outside the rectangle; me
     }
 };
 
-template <typename T>
+// kFast (a compile-time copy of "no resize, no --no_skip_inside, canvas cut from feat0 itself", the geometry every
+// benchmarked 416x544 call has): the bilinear-resize gather and the general scatter vanish from the instantiation.  Inlined
+// into every 16-byte chunk of the tensor-core chain's fully unrolled stage / epilogue code those branches made
+// loftr_query_tc<hist2image,128> 24 k SASS lines (390 KB), 26 % of its stall samples "no instruction" (instruction-cache
+// misses) on paths that geometry never takes.
+template <typename T, bool kFast = false>
 struct ZonePatchRows {         // hist2image queries: cells of the zone canvas, grouped per zone
     T* feat0; const T* emb; T* canvas; const uint8_t* mask;
     int H, W, C, zn, p1, p2, sy_wo, sx_wo, tzh, tzw, interpolate, assign; int64_t rows;
     FastDiv dP, dZ, dZn, dP2;
+    bool fast_eligible() const { return !interpolate && !assign && emb == feat0; }
+    explicit ZonePatchRows(const ZonePatchRows<T, !kFast>& o)
+        : feat0(o.feat0), emb(o.emb), canvas(o.canvas), mask(o.mask), H(o.H), W(o.W), C(o.C), zn(o.zn), p1(o.p1), p2(o.p2),
+          sy_wo(o.sy_wo), sx_wo(o.sx_wo), tzh(o.tzh), tzw(o.tzw), interpolate(o.interpolate), assign(o.assign), rows(o.rows),
+          dP(o.dP), dZ(o.dZ), dZn(o.dZn), dP2(o.dP2) {}
     ZonePatchRows(T* f, const T* e, T* cv, const uint8_t* m, int H_, int W_, int C_, int zn_, int p1_, int p2_, int sy, int sx,
                   int tzh_, int tzw_, int interp, int assign_, int64_t n)
         : feat0(f), emb(e), canvas(cv), mask(m), H(H_), W(W_), C(C_), zn(zn_), p1(p1_), p2(p2_), sy_wo(sy), sx_wo(sx),
@@ -214,7 +224,7 @@ struct ZonePatchRows {         // hist2image queries: cells of the zone canvas, 
     // the fp32 bilinear blend
     __device__ uint4 raw8(const R& q, int c) const {
         static_assert(sizeof(T) == 2, "raw8 is the bf16 fast path");
-        if (!interpolate) {
+        if (kFast || !interpolate) {
             const int y = sy_wo + q.cy, x = sx_wo + q.cx;
             if (y < 0 || y >= H || x < 0 || x >= W) return make_uint4(0u, 0u, 0u, 0u);
             return *reinterpret_cast<const uint4*>(emb + ((int64_t)q.b * H * W + (int64_t)y * W + x) * C + c);
@@ -243,7 +253,7 @@ struct ZonePatchRows {         // hist2image queries: cells of the zone canvas, 
     // feat0[zone] += out with out = x + msg: when the canvas is cut from feat0 itself (change_embedding, fusion.py:134),
     // no resize and no --no_skip_inside, the cell's current value IS the x the row was staged from, so the sum is
     // 2x + msg from registers: one 16-byte store instead of a read-modify-write whose load latency ends every tile.
-    __device__ bool sums_in_place() const { return !interpolate && !assign && emb == feat0; }
+    __device__ bool sums_in_place() const { return kFast || (!interpolate && !assign && emb == feat0); }
     __device__ void put8_sum(const R& q, int c, const float (&o8)[8], const float (&x8)[8]) const {
         const int y = sy_wo + q.cy, x = sx_wo + q.cx;
         if (!q.valid || y < 0 || y >= H || x < 0 || x >= W) return;      // hist_mask / pad_mask (fusion.py:144,112-118)
