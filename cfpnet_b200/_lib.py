@@ -18,7 +18,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CFP_LIB_PATH") or os.path.join(_HERE, "libcfp.so")   # override: debug builds (tools/)
 
 CFP_F32, CFP_BF16 = 0, 1
-ABI_VERSION = 13
+ABI_VERSION = 14
 _fp = C.POINTER(C.c_float)
 
 
@@ -72,6 +72,7 @@ SIGNATURES = {
     "cfp_dapm_fwd": (_i, [_p, _i, _i, _i, _i, C.POINTER(CfpGeom), C.POINTER(CfpDapmW), _p, _sz, _i, _p]),
     "cfp_lkpm_fwd": (_i, [_p, _i, _i, _i, _i, C.POINTER(CfpLkpmW), _p, _sz, _i, _p]),
     "cfp_twins_fwd": (_i, [_p, _i, _i, _i, _i, C.POINTER(CfpTwinsW), _p, _sz, _i, _p]),
+    "cfp_twins_nchw_fwd": (_i, [_p, _p, _i, _i, _i, _i, C.POINTER(CfpTwinsW), _p, _sz, _i, _p]),
     "cfp_tr_gemm": (_i, [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i, _i, _i, _p, _i, _p]),
     "cfp_tr_colsum": (_i, [_p, _p, _i64, _i, _p]),
     "cfp_tr_bn_stats": (_i, [_p, _i64, _i, C.c_float, C.c_float, _p, _p, _p, _p, _p, _p]),

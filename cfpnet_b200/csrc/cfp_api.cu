@@ -334,9 +334,21 @@ CFP_API int cfp_lkpm_fwd(void* feat0, int B, int H, int W, int C, const cfp_lkpm
     return lkpm_mlp(feat0, y, (int64_t)B * H * W, C, *w, dtype, st);
 }
 
+static int twins_call(void* feat0, void* out_nchw, int B, int H, int W, int C, const cfp_twins_w* w, void* workspace,
+                      size_t workspace_bytes, int dtype, void* stream);
 CFP_API int cfp_twins_fwd(void* feat0, int B, int H, int W, int C, const cfp_twins_w* w, void* workspace,
                   size_t workspace_bytes, int dtype, void* stream) {
     begin_call(stream);
+    return twins_call(feat0, nullptr, B, H, W, C, w, workspace, workspace_bytes, dtype, stream);
+}
+CFP_API int cfp_twins_nchw_fwd(void* feat0, void* out_nchw, int B, int H, int W, int C, const cfp_twins_w* w, void* workspace,
+                       size_t workspace_bytes, int dtype, void* stream) {
+    begin_call(stream);
+    CFP_REQUIRE(out_nchw != nullptr && out_nchw != feat0, "out_nchw must be a separate NCHW map");
+    return twins_call(feat0, out_nchw, B, H, W, C, w, workspace, workspace_bytes, dtype, stream);
+}
+static int twins_call(void* feat0, void* out_nchw, int B, int H, int W, int C, const cfp_twins_w* w, void* workspace,
+                      size_t workspace_bytes, int dtype, void* stream) {
     if (int e = check_common(feat0, B, H, W, C, dtype)) return e;
     CFP_REQUIRE(w && workspace, "null pointer");
     CFP_REQUIRE(w->ws > 1, "window size must be > 1 (transformer.py:79)");
@@ -345,7 +357,7 @@ CFP_API int cfp_twins_fwd(void* feat0, int B, int H, int W, int C, const cfp_twi
                 "fails here too, transformer.py:144)", H, W, w->ws, w->ws);
     WsLayout L = ws_layout(B, H, W, C, w->ws, 0, dtype, nullptr);
     CFP_REQUIRE(workspace_bytes >= L.total, "workspace too small: %zu < %zu", workspace_bytes, L.total);
-    return twins(feat0, B, H, W, C, *w, (char*)workspace, L, dtype, (cudaStream_t)stream);
+    return twins(feat0, out_nchw, B, H, W, C, *w, (char*)workspace, L, dtype, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------- training-step building blocks (fp32)

@@ -38,8 +38,8 @@ int d2i(void* feat0, const void* emb, const void* zone_tok, const float* pos2, c
         const WsLayout& L, int dtype, cudaStream_t st);
 int dapm_attention(const void* feat0, void* msg_map, int B, int H, int W, int C, const cfp_geom& g,
                    const cfp_loftr_w& w, char* ws, const WsLayout& L, int dtype, cudaStream_t st);
-int twins(void* feat0, int B, int H, int W, int C, const cfp_twins_w& w, char* ws, const WsLayout& L,
-          int dtype, cudaStream_t st);
+int twins(void* feat0, void* out_nchw, int B, int H, int W, int C, const cfp_twins_w& w, char* ws, const WsLayout& L,
+          int dtype, cudaStream_t st);     // out_nchw != nullptr: the result goes to that NCHW map instead of feat0
 
 // k_conv.cu
 // out = conv3x3(cat[in0, in1]) + shift (+ residual); in1 may be null; in1 is read as zero inside

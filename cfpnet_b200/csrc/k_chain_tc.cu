@@ -1500,6 +1500,10 @@ int query_tc_gsa(int C, const FrameRows<bf16>& q, const cfp_loftr_w& w, const fl
                  cudaStream_t st) {
     CFP_TC_DISPATCH(8, false, "loftr_query_tc<gsa")
 }
+int query_tc_gsa_nchw(int C, const FrameRowsToNCHW<bf16>& q, const cfp_loftr_w& w, const float* kv, const float* ksum,
+                      cudaStream_t st) {
+    CFP_TC_DISPATCH(8, false, "loftr_query_tc<gsa")
+}
 int query_tc_dapm(int C, const OutsideRows<bf16>& q, const cfp_loftr_w& w, const float* kv, const float* ksum,
                   cudaStream_t st) {
     CFP_TC_DISPATCH(4, true, "attn_query_tc<dapm")

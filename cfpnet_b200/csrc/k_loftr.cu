@@ -289,7 +289,7 @@ static int dapm_impl(const void* feat0, void* msg_map, int B, int H, int W, cons
 }
 
 template <int C, typename T>
-static int twins_impl(void* feat0, int B, int H, int W, const cfp_twins_w& w, char* ws, const WsLayout& L,
+static int twins_impl(void* feat0, void* out_nchw, int B, int H, int W, const cfp_twins_w& w, char* ws, const WsLayout& L,
                       cudaStream_t st) {
     const int wsz = w.ws;
     // LSA (transformer.py:94-116): pad to a multiple of ws, attention inside each window, 8 heads
@@ -323,8 +323,16 @@ static int twins_impl(void* feat0, int B, int H, int W, const cfp_twins_w& w, ch
         if (int e = run_kv_state<C, 8>("kv_state<gsa>", src, B, w.gsa.wkv_t, kv, ksum, st)) return e;
     }
     FrameRows<T> fr((T*)feat0, H * W, C, (int64_t)B * H * W);
-    if constexpr (std::is_same<T, bf16>::value) return query_tc_gsa(C, fr, w.gsa, kv, ksum, st);
-    else return run_query<C, 8, false>("loftr_query<gsa>", fr, w.gsa, kv, ksum, st);
+    if constexpr (std::is_same<T, bf16>::value) {
+        if (out_nchw) {     // last layer of a call: the query chain's last epilogue writes the caller's NCHW map itself
+            FrameRowsToNCHW<bf16> fo((const bf16*)feat0, (bf16*)out_nchw, H * W, C, (int64_t)B * H * W);
+            return query_tc_gsa_nchw(C, fo, w.gsa, kv, ksum, st);
+        }
+        return query_tc_gsa(C, fr, w.gsa, kv, ksum, st);
+    } else {
+        if (int e = run_query<C, 8, false>("loftr_query<gsa>", fr, w.gsa, kv, ksum, st)) return e;
+        return out_nchw ? tokens_to_nchw(feat0, out_nchw, B, C, H, W, CFP_F32, st) : 0;
+    }
 }
 
 #define CFP_DISPATCH_C_T(FN, ...)                                                        \
@@ -348,9 +356,9 @@ int dapm_attention(const void* feat0, void* msg_map, int B, int H, int W, int C,
                    const cfp_loftr_w& w, char* ws, const WsLayout& L, int dtype, cudaStream_t st) {
     CFP_DISPATCH_C_T(dapm_impl, feat0, msg_map, B, H, W, g, w, ws, L, st)
 }
-int twins(void* feat0, int B, int H, int W, int C, const cfp_twins_w& w, char* ws, const WsLayout& L, int dtype,
+int twins(void* feat0, void* out_nchw, int B, int H, int W, int C, const cfp_twins_w& w, char* ws, const WsLayout& L, int dtype,
           cudaStream_t st) {
-    CFP_DISPATCH_C_T(twins_impl, feat0, B, H, W, w, ws, L, st)
+    CFP_DISPATCH_C_T(twins_impl, feat0, out_nchw, B, H, W, w, ws, L, st)
 }
 
 }  // namespace cfp

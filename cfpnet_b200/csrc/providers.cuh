@@ -119,6 +119,32 @@ struct FrameRows {             // GSA queries: every token of a frame, group = f
     }
 };
 
+// GSA queries of the LAST layer of a call: rows are read token-major like FrameRows, the result goes straight to the
+// caller's NCHW map (fusion.py:186, the rearrange back) - lanes are consecutive tokens, so a channel's 32 two-byte stores
+// of a warp are one contiguous 64-byte segment.  Saves the tokens -> NCHW pass (a read + a write of the whole map).
+template <typename T>
+struct FrameRowsToNCHW {
+    const T* feat; T* out; int N, C; int64_t rows; FastDiv dN;
+    FrameRowsToNCHW(const T* f, T* o, int N_, int C_, int64_t n) : feat(f), out(o), N(N_), C(C_), rows(n), dN(N_) {}
+    struct R { int64_t off, ooff; int g; };
+    __host__ __device__ uint32_t rows_per_group() const { return dN.d; }
+    __device__ int group_of_row(int64_t r) const { return (int)dN.div((uint32_t)r); }
+    __device__ R locate(int64_t r) const {
+        const uint32_t b = dN.div((uint32_t)r), n = (uint32_t)r - b * (uint32_t)N;
+        return R{r * C, (int64_t)b * C * N + n, (int)b};
+    }
+    __device__ int group(const R& x) const { return x.g; }
+    __device__ float4 load4(const R& x, int c) const { return IO<T>::ld4(feat + x.off + c); }
+    __device__ uint4 raw8(const R& x, int c) const {
+        static_assert(sizeof(T) == 2, "raw8 is the bf16 fast path");
+        return *reinterpret_cast<const uint4*>(feat + x.off + c);
+    }
+    __device__ void store4(const R& x, int c, float4 v) const {
+        T* o = out + x.ooff + (int64_t)c * N;
+        IO<T>::st(o, v.x); IO<T>::st(o + N, v.y); IO<T>::st(o + 2 * (int64_t)N, v.z); IO<T>::st(o + 3 * (int64_t)N, v.w);
+    }
+};
+
 struct SrTokSrc {              // GSA keys/values: fp32 sub-sampled tokens [B][Ns][C]
     const float* tok; int Ns, C; int64_t rows; FastDiv dN;
     SrTokSrc(const float* t, int Ns_, int C_, int64_t n) : tok(t), Ns(Ns_), C(C_), rows(n), dN(Ns_) {}
@@ -326,6 +352,8 @@ int query_tc_lsa(int C, const WindowRows<bf16>& q, const cfp_loftr_w& w, const f
                  cudaStream_t st);
 int query_tc_gsa(int C, const FrameRows<bf16>& q, const cfp_loftr_w& w, const float* kv, const float* ksum,
                  cudaStream_t st);
+int query_tc_gsa_nchw(int C, const FrameRowsToNCHW<bf16>& q, const cfp_loftr_w& w, const float* kv, const float* ksum,
+                      cudaStream_t st);
 int query_tc_dapm(int C, const OutsideRows<bf16>& q, const cfp_loftr_w& w, const float* kv, const float* ksum,
                   cudaStream_t st);
 // attention state on tcgen05; S = rows per group

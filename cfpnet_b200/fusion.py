@@ -111,10 +111,18 @@ class TransformerFusion(nn.Module):
             ox = int(torch.randint(0, self.max_resolution[1] - W + 1, [1]))
         return oy, ox
 
-    def _run_layers(self, packed, pos2, feat0, feat1, mask, B, H, W, D, S, cg, work, ws_bytes, code, st, emb_copy):
-        """The layer list on the token-major map ``feat0`` [B, H*W, D] (in place), current stream."""
+    def _run_layers(self, packed, pos2, feat0, feat1, mask, B, H, W, D, S, cg, work, ws_bytes, code, st, emb_copy,
+                    out_nchw=None) -> bool:
+        """The layer list on the token-major map ``feat0`` [B, H*W, D] (in place), current stream.  With ``out_nchw`` (a
+        contiguous [B, D, H, W] tensor) and an ``image`` layer last, that layer's last epilogue writes the NCHW result
+        itself and True is returned; otherwise the result is in ``feat0`` (False)."""
         emb = feat0.clone() if emb_copy else feat0           # fusion.py:134-136: canvas cut from the first map
-        for w, name in zip(packed, self.layer_names):
+        last = len(self.layer_names) - 1
+        for i, (w, name) in enumerate(zip(packed, self.layer_names)):
+            if name == "image" and i == last and out_nchw is not None:
+                _lib.call("cfp_twins_nchw_fwd", feat0.data_ptr(), out_nchw.data_ptr(), B, H, W, D, C.byref(w), work.data_ptr(),
+                          ws_bytes, code, st)
+                return True
             if name == "image":
                 _lib.call("cfp_twins_fwd", feat0.data_ptr(), B, H, W, D, C.byref(w), work.data_ptr(), ws_bytes, code, st)
             elif name == "hist2image":
@@ -125,6 +133,7 @@ class TransformerFusion(nn.Module):
                 _lib.call("cfp_dapm_fwd", feat0.data_ptr(), B, H, W, D, C.byref(cg), C.byref(dapm_w), work.data_ptr(), ws_bytes,
                           code, st)
                 _lib.call("cfp_lkpm_fwd", feat0.data_ptr(), B, H, W, D, C.byref(lkpm_w), work.data_ptr(), ws_bytes, code, st)
+        return False
 
     def forward_tokens(self, x_tok, x_pitch, B, H, W, feat1, out_tok, out_pitch, out_coff, **kwargs):
         """The same call for a caller that holds its maps channels-last in bf16 (cfpnet_b200.decoder): ``x_tok`` is a
@@ -235,8 +244,9 @@ class TransformerFusion(nn.Module):
             else:
                 _lib.call("cfp_posenc_tokens_fwd", xp.data_ptr(), pos, feat0.data_ptr(), Bp, D, H, W,
                           self.max_resolution[0], self.max_resolution[1], oy, ox, code, st)
-            self._run_layers(packed, pos2, feat0, f1p, mp, Bp, H, W, D, S, cg, work, ws_bytes, code, st, emb_copy)
-            _lib.call("cfp_tokens_to_nchw", feat0.data_ptr(), op.data_ptr(), Bp, D, H, W, code, st)
+            if not self._run_layers(packed, pos2, feat0, f1p, mp, Bp, H, W, D, S, cg, work, ws_bytes, code, st, emb_copy,
+                                    out_nchw=op):
+                _lib.call("cfp_tokens_to_nchw", feat0.data_ptr(), op.data_ptr(), Bp, D, H, W, code, st)
 
         parts = max(1, min(int(self.micro_batches), B))
         with torch.cuda.device(dev):

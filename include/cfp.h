@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define CFP_ABI_VERSION 13
+#define CFP_ABI_VERSION 14
 
 #if defined(__GNUC__)
 #define CFP_API __attribute__((visibility("default")))
@@ -192,6 +192,11 @@ CFP_API int cfp_lkpm_fwd(void *feat0, int B, int H, int W, int C, const cfp_lkpm
  * 160-165): LSA then GSA, 8 heads; in place. */
 CFP_API int cfp_twins_fwd(void *feat0, int B, int H, int W, int C, const cfp_twins_w *w, void *workspace,
                   size_t workspace_bytes, int dtype, void *stream);
+/* The same layer as the LAST layer of a TransformerFusion call: the GSA result is written to the caller's contiguous NCHW
+ * map `out_nchw` (fusion.py:186, the rearrange back to 'b c h w') by the layer's last epilogue instead of going through
+ * feat0 and cfp_tokens_to_nchw; feat0 holds the LSA result afterwards and is scratch. */
+CFP_API int cfp_twins_nchw_fwd(void *feat0, void *out_nchw, int B, int H, int W, int C, const cfp_twins_w *w,
+                       void *workspace, size_t workspace_bytes, int dtype, void *stream);
 
 /* ---- Training step (BASELINE config 5; reference train.py:96-135 with the modules in .train() mode, BatchNorm on
  * batch statistics per replica as under nn.DataParallel, train.py:45).  The reference differentiates its modules with
