@@ -18,7 +18,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CFP_LIB_PATH") or os.path.join(_HERE, "libcfp.so")   # override: debug builds (tools/)
 
 CFP_F32, CFP_BF16 = 0, 1
-ABI_VERSION = 14
+ABI_VERSION = 15
 _fp = C.POINTER(C.c_float)
 
 
@@ -81,6 +81,12 @@ SIGNATURES = {
     "cfp_tr_ln_fwd": (_i, [_p, _p, _p, _p, _i64, _i, C.c_float, _p]),
     "cfp_tr_ln_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i, C.c_float, _p]),
     "cfp_tr_ew": (_i, [_p, _p, _p, _i64, _i, _p]),
+    "cfp_tr_gather_rows": (_i, [_p, _p, _p, _i64, _i, _p]),
+    "cfp_tr_scatter_add_rows": (_i, [_p, _p, _p, _p, _i64, _i64, _i, _p]),
+    "cfp_tr_attn_reduce": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "cfp_tr_attn_apply": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "cfp_tr_head_dot": (_i, [_p, _p, _p, _i64, _i, _i, _i, C.c_float, _p]),
+    "cfp_tr_rowop": (_i, [_p, _p, _p, _p, _i64, _i, _i, _i, _i, _p]),
     "cfp_tr_dwconv": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _p]),
     "cfp_tr_dwconv_wgrad": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "cfp_tr_sumsq": (_i, [_p, _i64, C.c_float, _p, _p]),

@@ -321,7 +321,8 @@ CFP_API int cfp_lkpm_fwd(void* feat0, int B, int H, int W, int C, const cfp_lkpm
     cudaStream_t st = (cudaStream_t)stream;
     void* y = ws + L.tok_a;
     if (dtype == CFP_BF16) {
-        if (w->ksize >= 15) {      // Toeplitz GEMM on the tensor pipe (k_dwconv_tc.cu); its planar output feeds the MLP directly
+        static const int tc_min = getenv("CFP_DW_TC_MIN") ? atoi(getenv("CFP_DW_TC_MIN")) : 15;   // A/B switch
+        if (w->ksize >= tc_min) {  // Toeplitz GEMM on the tensor pipe (k_dwconv_tc.cu); its planar output feeds the MLP directly
             const void* planar = nullptr;
             int pitch = 0;
             if (int e = dwconv_tc(feat0, &planar, &pitch, B, H, W, C, w->ksize, w->dw_toep, w->dw_shift, ws + L.planes, st)) return e;
@@ -405,6 +406,40 @@ CFP_API int cfp_tr_ew(const float* a, const float* b, float* out, int64_t n, int
     begin_call(stream);
     CFP_REQUIRE(a && out, "null pointer");
     return tr_ew(a, b, out, n, op, (cudaStream_t)stream);
+}
+CFP_API int cfp_tr_gather_rows(const float* src, const int* idx, float* out, int64_t n, int C, void* stream) {
+    begin_call(stream);
+    CFP_REQUIRE(src && idx && out && n >= 0, "bad arguments");
+    return tr_gather_rows(src, idx, out, n, C, (cudaStream_t)stream);
+}
+CFP_API int cfp_tr_scatter_add_rows(const float* src, const int* idx, const float* base, float* out, int64_t n, int64_t base_rows,
+                                    int C, void* stream) {
+    begin_call(stream);
+    CFP_REQUIRE(src && idx && base && out && n >= 0 && base_rows > 0 && C > 0, "bad arguments");
+    return tr_scatter_add_rows(src, idx, base, out, n, base_rows, C, (cudaStream_t)stream);
+}
+CFP_API int cfp_tr_attn_reduce(const float* a, const float* b, const float* w, float* kv, float* as, int G, int R, int C, int nh,
+                               void* stream) {
+    begin_call(stream);
+    CFP_REQUIRE(a && b && kv && as, "null pointer");
+    return tr_attn_reduce(a, b, w, kv, as, G, R, C, nh, (cudaStream_t)stream);
+}
+CFP_API int cfp_tr_attn_apply(const float* x, const float* kv, float* out, int G, int R, int C, int nh, int transpose, void* stream) {
+    begin_call(stream);
+    CFP_REQUIRE(x && kv && out, "null pointer");
+    return tr_attn_apply(x, kv, out, G, R, C, nh, transpose, (cudaStream_t)stream);
+}
+CFP_API int cfp_tr_head_dot(const float* a, const float* b, float* out, int64_t rows, int C, int nh, int rows_per_group, float eps,
+                            void* stream) {
+    begin_call(stream);
+    CFP_REQUIRE(a && b && out, "null pointer");
+    return tr_head_dot(a, b, out, rows, C, nh, rows_per_group, eps, (cudaStream_t)stream);
+}
+CFP_API int cfp_tr_rowop(const float* a, const float* s, const float* b, float* out, int64_t rows, int C, int nh, int rows_per_group,
+                         int op, void* stream) {
+    begin_call(stream);
+    CFP_REQUIRE(a && out, "null pointer");
+    return tr_rowop(a, s, b, out, rows, C, nh, rows_per_group, op, (cudaStream_t)stream);
 }
 CFP_API int cfp_tr_dwconv(const float* in, float* out, int B, int H, int W, int C, int ksize, const float* taps_t,
                           const float* shift, int relu, void* stream) {

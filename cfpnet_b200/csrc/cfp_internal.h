@@ -87,6 +87,16 @@ int tr_ln_fwd(const float* x, const float* g, const float* b, float* y, int64_t 
 int tr_ln_bwd(const float* x, const float* g, const float* dy, float* dx, float* dg, float* db, int64_t rows, int C, float eps,
               cudaStream_t st);
 int tr_ew(const float* a, const float* b, float* out, int64_t n, int op, cudaStream_t st);
+// k_train_attn.cu  (row regrouping + linear-attention building blocks of the training step)
+int tr_gather_rows(const float* src, const int* idx, float* out, int64_t n, int C, cudaStream_t st);
+int tr_scatter_add_rows(const float* src, const int* idx, const float* base, float* out, int64_t n, int64_t base_rows, int C,
+                        cudaStream_t st);
+int tr_attn_reduce(const float* A, const float* Bm, const float* w, float* KV, float* As, int G, int R, int C, int nh,
+                   cudaStream_t st);
+int tr_attn_apply(const float* X, const float* KV, float* out, int G, int R, int C, int nh, int transpose, cudaStream_t st);
+int tr_head_dot(const float* a, const float* b, float* out, int64_t rows, int C, int nh, int rpg, float eps, cudaStream_t st);
+int tr_rowop(const float* a, const float* s, const float* b, float* out, int64_t rows, int C, int nh, int rpg, int op,
+             cudaStream_t st);
 int tr_sumsq(const float* x, int64_t n, float scale, float* out, cudaStream_t st);
 int tr_adamw(float* p, const float* g, float* m, float* v, int64_t n, const int64_t* seg_end, const float* seg_lr, int nseg,
              float beta1, float beta2, float eps, float wd, int step, float grad_scale, const float* sumsq, float max_norm,

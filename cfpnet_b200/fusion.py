@@ -179,10 +179,42 @@ class TransformerFusion(nn.Module):
         return out_tok
 
     # ------------------------------------------------------------------ forward
+    def _forward_train(self, x, feat1, **kwargs):
+        """Train mode (BASELINE config 5; reference train.py:96-135 differentiates fusion.py:52-188 with autograd): fp32,
+        BatchNorm on batch statistics, differentiable w.r.t. x, feat1 and every parameter the reference's autograd
+        reaches - cfpnet_b200/train.py (FusionTrainFn) runs the op sequence of cfpnet_b200/train_seq.py on libcfp kernels."""
+        from . import train as T
+        from . import train_seq as TS
+        _lib.require_cuda(x, "x")
+        B, D, H, W = x.shape
+        if D != self.embedding_dim:
+            raise ValueError(f"x has {D} channels, module was built for {self.embedding_dim}")
+        if any(p.dtype != torch.float32 for p in self.parameters()):
+            raise _lib.CfpError("training runs in fp32 (as the reference trains): cast the module with .float()")
+        g = zone_geometry(kwargs["patch_info"], self.max_resolution[1], H, W)
+        if any(n in ("hist2image", "combine1") for n in self.layer_names):
+            check_geometry(g, H, W)
+        if g.interpolate or args.no_skip_inside or not args.change_embedding:
+            raise NotImplementedError("training serves the no-resize zone canvas with change_embedding (the reference's "
+                                      "training geometry); the resize branch / --no_skip_inside are eval-only here")
+        S = feat1.size(2)
+        if feat1.shape[0] != B or feat1.shape[1] != g.zone_num ** 2 or feat1.shape[3] != D or S != self.positional_encodings2.shape[0]:
+            raise ValueError(f"feat1 {tuple(feat1.shape)} does not match B={B}, zones={g.zone_num ** 2}, D={D}")
+        if tuple(kwargs["mask"].shape) != (B, g.zone_num ** 2):
+            raise ValueError(f"mask {tuple(kwargs['mask'].shape)} is not [B={B}, zones={g.zone_num ** 2}]")
+        oy, ox = self.draw_crop(H, W)
+        key = (B, H, W, g, str(x.device))             # the index vectors depend on the shapes and the zone geometry only
+        cache = self.__dict__.setdefault("_train_ix", {})
+        if key not in cache:
+            cache.clear()
+            cache[key] = TS.Indexer(B, H, W, g, self.ws, x.device)
+        zmask = kwargs["mask"].to(device=x.device, dtype=torch.float32).reshape(-1).contiguous()
+        params = [p for _, p in self.named_parameters()]
+        return T.FusionTrainFn.apply(self, x, feat1, zmask, cache[key], oy, ox, *params)
+
     def forward(self, x, feat1, **kwargs):
         if self.training:
-            raise NotImplementedError("libcfp serves eval-mode BatchNorm only (running statistics folded); "
-                                      "the training step is a later row of the scope table")
+            return self._forward_train(x, feat1, **kwargs)
         _lib.require_cuda(x, "x")
         B, D, H, W = x.shape
         if D != self.embedding_dim:

@@ -7,8 +7,10 @@ only sequences them - in the order of the closed-form backward (DESIGN.md sectio
 ``torch.autograd.Function`` wrappers make the modules differentiable drop-ins: ``loss.backward()`` reaches the same
 parameters the reference's autograd reaches, and the parameters the reference never uses keep ``grad is None``.
 
-Built so far (SURVEY.md 8 / VERDICT r1 item 4, the first vertical slice): the histogram encoder (``HistogramEncoder``)
-and LKPM (``Block14``).  The attention layers and the DAPM convs raise in training mode until their backward exists.
+Built (SURVEY.md 8 / VERDICT r1 item 4): the histogram encoder (``HistogramEncoder``), LKPM (``Block14``) and - as a
+sequence of primitive kernels ordered by ``cfpnet_b200/train_seq.py`` (``CudaOps`` / ``FusionTrainFn`` below) - a whole
+``TransformerFusion`` call: hist2image, DAPM (attention + the two 3x3 convs with train-mode BatchNorm), LKPM, LSA, GSA.
+Not served in training: the bilinear-resize branch of the zone canvas (fusion.py:141,146), ``--no_skip_inside``.
 """
 from __future__ import annotations
 
@@ -306,6 +308,160 @@ class LkpmTrainFn(torch.autograd.Function):
         by_id = {id(p): g for p, g in grads.items()}
         pg = tuple(None if id(p) not in by_id else by_id[id(p)].reshape(p.shape) for p in blk.parameters())
         return (None, dx) + pg
+
+
+# ---------------------------------------------------------------------------------------------- TransformerFusion in train mode
+EW_ELU1, EW_NEG_DIV = 6, 7
+_EW_CODES = {"add": EW_ADD, "relu": EW_RELU, "relu_mask": EW_RELU_MASK, "elu1": EW_ELU1, "elu1_grad_mul": EW_ELU1_GRAD,
+             "neg_div": EW_NEG_DIV}
+ROW_MUL, ROW_DIV, ROW_AXPY, ROW_GROUP_ADD, ROW_GROUP_SCALE = range(5)
+
+
+class CudaOps:
+    """The primitive ops ``cfpnet_b200/train_seq.py`` sequences, each one or two libcfp kernels on fp32 token-major
+    ``[rows, C]`` maps (``cfp_tr_*``, include/cfp.h).  Same method names and semantics as the plain-torch stand-in the CPU
+    test of the sequencing uses (tests/torch_ops.py); tests/test_gpu_train_fusion.py holds this class, through the same
+    sequencing, to the reference's own ``.train()`` output and gradients."""
+
+    # ---- dense
+    def linear(self, x, w, bias=None, acc=None):
+        x, w = _f32c(x), _f32c(w)
+        R, K = x.shape
+        N = w.shape[0]
+        y = torch.empty(R, N, device=x.device, dtype=torch.float32) if acc is None else acc
+        _lib.call("cfp_tr_gemm", x.data_ptr(), K, 1, w.data_ptr(), 1, K, y.data_ptr(), N, R, N, K,
+                  _p(None if bias is None else _f32c(bias)), int(acc is not None), _st())
+        return y
+
+    def linear_dx(self, dy, w):
+        return linear_dx(_f32c(dy), _f32c(w))
+
+    def linear_dw(self, dy, x):
+        return linear_dw(_f32c(dy), _f32c(x))
+
+    def colsum(self, x):
+        return colsum(_f32c(x))
+
+    def ln_fwd(self, x, g, b, eps):
+        return ln_fwd(x, _f32c(g), _f32c(b), eps)
+
+    def ln_bwd(self, x, g, dy, eps):
+        return ln_bwd(x, _f32c(g), _f32c(dy), eps)
+
+    def bn_fwd(self, x, bn, relu):
+        return bn_train_fwd(x, bn, relu)
+
+    def bn_bwd(self, dy, x, mean, rstd, bn, relu):
+        return bn_train_bwd(_f32c(dy), x, mean, rstd, bn, relu)
+
+    def ew(self, a, b, op):
+        return ew(_f32c(a), None if b is None else _f32c(b), _EW_CODES[op])
+
+    # ---- linear attention (attention.py:31-49 and its closed-form backward)
+    def attn_reduce(self, A, Bm, w, G, R, nh):
+        Cc = A.shape[1]
+        d = Cc // nh
+        KV = torch.empty(G, nh, d, d, device=A.device, dtype=torch.float32)
+        As = torch.empty(G, Cc, device=A.device, dtype=torch.float32)
+        _lib.call("cfp_tr_attn_reduce", A.data_ptr(), Bm.data_ptr(), _p(w), KV.data_ptr(), As.data_ptr(), G, R, Cc, nh, _st())
+        return KV, As
+
+    def attn_apply(self, X, KV, G, R, nh, transpose):
+        out = torch.empty_like(X)
+        _lib.call("cfp_tr_attn_apply", X.data_ptr(), KV.data_ptr(), out.data_ptr(), G, R, X.shape[1], nh, int(bool(transpose)), _st())
+        return out
+
+    def head_dot(self, a, b, nh, rows_per_group, eps):
+        n, Cc = a.shape
+        out = torch.empty(n, nh, device=a.device, dtype=torch.float32)
+        _lib.call("cfp_tr_head_dot", a.data_ptr(), b.data_ptr(), out.data_ptr(), n, Cc, nh, int(rows_per_group), float(eps), _st())
+        return out
+
+    def _rowop(self, a, s, b, out, nh, rpg, op):
+        n, Cc = a.shape
+        _lib.call("cfp_tr_rowop", a.data_ptr(), _p(s), _p(b), out.data_ptr(), n, Cc, nh, int(rpg), op, _st())
+        return out
+
+    def head_scale(self, a, s, nh, divide):
+        return self._rowop(a, s, None, torch.empty_like(a), nh, 0, ROW_DIV if divide else ROW_MUL)
+
+    def head_axpy(self, out, s, b, nh, rows_per_group):
+        self._rowop(out, s, b, out, nh, rows_per_group, ROW_AXPY)
+
+    def group_add(self, out, b, rows_per_group):
+        self._rowop(out, None, b, out, 1, rows_per_group, ROW_GROUP_ADD)
+
+    def group_scale(self, x, m, rows_per_group):
+        return self._rowop(x, None, _f32c(m), torch.empty_like(x), 1, rows_per_group, ROW_GROUP_SCALE)
+
+    # ---- regrouping
+    def gather_rows(self, src, idx):
+        src = _f32c(src)
+        out = torch.empty(idx.numel(), src.shape[1], device=src.device, dtype=torch.float32)
+        _lib.call("cfp_tr_gather_rows", src.data_ptr(), idx.data_ptr(), out.data_ptr(), idx.numel(), src.shape[1], _st())
+        return out
+
+    def scatter_add_rows(self, src, idx, base):
+        out = torch.empty_like(base)
+        _lib.call("cfp_tr_scatter_add_rows", src.data_ptr(), idx.data_ptr(), base.data_ptr(), out.data_ptr(), idx.numel(),
+                  base.shape[0], base.shape[1], _st())
+        return out
+
+    def zeros_like(self, t):
+        return torch.zeros_like(t)
+
+    def index_mod(self, n, S, device):
+        return (torch.arange(n, dtype=torch.int64) % S).to(torch.int32).to(device)
+
+    # ---- layout
+    def posenc_tokens(self, x, pos, max_res, oy, ox):
+        B, Cc, H, W = x.shape
+        tok = torch.empty(B * H * W, Cc, device=x.device, dtype=torch.float32)
+        _lib.call("cfp_posenc_tokens_fwd", _f32c(x).data_ptr(), _f32c(pos).data_ptr(), tok.data_ptr(), B, Cc, H, W,
+                  int(max_res[0]), int(max_res[1]), int(oy), int(ox), _lib.CFP_F32, _st())
+        return tok
+
+    def nchw_to_tokens(self, x):
+        return _nchw_to_tokens(_f32c(x))
+
+    def tokens_to_nchw(self, t, B, Cc, H, W):
+        return _tokens_to_nchw(t, B, Cc, H, W)
+
+    # ---- LKPM (the GPU-tested sequencing above)
+    def lkpm_fwd(self, blk, x_tok, B, H, W):
+        return lkpm_train_fwd(blk, x_tok, B, H, W)
+
+    def lkpm_bwd(self, blk, saved, d, B, H, W):
+        dx, grads = lkpm_train_bwd(blk, saved, d, B, H, W)
+        names = {id(p): n for n, p in blk.named_parameters()}
+        return dx, {names[id(p)]: g.reshape(p.shape) for p, g in grads.items()}
+
+
+class FusionTrainFn(torch.autograd.Function):
+    """forward(mod, x [B,C,H,W], feat1 [B,Z,S,C], zmask [B*Z] float, indexer, oy, ox, *parameters in
+    mod.named_parameters() order) -> [B,C,H,W]: ``TransformerFusion.forward`` (fusion.py:52-188) in train mode.  Forward
+    and backward are the op sequences of ``train_seq`` run on libcfp kernels; BatchNorm uses batch statistics and updates
+    its running buffers; parameters the reference's autograd never reaches get no gradient."""
+
+    @staticmethod
+    def forward(ctx, mod, x, feat1, zmask, ix, oy, ox, *params):
+        from . import train_seq as TS
+        ops = CudaOps()
+        P = {n: _f32c(p) for n, p in mod.named_parameters()}
+        with torch.cuda.device(x.device):
+            out, saved = TS.fusion_fwd(ops, mod, P, _f32c(x), _f32c(feat1), zmask, ix, oy, ox)
+        ctx.mod, ctx.P, ctx.saved, ctx.zmask, ctx.ix, ctx.crop, ctx.f1shape = mod, P, saved, zmask, ix, (oy, ox), tuple(feat1.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        from . import train_seq as TS
+        mod = ctx.mod
+        with torch.cuda.device(dout.device):
+            dx, dfeat1, grads = TS.fusion_bwd(CudaOps(), mod, ctx.P, ctx.saved, ctx.zmask, ctx.ix, ctx.crop[0], ctx.crop[1],
+                                              _f32c(dout), ctx.f1shape)
+        pg = tuple(None if n not in grads else grads[n].reshape(p.shape) for n, p in mod.named_parameters())
+        return (None, dx, dfeat1, None, None, None, None) + pg
 
 
 # ---------------------------------------------------------------------------------------------- the step around the modules

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define CFP_ABI_VERSION 14
+#define CFP_ABI_VERSION 15
 
 #if defined(__GNUC__)
 #define CFP_API __attribute__((visibility("default")))
@@ -231,8 +231,37 @@ CFP_API int cfp_tr_ln_fwd(const float *x, const float *g, const float *b, float 
 CFP_API int cfp_tr_ln_bwd(const float *x, const float *g, const float *dy, float *dx, float *dg, float *db, int64_t rows,
                           int C, float eps, void *stream);
 /* Elementwise: op 0 out = a + b | 1 out = a * (b > 0) | 2 out = gelu_erf(a) | 3 out = a * gelu_erf'(b) | 4 out = relu(a)
- * | 5 out = a * d/db(elu(b) + 1). */
+ * | 5 out = a * d/db(elu(b) + 1) | 6 out = elu(a) + 1 | 7 out = -a / b. */
 CFP_API int cfp_tr_ew(const float *a, const float *b, float *out, int64_t n, int op, void *stream);
+/* ---- second slice of the training step: the linear-attention layers and the DAPM convolutions of a TransformerFusion
+ * call in train mode (fusion.py:52-188, transformer.py:41-71,89-150,204-248, attention.py:31-49 under autograd in the
+ * reference).  cfpnet_b200/train_seq.py orders these primitives (forward and the closed-form backward); every
+ * regrouping of tokens is a gather / scatter-add over an int32 index vector built once on the host (-1 = a zero row).
+ *
+ * cfp_tr_gather_rows: out[i][:] = idx[i] >= 0 ? src[idx[i]][:] : 0 (zone canvas cells fusion.py:139-141, LSA windows
+ *   transformer.py:94-104, DAPM inside / outside sets transformer.py:214-221, 3x3 conv taps, the sr conv's strided taps).
+ * cfp_tr_scatter_add_rows: out = base (base_rows rows, copied unless out == base); out[idx[i]][:] += src[i][:] - the
+ *   adjoint of the gather and the `feat0[zone_mask] += ...` of fusion.py:157. */
+CFP_API int cfp_tr_gather_rows(const float *src, const int *idx, float *out, int64_t n, int C, void *stream);
+CFP_API int cfp_tr_scatter_add_rows(const float *src, const int *idx, const float *base, float *out, int64_t n,
+                                    int64_t base_rows, int C, void *stream);
+/* Attention state of G groups of R rows, nh heads of d = C / nh channels (attention.py:39-44):
+ *   kv[g][h][i][j] = sum_r a[g][r][h d + i] * b[g][r][h d + j];  as[g][c] = sum_r (w ? w[g][r][h(c)] : 1) * a[g][r][c].
+ * Forward: a = elu(k)+1, b = v.  Backward: a = Q, b = dnum, w = dden (the state's gradient). */
+CFP_API int cfp_tr_attn_reduce(const float *a, const float *b, const float *w, float *kv, float *as, int G, int R, int C,
+                               int nh, void *stream);
+/* out[g][r][h d + o] = sum_k x[g][r][h d + k] * (transpose ? kv[g][h][o][k] : kv[g][h][k][o])  (Q x KV and its adjoints). */
+CFP_API int cfp_tr_attn_apply(const float *x, const float *kv, float *out, int G, int R, int C, int nh, int transpose,
+                              void *stream);
+/* out[row][h] = sum_k a[row][h d + k] * b[brow][h d + k] + eps, brow = rows_per_group ? row / rows_per_group : row
+ * (the normaliser Q . Ksum + eps of attention.py:42; dmsg . msg in the backward). */
+CFP_API int cfp_tr_head_dot(const float *a, const float *b, float *out, int64_t rows, int C, int nh, int rows_per_group,
+                            float eps, void *stream);
+/* Row arithmetic with a per-(row, head) operand s [rows][nh] or a per-group operand b indexed by row / rows_per_group:
+ * op 0 out = a * s | 1 out = a / s | 2 out = a + s * b[group][c] | 3 out = a + b[group][c] | 4 out = a * b[group]
+ * (b a vector: the zone mask of fusion.py:144).  out may alias a. */
+CFP_API int cfp_tr_rowop(const float *a, const float *s, const float *b, float *out, int64_t rows, int C, int nh,
+                         int rows_per_group, int op, void *stream);
 /* k x k depthwise conv on a token-major map, out = conv(in) + shift[c] (ReLU when relu != 0): Block14.dwconv2 in train
  * mode (convnext.py:45; shift = the conv bias) and, with the taps flipped in both axes and shift = 0, its input
  * gradient.  taps_t [k*k][C]. */
