@@ -732,22 +732,22 @@ def run_aux(a):
 
 # ---------------------------------------------------------------------------------- training step (BASELINE.json configs[4])
 def run_train(a):
-    """--workload train_b32: the training step of the part of the path whose train-mode forward + backward exists as
-    CUDA (histogram encoder + the LKPM block of each decoder level; the attention layers and DAPM convs are not built
-    yet - DESIGN.md section 8), 32 frames per GPU, fp32 as the reference trains (train.py:96-135):
+    """--workload train_b32: the training step of the path (BASELINE.json configs[4]; reference train.py:96-135) - the
+    histogram encoder and the three TransformerFusion calls (hist2image, DAPM, LKPM, LSA, GSA; the encoder's outputs feed
+    the fusion calls, so the backward runs through both) in .train() mode, 32 frames per GPU, fp32 as the reference trains:
 
         zero_grad -> forward (BatchNorm on per-replica batch statistics) -> backward -> NCCL all-reduce of the flat
         gradient bucket -> clip_grad_norm_(0.1) -> AdamW
 
+    Every op of the forward and of the backward is a libcfp kernel (cfp_tr_*; cfpnet_b200/train.py sequences them).
     `value` = frames/s of that step with inputs resident in HBM; `e2e` = the same with the step's inputs copied from
     pinned host memory and the gradient norm read back.  `collective` reports the all-reduce inside the step (bytes,
-    CUDA-event time, share of the step, bus bandwidth) and, separately, the same NCCL all-reduce on a bucket of the
-    size the COMPLETE path's gradients have (26.6 MB fp32)."""
+    CUDA-event time, share of the step, bus bandwidth)."""
     import torch.distributed as dist
     import cfpnet_b200
     from cfpnet_b200 import _lib
     from cfpnet_b200.build import build
-    from cfpnet_b200.layers import Block14
+    from cfpnet_b200.config import args as cfg
     from cfpnet_b200.train import FlatTrainer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -763,48 +763,48 @@ def run_train(a):
     B = a.batch
     enc = cfpnet_b200.HistogramEncoder()
     enc.load_state_dict(synth.synthetic_state_dict({k: v.shape for k, v in enc.state_dict().items()}, 0))
-    blocks = {}
-    for lv in (3, 2, 1):
-        C, _, _, k = synth.LEVELS[lv]
-        blk = Block14(C, large_kernel=k)
-        blk.load_state_dict(synth.synthetic_state_dict({kk: v.shape for kk, v in blk.state_dict().items()}, 3))
-        blocks[lv] = blk
-    mods = [enc.to(dev).train()] + [blocks[lv].to(dev).train() for lv in (3, 2, 1)]
+    fusion = {}
+    saved_layers = list(cfg.attention_layer)
+    cfg.attention_layer = list(synth.COMBINE1_LAYERS)
+    try:
+        for lv in (3, 2, 1):
+            C, _, max_res, k = synth.LEVELS[lv]
+            m = cfpnet_b200.TransformerFusion(C, list(max_res), large_kernel=k, patch_size=640 // max_res[1])
+            m.load_state_dict(synth.synthetic_state_dict({kk: v.shape for kk, v in m.state_dict().items()}, lv))
+            fusion[lv] = m
+    finally:
+        cfg.attention_layer = saved_layers
+    mods = [enc.to(dev).train()] + [fusion[lv].to(dev).train() for lv in (3, 2, 1)]
     trainer = FlatTrainer(mods, lr=1e-4, weight_decay=0.1, max_norm=0.1)
 
     NSETS = 3
     host_sets, dev_sets = [], []
     for s_ in range(NSETS):
         inp = synth.make_inputs(GEOMETRY, B, seed=300 + rank * NSETS + s_)
-        h = {"hist": inp["hist_data"].unsqueeze(-1).contiguous().pin_memory()}
+        h = {"hist": inp["hist_data"].unsqueeze(-1).contiguous().pin_memory(), "mask": inp["mask"].to(torch.uint8).contiguous().pin_memory()}
         for lv in (3, 2, 1):
             h[f"x{lv}"] = inp[f"x{lv}"].float().contiguous().pin_memory()
         host_sets.append(h)
         dev_sets.append({k: v.to(dev) for k, v in h.items()})
+        patch_info, rect_data = inp["patch_info"], inp["rect_data"]      # the same zone layout in every set
     h2d = sum(v.numel() * v.element_size() for v in host_sets[0].values())
     g = torch.Generator().manual_seed(11 + rank)
-    # cotangents of the slice's outputs (what the rest of the network would send back), scaled like a mean loss
+    # cotangents of the three fused maps (what the decoder behind them would send back), scaled like a mean loss
     cts = {}
     for lv in (3, 2, 1):
         x = host_sets[0][f"x{lv}"]
         cts[f"x{lv}"] = (torch.randn(x.shape, generator=g) / x.numel()).to(dev)
-    for c_ in (32, 64, 128):
-        cts[f"h{c_}"] = (torch.randn(B, 64, 16, c_, generator=g) / (B * 64 * 16 * c_)).to(dev)
 
     ev_a = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
 
     def step(d, timed_exchange=False):
         trainer.zero_grad()
-        hist = d["hist"]
+        feats = dict(zip((32, 64, 128), enc(d["hist"])))   # differentiable: the fusion calls' feat1 gradients flow back into the encoder
         outs, grads = [], []
-        ho = enc(hist)
-        for o, c_ in zip(ho, (32, 64, 128)):
-            outs.append(o)
-            grads.append(cts[f"h{c_}"])
         for lv in (3, 2, 1):
-            x = d[f"x{lv}"].requires_grad_(True)            # the decoder upstream needs dx: the full backward runs
+            x = d[f"x{lv}"].requires_grad_(True)            # the image branch upstream needs dx: the full backward runs
             x.grad = None
-            outs.append(blocks[lv](x))
+            outs.append(fusion[lv](x, feats[synth.LEVELS[lv][0]], mask=d["mask"], patch_info=patch_info, rect_data=rect_data, rgb=None))
             grads.append(cts[f"x{lv}"])
         torch.autograd.backward(outs, grads)
         if trainer.flat_g is None:
@@ -929,12 +929,11 @@ def run_train(a):
     nparams = int(trainer.flat_g.numel())
     bus = lambda nbytes, ms: (2.0 * (world - 1) / world * nbytes / (ms * 1e-3) / 1e9) if world > 1 and ms else None   # noqa: E731
     line = {
-        "metric": "CFP path training step (hist encoder + LKPM blocks) frames/s @416x544, 8x8 zones", "value": frames / (ms_total * 1e-3),
+        "metric": "CFP path training step (hist encoder + three TransformerFusion calls) frames/s @416x544, 8x8 zones", "value": frames / (ms_total * 1e-3),
         "unit": "frames/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_total / a.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "training step of the CUDA-built part of the path: HistogramEncoder + Block14 (LKPM) of the three "
-                               f"decoder levels in .train() mode, fp32, {B} frames per GPU, 416x544 (BASELINE.json configs[4]; "
-                               "attention layers / DAPM convs have no backward kernels yet)",
+        "config": {"workload": "training step of the path: HistogramEncoder + cross_atten3/2/1 (combine1 layer list) in .train() mode, "
+                               f"forward + backward + all-reduce + clip + AdamW, fp32, {B} frames per GPU, 416x544 (BASELINE.json configs[4])",
                    "per_gpu_batch": B, "global_batch": B * world, "optimizer": "clip_grad_norm_(0.1) + AdamW on the flat bucket",
                    "l2_policy": "inputs rotate over 3 distinct batches; activations of a step (> 1 GB) exceed the 126 MB L2"},
         "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
