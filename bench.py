@@ -187,7 +187,7 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------------------------- reference arm
-def oracle_modules():
+def oracle_modules(kind="combine1"):
     """The CPU arm's weights: shapes from the dump of the REFERENCE modules' own state_dict
     (tests/golden/state_dict_keys.json) - nothing of the product (modules, kernels, library) is on this path."""
     from oracle import cfp_oracle as O
@@ -195,22 +195,22 @@ def oracle_modules():
         keys = json.load(fh)
     sds = {"hist_encoder": synth.synthetic_state_dict(keys["hist_encoder"], 0)}
     for lv, name in ((3, "cross_atten3"), (2, "cross_atten2"), (1, "cross_atten1")):
-        sds[name] = synth.synthetic_state_dict(keys[f"fusion_combine1_L{lv}"], lv)
+        sds[name] = synth.synthetic_state_dict(keys[f"fusion_{kind}_L{lv}"], lv)
     return O, sds
 
 
-def time_cpu_frames(n_frames, steps, warmup, seed=1):
+def time_cpu_frames(n_frames, steps, warmup, seed=1, geometry=GEOMETRY, layers=synth.COMBINE1_LAYERS):
     """Time the oracle port (fp32, all host threads) on `n_frames`-frame batches."""
-    O, sds = oracle_modules()
+    O, sds = oracle_modules("combine1" if "combine1" in layers else "baseline")
     torch.set_num_threads(os.cpu_count() or 1)
-    inp = synth.make_inputs(GEOMETRY, n_frames, seed=seed)
+    inp = synth.make_inputs(geometry, n_frames, seed=seed)
     xs = [inp["x3"], inp["x2"], inp["x1"]]
     times = []
     with torch.no_grad():
         for i in range(warmup + steps):
             torch.manual_seed(2)
             t0 = time.perf_counter()
-            O.fusion_path(sds, synth.COMBINE1_LAYERS, xs, inp["hist_data"], inp["mask"], inp["patch_info"])
+            O.fusion_path(sds, layers, xs, inp["hist_data"], inp["mask"], inp["patch_info"])
             dt = time.perf_counter() - t0
             if i >= warmup:
                 times.append(dt)
@@ -712,21 +712,61 @@ def run_aux(a):
                                "layers": list(layers), "median_ms": 1e3 * statistics.median(dts), "min_ms": 1e3 * min(dts),
                                "mode": "CUDA-graph replay (FusionPath.make_graphed)", "eager_ms": ms_eager}}
         else:
-            for i in range(max(a.warmup, 3)):
-                step(i)
-            torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for i in range(a.steps):
-                step(i)
-            e1.record()
-            torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1) / a.steps
+
+            def timed(fn):
+                for i in range(max(a.warmup, 3)):
+                    fn(i)
+                torch.cuda.synchronize()
+                e0.record()
+                for i in range(a.steps):
+                    fn(i)
+                e1.record()
+                torch.cuda.synchronize()
+                return e0.elapsed_time(e1) / a.steps
+
+            ms_eager = timed(step)            # ~90 host-side launches per step: bound by the launching thread, +-20 % run to run
+            d0 = sets[0]
+            run = path.make_graphed(d0["x3"], d0["x2"], d0["x1"], d0["hist_data"], d0["mask"], patch_info)
+
+            def replay(i):                    # positional-encoding crops drawn per replay, read from device memory
+                d = sets[i % 3]
+                shard.seed_posenc(i)
+                return run(d["x3"], d["x2"], d["x1"], d["hist_data"], d["mask"])
+
+            ms = timed(replay)
             line = {"metric": "DELTAR-style fusion (no cross-zone propagation) frames/s @416x544, 8x8 zones, batch 16", "value": B * 1e3 / ms,
                     "unit": "frames/s", "higher_is_better": True, "n_gpus": 1, "steps": a.steps, "warmup": max(a.warmup, 3),
                     "ms_per_step": ms, "dtype": a.dtype, "data": "synthetic", "vs_baseline": None,
                     "config": {"workload": "DELTAR-style baseline layer list (..._10x config), 416x544, batch 16, 1 GPU "
-                                           "(BASELINE.json configs[1])", "layers": list(layers), "per_gpu_batch": B}}
+                                           "(BASELINE.json configs[1])", "layers": list(layers), "per_gpu_batch": B,
+                               "mode": "CUDA-graph replay (FusionPath.make_graphed)", "eager_ms": ms_eager}}
+        # per-kernel breakdown (CUDA events on the launch stream, levels on one stream, eager launches) and its roofline
+        from cfpnet_b200 import _lib
+        n_prof = 20 if latency else a.steps
+        torch.cuda.synchronize()
+        path.concurrent_levels = False
+        _lib.profile_start()
+        for i in range(n_prof):
+            step(i)
+        prof = _lib.profile_stop()
+    peaks = load_peaks()
+    es = 2 if dtype == torch.bfloat16 else 4
+    roof, kernels = roofline_from_profile(prof, n_prof, B, es, peaks)
+    if latency:
+        # kernel_work() holds the algorithmic bytes / flops of the 416x544 shapes: at 480x640 only the time shares are reported
+        roof = {"kernel": roof["kernel"], "avg_launch_ms": roof["avg_launch_ms"], "bound": roof["bound"], "achieved": None,
+                "peak": roof["peak"], "unit": roof["unit"], "frac": None, "traffic": None,
+                "note": "batch-1 launches are latency-bound single waves; per-kernel time shares in `kernels`"}
+        kernels = {k: {kk: vv for kk, vv in v.items() if kk in ("launches_per_step", "ms_per_step", "share")} for k, v in kernels.items()}
+    line["roofline"], line["kernels"] = roof, kernels
+    if not a.no_cpu:
+        cores = os.cpu_count() or 1
+        t = time_cpu_frames(1, 6, 2, geometry=geom, layers=tuple(layers))
+        med = statistics.median(t)
+        line["cpu_baseline"] = ({"value": med * 1e3, "unit": "ms"} if latency else {"value": 1.0 / med, "unit": "frames/s"})
+        line["cpu_baseline"].update({"cores": cores, "kind": "port",
+                                     "sample": "1 frame/step, 2 warm-up + 6 timed, median, fp32 torch CPU ops on all host threads"})
     print(json.dumps(line), flush=True)
 
 

@@ -47,8 +47,11 @@ int sm_count() {
 }
 // Launch accounting and the optional event profiler (cfp_profile_*), process-wide: a training step enqueues its forward
 // from the caller's thread and its backward from autograd's device thread, and both belong in one count / one profile.
-// When profiling is on, one CUDA event is recorded on the call's stream after every kernel launch, so a kernel's time
-// is the gap to the previous event (meaningful when the profiled calls share one in-order stream).
+// When profiling is on, one CUDA event is recorded on the call's stream after every kernel launch and one at the start of
+// every API call; a kernel's time is the gap to the previous event (meaningful when the profiled calls share one in-order
+// stream).  The call-start marker keeps the time the device idles between two calls of a launch-bound caller (small
+// batches through Python: ~20 us per call) out of the next kernel's figure; on a saturated stream it fires right behind
+// the previous kernel and changes nothing.
 struct ProfileState {
     std::mutex mu;
     std::atomic<int64_t> launches{0};
@@ -65,11 +68,11 @@ static void begin_call(void* stream) {
     tl_stream = (cudaStream_t)stream;
     ProfileState& p = pstate();
     if (p.profiling.load(std::memory_order_relaxed)) {
+        cudaEvent_t ev;
+        cudaEventCreate(&ev);
+        cudaEventRecord(ev, tl_stream);
         std::lock_guard<std::mutex> lk(p.mu);
-        if (!p.first) {
-            cudaEventCreate(&p.first);
-            cudaEventRecord(p.first, tl_stream);
-        }
+        p.events.emplace_back(nullptr, ev);          // marker: not a kernel
     }
 }
 int check_launch(const char* what) {
@@ -582,6 +585,7 @@ CFP_API int cfp_profile_stop(char* out, size_t cap) {
     cudaEvent_t prev = t.first;
     for (auto& e : t.events) {
         cudaEventSynchronize(e.second);
+        if (!e.first) { prev = e.second; continue; }  // start of an API call
         float ms = 0.f;
         if (prev) cudaEventElapsedTime(&ms, prev, e.second);
         prev = e.second;

@@ -39,9 +39,9 @@ int tr_gather_rows(const float* src, const int* idx, float* out, int64_t n, int 
     return check_launch("tr_gather_rows");
 }
 
-// out[idx[i]][:] += src[i][:] for idx[i] >= 0 (out already holds the base map).  The index vectors of the path never
-// name a row twice within one call (a cell belongs to one zone / window / tap position), so the atomics do not race
-// and the result does not depend on the order; they are kept for callers that do repeat rows.
+// out[idx[i]][:] += src[i][:] for idx[i] >= 0 (out already holds the base map).  Zone / window / inside-outside / sr-conv
+// index vectors name a row at most once per call; the adjoint of the 3x3 im2col gather names every pixel nine times (a
+// pixel collects from its nine neighbours), so the sums are fp32 atomics and their rounding depends on the arrival order.
 __global__ void __launch_bounds__(256) tr_scatter_add_rows_kernel(const float* __restrict__ src, const int* __restrict__ idx,
                                                                   float* __restrict__ out, int64_t n, int C) {
     const int64_t total = n * C;

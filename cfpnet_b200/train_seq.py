@@ -56,6 +56,8 @@ class Indexer:
                 y, x = yy + dy - 1, xx + dx - 1
                 ok = (y >= 0) & (y < H) & (x >= 0) & (x < W)
                 self.conv_tap.append(finish(torch.where(ok, y * W + x, torch.full_like(y, -1)).reshape(1, -1).repeat(B, 1)))
+        # the nine taps of every output pixel side by side ([rows][9], row-major): one gather builds the im2col matrix
+        self.conv_col = torch.stack(self.conv_tap, dim=1).reshape(-1).contiguous()
         # LSA windows over the zero-padded map (transformer.py:94-104)
         self.ws = ws
         if ws:
@@ -76,6 +78,7 @@ class Indexer:
             self.Ns = nsy * nsx
             sy_, sx_ = torch.meshgrid(torch.arange(nsy), torch.arange(nsx), indexing="ij")
             self.sr_tap = [finish(((sy_ * ws + dy) * W + sx_ * ws + dx).reshape(1, -1).repeat(B, 1)) for dy in range(ws) for dx in range(ws)]
+            self.sr_col = torch.stack(self.sr_tap, dim=1).reshape(-1).contiguous()          # [B*Ns][ws*ws]
         # zone geometry (fusion.py:67-84,104; no resize branch in training)
         self.g = g
         if g is not None:
@@ -182,17 +185,18 @@ def lsa_bwd(ops, P, ls, ix: Indexer, dout):
     return ops.gather_rows(ops.ew(dq, dsrc, "add"), ix.win_inv), _pre("encoder_layer.", g)
 
 
-def _sr_weights(P, ws):
-    w = P["sr.weight"]                                                       # [C, C, ws, ws]
-    return [w[:, :, dy, dx].contiguous() for dy in range(ws) for dx in range(ws)]
+def _sr_matrix(P):
+    """sr.weight [C, C, ws, ws] -> [C, ws*ws*C] with the columns ordered (tap, cin) like the im2col rows below."""
+    w = P["sr.weight"]
+    return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous()
 
 
 def gsa_fwd(ops, P, x, ix: Indexer):
-    taps = _sr_weights(P, ix.ws)
-    s0 = None
-    for t, wt in enumerate(taps):
-        rows = ops.gather_rows(x, ix.sr_tap[t])
-        s0 = ops.linear(rows, wt, P["sr.bias"]) if s0 is None else ops.linear(rows, wt, acc=s0)
+    """transformer.py:138-150.  The kernel = stride = ws sub-sampling conv is ONE gather (the ws*ws taps of every
+    sub-sampled token side by side: an im2col matrix [B*Ns, ws*ws*C]) and ONE product with the [C, ws*ws*C] weight."""
+    C = x.shape[1]
+    col = ops.gather_rows(x, ix.sr_col).view(ix.B * ix.Ns, -1)
+    s0 = ops.linear(col, _sr_matrix(P), P["sr.bias"])
     s1 = ops.ln_fwd(s0, P["norm.weight"], P["norm.bias"], LN_EPS)
     out, ls = loftr_fwd(ops, sub(P, "encoder_layer."), x, s1, ix.B, ix.N, ix.Ns, 8)
     return out, (ls, s0, x)
@@ -204,38 +208,39 @@ def gsa_bwd(ops, P, saved, ix: Indexer, dout):
     grads = _pre("encoder_layer.", g)
     ds0, grads["norm.weight"], grads["norm.bias"] = ops.ln_bwd(s0, P["norm.weight"], ds1, LN_EPS)
     grads["sr.bias"] = ops.colsum(ds0)
-    ws = ix.ws
-    gw = []
-    for t, wt in enumerate(_sr_weights(P, ws)):
-        gw.append(ops.linear_dw(ds0, ops.gather_rows(x, ix.sr_tap[t])))
-        dx = ops.scatter_add_rows(ops.linear_dx(ds0, wt), ix.sr_tap[t], dx)
-    C = x.shape[1]
-    grads["sr.weight"] = torch.stack(gw, dim=-1).view(C, C, ws, ws)
-    return dx, grads
+    C, ws = x.shape[1], ix.ws
+    col = ops.gather_rows(x, ix.sr_col).view(ix.B * ix.Ns, -1)                      # recomputed, not kept
+    grads["sr.weight"] = ops.linear_dw(ds0, col).view(C, ws, ws, C).permute(0, 3, 1, 2).contiguous()
+    dcol = ops.linear_dx(ds0, _sr_matrix(P)).view(-1, C)                           # [B*Ns*ws*ws, C]: the windows do not overlap
+    return ops.scatter_add_rows(dcol, ix.sr_col, dx), grads
+
+
+def _conv_matrix(w):
+    """[Cout, Cin, 3, 3] -> [Cout, 9*Cin], columns ordered (tap, cin)."""
+    return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous()
 
 
 def _conv3x3(ops, srcs, weights, ix: Indexer):
-    """sum over taps and sources of gather(src, tap) @ w[:, :, tap]^T;  weights[i] [Cout, Cin_i, 3, 3]."""
+    """3x3 conv, zero padding 1, of the concatenated sources: per source ONE gather (the nine taps of every pixel side by
+    side, [rows, 9*Cin]) and ONE product with the [Cout, 9*Cin] weight;  weights[i] [Cout, Cin_i, 3, 3]."""
     out = None
-    for t in range(9):
-        for s_, w in zip(srcs, weights):
-            rows = ops.gather_rows(s_, ix.conv_tap[t])
-            wt = w[:, :, t // 3, t % 3].contiguous()
-            out = ops.linear(rows, wt) if out is None else ops.linear(rows, wt, acc=out)
+    for s_, w in zip(srcs, weights):
+        col = ops.gather_rows(s_, ix.conv_col).view(s_.shape[0], -1)
+        out = ops.linear(col, _conv_matrix(w)) if out is None else ops.linear(col, _conv_matrix(w), acc=out)
     return out
 
 
 def _conv3x3_bwd(ops, srcs, weights, ix: Indexer, dy):
-    """Returns ([d src_i], [d weights_i])."""
-    dsrc = [None] * len(srcs)
-    dws = [[] for _ in srcs]
-    for t in range(9):
-        opp = 8 - t                                             # the mirrored tap: dsrc[p] += (dy w_t)[p - offset_t]
-        for i, (s_, w) in enumerate(zip(srcs, weights)):
-            dws[i].append(ops.linear_dw(dy, ops.gather_rows(s_, ix.conv_tap[t])))
-            contrib = ops.gather_rows(ops.linear_dx(dy, w[:, :, t // 3, t % 3].contiguous()), ix.conv_tap[opp])
-            dsrc[i] = contrib if dsrc[i] is None else ops.ew(dsrc[i], contrib, "add")
-    return dsrc, [torch.stack(d, dim=-1).view(d[0].shape[0], d[0].shape[1], 3, 3) for d in dws]
+    """Returns ([d src_i], [d weights_i]).  dW = dy^T x im2col (recomputed); d src = the adjoint of the im2col gather
+    (scatter-add of dy x W over the same index matrix: a pixel collects from its nine neighbours)."""
+    dsrc, dws = [], []
+    for s_, w in zip(srcs, weights):
+        cin = w.shape[1]
+        col = ops.gather_rows(s_, ix.conv_col).view(s_.shape[0], -1)
+        dws.append(ops.linear_dw(dy, col).view(w.shape[0], 3, 3, cin).permute(0, 3, 1, 2).contiguous())
+        dcol = ops.linear_dx(dy, _conv_matrix(w)).view(-1, cin)
+        dsrc.append(ops.scatter_add_rows(dcol, ix.conv_col, ops.zeros_like(s_)))
+    return dsrc, dws
 
 
 def dapm_fwd(ops, P, bn1, bn2, feat, ix: Indexer):
