@@ -228,16 +228,39 @@ struct ZonePatchRows {         // hist2image queries: cells of the zone canvas, 
                   int tzh_, int tzw_, int interp, int assign_, int64_t n)
         : feat0(f), emb(e), canvas(cv), mask(m), H(H_), W(W_), C(C_), zn(zn_), p1(p1_), p2(p2_), sy_wo(sy), sx_wo(sx),
           tzh(tzh_), tzw(tzw_), interpolate(interp), assign(assign_), rows(n), dP(p1_ * p2_), dZ(zn_ * zn_), dZn(zn_), dP2(p2_) {}
-    struct R { int b, cy, cx, g; bool valid; };
+    // o / w: resize branch only - element offsets into emb of the four canvas cells a resized cell blends (-1: outside the
+    // map, reads as zero) and their bilinear weights, computed ONCE per row in locate().  (Recomputed inside every
+    // 4-channel load they made the unrolled stage / last-epilogue code of the chain 14.5 k SASS lines; at batch 1 - the
+    // 480x640 latency workload, one wave, cold instruction cache - fetching them was most of the launch.  As an
+    // out-of-line call the gather was slower still: 0.40 vs 0.26 ms.)
+    struct R { int b, cy, cx, g; bool valid; int64_t o[4]; float w[4]; };
     __host__ __device__ uint32_t rows_per_group() const { return dP.d; }
     __device__ int group_of_row(int64_t r) const { return (int)dP.div((uint32_t)r); }
+    __device__ int64_t canvas_off(int b, int ty, int tx) const {
+        const int y = sy_wo + ty, x = sx_wo + tx;
+        if (y < 0 || y >= H || x < 0 || x >= W) return -1;
+        return ((int64_t)b * H * W + (int64_t)y * W + x) * C;
+    }
     __device__ R locate(int64_t r) const {
         uint32_t g, l, b, z, zy, zx, py, px;
         dP.divmod((uint32_t)r, g, l);
         dZ.divmod(g, b, z);
         dZn.divmod(z, zy, zx);
         dP2.divmod(l, py, px);
-        return R{(int)b, (int)(zy * p1 + py), (int)(zx * p2 + px), (int)g, mask[g] != 0};
+        R q{(int)b, (int)(zy * p1 + py), (int)(zx * p2 + px), (int)g, mask[g] != 0, {0, 0, 0, 0}, {0.f, 0.f, 0.f, 0.f}};
+        if (!kFast && interpolate) {
+            // F.interpolate(bilinear, align_corners=True) from [tzh,tzw] to [zn*p1, zn*p2]  (fusion.py:141)
+            const int oh = zn * p1, ow = zn * p2;
+            const float fy = oh > 1 ? q.cy * ((float)(tzh - 1) / (float)(oh - 1)) : 0.f;
+            const float fx = ow > 1 ? q.cx * ((float)(tzw - 1) / (float)(ow - 1)) : 0.f;
+            const int y0 = (int)fy, x0 = (int)fx;
+            const int y1 = min(y0 + 1, tzh - 1), x1 = min(x0 + 1, tzw - 1);
+            const float ly = fy - y0, lx = fx - x0;
+            q.o[0] = canvas_off(q.b, y0, x0); q.o[1] = canvas_off(q.b, y0, x1);
+            q.o[2] = canvas_off(q.b, y1, x0); q.o[3] = canvas_off(q.b, y1, x1);
+            q.w[0] = (1.f - ly) * (1.f - lx); q.w[1] = (1.f - ly) * lx; q.w[2] = ly * (1.f - lx); q.w[3] = ly * lx;
+        }
+        return q;
     }
     __device__ int group(const R& x) const { return x.g; }
     // value of the zero-padded map at canvas cell (ty,tx) of the un-resized canvas
@@ -260,17 +283,11 @@ struct ZonePatchRows {         // hist2image queries: cells of the zone canvas, 
         return pack8_bf16_fwd(v8);
     }
     __device__ float4 load4(const R& q, int c) const {
-        if (!interpolate) return canvas_at(q.b, q.cy, q.cx, c);
-        // F.interpolate(bilinear, align_corners=True) from [tzh,tzw] to [zn*p1, zn*p2]  (fusion.py:141)
-        const int oh = zn * p1, ow = zn * p2;
-        float fy = oh > 1 ? q.cy * ((float)(tzh - 1) / (float)(oh - 1)) : 0.f;
-        float fx = ow > 1 ? q.cx * ((float)(tzw - 1) / (float)(ow - 1)) : 0.f;
-        int y0 = (int)fy, x0 = (int)fx;
-        int y1 = min(y0 + 1, tzh - 1), x1 = min(x0 + 1, tzw - 1);
-        float ly = fy - y0, lx = fx - x0;
-        float4 a = canvas_at(q.b, y0, x0, c), bq = canvas_at(q.b, y0, x1, c);
-        float4 cq = canvas_at(q.b, y1, x0, c), d = canvas_at(q.b, y1, x1, c);
-        float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+        if (kFast || !interpolate) return canvas_at(q.b, q.cy, q.cx, c);
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 a = q.o[0] >= 0 ? IO<T>::ld4(emb + q.o[0] + c) : z4, bq = q.o[1] >= 0 ? IO<T>::ld4(emb + q.o[1] + c) : z4;
+        const float4 cq = q.o[2] >= 0 ? IO<T>::ld4(emb + q.o[2] + c) : z4, d = q.o[3] >= 0 ? IO<T>::ld4(emb + q.o[3] + c) : z4;
+        const float w00 = q.w[0], w01 = q.w[1], w10 = q.w[2], w11 = q.w[3];
         return make_float4(w00 * a.x + w01 * bq.x + w10 * cq.x + w11 * d.x,
                            w00 * a.y + w01 * bq.y + w10 * cq.y + w11 * d.y,
                            w00 * a.z + w01 * bq.z + w10 * cq.z + w11 * d.z,
