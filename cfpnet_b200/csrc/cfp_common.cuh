@@ -58,7 +58,11 @@ template <> struct IO<bf16> {
 
 // ---------------------------------------------------------------- small math
 __device__ __forceinline__ float elu1(float x) {          // elu(x)+1, attention.py:10-11
-    return x > 0.f ? x + 1.f : __expf(x);
+    // branch-free: written as `x > 0 ? x + 1 : __expf(x)` ptxas put a divergent branch (BSSY / BSYNC pair) around every
+    // exp - 116 of them in a C = 128 kv_state epilogue, which made that epilogue 6 us where the same walk with a relu
+    // takes 1 us.  The exponent's argument is clamped so that the unused lane of the select cannot overflow.
+    const float e = __expf(fminf(x, 0.f));
+    return x > 0.f ? x + 1.f : e;
 }
 __device__ __forceinline__ float gelu_erf(float x) {      // nn.GELU() default (erf form)
     return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));

@@ -140,3 +140,35 @@ def test_micro_batched_forward_equals_whole_batch(parts):
             outs.append(m(inp["x3"].to(dev), f128, mask=inp["mask"].to(dev), patch_info=inp["patch_info"], rect_data=None, rgb=None).float().cpu())
     torch.cuda.synchronize()
     assert rel_l2(outs[1], outs[0]) <= 1e-5
+
+
+@pytest.mark.parametrize("level,dtype", [(3, torch.bfloat16), (2, torch.bfloat16), (1, torch.bfloat16), (3, torch.float32)])
+def test_last_layer_nchw_epilogue_equals_layer_then_transpose(level, dtype):
+    """cfp_twins_nchw_fwd (the GSA chain's last epilogue stores the caller's NCHW map) against cfp_twins_fwd followed by
+    cfp_tokens_to_nchw on the same input: the same arithmetic, only the store differs.  The LSA state of the bf16 engine is
+    accumulated with fp32 atomics (windows straddle tiles), so two runs agree to rounding, not bit for bit: 2e-3 rel-L2
+    (bf16 output resolution 4e-3); the fp32 engine is deterministic here."""
+    m, _ = module_for(level)
+    m = m.to(dtype)
+    C = m.embedding_dim
+    H, W = synth.level_hw("G416", level)
+    B = 3
+    feat0 = (torch.randn(B, H * W, C, generator=torch.Generator().manual_seed(5)) * 0.5).to(dtype).to(DEV)
+    two_step, _ = layer_call(m, "twins", 2, feat0, level=level)
+    code = _lib.dtype_code(dtype)
+    want = torch.empty(B, C, H, W, device=DEV, dtype=dtype)
+    _lib.call("cfp_tokens_to_nchw", two_step.data_ptr(), want.data_ptr(), B, C, H, W, code, _lib.stream_ptr())
+    packed, _pos, _pos2, _keep = m._cache.get(m, m._pack)
+    lib = _lib.load()
+    nbytes = lib.cfp_workspace_bytes(B, H, W, C, m.ws, m.large_kernel, code, None)
+    work = torch.empty(nbytes, device=DEV, dtype=torch.uint8)
+    x = feat0.clone()
+    got = torch.full((B, C, H, W), float("nan"), device=DEV, dtype=dtype)
+    _lib.call("cfp_twins_nchw_fwd", x.data_ptr(), got.data_ptr(), B, H, W, C, ctypes.byref(packed[2]), work.data_ptr(), nbytes, code,
+              _lib.stream_ptr())
+    torch.cuda.synchronize()
+    assert torch.isfinite(got.float()).all()
+    assert rel_l2(got.float(), want.float()) <= (2e-3 if dtype == torch.bfloat16 else 1e-6)
+    with pytest.raises(_lib.CfpError):                      # the result map must not alias the token map
+        _lib.call("cfp_twins_nchw_fwd", x.data_ptr(), x.data_ptr(), B, H, W, C, ctypes.byref(packed[2]), work.data_ptr(), nbytes, code,
+                  _lib.stream_ptr())

@@ -279,3 +279,22 @@ def test_header_constants_match_the_host_side():
                       ("CFP_METRICS_SCRATCH_DOUBLES", headers.METRICS_SCRATCH_DOUBLES)):
         m = re.search(r"#define\s+%s\s+(\d+)" % name, src)
         assert m and int(m.group(1)) == val, name
+
+
+def test_cuda_ops_and_the_torch_stand_in_expose_the_same_interface():
+    """train_seq.py is written once against an ops interface: the product's CudaOps (libcfp kernels) and the CPU test's
+    TorchOps (plain torch, float64) must offer the same methods with the same parameters, or the CPU pin of the
+    sequencing would not be a pin of what runs on the GPU."""
+    import inspect
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from torch_ops import TorchOps
+    from cfpnet_b200.train import CudaOps
+    pub = lambda cls: {n: f for n, f in inspect.getmembers(cls, inspect.isfunction) if not n.startswith("_")}   # noqa: E731
+    a, b = pub(CudaOps), pub(TorchOps)
+    assert set(a) == set(b), (sorted(set(a) - set(b)), sorted(set(b) - set(a)))
+    for n in a:
+        pa, pb = list(inspect.signature(a[n]).parameters), list(inspect.signature(b[n]).parameters)
+        assert len(pa) == len(pb), (n, pa, pb)
+    used = set(re.findall(r"ops\.([a-z_0-9]+)\(", open(os.path.join(ROOT, "cfpnet_b200", "train_seq.py")).read()))
+    assert used <= set(a), sorted(used - set(a))

@@ -1,0 +1,4 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests -m gpu -q -x -k "parity or layers or depth" 2>&1 | tail -n 3
+timeout 300 python bench.py --no-cpu > gpurun_out/r2ah_bench.json 2> gpurun_out/r2ah_bench.err; python tools/show_bench.py gpurun_out/r2ah_bench.json 2>/dev/null | grep "value\|kv_state\|loftr_query\|attn_query"
