@@ -1009,6 +1009,14 @@ template <int C> struct KvTC {
 // NT = threads per row (KvNT<C>): at C = 128 a CTA per SM with four row warps left every scheduler with one warp of long
 // serial epilogues; two threads share a row (x chunks, then K columns | V columns, then half of the zones each).
 template <int C> struct KvNT { static constexpr int NT = C >= 64 ? 2 : 1; };
+template <class S> struct IsZoneTok { static constexpr bool value = false; };
+template <> struct IsZoneTok<ZoneTokSrc<bf16>> { static constexpr bool value = true; };
+// kZone16 at C = 128 (kZoneMma): the per-zone reduction goes back to the tensor pipe, but without the serial
+// accumulate / read / flush of ONE accumulator: the projection's 2C TMEM columns are free once K | V sit in shared
+// memory, so two zones are reduced at a time (one M = 128, N = C, K = 16 MMA each, MN-major views of the K | V tile,
+// accumulators at columns 0 and C), thread (c1, half) stores its head's dh columns of zone 2 b + half, four batches per
+// tile.  The FMA form cost ~4.5 k instructions per thread and tile there (16 rows x dh products per channel and zone,
+// half of them bf16 unpacking); Ksum stays a 16-term row-thread sum.
 template <int C, int NH, bool kComplete, class Src, bool kZone16 = false>
 __global__ void __launch_bounds__((4 * KvNT<C>::NT + 2) * 32) kv_state_tc_kernel(Src src, int S, int S_pad, FastDiv dSp, int groups, const bf16* __restrict__ wkv_tc,
                                                           float* __restrict__ kv, float* __restrict__ ksum, int ntiles) {
@@ -1023,6 +1031,8 @@ __global__ void __launch_bounds__((4 * KvNT<C>::NT + 2) * 32) kv_state_tc_kernel
     const int tid_all = threadIdx.x, warp = umma::warp_idx_sync(), lane = tid_all & 31;
     const int tid = tid_all & 127, half = warp >> 2, wq = warp & 3;       // row, which of the row's NT threads, TMEM lane quarter
     auto rows_barrier = [&]() { asm volatile("bar.sync 1, %0;\n" ::"n"(ROWT) : "memory"); };
+    constexpr bool kZoneMma = kZone16 && C >= 128 && DH == 32 && NT == 2;
+    constexpr bool kZonePos = kZone16 && IsZoneTok<Src>::value;      // zone tokens: the positional row of a thread never changes
 
     if (tid_all == 0) {
         umma::mbar_init(&bars.full[0], 1);
@@ -1043,6 +1053,18 @@ __global__ void __launch_bounds__((4 * KvNT<C>::NT + 2) * 32) kv_state_tc_kernel
                                                                       // multiply-high division (a 64-bit divide per run used to cost ~25 % here)
 
     if (warp < 4 * NT) {
+        constexpr int KGT = KG / NT;                           // this thread's share of the row's 16-byte chunks
+        // S_pad = 16 divides the tile: row `tid` is sample tid % 16 of its zone in EVERY tile, so its slice of the
+        // positional table (weights, not produced by the previous kernel) is read once, before the grid dependency
+        [[maybe_unused]] float pos[kZonePos ? KGT * 8 : 1];
+        if constexpr (kZonePos) {
+            const int s = (tid & 15) < S ? (tid & 15) : 0;
+#pragma unroll
+            for (int k = 0; k < KGT * 2; ++k) {
+                const float4 p4 = *reinterpret_cast<const float4*>(src.pos2 + (size_t)s * C + half * (KGT * 8) + k * 4);
+                pos[4 * k] = p4.x; pos[4 * k + 1] = p4.y; pos[4 * k + 2] = p4.z; pos[4 * k + 3] = p4.w;
+            }
+        }
         pdl_wait();
         uint32_t ph = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -1054,10 +1076,24 @@ __global__ void __launch_bounds__((4 * KvNT<C>::NT + 2) * 32) kv_state_tc_kernel
             CFP_CHAIN_MARK(0, dbg_it);
             {
                 const typename Src::R ref = src.locate(real ? (int64_t)myg * S + mys : 0);
-                constexpr int KGT = KG / NT;                   // this thread's share of the row's 16-byte chunks
                 uint4 v[KGT];
+                if constexpr (kZonePos) {
+                    uint4 raw[KGT];
 #pragma unroll
-                for (int k = 0; k < KGT; ++k) v[k] = real ? load8_bf16(src, ref, (half * KGT + k) * 8) : make_uint4(0u, 0u, 0u, 0u);
+                    for (int k = 0; k < KGT; ++k)
+                        raw[k] = real ? *reinterpret_cast<const uint4*>(src.tok + ref.off + (half * KGT + k) * 8) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                    for (int k = 0; k < KGT; ++k) {
+                        float x8[8];
+                        unpack8(raw[k], x8);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) x8[i] += pos[k * 8 + i];
+                        v[k] = real ? pack8_bf16(x8) : make_uint4(0u, 0u, 0u, 0u);
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < KGT; ++k) v[k] = real ? load8_bf16(src, ref, (half * KGT + k) * 8) : make_uint4(0u, 0u, 0u, 0u);
+                }
 #pragma unroll
                 for (int k = 0; k < KGT; ++k) *reinterpret_cast<uint4*>(a0 + (size_t)(half * KGT + k) * P::LBO + tid * 16) = v[k];
             }
@@ -1095,7 +1131,45 @@ __global__ void __launch_bounds__((4 * KvNT<C>::NT + 2) * 32) kv_state_tc_kernel
                     }
                 }
             }
-            if constexpr (kZone16) {
+            if constexpr (kZoneMma) {
+                umma::fence_async_smem();
+                umma::fence_before_sync();
+                mbar_arrive(&bars.a_ready);                    // K | V staged, projection accumulator consumed: batch 0 may issue
+                rows_barrier();                                // ... and visible to the other row threads (Ksum below)
+                const int c1 = tid;                            // channel = TMEM lane; its head's columns start at wq * 32
+                {
+                    const uint8_t* kp = a1 + (size_t)(c1 / 8) * P::LBO + (c1 % 8) * 2;
+#pragma unroll
+                    for (int zz = 0; zz < 4; ++zz) {
+                        const int z = half * 4 + zz;
+                        float ks = 0.f;
+#pragma unroll
+                        for (int rr = 0; rr < 16; ++rr)
+                            ks += __uint_as_float((uint32_t)*reinterpret_cast<const uint16_t*>(kp + (z * 16 + rr) * 16) << 16);
+                        const int64_t g = (int64_t)tile * 8 + z;
+                        if (g < groups) ksum[(size_t)g * C + c1] = ks;
+                    }
+                }
+#pragma unroll 1
+                for (int b = 0; b < 4; ++b) {
+                    umma::mbar_wait(&bars.acc_ready, ph); ph ^= 1;
+                    umma::fence_after_sync();
+                    const int64_t g = (int64_t)tile * 8 + 2 * b + half;
+                    float t0[16], t1[16];
+                    umma::tmem_ld16(umma::tmem_addr(tmem, wq * 32, half * C + wq * 32), t0);
+                    umma::tmem_ld16(umma::tmem_addr(tmem, wq * 32, half * C + wq * 32 + 16), t1);
+                    if (g < groups) {
+                        float* dst = kv + (size_t)g * (C * DH) + (size_t)c1 * DH;
+#pragma unroll
+                        for (int v = 0; v < 16; v += 4) *reinterpret_cast<float4*>(dst + v) = make_float4(t0[v], t0[v + 1], t0[v + 2], t0[v + 3]);
+#pragma unroll
+                        for (int v = 0; v < 16; v += 4) *reinterpret_cast<float4*>(dst + 16 + v) = make_float4(t1[v], t1[v + 1], t1[v + 2], t1[v + 3]);
+                    }
+                    umma::fence_before_sync();
+                    if (b < 3) mbar_arrive(&bars.a_ready);     // both accumulators read: the next two zones may overwrite them
+                }
+                continue;                                      // the next tile's a_ready arrival orders a0 / a1 / TMEM reuse
+            } else if constexpr (kZone16) {
                 umma::fence_before_sync();
                 rows_barrier();                                // K | V of all 128 rows staged; accumulator consumed
                 constexpr int ZPT = 8 / (ROWT / C);            // zones per thread: thread = (channel c1, zone subset)
@@ -1201,6 +1275,19 @@ __global__ void __launch_bounds__((4 * KvNT<C>::NT + 2) * 32) kv_state_tc_kernel
                         umma::mma_bf16(tmem + half * C, umma::smem_desc(a0s + 2 * ks * P::LBO, P::LBO),
                                        umma::smem_desc(ws + half * 2 * C * C + ks * 2 * LBO_B, LBO_B), idesc, ks > 0);
                 umma::commit(&bars.acc_ready);
+                if constexpr (kZoneMma) {                     // two zones per batch: K^T V of 16 rows into columns 0 / C
+                    const uint32_t idesc_z = umma::idesc_bf16(128, C) | (1u << 15) | (1u << 16);
+#pragma unroll 1
+                    for (int b = 0; b < 4; ++b) {
+                        wait_a();                             // K | V staged (b = 0) / previous batch read
+#pragma unroll
+                        for (int zz = 0; zz < 2; ++zz)
+                            umma::mma_bf16(tmem + zz * C, umma::smem_desc(a1s + (2 * b + zz) * 256, 128, P::LBO),
+                                           umma::smem_desc(a1s + KG * P::LBO + (2 * b + zz) * 256, 128, P::LBO), idesc_z, false);
+                        umma::commit(&bars.acc_ready);
+                    }
+                    continue;
+                }
                 if constexpr (kZone16) continue;              // the row threads reduce the groups themselves
                 wait_a();                                     // K | V | ones staged
                 int ks = 0;
