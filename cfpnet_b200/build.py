@@ -36,14 +36,32 @@ def _stamp():
     return h.hexdigest()
 
 
-def _compile(src):
+def _src_stamp(src):
+    """Hash of what one object depends on: the flags, its source and every header (csrc/*.cuh, *.h, include/*.h)."""
+    h = hashlib.sha256(" ".join(FLAGS).encode())
+    with open(os.path.join(CSRC, src), "rb") as fh:
+        h.update(fh.read())
+    for root in (CSRC, os.path.join(os.path.dirname(HERE), "include")):
+        for f in sorted(os.listdir(root)):
+            if f.endswith((".cuh", ".h")):
+                with open(os.path.join(root, f), "rb") as fh:
+                    h.update(f.encode() + fh.read())
+    return h.hexdigest()
+
+
+def _compile(src, force=False):
     obj = os.path.join(OBJ_DIR, src[:-3] + ".o")
+    stamp_file, stamp = obj + ".stamp", _src_stamp(src)
+    if not force and os.path.exists(obj) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
+        return obj                                      # unchanged source, headers and flags: keep the object
     cmd = [NVCC, *FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     with open(obj + ".log", "w") as fh:
         fh.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
     if r.returncode != 0:
         raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+    with open(stamp_file, "w") as fh:
+        fh.write(stamp)
     return obj
 
 
@@ -55,7 +73,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             and open(stamp_file).read() == stamp):
         return LIB_PATH
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
-        objs = list(ex.map(_compile, _sources()))
+        objs = list(ex.map(lambda f: _compile(f, force), _sources()))
     cmd = [NVCC, "-shared", "-o", LIB_PATH, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
            "-Xcompiler", "-fPIC", "-lcudart_static", "-lpthread", "-ldl", "-lrt"]
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -160,6 +160,16 @@ struct ChainStages {
     static_assert(NT == 1 || NT == 2, "one or two threads per row");
     static_assert(CH % G == 0 && CH % 16 == 0, "a thread owns whole heads and whole 16-column pieces");
     struct Row { typename Q::R ref; int g; };
+    // C = 128, dh = 16 (LSA, GSA): the group state is read from global memory (no room for it in shared memory) and the
+    // attention epilogue stalled on its first touch of every line - a head block's slice (G x dh floats = 1 KB of one
+    // group) is prefetched into L1 one block ahead, the first one while the q projection runs.
+    static constexpr bool kPrefetchState = C >= 128 && DH <= 16;
+    static __device__ __forceinline__ void prefetch_state(const float* __restrict__ kv, int g, int c0) {
+        if (g < 0) return;
+        const char* p = reinterpret_cast<const char*>(kv + (size_t)g * (C * DH) + (size_t)c0 * DH);
+#pragma unroll
+        for (int i = 0; i < G * DH * 4; i += 128) asm volatile("prefetch.global.L1 [%0];\n" ::"l"(p + i));
+    }
 
     // stage x: locate the row once, copy this thread's chunks of its C channels into a0[:, 0:C)
     static __device__ __forceinline__ Row stage_x(const Q& q, int64_t row0, int tid, uint8_t* a0, int half = 0) {
@@ -184,6 +194,9 @@ struct ChainStages {
         const int g = r.g;
 #pragma unroll 1
         for (int c0 = half * CH; c0 < half * CH + CH; c0 += G) {
+            if constexpr (kPrefetchState) {                  // the next head block's slice of the group state -> L1
+                if (c0 + G < half * CH + CH) prefetch_state(kv, g, c0 + G);
+            }
             float qv[G], out[G];
 #pragma unroll
             for (int j = 0; j < G; j += 16) {
@@ -377,7 +390,7 @@ template <int C> struct ChainOcc { static constexpr int CTAS = C >= 128 ? 1 : (C
 // through the provider (L2-hot) in the last epilogue.
 template <int C, int NH, bool kAttnOnly, class Q, int NT>
 __global__ void __launch_bounds__((8 * NT + 2) * 32, 1) loftr_query_tc_kernel(Q q, cfp_loftr_w w, const float* __restrict__ kv,
-                                                             const float* __restrict__ ksum, int ntiles) {
+                                                             const float* __restrict__ ksum, int ntiles, int spread) {
     using P = ChainTC<C>;
     using S = ChainStages<C, NH, kAttnOnly, Q, NT>;
     constexpr int KG = P::KG;
@@ -388,7 +401,13 @@ __global__ void __launch_bounds__((8 * NT + 2) * 32, 1) loftr_query_tc_kernel(Q 
     __shared__ float2 ln_xch[2][NT][128];                    // LayerNorm statistics of split rows, per tile group
     uint8_t* ring = smem + 2 * (size_t)P::ABUF;
     const int tid = threadIdx.x, warp = umma::warp_idx_sync();
-    const int npairs = (ntiles + 1) / 2;
+    // Tiles of round `it`: group g of CTA c takes tile  it * 2 G + c * ca + g * cg.  spread = 0: (ca, cg) = (2, 1), a CTA owns
+    // two neighbouring tiles; spread = 1: (1, G), the first G tiles of a round go to the groups 0 and the next G to the groups
+    // 1 - a last round of fewer than 2 G tiles then runs one tile on (almost) every SM instead of two on half of them.
+    // A group without a tile only keeps the hand-over protocol going (arrivals, barrier), and its MMAs are not issued.
+    const int round_tiles = 2 * (int)gridDim.x;
+    const int ca = spread ? 1 : 2, cg = spread ? (int)gridDim.x : 1;
+    const int first0 = (int)blockIdx.x * ca;
 
     if (tid == 0) {
         for (int i = 0; i < P::NSLOT; ++i) { umma::mbar_init(&bars.full[i], 1); umma::mbar_init(&bars.empty[i], 1); }
@@ -416,12 +435,24 @@ __global__ void __launch_bounds__((8 * NT + 2) * 32, 1) loftr_query_tc_kernel(Q 
             umma::mbar_wait(&bars.acc_ready, ph); ph ^= 1;
             umma::fence_after_sync();
         };
-        for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
-            const int tile = 2 * pair + grp;                 // an odd tile count leaves group 1 of the last pair with dead rows
-            const int64_t row0 = tile < ntiles ? (int64_t)tile * 128 : q.rows;
-            [[maybe_unused]] const int dbg_it = 1 - (pair - (int)blockIdx.x) / (int)gridDim.x;      // marks on the FIRST pair of CTA 5
+        for (int first = first0; first < ntiles; first += round_tiles) {
+            const int tile = first + grp * cg;
+            if (tile >= ntiles) {                            // (group 1 only) no tile this round: keep the protocol going
+#pragma unroll 1
+                for (int i = 0; i < (kAttnOnly ? 1 : 4); ++i) hand_over();
+                umma::fence_before_sync();
+                asm volatile("bar.sync 1, %0;\n" ::"n"(NRW * 32) : "memory");
+                continue;
+            }
+            const int64_t row0 = (int64_t)tile * 128;
+            [[maybe_unused]] const int dbg_it = 1 - (first - first0) / round_tiles;      // marks on the FIRST pair of CTA 5
             CFP_CHAIN_MARK(0, dbg_it);
             const typename S::Row r = S::stage_x(q, row0, tid_g, a0, half);
+            if constexpr (S::kPrefetchState) S::prefetch_state(kv, r.g, half * S::CH);
+            if constexpr (kAttnOnly && C >= 128) {           // DAPM: group = frame, one or two per tile - row t fetches line t of
+                if (r.g >= 0 && half == 0)                   // its group's 16 KB state, together the whole of it
+                    asm volatile("prefetch.global.L1 [%0];\n" ::"l"(reinterpret_cast<const char*>(kv + (size_t)r.g * (C * S::DH)) + tid_g * 128));
+            }
             CFP_CHAIN_MARK(1, dbg_it);
             hand_over();
             CFP_CHAIN_MARK(2, dbg_it);
@@ -447,7 +478,7 @@ __global__ void __launch_bounds__((8 * NT + 2) * 32, 1) loftr_query_tc_kernel(Q 
     } else if (warp == NRW) {
         const bf16* wsrc = reinterpret_cast<const bf16*>(w.tc);
         int cc = 0;
-        for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x)
+        for (int first = first0; first < ntiles; first += round_tiles)
             for (int c = 0; c < NCHUNK; ++c, ++cc) {
                 const int slot = cc % P::NSLOT, round = cc / P::NSLOT;
                 if (round > 0) umma::mbar_wait(&bars.empty[slot], (round - 1) & 1);
@@ -460,18 +491,21 @@ __global__ void __launch_bounds__((8 * NT + 2) * 32, 1) loftr_query_tc_kernel(Q 
         uint32_t ph = 0;
         int cc = 0;
         // one weight block, both tiles: D_g[:, dcol:dcol+C] (+)= A_g[:, kg0*8 : kg0*8+C] * W^T
+        int nlive = 2;
         auto block = [&](int kg0, int dcol, bool acc_first) {
             const int slot = cc % P::NSLOT, round = cc / P::NSLOT;
             umma::mbar_wait(&bars.full[slot], round & 1);
             umma::fence_after_sync();
 #pragma unroll
             for (int g2 = 0; g2 < 2; ++g2)
-                issue_block<C>(tmem + g2 * 256 + dcol, a0s + g2 * P::ABUF + kg0 * P::LBO, rs + slot * P::SLOT, idesc, acc_first);
+                if (g2 < nlive)
+                    issue_block<C>(tmem + g2 * 256 + dcol, a0s + g2 * P::ABUF + kg0 * P::LBO, rs + slot * P::SLOT, idesc, acc_first);
             umma::commit(&bars.empty[slot]);
             ++cc;
         };
         auto wait_a = [&]() { umma::mbar_wait(&bars.a_ready, ph); ph ^= 1; umma::fence_after_sync(); };
-        for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+        for (int first = first0; first < ntiles; first += round_tiles) {
+            nlive = first + cg < ntiles ? 2 : 1;
             wait_a();
             block(0, 0, false);                            // q
             umma::commit(&bars.acc_ready);
@@ -691,11 +725,17 @@ static int run_query_tc_nt(const char* name, const Q& q, const cfp_loftr_w& w, c
         }
 #endif
     } else {
+        // CFP_CHAIN_SPREAD=1: the tiles of a round are spread over the SMs (one tile per CTA in a thin last round) instead of
+        // two neighbouring tiles per CTA.  Measured (B = 64, L3): GSA 0.147 -> 0.129 ms alone and 4.39 -> 4.37 ms per step with
+        // the levels on one stream, but 3.85 -> 3.91 ms with the three levels concurrent - a CTA with one tile takes 0.75 of
+        // the time of a CTA with two and still owns the SM's shared memory, so it costs SM-time the other levels could use.
+        static const bool spread = [] { const char* e = getenv("CFP_CHAIN_SPREAD"); return e && e[0] == '1'; }();
         const int64_t npairs = (ntiles + 1) / 2;
-        const int grid = (int)(npairs < sm_count() ? npairs : sm_count());
+        const int64_t want = spread ? ntiles : npairs;
+        const int grid = (int)(want < sm_count() ? want : sm_count());
         auto k = loftr_query_tc_kernel<C, NH, kAttnOnly, Q, NT>;
         if (int e = set_smem(k, P::SMEM)) return e;
-        launch_pdl(k, grid, (8 * NT + 2) * 32, P::SMEM, st, q, w, kv, ksum, (int)ntiles);
+        launch_pdl(k, grid, (8 * NT + 2) * 32, P::SMEM, st, q, w, kv, ksum, (int)ntiles, (int)spread);
 #ifdef CFP_DEBUG_TIMING
         {
             cudaStreamSynchronize(st);
@@ -1134,6 +1174,7 @@ __global__ void __launch_bounds__((4 * KvNT<C>::NT + 2) * 32) kv_state_tc_kernel
             if constexpr (kZoneMma) {
                 umma::fence_async_smem();
                 umma::fence_before_sync();
+                CFP_CHAIN_MARK(3, dbg_it);
                 mbar_arrive(&bars.a_ready);                    // K | V staged, projection accumulator consumed: batch 0 may issue
                 rows_barrier();                                // ... and visible to the other row threads (Ksum below)
                 const int c1 = tid;                            // channel = TMEM lane; its head's columns start at wq * 32
@@ -1150,6 +1191,7 @@ __global__ void __launch_bounds__((4 * KvNT<C>::NT + 2) * 32) kv_state_tc_kernel
                         if (g < groups) ksum[(size_t)g * C + c1] = ks;
                     }
                 }
+                CFP_CHAIN_MARK(4, dbg_it);
 #pragma unroll 1
                 for (int b = 0; b < 4; ++b) {
                     umma::mbar_wait(&bars.acc_ready, ph); ph ^= 1;
@@ -1168,6 +1210,7 @@ __global__ void __launch_bounds__((4 * KvNT<C>::NT + 2) * 32) kv_state_tc_kernel
                     umma::fence_before_sync();
                     if (b < 3) mbar_arrive(&bars.a_ready);     // both accumulators read: the next two zones may overwrite them
                 }
+                CFP_CHAIN_MARK(5, dbg_it);
                 continue;                                      // the next tile's a_ready arrival orders a0 / a1 / TMEM reuse
             } else if constexpr (kZone16) {
                 umma::fence_before_sync();

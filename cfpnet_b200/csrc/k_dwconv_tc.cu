@@ -87,6 +87,11 @@ size_t dwconv_tc_plane_bytes(int B, int H, int W, int C, int K) {
     return ((in_bytes + 255) & ~(size_t)255) + ((out_bytes + 255) & ~(size_t)255);
 }
 
+__host__ __device__ inline int dw_slab_row_words(int W, int C) {
+    const int n = W * (C / 2 + 1);
+    return n + ((1 - n) % 32 + 32) % 32;
+}
+
 // ---------------------------------------------------------------- token-major -> padded planes
 // CTA = (plane stack, 8 consecutive PLANE rows): coalesced read of the image rows among them ([W][C] slabs),
 // transpose through shared memory, then each thread emits 16-byte chunks (8 columns of one channel, one
@@ -95,9 +100,13 @@ size_t dwconv_tc_plane_bytes(int B, int H, int W, int C, int K) {
 // stacked frames, PAD columns left and right, the slack rows and column groups the 128-row / 64-column operand
 // views reach into) - so the planes need no memset and stale workspace bytes never enter an MMA.
 __global__ void __launch_bounds__(256) dw_plane_pack_kernel(const bf16* __restrict__ in, bf16* __restrict__ planes, DwGeom g, int B) {
-    extern __shared__ __align__(16) uint32_t slab[];          // [8 rows][W][C/2 + 1] channel pairs (odd stride: no conflicts)
+    extern __shared__ __align__(16) uint32_t slab[];          // [8 rows][RS]: per row [W][C/2 + 1] channel pairs + padding
     const int stack = blockIdx.y, pr0 = blockIdx.x * 8;
     const int C = g.C, W = g.W, C2 = C / 2, LD = C2 + 1;
+    // phase 2 reads with a warp = 8 plane rows x 4 consecutive x-groups: word address r * RS + xg * 8 * LD + const.  LD = 1
+    // (mod 4) puts the x-groups 8 banks apart; RS = 1 (mod 32) puts the rows on the banks in between - conflict-free (with
+    // RS = W * LD the eight rows fell on four banks, the x-groups on the same four: 8-way conflicts on every load)
+    const int RS = dw_slab_row_words(W, C);
     pdl_wait();
     // every plane row an A view can touch (HP >= PAD + F x (H + PAD)): the rows below the last frame's halo are only
     // multiplied by all-zero Toeplitz blocks (taps dy >= K of the last group of eight), but a stale NaN would survive that
@@ -118,7 +127,7 @@ __global__ void __launch_bounds__(256) dw_plane_pack_kernel(const bf16* __restri
             const uint4* src = reinterpret_cast<const uint4*>(in) + (size_t)sr * nvec;
             for (int i = threadIdx.x; i < nvec; i += 256) {
                 const uint4 v = src[i];
-                uint32_t* d = slab + (r * W + i / V) * LD + (i % V) * 4;
+                uint32_t* d = slab + r * RS + (i / V) * LD + (i % V) * 4;
                 d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
             }
         }
@@ -138,7 +147,7 @@ __global__ void __launch_bounds__(256) dw_plane_pack_kernel(const bf16* __restri
         uint4 lo = make_uint4(0u, 0u, 0u, 0u), hi = lo;
         if (img_row && xb + 7 >= 0 && xb < W) {
             uint32_t v[8];
-            const uint32_t* sp = slab + (r * W + xb) * LD + c2;
+            const uint32_t* sp = slab + r * RS + xb * LD + c2;
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = (xb + j >= 0 && xb + j < W) ? sp[j * LD] : 0u;
             lo.x = __byte_perm(v[0], v[1], 0x5410); hi.x = __byte_perm(v[0], v[1], 0x7632);
@@ -388,7 +397,7 @@ int dwconv_tc(const void* in, const void** planar_out_p, int* planar_pitch, int 
     *planar_out_p = planar_out;          // [B][C][H][WO]; lkpm_mlp_tc reads it in place (no transpose back)
     *planar_pitch = g.WO;
     {
-        const size_t smem = (size_t)8 * W * (C / 2 + 1) * 4;
+        const size_t smem = (size_t)8 * dw_slab_row_words(W, C) * 4;
         CFP_REQUIRE(smem <= 200 * 1024, "dw_plane_pack: %zu B shared memory", smem);
         if (int err = set_smem(dw_plane_pack_kernel, smem)) return err;
         launch_pdl(dw_plane_pack_kernel, dim3((g.HP + 7) / 8, g.NB), 256, smem, st, (const bf16*)in, planes, g, B);

@@ -4,6 +4,7 @@
 // Eval-mode BN (and the conv bias) are folded by the host wrapper into the taps / `dw_shift`.
 #include "cfp_common.cuh"
 #include "cfp_internal.h"
+#include <stdlib.h>
 
 namespace cfp {
 
@@ -14,30 +15,35 @@ namespace cfp {
 // on opposite halves of the 32 banks.  A thread owns 2 rows x 8 (stride-2) columns and slides
 // over the input rows with the row segment held in registers: 2*8*K FMAs per (2K + 2*8+K-2)
 // shared loads.
+// The tile is TY x TX = (2 x warps) x (2 Q) output pixels: 16 x 16 in general (Q = 8, eight warps); on a small map
+// (the 1/16-scale level: 26 x 34, 30 x 40) ONE CTA takes the whole frame (Q = 17 or 20, a warp per two rows) - 16 x 16
+// tiles covered 32 x 48 cells of a 26 x 34 map and staged a 22 x 22 halo per 256 outputs (43 % of the FMAs and 1.9x
+// of the loads wasted); the frame-sized tile wastes nothing and stages 1.45x.
 constexpr int kDwTile = 16, kDwCh = 16;
 
-template <int K, typename T>
-__global__ void __launch_bounds__(kThreads) dwconv_bn_relu_kernel(const T* __restrict__ in, T* __restrict__ out,
-                                                                  int H, int W, int C,
-                                                                  const float* __restrict__ dw_t,
-                                                                  const float* __restrict__ dw_shift, int relu) {
-    constexpr int HP = kDwTile + K - 1, PADK = (K - 1) / 2, Q = 8, NIN = 2 * (Q - 1) + K;
+template <int K, typename T, int Q, int MAXT>
+__global__ void __launch_bounds__(MAXT) dwconv_bn_relu_kernel(const T* __restrict__ in, T* __restrict__ out,
+                                                              int H, int W, int C,
+                                                              const float* __restrict__ dw_t,
+                                                              const float* __restrict__ dw_shift, int relu) {
+    constexpr int TX = 2 * Q, HPX = TX + K - 1, PADK = (K - 1) / 2, NIN = 2 * (Q - 1) + K;
+    const int nthreads = blockDim.x, TY = 2 * (nthreads >> 5), HPY = TY + K - 1;
     extern __shared__ __align__(16) float smem[];
-    float* halo = smem;                         // [HP][HP][16]
-    float* wsm = halo + HP * HP * kDwCh;        // [K*K][16]
+    float* halo = smem;                         // [HPY][HPX][16]
+    float* wsm = halo + HPY * HPX * kDwCh;      // [K*K][16]
     const int cgroups = C / kDwCh;
     const int b = blockIdx.z / cgroups, c0 = (blockIdx.z % cgroups) * kDwCh;
-    const int y0 = blockIdx.y * kDwTile, x0 = blockIdx.x * kDwTile;
+    const int y0 = blockIdx.y * TY, x0 = blockIdx.x * TX;
     const size_t frame = (size_t)b * H * W;
 
-    for (int i = threadIdx.x; i < K * K * (kDwCh / 4); i += kThreads) {          // taps: weights, before the wait
+    for (int i = threadIdx.x; i < K * K * (kDwCh / 4); i += nthreads) {          // taps: weights, before the wait
         const int tap = i / (kDwCh / 4), c = (i % (kDwCh / 4)) * 4;
         *reinterpret_cast<float4*>(wsm + tap * kDwCh + c) = *reinterpret_cast<const float4*>(dw_t + (size_t)tap * C + c0 + c);
     }
     pdl_wait();
-    for (int i = threadIdx.x; i < HP * HP * (kDwCh / 4); i += kThreads) {
+    for (int i = threadIdx.x; i < HPY * HPX * (kDwCh / 4); i += nthreads) {
         const int cell = i / (kDwCh / 4), c = (i % (kDwCh / 4)) * 4;
-        const int y = y0 - PADK + cell / HP, x = x0 - PADK + cell % HP;
+        const int y = y0 - PADK + cell / HPX, x = x0 - PADK + cell % HPX;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (y >= 0 && y < H && x >= 0 && x < W) v = IO<T>::ld4(in + (frame + (size_t)y * W + x) * C + c0 + c);
         *reinterpret_cast<float4*>(halo + cell * kDwCh + c) = v;
@@ -53,7 +59,7 @@ __global__ void __launch_bounds__(kThreads) dwconv_bn_relu_kernel(const T* __res
 #pragma unroll 1
     for (int iy = 0; iy < K + 1; ++iy) {
         float v[NIN];
-        const float* hrow = halo + ((oy + iy) * HP + xh) * kDwCh + c;
+        const float* hrow = halo + ((oy + iy) * HPX + xh) * kDwCh + c;
 #pragma unroll
         for (int i = 0; i < NIN; ++i) v[i] = hrow[i * kDwCh];
         if (iy < K) {
@@ -89,16 +95,30 @@ __global__ void __launch_bounds__(kThreads) dwconv_bn_relu_kernel(const T* __res
     }
 }
 
+template <int K, typename T, int Q, int MAXT>
+static int dw_launch_tile(const void* in, void* out, int B, int H, int W, int C, const float* dw_t, const float* dw_shift,
+                          int relu, int warps, cudaStream_t st) {
+    const int TY = 2 * warps, TX = 2 * Q;
+    const size_t smem = (size_t)((TY + K - 1) * (TX + K - 1) * kDwCh + K * K * kDwCh) * sizeof(float);
+    auto k = dwconv_bn_relu_kernel<K, T, Q, MAXT>;
+    if (int e = set_smem(k, smem)) return e;
+    dim3 grid((W + TX - 1) / TX, (H + TY - 1) / TY, B * (C / kDwCh));
+    launch_pdl(k, grid, warps * 32, smem, st, (const T*)in, (T*)out, H, W, C, dw_t, dw_shift, relu);
+    return check_launch(K == 31 ? "dwconv<31>" : K == 15 ? "dwconv<15>" : "dwconv<7>");
+}
+
 template <int K, typename T>
 static int dw_launch(const void* in, void* out, int B, int H, int W, int C, const float* dw_t, const float* dw_shift,
                      int relu, cudaStream_t st) {
-    constexpr int HP = kDwTile + K - 1;
-    const size_t smem = (size_t)(HP * HP * kDwCh + K * K * kDwCh) * sizeof(float);
-    auto k = dwconv_bn_relu_kernel<K, T>;
-    if (int e = set_smem(k, smem)) return e;
-    dim3 grid((W + kDwTile - 1) / kDwTile, (H + kDwTile - 1) / kDwTile, B * (C / kDwCh));
-    launch_pdl(k, grid, kThreads, smem, st, (const T*)in, (T*)out, H, W, C, dw_t, dw_shift, relu);
-    return check_launch(K == 31 ? "dwconv<31>" : K == 15 ? "dwconv<15>" : "dwconv<7>");
+    if constexpr (K == 7) {                     // whole-frame tiles for small maps (CFP_DW_FRAME=0: always 16 x 16 tiles)
+        static const bool frame_tiles = [] { const char* e = getenv("CFP_DW_FRAME"); return !(e && e[0] == '0'); }();
+        if (frame_tiles && H <= 32 && W <= 40 && H * W > 16 * 16) {
+            const int warps = (H + 1) / 2;
+            if (W <= 34) return dw_launch_tile<K, T, 17, 512>(in, out, B, H, W, C, dw_t, dw_shift, relu, warps, st);
+            return dw_launch_tile<K, T, 20, 512>(in, out, B, H, W, C, dw_t, dw_shift, relu, warps, st);
+        }
+    }
+    return dw_launch_tile<K, T, kDwTile / 2, kThreads>(in, out, B, H, W, C, dw_t, dw_shift, relu, kThreads / 32, st);
 }
 
 // relu = 0: the plain depthwise conv + per-channel shift (train mode: shift = the conv bias, BatchNorm follows as its
