@@ -61,7 +61,10 @@ __device__ __forceinline__ float elu1(float x) {          // elu(x)+1, attention
     // branch-free: written as `x > 0 ? x + 1 : __expf(x)` ptxas put a divergent branch (BSSY / BSYNC pair) around every
     // exp - 116 of them in a C = 128 kv_state epilogue, which made that epilogue 6 us where the same walk with a relu
     // takes 1 us.  The exponent's argument is clamped so that the unused lane of the select cannot overflow.
-    const float e = __expf(fminf(x, 0.f));
+    // ex2.approx.ftz directly: __expf without -ftz carries a denormal-range fix-up (compare with -126, halve, square) that
+    // is three more instructions per value; results below 2^-126 may flush to zero here.
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(x, 0.f) * 1.4426950408889634f));
     return x > 0.f ? x + 1.f : e;
 }
 __device__ __forceinline__ float gelu_erf(float x) {      // nn.GELU() default (erf form)

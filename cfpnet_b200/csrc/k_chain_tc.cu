@@ -399,7 +399,10 @@ __global__ void __launch_bounds__((8 * NT + 2) * 32, 1) loftr_query_tc_kernel(Q 
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ ChainBars bars;
     __shared__ float2 ln_xch[2][NT][128];                    // LayerNorm statistics of split rows, per tile group
-    uint8_t* ring = smem + 2 * (size_t)P::ABUF;
+    // the attention-only chain (DAPM) stages x only: half an operand buffer per tile, and the shared memory it does not
+    // ask for stays L1 - where its per-frame attention state (16 KB a group at C = 128) is read from
+    constexpr size_t ABUF = kAttnOnly ? (size_t)KG * P::LBO : (size_t)P::ABUF;
+    uint8_t* ring = smem + 2 * ABUF;
     const int tid = threadIdx.x, warp = umma::warp_idx_sync();
     // Tiles of round `it`: group g of CTA c takes tile  it * 2 G + c * ca + g * cg.  spread = 0: (ca, cg) = (2, 1), a CTA owns
     // two neighbouring tiles; spread = 1: (1, G), the first G tiles of a round go to the groups 0 and the next G to the groups
@@ -423,7 +426,7 @@ __global__ void __launch_bounds__((8 * NT + 2) * 32, 1) loftr_query_tc_kernel(Q 
     if (warp < NRW) {
         pdl_wait();                       // rows and attention state come from the previous kernels of the stream
         const int grp = warp / RW, half = (warp % RW) >> 2, wq = warp & 3, tid_g = tid & 127;
-        uint8_t* a0 = smem + (size_t)grp * P::ABUF;          // [x | msg, then LN1(merge(msg))], then the MLP hidden
+        uint8_t* a0 = smem + (size_t)grp * ABUF;             // [x | msg, then LN1(merge(msg))], then the MLP hidden
         const uint32_t tmem = bars.tmem_slot + grp * 256;
         float2* xch = &ln_xch[grp][0][0];
         auto group_sync = [&]() { asm volatile("bar.sync %0, %1;\n" ::"r"(2 + grp), "n"(RW * 32) : "memory"); };
@@ -499,7 +502,7 @@ __global__ void __launch_bounds__((8 * NT + 2) * 32, 1) loftr_query_tc_kernel(Q 
 #pragma unroll
             for (int g2 = 0; g2 < 2; ++g2)
                 if (g2 < nlive)
-                    issue_block<C>(tmem + g2 * 256 + dcol, a0s + g2 * P::ABUF + kg0 * P::LBO, rs + slot * P::SLOT, idesc, acc_first);
+                    issue_block<C>(tmem + g2 * 256 + dcol, a0s + g2 * (uint32_t)ABUF + kg0 * P::LBO, rs + slot * P::SLOT, idesc, acc_first);
             umma::commit(&bars.empty[slot]);
             ++cc;
         };
@@ -734,8 +737,9 @@ static int run_query_tc_nt(const char* name, const Q& q, const cfp_loftr_w& w, c
         const int64_t want = spread ? ntiles : npairs;
         const int grid = (int)(want < sm_count() ? want : sm_count());
         auto k = loftr_query_tc_kernel<C, NH, kAttnOnly, Q, NT>;
-        if (int e = set_smem(k, P::SMEM)) return e;
-        launch_pdl(k, grid, (8 * NT + 2) * 32, P::SMEM, st, q, w, kv, ksum, (int)ntiles, (int)spread);
+        constexpr size_t smem = kAttnOnly ? 2 * (size_t)P::KG * P::LBO + (size_t)P::NSLOT * P::SLOT : P::SMEM;
+        if (int e = set_smem(k, smem)) return e;
+        launch_pdl(k, grid, (8 * NT + 2) * 32, smem, st, q, w, kv, ksum, (int)ntiles, (int)spread);
 #ifdef CFP_DEBUG_TIMING
         {
             cudaStreamSynchronize(st);
@@ -1145,28 +1149,45 @@ __global__ void __launch_bounds__((4 * KvNT<C>::NT + 2) * 32) kv_state_tc_kernel
             umma::mbar_wait(&bars.acc_ready, ph); ph ^= 1;
             CFP_CHAIN_MARK(2, dbg_it);
             umma::fence_after_sync();
-            if constexpr (C >= 64) {                           // NT = 2: K columns | V columns
-                const int cb = half * (2 * C / NT);
-                umma::tmem_for_each16<2 * C / NT>(umma::tmem_addr(tmem, wq * 32, cb), [&](int cc, const float (&t)[16]) {
-                    const int c0 = cb + cc;
+            // padding rows are zeroed with a multiplicative mask (their x row was staged as zeros, so the accumulator is
+            // finite): written as `!real ? 0 : ...` ptxas wrapped every elu in a divergent branch (114 BSSY / BSYNC pairs at
+            // C = 128, 5.5 us per tile for ~900 instructions per thread)
+            const float live = real ? 1.f : 0.f;
+            if constexpr (C >= 64) {                           // NT = 2: thread `half` 0 owns the K columns, 1 the V columns
+                static_assert(2 * C / NT == C, "a thread owns exactly K or V");
+                const int cb = half * C;
+                if (half == 0) {
+                    umma::tmem_for_each16<C>(umma::tmem_addr(tmem, wq * 32, 0), [&](int cc, const float (&t)[16]) {
 #pragma unroll
-                    for (int j = 0; j < 16; j += 8) {
-                        float o8[8];
+                        for (int j = 0; j < 16; j += 8) {
+                            float o8[8];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) o8[i] = !real ? 0.f : (c0 < C ? elu1(t[j + i]) : t[j + i]);
-                        umma::store_chunk(a1, P::LBO, tid, (c0 + j) / 8, o8);
-                    }
-                });
+                            for (int i = 0; i < 8; ++i) o8[i] = elu1(t[j + i]) * live;
+                            umma::store_chunk(a1, P::LBO, tid, (cc + j) / 8, o8);
+                        }
+                    });
+                } else {
+                    umma::tmem_for_each16<C>(umma::tmem_addr(tmem, wq * 32, cb), [&](int cc, const float (&t)[16]) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 8) {
+                            float o8[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) o8[i] = t[j + i] * live;
+                            umma::store_chunk(a1, P::LBO, tid, (cb + cc + j) / 8, o8);
+                        }
+                    });
+                }
             } else {                                           // four pieces only: the rolled loop measured 15 % faster at C = 32
 #pragma unroll 1
                 for (int c0 = 0; c0 < 2 * C; c0 += 16) {
                     float t[16];
                     umma::tmem_ld16(umma::tmem_addr(tmem, wq * 32, c0), t);
+                    const bool isk = c0 < C;                   // warp-uniform
 #pragma unroll
                     for (int j = 0; j < 16; j += 8) {
                         float o8[8];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) o8[i] = !real ? 0.f : (c0 < C ? elu1(t[j + i]) : t[j + i]);
+                        for (int i = 0; i < 8; ++i) o8[i] = (isk ? elu1(t[j + i]) : t[j + i]) * live;
                         umma::store_chunk(a1, P::LBO, tid, (c0 + j) / 8, o8);
                     }
                 }

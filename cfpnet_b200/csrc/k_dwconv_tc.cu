@@ -37,6 +37,7 @@
 #include "cfp_common.cuh"
 #include "cfp_internal.h"
 #include "umma.cuh"
+#include <stdlib.h>
 
 namespace cfp {
 
@@ -99,9 +100,10 @@ __host__ __device__ inline int dw_slab_row_words(int W, int C) {
 // writes EVERY chunk of the planes - image cells and zeros everywhere else (PAD rows above / between / below the
 // stacked frames, PAD columns left and right, the slack rows and column groups the 128-row / 64-column operand
 // views reach into) - so the planes need no memset and stale workspace bytes never enter an MMA.
+template <int RPC>
 __global__ void __launch_bounds__(256) dw_plane_pack_kernel(const bf16* __restrict__ in, bf16* __restrict__ planes, DwGeom g, int B) {
     extern __shared__ __align__(16) uint32_t slab[];          // [8 rows][RS]: per row [W][C/2 + 1] channel pairs + padding
-    const int stack = blockIdx.y, pr0 = blockIdx.x * 8;
+    const int stack = blockIdx.y, pr0 = blockIdx.x * RPC;
     const int C = g.C, W = g.W, C2 = C / 2, LD = C2 + 1;
     // phase 2 reads with a warp = 8 plane rows x 4 consecutive x-groups: word address r * RS + xg * 8 * LD + const.  LD = 1
     // (mod 4) puts the x-groups 8 banks apart; RS = 1 (mod 32) puts the rows on the banks in between - conflict-free (with
@@ -110,7 +112,7 @@ __global__ void __launch_bounds__(256) dw_plane_pack_kernel(const bf16* __restri
     pdl_wait();
     // every plane row an A view can touch (HP >= PAD + F x (H + PAD)): the rows below the last frame's halo are only
     // multiplied by all-zero Toeplitz blocks (taps dy >= K of the last group of eight), but a stale NaN would survive that
-    const int rows = min(8, g.HP - pr0);
+    const int rows = min(RPC, g.HP - pr0);
     // plane row pr -> (stacked frame f, image row y) -> source row index, or -1 for a zero row
     auto src_row = [&](int r) {
         const int qr = pr0 + r - g.PAD;                        // row relative to the first frame's first row
@@ -121,7 +123,7 @@ __global__ void __launch_bounds__(256) dw_plane_pack_kernel(const bf16* __restri
     // phase 1: the image rows among the 8, 16-byte loads (8 channels), rows one after the other
     {
         const int V = C2 / 4, nvec = W * V;                   // uint4 per pixel (C % 8 == 0), per row
-        for (int r = 0; r < 8; ++r) {
+        for (int r = 0; r < RPC; ++r) {
             const int sr = src_row(r);
             if (sr < 0) continue;                             // block-uniform
             const uint4* src = reinterpret_cast<const uint4*>(in) + (size_t)sr * nvec;
@@ -136,13 +138,13 @@ __global__ void __launch_bounds__(256) dw_plane_pack_kernel(const bf16* __restri
     pdl_trigger();
     // phase 2: thread = (plane row r, slot); a slot walks over the (channel pair, x-group) chunks.  8 consecutive threads
     // (r = 0..7) write 128 contiguous bytes of a plane.  Chunks without image cells are plain zero stores.
-    const int r = threadIdx.x & 7;
+    const int r = threadIdx.x & (RPC - 1);
     if (r >= rows) return;
     const bool img_row = src_row(r) >= 0;
     const int npair = C2 * g.WG;
-    int pair = threadIdx.x >> 3, c2 = pair / g.WG, xg = pair - c2 * g.WG;
+    int pair = threadIdx.x / RPC, c2 = pair / g.WG, xg = pair - c2 * g.WG;
     const size_t plane_stride = (size_t)g.WG * g.HP * 8;       // elements per channel plane
-    for (; pair < npair; pair += 32) {
+    for (; pair < npair; pair += 256 / RPC) {
         const int xb = xg * 8 - g.PAD;                         // image column of the chunk's first element
         uint4 lo = make_uint4(0u, 0u, 0u, 0u), hi = lo;
         if (img_row && xb + 7 >= 0 && xb < W) {
@@ -158,7 +160,7 @@ __global__ void __launch_bounds__(256) dw_plane_pack_kernel(const bf16* __restri
         const size_t off = ((((size_t)stack * C + 2 * c2) * g.WG + xg) * g.HP + (pr0 + r)) * 8;
         *reinterpret_cast<uint4*>(planes + off) = lo;
         *reinterpret_cast<uint4*>(planes + off + plane_stride) = hi;
-        xg += 32;
+        xg += 256 / RPC;
         while (xg >= g.WG) { xg -= g.WG; ++c2; }
     }
 }
@@ -397,10 +399,13 @@ int dwconv_tc(const void* in, const void** planar_out_p, int* planar_pitch, int 
     *planar_out_p = planar_out;          // [B][C][H][WO]; lkpm_mlp_tc reads it in place (no transpose back)
     *planar_pitch = g.WO;
     {
-        const size_t smem = (size_t)8 * dw_slab_row_words(W, C) * 4;
+        // plane rows per CTA: 8 (128 contiguous bytes per chunk column) or, CFP_DW_PACK_ROWS=4, 4 (half the slab, twice the CTAs per SM)
+        static const int rpc = [] { const char* e = getenv("CFP_DW_PACK_ROWS"); return e && e[0] == '4' ? 4 : 8; }();
+        const size_t smem = (size_t)rpc * dw_slab_row_words(W, C) * 4;
         CFP_REQUIRE(smem <= 200 * 1024, "dw_plane_pack: %zu B shared memory", smem);
-        if (int err = set_smem(dw_plane_pack_kernel, smem)) return err;
-        launch_pdl(dw_plane_pack_kernel, dim3((g.HP + 7) / 8, g.NB), 256, smem, st, (const bf16*)in, planes, g, B);
+        auto kp = rpc == 4 ? dw_plane_pack_kernel<4> : dw_plane_pack_kernel<8>;
+        if (int err = set_smem(kp, smem)) return err;
+        launch_pdl(kp, dim3((g.HP + rpc - 1) / rpc, g.NB), 256, smem, st, (const bf16*)in, planes, g, B);
         if (int err = check_launch("dw_plane_pack")) return err;
     }
     {
