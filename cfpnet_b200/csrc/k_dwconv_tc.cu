@@ -94,7 +94,7 @@ __host__ __device__ inline int dw_slab_row_words(int W, int C) {
 }
 
 // ---------------------------------------------------------------- token-major -> padded planes
-// CTA = (plane stack, 8 consecutive PLANE rows): coalesced read of the image rows among them ([W][C] slabs),
+// CTA = (plane stack, RPC consecutive PLANE rows): coalesced read of the image rows among them ([W][C] slabs),
 // transpose through shared memory, then each thread emits 16-byte chunks (8 columns of one channel, one
 // plane row); 8 consecutive rows of one (channel, x-group) are 128 contiguous bytes of the plane.  The kernel
 // writes EVERY chunk of the planes - image cells and zeros everywhere else (PAD rows above / between / below the
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(256) dw_plane_pack_kernel(const bf16* __restri
         const int frame = stack * g.F + f;
         return (r < rows && qr >= 0 && f < g.F && y < g.H && frame < B) ? frame * g.H + y : -1;
     };
-    // phase 1: the image rows among the 8, 16-byte loads (8 channels), rows one after the other
+    // phase 1: the image rows among the RPC, 16-byte loads (8 channels), rows one after the other
     {
         const int V = C2 / 4, nvec = W * V;                   // uint4 per pixel (C % 8 == 0), per row
         for (int r = 0; r < RPC; ++r) {
@@ -399,11 +399,12 @@ int dwconv_tc(const void* in, const void** planar_out_p, int* planar_pitch, int 
     *planar_out_p = planar_out;          // [B][C][H][WO]; lkpm_mlp_tc reads it in place (no transpose back)
     *planar_pitch = g.WO;
     {
-        // plane rows per CTA: 8 (128 contiguous bytes per chunk column) or, CFP_DW_PACK_ROWS=4, 4 (half the slab, twice the CTAs per SM)
-        static const int rpc = [] { const char* e = getenv("CFP_DW_PACK_ROWS"); return e && e[0] == '4' ? 4 : 8; }();
+        // plane rows per CTA: 4 (64 contiguous bytes per chunk column, 35 KB slab at L1: six CTAs per SM overlap their load
+        // and store phases) - measured 0.149 ms per step against 0.189 ms with 8 rows (CFP_DW_PACK_ROWS=8 | 2 for A/B runs)
+        static const int rpc = [] { const char* e = getenv("CFP_DW_PACK_ROWS"); return e && e[0] == '8' ? 8 : (e && e[0] == '2' ? 2 : 4); }();
         const size_t smem = (size_t)rpc * dw_slab_row_words(W, C) * 4;
         CFP_REQUIRE(smem <= 200 * 1024, "dw_plane_pack: %zu B shared memory", smem);
-        auto kp = rpc == 4 ? dw_plane_pack_kernel<4> : dw_plane_pack_kernel<8>;
+        auto kp = rpc == 4 ? dw_plane_pack_kernel<4> : (rpc == 2 ? dw_plane_pack_kernel<2> : dw_plane_pack_kernel<8>);
         if (int err = set_smem(kp, smem)) return err;
         launch_pdl(kp, dim3((g.HP + rpc - 1) / rpc, g.NB), 256, smem, st, (const bf16*)in, planes, g, B);
         if (int err = check_launch("dw_plane_pack")) return err;
