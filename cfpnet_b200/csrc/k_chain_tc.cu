@@ -641,19 +641,23 @@ __global__ void __launch_bounds__(128 * NT, MonoOcc<C>::CTAS) loftr_query_mono_k
             }
             block(base + 0, a0s, 0, false);
         });
-        const float* kv_t = kv;
-        const float* ks_t = ksum;
-        if (kv_slots > 0) {
-            umma::mbar_wait(&bars.kv_full, kvph); kvph ^= 1;
-            kv_t = kvs; ks_t = kss;
-        }
+        // two instantiations of the epilogue, one per address space of the state: selected through one pointer variable
+        // its loads were generic (LD.E) - also when they hit the shared-memory copy - instead of LDS / LDG
+        auto attention = [&]() {
+            if (kv_slots > 0) {
+                umma::mbar_wait(&bars.kv_full, kvph); kvph ^= 1;
+                S::epi_attention(q, r, tmem, wq, tid, a0, kvs, kss, g_first, half);
+            } else {
+                S::epi_attention(q, r, tmem, wq, tid, a0, kv, ksum, 0, half);
+            }
+        };
         if (kAttnOnly) {
             if (warp == 0) prefetch(base + 4);               // slot of block `base` is free again
-            S::epi_attention(q, r, tmem, wq, tid, a0, kv_t, ks_t, g_first, half);
+            attention();
             continue;                                        // next stage() barrier orders a0 / TMEM reuse
         }
         CFP_CHAIN_MARK(2, dbg_it);
-        S::epi_attention(q, r, tmem, wq, tid, a0, kv_t, ks_t, g_first, half);
+        attention();
         CFP_CHAIN_MARK(3, dbg_it);
         stage([&] { block(base + 1, a0s + KG * P::LBO, 0, false); });                     // merge
         CFP_CHAIN_MARK(4, dbg_it);
