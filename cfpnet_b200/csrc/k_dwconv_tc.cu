@@ -116,20 +116,24 @@ __global__ void __launch_bounds__(256) dw_plane_pack_kernel(const bf16* __restri
     // plane row pr -> (stacked frame f, image row y) -> source row index, or -1 for a zero row
     auto src_row = [&](int r) {
         const int qr = pr0 + r - g.PAD;                        // row relative to the first frame's first row
-        const int f = qr >= 0 ? qr / g.RS : -1, y = qr - f * g.RS;
+        int f = 0, y = qr;                                     // F is 1 - 3: subtract instead of an integer division
+        for (; f < g.F && y >= g.RS; ++f) y -= g.RS;
         const int frame = stack * g.F + f;
         return (r < rows && qr >= 0 && f < g.F && y < g.H && frame < B) ? frame * g.H + y : -1;
     };
     // phase 1: the image rows among the RPC, 16-byte loads (8 channels), rows one after the other
     {
         const int V = C2 / 4, nvec = W * V;                   // uint4 per pixel (C % 8 == 0), per row
+        const bool vp2 = (V & (V - 1)) == 0;                  // a power of two for every served C: shift / mask, not ~50
+        const int vsh = 31 - __clz(V);                        // instructions of integer division per 16-byte load
         for (int r = 0; r < RPC; ++r) {
             const int sr = src_row(r);
             if (sr < 0) continue;                             // block-uniform
             const uint4* src = reinterpret_cast<const uint4*>(in) + (size_t)sr * nvec;
             for (int i = threadIdx.x; i < nvec; i += 256) {
                 const uint4 v = src[i];
-                uint32_t* d = slab + r * RS + (i / V) * LD + (i % V) * 4;
+                const int px = vp2 ? i >> vsh : i / V, q4 = vp2 ? i & (V - 1) : i % V;
+                uint32_t* d = slab + r * RS + px * LD + q4 * 4;
                 d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
             }
         }
@@ -182,6 +186,17 @@ __device__ __forceinline__ DwItem dw_item(int i, const DwGeom& g) {
     it.xt = i % g.nX;
     it.c = i / g.nX;
     return it;
+}
+// A CTA's items are consecutive: decoded once (four integer divisions, ~25 instructions each - per item and thread that was
+// a third of the epilogue's instruction count), then stepped
+__device__ __forceinline__ void dw_next(DwItem& it, const DwGeom& g) {
+    if (++it.mt < g.nM) return;
+    it.mt = 0;
+    if (++it.b < g.NB) return;
+    it.b = 0;
+    if (++it.xt < g.nX) return;
+    it.xt = 0;
+    ++it.c;
 }
 
 constexpr int kXchLd = 36;                                 // floats per exchanged row (16-byte aligned, bank-staggered)
@@ -242,9 +257,9 @@ __global__ void __launch_bounds__(kDwThreads) dwconv_tc_kernel(const bf16* __res
         // 32 output columns):  out[m][n] = sum_b E_b[m + b][n]
         constexpr int NC = kDwCols;
         const int q = warp & 3, part = warp >> 2, row = q * 32 + lane;
-        for (int i = i0; i < i1; ++i) {
+        DwItem it = dw_item(i0, g);
+        for (int i = i0; i < i1; ++i, dw_next(it, g)) {
             const int n = i - i0, ab = n & 1;
-            const DwItem it = dw_item(i, g);
             const float sh = shift[it.c];
             float* xw = xch + (size_t)ab * (3 * kXchRows * kXchLd) + part * NC;
             float* bw = bnd + ((size_t)ab * kDwEpiWarps + warp) * ((kDwNB - 1) * NC);
@@ -300,7 +315,9 @@ __global__ void __launch_bounds__(kDwThreads) dwconv_tc_kernel(const bf16* __res
                 __syncwarp();                                  // `bw` is rewritten two items later (ab parity) - cheap insurance
             }
             const int m = it.mt * kDwMS + row, x0 = it.xt * 32 + part * NC;
-            const int f = m / g.RS, y = m - f * g.RS, frame = it.b * g.F + f;      // stacked frame and its row
+            int f = 0, y = m;                                  // stacked frame and its row (F is 1 - 3: no division)
+            for (; f < g.F && y >= g.RS; ++f) y -= g.RS;
+            const int frame = it.b * g.F + f;
             if (row < kDwMS && f < g.F && y < g.H && frame < B) {
                 bf16* dst = planar_out + (((size_t)frame * g.C + it.c) * g.H + y) * g.WO + x0;
 #pragma unroll
@@ -320,9 +337,9 @@ __global__ void __launch_bounds__(kDwThreads) dwconv_tc_kernel(const bf16* __res
         // ---------------- producer: Toeplitz blocks per channel, one bulk copy per work item
         {
             int cur_c = -1, nt = 0;
-            for (int i = i0; i < i1; ++i) {
+            DwItem it = dw_item(i0, g);
+            for (int i = i0; i < i1; ++i, dw_next(it, g)) {
                 const int n = i - i0, s = n % 3;
-                const DwItem it = dw_item(i, g);
                 if (it.c != cur_c) {
                     if (nt > 0) umma::mbar_wait(&bars.t_empty, (nt - 1) & 1);   // MMAs on the old blocks are done
                     if (umma::elect_one()) {
@@ -348,9 +365,9 @@ __global__ void __launch_bounds__(kDwThreads) dwconv_tc_kernel(const bf16* __res
             const uint64_t tdesc0 = umma::smem_desc(umma::smem_u32(t_sm), kDwN * 16);
             const uint32_t as0 = umma::smem_u32(a_sm);
             int cur_c = -1, nt = 0;
-            for (int i = i0; i < i1; ++i) {
+            DwItem it = dw_item(i0, g);
+            for (int i = i0; i < i1; ++i, dw_next(it, g)) {
                 const int n = i - i0, s = n % 3, ab = n & 1;
-                const DwItem it = dw_item(i, g);
                 if (it.c != cur_c) {
                     if (nt > 0) umma::commit(&bars.t_empty);
                     umma::mbar_wait(&bars.t_full, nt & 1);
