@@ -48,7 +48,7 @@ template <int C> struct ChainTC {
 };
 
 struct ChainBars {
-    uint64_t full[4], empty[4], a_ready, acc_ready;
+    uint64_t full[4], empty[4], a_ready, acc_ready, kv_full;
     uint32_t tmem_slot;
 };
 
@@ -160,17 +160,6 @@ struct ChainStages {
     static_assert(NT == 1 || NT == 2, "one or two threads per row");
     static_assert(CH % G == 0 && CH % 16 == 0, "a thread owns whole heads and whole 16-column pieces");
     struct Row { typename Q::R ref; int g; };
-    // C = 128, dh = 16 (LSA, GSA): the group state is read from global memory (no room for it in shared memory) and the
-    // attention epilogue stalled on its first touch of every line - a head block's slice (G x dh floats = 1 KB of one
-    // group) is prefetched into L1 one block ahead, the first one while the q projection runs.
-    static constexpr bool kPrefetchState = C >= 128 && DH <= 16;
-    static __device__ __forceinline__ void prefetch_state(const float* __restrict__ kv, int g, int c0) {
-        if (g < 0) return;
-        const char* p = reinterpret_cast<const char*>(kv + (size_t)g * (C * DH) + (size_t)c0 * DH);
-#pragma unroll
-        for (int i = 0; i < G * DH * 4; i += 128) asm volatile("prefetch.global.L1 [%0];\n" ::"l"(p + i));
-    }
-
     // stage x: locate the row once, copy this thread's chunks of its C channels into a0[:, 0:C)
     static __device__ __forceinline__ Row stage_x(const Q& q, int64_t row0, int tid, uint8_t* a0, int half = 0) {
         const int64_t row = row0 + tid;
@@ -194,9 +183,6 @@ struct ChainStages {
         const int g = r.g;
 #pragma unroll 1
         for (int c0 = half * CH; c0 < half * CH + CH; c0 += G) {
-            if constexpr (kPrefetchState) {                  // the next head block's slice of the group state -> L1
-                if (c0 + G < half * CH + CH) prefetch_state(kv, g, c0 + G);
-            }
             float qv[G], out[G];
 #pragma unroll
             for (int j = 0; j < G; j += 16) {
@@ -390,7 +376,7 @@ template <int C> struct ChainOcc { static constexpr int CTAS = C >= 128 ? 1 : (C
 // through the provider (L2-hot) in the last epilogue.
 template <int C, int NH, bool kAttnOnly, class Q, int NT>
 __global__ void __launch_bounds__((8 * NT + 2) * 32, 1) loftr_query_tc_kernel(Q q, cfp_loftr_w w, const float* __restrict__ kv,
-                                                             const float* __restrict__ ksum, int ntiles, int spread) {
+                                                             const float* __restrict__ ksum, int ntiles, int spread, int kv_slots) {
     using P = ChainTC<C>;
     using S = ChainStages<C, NH, kAttnOnly, Q, NT>;
     constexpr int KG = P::KG;
@@ -403,6 +389,11 @@ __global__ void __launch_bounds__((8 * NT + 2) * 32, 1) loftr_query_tc_kernel(Q 
     // ask for stays L1 - where its per-frame attention state (16 KB a group at C = 128) is read from
     constexpr size_t ABUF = kAttnOnly ? (size_t)KG * P::LBO : (size_t)P::ABUF;
     uint8_t* ring = smem + 2 * ABUF;
+    // kv_slots > 0 (groups of a frame - GSA, DAPM - where a tile pair touches two of them and their state fits beside
+    // the operand buffers): the pair's group states are brought into shared memory by two bulk copies while x is staged and
+    // q is projected, and the attention epilogue reads them with LDS (as the C <= 64 chains do)
+    float* kvs = reinterpret_cast<float*>(ring + (size_t)P::NSLOT * P::SLOT);
+    float* kss = kvs + (size_t)kv_slots * (C * S::DH);
     const int tid = threadIdx.x, warp = umma::warp_idx_sync();
     // Tiles of round `it`: group g of CTA c takes tile  it * 2 G + c * ca + g * cg.  spread = 0: (ca, cg) = (2, 1), a CTA owns
     // two neighbouring tiles; spread = 1: (1, G), the first G tiles of a round go to the groups 0 and the next G to the groups
@@ -416,6 +407,7 @@ __global__ void __launch_bounds__((8 * NT + 2) * 32, 1) loftr_query_tc_kernel(Q 
         for (int i = 0; i < P::NSLOT; ++i) { umma::mbar_init(&bars.full[i], 1); umma::mbar_init(&bars.empty[i], 1); }
         umma::mbar_init(&bars.a_ready, NRW * 32);
         umma::mbar_init(&bars.acc_ready, 1);
+        umma::mbar_init(&bars.kv_full, 1);
         umma::fence_mbar_init();
     }
     if (warp == NRW) umma::tmem_alloc(&bars.tmem_slot, 512);
@@ -430,7 +422,7 @@ __global__ void __launch_bounds__((8 * NT + 2) * 32, 1) loftr_query_tc_kernel(Q 
         const uint32_t tmem = bars.tmem_slot + grp * 256;
         float2* xch = &ln_xch[grp][0][0];
         auto group_sync = [&]() { asm volatile("bar.sync %0, %1;\n" ::"r"(2 + grp), "n"(RW * 32) : "memory"); };
-        uint32_t ph = 0;
+        uint32_t ph = 0, kvph = 0;
         auto hand_over = [&]() {          // operands staged / accumulator consumed -> MMA warp; then wait for its result
             umma::fence_async_smem();
             umma::fence_before_sync();
@@ -440,6 +432,18 @@ __global__ void __launch_bounds__((8 * NT + 2) * 32, 1) loftr_query_tc_kernel(Q 
         };
         for (int first = first0; first < ntiles; first += round_tiles) {
             const int tile = first + grp * cg;
+            int g_first = 0;
+            if (kv_slots > 0) {                              // (never with spread rounds: the pair's rows are contiguous)
+                const int64_t r_first = (int64_t)first * 128;
+                const int64_t r_last = r_first + 255 < q.rows ? r_first + 255 : q.rows - 1;
+                g_first = q.group_of_row(r_first);
+                if (tid == 0) {                              // every row thread is past the previous pair's epilogue (bar.sync 1)
+                    const uint32_t ng = (uint32_t)(q.group_of_row(r_last) - g_first + 1);
+                    umma::mbar_expect_tx(&bars.kv_full, ng * (uint32_t)((C * S::DH + C) * sizeof(float)));
+                    umma::bulk_g2s(kvs, kv + (size_t)g_first * (C * S::DH), ng * (uint32_t)(C * S::DH * sizeof(float)), &bars.kv_full);
+                    umma::bulk_g2s(kss, ksum + (size_t)g_first * C, ng * (uint32_t)(C * sizeof(float)), &bars.kv_full);
+                }
+            }
             if (tile >= ntiles) {                            // (group 1 only) no tile this round: keep the protocol going
 #pragma unroll 1
                 for (int i = 0; i < (kAttnOnly ? 1 : 4); ++i) hand_over();
@@ -451,15 +455,15 @@ __global__ void __launch_bounds__((8 * NT + 2) * 32, 1) loftr_query_tc_kernel(Q 
             [[maybe_unused]] const int dbg_it = 1 - (first - first0) / round_tiles;      // marks on the FIRST pair of CTA 5
             CFP_CHAIN_MARK(0, dbg_it);
             const typename S::Row r = S::stage_x(q, row0, tid_g, a0, half);
-            if constexpr (S::kPrefetchState) S::prefetch_state(kv, r.g, half * S::CH);
-            if constexpr (kAttnOnly && C >= 128) {           // DAPM: group = frame, one or two per tile - row t fetches line t of
-                if (r.g >= 0 && half == 0)                   // its group's 16 KB state, together the whole of it
-                    asm volatile("prefetch.global.L1 [%0];\n" ::"l"(reinterpret_cast<const char*>(kv + (size_t)r.g * (C * S::DH)) + tid_g * 128));
-            }
             CFP_CHAIN_MARK(1, dbg_it);
             hand_over();
             CFP_CHAIN_MARK(2, dbg_it);
-            S::epi_attention(q, r, tmem, wq, tid_g, a0, kv, ksum, 0, half);
+            if (kv_slots > 0) {
+                umma::mbar_wait(&bars.kv_full, kvph); kvph ^= 1;
+                S::epi_attention(q, r, tmem, wq, tid_g, a0, kvs, kss, g_first, half);
+            } else {
+                S::epi_attention(q, r, tmem, wq, tid_g, a0, kv, ksum, 0, half);
+            }
             CFP_CHAIN_MARK(3, dbg_it);
             if (!kAttnOnly) {
                 hand_over();
@@ -741,9 +745,16 @@ static int run_query_tc_nt(const char* name, const Q& q, const cfp_loftr_w& w, c
         const int64_t want = spread ? ntiles : npairs;
         const int grid = (int)(want < sm_count() ? want : sm_count());
         auto k = loftr_query_tc_kernel<C, NH, kAttnOnly, Q, NT>;
-        constexpr size_t smem = kAttnOnly ? 2 * (size_t)P::KG * P::LBO + (size_t)P::NSLOT * P::SLOT : P::SMEM;
+        constexpr size_t smem0 = kAttnOnly ? 2 * (size_t)P::KG * P::LBO + (size_t)P::NSLOT * P::SLOT : P::SMEM;
+        // shared-memory copy of the group states a tile pair (256 consecutive rows) touches, where it fits (groups of a frame)
+        constexpr int DH = C / NH;
+        const uint32_t rpg = q.rows_per_group();
+        int kv_slots = (int)((256 + rpg - 2) / rpg + 1);
+        const size_t kv_bytes = (size_t)kv_slots * (C * DH + C) * sizeof(float);
+        if (spread || smem0 + kv_bytes + 1024 > 227 * 1024 || getenv("CFP_NO_KV_SMEM")) kv_slots = 0;
+        const size_t smem = smem0 + (kv_slots > 0 ? kv_bytes : 0);
         if (int e = set_smem(k, smem)) return e;
-        launch_pdl(k, grid, (8 * NT + 2) * 32, smem, st, q, w, kv, ksum, (int)ntiles, (int)spread);
+        launch_pdl(k, grid, (8 * NT + 2) * 32, smem, st, q, w, kv, ksum, (int)ntiles, (int)spread, kv_slots);
 #ifdef CFP_DEBUG_TIMING
         {
             cudaStreamSynchronize(st);
@@ -811,7 +822,8 @@ __device__ __forceinline__ uint32_t gelu_tanh_h2(float x0, float x1) {
 
 template <int C>
 __global__ void __launch_bounds__(192) lkpm_mlp_tc_kernel(bf16* __restrict__ feat0, const bf16* __restrict__ y,
-                                                          int64_t rows, int planar_n, int planar_w, int planar_pitch, cfp_lkpm_w w, int ntiles) {
+                                                          int64_t rows, int planar_n, int planar_w, int planar_pitch, cfp_lkpm_w w, int ntiles,
+                                                          FastDiv dPn, FastDiv dPw) {
     using P = ChainTC<C>;
     using M = MlpTC<C>;
     constexpr int KG = P::KG;
@@ -859,8 +871,9 @@ __global__ void __launch_bounds__(192) lkpm_mlp_tc_kernel(bf16* __restrict__ fea
                 if (planar_n > 0) {
                     // planar dwconv output [frame][C][H][pitch]: lanes are consecutive tokens, so each of the C two-byte
                     // loads of a warp is (mostly) one contiguous 64-byte segment
-                    const uint32_t fr = (uint32_t)row / (uint32_t)planar_n, n = (uint32_t)row - fr * (uint32_t)planar_n;   // rows < 2^31
-                    const uint32_t yy = n / (uint32_t)planar_w, xx = n - yy * (uint32_t)planar_w;
+                    uint32_t fr, n, yy, xx;                       // rows < 2^31; multiply-high divisions
+                    dPn.divmod((uint32_t)row, fr, n);
+                    dPw.divmod(n, yy, xx);
                     const size_t cstride = (size_t)(planar_n / planar_w) * planar_pitch;
                     const uint16_t* p = reinterpret_cast<const uint16_t*>(y) + (size_t)fr * C * cstride + (size_t)yy * planar_pitch + xx;
 #pragma unroll
@@ -1012,7 +1025,8 @@ static int run_lkpm_mlp_tc(void* feat0, const void* y, int64_t rows, int planar_
     const int64_t ntiles = (rows + 127) / 128;
     const int per_sm = C >= 128 ? 1 : (C == 64 ? 2 : 3);
     const int grid = (int)(ntiles < sm_count() * per_sm ? ntiles : sm_count() * per_sm);
-    launch_pdl(k, grid, 192, M::SMEM, st, (bf16*)feat0, (const bf16*)y, rows, planar_n, planar_w, planar_pitch, w, (int)ntiles);
+    launch_pdl(k, grid, 192, M::SMEM, st, (bf16*)feat0, (const bf16*)y, rows, planar_n, planar_w, planar_pitch, w, (int)ntiles,
+               FastDiv((uint32_t)(planar_n > 0 ? planar_n : 1)), FastDiv((uint32_t)(planar_w > 0 ? planar_w : 1)));
     return check_launch(C == 32 ? "lkpm_mlp_tc<32>" : C == 64 ? "lkpm_mlp_tc<64>" : "lkpm_mlp_tc<128>");
 }
 
@@ -1457,7 +1471,8 @@ struct SrBars {
 template <int C>
 __global__ void __launch_bounds__(192) sr_conv_tc_kernel(const bf16* __restrict__ feat, float* __restrict__ acc_out,
                                                          int64_t rows, int H, int W, int ws, int nsx, int Ns,
-                                                         const bf16* __restrict__ sr_tc, int taps_per_cta) {
+                                                         const bf16* __restrict__ sr_tc, int taps_per_cta, FastDiv dNs, FastDiv dNsx,
+                                                         FastDiv dWs) {
     using P = ChainTC<C>;
     constexpr int KG = P::KG, TCOLS = C < 32 ? 32 : C, NST = SrTC<C>::NST;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -1496,8 +1511,10 @@ __global__ void __launch_bounds__(192) sr_conv_tc_kernel(const bf16* __restrict_
             const int64_t row = row0 + r;
             base[k] = -1;
             if (row < rows) {
-                const uint32_t b = (uint32_t)row / (uint32_t)Ns, sidx = (uint32_t)row - b * (uint32_t)Ns;
-                const int y = (int)(sidx / (uint32_t)nsx) * ws, x = (int)(sidx % (uint32_t)nsx) * ws;
+                uint32_t b, sidx, sy, sx;                       // multiply-high divisions (48 integer divisions per thread at C = 128)
+                dNs.divmod((uint32_t)row, b, sidx);
+                dNsx.divmod(sidx, sy, sx);
+                const int y = (int)sy * ws, x = (int)sx * ws;
                 base[k] = (((int64_t)b * H + y) * W + x) * C + kg * 8;
             }
             dst[k] = (uint32_t)(kg * P::LBO + r * 16);
@@ -1506,7 +1523,9 @@ __global__ void __launch_bounds__(192) sr_conv_tc_kernel(const bf16* __restrict_
         auto issue = [&](int t) {                        // copies of tap t into stage (t - t0) % NST
             const int n = t - t0, st = n % NST;
             if (n >= NST) umma::mbar_wait(&bars.empty[st], ((n / NST) - 1) & 1);
-            const int64_t toff = ((int64_t)(t / ws) * W + (t % ws)) * C;
+            uint32_t ty, tx;
+            dWs.divmod((uint32_t)t, ty, tx);
+            const int64_t toff = ((int64_t)ty * W + tx) * C;
 #pragma unroll
             for (int k = 0; k < KG; ++k) {
                 const bf16* g = base[k] >= 0 ? feat + base[k] + toff : feat;
@@ -1617,7 +1636,7 @@ static int run_sr_conv_tc(const void* feat0, float* sr_tok, int B, int H, int W,
     auto k = sr_conv_tc_kernel<C>;
     if (int err = set_smem(k, smem)) return err;
     launch_pdl(k, dim3(tiles, splits), 192, smem, st, (const bf16*)feat0, sr_tok, rows, H, W, ws, nsx, Ns, (const bf16*)sr_tc,
-               taps_per_cta);
+               taps_per_cta, FastDiv((uint32_t)Ns), FastDiv((uint32_t)nsx), FastDiv((uint32_t)ws));
     if (int err = check_launch(C == 32 ? "sr_conv_tc<32>" : C == 64 ? "sr_conv_tc<64>" : "sr_conv_tc<128>")) return err;
     launch_pdl(sr_bias_ln_kernel<C>, (unsigned)((rows + 7) / 8), 256, 0, st, sr_tok, rows, sr_b, g, b);
     return check_launch("sr_bias_ln");
