@@ -42,7 +42,10 @@ __device__ __forceinline__ unsigned long long dbg_now() { unsigned long long t; 
 
 template <int C, int TCOLS> struct ConvTC {
     static constexpr int T = TCOLS / C;               // M-tiles per CTA: T*C = TCOLS TMEM columns (256 or 128)
-    static constexpr int NSLOT = C >= 128 ? 2 : 3;    // weight ring depth (measured: 2 slots and 9 / 4 slots change nothing or cost occupancy)
+    // weight ring depth (measured: 2 slots and 9 / 4 slots change nothing or cost occupancy; measured again at C = 32 with the
+    // per-stage timeline in hand - 72 MMAs of a source take 4.5 us against 1.5 us of tensor time - nine 2 KB slots, a whole
+    // source's taps, still four CTAs per SM: conv3x3_tc<2C->C,32> 0.199 -> 0.207 ms.  The issuer is not waiting for weights.)
+    static constexpr int NSLOT = C >= 128 ? 2 : 3;
     static constexpr int SLOT_BYTES = C * C * 2;      // one [C x C] bf16 block
     static constexpr int KG = C / 8;                  // 16-byte channel groups per source
 };
