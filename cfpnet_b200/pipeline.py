@@ -36,10 +36,12 @@ class FusionPath(nn.Module):
         self.hist_encoder.out_dtype = dtype
         return self
 
+    # stream_host: per-input "landed" / per-level "done" events instead of one of each per batch (CFP_COARSE_EVENTS=1: the old form)
+    fine_grained_events = not bool(__import__("os").environ.get("CFP_COARSE_EVENTS"))
     # run the three fusion calls of the synthetic harness on three streams (CFP_SEQUENTIAL_LEVELS=1: one stream, the drop-in order)
     concurrent_levels = not bool(__import__("os").environ.get("CFP_SEQUENTIAL_LEVELS"))
 
-    def forward(self, x3, x2, x1, hist_data, mask, patch_info, rect_data=None) -> List[torch.Tensor]:
+    def forward(self, x3, x2, x1, hist_data, mask, patch_info, rect_data=None, ready=None, done=None) -> List[torch.Tensor]:
         """x3/x2/x1: decoder features [B,128,h/16,w/16], [B,64,h/8,w/8], [B,32,h/4,w/4];
         hist_data [B,Z,S]; mask [B,Z] bool.  Returns the fused maps in call order.
 
@@ -50,12 +52,28 @@ class FusionPath(nn.Module):
         after the other: ``concurrent_levels = False`` (or ``CFP_SEQUENTIAL_LEVELS=1``) is that configuration, and
         ``bench.py`` reports it next to the headline as ``drop_in_sequential``; ``cfpnet_b200.decoder.Decoder`` is the
         integrated form.  The host-side order of the calls - and with it the order of the positional-encoding RNG
-        draws - stays L3, L2, L1 as in the reference decoder."""
+        draws - stays L3, L2, L1 as in the reference decoder.
+
+        ``ready`` / ``done`` (used by :meth:`stream_host`): CUDA events per input - ``ready["hist"]`` (histograms and mask),
+        ``ready["x3"]``, ``["x2"]``, ``["x1"]`` - that the consuming stream waits for right before its first use, and one
+        event per level, recorded when that level's fused map is complete.  With them a level starts as soon as ITS inputs have
+        landed and its result can leave as soon as it exists, instead of the whole call waiting for the largest map either way.
+        Created with ``external=True`` they stay external wait / record nodes when the call is captured into a CUDA graph."""
+        if ready is not None and x3.is_cuda:
+            torch.cuda.current_stream(x3.device).wait_event(ready["hist"])
         f32, f64, f128 = self.hist_encoder(hist_data.unsqueeze(-1))
         kw = dict(rect_data=rect_data, mask=mask, patch_info=patch_info, rgb=None)
         jobs = ((self.cross_atten3, x3, f128), (self.cross_atten2, x2, f64), (self.cross_atten1, x1, f32))
+        names = ("x3", "x2", "x1")
         if not (self.concurrent_levels and x3.is_cuda):
-            return [m(x, f, **kw) for m, x, f in jobs]
+            outs = []
+            for i, (m, x, f) in enumerate(jobs):
+                if ready is not None and x.is_cuda:
+                    torch.cuda.current_stream(x.device).wait_event(ready[names[i]])
+                outs.append(m(x, f, **kw))
+                if done is not None and x.is_cuda:
+                    done[i].record(torch.cuda.current_stream(x.device))
+            return outs
         dev = x3.device
         cur = torch.cuda.current_stream(dev)
         # (measured: stream priorities do not help - higher priority for the two smaller levels costs 2.5 %, for the
@@ -74,12 +92,20 @@ class FusionPath(nn.Module):
         try:
             for i, (m, x, f) in enumerate(jobs):
                 if i == 2:                                   # the largest level stays on the caller's stream
+                    if ready is not None:
+                        cur.wait_event(ready[names[i]])
                     m(x, f, out=outs[i], **kw)
+                    if done is not None:
+                        done[i].record(cur)
                     continue
                 s = side[i]
                 s.wait_event(fork)
+                if ready is not None:
+                    s.wait_event(ready[names[i]])
                 with torch.cuda.stream(s):
                     m(x, f, out=outs[i], **kw)
+                    if done is not None:
+                        done[i].record(s)
                     e = torch.cuda.Event()
                     e.record(s)
                 joins.append(e)
@@ -90,7 +116,7 @@ class FusionPath(nn.Module):
         return outs
 
     # ------------------------------------------------------------------ CUDA-graph replay (latency mode)
-    def make_graphed(self, x3, x2, x1, hist_data, mask, patch_info, copy_inputs: bool = True):
+    def make_graphed(self, x3, x2, x1, hist_data, mask, patch_info, copy_inputs: bool = True, ready=None, done=None):
         """Capture one forward (every launch of the three levels, on all their streams) into a CUDA graph and return
         ``run(x3, x2, x1, hist_data, mask) -> [fused3, fused2, fused1]`` that replays it: the ~95 host-side launches of
         a forward (~20 us each through Python + ctypes) become one graph launch.  ``copy_inputs``: the arguments of
@@ -121,8 +147,8 @@ class FusionPath(nn.Module):
                     self.forward(*static, patch_info)
             torch.cuda.current_stream(dev).wait_stream(side)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph), torch.no_grad():
-                outs = self.forward(*static, patch_info)
+            with torch.cuda.graph(graph), torch.no_grad():   # ready / done: external wait / record nodes of the graph
+                outs = self.forward(*static, patch_info, ready=ready, done=done)
         finally:
             for m, _x in mods:
                 m.__dict__.pop("_crop_dev", None)
@@ -172,7 +198,10 @@ class FusionPath(nn.Module):
             cache[(str(dev), depth)] = dict(
                 h2d=torch.cuda.Stream(dev), d2h=torch.cuda.Stream(dev),
                 slots=[dict(inp=None, out=None, in_ready=torch.cuda.Event(), comp_done=torch.cuda.Event(),
-                            out_ready=torch.cuda.Event(), busy=False, graph=None) for _ in range(depth)])
+                            out_ready=torch.cuda.Event(), busy=False, graph=None,
+                            # per-input / per-level events (external: they survive CUDA-graph capture as event nodes)
+                            ready={k: torch.cuda.Event(external=True) for k in ("hist", "x3", "x2", "x1")},
+                            done=[torch.cuda.Event(external=True) for _ in range(3)]) for _ in range(depth)])
         st = cache[(str(dev), depth)]
         h2d, d2h, slots = st["h2d"], st["d2h"], st["slots"]
         for sl in slots:
@@ -194,28 +223,41 @@ class FusionPath(nn.Module):
             if sl["inp"] is None or any(sl["inp"][k].shape != hb[k].shape or sl["inp"][k].dtype != hb[k].dtype for k in keys):
                 sl["inp"] = {k: torch.empty(hb[k].shape, dtype=hb[k].dtype, device=dev) for k in keys}
                 sl["graph"] = None
+            fine = self.fine_grained_events
             with torch.cuda.stream(h2d):
                 h2d.wait_event(sl["comp_done"])          # previous compute on these input buffers finished
-                for k in keys:
+                # smallest first: histograms + mask, then the 1/16, 1/8, 1/4 maps - each followed by its own event, so that a
+                # level starts when ITS map has landed (the first batch of a run no longer waits for all 100 MB)
+                for k in ("hist_data", "mask"):
                     sl["inp"][k].copy_(hb[k], non_blocking=True)
+                sl["ready"]["hist"].record(h2d)
+                for k in ("x3", "x2", "x1"):
+                    sl["inp"][k].copy_(hb[k], non_blocking=True)
+                    sl["ready"][k].record(h2d)
                 sl["in_ready"].record(h2d)
-            comp.wait_event(sl["in_ready"])
+            if not fine:
+                comp.wait_event(sl["in_ready"])
+            ev = dict(ready=sl["ready"], done=sl["done"]) if fine else {}
             if seed_it is not None:
                 torch.manual_seed(next(seed_it))
             d = sl["inp"]
             if graph:                                    # one captured forward per slot (its device buffers are the static inputs)
                 if sl.get("graph") is None:
                     comp.synchronize()                   # capture replays the forward: the slot's first inputs must have landed
-                    sl["graph"] = self.make_graphed(d["x3"], d["x2"], d["x1"], d["hist_data"], d["mask"], patch_info, copy_inputs=False)
+                    h2d.synchronize()                    # ... all of them (with per-level events `comp` does not wait for h2d)
+                    sl["graph"] = self.make_graphed(d["x3"], d["x2"], d["x1"], d["hist_data"], d["mask"], patch_info, copy_inputs=False, **ev)
                 outs = sl["graph"]()
             else:
-                outs = self.forward(d["x3"], d["x2"], d["x1"], d["hist_data"], d["mask"], patch_info)
+                outs = self.forward(d["x3"], d["x2"], d["x1"], d["hist_data"], d["mask"], patch_info, **ev)
             sl["comp_done"].record(comp)
             if sl["out"] is None or any(p.shape != o.shape or p.dtype != o.dtype for p, o in zip(sl["out"], outs)):
                 sl["out"] = [torch.empty(o.shape, dtype=o.dtype, pin_memory=True) for o in outs]
             with torch.cuda.stream(d2h):
-                d2h.wait_event(sl["comp_done"])
-                for p, o in zip(sl["out"], outs):
+                if not fine:
+                    d2h.wait_event(sl["comp_done"])
+                for j, (p, o) in enumerate(zip(sl["out"], outs)):
+                    if fine:
+                        d2h.wait_event(sl["done"][j])     # this level's map is complete (the others may still be running)
                     p.copy_(o, non_blocking=True)
                 sl["out_ready"].record(d2h)
             # keep the device results referenced until this slot is drained (host-synchronised on out_ready):

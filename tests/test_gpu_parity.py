@@ -232,9 +232,11 @@ def test_full_batch_properties():
             assert rel_l2(one, full[i:i + 1]) <= 1e-2
 
 
-def test_stream_host_equals_direct_forward():
-    """The pipelined host-buffer API (separate H2D / compute / D2H streams) returns, for every batch,
-    what a plain forward on device-resident copies of the same batch returns."""
+@pytest.mark.parametrize("graph,B", [(False, 2), (True, 2), (True, 16)])
+def test_stream_host_equals_direct_forward(graph, B):
+    """The pipelined host-buffer API (separate H2D / compute / D2H streams, per-input "landed" and per-level "done" events;
+    with ``graph`` every slot replays a captured forward in which those events are external wait / record nodes) returns,
+    for every batch, what a plain forward on device-resident copies of the same batch returns."""
     from cfpnet_b200 import FusionPath
     path = FusionPath(synth.COMBINE1_LAYERS)
     path.hist_encoder.load_state_dict(synth.synthetic_state_dict(ref_keys()["hist_encoder"], seed=0))
@@ -243,13 +245,13 @@ def test_stream_host_equals_direct_forward():
     path = path.to(DEV).eval().set_dtype(torch.bfloat16)
     batches, pi = [], None
     for s in range(5):
-        inp = synth.make_inputs("G416", 2, seed=20 + s)
+        inp = synth.make_inputs("G416", B, seed=20 + s)
         pi = inp["patch_info"]
         batches.append({"x3": inp["x3"].bfloat16().pin_memory(), "x2": inp["x2"].bfloat16().pin_memory(),
                         "x1": inp["x1"].bfloat16().pin_memory(), "hist_data": inp["hist_data"].pin_memory(),
                         "mask": inp["mask"].pin_memory()})
     got = {}
-    for idx, outs in path.stream_host(batches, pi, DEV, depth=2, seeds=range(100, 105)):
+    for idx, outs in path.stream_host(batches, pi, DEV, depth=2, seeds=range(100, 105), graph=graph):
         got[idx] = [o.clone() for o in outs]            # buffers are recycled after `depth` more batches
     assert sorted(got) == list(range(5))
     for i, hb in enumerate(batches):
