@@ -152,6 +152,9 @@ __device__ __forceinline__ void layernorm_half(float (&v)[C / 2], const float* _
 // one long dependent instruction stream (issue-slot utilisation 0.11-0.26); two threads per row halve every epilogue
 // and double the warps the schedulers can pick from.  Only the two LayerNorms need the other half: one exchange of
 // (mean, centred sum of squares) through shared memory each.
+template <class Q> struct IsZonePatch { static constexpr bool value = false; };
+template <class T, bool F> struct IsZonePatch<ZonePatchRows<T, F>> { static constexpr bool value = true; };
+
 template <int C, int NH, bool kAttnOnly, class Q, int NT = 1>
 struct ChainStages {
     using P = ChainTC<C>;
@@ -234,6 +237,90 @@ struct ChainStages {
                 }
             }
         }
+    }
+    // epilogue 1, group-stationary form (hist2image at C = 128: dh = 32, 9-row zone groups).  The row-stationary form above
+    // has every row walk its group's whole [C x dh] state - 1024 sixteen-byte loads per row, 4-5 distinct addresses per warp
+    // instruction because 9 consecutive rows share a group: 37 us of a 65 us tile pair, bound by LSU wavefronts.  Here
+    //   phase A (thread = row half, as before): Q = elu(q)+1 -> a0[:, C:2C) as bf16 (where msg will go), 1 / (Q.Ksum + eps)
+    //           per head -> inv[row][head];
+    //   phase B (warp = task (group segment of the tile, head), lane = value column c2): the lane loads ITS column of the
+    //           head's state once (dh coalesced loads) and applies it to the segment's rows, whose Q chunks are warp-wide
+    //           broadcast reads of shared memory; msg overwrites Q in place (the task owns those rows x columns).
+    // Each state element is loaded once per group and head instead of once per row; Q passes through bf16.
+    static constexpr bool kGroupStationary = C >= 128 && DH == 32 && NT == 2 && !kAttnOnly && IsZonePatch<Q>::value;
+    template <class Sync>
+    static __device__ __forceinline__ void epi_attention_gs(const Q& q, const Row& r, uint32_t tmem, int wq, int tid, uint8_t* a0,
+                                                            const float* __restrict__ kv, const float* __restrict__ ksum, int half,
+                                                            float* inv, int64_t row0, int wg, int nwarps, Sync&& sync) {
+        const int g = r.g;
+        // ---- phase A
+#pragma unroll 1
+        for (int c0 = half * CH; c0 < half * CH + CH; c0 += DH) {
+            float qv[DH];
+#pragma unroll
+            for (int j = 0; j < DH; j += 16) {
+                float t[16];
+                umma::tmem_ld16(umma::tmem_addr(tmem, wq * 32, c0 + j), t);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) qv[j + i] = g >= 0 ? elu1(t[i]) : 0.f;
+            }
+            float den = kAttnEps;
+            if (g >= 0) {
+                const float* ksh = ksum + (size_t)g * C + c0;
+#pragma unroll
+                for (int d = 0; d < DH; d += 4) {
+                    const float4 k4 = *reinterpret_cast<const float4*>(ksh + d);
+                    den = fmaf(qv[d], k4.x, den); den = fmaf(qv[d + 1], k4.y, den);
+                    den = fmaf(qv[d + 2], k4.z, den); den = fmaf(qv[d + 3], k4.w, den);
+                }
+            }
+            inv[tid * NH + c0 / DH] = g >= 0 ? __fdividef(1.f, den) : 0.f;
+#pragma unroll
+            for (int j = 0; j < DH; j += 8) {
+                float o8[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o8[i] = qv[j + i];
+                umma::store_chunk(a0, P::LBO, tid, KG + (c0 + j) / 8, o8);
+            }
+        }
+        sync();                                            // Q and inv of the whole tile are in shared memory
+        // ---- phase B
+        const int lane = threadIdx.x & 31;
+        const int rpg = (int)q.rows_per_group();
+        const int64_t left = q.rows - row0;
+        const int live = left < 128 ? (int)left : 128;
+        if (live > 0) {
+            const int g0 = q.group_of_row(row0), g1 = q.group_of_row(row0 + live - 1);
+            const int ntask = (g1 - g0 + 1) * NH;
+#pragma unroll 1
+            for (int t = wg; t < ntask; t += nwarps) {
+                const int seg = t / NH, h = t - seg * NH, gg = g0 + seg;
+                int ra = (int)((int64_t)gg * rpg - row0), rb = ra + rpg;
+                ra = ra < 0 ? 0 : ra;
+                rb = rb > live ? live : rb;
+                float kvc[DH];                               // this lane's column of the head's dh x dh state
+                const float* kp = kv + (size_t)gg * (C * DH) + (size_t)(h * DH) * DH + lane;
+#pragma unroll
+                for (int d = 0; d < DH; ++d) kvc[d] = kp[d * DH];
+                uint8_t* qrow = a0 + (size_t)(KG + h * (DH / 8)) * P::LBO;
+                uint8_t* mdst = a0 + (size_t)(KG + (h * DH + lane) / 8) * P::LBO + (lane & 7) * 2;
+#pragma unroll 1
+                for (int rr = ra; rr < rb; ++rr) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int j = 0; j < DH / 8; ++j) {
+                        float q8[8];
+                        unpack8(*reinterpret_cast<const uint4*>(qrow + (size_t)j * P::LBO + rr * 16), q8);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) acc = fmaf(q8[i], kvc[j * 8 + i], acc);
+                    }
+                    acc *= inv[rr * NH + h];
+                    __syncwarp();                            // every lane has read row rr's Q chunks of this head
+                    *reinterpret_cast<__nv_bfloat16*>(mdst + rr * 16) = __float2bfloat16_rn(acc);
+                }
+            }
+        }
+        sync();                                            // msg complete for the tile (the caller hands over to the merge MMA)
     }
     // epilogue 2: LN1(merge) -> a0[:, C:2C)
     template <class Sync>
@@ -385,6 +472,8 @@ __global__ void __launch_bounds__((8 * NT + 2) * 32, 1) loftr_query_tc_kernel(Q 
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ ChainBars bars;
     __shared__ float2 ln_xch[2][NT][128];                    // LayerNorm statistics of split rows, per tile group
+    __shared__ float inv_den[2][S::kGroupStationary ? 128 * NH : 1];   // 1 / (Q.Ksum + eps) per (row, head), per tile group
+    const bool gs_on = (spread & 2) == 0;                    // bit 1 of `spread`: row-stationary attention epilogue (A/B runs)
     // the attention-only chain (DAPM) stages x only: half an operand buffer per tile, and the shared memory it does not
     // ask for stays L1 - where its per-frame attention state (16 KB a group at C = 128) is read from
     constexpr size_t ABUF = kAttnOnly ? (size_t)KG * P::LBO : (size_t)P::ABUF;
@@ -400,7 +489,7 @@ __global__ void __launch_bounds__((8 * NT + 2) * 32, 1) loftr_query_tc_kernel(Q 
     // 1 - a last round of fewer than 2 G tiles then runs one tile on (almost) every SM instead of two on half of them.
     // A group without a tile only keeps the hand-over protocol going (arrivals, barrier), and its MMAs are not issued.
     const int round_tiles = 2 * (int)gridDim.x;
-    const int ca = spread ? 1 : 2, cg = spread ? (int)gridDim.x : 1;
+    const int ca = (spread & 1) ? 1 : 2, cg = (spread & 1) ? (int)gridDim.x : 1;
     const int first0 = (int)blockIdx.x * ca;
 
     if (tid == 0) {
@@ -458,7 +547,10 @@ __global__ void __launch_bounds__((8 * NT + 2) * 32, 1) loftr_query_tc_kernel(Q 
             CFP_CHAIN_MARK(1, dbg_it);
             hand_over();
             CFP_CHAIN_MARK(2, dbg_it);
-            if (kv_slots > 0) {
+            if constexpr (S::kGroupStationary) {
+                if (gs_on) S::epi_attention_gs(q, r, tmem, wq, tid_g, a0, kv, ksum, half, &inv_den[grp][0], row0, warp % RW, RW, group_sync);
+                else S::epi_attention(q, r, tmem, wq, tid_g, a0, kv, ksum, 0, half);
+            } else if (kv_slots > 0) {
                 umma::mbar_wait(&bars.kv_full, kvph); kvph ^= 1;
                 S::epi_attention(q, r, tmem, wq, tid_g, a0, kvs, kss, g_first, half);
             } else {
@@ -741,6 +833,7 @@ static int run_query_tc_nt(const char* name, const Q& q, const cfp_loftr_w& w, c
         // the levels on one stream, but 3.85 -> 3.91 ms with the three levels concurrent - a CTA with one tile takes 0.75 of
         // the time of a CTA with two and still owns the SM's shared memory, so it costs SM-time the other levels could use.
         static const bool spread = [] { const char* e = getenv("CFP_CHAIN_SPREAD"); return e && e[0] == '1'; }();
+        static const int no_gs = getenv("CFP_NO_GROUP_STATIONARY") ? 2 : 0;   // hist2image at C = 128: row-stationary apply (A/B)
         const int64_t npairs = (ntiles + 1) / 2;
         const int64_t want = spread ? ntiles : npairs;
         const int grid = (int)(want < sm_count() ? want : sm_count());
@@ -754,7 +847,7 @@ static int run_query_tc_nt(const char* name, const Q& q, const cfp_loftr_w& w, c
         if (spread || smem0 + kv_bytes + 1024 > 227 * 1024 || getenv("CFP_NO_KV_SMEM")) kv_slots = 0;
         const size_t smem = smem0 + (kv_slots > 0 ? kv_bytes : 0);
         if (int e = set_smem(k, smem)) return e;
-        launch_pdl(k, grid, (8 * NT + 2) * 32, smem, st, q, w, kv, ksum, (int)ntiles, (int)spread, kv_slots);
+        launch_pdl(k, grid, (8 * NT + 2) * 32, smem, st, q, w, kv, ksum, (int)ntiles, (int)spread | no_gs, kv_slots);
 #ifdef CFP_DEBUG_TIMING
         {
             cudaStreamSynchronize(st);

@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests -m gpu -q -x -k "parity or layers or depth" 2>&1 | tail -n 3
+timeout 300 python bench.py --no-cpu --steps 20 > gpurun_out/r2ay_bench.json 2> gpurun_out/r2ay_bench.err
+python tools/show_bench.py gpurun_out/r2ay_bench.json 2>/dev/null | grep "ms_per_step\|hist2image,128" | cut -c1-150
+CFP_NO_GROUP_STATIONARY=1 timeout 300 python bench.py --no-cpu --steps 20 > gpurun_out/r2ay_bench_nogs.json 2>> gpurun_out/r2ay_bench.err
+python tools/show_bench.py gpurun_out/r2ay_bench_nogs.json 2>/dev/null | grep "ms_per_step\|hist2image,128" | cut -c1-150
