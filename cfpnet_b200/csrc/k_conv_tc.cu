@@ -505,13 +505,15 @@ int conv3x3_tc(const void* in0, const void* in1, const void* wpk, const float* s
     static const int tcols_env = getenv("CFP_CONV_TCOLS") ? atoi(getenv("CFP_CONV_TCOLS")) : 0;
     const int tcols = tcols_env ? tcols_env : (C <= 64 ? 128 : 256);
 #define CFP_CONV_ARGS in0, in1, wpk, shift, residual, out, B, H, W, zy0, zy1, zx0, zx1, st
-    // raster staging: tensor-map TMA at C >= 64, per-thread zero-fill cp.async at C = 32 (CFP_CONV_TMA=0 / 1 forces one
-    // of them).  Measured (B200, 64 frames, both convs of a DAPM): C = 64 0.255 vs 0.254 ms, C = 128 0.193 vs 0.189 ms -
-    // equal, with the row warps free during staging; C = 32 0.374 vs 0.351 ms - the box's innermost extent is one 16-byte
-    // channel group (the no-swizzle operand layout keeps a cell's groups 16 B x cells apart), so the engine fetches
-    // half-used 32-byte sectors once per group where consecutive cp.async threads cover whole lines.
+    // raster staging: per-thread zero-fill cp.async by default, tensor-map TMA (cp.async.bulk.tensor, one 5-D box per source)
+    // with CFP_CONV_TMA=1.  Measured (B200, 64 frames, both convs of a DAPM, alone on the GPU): C = 64 0.255 (TMA) vs 0.254 ms,
+    // C = 128 0.193 vs 0.189 ms - equal; C = 32 0.374 vs 0.351 ms - the box's innermost extent is one 16-byte channel group
+    // (the no-swizzle operand layout keeps a cell's groups 16 B x cells apart), so the engine fetches half-used 32-byte
+    // sectors once per group where consecutive cp.async threads cover whole lines.  With the three levels concurrent (the
+    // headline workload) the cp.async form is 1.3 % faster on the whole step (3.47 -> 3.42 ms, final build of round 2), which
+    // is why it is the default; tests/test_gpu_layers.py runs the DAPM parity cases through the TMA form in a subprocess.
     static const int tma_env = getenv("CFP_CONV_TMA") ? atoi(getenv("CFP_CONV_TMA")) : -1;
-    const bool use_tma = tma_env >= 0 ? tma_env != 0 : C >= 64;
+    const bool use_tma = tma_env >= 0 ? tma_env != 0 : false;
     if (use_tma && W + 2 <= 256) {
         if (tcols == 128) {
             if (C == 32) return conv_tma_launch<32, 128>(CFP_CONV_ARGS);

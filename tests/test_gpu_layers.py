@@ -1,6 +1,7 @@
 """Per-layer checks through the C ABI: each bf16 (tensor-core) layer entry point against the
 fp32 (exact FFMA) entry point of the same library on identical inputs, and against the oracle."""
 import ctypes
+import os
 
 import pytest
 import torch
@@ -172,3 +173,17 @@ def test_last_layer_nchw_epilogue_equals_layer_then_transpose(level, dtype):
     with pytest.raises(_lib.CfpError):                      # the result map must not alias the token map
         _lib.call("cfp_twins_nchw_fwd", x.data_ptr(), x.data_ptr(), B, H, W, C, ctypes.byref(packed[2]), work.data_ptr(), nbytes, code,
                   _lib.stream_ptr())
+
+
+def test_dapm_bf16_through_the_tensor_map_tma_staging():
+    """conv3x3_tma_kernel (raster staged by cp.async.bulk.tensor boxes) is not the default staging any more (the cp.async
+    form is 1.3 % faster on the concurrent step): the library reads CFP_CONV_TMA once per process, so the DAPM bf16-vs-fp32
+    cases of this file are run again in a child process with CFP_CONV_TMA=1 to keep that kernel under test."""
+    import subprocess
+    import sys
+    env = dict(os.environ, CFP_CONV_TMA="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_layers.py"), "-q", "-x", "-m", "gpu",
+                        "-k", "test_bf16_layer_matches_fp32_layer and dapm"], env=env, cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "3 passed" in r.stdout, r.stdout[-500:]
